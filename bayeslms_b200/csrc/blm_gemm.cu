@@ -1,0 +1,563 @@
+// tcgen05 / TMEM / TMA GEMM family for sm_100a.
+//
+//   blm_gemm       C = epilogue(sum_s A_s B_s^T)        (a),(c): linear layers
+//   blm_vocab_nll  nll = LSE(h E^T + b) - (h E^T + b)[t]  (d): logits stay in TMEM
+//
+// One persistent CTA per SM, 256 threads:
+//   warp 0   TMA producer   (lane 0): A/B tiles -> 128B-swizzled smem ring
+//   warp 1   MMA issuer     (lane 0): tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
+//   warp 2   TMEM allocator
+//   warp 4-7 epilogue: tcgen05.ld one accumulator row per thread, fused
+//            bias / scale / GELU / GP-mix / residual / (hi,lo) split, or the
+//            online log-sum-exp + target gather of the vocabulary sweep.
+// Two TMEM accumulator stages let the MMA of tile i+1 overlap the epilogue of
+// tile i.  Ragged M/N/K edges rely on TMA zero fill; the epilogue masks rows
+// >= M and columns >= N.
+#include "blm_host.h"
+#include "blm_ptx.cuh"
+
+namespace blm {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+enum { EPI_STORE = 0, EPI_NLL = 1 };
+
+struct GemmParams {
+  CUtensorMap tmA[BLM_MAX_SEG];
+  CUtensorMap tmB[BLM_MAX_SEG];
+  int kblocks[BLM_MAX_SEG];
+  int nseg;
+  int M, N;
+  int m_tiles, n_tiles;
+  // work decomposition: work w -> (m_tile = w / n_groups, group = w % n_groups),
+  // n tiles [group * tiles_per_group, min(n_tiles, (group+1) * tiles_per_group))
+  int n_groups, tiles_per_group, num_works;
+  // EPI_STORE
+  const float* bias;
+  const float* coef;
+  float col_scale;
+  int col_scale_cols;
+  const float* resid;
+  long long ldr;
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ldc;
+  // EPI_NLL
+  const int* targets;
+  float* part_max;  // [n_groups, M]
+  float* part_sum;
+  float* part_tgt;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem ptr
+  static constexpr int kBytes = kBarOffset + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-B alignment
+};
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float z, const float* __restrict__ coef, int N, int n) {
+  if constexpr (ACT == BLM_ACT_GELU) {
+    return gelu_erf(z);
+  } else if constexpr (ACT == BLM_ACT_GPMIX) {
+    const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n),
+                c3 = __ldg(coef + 3 * N + n);
+    return c0 * tanhf(z) + c1 * (1.0f / (1.0f + expf(-z))) + c2 * fmaxf(z, 0.0f) + c3 * gelu_erf(z);
+  } else {
+    return z;
+  }
+}
+
+template <int BN, int STAGES, int EPI, int ACT>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                            : (2 * BN <= 256) ? 256 : 512;
+  static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      tma_prefetch_desc(&p.tmA[s]);
+      tma_prefetch_desc(&p.tmB[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int total_kb = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+
+  if (warp == 0) {
+    // ------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
+        const int m_tile = w / p.n_groups;
+        const int grp = w - m_tile * p.n_groups;
+        const int n0 = grp * p.tiles_per_group;
+        const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+        for (int n = n0; n < n1; ++n) {
+          for (int s = 0; s < p.nseg; ++s) {
+            const int kbs = p.kblocks[s];
+            for (int kb = 0; kb < kbs; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+              uint8_t* sa = smem + stage * L::kStageBytes;
+              uint8_t* sb = sa + L::kABytes;
+              // activations stream once (evict-first); weights are re-read by
+              // every M tile and stay L2 resident (evict-last).
+              tma_load_2d(sa, &p.tmA[s], &full_bar[stage], kb * kBK, m_tile * kBM, kEvictNormal);
+              tma_load_2d(sb, &p.tmB[s], &full_bar[stage], kb * kBK, n * BN, kEvictLast);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
+        const int m_tile = w / p.n_groups;
+        const int grp = w - m_tile * p.n_groups;
+        const int n0 = grp * p.tiles_per_group;
+        const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+        for (int n = n0; n < n1; ++n) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = 0; kb < total_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+            const uint64_t da = umma_desc_sw128(sa);
+            const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 bytes per 16-element K step inside the 128-byte swizzle row
+              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                           idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kEpiWarp0) {
+    // ---------------------------------------------------------- epilogue
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) belong to this warp
+    const int row_in_tile = lane_grp * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
+      const int m_tile = w / p.n_groups;
+      const int grp = w - m_tile * p.n_groups;
+      const int n0 = grp * p.tiles_per_group;
+      const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+      const int m = m_tile * kBM + row_in_tile;
+      const bool row_ok = m < p.M;
+
+      // EPI_NLL running state (base-2 domain: logits pre-multiplied by log2 e)
+      float run_max = -INFINITY, run_sum = 0.0f, tgt_logit = -INFINITY;
+      int tgt = -1;
+      if constexpr (EPI == EPI_NLL) {
+        if (row_ok) tgt = __ldg(p.targets + m);
+      }
+
+      for (int n = n0; n < n1; ++n) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked branches
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          const int col0 = n * BN + c * 32;
+          if (col0 >= p.N) continue;  // warp-uniform
+          if constexpr (EPI == EPI_STORE) {
+            if (row_ok) {
+            const bool full = (col0 + 32 <= p.N);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              const int colc = full ? col : min(col, p.N - 1);
+              float z = v[j];
+              if (p.bias) z += __ldg(p.bias + colc);
+              if (col < p.col_scale_cols) z *= p.col_scale;
+              z = apply_act<ACT>(z, p.coef, p.N, colc);
+              v[j] = z;
+            }
+            if (p.resid) {
+              const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.N) {
+                  const float4 rr = __ldg(reinterpret_cast<const float4*>(r + j));
+                  v[j] += rr.x;
+                  v[j + 1] += rr.y;
+                  v[j + 2] += rr.z;
+                  v[j + 3] += rr.w;
+                }
+              }
+            }
+            const long long off = static_cast<long long>(m) * p.ldc + col0;
+            if (p.out_f32) {
+              float* o = p.out_f32 + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (col0 + j < p.N)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.out_hi) {
+              __nv_bfloat16* oh = p.out_hi + off;
+              __nv_bfloat16* ol = p.out_lo ? p.out_lo + off : nullptr;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j < p.N) {
+                  uint32_t h[4], l[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float a = v[j + 2 * q], b = v[j + 2 * q + 1];
+                    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                    h[q] = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) |
+                           (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
+                    l[q] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+                  }
+                  *reinterpret_cast<uint4*>(oh + j) = make_uint4(h[0], h[1], h[2], h[3]);
+                  if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+              }
+            }
+            }  // row_ok
+          } else {
+            // online log-sum-exp over this 32-column chunk
+            constexpr float kLog2e = 1.4426950408889634f;
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              float z = v[j];
+              if (col < p.N) {
+                if (p.bias) z += __ldg(p.bias + col);
+                if (col == tgt) tgt_logit = z;
+                z *= kLog2e;
+              } else {
+                z = -INFINITY;
+              }
+              v[j] = z;
+              cmax = fmaxf(cmax, z);
+            }
+            const float new_max = fmaxf(run_max, cmax);
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += exp2f(v[j] - new_max);
+            run_sum = run_sum * exp2f(run_max - new_max) + s;
+            run_max = new_max;
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      if constexpr (EPI == EPI_NLL) {
+        if (row_ok) {
+          const long long o = static_cast<long long>(grp) * p.M + m;
+          p.part_max[o] = run_max;
+          p.part_sum[o] = run_sum;
+          p.part_tgt[o] = tgt_logit;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// nll[m] = ln2 * (gmax + log2(sum_g sum_g * 2^(max_g - gmax))) - target logit
+__global__ void nll_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                 const float* __restrict__ part_tgt, int groups, int M,
+                                 float* __restrict__ nll) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float gmax = -INFINITY, tgt = -INFINITY;
+  for (int g = 0; g < groups; ++g) {
+    gmax = fmaxf(gmax, part_max[static_cast<long long>(g) * M + m]);
+    tgt = fmaxf(tgt, part_tgt[static_cast<long long>(g) * M + m]);
+  }
+  float s = 0.0f;
+  for (int g = 0; g < groups; ++g)
+    s += part_sum[static_cast<long long>(g) * M + m] *
+         exp2f(part_max[static_cast<long long>(g) * M + m] - gmax);
+  constexpr float kLn2 = 0.6931471805599453f;
+  nll[m] = kLn2 * (gmax + log2f(s)) - tgt;
+}
+
+__global__ void segment_sum_kernel(const float* __restrict__ x, const int* __restrict__ offs,
+                                   long long nseg, float* __restrict__ out) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (i >= nseg) return;
+  const int lane = threadIdx.x & 31;
+  const int b = offs[i], e = offs[i + 1];
+  float s = 0.0f;
+  for (int t = b + lane; t < e; t += 32) s += x[t];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = s;
+}
+
+// ------------------------------------------------------------------ host
+template <int BN, int STAGES, int EPI, int ACT>
+static int set_smem_attr() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI, ACT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SmemLayout<BN, STAGES>::kDynBytes));
+  return BLM_OK;
+}
+
+constexpr int kStages256 = 4;
+constexpr int kStages128 = 6;
+
+int gemm_init() {
+  int rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_NONE>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GELU>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_NONE>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GELU>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_NLL, BLM_ACT_NONE>()) != BLM_OK) return rc;
+  return BLM_OK;
+}
+
+template <int BN, int STAGES, int EPI, int ACT>
+static int launch(const GemmParams& p, cudaStream_t st) {
+  const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
+  gemm_kernel<BN, STAGES, EPI, ACT>
+      <<<grid, kThreads, SmemLayout<BN, STAGES>::kDynBytes, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+static int fill_segments(GemmParams& p, int nseg, const blm_bf16* const* A, const blm_bf16* const* B,
+                         const int64_t* K, const int64_t* lda, const int64_t* ldb, int64_t M,
+                         int64_t N, int BN) {
+  BLM_REQUIRE(nseg >= 1 && nseg <= BLM_MAX_SEG, BLM_ERR_ARG, "nseg=%d out of range", nseg);
+  p.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    BLM_REQUIRE(A[s] && B[s], BLM_ERR_ARG, "segment %d has a null operand", s);
+    BLM_REQUIRE(K[s] > 0 && (K[s] % 8) == 0, BLM_ERR_SHAPE, "K[%d]=%lld must be a positive multiple of 8",
+                s, (long long)K[s]);
+    int rc = encode_tmap_bf16(&p.tmA[s], A[s], M, K[s], lda[s], kBM);
+    if (rc != BLM_OK) return rc;
+    rc = encode_tmap_bf16(&p.tmB[s], B[s], N, K[s], ldb[s], BN);
+    if (rc != BLM_OK) return rc;
+    p.kblocks[s] = static_cast<int>((K[s] + kBK - 1) / kBK);
+  }
+  return BLM_OK;
+}
+
+}  // namespace blm
+
+extern "C" {
+
+int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(d != nullptr, BLM_ERR_ARG, "null descriptor");
+  BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
+  BLM_REQUIRE(d->M > 0 && d->N > 0 && d->M < (1ll << 31) && d->N < (1ll << 31), BLM_ERR_SHAPE,
+              "bad GEMM shape M=%lld N=%lld", (long long)d->M, (long long)d->N);
+  BLM_REQUIRE((d->N % 8) == 0, BLM_ERR_SHAPE, "N=%lld must be a multiple of 8", (long long)d->N);
+  BLM_REQUIRE(d->out_f32 || d->out_hi, BLM_ERR_ARG, "no output buffer");
+  BLM_REQUIRE(!d->out_lo || d->out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
+  BLM_REQUIRE((d->ldc % 8) == 0 && d->ldc >= d->N, BLM_ERR_ALIGN, "ldc=%lld", (long long)d->ldc);
+  BLM_REQUIRE(aligned16(d->out_f32) && aligned16(d->out_hi) && aligned16(d->out_lo) &&
+                  aligned16(d->resid) && aligned16(d->bias),
+              BLM_ERR_ALIGN, "output / residual / bias pointers must be 16-byte aligned");
+  BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld",
+              (long long)d->ldr);
+  BLM_REQUIRE(d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX,
+              BLM_ERR_ARG, "unknown activation %d", d->act);
+  BLM_REQUIRE(d->act != BLM_ACT_GPMIX || d->coef, BLM_ERR_ARG, "GP-mix epilogue needs coef");
+
+  // Tile choice: 128x256 tiles unless that leaves most SMs idle, then 128x128.
+  const int m_tiles = static_cast<int>((d->M + kBM - 1) / kBM);
+  const int n_tiles256 = static_cast<int>((d->N + 255) / 256);
+  const bool use256 = (d->N >= 256) && (static_cast<long long>(m_tiles) * n_tiles256 >= num_sms());
+  const int BN = use256 ? 256 : 128;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_segments(p, d->nseg, d->A, d->B, d->K, d->lda, d->ldb, d->M, d->N, BN);
+  if (rc != BLM_OK) return rc;
+  p.M = static_cast<int>(d->M);
+  p.N = static_cast<int>(d->N);
+  p.m_tiles = m_tiles;
+  p.n_tiles = static_cast<int>((d->N + BN - 1) / BN);
+  p.n_groups = p.n_tiles;
+  p.tiles_per_group = 1;
+  p.num_works = p.m_tiles * p.n_tiles;
+  p.bias = d->bias;
+  p.coef = d->coef;
+  p.col_scale = d->col_scale;
+  p.col_scale_cols = d->col_scale_cols;
+  p.resid = d->resid;
+  p.ldr = d->ldr;
+  p.out_f32 = d->out_f32;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+  p.ldc = d->ldc;
+  cudaStream_t st = as_stream(stream);
+  if (BN == 256) {
+    switch (d->act) {
+      case BLM_ACT_NONE: return launch<256, kStages256, EPI_STORE, BLM_ACT_NONE>(p, st);
+      case BLM_ACT_GELU: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU>(p, st);
+      default: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+    }
+  }
+  switch (d->act) {
+    case BLM_ACT_NONE: return launch<128, kStages128, EPI_STORE, BLM_ACT_NONE>(p, st);
+    case BLM_ACT_GELU: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU>(p, st);
+    default: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+  }
+}
+
+// vocabulary groups: enough (m_tile, group) work items to fill the chip, but no
+// more than needed -- each group costs one partial (max, sum, tgt) per row.
+static int nll_groups(int64_t M, int64_t V) {
+  const int m_tiles = static_cast<int>((M + blm::kBM - 1) / blm::kBM);
+  const int n_tiles = static_cast<int>((V + 255) / 256);
+  int sms = blm::num_sms() > 0 ? blm::num_sms() : 148;
+  int g = (sms + m_tiles - 1) / m_tiles;
+  if (g > n_tiles) g = n_tiles;
+  if (g < 1) g = 1;
+  return g;
+}
+
+int64_t blm_vocab_nll_workspace_bytes(int64_t M, int64_t V) {
+  // worst case: one group per N tile
+  const int64_t n_tiles = (V + 255) / 256;
+  const int64_t g = n_tiles < 148 ? n_tiles : 148;
+  return 3 * g * M * static_cast<int64_t>(sizeof(float)) + 64;
+}
+
+int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(d != nullptr, BLM_ERR_ARG, "null descriptor");
+  BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
+  BLM_REQUIRE(d->M > 0 && d->V > 0 && d->M < (1ll << 31) && d->V < (1ll << 31), BLM_ERR_SHAPE,
+              "bad shape M=%lld V=%lld", (long long)d->M, (long long)d->V);
+  BLM_REQUIRE(d->targets && d->nll && d->workspace, BLM_ERR_ARG, "null targets / nll / workspace");
+  BLM_REQUIRE(aligned16(d->workspace), BLM_ERR_ALIGN, "workspace must be 16-byte aligned");
+  const int groups = nll_groups(d->M, d->V);
+  BLM_REQUIRE(d->workspace_bytes >= 3ll * groups * d->M * (int64_t)sizeof(float), BLM_ERR_ARG,
+              "workspace too small: %lld bytes", (long long)d->workspace_bytes);
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_segments(p, d->nseg, d->H, d->E, d->K, d->ldh, d->lde, d->M, d->V, 256);
+  if (rc != BLM_OK) return rc;
+  p.M = static_cast<int>(d->M);
+  p.N = static_cast<int>(d->V);
+  p.m_tiles = static_cast<int>((d->M + kBM - 1) / kBM);
+  p.n_tiles = static_cast<int>((d->V + 255) / 256);
+  p.tiles_per_group = (p.n_tiles + groups - 1) / groups;
+  const int used_groups = (p.n_tiles + p.tiles_per_group - 1) / p.tiles_per_group;  // no empty groups
+  p.n_groups = used_groups;
+  p.num_works = p.m_tiles * used_groups;
+  p.bias = d->bias;
+  p.targets = d->targets;
+  float* ws = reinterpret_cast<float*>(d->workspace);
+  p.part_max = ws;
+  p.part_sum = ws + static_cast<int64_t>(used_groups) * d->M;
+  p.part_tgt = ws + 2 * static_cast<int64_t>(used_groups) * d->M;
+  cudaStream_t st = as_stream(stream);
+  rc = launch<256, kStages256, EPI_NLL, BLM_ACT_NONE>(p, st);
+  if (rc != BLM_OK) return rc;
+  const int threads = 256;
+  const int blocks = static_cast<int>((d->M + threads - 1) / threads);
+  nll_merge_kernel<<<blocks, threads, 0, st>>>(p.part_max, p.part_sum, p.part_tgt, used_groups, p.M,
+                                               d->nll);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_segment_sum(const float* x, const int32_t* seg_offsets, int64_t nseg, float* out,
+                    blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(x && seg_offsets && out && nseg > 0, BLM_ERR_ARG, "bad segment_sum arguments");
+  const int threads = 256;
+  const long long blocks = (nseg * 32 + threads - 1) / threads;
+  segment_sum_kernel<<<static_cast<unsigned>(blocks), threads, 0, as_stream(stream)>>>(
+      x, seg_offsets, nseg, out);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+}  // extern "C"

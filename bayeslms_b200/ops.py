@@ -1,0 +1,237 @@
+"""Tensor-level wrappers over the C ABI: torch owns the memory and the stream, the
+kernels in ``libbayeslm_b200.so`` do all the arithmetic.
+
+Precision modes (``prec``):
+  ``"bf16"``    one bf16 product per GEMM, fp32 accumulation (fast path);
+  ``"bf16x3"``  every fp32 operand is carried as ``hi + lo`` bf16 pairs and each GEMM
+                accumulates ``hi*hi + hi*lo + lo*hi`` in fp32 -- about 16 mantissa bits,
+                the mode held to the reference's fp32 results within 1e-3.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_GPMIX, ACT_NONE, EPS_NONE, EPS_PHILOX, EPS_PTR, GemmDesc, VocabNllDesc,
+                   check, lib)
+
+PRECISIONS = ("bf16", "bf16x3")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.BlmError("bayeslms_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+@dataclass
+class Split:
+    """An fp32 matrix carried as bf16 ``hi`` (+ optional ``lo`` residual), both [rows, cols]."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor] = None
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def float(self) -> torch.Tensor:
+        x = self.hi.float()
+        return x if self.lo is None else x + self.lo.float()
+
+
+def empty_split(rows: int, cols: int, prec: str, device) -> Split:
+    hi = torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
+    lo = torch.empty(rows, cols, dtype=torch.bfloat16, device=device) if prec == "bf16x3" else None
+    return Split(hi, lo)
+
+
+def split(x: torch.Tensor, prec: str = "bf16x3") -> Split:
+    """fp32 [rows, cols] -> Split."""
+    _require_cuda(x)
+    x = x.detach().contiguous().float()
+    out = empty_split(x.shape[0] if x.dim() == 2 else 1, x.shape[-1] if x.dim() == 2 else x.numel(), prec, x.device)
+    check(lib().blm_split_bf16(_ptr(x), _ptr(out.hi), _ptr(out.lo), x.numel(), _stream()), "blm_split_bf16")
+    if x.dim() != 2:
+        out = Split(out.hi.view(x.shape), None if out.lo is None else out.lo.view(x.shape))
+    return out
+
+
+def _segments(a: Split, b: Split, prec: str):
+    if prec == "bf16":
+        return [(a.hi, b.hi)]
+    if prec == "bf16x3":
+        if a.lo is None or b.lo is None:
+            raise _lib.BlmError("bf16x3 needs (hi, lo) operands")
+        return [(a.hi, b.hi), (a.hi, b.lo), (a.lo, b.hi)]
+    raise _lib.BlmError(f"unknown precision {prec!r}")
+
+
+def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         coef: Optional[torch.Tensor] = None, col_scale: float = 1.0, col_scale_cols: int = 0,
+         resid: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+         out: Optional[Split] = None, extra: Sequence = ()):
+    """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
+    accumulated into the same output (K-concatenation)."""
+    segs = _segments(a, b, prec)
+    for (a2, b2) in extra:
+        segs += _segments(a2, b2, prec)
+    M, N = a.hi.shape[0], b.hi.shape[0]
+    d = GemmDesc()
+    d.M, d.N, d.nseg, d.act = M, N, len(segs), act
+    for i, (x, w) in enumerate(segs):
+        _require_cuda(x, w)
+        assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+        assert x.shape[1] == w.shape[1] and x.stride(1) == 1 and w.stride(1) == 1
+        d.A[i], d.B[i] = x.data_ptr(), w.data_ptr()
+        d.K[i], d.lda[i], d.ldb[i] = x.shape[1], x.stride(0), w.stride(0)
+    d.bias, d.coef = _ptr(bias), _ptr(coef)
+    d.col_scale, d.col_scale_cols = col_scale, col_scale_cols
+    if resid is not None:
+        assert resid.dtype == torch.float32 and resid.stride(1) == 1
+        d.resid, d.ldr = _ptr(resid), resid.stride(0)
+    ldc = None
+    for t in (out_f32, None if out is None else out.hi, None if out is None else out.lo):
+        if t is not None:
+            assert t.stride(1) == 1 and (ldc is None or ldc == t.stride(0))
+            ldc = t.stride(0)
+    d.out_f32 = _ptr(out_f32)
+    d.out_hi = _ptr(None if out is None else out.hi)
+    d.out_lo = _ptr(None if out is None else out.lo)
+    d.ldc = ldc if ldc is not None else N
+    check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
+
+
+_nll_ws = {}
+
+
+def vocab_nll(h: Split, e: Split, bias: Optional[torch.Tensor], targets: torch.Tensor, *, prec: str = "bf16",
+              extra: Sequence = (), out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-row ``-log softmax(h @ e.T + bias)[target]`` without materialising the logits."""
+    segs = _segments(h, e, prec)
+    for (h2, e2) in extra:
+        segs += _segments(h2, e2, prec)
+    M, V = h.hi.shape[0], e.hi.shape[0]
+    dev = h.hi.device
+    nbytes = lib().blm_vocab_nll_workspace_bytes(M, V)
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _nll_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _nll_ws[key] = ws
+    if out is None:
+        out = torch.empty(M, dtype=torch.float32, device=dev)
+    assert targets.dtype == torch.int32 and targets.numel() == M
+    d = VocabNllDesc()
+    d.M, d.V, d.nseg = M, V, len(segs)
+    for i, (x, w) in enumerate(segs):
+        _require_cuda(x, w)
+        d.H[i], d.E[i] = x.data_ptr(), w.data_ptr()
+        d.K[i], d.ldh[i], d.lde[i] = x.shape[1], x.stride(0), w.stride(0)
+    d.bias, d.targets, d.nll = _ptr(bias), _ptr(targets), _ptr(out)
+    d.workspace, d.workspace_bytes = _ptr(ws), ws.numel()
+    check(lib().blm_vocab_nll(C.byref(d), _stream()), "blm_vocab_nll")
+    return out
+
+
+def segment_sum(x: torch.Tensor, offsets: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = offsets.numel() - 1
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    assert offsets.dtype == torch.int32
+    check(lib().blm_segment_sum(_ptr(x), _ptr(offsets), n, _ptr(out), _stream()), "blm_segment_sum")
+    return out
+
+
+def embed(tokens: torch.Tensor, pos: Optional[torch.Tensor], emb: torch.Tensor, pe: Optional[torch.Tensor],
+          scale: float, *, prec: str = "bf16", want_f32: bool = True):
+    """Returns (x_f32 or None, Split)."""
+    M, d = tokens.numel(), emb.shape[1]
+    dev = emb.device
+    x = torch.empty(M, d, dtype=torch.float32, device=dev) if want_f32 else None
+    s = empty_split(M, d, prec, dev)
+    check(lib().blm_embed(_ptr(tokens), _ptr(pos), _ptr(emb), _ptr(pe), scale, M, d, _ptr(x), _ptr(s.hi),
+                          _ptr(s.lo), _stream()), "blm_embed")
+    return x, s
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, prec: str = "bf16",
+              want_f32: bool = True):
+    M, d = x.shape
+    y = torch.empty_like(x) if want_f32 else None
+    s = empty_split(M, d, prec, x.device)
+    check(lib().blm_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), eps, M, d, _ptr(y), _ptr(s.hi), _ptr(s.lo),
+                              _stream()), "blm_layernorm")
+    return y, s
+
+
+def reparam(mu: torch.Tensor, lgstd: Optional[torch.Tensor], *, eps: Optional[torch.Tensor] = None,
+            seed: Optional[int] = None, stream_id: int = 0, prec: str = "bf16", want_f32: bool = False):
+    """``mu + exp(lgstd) * eps`` for a 2-D row-slice view ``mu`` (unit column stride).
+    eps: explicit tensor, or Philox(seed, stream_id) when ``seed`` is given, or none (mean)."""
+    if mu.dim() == 1:
+        mu = mu.view(1, -1)
+        lgstd = None if lgstd is None else lgstd.view(1, -1)
+        eps = None if eps is None else eps.view(1, -1)
+    rows, cols = mu.shape
+    assert mu.stride(1) == 1
+    mode = EPS_PTR if eps is not None else (EPS_PHILOX if seed is not None else EPS_NONE)
+    dev = mu.device
+    w = torch.empty(rows, cols, dtype=torch.float32, device=dev) if want_f32 else None
+    s = empty_split(rows, cols, prec, dev)
+    if lgstd is not None:
+        lgstd = lgstd.contiguous()
+    if eps is not None:
+        eps = eps.contiguous().float()
+    check(lib().blm_reparam(_ptr(mu), mu.stride(0), _ptr(lgstd), _ptr(eps), mode, int(seed or 0), int(stream_id),
+                            rows, cols, _ptr(w), _ptr(s.hi), _ptr(s.lo), _stream()), "blm_reparam")
+    return w, s
+
+
+def philox_normal(seed: int, stream_id: int, n: int, device) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(lib().blm_philox_normal(int(seed), int(stream_id), n, _ptr(out), _stream()), "blm_philox_normal")
+    return out
+
+
+def mha_causal(qkv: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len: int, *, prec: str = "bf16",
+               want_f32: bool = False):
+    M, d3 = qkv.shape
+    d = d3 // 3
+    nseq = seq_offsets.numel() - 1
+    o = torch.empty(M, d, dtype=torch.float32, device=qkv.device) if want_f32 else None
+    s = empty_split(M, d, prec, qkv.device)
+    check(lib().blm_mha_causal(_ptr(qkv), _ptr(seq_offsets), nseq, nhead, d // nhead, max_len, _ptr(o), _ptr(s.hi),
+                               _ptr(s.lo), _stream()), "blm_mha_causal")
+    return o, s
+
+
+_kl_ws = {}
+
+
+def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_one: bool = False,
+             scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+    """out[0] (+)= scale * 0.5 * mean(mu^2 - 2 lgstd + exp(2 lgstd) [- 1]) over a 2-D row-slice view."""
+    if mu.dim() == 1:
+        mu, lgstd = mu.view(1, -1), lgstd.view(1, -1)
+    rows, cols = mu.shape
+    assert mu.stride(1) == 1 and lgstd.is_contiguous() and lgstd.shape == mu.shape
+    key = (mu.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _kl_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(lib().blm_kl_workspace_bytes(), dtype=torch.uint8, device=mu.device)
+        _kl_ws[key] = ws
+    check(lib().blm_kl_gauss(_ptr(mu), mu.stride(0), _ptr(lgstd), rows, cols, int(minus_one), scale,
+                             int(accumulate), _ptr(out), _ptr(ws), _stream()), "blm_kl_gauss")
+    return out

@@ -1,0 +1,218 @@
+/*
+ * bayeslm_b200 -- C ABI of the B200 (sm_100a) kernels behind the BayesLMs
+ * n-best rescoring / fine-tune hot path.
+ *
+ * The reference (AmourWaltz/BayesLMs) has no FFI of its own: its seam is the
+ * Python module `steps/pytorchnn/model.py`, whose nn.Module classes call into
+ * PyTorch (cuBLAS/cuDNN/ATen).  Each entry point below replaces one group of
+ * those library calls; the citation after "replaces:" is the reference call
+ * site (path:line under the reference checkout).  The Python classes in
+ * bayeslms_b200/model.py keep the reference constructors / forward signatures
+ * and call these functions through ctypes (bayeslms_b200/_lib.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library
+ *     never allocates device memory, never synchronises and only touches the
+ *     stream it is given;
+ *   - matrices are row-major; "ld*" are leading dimensions in ELEMENTS;
+ *   - bf16 buffers are raw uint16_t storage (`blm_bf16`);
+ *   - return value: BLM_OK or a negative BLM_ERR_*; blm_last_error() returns a
+ *     thread-local message for the last failure;
+ *   - there is no CPU fallback and no other architecture: blm_init() fails
+ *     with BLM_ERR_ARCH unless the device is compute capability 10.0.
+ */
+#ifndef BAYESLM_B200_H_
+#define BAYESLM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t blm_bf16;
+typedef void* blm_stream; /* cudaStream_t */
+
+enum {
+  BLM_OK = 0,
+  BLM_ERR_SHAPE = -1, /* unsupported / inconsistent sizes            */
+  BLM_ERR_ALIGN = -2, /* pointer or leading dimension not 16-B aligned */
+  BLM_ERR_ARCH = -3,  /* device is not sm_100                          */
+  BLM_ERR_CUDA = -4,  /* a CUDA runtime / driver call failed           */
+  BLM_ERR_ARG = -5    /* null pointer / bad enum                       */
+};
+
+/* activation fused into the GEMM epilogue */
+enum {
+  BLM_ACT_NONE = 0,
+  BLM_ACT_GELU = 1,  /* exact erf GELU, model.py:1035                          */
+  BLM_ACT_GPMIX = 2  /* sum_i coef[i,n]*act_i(z), acts tanh,sigmoid,relu,gelu;
+                        model.py:1893-1899 with act_set of model.py:2263       */
+};
+
+/* where the N(0,1) noise of a reparameterised tensor comes from */
+enum {
+  BLM_EPS_NONE = 0,   /* posterior mean: W = mu                                */
+  BLM_EPS_PTR = 1,    /* explicit eps tensor (parity with injected noise)      */
+  BLM_EPS_PHILOX = 2  /* Philox4x32-10, key=(seed), counter=(element, stream)  */
+};
+
+int blm_version(void);
+const char* blm_last_error(void);
+/* one-time per-device setup: checks cc 10.0, raises dynamic-smem limits. */
+int blm_init(int device);
+int blm_num_sms(void);
+
+/* ------------------------------------------------------------------ GEMM
+ * C[M,N] = epilogue( sum over segments s of  A_s[M,K_s] * B_s[N,K_s]^T )
+ *
+ * Every operand is bf16, K-major.  fp32 tensors are carried as a (hi, lo)
+ * bf16 pair (x ~= hi + lo, see blm_split_bf16); "precise" products
+ * hi*hi + hi*lo + lo*hi are expressed as three segments, a plain bf16 GEMM as
+ * one.  Up to BLM_MAX_SEG segments let two models share one accumulation
+ * (logit interpolation, compute_sentence_scores_bayes_jianwei.py:163).
+ *
+ * epilogue:  z = acc + bias[n];  z *= col_scale for n < col_scale_cols
+ *            (the q-scaling of model.py:877);  z = act(z);  z += resid[m,n];
+ *            then stored to whichever of out_f32 / out_hi / out_lo is non-null
+ *            (out_lo = bf16(z - float(out_hi))).
+ *
+ * replaces: F.linear / nn.Linear at model.py:850,855,876,921,1026,1028,1043,
+ *           1129,1290,1303,1885 (cuBLAS behind ATen in the reference).
+ * needs:    K_s % 8 == 0, N % 8 == 0, lda/ldb % 8 == 0, 16-B aligned pointers.
+ */
+#define BLM_MAX_SEG 6
+
+typedef struct blm_gemm_desc {
+  int64_t M, N;
+  int32_t nseg;
+  int32_t act;                    /* BLM_ACT_*                                 */
+  const blm_bf16* A[BLM_MAX_SEG]; /* [M, K_s], leading dimension lda[s]        */
+  const blm_bf16* B[BLM_MAX_SEG]; /* [N, K_s], leading dimension ldb[s]        */
+  int64_t K[BLM_MAX_SEG];
+  int64_t lda[BLM_MAX_SEG];
+  int64_t ldb[BLM_MAX_SEG];
+  const float* bias;   /* [N] or null                                          */
+  const float* coef;   /* [4, N] (BLM_ACT_GPMIX only)                          */
+  float col_scale;     /* applied to columns [0, col_scale_cols)               */
+  int32_t col_scale_cols;
+  const float* resid;  /* [M, N] fp32 or null, leading dimension ldr           */
+  int64_t ldr;
+  float* out_f32;      /* any of the three may be null                         */
+  blm_bf16* out_hi;
+  blm_bf16* out_lo;
+  int64_t ldc;         /* shared by the three outputs                          */
+} blm_gemm_desc;
+
+int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
+
+/* ------------------------------------------- output projection + NLL (d)
+ * nll[m] = logsumexp_v( h[m,:] . E[v,:] + b[v] ) - ( h[m,:] . E[t_m,:] + b[t_m] )
+ * with the [M, V] logits living only in tensor memory: the vocabulary is
+ * streamed tile by tile through the tensor cores and folded into a running
+ * (max, sum-exp, target-logit) per row.  Segments as in blm_gemm (3 for the
+ * precise product, 2x3 for two interpolated models whose activations were
+ * pre-scaled by alpha / 1-alpha).
+ *
+ * workspace: blm_vocab_nll_workspace_bytes(M, V) bytes, 16-B aligned.
+ * replaces: decoder nn.Linear (model.py:201,1220,1306) + nn.CrossEntropyLoss
+ *           (compute_sentence_scores_bayes_jianwei.py:168,474).
+ */
+typedef struct blm_vocab_nll_desc {
+  int64_t M, V;
+  int32_t nseg;
+  int32_t reserved;
+  const blm_bf16* H[BLM_MAX_SEG]; /* [M, K_s] hidden states                    */
+  const blm_bf16* E[BLM_MAX_SEG]; /* [V, K_s] output embedding                 */
+  int64_t K[BLM_MAX_SEG];
+  int64_t ldh[BLM_MAX_SEG];
+  int64_t lde[BLM_MAX_SEG];
+  const float* bias;      /* [V] or null                                       */
+  const int32_t* targets; /* [M]                                               */
+  float* nll;             /* [M] out                                           */
+  void* workspace;
+  int64_t workspace_bytes;
+} blm_vocab_nll_desc;
+
+int64_t blm_vocab_nll_workspace_bytes(int64_t M, int64_t V);
+int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream);
+
+/* out[i] = sum of x[seg_offsets[i] .. seg_offsets[i+1])  (per-hypothesis score,
+ * compute_sentence_scores_bayes_jianwei.py:170: length * mean CE).            */
+int blm_segment_sum(const float* x, const int32_t* seg_offsets, int64_t nseg, float* out,
+                    blm_stream stream);
+
+/* ------------------------------------------------------------ elementwise */
+/* fp32 -> bf16 hi (+ optional lo = bf16(x - hi)); n elements. */
+int blm_split_bf16(const float* x, blm_bf16* hi, blm_bf16* lo, int64_t n, blm_stream stream);
+
+/* x[m,:] = emb[tok[m],:] * scale + pe[pos[m],:]      (model.py:1284,116)
+ * pe may be null (LSTM: plain lookup, model.py:218).                          */
+int blm_embed(const int32_t* tokens, const int32_t* pos, const float* emb, const float* pe,
+              float scale, int64_t M, int32_t d, float* out_f32, blm_bf16* out_hi,
+              blm_bf16* out_lo, blm_stream stream);
+
+/* y = LayerNorm(x) * gamma + beta, eps inside the sqrt (nn.LayerNorm,
+ * model.py:1030-1031,1042,1045).                                              */
+int blm_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t M,
+                  int32_t d, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo,
+                  blm_stream stream);
+
+/* Reparameterised tensor  w = mu + exp(lgstd) * eps   (model.py:670-725,
+ * 1086-1102, 1876-1883), written as fp32 and/or a bf16 (hi, lo) pair.
+ * mu is [rows, cols] with leading dimension ldmu (row slices of a larger
+ * tensor, model.py:718); lgstd/eps/out are dense [rows, cols].
+ * eps_mode BLM_EPS_PHILOX draws eps[i] from Philox4x32-10 with key `seed`,
+ * counter (i/4, stream_id), Box-Muller; every rank / launch shape sees the
+ * same noise for the same (seed, stream_id).                                  */
+int blm_reparam(const float* mu, int64_t ldmu, const float* lgstd, const float* eps,
+                int32_t eps_mode, uint64_t seed, uint64_t stream_id, int64_t rows, int64_t cols,
+                float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, blm_stream stream);
+/* The N(0,1) stream blm_reparam uses, exposed so tests can inject it into the
+ * oracle. */
+int blm_philox_normal(uint64_t seed, uint64_t stream_id, int64_t n, float* out, blm_stream stream);
+
+/* ------------------------------------------------------------ attention (c)
+ * Causal multi-head self-attention over packed variable-length hypotheses.
+ * qkv is [M, 3*d] fp32 (q already scaled), hypothesis i owns rows
+ * [seq_offsets[i], seq_offsets[i+1]); heads are contiguous head_dim-wide
+ * column groups; out[M, d] = softmax(q k^T + causal mask) v.
+ * replaces: torch.bmm + mask add + F.softmax + torch.bmm, model.py:889-920.
+ * needs:    head_dim <= 128, sequence length <= 128.                          */
+int blm_mha_causal(const float* qkv, const int32_t* seq_offsets, int64_t nseq, int32_t nhead,
+                   int32_t head_dim, int32_t max_len, float* out_f32, blm_bf16* out_hi,
+                   blm_bf16* out_lo, blm_stream stream);
+
+/* ------------------------------------------------------------------ KL (e)
+ * out[0] (+)= scale * 0.5 * mean_{rows x cols}( mu^2 - 2 lgstd + exp(2 lgstd) [- 1] )
+ * (model.py:762-765 without the -1; 1115; 1255; 1821-1825 with it).
+ * mu is a [rows, cols] view with leading dimension ldmu, lgstd is dense.
+ * `accumulate` adds to out[0] instead of overwriting it.
+ * workspace: blm_kl_workspace_bytes() bytes.                                  */
+int64_t blm_kl_workspace_bytes(void);
+int blm_kl_gauss(const float* mu, int64_t ldmu, const float* lgstd, int64_t rows, int64_t cols,
+                 int32_t minus_one, float scale, int32_t accumulate, float* out, void* workspace,
+                 blm_stream stream);
+
+/* ---------------------------------------------------------------- LSTM (b)
+ * One layer of the LSTM recurrence (gate order i,f,g,o; model.py:812 ->
+ * torch LSTM) over a batch of B independent sequences advanced in lock step.
+ *   gates_x [T, B, 4H] fp32 : x_t W_ih^T + b_ih + b_hh, hoisted (blm_gemm)
+ *   w_hh_hi/lo [4H, H] bf16 : recurrent weight (hi, lo may be null)
+ *   h0, c0 [B, H] fp32      : initial state
+ *   lengths [B] int32       : steps t >= lengths[b] leave (h, c) of row b
+ *                             untouched (right padding)
+ *   out_* [T, B, H]         : h_t (fp32 and/or bf16 hi/lo), zero where padded
+ *   hT, cT [B, H] fp32      : state after each row's last valid step
+ * workspace: blm_lstm_workspace_bytes(B, H) bytes, zero-initialised once.     */
+int64_t blm_lstm_workspace_bytes(int64_t B, int64_t H);
+int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo,
+                   const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
+                   int64_t H, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, float* hT,
+                   float* cT, void* workspace, blm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESLM_B200_H_ */
