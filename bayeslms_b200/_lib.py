@@ -60,6 +60,7 @@ SIGNATURES = {
     "blm_vocab_nll_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_vocab_nll": (C.c_int, [C.POINTER(VocabNllDesc), _p]),
     "blm_segment_sum": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "blm_mc_combine": (C.c_int, [_p, _i64, _i64, _p, _p]),
     "blm_split_bf16": (C.c_int, [_p, _p, _p, _i64, _p]),
     "blm_embed": (C.c_int, [_p, _p, _p, _p, _f, _i64, _i32, _p, _p, _p, _p]),
     "blm_layernorm": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _p]),

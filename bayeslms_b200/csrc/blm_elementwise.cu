@@ -262,6 +262,18 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, l
   }
 }
 
+// Monte-Carlo predictive over K posterior samples: out[m] = -log( 1/K sum_k exp(-nll[k, m]) )
+__global__ void mc_combine_kernel(const float* __restrict__ nll, long long K, long long M, float* __restrict__ out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; m < M; m += stride) {
+    float mn = INFINITY;
+    for (long long k = 0; k < K; ++k) mn = fminf(mn, nll[k * M + m]);
+    float s = 0.0f;
+    for (long long k = 0; k < K; ++k) s += expf(mn - nll[k * M + m]);
+    out[m] = mn - logf(s / static_cast<float>(K));
+  }
+}
+
 static int grid_for(long long work_items, int threads, int per_sm) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * per_sm;
@@ -351,6 +363,14 @@ int blm_philox_normal(uint64_t seed, uint64_t stream_id, int64_t n, float* out, 
   using namespace blm;
   BLM_REQUIRE(out && n > 0, BLM_ERR_ARG, "bad philox arguments");
   philox_normal_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, as_stream(stream)>>>(seed, stream_id, n, out);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_mc_combine(const float* nll, int64_t K, int64_t M, float* out, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(nll && out && K > 0 && M > 0, BLM_ERR_ARG, "bad mc_combine arguments");
+  mc_combine_kernel<<<grid_for(M, 256, 8), 256, 0, as_stream(stream)>>>(nll, K, M, out);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

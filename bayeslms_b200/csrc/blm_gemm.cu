@@ -246,33 +246,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
               z = apply_act<ACT>(z, p.coef, p.N, colc);
               v[j] = z;
             }
+            const long long off = static_cast<long long>(m) * p.ldc + col0;
             if (p.resid) {
               const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
+              if (full) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (col0 + j < p.N) {
+                for (int j = 0; j < 32; j += 4) {
                   const float4 rr = __ldg(reinterpret_cast<const float4*>(r + j));
                   v[j] += rr.x;
                   v[j + 1] += rr.y;
                   v[j + 2] += rr.z;
                   v[j + 3] += rr.w;
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] += __ldg(r + j);
               }
             }
-            const long long off = static_cast<long long>(m) * p.ldc + col0;
-            if (p.out_f32) {
-              float* o = p.out_f32 + off;
+            if (full) {
+              if (p.out_f32) {
+                float* o = p.out_f32 + off;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (col0 + j < p.N)
+                for (int j = 0; j < 32; j += 4)
                   *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (p.out_hi) {
-              __nv_bfloat16* oh = p.out_hi + off;
-              __nv_bfloat16* ol = p.out_lo ? p.out_lo + off : nullptr;
+              }
+              if (p.out_hi) {
+                __nv_bfloat16* oh = p.out_hi + off;
+                __nv_bfloat16* ol = p.out_lo ? p.out_lo + off : nullptr;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (col0 + j < p.N) {
+                for (int j = 0; j < 32; j += 8) {
                   uint32_t h[4], l[4];
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
@@ -284,6 +287,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                   }
                   *reinterpret_cast<uint4*>(oh + j) = make_uint4(h[0], h[1], h[2], h[3]);
                   if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+              }
+            } else {
+              // ragged right edge (N not a multiple of 32): scalar stores
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < p.N) {
+                  if (p.out_f32) p.out_f32[off + j] = v[j];
+                  if (p.out_hi) {
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(v[j]);
+                    p.out_hi[off + j] = hh;
+                    if (p.out_lo) p.out_lo[off + j] = __float2bfloat16_rn(v[j] - __bfloat162float(hh));
+                  }
                 }
               }
             }
@@ -433,13 +449,11 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
   BLM_REQUIRE(d->M > 0 && d->N > 0 && d->M < (1ll << 31) && d->N < (1ll << 31), BLM_ERR_SHAPE,
               "bad GEMM shape M=%lld N=%lld", (long long)d->M, (long long)d->N);
-  BLM_REQUIRE((d->N % 8) == 0, BLM_ERR_SHAPE, "N=%lld must be a multiple of 8", (long long)d->N);
   BLM_REQUIRE(d->out_f32 || d->out_hi, BLM_ERR_ARG, "no output buffer");
   BLM_REQUIRE(!d->out_lo || d->out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
   BLM_REQUIRE((d->ldc % 8) == 0 && d->ldc >= d->N, BLM_ERR_ALIGN, "ldc=%lld", (long long)d->ldc);
-  BLM_REQUIRE(aligned16(d->out_f32) && aligned16(d->out_hi) && aligned16(d->out_lo) &&
-                  aligned16(d->resid) && aligned16(d->bias),
-              BLM_ERR_ALIGN, "output / residual / bias pointers must be 16-byte aligned");
+  BLM_REQUIRE(aligned16(d->out_f32) && aligned16(d->out_hi) && aligned16(d->out_lo) && aligned16(d->resid),
+              BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
   BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld",
               (long long)d->ldr);
   BLM_REQUIRE(d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX,

@@ -1,0 +1,397 @@
+"""Execution engine: walks a model of :mod:`bayeslms_b200.model` and issues the kernels.
+
+Layout in HBM.  Hypotheses are *packed*: the tokens of all hypotheses of a batch are
+concatenated into one [M] axis (no padding), ``offsets`` [n_hyp + 1] marks the hypothesis
+boundaries and ``pos`` holds each token's index inside its hypothesis.  Every activation is a
+row-major [M, width] matrix; fp32 residual streams are kept next to the bf16 (hi[, lo])
+copies the tensor cores read.  Weights are converted once per precision mode into bf16
+(hi[, lo]) K-major matrices and cached until a parameter changes.
+
+Posterior samples.  ``samples`` is a list with one entry per posterior sample: either an
+explicit noise dict (the oracle's ``draw_eps`` layout; parity tests) or an integer sample
+index k whose noise is Philox(seed, tensor_id, k) generated on the device -- a pure function
+of (seed, tensor, k, element), hence identical on every rank whatever the sharding.
+Work that does not depend on the sampled tensor (everything before the first Bayesian
+operator) is done once and shared by all K samples.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .ops import ACT_GELU, ACT_GPMIX, ACT_NONE, Split
+
+Sample = Union[int, dict]
+
+
+# ------------------------------------------------------------------------ batches
+@dataclass
+class PackedBatch:
+    tokens: torch.Tensor    # int32 [M]  input ids  (<s> w1 .. wL)
+    targets: torch.Tensor   # int32 [M]  target ids (w1 .. wL <s>)
+    pos: torch.Tensor       # int32 [M]  position inside the hypothesis
+    offsets: torch.Tensor   # int32 [n_hyp + 1]
+    max_len: int
+    n_tokens: int
+    n_hyp: int
+
+    @staticmethod
+    def from_lists(inputs: Sequence[Sequence[int]], targets: Sequence[Sequence[int]], device) -> "PackedBatch":
+        lens = np.fromiter((len(x) for x in inputs), dtype=np.int64, count=len(inputs))
+        offs = np.zeros(len(inputs) + 1, dtype=np.int32)
+        np.cumsum(lens, out=offs[1:])
+        M = int(offs[-1])
+        host = torch.empty(3 * M + len(offs), dtype=torch.int32).pin_memory() if torch.cuda.is_available() \
+            else torch.empty(3 * M + len(offs), dtype=torch.int32)
+        buf = host.numpy()
+        buf[:M] = np.concatenate([np.asarray(x, dtype=np.int32) for x in inputs]) if M else 0
+        buf[M:2 * M] = np.concatenate([np.asarray(y, dtype=np.int32) for y in targets]) if M else 0
+        buf[2 * M:3 * M] = np.arange(M, dtype=np.int32) - np.repeat(offs[:-1], lens)
+        buf[3 * M:] = offs
+        dev = host.to(device, non_blocking=True)
+        return PackedBatch(dev[:M], dev[M:2 * M], dev[2 * M:3 * M], dev[3 * M:], int(lens.max()) if len(lens) else 0,
+                           M, len(inputs))
+
+    @property
+    def h2d_bytes(self) -> int:
+        return 4 * (3 * self.n_tokens + self.n_hyp + 1)
+
+
+# ------------------------------------------------------------------------- plans
+def _params_version(model) -> int:
+    return sum(p._version for p in model.parameters()) + sum(p.data_ptr() & 0xFFFF for p in model.parameters())
+
+
+class _Plan:
+    """bf16 (hi[, lo]) copies of the weights of one model for one precision mode."""
+
+    def __init__(self, model, prec: str):
+        if prec not in ops.PRECISIONS:
+            raise _lib.BlmError(f"unknown precision {prec!r}; choose from {ops.PRECISIONS}")
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.BlmError("the model must live on a CUDA device: bayeslms_b200 has no CPU path")
+        _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.prec, self.device = prec, dev
+        self.version = _params_version(model)
+        self.split = lambda w: ops.split(w.detach(), prec)
+        with torch.no_grad():
+            self.emb = model.encoder.weight.detach().float().contiguous()
+            self.E = self.split(model.decoder.weight)
+            self.dec_b = model.decoder.bias.detach().float().contiguous()
+            if model.family == "bayes_lstm":
+                self._lstm(model)
+            else:
+                self._transformer(model)
+
+    def _transformer(self, m):
+        sp = self.split
+        self.pe = m.pos_encoder.pe.detach()[:, 0, :].float().contiguous()
+        self.layers = []
+        for layer in m.transformerlayers:
+            a = layer.self_attn
+            L = {"kind": layer.kind}
+            if layer.kind == "bayes_mha":
+                w = torch.cat([a.q_net.weight, a.k_net.weight, a.v_net.weight], 0)
+                b = torch.cat([a.q_net.bias, a.k_net.bias, a.v_net.bias], 0)
+                L["qkv"], L["qkv_b"] = sp(w), b.detach().float().contiguous()
+                L["o"], L["o_b"] = sp(a.o_net.weight_mean), None
+                L["o_mu"], L["o_ls"] = a.o_net.weight_mean.detach(), a.o_net.weight_lgstd.detach()
+            else:
+                L["qkv"], L["qkv_b"] = sp(a.qkv_net.weight), a.qkv_net.bias.detach().float().contiguous()
+                L["o"], L["o_b"] = sp(a.o_net.weight), a.o_net.bias.detach().float().contiguous()
+            if layer.kind == "gauss":
+                g = layer.gpnn
+                L["w1"], L["b1"] = sp(g.weights_mean), g.bias_mean.detach().float().contiguous()
+                L["coef"] = g.coef_mean.detach().float().contiguous()
+                L["gp"] = g
+            else:
+                L["w1"], L["b1"] = sp(layer.linear1.weight), layer.linear1.bias.detach().float().contiguous()
+            if layer.kind == "bayes_ffn":
+                L["w2"], L["b2"] = sp(layer.linear2.weight_mean), None
+                L["w2_mu"], L["w2_ls"] = layer.linear2.weight_mean.detach(), layer.linear2.weight_lgstd.detach()
+            else:
+                L["w2"], L["b2"] = sp(layer.linear2.weight), layer.linear2.bias.detach().float().contiguous()
+            for n in ("norm1", "norm2"):
+                ln = getattr(layer, n)
+                L[n] = (ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous(), ln.eps)
+            self.layers.append(L)
+        if getattr(m, "bayes_embed", False):
+            self.embed_w = sp(m.embed_mean)
+            self.embed_wt = sp(m.embed_mean.detach().t().contiguous())
+            self.embed_mu, self.embed_ls = m.embed_mean.detach(), m.embed_lgstd.detach()
+
+    def _lstm(self, m):
+        r = m.rnn
+        self.lstm = []
+        for layer in (1, 2):
+            self.lstm.append({
+                "w_ih": self.split(getattr(r, f"weight_ih_mean_{layer}")),
+                "w_hh": self.split(getattr(r, f"weight_hh_mean_{layer}")),
+                "bias": (getattr(r, f"bias_ih_mean_{layer}") + getattr(r, f"bias_hh_mean_{layer}")).detach().float().contiguous(),
+            })
+
+
+def plan_for(model, prec: str) -> _Plan:
+    cache = model.__dict__.setdefault("_blm_plans", {})
+    p = cache.get(prec)
+    if p is None or p.version != _params_version(model):
+        p = cache[prec] = _Plan(model, prec)
+    return p
+
+
+# --------------------------------------------------------------------- sampling
+# tensor ids of the Philox streams (stream_id = tensor_id << 32 | sample index)
+_TID = {"ffn_w2": 1, "mha_o": 2, "embed": 3, "gp_coef": 4, "gp_w": 5, "gp_b": 6,
+        "lstm": 16}  # lstm tensors use 16 + index in the reference draw order
+
+
+def _stream_id(tid: int, k: int) -> int:
+    return (tid << 32) | (k & 0xFFFFFFFF)
+
+
+def _sampled(mu, lgstd, tid: int, sample: Sample, eps_value, seed, prec, want_f32=False):
+    if isinstance(sample, dict):
+        eps = eps_value.to(mu.device, non_blocking=True).float()
+        return ops.reparam(mu, lgstd, eps=eps, prec=prec, want_f32=want_f32)
+    if seed is None:
+        raise _lib.BlmError("Philox sampling needs a seed")
+    return ops.reparam(mu, lgstd, seed=seed, stream_id=_stream_id(tid, int(sample)), prec=prec, want_f32=want_f32)
+
+
+def _first_sampled_part(model) -> Optional[str]:
+    """Which part of the forward pass first depends on the posterior sample."""
+    fam = model.family
+    if fam == "bayes_tm":
+        return {"FFN": "D", "MHA": "B", "EMB": "E"}.get(model.bayes_pos)
+    if fam == "gauss_tm" and model.gauss_pos in (1, 2, 3):
+        return "C"
+    return None
+
+
+# ------------------------------------------------------------------ transformer
+class _TmRun:
+    def __init__(self, model, plan: _Plan, batch: PackedBatch):
+        self.m, self.p, self.b = model, plan, batch
+        self.prec = plan.prec
+        self.d = model.ninp
+        self.nhead = model.nhead
+        self.M = batch.n_tokens
+        self.dev = plan.device
+
+    def f32(self, cols):
+        return torch.empty(self.M, cols, dtype=torch.float32, device=self.dev)
+
+    # part A: fused QKV projection (q scaled by head_dim^-1/2 after the bias) + causal attention
+    def part_a(self, L, xs: Split) -> Split:
+        d = self.d
+        qkv = self.f32(3 * d)
+        ops.gemm(xs, L["qkv"], prec=self.prec, bias=L["qkv_b"], col_scale=float(d // self.nhead) ** -0.5,
+                 col_scale_cols=d, out_f32=qkv)
+        _, att = ops.mha_causal(qkv, self.b.offsets, self.nhead, self.b.max_len, prec=self.prec)
+        return att
+
+    # part B: output projection + residual, LayerNorm 1
+    def part_b(self, L, x32, att: Split, w_o: Split):
+        y = self.f32(self.d)
+        ops.gemm(att, w_o, prec=self.prec, bias=L["o_b"], resid=x32, out_f32=y)
+        g, b, eps = L["norm1"]
+        return ops.layernorm(y, g, b, eps, prec=self.prec)
+
+    # part C: first FFN projection with the activation fused (GELU, or the GP mixture)
+    def part_c(self, L, x1s: Split, w1: Split, b1, coef) -> Split:
+        h = ops.empty_split(self.M, w1.hi.shape[0], self.prec, self.dev)
+        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=ACT_GPMIX if coef is not None else ACT_GELU, coef=coef, out=h)
+        return h
+
+    # part D: second FFN projection + residual, LayerNorm 2
+    def part_d(self, L, x1_32, h: Split, w2: Split):
+        y = self.f32(self.d)
+        ops.gemm(h, w2, prec=self.prec, bias=L["b2"], resid=x1_32, out_f32=y)
+        g, b, eps = L["norm2"]
+        return ops.layernorm(y, g, b, eps, prec=self.prec)
+
+    def gp_weights(self, L, sample: Optional[Sample], seed):
+        """(w1, b1, coef) of the GP layer for one posterior sample (None = mean)."""
+        g = L["gp"]
+        w1, b1, coef = L["w1"], L["b1"], L["coef"]
+        if sample is None:
+            return w1, b1, coef
+        e = sample.get("layer0", {}) if isinstance(sample, dict) else {}
+        if g.gpnn_type in (1, 3):
+            coef, _ = _sampled(g.coef_mean.detach(), g.coef_lgstd.detach(), _TID["gp_coef"], sample, e.get("coef"), seed,
+                               "bf16", want_f32=True)
+        if g.gpnn_type in (2, 3):
+            _, w1 = _sampled(g.weights_mean.detach(), g.weights_lgstd.detach(), _TID["gp_w"], sample, e.get("weights"),
+                             seed, self.prec)
+            b1, _ = _sampled(g.bias_mean.detach(), g.bias_lgstd.detach(), _TID["gp_b"], sample, e.get("bias"), seed,
+                             "bf16", want_f32=True)
+            b1 = b1.view(-1)
+        return w1, b1, coef
+
+    def layer(self, L, x32, xs, sample: Optional[Sample], seed, start="A", carry=None):
+        """Run one layer from part ``start``; ``carry`` holds what the skipped parts produced."""
+        kind = L["kind"]
+        if start == "A":
+            att = self.part_a(L, xs)
+        else:
+            att = carry["att"]
+        if start in ("A", "B"):
+            w_o = L["o"]
+            if kind == "bayes_mha" and sample is not None:
+                e = sample.get("layer0") if isinstance(sample, dict) else None
+                _, w_o = _sampled(L["o_mu"], L["o_ls"], _TID["mha_o"], sample, e, seed, self.prec)
+            x1_32, x1s = self.part_b(L, x32, att, w_o)
+        else:
+            x1_32, x1s = carry["x1"]
+        if start in ("A", "B", "C"):
+            if kind == "gauss":
+                w1, b1, coef = self.gp_weights(L, sample, seed)
+            else:
+                w1, b1, coef = L["w1"], L["b1"], None
+            h = self.part_c(L, x1s, w1, b1, coef)
+        else:
+            h = carry["h"]
+        w2 = L["w2"]
+        if kind == "bayes_ffn" and sample is not None:
+            e = sample.get("layer0") if isinstance(sample, dict) else None
+            _, w2 = _sampled(L["w2_mu"], L["w2_ls"], _TID["ffn_w2"], sample, e, seed, self.prec)
+        return self.part_d(L, x1_32, h, w2)
+
+    def prefix(self, upto: Optional[str]):
+        """Sample-independent work: embedding and the parts of layer 0 before ``upto``."""
+        p, b = self.p, self.b
+        if getattr(self.m, "bayes_embed", False):
+            # EMB variant: x = (E[tok] sqrt(d)) W^T + pe (model.py:1284-1293); the embedding rows and
+            # the positional rows (gathered by the same lookup kernel) are all that can be shared
+            _, x0s = ops.embed(b.tokens, None, p.emb, None, math.sqrt(self.d), prec=self.prec, want_f32=False)
+            pe_rows, _ = ops.embed(b.pos, None, p.pe, None, 1.0, prec="bf16", want_f32=True)
+            return {"x0s": x0s, "pe_rows": pe_rows}
+        carry = {"x": ops.embed(b.tokens, b.pos, p.emb, p.pe, math.sqrt(self.d), prec=self.prec)}
+        if upto is None or not p.layers:
+            return carry
+        x32, xs = carry["x"]
+        L = p.layers[0]
+        if upto in ("B", "C", "D"):
+            carry["att"] = self.part_a(L, xs)
+        if upto in ("C", "D"):
+            carry["x1"] = self.part_b(L, x32, carry["att"], L["o"])
+        if upto == "D":
+            carry["h"] = self.part_c(L, carry["x1"][1], L["w1"], L["b1"], None)
+        return carry
+
+    def hidden(self, carry, upto: Optional[str], sample: Optional[Sample], seed) -> Split:
+        """Finish the forward pass for one posterior sample; returns the decoder input."""
+        p = self.p
+        emb_variant = getattr(self.m, "bayes_embed", False)
+        if emb_variant:
+            w = p.embed_w
+            if sample is not None:
+                e = sample.get("embed") if isinstance(sample, dict) else None
+                _, w = _sampled(p.embed_mu, p.embed_ls, _TID["embed"], sample, e, seed, self.prec)
+            x32 = self.f32(self.d)
+            xs = ops.empty_split(self.M, self.d, self.prec, self.dev)
+            ops.gemm(carry["x0s"], w, prec=self.prec, resid=carry["pe_rows"], out_f32=x32, out=xs)
+        else:
+            x32, xs = carry["x"]
+        for i, L in enumerate(p.layers):
+            start = upto if (i == 0 and upto in ("B", "C", "D")) else "A"
+            x32, xs = self.layer(L, x32, xs, sample if i == 0 else None, seed, start, carry if i == 0 else None)
+        if emb_variant:
+            out = ops.empty_split(self.M, self.d, self.prec, self.dev)
+            ops.gemm(xs, p.embed_wt, prec=self.prec, out=out)  # F.linear(x, embed_mean.t()), mean only (model.py:1303)
+            xs = out
+        return xs
+
+
+def _normalise_samples(K, seed, eps_list) -> Optional[List[Sample]]:
+    if eps_list is not None:
+        return list(eps_list)
+    if K and K >= 1 and seed is not None:
+        return list(range(K))
+    return None
+
+
+@torch.no_grad()
+def transformer_score(model, batch: PackedBatch, *, K: int = 0, seed: Optional[int] = None,
+                      eps_list: Optional[Sequence[dict]] = None, prec: str = "bf16",
+                      return_token_nll: bool = False):
+    """Per-hypothesis NLL [n_hyp] (fp32, device).  Posterior mean unless ``eps_list`` (injected noise)
+    or ``K`` + ``seed`` (device Philox noise) ask for sampling; K samples are combined per token as
+    the Monte-Carlo predictive -log(1/K sum_k p_k)."""
+    plan = plan_for(model, prec)
+    run = _TmRun(model, plan, batch)
+    samples = _normalise_samples(K, seed, eps_list)
+    upto = _first_sampled_part(model) if samples else None
+    carry = run.prefix(upto)
+    if not samples:
+        xs = run.hidden(carry, None, None, None)
+        tok_nll = ops.vocab_nll(xs, plan.E, plan.dec_b, batch.targets, prec=prec)
+    else:
+        per = torch.empty(len(samples), batch.n_tokens, dtype=torch.float32, device=plan.device)
+        for k, s in enumerate(samples):
+            xs = run.hidden(carry, upto, s if upto else None, seed)
+            ops.vocab_nll(xs, plan.E, plan.dec_b, batch.targets, prec=prec, out=per[k])
+            if upto is None:  # deterministic model: all samples identical
+                per[1:] = per[0]
+                break
+        tok_nll = per[0] if len(samples) == 1 else ops.mc_combine(per)
+    if return_token_nll:
+        return tok_nll
+    return ops.segment_sum(tok_nll, batch.offsets)
+
+
+@torch.no_grad()
+def transformer_logits(model, src: torch.Tensor) -> torch.Tensor:
+    """Reference-compatible ``forward``: (T, B) -> (T, B, V) fp32 logits, computed with the
+    precise (bf16x3) product.  Eval mode = posterior mean (score.py:225).  Train mode draws one
+    fresh Philox sample per call for the Bayesian tensors (model.py:1084,1244,1876); dropout is not
+    applied -- use p=0 modules for training-mode parity tests."""
+    T, B = src.shape
+    prec = "bf16x3"
+    plan = plan_for(model, prec)
+    cols = src.t().contiguous().to(torch.int32)  # hypothesis-major packing
+    offs = torch.arange(0, (B + 1) * T, T, dtype=torch.int32, device=src.device)
+    pos = torch.arange(T, dtype=torch.int32, device=src.device).repeat(B)
+    batch = PackedBatch(cols.view(-1), cols.view(-1), pos, offs, T, T * B, B)
+    run = _TmRun(model, plan, batch)
+    sample, seed, upto = None, None, None
+    if model.training:
+        gp_off = model.family == "gauss_tm" and not model.transformerlayers[0].gpnn.sample
+        if _first_sampled_part(model) and not gp_off:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            sample, upto = 0, _first_sampled_part(model)
+    xs = run.hidden(run.prefix(upto), upto, sample, seed)
+    V = plan.E.hi.shape[0]
+    ld = (V + 7) // 8 * 8
+    logits = torch.empty(T * B, ld, dtype=torch.float32, device=src.device)
+    ops.gemm(xs, plan.E, prec=prec, bias=plan.dec_b, out_f32=logits)
+    return logits[:, :V].reshape(B, T, V).transpose(0, 1)
+
+
+# --------------------------------------------------------------------------- KL
+def kl_sum(terms, minus_one: bool) -> torch.Tensor:
+    """sum_i scale_i * 0.5 * mean(mu_i^2 - 2 rho_i + exp(2 rho_i) [- 1]) as a 0-dim device tensor."""
+    dev = terms[0][0].device
+    if dev.type != "cuda":
+        raise _lib.BlmError("KL runs on the GPU: move the model to a CUDA device")
+    _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+    out = torch.zeros(1, dtype=torch.float32, device=dev)
+    for mu, lgstd, scale in terms:
+        ops.kl_gauss(mu.detach(), lgstd.detach().contiguous(), out, minus_one=minus_one, scale=float(scale),
+                     accumulate=True)
+    return out[0]
+
+
+# ------------------------------------------------------------------------- LSTM
+def lstm_logits(model, x, hidden):
+    raise _lib.BlmError("LSTM path not built yet")
+
+
+def lstm_score(model, batch, hidden, **kw):
+    raise _lib.BlmError("LSTM path not built yet")

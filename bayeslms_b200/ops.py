@@ -154,6 +154,16 @@ def segment_sum(x: torch.Tensor, offsets: torch.Tensor, out: Optional[torch.Tens
     return out
 
 
+def mc_combine(nll_km: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[K, M] per-sample token NLLs -> [M] Monte-Carlo predictive NLL."""
+    K, M = nll_km.shape
+    assert nll_km.is_contiguous() and nll_km.dtype == torch.float32
+    if out is None:
+        out = torch.empty(M, dtype=torch.float32, device=nll_km.device)
+    check(lib().blm_mc_combine(_ptr(nll_km), K, M, _ptr(out), _stream()), "blm_mc_combine")
+    return out
+
+
 def embed(tokens: torch.Tensor, pos: Optional[torch.Tensor], emb: torch.Tensor, pe: Optional[torch.Tensor],
           scale: float, *, prec: str = "bf16", want_f32: bool = True):
     """Returns (x_f32 or None, Split)."""

@@ -1,0 +1,258 @@
+"""N-best rescoring driver: the B200 counterpart of the reference's
+``steps/pytorchnn/compute_sentence_scores_bayes_jianwei.py`` (``score.py`` below).
+
+Same command line (score.py:310-359), same input (``words_text``: ``<utt>-<n> w1 w2 ...``,
+vocabulary ``word idx``) and output (``lmwt.nn``: ``<utt>-<n> %.4f``) formats, so it drops into
+stage 6 of ``lmrescore_nbest_pytorchnn_cuda.sh``.  What changes is how the work is laid out:
+
+* the reference scores one hypothesis at a time at batch size 1 with two host syncs per
+  hypothesis (score.py:148-170); here all hypotheses are packed into token-major batches of
+  up to ``max_tokens`` tokens, ids go to the device once per batch and scores come back once;
+* Transformer hypotheses are independent -> any packing order is valid;
+* LSTM: all hypotheses of an utterance share their initial state and the next utterance
+  starts from the state after hypothesis #0 (score.py:271-274), which makes a *session*
+  (the reference's per-JOB archive, state reset at score.py:232) the independent unit:
+  phase 1 runs the hypothesis-#0 chain of every session in lock step, phase 2 scores all
+  hypotheses of all utterances in parallel from the recorded states;
+* multi-GPU: utterances (Transformer) or sessions (LSTM) are sharded over ranks with
+  replicated weights; the only communication is one final gather of the score vector.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import engine
+from .engine import PackedBatch
+
+
+# ----------------------------------------------------------------------- file formats
+def read_vocab(path: str) -> Dict[str, int]:
+    """``word idx`` per line; the id is the order of first appearance, not the second column
+    (score.py:63-84)."""
+    vocab: Dict[str, int] = {}
+    with open(path, "r", encoding="utf-8") as f:
+        for ln, line in enumerate(f, 1):
+            fields = line.split()
+            if len(fields) != 2:
+                raise ValueError(f"{path}:{ln}: expected 'word index', got {line!r}")
+            vocab.setdefault(fields[0], len(vocab))
+    return vocab
+
+
+def load_nbest(path: str) -> "OrderedDict[str, List[str]]":
+    """``<utt>-<n> words...`` -> {utt: [hyp, ...]} in file order; a line with no words is the
+    empty hypothesis ' ' (score.py:20-51)."""
+    nbest: "OrderedDict[str, List[str]]" = OrderedDict()
+    with open(path, "r", encoding="utf-8") as f:
+        for line in f:
+            line = line.strip()
+            key, sep, hyp = line.partition(" ")
+            if not sep:
+                hyp = " "
+            nbest.setdefault(key.rsplit("-", 1)[0], []).append(hyp)
+    return nbest
+
+
+def ids_for(hyp: str, vocab: Dict[str, int]) -> Tuple[List[int], List[int]]:
+    """input = <s> + words, target = words + <s>, OOV -> <unk> (score.py:87-120)."""
+    bos = vocab["<s>"]
+    unk = vocab.get("<unk>")
+    words = []
+    for w in hyp.split():
+        i = vocab.get(w, unk)
+        if i is None:
+            raise KeyError(f"word {w!r} is out of vocabulary and the vocabulary has no <unk>")
+        words.append(i)
+    return [bos] + words, words + [bos]
+
+
+def write_scores(scores: "OrderedDict[str, List[Tuple[str, float]]]", path: str) -> None:
+    """``<utt>-<idx from 1> %.4f`` (score.py:283-303)."""
+    with open(path, "w", encoding="utf-8") as f:
+        for key, items in scores.items():
+            for idx, (_, s) in enumerate(items, 1):
+                f.write("%s-%d %.4f\n" % (key, idx, s))
+
+
+# ------------------------------------------------------------------------- sharding
+def shard_ranges(weights: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Split items 0..n into ``world`` contiguous ranges with near-equal total weight."""
+    n = len(weights)
+    csum = np.concatenate([[0], np.cumsum(np.asarray(weights, dtype=np.int64))])
+    total = int(csum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        bounds.append(int(np.searchsorted(csum, target, side="left")))
+    bounds.append(n)
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+def _chunks_by_tokens(lengths: Sequence[int], max_tokens: int) -> List[Tuple[int, int]]:
+    out, start, tot = [], 0, 0
+    for i, n in enumerate(lengths):
+        if tot and tot + n > max_tokens:
+            out.append((start, i))
+            start, tot = i, 0
+        tot += n
+    if start < len(lengths):
+        out.append((start, len(lengths)))
+    return out
+
+
+# -------------------------------------------------------------------------- scoring
+class Rescorer:
+    """Scores tokenised n-best lists with one model replica on one GPU."""
+
+    def __init__(self, model, *, prec: str = "bf16", K: int = 0, seed: Optional[int] = None,
+                 max_tokens: int = 65536, eps_list=None):
+        self.model, self.prec, self.K, self.seed, self.max_tokens = model, prec, K, seed, max_tokens
+        self.eps_list = eps_list
+        self.device = next(model.parameters()).device
+        self.is_rnn = model.family.endswith("lstm")
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # hyps: list of (input_ids, target_ids); returns fp32 numpy [n_hyp]
+    def score_transformer(self, hyps: Sequence[Tuple[Sequence[int], Sequence[int]]]) -> np.ndarray:
+        lengths = [len(x) for x, _ in hyps]
+        outs = []
+        for a, b in _chunks_by_tokens(lengths, self.max_tokens):
+            batch = PackedBatch.from_lists([h[0] for h in hyps[a:b]], [h[1] for h in hyps[a:b]], self.device)
+            self.h2d_bytes += batch.h2d_bytes
+            outs.append(self.model.score(batch, K=self.K, seed=self.seed, eps_list=self.eps_list, prec=self.prec))
+        res = torch.cat(outs) if outs else torch.empty(0, device=self.device)
+        host = res.cpu()
+        self.d2h_bytes += host.numel() * 4
+        return host.numpy()
+
+    def score_sessions(self, sessions):
+        """sessions: list of sessions, each a list of utterances, each a list of (input, target)."""
+        return engine.lstm_score_sessions(self, sessions)
+
+
+def score_nbest(model, nbest: "OrderedDict[str, List[str]]", vocab: Dict[str, int], *, prec: str = "bf16",
+                K: int = 0, seed: Optional[int] = None, max_tokens: int = 65536, eps_list=None,
+                session_size: Optional[int] = None, rank: int = 0, world: int = 1, group=None,
+                rescorer: Optional[Rescorer] = None):
+    """Score every hypothesis; returns {utt: [(hyp, score), ...]} in input order (score.py:206-280).
+
+    With ``world > 1`` each rank scores its shard and the full result is assembled on every rank
+    by one all-gather of the fp32 score vector.  ``session_size`` groups consecutive utterances
+    into LSTM sessions (None = the whole list is one session, like one reference JOB).
+    """
+    rs = rescorer or Rescorer(model, prec=prec, K=K, seed=seed, max_tokens=max_tokens, eps_list=eps_list)
+    keys = list(nbest.keys())
+    tokenised = [[ids_for(h, vocab) for h in nbest[k]] for k in keys]
+    counts = [len(u) for u in tokenised]
+    n_total = sum(counts)
+    if rs.is_rnn:
+        size = session_size or len(keys) or 1
+        sessions = [list(range(s, min(s + size, len(keys)))) for s in range(0, len(keys), size)]
+        weights = [sum(sum(len(x) for x, _ in tokenised[u]) for u in sess) for sess in sessions]
+        lo, hi = shard_ranges(weights, world)[rank]
+        mine_utts = [u for sess in sessions[lo:hi] for u in sess]
+        local = rs.score_sessions([[tokenised[u] for u in sess] for sess in sessions[lo:hi]])
+    else:
+        weights = [sum(len(x) for x, _ in u) for u in tokenised]
+        lo, hi = shard_ranges(weights, world)[rank]
+        mine_utts = list(range(lo, hi))
+        local = rs.score_transformer([h for u in mine_utts for h in tokenised[u]])
+    utt_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    if world > 1:
+        import torch.distributed as dist
+        full = torch.zeros(n_total, dtype=torch.float32, device=rs.device if dist.get_backend(group) == "nccl" else "cpu")
+        if len(mine_utts):
+            a, b = int(utt_start[mine_utts[0]]), int(utt_start[mine_utts[-1] + 1])
+            full[a:b] = torch.from_numpy(np.ascontiguousarray(local)).to(full.device)
+        dist.all_reduce(full, group=group)  # disjoint slices: the sum is the gather
+        flat = full.cpu().numpy()
+    else:
+        flat = local
+    out: "OrderedDict[str, List[Tuple[str, float]]]" = OrderedDict()
+    for u, k in enumerate(keys):
+        a = int(utt_start[u])
+        out[k] = [(h, float(flat[a + i])) for i, h in enumerate(nbest[k])]
+    return out
+
+
+# ------------------------------------------------------------------------------ CLI
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="Compute sentence scores of n-best lists with a Bayesian / GP / "
+                                            "Variational neural LM on B200.")
+    p.add_argument("--nbest-list", type=str, required=True)
+    p.add_argument("--outfile", type=str, required=True)
+    p.add_argument("--vocabulary", type=str, required=True)
+    p.add_argument("--model-path", type=str, required=True)
+    p.add_argument("--model", type=str, default="LSTM")
+    p.add_argument("--emsize", type=int, default=1024)
+    p.add_argument("--nhid", type=int, default=1024)
+    p.add_argument("--nlayers", type=int, default=2)
+    p.add_argument("--nhead", type=int, default=8)
+    p.add_argument("--uncertainty", type=str, default="none")
+    p.add_argument("--T_bayes_pos", type=str, default="none")
+    p.add_argument("--L_bayes_pos", type=int, default=0)
+    p.add_argument("--L_gauss_pos", type=str, default="00")
+    p.add_argument("--T_gauss_pos", type=int, default=3)
+    p.add_argument("--L_v_pos", type=str, default="11")
+    p.add_argument("--T_v_pos", type=str, default="0", help="0..3, or the per-layer bit string 00/01/10/11")
+    p.add_argument("--interpolation_flag", type=int, default=0)
+    p.add_argument("--inter_path", type=str, default=None)
+    p.add_argument("--inter_alpha", type=float, default=0.8)
+    # additions (all optional; defaults reproduce the reference's posterior-mean scoring)
+    p.add_argument("--precision", type=str, default="bf16x3", choices=["bf16", "bf16x3"])
+    p.add_argument("--num-samples", type=int, default=0, help="K posterior samples (0 = posterior mean)")
+    p.add_argument("--seed", type=int, default=1111)
+    p.add_argument("--max-tokens", type=int, default=65536)
+    p.add_argument("--session-size", type=int, default=0, help="LSTM: utterances per session (0 = one session)")
+    return p
+
+
+def load_checkpoint(model, path: str) -> None:
+    """Keep the checkpoint keys the model knows, load the rest from the initialisation (score.py:457-462)."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    own = model.state_dict()
+    own.update({k: v for k, v in ckpt.items() if k in own})
+    model.load_state_dict(own)
+
+
+def main(argv=None) -> int:
+    from . import model as models
+    args = build_parser().parse_args(argv)
+    for pth in (args.nbest_list, args.vocabulary, args.model_path):
+        if not os.path.exists(pth):
+            raise FileNotFoundError(pth)
+    if args.interpolation_flag == 1:
+        raise NotImplementedError("logit interpolation (--interpolation_flag 1) is listed as next in SURVEY.md 8f")
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    vocab = read_vocab(args.vocabulary)
+    net = models.build_model(args, len(vocab))
+    load_checkpoint(net, args.model_path)
+    net = net.cuda().eval()
+    nbest = load_nbest(args.nbest_list)
+    res = score_nbest(net, nbest, vocab, prec=args.precision, K=args.num_samples,
+                      seed=args.seed if args.num_samples else None, max_tokens=args.max_tokens,
+                      session_size=args.session_size or None, rank=rank, world=world)
+    if rank == 0:
+        write_scores(res, args.outfile)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

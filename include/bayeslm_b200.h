@@ -80,7 +80,8 @@ int blm_num_sms(void);
  *
  * replaces: F.linear / nn.Linear at model.py:850,855,876,921,1026,1028,1043,
  *           1129,1290,1303,1885 (cuBLAS behind ATen in the reference).
- * needs:    K_s % 8 == 0, N % 8 == 0, lda/ldb % 8 == 0, 16-B aligned pointers.
+ * needs:    K_s % 8 == 0, lda/ldb/ldc % 8 == 0, ldr % 4 == 0, 16-B aligned pointers
+ *           (M and N are arbitrary: ragged edges are masked).
  */
 #define BLM_MAX_SEG 6
 
@@ -143,6 +144,10 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream);
 int blm_segment_sum(const float* x, const int32_t* seg_offsets, int64_t nseg, float* out,
                     blm_stream stream);
 
+/* Monte-Carlo predictive over K posterior samples (the K-sample score the
+ * harness defines):  out[m] = -log( 1/K sum_k exp(-nll[k*M + m]) ). */
+int blm_mc_combine(const float* nll, int64_t K, int64_t M, float* out, blm_stream stream);
+
 /* ------------------------------------------------------------ elementwise */
 /* fp32 -> bf16 hi (+ optional lo = bf16(x - hi)); n elements. */
 int blm_split_bf16(const float* x, blm_bf16* hi, blm_bf16* lo, int64_t n, blm_stream stream);
@@ -189,7 +194,8 @@ int blm_mha_causal(const float* qkv, const int32_t* seq_offsets, int64_t nseq, i
  * (model.py:762-765 without the -1; 1115; 1255; 1821-1825 with it).
  * mu is a [rows, cols] view with leading dimension ldmu, lgstd is dense.
  * `accumulate` adds to out[0] instead of overwriting it.
- * workspace: blm_kl_workspace_bytes() bytes.                                  */
+ * workspace: blm_kl_workspace_bytes() bytes, zero-initialised once by the
+ * caller (the kernel leaves it zeroed again).                                 */
 int64_t blm_kl_workspace_bytes(void);
 int blm_kl_gauss(const float* mu, int64_t ldmu, const float* lgstd, int64_t rows, int64_t cols,
                  int32_t minus_one, float scale, int32_t accumulate, float* out, void* workspace,

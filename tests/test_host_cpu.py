@@ -1,0 +1,148 @@
+"""CPU-side checks: C-ABI surface, state_dict compatibility, host logic, sharding (gloo)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "bayeslm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(blm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bayeslms_b200 import _lib
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/bayeslm_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and header disagree"
+    assert _lib.lib().blm_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Product ops refuse CPU tensors instead of silently computing on the host."""
+    from bayeslms_b200 import _lib, model as M
+    net = M.BayesTransformerModel(50, 32, 4, 64, 2, 0.5, True, "FFN")
+    with pytest.raises(_lib.BlmError):
+        net(torch.zeros(4, 1, dtype=torch.long))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bayeslms_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+@pytest.mark.parametrize("name", ["bayes_tm_FFN", "bayes_tm_MHA", "bayes_tm_EMB", "bayes_tm_none", "gauss_tm_0",
+                                  "gauss_tm_3", "v_tm_0", "v_tm_1", "v_tm_2", "v_tm_3", "bayes_lstm_0",
+                                  "bayes_lstm_3"])
+def test_state_dict_layout_matches_reference(golden, name):
+    from tests.util import build_from_cfg
+    rec = golden(name + ".pt")
+    net = build_from_cfg(rec["cfg"])
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in rec["state_dict"].items()}
+    if "pos_encoder.pe" in mine:
+        assert mine.pop("pos_encoder.pe")[1:] == (1, rec["cfg"]["ninp"])
+    assert mine == ref
+    net.load_state_dict(rec["state_dict"], strict=False)
+
+
+def test_v_pos_normalisation():
+    from bayeslms_b200.model import normalise_v_pos, VTransformerModel
+    assert [normalise_v_pos(v) for v in (0, 1, 2, 3, "00", "01", "10", "11", 11, "3")] == [0, 1, 2, 3, 0, 1, 2, 3, 3, 3]
+    with pytest.raises(ValueError):
+        normalise_v_pos(7)
+    assert len(VTransformerModel(20, 16, 2, 32, 6, 0.5, True, "11").transformerlayers) == 5
+
+
+def test_host_parsers_match_oracle(golden, tmp_path):
+    from bayeslms_b200 import scorer as S
+    from oracle import bayeslm_oracle as O
+    rec = golden("scorer_loop.pt")
+    vp, npth = tmp_path / "words.txt", tmp_path / "words_text"
+    vp.write_text("".join(f"{w} {i}\n" for i, w in enumerate(rec["vocab_words"])) + "w000 999\n")
+    npth.write_text("\n".join(rec["nbest_lines"]) + "\n")
+    assert S.read_vocab(str(vp)) == O.read_vocab(str(vp))
+    a, b = S.load_nbest(str(npth)), O.load_nbest(str(npth))
+    assert list(a.items()) == list(b.items())
+    vocab = S.read_vocab(str(vp))
+    for hyps in a.values():
+        for h in hyps:
+            assert S.ids_for(h, vocab) == O.get_input_and_target(h, vocab)
+    scores = {k: [(h, 1.23456 + i) for i, h in enumerate(v)] for k, v in a.items()}
+    S.write_scores(scores, str(tmp_path / "a.nn"))
+    O.write_scores(scores, str(tmp_path / "b.nn"))
+    assert (tmp_path / "a.nn").read_text() == (tmp_path / "b.nn").read_text()
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.txt").write_text("only-one-column\n")
+        S.read_vocab(str(tmp_path / "bad.txt"))
+
+
+def test_shard_ranges_cover_and_balance():
+    from bayeslms_b200.scorer import shard_ranges
+    w = list(np.random.RandomState(0).randint(1, 50, size=103))
+    for world in (1, 2, 3, 8):
+        r = shard_ranges(w, world)
+        assert r[0][0] == 0 and r[-1][1] == len(w)
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        loads = [sum(w[a:b]) for a, b in r]
+        assert max(loads) - min(loads) <= 2 * max(w)
+    assert shard_ranges([], 2) == [(0, 0), (0, 0)]
+    assert shard_ranges([5], 4)[-1][1] == 1
+
+
+def test_packed_batch_layout():
+    from bayeslms_b200.engine import PackedBatch
+    b = PackedBatch.from_lists([[0, 5, 6], [0], [0, 9]], [[5, 6, 0], [0], [9, 0]], "cpu")
+    assert b.tokens.tolist() == [0, 5, 6, 0, 0, 9] and b.targets.tolist() == [5, 6, 0, 0, 9, 0]
+    assert b.pos.tolist() == [0, 1, 2, 0, 0, 1] and b.offsets.tolist() == [0, 3, 4, 6]
+    assert (b.max_len, b.n_tokens, b.n_hyp) == (3, 6, 3)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from collections import OrderedDict
+    from bayeslms_b200 import scorer as S
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeRescorer:  # host-side sharding logic only: the "score" is a function of the token ids
+        is_rnn, device = False, torch.device("cpu")
+
+        def score_transformer(self, hyps):
+            return np.asarray([float(sum(x) * 0.5 + len(y)) for x, y in hyps], dtype=np.float32)
+
+    vocab = {"<s>": 0, "<unk>": 1, **{f"w{i}": i + 2 for i in range(30)}}
+    rs = np.random.RandomState(3)
+    nbest = OrderedDict((f"utt{u}", [" ".join(f"w{rs.randint(30)}" for _ in range(rs.randint(0, 7))) or " "
+                                     for _ in range(rs.randint(1, 5))]) for u in range(17))
+    res = S.score_nbest(None, nbest, vocab, rank=rank, world=world, rescorer=FakeRescorer())
+    single = S.score_nbest(None, nbest, vocab, rank=0, world=1, rescorer=FakeRescorer())
+    q.put((rank, res == single))
+    dist.destroy_process_group()
+
+
+def test_sharded_scoring_equals_single_rank_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert got == [(0, True), (1, True)]
