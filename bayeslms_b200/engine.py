@@ -192,27 +192,28 @@ class _TmRun:
         d = self.d
         qkv = self.f32(3 * d)
         ops.gemm(xs, L["qkv"], prec=self.prec, bias=L["qkv_b"], col_scale=float(d // self.nhead) ** -0.5,
-                 col_scale_cols=d, out_f32=qkv)
+                 col_scale_cols=d, out_f32=qkv, tag="qkv")
         _, att = ops.mha_causal(qkv, self.b.offsets, self.nhead, self.b.max_len, prec=self.prec)
         return att
 
     # part B: output projection + residual, LayerNorm 1
     def part_b(self, L, x32, att: Split, w_o: Split):
         y = self.f32(self.d)
-        ops.gemm(att, w_o, prec=self.prec, bias=L["o_b"], resid=x32, out_f32=y)
+        ops.gemm(att, w_o, prec=self.prec, bias=L["o_b"], resid=x32, out_f32=y, tag="o_net")
         g, b, eps = L["norm1"]
         return ops.layernorm(y, g, b, eps, prec=self.prec)
 
     # part C: first FFN projection with the activation fused (GELU, or the GP mixture)
     def part_c(self, L, x1s: Split, w1: Split, b1, coef) -> Split:
         h = ops.empty_split(self.M, w1.hi.shape[0], self.prec, self.dev)
-        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=ACT_GPMIX if coef is not None else ACT_GELU, coef=coef, out=h)
+        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=ACT_GPMIX if coef is not None else ACT_GELU, coef=coef, out=h,
+                 tag="ffn1")
         return h
 
     # part D: second FFN projection + residual, LayerNorm 2
     def part_d(self, L, x1_32, h: Split, w2: Split):
         y = self.f32(self.d)
-        ops.gemm(h, w2, prec=self.prec, bias=L["b2"], resid=x1_32, out_f32=y)
+        ops.gemm(h, w2, prec=self.prec, bias=L["b2"], resid=x1_32, out_f32=y, tag="ffn2")
         g, b, eps = L["norm2"]
         return ops.layernorm(y, g, b, eps, prec=self.prec)
 

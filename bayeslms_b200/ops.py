@@ -22,6 +22,35 @@ from ._lib import (ACT_GELU, ACT_GPMIX, ACT_NONE, EPS_NONE, EPS_PHILOX, EPS_PTR,
 PRECISIONS = ("bf16", "bf16x3")
 
 
+class _Stats:
+    """Launch accounting for bench.py: how many of OUR kernels were launched, and (when
+    ``timing`` is a dict) CUDA-event brackets around every launch on the launching stream."""
+    launches = 0
+    timing = None   # None, or {op name: [(start_event, end_event, work), ...]}
+
+
+STATS = _Stats()
+
+
+class _op:
+    def __init__(self, name: str, kernels: int = 1, work: float = 0.0):
+        self.name, self.kernels, self.work = name, kernels, work
+
+    def __enter__(self):
+        STATS.launches += self.kernels
+        if STATS.timing is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STATS.timing is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            STATS.timing.setdefault(self.name, []).append((self.e0, e1, self.work))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -62,7 +91,8 @@ def split(x: torch.Tensor, prec: str = "bf16x3") -> Split:
     _require_cuda(x)
     x = x.detach().contiguous().float()
     out = empty_split(x.shape[0] if x.dim() == 2 else 1, x.shape[-1] if x.dim() == 2 else x.numel(), prec, x.device)
-    check(lib().blm_split_bf16(_ptr(x), _ptr(out.hi), _ptr(out.lo), x.numel(), _stream()), "blm_split_bf16")
+    with _op("split_bf16", 1):
+        check(lib().blm_split_bf16(_ptr(x), _ptr(out.hi), _ptr(out.lo), x.numel(), _stream()), "blm_split_bf16")
     if x.dim() != 2:
         out = Split(out.hi.view(x.shape), None if out.lo is None else out.lo.view(x.shape))
     return out
@@ -81,7 +111,7 @@ def _segments(a: Split, b: Split, prec: str):
 def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          coef: Optional[torch.Tensor] = None, col_scale: float = 1.0, col_scale_cols: int = 0,
          resid: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
-         out: Optional[Split] = None, extra: Sequence = ()):
+         out: Optional[Split] = None, extra: Sequence = (), tag: str = ""):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
     accumulated into the same output (K-concatenation)."""
     segs = _segments(a, b, prec)
@@ -110,7 +140,8 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     d.out_hi = _ptr(None if out is None else out.hi)
     d.out_lo = _ptr(None if out is None else out.lo)
     d.ldc = ldc if ldc is not None else N
-    check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
+    with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[1] for x, _ in segs)):
+        check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
 
 
 _nll_ws = {}
@@ -141,7 +172,8 @@ def vocab_nll(h: Split, e: Split, bias: Optional[torch.Tensor], targets: torch.T
         d.K[i], d.ldh[i], d.lde[i] = x.shape[1], x.stride(0), w.stride(0)
     d.bias, d.targets, d.nll = _ptr(bias), _ptr(targets), _ptr(out)
     d.workspace, d.workspace_bytes = _ptr(ws), ws.numel()
-    check(lib().blm_vocab_nll(C.byref(d), _stream()), "blm_vocab_nll")
+    with _op("vocab_nll", 2, 2.0 * M * V * sum(x.shape[1] for x, _ in segs)):
+        check(lib().blm_vocab_nll(C.byref(d), _stream()), "blm_vocab_nll")
     return out
 
 
@@ -150,7 +182,8 @@ def segment_sum(x: torch.Tensor, offsets: torch.Tensor, out: Optional[torch.Tens
     if out is None:
         out = torch.empty(n, dtype=torch.float32, device=x.device)
     assert offsets.dtype == torch.int32
-    check(lib().blm_segment_sum(_ptr(x), _ptr(offsets), n, _ptr(out), _stream()), "blm_segment_sum")
+    with _op("segment_sum", 1):
+        check(lib().blm_segment_sum(_ptr(x), _ptr(offsets), n, _ptr(out), _stream()), "blm_segment_sum")
     return out
 
 
@@ -160,7 +193,8 @@ def mc_combine(nll_km: torch.Tensor, out: Optional[torch.Tensor] = None) -> torc
     assert nll_km.is_contiguous() and nll_km.dtype == torch.float32
     if out is None:
         out = torch.empty(M, dtype=torch.float32, device=nll_km.device)
-    check(lib().blm_mc_combine(_ptr(nll_km), K, M, _ptr(out), _stream()), "blm_mc_combine")
+    with _op("mc_combine", 1):
+        check(lib().blm_mc_combine(_ptr(nll_km), K, M, _ptr(out), _stream()), "blm_mc_combine")
     return out
 
 
@@ -171,8 +205,9 @@ def embed(tokens: torch.Tensor, pos: Optional[torch.Tensor], emb: torch.Tensor, 
     dev = emb.device
     x = torch.empty(M, d, dtype=torch.float32, device=dev) if want_f32 else None
     s = empty_split(M, d, prec, dev)
-    check(lib().blm_embed(_ptr(tokens), _ptr(pos), _ptr(emb), _ptr(pe), scale, M, d, _ptr(x), _ptr(s.hi),
-                          _ptr(s.lo), _stream()), "blm_embed")
+    with _op("embed", 1):
+        check(lib().blm_embed(_ptr(tokens), _ptr(pos), _ptr(emb), _ptr(pe), scale, M, d, _ptr(x), _ptr(s.hi),
+                              _ptr(s.lo), _stream()), "blm_embed")
     return x, s
 
 
@@ -181,8 +216,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     M, d = x.shape
     y = torch.empty_like(x) if want_f32 else None
     s = empty_split(M, d, prec, x.device)
-    check(lib().blm_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), eps, M, d, _ptr(y), _ptr(s.hi), _ptr(s.lo),
-                              _stream()), "blm_layernorm")
+    with _op("layernorm", 1):
+        check(lib().blm_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), eps, M, d, _ptr(y), _ptr(s.hi), _ptr(s.lo),
+                                  _stream()), "blm_layernorm")
     return y, s
 
 
@@ -204,14 +240,16 @@ def reparam(mu: torch.Tensor, lgstd: Optional[torch.Tensor], *, eps: Optional[to
         lgstd = lgstd.contiguous()
     if eps is not None:
         eps = eps.contiguous().float()
-    check(lib().blm_reparam(_ptr(mu), mu.stride(0), _ptr(lgstd), _ptr(eps), mode, int(seed or 0), int(stream_id),
-                            rows, cols, _ptr(w), _ptr(s.hi), _ptr(s.lo), _stream()), "blm_reparam")
+    with _op("reparam", 1):
+        check(lib().blm_reparam(_ptr(mu), mu.stride(0), _ptr(lgstd), _ptr(eps), mode, int(seed or 0), int(stream_id),
+                                rows, cols, _ptr(w), _ptr(s.hi), _ptr(s.lo), _stream()), "blm_reparam")
     return w, s
 
 
 def philox_normal(seed: int, stream_id: int, n: int, device) -> torch.Tensor:
     out = torch.empty(n, dtype=torch.float32, device=device)
-    check(lib().blm_philox_normal(int(seed), int(stream_id), n, _ptr(out), _stream()), "blm_philox_normal")
+    with _op("philox_normal", 1):
+        check(lib().blm_philox_normal(int(seed), int(stream_id), n, _ptr(out), _stream()), "blm_philox_normal")
     return out
 
 
@@ -222,8 +260,9 @@ def mha_causal(qkv: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len
     nseq = seq_offsets.numel() - 1
     o = torch.empty(M, d, dtype=torch.float32, device=qkv.device) if want_f32 else None
     s = empty_split(M, d, prec, qkv.device)
-    check(lib().blm_mha_causal(_ptr(qkv), _ptr(seq_offsets), nseq, nhead, d // nhead, max_len, _ptr(o), _ptr(s.hi),
-                               _ptr(s.lo), _stream()), "blm_mha_causal")
+    with _op("mha_causal", 1):
+        check(lib().blm_mha_causal(_ptr(qkv), _ptr(seq_offsets), nseq, nhead, d // nhead, max_len, _ptr(o), _ptr(s.hi),
+                                   _ptr(s.lo), _stream()), "blm_mha_causal")
     return o, s
 
 
@@ -242,6 +281,7 @@ def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_
     if ws is None:
         ws = torch.zeros(lib().blm_kl_workspace_bytes(), dtype=torch.uint8, device=mu.device)
         _kl_ws[key] = ws
-    check(lib().blm_kl_gauss(_ptr(mu), mu.stride(0), _ptr(lgstd), rows, cols, int(minus_one), scale,
-                             int(accumulate), _ptr(out), _ptr(ws), _stream()), "blm_kl_gauss")
+    with _op("kl_gauss", 1, 4.0 * 2 * rows * cols):
+        check(lib().blm_kl_gauss(_ptr(mu), mu.stride(0), _ptr(lgstd), rows, cols, int(minus_one), scale,
+                                 int(accumulate), _ptr(out), _ptr(ws), _stream()), "blm_kl_gauss")
     return out

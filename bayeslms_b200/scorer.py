@@ -120,6 +120,8 @@ class Rescorer:
         self.is_rnn = model.family.endswith("lstm")
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._stage = None   # pinned int32 staging for ids (grown on demand, reused across calls)
+        self._out = None     # pinned fp32 landing buffer for the scores
 
     # hyps: list of (input_ids, target_ids); returns fp32 numpy [n_hyp]
     def score_transformer(self, hyps: Sequence[Tuple[Sequence[int], Sequence[int]]]) -> np.ndarray:
@@ -133,6 +135,38 @@ class Rescorer:
         host = res.cpu()
         self.d2h_bytes += host.numel() * 4
         return host.numpy()
+
+    def score_packed_host(self, tokens: np.ndarray, targets: np.ndarray, pos: np.ndarray,
+                          offsets: np.ndarray) -> np.ndarray:
+        """Flat host arrays in, host scores out -- the plain-pointer form of the scoring call
+        (int32 ids [M], int32 offsets [n_hyp + 1]).  Hypotheses are cut into batches of at most
+        ``max_tokens`` tokens; each batch is one pinned H2D copy, and all scores return in one D2H."""
+        n_hyp = len(offsets) - 1
+        lengths = np.diff(offsets)
+        chunks = _chunks_by_tokens(lengths.tolist(), self.max_tokens)
+        need = 3 * int(offsets[-1]) + n_hyp + len(chunks)
+        if self._stage is None or self._stage.numel() < need:
+            self._stage = torch.empty(max(need, 1 << 16), dtype=torch.int32, pin_memory=True)
+        stage, at = self._stage.numpy(), 0
+        outs = []
+        for a, b in chunks:
+            t0, t1 = int(offsets[a]), int(offsets[b])
+            M, n = t1 - t0, 3 * (t1 - t0) + (b - a + 1)
+            buf = stage[at:at + n]
+            buf[:M], buf[M:2 * M], buf[2 * M:3 * M] = tokens[t0:t1], targets[t0:t1], pos[t0:t1]
+            buf[3 * M:] = offsets[a:b + 1] - offsets[a]
+            dev = self._stage[at:at + n].to(self.device, non_blocking=True)
+            at += n
+            batch = PackedBatch(dev[:M], dev[M:2 * M], dev[2 * M:3 * M], dev[3 * M:], int(lengths[a:b].max()), M, b - a)
+            self.h2d_bytes += batch.h2d_bytes
+            outs.append(self.model.score(batch, K=self.K, seed=self.seed, eps_list=self.eps_list, prec=self.prec))
+        res = torch.cat(outs) if outs else torch.empty(0, device=self.device)
+        if self._out is None or self._out.numel() < n_hyp:
+            self._out = torch.empty(max(n_hyp, 1 << 12), dtype=torch.float32, pin_memory=True)
+        self._out[:n_hyp].copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # scores are on the host; staging buffers reusable
+        self.d2h_bytes += n_hyp * 4
+        return self._out[:n_hyp].numpy().copy()
 
     def score_sessions(self, sessions):
         """sessions: list of sessions, each a list of utterances, each a list of (input, target)."""

@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: n-best rescoring tokens/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload at N=1 (BASELINE.json configs[1]): Bayesian Transformer LM, 6 layers, d=512, FFN=4096,
+8 heads, V=30000, T_bayes_pos=FFN, 50-best lists, random-init weights of that architecture,
+synthetic n-best lists (bayeslms_b200/synth.py).  One *step* scores UTTS_PER_STEP utterances x
+50 hypotheses (~0.2 M scored positions) in packed batches of <= 65536 tokens; with N ranks every
+rank scores its own UTTS_PER_STEP utterances (weak scaling, no data-path collective; one score
+gather per step).  Reported:
+
+  value        tokens/s, posterior mean, bf16 operands / fp32 accumulate, ids already in HBM
+  e2e          same through Rescorer.score_packed_host: pinned host ids -> device, scores -> host
+  sampled_k4   K=4 Philox posterior samples (Monte-Carlo predictive), device-resident
+  precise      bf16x3 (hi/lo split) mode that holds the 1e-3 parity bar
+  roofline     the vocabulary-streaming projection+NLL kernel, 2*M*d*V FLOP per launch over the
+               CUDA-event time of its launches, against MEASURED_PEAKS.json (sustained bf16)
+  cpu_baseline the CPU oracle port (reference algorithm, torch CPU fp32, batch 1 per hypothesis)
+               on a bounded sample of the same lists, rank 0, N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, D, NHEAD, FF, NLAYERS, NBEST = 30000, 512, 8, 4096, 6, 50
+UTTS_PER_STEP = 256
+MAX_TOKENS = 65536
+WORKLOAD = "Bayesian Transformer LM 6L d512 FFN4096 h8 V30000 T_bayes_pos=FFN, 50-best rescoring"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tensor": p.get("bf16_tflops_sustained", 1397.3), "tensor_burst": p.get("bf16_tflops", 1663.3),
+                "hbm": p.get("hbm_gbs", 6550.4), "src": "measured"}
+    return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(device):
+    from bayeslms_b200 import model as M
+    torch.manual_seed(1111)
+    net = M.BayesTransformerModel(V, D, NHEAD, FF, NLAYERS, 0.5, True, "FFN")
+    with torch.no_grad():
+        net.decoder.bias.uniform_(-0.1, 0.1)   # exercise the bias term
+    return net.to(device).eval()
+
+
+def cpu_port_tokens_per_s(data, n_utts, state_dict):
+    """The reference algorithm on the host: one hypothesis at a time, batch 1, fp32 torch CPU."""
+    from oracle import bayeslm_oracle as O
+    cfg = O.Config(family="bayes_tm", bayes_pos="FFN", ntoken=V, ninp=D, nhead=NHEAD, nhid=FF, nlayers=NLAYERS)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    toks = 0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for utt in data.tokenised(0, n_utts):
+            for x, y in utt:
+                lg = O.transformer_forward(state_dict, torch.tensor(x).view(-1, 1), cfg)
+                O.sentence_nll(lg, torch.tensor(y))
+                toks += len(x)
+    dt = time.perf_counter() - t0
+    return toks / dt, toks, dt, cores
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
+    reference cannot travel to the GPU box), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from bayeslms_b200 import synth
+    from bayeslms_b200 import model as M   # parameter container only: same random-init weights, no GPU
+    torch.manual_seed(1111)
+    net = M.BayesTransformerModel(V, D, NHEAD, FF, NLAYERS, 0.5, True, "FFN")
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    n_utts = 2  # ~1.6 k tokens, a few seconds per step on 8+ cores
+    data = synth.make_nbest(n_utts, NBEST, V, seed=1111)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_port_tokens_per_s(data, 1, sd)
+    vals, tok = [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, tok, _, cores = cpu_port_tokens_per_s(data, n_utts, sd)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = tok * args.steps / dt
+    sample = f"{n_utts} utterances x {NBEST}-best ({tok} tokens) per step, batch 1 per hypothesis"
+    print(json.dumps({
+        "impl": "reference", "metric": "nbest_rescoring_tokens_per_sec", "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts-per-step", type=int, default=UTTS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch.distributed as dist
+    from bayeslms_b200 import _lib, ops, synth
+    from bayeslms_b200.engine import PackedBatch
+    from bayeslms_b200.scorer import Rescorer, _chunks_by_tokens
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.init(local_rank)
+    warmup = max(args.warmup, 3)
+    net = build_model(dev)
+    # every rank scores its own utterances of one global synthetic set (weak scaling)
+    data = synth.make_nbest(args.utts_per_step * world, NBEST, V, seed=1111)
+    lo, hi = rank * args.utts_per_step, (rank + 1) * args.utts_per_step
+    tok, tgt, pos, offs = data.flat_host(lo, hi)
+    n_tokens, n_hyp = int(offs[-1]), len(offs) - 1
+    lengths = np.diff(offs)
+    chunks = _chunks_by_tokens(lengths.tolist(), MAX_TOKENS)
+
+    def device_batches():
+        out = []
+        for a, b in chunks:
+            t0, t1 = int(offs[a]), int(offs[b])
+            mk = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+            out.append(PackedBatch(mk(tok[t0:t1]), mk(tgt[t0:t1]), mk(pos[t0:t1]), mk(offs[a:b + 1] - offs[a]),
+                                   int(lengths[a:b].max()), t1 - t0, b - a))
+        return out
+
+    batches = device_batches()
+    gather_buf = torch.zeros(world * n_hyp, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(prec="bf16", K=0, seed=None):
+        outs = [net.score(b, prec=prec, K=K, seed=seed) for b in batches]
+        res = torch.cat(outs)
+        if world > 1:  # the one collective of the path: gather the score vector
+            dist.all_gather_into_tensor(gather_buf, res)
+        return res
+
+    def timed(fn, steps, sync_each=False):
+        """max-over-ranks device time of `steps` calls (CUDA events on the launching stream)."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(warmup):
+        step()
+    # ---- timed region: posterior mean, bf16, ids resident in HBM
+    ops.STATS.launches = 0
+    ops.STATS.timing = {}
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step, args.steps)
+    launches = ops.STATS.launches
+    timing, ops.STATS.timing = ops.STATS.timing, None
+    value = n_tokens * world * args.steps / (ms / 1e3)
+
+    # per-kernel shares from the event brackets recorded inside the timed region
+    shares, nll_ms, nll_flops, nll_n = {}, 0.0, 0.0, 0
+    for name, evs in timing.items():
+        t = sum(a.elapsed_time(b) for a, b, _ in evs)
+        shares[name] = t
+        if name == "vocab_nll":
+            nll_ms, nll_flops, nll_n = t, sum(w for _, _, w in evs), len(evs)
+    tot = sum(shares.values()) or 1.0
+    pk = peaks()
+    achieved = (nll_flops / nll_n) / (nll_ms / nll_n / 1e3) / 1e12 if nll_n else 0.0
+
+    # ---- e2e: host ids -> pinned staging -> device -> scores back on the host, every step
+    rs = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS)
+    for _ in range(2):
+        rs.score_packed_host(tok, tgt, pos, offs)
+    rs.h2d_bytes = rs.d2h_bytes = 0
+
+    def e2e_step():
+        res = rs.score_packed_host(tok, tgt, pos, offs)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, torch.from_numpy(res).to(dev))
+
+    e2e_ms = timed(e2e_step, args.steps)
+    e2e_val = n_tokens * world * args.steps / (e2e_ms / 1e3)
+    h2d, d2h = rs.h2d_bytes // args.steps, rs.d2h_bytes // args.steps
+
+    # ---- K = 4 sampled and precise-mode numbers (same lists)
+    k4_steps = max(1, args.steps // 2)
+    step(K=4, seed=1111)
+    k4_ms = timed(lambda: step(K=4, seed=1111), k4_steps)
+    step(prec="bf16x3")
+    px_ms = timed(lambda: step(prec="bf16x3"), k4_steps)
+
+    # ---- fast-vs-precise agreement on this step's lists (ranking evidence)
+    fast = step().float().cpu().numpy()
+    precise = step(prec="bf16x3").float().cpu().numpy()
+    per_utt = lambda s: [s[i * NBEST:(i + 1) * NBEST] for i in range(args.utts_per_step)]  # noqa: E731
+    _, picks_f = synth.wer(data, per_utt(fast), lo=lo)
+    wer_p, picks_p = synth.wer(data, per_utt(precise), lo=lo)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        n_cpu = 8
+        v_cpu, t_cpu, dt_cpu, cores = cpu_port_tokens_per_s(data, n_cpu, sd)
+        cpu = {"value": v_cpu, "unit": "tokens/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_cpu} utterances x {NBEST}-best of the same lists ({t_cpu} tokens, {dt_cpu:.1f} s), "
+                         "oracle port of the reference loop: batch 1 per hypothesis, torch CPU fp32"}
+
+    if rank == 0:
+        line = {
+            "metric": "nbest_rescoring_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "posterior": "mean", "utterances_per_step_per_gpu": args.utts_per_step,
+                       "tokens_per_step_per_gpu": n_tokens, "max_tokens_per_batch": MAX_TOKENS,
+                       "parallelism": f"n-best sharded over {world} rank(s), replicated weights, one score gather",
+                       "l2": "activations per batch (>= 0.5 GB) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+            "roofline": {"kernel": "gemm_kernel<256,4,EPI_NLL> (vocab projection + online LSE + target gather)",
+                         "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tensor"] if pk["tensor"] else None, "traffic": None,
+                         "peak_source": pk["src"] + " bf16_tflops_sustained", "launches": nll_n,
+                         "avg_launch_ms": nll_ms / nll_n if nll_n else None,
+                         "share_of_step": nll_ms / tot},
+            "kernel_time_shares": {k: round(v / tot, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
+            "sampled_k4": {"value": n_tokens * world * k4_steps / (k4_ms / 1e3), "unit": "tokens/s", "K": 4,
+                           "noise": "Philox4x32-10 on device"},
+            "precise": {"value": n_tokens * world * k4_steps / (px_ms / 1e3), "unit": "tokens/s", "dtype": "bf16x3",
+                        "max_abs_score_diff_vs_bf16": float(np.abs(fast - precise).max()),
+                        "one_best_agreement": float(np.mean(np.asarray(picks_f) == np.asarray(picks_p))),
+                        "synthetic_wer": wer_p},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
