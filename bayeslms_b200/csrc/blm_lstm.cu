@@ -1,10 +1,364 @@
-// placeholder until the persistent recurrence kernel lands (next commit)
+// Persistent LSTM recurrence for sm_100a  (SURVEY.md 8 row a6 / north_star (b)).
+//
+// One cooperative launch runs all T steps of one layer for a batch of B sequences advanced in
+// lock step.  CTA j owns hidden units [8j, 8j+8): its 32 rows of W_hh (4 gates x 8 units, bf16
+// hi [+ lo]) are TMA-loaded ONCE into 128B-swizzled shared memory and stay resident for every
+// timestep -- HBM never sees W_hh again.  Per step each CTA
+//   * streams h_{t-1} [B, H] (bf16 hi [+ lo], double-buffered in global, L2 resident) through a
+//     TMA ring and issues tcgen05.mma  D[128 x 32] += h_tile[128 x 64] . W_slice[32 x 64]^T into
+//     one 32-column TMEM accumulator per 128-row batch tile;
+//   * epilogue warps read the accumulator (one batch row per thread), add the hoisted input
+//     projection gates_x[t], apply the four gate nonlinearities (i, f, o = sigmoid, g = tanh),
+//     update c and h for their 8 units, and publish h_t (fp32 state, layer output, bf16 operand
+//     for the next step);
+//   * a grid-wide barrier (one atomic per CTA, bounded spin) separates the steps.
+// Rows past their own length (right padding) keep (h, c) untouched, so the final state is the
+// state after each row's last valid token (the hidden carry of score.py:271-274).
+#include <string.h>
+
 #include "blm_host.h"
-namespace blm { int lstm_init() { return BLM_OK; } }
-extern "C" int64_t blm_lstm_workspace_bytes(int64_t, int64_t) { return 64; }
-extern "C" int blm_lstm_layer(const float*, const blm_bf16*, const blm_bf16*, const float*, const float*,
-                              const int32_t*, int64_t, int64_t, int64_t, float*, blm_bf16*, blm_bf16*, float*,
-                              float*, void*, blm_stream) {
-  blm::set_error("blm_lstm_layer: not built yet");
-  return BLM_ERR_ARG;
+#include "blm_ptx.cuh"
+
+namespace blm {
+
+constexpr int kU = 8;            // hidden units per CTA
+constexpr int kLN = 4 * kU;      // MMA N: 4 gates x 8 units
+constexpr int kLStages = 5;      // h-tile ring depth
+constexpr int kLThreads = 256;
+constexpr int kLMaxTiles = 16;   // 16 x 32 TMEM columns = 512
+constexpr int kLABytes = 128 * 64 * 2;
+constexpr int kLWTile = kLN * 64 * 2;  // one K block of the W slice: 4096 B
+
+struct LstmParams {
+  CUtensorMap tmH[2][2];  // [buffer][hi, lo] : h state [B, H] bf16, box 128 x 64
+  CUtensorMap tmW[2];     // [hi, lo]         : W_hh [4H, H] bf16, box 8 x 64
+  const float* gates_x;   // [T, B, 4H]
+  const float* h0;
+  const float* c0;
+  const int* lengths;
+  int T, B, H;
+  int nsplit;             // 1: bf16, 3: hi*hi + hi*lo + lo*hi
+  int kblocks, m_tiles;
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* hT;
+  float* cT;
+  __nv_bfloat16* hbuf[2][2];
+  unsigned int* barrier;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+
+// all CTAs of the (cooperative, co-resident) grid arrive; bounded spin like mbar_wait
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    unsigned int polls = 0;
+    while (ld_acquire_u32(ctr) < target) {
+      if (((++polls) & 0xfffu) == 0u && (clock64() - t0) > 8000000000LL) {
+        printf("blm: LSTM grid barrier timed out (block %d target %u)\n", (int)blockIdx.x, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void store_h8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&h)[8]) {
+  uint32_t a[4], b[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat16 x = __float2bfloat16_rn(h[2 * q]), y = __float2bfloat16_rn(h[2 * q + 1]);
+    a[q] = static_cast<uint32_t>(__bfloat16_as_ushort(x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(y)) << 16);
+    b[q] = pack_bf16x2(h[2 * q] - __bfloat162float(x), h[2 * q + 1] - __bfloat162float(y));
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(a[0], a[1], a[2], a[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(b[0], b[1], b[2], b[3]);
+}
+
+__global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_constant__ LstmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
+  const int w_bytes = p.kblocks * kLWTile;
+  uint8_t* sW[2] = {smem, smem + w_bytes};
+  uint8_t* sA = smem + (p.nsplit == 3 ? 2 : 1) * w_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kLStages * kLABytes);
+  uint64_t* empty_bar = full_bar + kLStages;
+  uint64_t* tfull_bar = empty_bar + kLStages;  // [kLMaxTiles]
+  uint64_t* w_bar = tfull_bar + kLMaxTiles;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x;  // unit block
+  const int H = p.H, B = p.B;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kLStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kLMaxTiles; ++s) mbar_init(&tfull_bar[s], 1);
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // resident W slice: rows {g*H + 8j + u}, one 8-row TMA box per (gate, K block) = one swizzle atom
+  if (warp == 0 && lane == 0) {
+    const int parts = p.nsplit == 3 ? 2 : 1;
+    mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(parts * w_bytes));
+    for (int part = 0; part < parts; ++part)
+      for (int kb = 0; kb < p.kblocks; ++kb)
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(sW[part] + kb * kLWTile + g * 1024, &p.tmW[part], w_bar, kb * 64, g * H + j * kU,
+                      kEvictFirst);
+  }
+
+  // prologue: publish h_{-1} = h0 as the bf16 operand and seed the running (h, c) state, own columns
+  for (int b = threadIdx.x; b < B; b += kLThreads) {
+    const long long o = static_cast<long long>(b) * H + j * kU;
+    float h[8], c[8];
+    *reinterpret_cast<float4*>(h) = __ldg(reinterpret_cast<const float4*>(p.h0 + o));
+    *reinterpret_cast<float4*>(h + 4) = __ldg(reinterpret_cast<const float4*>(p.h0 + o + 4));
+    *reinterpret_cast<float4*>(c) = __ldg(reinterpret_cast<const float4*>(p.c0 + o));
+    *reinterpret_cast<float4*>(c + 4) = __ldg(reinterpret_cast<const float4*>(p.c0 + o + 4));
+    *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
+    *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
+    *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
+    *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
+    store_h8(p.hbuf[0][0] + o, p.nsplit == 3 ? p.hbuf[0][1] + o : nullptr, h);
+  }
+  fence_proxy_async_all();
+  unsigned int bar_n = 0;
+  grid_barrier(p.barrier, (++bar_n) * gridDim.x);
+  mbar_wait(w_bar, 0);
+
+  int stage = 0;
+  uint32_t phase = 0;  // ring position, advanced identically by producer and MMA threads
+  const int a_parts = p.nsplit == 3 ? 2 : 1;
+
+  for (int t = 0; t < p.T; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();  // h_{t-1} was written with generic stores by other SMs
+        for (int mt = 0; mt < p.m_tiles; ++mt)
+          for (int part = 0; part < a_parts; ++part)
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[stage], kLABytes);
+              tma_load_2d(sA + stage * kLABytes, &p.tmH[cur][part], &full_bar[stage], kb * 64, mt * 128,
+                          kEvictNormal);
+              if (++stage == kLStages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, kLN);
+        tcgen05_fence_after();
+        for (int mt = 0; mt < p.m_tiles; ++mt) {
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kLN);
+          uint32_t accum = 0;
+          for (int part = 0; part < a_parts; ++part)
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kLABytes));
+              const uint64_t dw_hi = umma_desc_sw128(smem_u32(sW[0] + kb * kLWTile));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_hi + static_cast<uint64_t>(2 * k), idesc, accum);
+                accum = 1;
+              }
+              if (part == 0 && p.nsplit == 3) {  // h_hi . W_lo
+                const uint64_t dw_lo = umma_desc_sw128(smem_u32(sW[1] + kb * kLWTile));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == kLStages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          umma_commit(&tfull_bar[mt]);
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 4) {
+      const int lane_grp = warp & 3;
+      for (int mt = 0; mt < p.m_tiles; ++mt) {
+        mbar_wait(&tfull_bar[mt], static_cast<uint32_t>(t & 1));
+        tcgen05_fence_after();
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(mt * kLN), v);
+        tmem_ld_wait();
+        const int b = mt * 128 + lane_grp * 32 + lane;
+        if (b < B) {
+          const long long o = static_cast<long long>(b) * H + j * kU;
+          const long long ot = (static_cast<long long>(t) * B + b) * H + j * kU;
+          __nv_bfloat16* nh = p.hbuf[nxt][0] + o;
+          __nv_bfloat16* nl = p.nsplit == 3 ? p.hbuf[nxt][1] + o : nullptr;
+          if (t < __ldg(p.lengths + b)) {
+            const float* gx = p.gates_x + (static_cast<long long>(t) * B + b) * 4 * H + j * kU;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 x0 = __ldg(reinterpret_cast<const float4*>(gx + g * H));
+              const float4 x1 = __ldg(reinterpret_cast<const float4*>(gx + g * H + 4));
+              v[g * 8 + 0] += x0.x; v[g * 8 + 1] += x0.y; v[g * 8 + 2] += x0.z; v[g * 8 + 3] += x0.w;
+              v[g * 8 + 4] += x1.x; v[g * 8 + 5] += x1.y; v[g * 8 + 6] += x1.z; v[g * 8 + 7] += x1.w;
+            }
+            float c[8], h[8];
+            *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(p.cT + o);
+            *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(p.cT + o + 4);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float ig = 1.0f / (1.0f + expf(-v[u]));
+              const float fg = 1.0f / (1.0f + expf(-v[8 + u]));
+              const float gg = tanhf(v[16 + u]);
+              const float og = 1.0f / (1.0f + expf(-v[24 + u]));
+              c[u] = fg * c[u] + ig * gg;
+              h[u] = og * tanhf(c[u]);
+            }
+            *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
+            *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
+            *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
+            *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
+            store_h8(nh, nl, h);
+            if (p.out_f32) {
+              *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
+              *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
+            }
+            if (p.out_hi) store_h8(p.out_hi + ot, p.out_lo ? p.out_lo + ot : nullptr, h);
+          } else {
+            // padded step: state unchanged; carry the bf16 operand into the other buffer
+            *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(p.hbuf[cur][0] + o);
+            if (nl) *reinterpret_cast<uint4*>(nl) = *reinterpret_cast<const uint4*>(p.hbuf[cur][1] + o);
+            if (p.out_f32) {
+              *reinterpret_cast<float4*>(p.out_f32 + ot) = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (p.out_hi) {
+              *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
+              if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + ot) = make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+      }
+      fence_proxy_async_all();  // h_t must be visible to the TMA (async proxy) reads of step t+1
+    }
+    tcgen05_fence_before();
+    if (t + 1 < p.T) {
+      grid_barrier(p.barrier, (++bar_n) * gridDim.x);
+    } else {
+      __syncthreads();
+    }
+    tcgen05_fence_after();
+  }
+
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+static size_t lstm_smem_bytes(int kblocks, int nsplit) {
+  return static_cast<size_t>((nsplit == 3 ? 2 : 1) * kblocks * kLWTile + kLStages * kLABytes +
+                             (2 * kLStages + kLMaxTiles + 1) * 8 + 16 + 1024);
+}
+
+int lstm_init() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 3))));
+  return BLM_OK;
+}
+
+}  // namespace blm
+
+extern "C" {
+
+int64_t blm_lstm_workspace_bytes(int64_t B, int64_t H) {
+  // barrier counter (256 B) + 2 buffers x (hi, lo) x [B, H] bf16
+  return 256 + 4 * B * H * 2;
+}
+
+int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo, const float* h0,
+                   const float* c0, const int32_t* lengths, int64_t T, int64_t B, int64_t H, float* out_f32,
+                   blm_bf16* out_hi, blm_bf16* out_lo, float* hT, float* cT, void* workspace, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
+  BLM_REQUIRE(gates_x && w_hh_hi && h0 && c0 && lengths && hT && cT && workspace, BLM_ERR_ARG,
+              "null LSTM argument");
+  BLM_REQUIRE(T >= 1 && B >= 1 && T < (1 << 20), BLM_ERR_SHAPE, "bad LSTM shape T=%lld B=%lld", (long long)T,
+              (long long)B);
+  BLM_REQUIRE(H >= kU && (H % kU) == 0 && H <= 1024, BLM_ERR_SHAPE,
+              "hidden size %lld must be a multiple of 8 and <= 1024 (W_hh slice must fit in shared memory)",
+              (long long)H);
+  BLM_REQUIRE(H / kU <= num_sms(), BLM_ERR_SHAPE, "hidden size %lld needs more CTAs than SMs", (long long)H);
+  BLM_REQUIRE(B <= 128 * kLMaxTiles, BLM_ERR_SHAPE, "batch %lld exceeds %d rows per launch", (long long)B,
+              128 * kLMaxTiles);
+  BLM_REQUIRE(!out_lo || out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
+  BLM_REQUIRE(aligned16(gates_x) && aligned16(h0) && aligned16(c0) && aligned16(hT) && aligned16(cT) &&
+                  aligned16(out_f32) && aligned16(out_hi) && aligned16(out_lo) && aligned16(workspace),
+              BLM_ERR_ALIGN, "LSTM pointers must be 16-byte aligned");
+
+  LstmParams p;
+  memset(&p, 0, sizeof(p));
+  p.nsplit = w_hh_lo ? 3 : 1;
+  p.T = static_cast<int>(T);
+  p.B = static_cast<int>(B);
+  p.H = static_cast<int>(H);
+  p.kblocks = static_cast<int>((H + 63) / 64);
+  p.m_tiles = static_cast<int>((B + 127) / 128);
+  p.gates_x = gates_x;
+  p.h0 = h0;
+  p.c0 = c0;
+  p.lengths = lengths;
+  p.out_f32 = out_f32;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  p.hT = hT;
+  p.cT = cT;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  p.barrier = reinterpret_cast<unsigned int*>(ws);
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(ws + 256);
+  for (int buf = 0; buf < 2; ++buf)
+    for (int part = 0; part < 2; ++part) {
+      p.hbuf[buf][part] = hb + (static_cast<int64_t>(buf) * 2 + part) * B * H;
+      int rc = encode_tmap_bf16(&p.tmH[buf][part], p.hbuf[buf][part], B, H, H, 128);
+      if (rc != BLM_OK) return rc;
+    }
+  int rc = encode_tmap_bf16(&p.tmW[0], w_hh_hi, 4 * H, H, H, 8);
+  if (rc != BLM_OK) return rc;
+  rc = encode_tmap_bf16(&p.tmW[1], w_hh_lo ? w_hh_lo : w_hh_hi, 4 * H, H, H, 8);
+  if (rc != BLM_OK) return rc;
+
+  cudaStream_t st = as_stream(stream);
+  BLM_CHECK_CUDA(cudaMemsetAsync(p.barrier, 0, 256, st));
+  void* args[] = {&p};
+  const dim3 grid(static_cast<unsigned>(H / kU)), block(kLThreads);
+  BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_layer_kernel), grid, block, args,
+                                             lstm_smem_bytes(p.kblocks, p.nsplit), st));
+  return BLM_OK;
+}
+
+}  // extern "C"

@@ -390,9 +390,204 @@ def kl_sum(terms, minus_one: bool) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------- LSTM
-def lstm_logits(model, x, hidden):
-    raise _lib.BlmError("LSTM path not built yet")
+LSTM_EPS_ORDER = ("weight_hh_1", "weight_ih_1", "bias_hh_1", "bias_ih_1",
+                  "weight_hh_2", "weight_ih_2", "bias_hh_2", "bias_ih_2")  # draw order of model.py:670-700
+LSTM_MAX_ROWS = 2048     # rows (sequences) per recurrence launch: 16 TMEM accumulators x 128
 
 
+def _lstm_weights(model, plan: _Plan, sample: Optional[Sample], seed):
+    """Per-layer (w_ih, w_hh, bias) for one posterior sample: copies of the mean matrices whose
+    gate-row block [(p-1)H, pH) is overwritten with mu + exp(lgstd) * eps (model.py:716-725)."""
+    r = model.rnn
+    if sample is None or not 1 <= r.position <= 4:
+        return plan.lstm
+    rows = r.gate_rows()
+    out = []
+    for li, layer in enumerate((1, 2)):
+        base = plan.lstm[li]
+        W = {}
+        for name in ("ih", "hh"):
+            src = base["w_" + name]
+            dst = Split(src.hi.clone(), None if src.lo is None else src.lo.clone())
+            key = f"weight_{name}_{layer}"
+            mu = getattr(r, f"weight_{name}_mean_{layer}").detach()[rows]
+            ls = getattr(r, f"weight_{name}_lgstd_{layer}").detach()
+            view = Split(dst.hi[rows], None if dst.lo is None else dst.lo[rows])
+            if isinstance(sample, dict):
+                ops.reparam(mu, ls, eps=sample[key].to(mu.device).float(), prec=plan.prec, out=view)
+            else:
+                ops.reparam(mu, ls, seed=seed, stream_id=_stream_id(_TID["lstm"] + LSTM_EPS_ORDER.index(key), int(sample)),
+                            prec=plan.prec, out=view)
+            W["w_" + name] = dst
+        bias = base["bias"].clone()
+        cur = bias[rows]  # b_ih + b_hh on the gate rows; add the two noise terms one after the other
+        for name in ("ih", "hh"):
+            key = f"bias_{name}_{layer}"
+            ls = getattr(r, f"bias_{name}_lgstd_{layer}").detach()
+            tmp = torch.empty_like(cur)
+            if isinstance(sample, dict):
+                ops.reparam(cur, ls, eps=sample[key].to(cur.device).float(), out_f32=tmp.view(1, -1), want_f32=True)
+            else:
+                ops.reparam(cur, ls, seed=seed, stream_id=_stream_id(_TID["lstm"] + LSTM_EPS_ORDER.index(key), int(sample)),
+                            out_f32=tmp.view(1, -1), want_f32=True)
+            cur = tmp
+        bias[rows] = cur
+        W["bias"] = bias
+        out.append(W)
+    return out
+
+
+def _lstm_forward(model, plan: _Plan, weights, tokens_tb: torch.Tensor, lengths: torch.Tensor, h0, c0,
+                  want_f32: bool, want_split: bool):
+    """tokens_tb int32 [T, B] (time-major, right padded), lengths int32 [B], h0/c0 [2, B, H] fp32.
+    Returns (last-layer out fp32 [T*B, H] or None, last-layer out Split or None, hT [2,B,H], cT [2,B,H])."""
+    T, B = tokens_tb.shape
+    H = model.nhid
+    prec = plan.prec
+    _, x = ops.embed(tokens_tb.reshape(-1), None, plan.emb, None, 1.0, prec=prec, want_f32=False)
+    hs, cs = [], []
+    out32 = None
+    for li in range(2):
+        W = weights[li]
+        gates = torch.empty(T * B, 4 * H, dtype=torch.float32, device=plan.device)
+        ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+        last = li == 1
+        out32, x, hT, cT = ops.lstm_layer(gates, W["w_hh"], h0[li], c0[li], lengths, T, B, H, prec=prec,
+                                          want_f32=last and want_f32, want_split=(not last) or want_split)
+        hs.append(hT)
+        cs.append(cT)
+    return out32, x, torch.stack(hs), torch.stack(cs)
+
+
+def _fresh_train_sample(model):
+    if model.training and 1 <= model.rnn.position <= 4:
+        return 0, int(torch.randint(0, 2 ** 62, (1,)).item())
+    return None, None
+
+
+@torch.no_grad()
+def lstm_logits(model, x: torch.Tensor, hidden):
+    """Reference-compatible ``forward``: (T, B) int64 + (h, c) -> logits (T, B, V), (h, c), precise mode.
+    Train mode draws one Philox sample for the Bayesian gate (model.py:669); dropout is not applied."""
+    T, B = x.shape
+    if B > LSTM_MAX_ROWS:
+        raise _lib.BlmError(f"batch {B} exceeds {LSTM_MAX_ROWS} rows per recurrence launch")
+    prec = "bf16x3"
+    plan = plan_for(model, prec)
+    sample, seed = _fresh_train_sample(model)
+    W = _lstm_weights(model, plan, sample, seed)
+    lengths = torch.full((B,), T, dtype=torch.int32, device=x.device)
+    _, out, hT, cT = _lstm_forward(model, plan, W, x.to(torch.int32).contiguous(), lengths, hidden[0].float(),
+                                   hidden[1].float(), want_f32=False, want_split=True)
+    V = plan.E.hi.shape[0]
+    ld = (V + 7) // 8 * 8
+    logits = torch.empty(T * B, ld, dtype=torch.float32, device=x.device)
+    ops.gemm(out, plan.E, prec=prec, bias=plan.dec_b, out_f32=logits, tag="decoder")
+    return logits[:, :V].reshape(T, B, V), (hT, cT)
+
+
+def _pad_time_major(seqs: Sequence[Sequence[int]], device):
+    """list of id lists -> (int32 [T, B] time-major right-padded with 0, int32 lengths [B]) on device."""
+    B = len(seqs)
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int32, count=B)
+    T = max(int(lens.max()) if B else 0, 1)
+    host = torch.zeros(T * B + B, dtype=torch.int32)
+    if torch.cuda.is_available():
+        host = host.pin_memory()
+    mat = host[:T * B].view(T, B).numpy()
+    for b, s in enumerate(seqs):
+        if len(s):
+            mat[:len(s), b] = s
+    host[T * B:] = torch.from_numpy(lens)
+    dev = host.to(device, non_blocking=True)
+    return dev[:T * B].view(T, B), dev[T * B:], lens
+
+
+@torch.no_grad()
 def lstm_score(model, batch, hidden, **kw):
-    raise _lib.BlmError("LSTM path not built yet")
+    raise _lib.BlmError("use Rescorer.score_sessions / lstm_score_sessions for LSTM rescoring")
+
+
+@torch.no_grad()
+def lstm_score_sessions(rs, sessions):
+    """Score LSTM sessions (see scorer.py).  sessions[s][u] = [(input ids, target ids), ...].
+    Returns fp32 numpy scores in (session, utterance, hypothesis) order.
+
+    Phase 1: the hypothesis-#0 chain.  For u = 0, 1, ...: hypothesis #0 of utterance u of EVERY session
+    advances in lock step from that session's carried state; the state before each utterance is
+    recorded (rows of sessions that have run out of utterances have length 0 and keep their state).
+    Phase 2: every hypothesis of every utterance, sorted by length and cut into lock-step batches,
+    starts from its utterance's recorded state; the last layer's hidden states of the valid
+    positions are gathered hypothesis-major and go through the vocabulary-streaming NLL kernel.
+    With K posterior samples both phases run once per sample (each sample carries its own chain)
+    and the per-token log-probabilities are combined as the Monte-Carlo predictive."""
+    model, prec, dev = rs.model, rs.prec, rs.device
+    plan = plan_for(model, prec)
+    H = model.nhid
+    samples = _normalise_samples(rs.K, rs.seed, rs.eps_list) or [None]
+    S = len(sessions)
+    U = max((len(s) for s in sessions), default=0)
+    rows = [(s, u, n) for s in range(S) for u in range(len(sessions[s])) for n in range(len(sessions[s][u]))]
+    if not rows:
+        return np.zeros(0, dtype=np.float32)
+
+    # ---------------- phase 1 (per sample): init state of every (session, utterance)
+    init_h = torch.zeros(len(samples), U, 2, S, H, dtype=torch.float32, device=dev)
+    init_c = torch.zeros_like(init_h)
+    weights = [_lstm_weights(model, plan, k, rs.seed) for k in samples]
+    for s0 in range(0, S, LSTM_MAX_ROWS):
+        s1 = min(S, s0 + LSTM_MAX_ROWS)
+        chain_in = [[sessions[s][u][0][0] if u < len(sessions[s]) else [] for s in range(s0, s1)] for u in range(U)]
+        padded = [_pad_time_major(c, dev) for c in chain_in[:-1]]   # the last utterance feeds nobody
+        rs.h2d_bytes += sum(4 * (t.numel() + l.numel()) for t, l, _ in padded)
+        for k in range(len(samples)):
+            h = torch.zeros(2, s1 - s0, H, dtype=torch.float32, device=dev)
+            c = torch.zeros_like(h)
+            for u in range(U):
+                init_h[k, u, :, s0:s1], init_c[k, u, :, s0:s1] = h, c
+                if u + 1 < U:
+                    tok, lens, _ = padded[u]
+                    _, _, h, c = _lstm_forward(model, plan, weights[k], tok, lens, h, c, want_f32=False, want_split=False)
+
+    # ---------------- phase 2: all hypotheses, longest first, in lock-step batches
+    lens_all = np.asarray([len(sessions[s][u][n][0]) for s, u, n in rows], dtype=np.int64)
+    order = np.argsort(-lens_all, kind="stable")
+    scores = np.zeros(len(rows), dtype=np.float32)
+    outs = []
+    i = 0
+    while i < len(order):
+        T = int(lens_all[order[i]])
+        nb = int(min(LSTM_MAX_ROWS, max(1, rs.max_tokens // max(T, 1)), len(order) - i))
+        idx = order[i:i + nb]
+        i += nb
+        seqs = [sessions[rows[r][0]][rows[r][1]][rows[r][2]] for r in idx]
+        tok, lens_d, lens = _pad_time_major([x for x, _ in seqs], dev)
+        B = len(seqs)
+        # hypothesis-major gather list of the valid (t, b) rows + packed targets
+        offs = np.zeros(B + 1, dtype=np.int32)
+        np.cumsum(lens, out=offs[1:])
+        M = int(offs[-1])
+        b_of = np.repeat(np.arange(B, dtype=np.int32), lens)
+        t_of = (np.arange(M, dtype=np.int32) - np.repeat(offs[:-1], lens)).astype(np.int32)
+        meta = np.concatenate([t_of * B + b_of, np.concatenate([np.asarray(y, dtype=np.int32) for _, y in seqs]),
+                               offs, np.asarray([rows[r][0] for r in idx], dtype=np.int32),
+                               np.asarray([rows[r][1] for r in idx], dtype=np.int32)]).astype(np.int32)
+        meta_h = torch.from_numpy(meta)
+        meta_d = (meta_h.pin_memory() if torch.cuda.is_available() else meta_h).to(dev, non_blocking=True)
+        rs.h2d_bytes += 4 * (meta.size + tok.numel() + lens_d.numel())
+        gather, tgt, offs_d = meta_d[:M], meta_d[M:2 * M], meta_d[2 * M:2 * M + B + 1]
+        s_idx, u_idx = meta_d[2 * M + B + 1:2 * M + 2 * B + 1].long(), meta_d[2 * M + 2 * B + 1:].long()
+        per = torch.empty(len(samples), M, dtype=torch.float32, device=dev)
+        for k in range(len(samples)):
+            h0 = init_h[k, u_idx, :, s_idx].transpose(0, 1).contiguous()   # [2, B, H]
+            c0 = init_c[k, u_idx, :, s_idx].transpose(0, 1).contiguous()
+            out32, _, _, _ = _lstm_forward(model, plan, weights[k], tok, lens_d, h0, c0, want_f32=True, want_split=False)
+            _, hs = ops.embed(gather, None, out32, None, 1.0, prec=prec, want_f32=False)  # row gather + bf16 split
+            ops.vocab_nll(hs, plan.E, plan.dec_b, tgt, prec=prec, out=per[k])
+        tok_nll = per[0] if len(samples) == 1 else ops.mc_combine(per)
+        outs.append((idx, ops.segment_sum(tok_nll, offs_d)))
+    for idx, dev_scores in outs:
+        host = dev_scores.cpu()
+        rs.d2h_bytes += host.numel() * 4
+        scores[idx] = host.numpy()
+    return scores

@@ -223,9 +223,12 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def reparam(mu: torch.Tensor, lgstd: Optional[torch.Tensor], *, eps: Optional[torch.Tensor] = None,
-            seed: Optional[int] = None, stream_id: int = 0, prec: str = "bf16", want_f32: bool = False):
+            seed: Optional[int] = None, stream_id: int = 0, prec: str = "bf16", want_f32: bool = False,
+            out: Optional[Split] = None, out_f32: Optional[torch.Tensor] = None):
     """``mu + exp(lgstd) * eps`` for a 2-D row-slice view ``mu`` (unit column stride).
-    eps: explicit tensor, or Philox(seed, stream_id) when ``seed`` is given, or none (mean)."""
+    eps: explicit tensor, or Philox(seed, stream_id) when ``seed`` is given, or none (mean).
+    ``out`` / ``out_f32`` write into caller-provided dense [rows, cols] buffers (e.g. the gate-row
+    block of a full LSTM weight copy)."""
     if mu.dim() == 1:
         mu = mu.view(1, -1)
         lgstd = None if lgstd is None else lgstd.view(1, -1)
@@ -234,15 +237,24 @@ def reparam(mu: torch.Tensor, lgstd: Optional[torch.Tensor], *, eps: Optional[to
     assert mu.stride(1) == 1
     mode = EPS_PTR if eps is not None else (EPS_PHILOX if seed is not None else EPS_NONE)
     dev = mu.device
-    w = torch.empty(rows, cols, dtype=torch.float32, device=dev) if want_f32 else None
-    s = empty_split(rows, cols, prec, dev)
+    w = out_f32
+    if w is None and want_f32:
+        w = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+    s = out
+    if s is None and (out_f32 is None or not want_f32):
+        s = empty_split(rows, cols, prec, dev) if out_f32 is None else None
+    if w is not None:
+        assert w.is_contiguous() and w.numel() == rows * cols
+    if s is not None:
+        assert s.hi.is_contiguous() and s.hi.numel() == rows * cols and (s.lo is None or s.lo.is_contiguous())
     if lgstd is not None:
         lgstd = lgstd.contiguous()
     if eps is not None:
         eps = eps.contiguous().float()
     with _op("reparam", 1):
         check(lib().blm_reparam(_ptr(mu), mu.stride(0), _ptr(lgstd), _ptr(eps), mode, int(seed or 0), int(stream_id),
-                                rows, cols, _ptr(w), _ptr(s.hi), _ptr(s.lo), _stream()), "blm_reparam")
+                                rows, cols, _ptr(w), _ptr(None if s is None else s.hi),
+                                _ptr(None if s is None else s.lo), _stream()), "blm_reparam")
     return w, s
 
 
@@ -285,3 +297,30 @@ def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_
         check(lib().blm_kl_gauss(_ptr(mu), mu.stride(0), _ptr(lgstd), rows, cols, int(minus_one), scale,
                                  int(accumulate), _ptr(out), _ptr(ws), _stream()), "blm_kl_gauss")
     return out
+
+
+_lstm_ws = {}
+
+
+def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.Tensor, lengths: torch.Tensor,
+               T: int, B: int, H: int, *, prec: str = "bf16", want_f32: bool = False, want_split: bool = True):
+    """One LSTM layer over [T, B] lock-stepped rows.  Returns (out_f32 or None, out Split or None, hT, cT)."""
+    dev = gates_x.device
+    assert gates_x.is_contiguous() and gates_x.numel() == T * B * 4 * H and lengths.dtype == torch.int32
+    h0, c0 = h0.contiguous(), c0.contiguous()
+    out32 = torch.empty(T * B, H, dtype=torch.float32, device=dev) if want_f32 else None
+    outs = empty_split(T * B, H, prec, dev) if want_split else None
+    hT = torch.empty(B, H, dtype=torch.float32, device=dev)
+    cT = torch.empty(B, H, dtype=torch.float32, device=dev)
+    nbytes = lib().blm_lstm_workspace_bytes(B, H)
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _lstm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _lstm_ws[key] = ws
+    with _op("lstm_layer", 1, 2.0 * T * B * 4 * H * H):
+        check(lib().blm_lstm_layer(_ptr(gates_x), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
+                                   _ptr(c0), _ptr(lengths), T, B, H, _ptr(out32),
+                                   _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),
+                                   _ptr(hT), _ptr(cT), _ptr(ws), _stream()), "blm_lstm_layer")
+    return out32, outs, hT, cT

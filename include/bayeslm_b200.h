@@ -211,7 +211,9 @@ int blm_kl_gauss(const float* mu, int64_t ldmu, const float* lgstd, int64_t rows
  *                             untouched (right padding)
  *   out_* [T, B, H]         : h_t (fp32 and/or bf16 hi/lo), zero where padded
  *   hT, cT [B, H] fp32      : state after each row's last valid step
- * workspace: blm_lstm_workspace_bytes(B, H) bytes, zero-initialised once.     */
+ * workspace: blm_lstm_workspace_bytes(B, H) bytes (the call resets its barrier
+ * counter itself with a stream-ordered memset).  H % 8 == 0, H <= 1024,
+ * B <= 2048 rows per launch.                                                  */
 int64_t blm_lstm_workspace_bytes(int64_t B, int64_t H);
 int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo,
                    const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
