@@ -13,6 +13,9 @@
 // Two TMEM accumulator stages let the MMA of tile i+1 overlap the epilogue of
 // tile i.  Ragged M/N/K edges rely on TMA zero fill; the epilogue masks rows
 // >= M and columns >= N.
+#include <stdlib.h>
+#include <string.h>
+
 #include "blm_host.h"
 #include "blm_ptx.cuh"
 
@@ -53,33 +56,205 @@ struct GemmParams {
   float* part_tgt;
 };
 
-template <int BN, int STAGES>
+// ARES > 0: the A operand of a work item (ARES K blocks of 128 x 64) stays resident in shared
+// memory for the whole sweep over its N tiles and only B streams through the ring.
+template <int BN, int STAGES, int ARES = 0>
 struct SmemLayout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem ptr
-  static constexpr int kBytes = kBarOffset + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kResBytes = ARES * kABytes;
+  static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
+  static constexpr int kBarOffset = kResBytes + STAGES * kStageBytes;
+  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] a_full a_empty + tmem ptr
+  static constexpr int kBytes = kBarOffset + (2 * STAGES + 6) * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-B alignment
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exact-erf GELU to 4e-7 absolute: erf(t) = 1 - 2^(-t q(t)) with q a degree-6 fit of -log2(erfc(t))/t
+// on [0, 4] (erfc(4) = 1.5e-8, so t is clamped there); one MUFU.EX2 and nine FMAs per element
+// instead of libdevice erff -- the FFN1 epilogue has ~16 issue slots per element before it, not
+// the tensor pipe, becomes the bound at K = 512.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float q = fmaf(t, -1.002195230e-04f, 4.615629764e-04f);
+  q = fmaf(q, t, 2.302262028e-03f);
+  q = fmaf(q, t, -2.945254180e-02f);
+  q = fmaf(q, t, 1.489636837e-01f);
+  q = fmaf(q, t, 9.183286407e-01f);
+  q = fmaf(q, t, 1.627913732e+00f);
+  const float w = 0.5f * x * ex2_approx(-(q * t));
+  return x >= 0.0f ? x - w : w;
+}
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float z, const float* __restrict__ coef, int N, int n) {
   if constexpr (ACT == BLM_ACT_GELU) {
-    return gelu_erf(z);
+    return gelu_fast(z);
   } else if constexpr (ACT == BLM_ACT_GPMIX) {
     const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n),
                 c3 = __ldg(coef + 3 * N + n);
-    return c0 * tanhf(z) + c1 * (1.0f / (1.0f + expf(-z))) + c2 * fmaxf(z, 0.0f) + c3 * gelu_erf(z);
+    return c0 * tanhf(z) + c1 * (1.0f / (1.0f + expf(-z))) + c2 * fmaxf(z, 0.0f) + c3 * gelu_fast(z);
   } else {
     return z;
   }
 }
 
-template <int BN, int STAGES, int EPI, int ACT>
+// ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
+
+// bias / q-scale / activation / residual / (hi, lo) split / stores for one 32-column chunk
+template <int ACT>
+__device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, int col0) {
+  const bool full = (col0 + 32 <= p.N);
+  if (full) {
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += bb.x;
+        v[j + 1] += bb.y;
+        v[j + 2] += bb.z;
+        v[j + 3] += bb.w;
+      }
+    }
+    if (col0 + 32 <= p.col_scale_cols) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.col_scale;
+    } else if (col0 < p.col_scale_cols) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.col_scale_cols) v[j] *= p.col_scale;
+    }
+    if constexpr (ACT != BLM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
+    }
+    if (p.resid) {
+      const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 rr = __ldg(reinterpret_cast<const float4*>(r + j));
+        v[j] += rr.x;
+        v[j + 1] += rr.y;
+        v[j + 2] += rr.z;
+        v[j + 3] += rr.w;
+      }
+    }
+    const long long off = static_cast<long long>(m) * p.ldc + col0;
+    if (p.out_f32) {
+      float* o = p.out_f32 + off;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    if (p.out_hi) {
+      __nv_bfloat16* oh = p.out_hi + off;
+      __nv_bfloat16* ol = p.out_lo ? p.out_lo + off : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t h[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = pack_bf16x2(v[j + 2 * q], v[j + 2 * q + 1]);
+        *reinterpret_cast<uint4*>(oh + j) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (ol) {
+          uint32_t l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = v[j + 2 * q] - __uint_as_float(h[q] << 16);
+            const float b = v[j + 2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u);
+            l[q] = pack_bf16x2(a, b);
+          }
+          *reinterpret_cast<uint4*>(ol + j) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    }
+  } else {
+    // ragged right edge (N not a multiple of 32): scalar path, only the last chunk of a row
+    const long long off = static_cast<long long>(m) * p.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {  // static register indices: v must not fall into local memory
+      const int col = col0 + j;
+      if (col >= p.N) continue;
+      float z = v[j];
+      if (p.bias) z += __ldg(p.bias + col);
+      if (col < p.col_scale_cols) z *= p.col_scale;
+      z = apply_act<ACT>(z, p.coef, p.N, col);
+      if (p.resid) z += __ldg(p.resid + static_cast<long long>(m) * p.ldr + col);
+      if (p.out_f32) p.out_f32[off + j] = z;
+      if (p.out_hi) {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(z);
+        p.out_hi[off + j] = hh;
+        if (p.out_lo) p.out_lo[off + j] = __float2bfloat16_rn(z - __bfloat162float(hh));
+      }
+    }
+  }
+}
+
+struct NllState {
+  float run_max;  // log2 domain: fl(max logit * log2 e)
+  float run_sum, tgt_logit;
+  int tgt;
+};
+
+// online log-sum-exp over one 32-column chunk of logits (natural-log units; exponentials via ex2)
+__device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], int col0, NllState& st) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  if (col0 + 32 <= p.N) {
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += bb.x;
+        v[j + 1] += bb.y;
+        v[j + 2] += bb.z;
+        v[j + 3] += bb.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      v[j] = col < p.N ? v[j] + (p.bias ? __ldg(p.bias + col) : 0.0f) : -INFINITY;
+    }
+  }
+  const unsigned int rel = static_cast<unsigned int>(st.tgt - col0);
+  if (rel < 32u) {  // the target column lives in this chunk: once per row per sweep
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (rel == static_cast<unsigned int>(j)) st.tgt_logit = v[j];
+  }
+  float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
+#pragma unroll
+  for (int j = 8; j < 32; j += 8) {
+    m0 = fmaxf(m0, fmaxf(v[j], v[j + 1]));
+    m1 = fmaxf(m1, fmaxf(v[j + 2], v[j + 3]));
+    m2 = fmaxf(m2, fmaxf(v[j + 4], v[j + 5]));
+    m3 = fmaxf(m3, fmaxf(v[j + 6], v[j + 7]));
+  }
+  // running maximum kept in the log2 domain as the ROUNDED product max * log2(e): every term and
+  // every rescale is then measured against exactly the same power of two (a rescale by the
+  // unchanged maximum is exactly 1, so nothing compounds over the ~1000 chunks of a row)
+  const float new_m2 = fmaxf(st.run_max, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * kLog2e);
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    s0 += ex2_approx(fmaf(v[j], kLog2e, -new_m2));
+    s1 += ex2_approx(fmaf(v[j + 1], kLog2e, -new_m2));
+    s2 += ex2_approx(fmaf(v[j + 2], kLog2e, -new_m2));
+    s3 += ex2_approx(fmaf(v[j + 3], kLog2e, -new_m2));
+  }
+  st.run_sum = st.run_sum * ex2_approx(st.run_max - new_m2) + ((s0 + s1) + (s2 + s3));
+  st.run_max = new_m2;
+}
+
+template <int BN, int STAGES, int EPI, int ACT, int ARES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, ARES>;
   constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                             : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
@@ -87,11 +262,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
+  uint8_t* ring = smem + L::kResBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* afull_bar = tempty_bar + 2;
+  uint64_t* aempty_bar = afull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,6 +289,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
     }
+    mbar_init(afull_bar, 1);
+    mbar_init(aempty_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -126,24 +306,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // ------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, a_phase = 0;
       for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
         const int m_tile = w / p.n_groups;
         const int grp = w - m_tile * p.n_groups;
         const int n0 = grp * p.tiles_per_group;
         const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+        if constexpr (ARES > 0) {
+          // the previous work's MMAs must have drained the resident A before it is overwritten
+          mbar_wait(aempty_bar, a_phase ^ 1u);
+          mbar_arrive_expect_tx(afull_bar, static_cast<uint32_t>(total_kb * L::kABytes));
+          int idx = 0;
+          for (int s = 0; s < p.nseg; ++s)
+            for (int kb = 0; kb < p.kblocks[s]; ++kb, ++idx)
+              tma_load_2d(smem + idx * L::kABytes, &p.tmA[s], afull_bar, kb * kBK, m_tile * kBM, kEvictFirst);
+          a_phase ^= 1u;
+        }
         for (int n = n0; n < n1; ++n) {
           for (int s = 0; s < p.nseg; ++s) {
             const int kbs = p.kblocks[s];
             for (int kb = 0; kb < kbs; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-              uint8_t* sa = smem + stage * L::kStageBytes;
-              uint8_t* sb = sa + L::kABytes;
-              // activations stream once (evict-first); weights are re-read by
-              // every M tile and stay L2 resident (evict-last).
-              tma_load_2d(sa, &p.tmA[s], &full_bar[stage], kb * kBK, m_tile * kBM, kEvictNormal);
-              tma_load_2d(sb, &p.tmB[s], &full_bar[stage], kb * kBK, n * BN, kEvictLast);
+              uint8_t* st = ring + stage * L::kStageBytes;
+              // activations stream once; weights are re-read by every M tile and stay L2 resident
+              if constexpr (ARES == 0) {
+                tma_load_2d(st, &p.tmA[s], &full_bar[stage], kb * kBK, m_tile * kBM, kEvictNormal);
+                st += L::kABytes;
+              }
+              tma_load_2d(st, &p.tmB[s], &full_bar[stage], kb * kBK, n * BN, kEvictLast);
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -159,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, a_phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
@@ -167,6 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         const int grp = w - m_tile * p.n_groups;
         const int n0 = grp * p.tiles_per_group;
         const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+        if constexpr (ARES > 0) {
+          mbar_wait(afull_bar, a_phase);
+          a_phase ^= 1u;
+        }
         for (int n = n0; n < n1; ++n) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
           tcgen05_fence_after();
@@ -174,8 +369,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           for (int kb = 0; kb < total_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-            const uint32_t sb = sa + L::kABytes;
+            const uint32_t st = smem_u32(ring + stage * L::kStageBytes);
+            const uint32_t sa = ARES > 0 ? smem_u32(smem + kb * L::kABytes) : st;
+            const uint32_t sb = ARES > 0 ? st : st + L::kABytes;
             const uint64_t da = umma_desc_sw128(sa);
             const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
@@ -196,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             acc_phase ^= 1u;
           }
         }
+        if constexpr (ARES > 0) umma_commit(aempty_bar);  // resident A free once this work's MMAs retire
       }
     }
     __syncwarp();
@@ -203,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // ---------------------------------------------------------- epilogue
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) belong to this warp
     const int row_in_tile = lane_grp * 32 + lane;
+    constexpr int kChunks = BN / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
@@ -213,11 +411,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       const int m = m_tile * kBM + row_in_tile;
       const bool row_ok = m < p.M;
 
-      // EPI_NLL running state (base-2 domain: logits pre-multiplied by log2 e)
-      float run_max = -INFINITY, run_sum = 0.0f, tgt_logit = -INFINITY;
-      int tgt = -1;
+      NllState st{-INFINITY, 0.0f, -INFINITY, -1};
       if constexpr (EPI == EPI_NLL) {
-        if (row_ok) tgt = __ldg(p.targets + m);
+        if (row_ok) st.tgt = __ldg(p.targets + m);
       }
 
       for (int n = n0; n < n1; ++n) {
@@ -225,114 +421,45 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         tcgen05_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+        float va[32], vb[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked branches
-          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+        for (int c = 0; c < kChunks; c += 2) {
           tmem_ld_wait();
-          const int col0 = n * BN + c * 32;
-          if (col0 >= p.N) continue;  // warp-uniform
-          if constexpr (EPI == EPI_STORE) {
-            if (row_ok) {
-            const bool full = (col0 + 32 <= p.N);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              const int colc = full ? col : min(col, p.N - 1);
-              float z = v[j];
-              if (p.bias) z += __ldg(p.bias + colc);
-              if (col < p.col_scale_cols) z *= p.col_scale;
-              z = apply_act<ACT>(z, p.coef, p.N, colc);
-              v[j] = z;
-            }
-            const long long off = static_cast<long long>(m) * p.ldc + col0;
-            if (p.resid) {
-              const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 rr = __ldg(reinterpret_cast<const float4*>(r + j));
-                  v[j] += rr.x;
-                  v[j + 1] += rr.y;
-                  v[j + 2] += rr.z;
-                  v[j + 3] += rr.w;
-                }
+          __syncwarp();
+          tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 1) * 32), vb);
+          {
+            const int col0 = n * BN + c * 32;
+            if (col0 < p.N) {
+              if constexpr (EPI == EPI_STORE) {
+                if (row_ok) store_chunk<ACT>(p, va, m, col0);
               } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) v[j] += __ldg(r + j);
+                nll_chunk(p, va, col0, st);
               }
             }
-            if (full) {
-              if (p.out_f32) {
-                float* o = p.out_f32 + off;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              }
-              if (p.out_hi) {
-                __nv_bfloat16* oh = p.out_hi + off;
-                __nv_bfloat16* ol = p.out_lo ? p.out_lo + off : nullptr;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint32_t h[4], l[4];
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float a = v[j + 2 * q], b = v[j + 2 * q + 1];
-                    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                    h[q] = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) |
-                           (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
-                    l[q] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
-                  }
-                  *reinterpret_cast<uint4*>(oh + j) = make_uint4(h[0], h[1], h[2], h[3]);
-                  if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(l[0], l[1], l[2], l[3]);
-                }
-              }
-            } else {
-              // ragged right edge (N not a multiple of 32): scalar stores
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (col0 + j < p.N) {
-                  if (p.out_f32) p.out_f32[off + j] = v[j];
-                  if (p.out_hi) {
-                    const __nv_bfloat16 hh = __float2bfloat16_rn(v[j]);
-                    p.out_hi[off + j] = hh;
-                    if (p.out_lo) p.out_lo[off + j] = __float2bfloat16_rn(v[j] - __bfloat162float(hh));
-                  }
-                }
-              }
-            }
-            }  // row_ok
+          }
+          tmem_ld_wait();
+          __syncwarp();
+          if (c + 2 < kChunks) {
+            tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), va);
           } else {
-            // online log-sum-exp over this 32-column chunk
-            constexpr float kLog2e = 1.4426950408889634f;
-            float cmax = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              float z = v[j];
-              if (col < p.N) {
-                if (p.bias) z += __ldg(p.bias + col);
-                if (col == tgt) tgt_logit = z;
-                z *= kLog2e;
+            // every column of this accumulator stage is in registers: hand it back to the MMA warp
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          {
+            const int col0 = n * BN + (c + 1) * 32;
+            if (col0 < p.N) {
+              if constexpr (EPI == EPI_STORE) {
+                if (row_ok) store_chunk<ACT>(p, vb, m, col0);
               } else {
-                z = -INFINITY;
+                nll_chunk(p, vb, col0, st);
               }
-              v[j] = z;
-              cmax = fmaxf(cmax, z);
             }
-            const float new_max = fmaxf(run_max, cmax);
-            float s = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s += exp2f(v[j] - new_max);
-            run_sum = run_sum * exp2f(run_max - new_max) + s;
-            run_max = new_max;
           }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -341,9 +468,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       if constexpr (EPI == EPI_NLL) {
         if (row_ok) {
           const long long o = static_cast<long long>(grp) * p.M + m;
-          p.part_max[o] = run_max;
-          p.part_sum[o] = run_sum;
-          p.part_tgt[o] = tgt_logit;
+          p.part_max[o] = st.run_max;
+          p.part_sum[o] = st.run_sum;
+          p.part_tgt[o] = st.tgt_logit;
         }
       }
     }
@@ -357,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   }
 }
 
-// nll[m] = ln2 * (gmax + log2(sum_g sum_g * 2^(max_g - gmax))) - target logit
+// nll[m] = ln2 * (gmax2 + log2(sum_g sum_g * 2^(max2_g - gmax2))) - target logit
 __global__ void nll_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                                  const float* __restrict__ part_tgt, int groups, int M,
                                  float* __restrict__ nll) {
@@ -370,10 +497,9 @@ __global__ void nll_merge_kernel(const float* __restrict__ part_max, const float
   }
   float s = 0.0f;
   for (int g = 0; g < groups; ++g)
-    s += part_sum[static_cast<long long>(g) * M + m] *
-         exp2f(part_max[static_cast<long long>(g) * M + m] - gmax);
+    s += part_sum[static_cast<long long>(g) * M + m] * exp2f(part_max[static_cast<long long>(g) * M + m] - gmax);
   constexpr float kLn2 = 0.6931471805599453f;
-  nll[m] = kLn2 * (gmax + log2f(s)) - tgt;
+  nll[m] = kLn2 * (gmax + log2f(s)) - tgt;  // partial maxima are in the log2 domain
 }
 
 __global__ void segment_sum_kernel(const float* __restrict__ x, const int* __restrict__ offs,
@@ -389,16 +515,18 @@ __global__ void segment_sum_kernel(const float* __restrict__ x, const int* __res
 }
 
 // ------------------------------------------------------------------ host
-template <int BN, int STAGES, int EPI, int ACT>
+template <int BN, int STAGES, int EPI, int ACT, int ARES = 0>
 static int set_smem_attr() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI, ACT>,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI, ACT, ARES>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SmemLayout<BN, STAGES>::kDynBytes));
+                                      SmemLayout<BN, STAGES, ARES>::kDynBytes));
   return BLM_OK;
 }
 
 constexpr int kStages256 = 4;
 constexpr int kStages128 = 6;
+constexpr int kNllAres = 8;        // resident A: 8 K blocks = K <= 512 (128 KB)
+constexpr int kNllAresStages = 3;  // + 3 x 32 KB of streamed vocabulary tiles
 
 int gemm_init() {
   int rc;
@@ -409,14 +537,15 @@ int gemm_init() {
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_NLL, BLM_ACT_NONE>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kNllAresStages, EPI_NLL, BLM_ACT_NONE, kNllAres>()) != BLM_OK) return rc;
   return BLM_OK;
 }
 
-template <int BN, int STAGES, int EPI, int ACT>
+template <int BN, int STAGES, int EPI, int ACT, int ARES = 0>
 static int launch(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<BN, STAGES, EPI, ACT>
-      <<<grid, kThreads, SmemLayout<BN, STAGES>::kDynBytes, st>>>(p);
+  gemm_kernel<BN, STAGES, EPI, ACT, ARES>
+      <<<grid, kThreads, SmemLayout<BN, STAGES, ARES>::kDynBytes, st>>>(p);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }
@@ -552,7 +681,15 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   p.part_sum = ws + static_cast<int64_t>(used_groups) * d->M;
   p.part_tgt = ws + 2 * static_cast<int64_t>(used_groups) * d->M;
   cudaStream_t st = as_stream(stream);
-  rc = launch<256, kStages256, EPI_NLL, BLM_ACT_NONE>(p, st);
+  int total_kb = 0;
+  for (int i = 0; i < p.nseg; ++i) total_kb += p.kblocks[i];
+  // K <= 512 in one segment (the bf16 Transformer case): keep the hidden-state tile resident in
+  // shared memory for the whole vocabulary sweep, so only the embedding tiles stream from L2
+  static const bool no_ares = getenv("BLM_NLL_NO_ARES") != nullptr;  // A/B switch for profiling
+  if (total_kb <= kNllAres && !no_ares)
+    rc = launch<256, kNllAresStages, EPI_NLL, BLM_ACT_NONE, kNllAres>(p, st);
+  else
+    rc = launch<256, kStages256, EPI_NLL, BLM_ACT_NONE>(p, st);
   if (rc != BLM_OK) return rc;
   const int threads = 256;
   const int blocks = static_cast<int>((d->M + threads - 1) / threads);
