@@ -48,9 +48,9 @@ def gemm_case(M, N, K, prec, act=ops.ACT_NONE, bias=False, resid=False, colscale
         c = coef.double()
         z = c[0] * torch.tanh(z) + c[1] * torch.sigmoid(z) + c[2] * torch.relu(z) + c[3] * torch.nn.functional.gelu(z)
     if resid: z = z + r.double()
-    tol = 2e-5 if prec == "bf16x3" else 2e-5   # bf16 case compares against the bf16-rounded operands
+    tol = 4e-5 if prec == "bf16x3" else 2e-5   # bf16 case compares against the bf16-rounded operands
     report(f"gemm M={M} N={N} K={K} {prec} act={act} bias={bias} resid={resid} cs={colscale}", out32, z, tol)
-    report(f"   (hi+lo output)", out.float(), z, 4e-5)
+    report(f"   (hi+lo output)", out.float(), z, 6e-5)
 
 t0 = time.time()
 gemm_case(128, 128, 64, "bf16")
@@ -77,7 +77,7 @@ def nll_case(M, V, K, prec):
     else:
         logits = h.double() @ e.double().T + b.double()
     ref = torch.logsumexp(logits, -1) - logits.gather(1, t.long().view(-1, 1)).squeeze(1)
-    report(f"vocab_nll M={M} V={V} K={K} {prec}", nll, ref, 3e-6)
+    report(f"vocab_nll M={M} V={V} K={K} {prec}", nll, ref, 6e-6)
 
 nll_case(100, 1000, 64, "bf16")
 nll_case(100, 1000, 64, "bf16x3")
@@ -126,6 +126,8 @@ def attn_case(lens, nhead, hd):
 
 attn_case([1, 5, 17, 26, 33, 64], 8, 64)
 attn_case([100, 100, 7], 8, 64)
+attn_case([1, 2, 7, 8, 9, 15, 16, 17, 26, 31, 32, 5, 5, 5, 11, 13, 3], 8, 64)
+attn_case(list(range(1, 27)) * 3, 8, 64)
 attn_case([3, 9, 128], 4, 16)
 
 # KL
