@@ -38,6 +38,17 @@ class GemmDesc(C.Structure):
     ]
 
 
+class GemmSampledDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("mu", C.c_void_p), ("ldmu", C.c_int64),
+        ("sigma", C.c_void_p), ("eps", C.c_void_p), ("eps_mode", C.c_int32), ("act", C.c_int32),
+        ("seed", C.c_uint64), ("stream_id", C.c_uint64),
+        ("bias", C.c_void_p), ("coef", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
+    ]
+
+
 class VocabNllDesc(C.Structure):
     _fields_ = [
         ("M", C.c_int64), ("V", C.c_int64), ("nseg", C.c_int32), ("reserved", C.c_int32),
@@ -57,6 +68,8 @@ SIGNATURES = {
     "blm_init": (C.c_int, [C.c_int]),
     "blm_num_sms": (C.c_int, []),
     "blm_gemm": (C.c_int, [C.POINTER(GemmDesc), _p]),
+    "blm_gemm_sampled": (C.c_int, [C.POINTER(GemmSampledDesc), _p]),
+    "blm_sigma_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "blm_vocab_nll_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_vocab_nll": (C.c_int, [C.POINTER(VocabNllDesc), _p]),
     "blm_segment_sum": (C.c_int, [_p, _p, _i64, _p, _p]),

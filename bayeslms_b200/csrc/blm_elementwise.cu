@@ -4,6 +4,7 @@
 // operands with 128-bit accesses; grids are sized in multiples of the SM count.
 #include "blm_host.h"
 #include "blm_ptx.cuh"
+#include "blm_philox.cuh"
 
 namespace blm {
 
@@ -38,6 +39,12 @@ __global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restr
       if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
   }
+}
+
+__global__ void sigma_kernel(const float* __restrict__ lgstd, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16_rn(expf(lgstd[i]));
 }
 
 // one warp per token row; d % 4 == 0
@@ -116,44 +123,6 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
-// ------------------------------------------------------------------ Philox
-// Philox4x32-10 (Salmon et al., SC'11).  counter = (idx_lo, idx_hi, stream_lo,
-// stream_hi), key = (seed_lo, seed_hi).  One call yields four uniform words ->
-// four N(0,1) values by two Box-Muller pairs, so element i of a tensor uses
-// counter i/4, lane i%4: the noise is a pure function of (seed, stream, i) and
-// therefore identical on every rank and for every launch geometry.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(kM0, ctr.x), lo0 = kM0 * ctr.x;
-    const uint32_t hi1 = __umulhi(kM1, ctr.z), lo1 = kM1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += kW0;
-    key.y += kW1;
-  }
-  return ctr;
-}
-
-__device__ __forceinline__ float u32_to_unit_open(uint32_t u) {
-  // (0, 1]: never 0 so the log below is finite
-  return (static_cast<float>(u >> 8) + 1.0f) * (1.0f / 16777216.0f);
-}
-
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream, uint64_t idx4) {
-  const uint4 r = philox4x32_10(
-      make_uint4(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32),
-                 static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32)),
-      make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-  constexpr float kTwoPi = 6.283185307179586f;
-  const float r0 = sqrtf(-2.0f * logf(u32_to_unit_open(r.x)));
-  const float r1 = sqrtf(-2.0f * logf(u32_to_unit_open(r.z)));
-  float s0, c0, s1, c1;
-  sincosf(kTwoPi * u32_to_unit_open(r.y), &s0, &c0);
-  sincosf(kTwoPi * u32_to_unit_open(r.w), &s1, &c1);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
-}
-
 __global__ void philox_normal_kernel(uint64_t seed, uint64_t stream, long long n, float* __restrict__ out) {
   const long long n4 = (n + 3) / 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -184,10 +153,10 @@ __global__ void reparam_kernel(const float* __restrict__ mu, long long ldmu, con
       } else {
         e = philox_normal4(seed, stream, static_cast<uint64_t>(i));  // dense index (r*cols+c)/4 == i
       }
-      w.x += expf(ls.x) * e.x;
-      w.y += expf(ls.y) * e.y;
-      w.z += expf(ls.z) * e.z;
-      w.w += expf(ls.w) * e.w;
+      w.x = reparam_value(w.x, ls.x, e.x);
+      w.y = reparam_value(w.y, ls.y, e.y);
+      w.z = reparam_value(w.z, ls.z, e.z);
+      w.w = reparam_value(w.w, ls.w, e.w);
     }
     const long long o = r * cols + c;
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = w;
@@ -293,6 +262,14 @@ int blm_split_bf16(const float* x, blm_bf16* hi, blm_bf16* lo, int64_t n, blm_st
   const long long n4 = n / 4;
   split_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, as_stream(stream)>>>(
       x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n4, n);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_sigma_bf16(const float* lgstd, blm_bf16* sigma, int64_t n, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(lgstd && sigma && n > 0, BLM_ERR_ARG, "bad sigma arguments");
+  sigma_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(lgstd, reinterpret_cast<__nv_bfloat16*>(sigma), n);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

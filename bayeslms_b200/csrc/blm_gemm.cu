@@ -16,184 +16,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "blm_host.h"
-#include "blm_ptx.cuh"
+#include "blm_gemm_common.cuh"
 
 namespace blm {
-
-constexpr int kBM = 128;
-constexpr int kBK = 64;
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;
-
-enum { EPI_STORE = 0, EPI_NLL = 1 };
-
-struct GemmParams {
-  CUtensorMap tmA[BLM_MAX_SEG];
-  CUtensorMap tmB[BLM_MAX_SEG];
-  int kblocks[BLM_MAX_SEG];
-  int nseg;
-  int M, N;
-  int m_tiles, n_tiles;
-  // work decomposition: work w -> (m_tile = w / n_groups, group = w % n_groups),
-  // n tiles [group * tiles_per_group, min(n_tiles, (group+1) * tiles_per_group))
-  int n_groups, tiles_per_group, num_works;
-  // EPI_STORE
-  const float* bias;
-  const float* coef;
-  float col_scale;
-  int col_scale_cols;
-  const float* resid;
-  long long ldr;
-  float* out_f32;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
-  long long ldc;
-  // EPI_NLL
-  const int* targets;
-  float* part_max;  // [n_groups, M]
-  float* part_sum;
-  float* part_tgt;
-};
-
-// ARES > 0: the A operand of a work item (ARES K blocks of 128 x 64) stays resident in shared
-// memory for the whole sweep over its N tiles and only B streams through the ring.
-template <int BN, int STAGES, int ARES = 0>
-struct SmemLayout {
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kResBytes = ARES * kABytes;
-  static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
-  static constexpr int kBarOffset = kResBytes + STAGES * kStageBytes;
-  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] a_full a_empty + tmem ptr
-  static constexpr int kBytes = kBarOffset + (2 * STAGES + 6) * 8 + 16;
-  static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-B alignment
-};
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// exact-erf GELU to 4e-7 absolute: erf(t) = 1 - 2^(-t q(t)) with q a degree-6 fit of -log2(erfc(t))/t
-// on [0, 4] (erfc(4) = 1.5e-8, so t is clamped there); one MUFU.EX2 and nine FMAs per element
-// instead of libdevice erff -- the FFN1 epilogue has ~16 issue slots per element before it, not
-// the tensor pipe, becomes the bound at K = 512.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
-  float q = fmaf(t, -1.002195230e-04f, 4.615629764e-04f);
-  q = fmaf(q, t, 2.302262028e-03f);
-  q = fmaf(q, t, -2.945254180e-02f);
-  q = fmaf(q, t, 1.489636837e-01f);
-  q = fmaf(q, t, 9.183286407e-01f);
-  q = fmaf(q, t, 1.627913732e+00f);
-  const float w = 0.5f * x * ex2_approx(-(q * t));
-  return x >= 0.0f ? x - w : w;
-}
-
-template <int ACT>
-__device__ __forceinline__ float apply_act(float z, const float* __restrict__ coef, int N, int n) {
-  if constexpr (ACT == BLM_ACT_GELU) {
-    return gelu_fast(z);
-  } else if constexpr (ACT == BLM_ACT_GPMIX) {
-    const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n),
-                c3 = __ldg(coef + 3 * N + n);
-    return c0 * tanhf(z) + c1 * (1.0f / (1.0f + expf(-z))) + c2 * fmaxf(z, 0.0f) + c3 * gelu_fast(z);
-  } else {
-    return z;
-  }
-}
-
-// ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
-
-// bias / q-scale / activation / residual / (hi, lo) split / stores for one 32-column chunk
-template <int ACT>
-__device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, int col0) {
-  const bool full = (col0 + 32 <= p.N);
-  if (full) {
-    if (p.bias) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += bb.x;
-        v[j + 1] += bb.y;
-        v[j + 2] += bb.z;
-        v[j + 3] += bb.w;
-      }
-    }
-    if (col0 + 32 <= p.col_scale_cols) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= p.col_scale;
-    } else if (col0 < p.col_scale_cols) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.col_scale_cols) v[j] *= p.col_scale;
-    }
-    if constexpr (ACT != BLM_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
-    }
-    if (p.resid) {
-      const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 rr = __ldg(reinterpret_cast<const float4*>(r + j));
-        v[j] += rr.x;
-        v[j + 1] += rr.y;
-        v[j + 2] += rr.z;
-        v[j + 3] += rr.w;
-      }
-    }
-    const long long off = static_cast<long long>(m) * p.ldc + col0;
-    if (p.out_f32) {
-      float* o = p.out_f32 + off;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-    if (p.out_hi) {
-      __nv_bfloat16* oh = p.out_hi + off;
-      __nv_bfloat16* ol = p.out_lo ? p.out_lo + off : nullptr;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint32_t h[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = pack_bf16x2(v[j + 2 * q], v[j + 2 * q + 1]);
-        *reinterpret_cast<uint4*>(oh + j) = make_uint4(h[0], h[1], h[2], h[3]);
-        if (ol) {
-          uint32_t l[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float a = v[j + 2 * q] - __uint_as_float(h[q] << 16);
-            const float b = v[j + 2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u);
-            l[q] = pack_bf16x2(a, b);
-          }
-          *reinterpret_cast<uint4*>(ol + j) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-      }
-    }
-  } else {
-    // ragged right edge (N not a multiple of 32): scalar path, only the last chunk of a row
-    const long long off = static_cast<long long>(m) * p.ldc + col0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {  // static register indices: v must not fall into local memory
-      const int col = col0 + j;
-      if (col >= p.N) continue;
-      float z = v[j];
-      if (p.bias) z += __ldg(p.bias + col);
-      if (col < p.col_scale_cols) z *= p.col_scale;
-      z = apply_act<ACT>(z, p.coef, p.N, col);
-      if (p.resid) z += __ldg(p.resid + static_cast<long long>(m) * p.ldr + col);
-      if (p.out_f32) p.out_f32[off + j] = z;
-      if (p.out_hi) {
-        const __nv_bfloat16 hh = __float2bfloat16_rn(z);
-        p.out_hi[off + j] = hh;
-        if (p.out_lo) p.out_lo[off + j] = __float2bfloat16_rn(z - __bfloat162float(hh));
-      }
-    }
-  }
-}
 
 struct NllState {
   float run_max;  // log2 domain: fl(max logit * log2 e)

@@ -1,0 +1,360 @@
+// Tile-fused reparameterised-weight GEMM for sm_100a  (north_star (a)).
+//
+//   C[M, N] = epilogue( A[M, K] . W~[N, K]^T ),   W~ = bf16( mu + sigma * eps ),  sigma = exp(lgstd)
+//
+// W~ never exists in HBM.  For every K block the TMA warp stages the bf16 tiles of mu and sigma
+// ([128 x 64] each, 128B-swizzled); eight generator warps read their 16-byte chunks, draw eps in
+// registers (Philox4x32-10 -> Box-Muller, or an explicit eps tensor for parity runs), form W~ in fp32,
+// round to bf16 and write it back IN PLACE over the mu tile -- same swizzled position, so the buffer TMA
+// filled is exactly the B operand `tcgen05.mma` reads; `fence.proxy.async` + an mbarrier hand it to the
+// MMA warp.  A generated element costs ~2 MUFU and ~24 issue slots, far above what one 128-row MMA
+// consumes, so the loop is W-STATIONARY: one generated B tile feeds FOUR M tiles whose fp32 accumulators
+// fill all 512 TMEM columns (4 x 128), and A tiles stream through their own TMA ring.
+//
+//   warp 0      TMA producer (mu/sigma tiles + A tiles)   warp 1    tcgen05.mma issuer (lane 0)
+//   warp 2      TMEM allocator                            warp 4-7  epilogue (fused epilogue of blm_gemm)
+//   warp 8-15   W~ generators (256 threads: row = tid / 2, four 16-byte chunks = 32 K elements each)
+//
+// Noise indexing matches blm_reparam: element (n, k) of the [N, K] tensor uses Philox counter
+// (n*K + k) / 4, lane (n*K + k) % 4 of stream `stream_id`: every rank, batch shape and code path draws
+// the same eps for the same (seed, stream).
+#include <string.h>
+
+#include "blm_gemm_common.cuh"
+#include "blm_philox.cuh"
+
+namespace blm {
+
+constexpr int kSBN = 128;        // N tile
+constexpr int kSMT = 4;          // M tiles per work item (accumulators resident in TMEM)
+constexpr int kSAStages = 6;     // A ring: 6 x 16 KB
+constexpr int kSWStages = 3;     // (mu | sigma) ring: 3 x 32 KB
+constexpr int kSThreads = 512;
+constexpr int kSGenWarp0 = 8;
+constexpr int kSGenThreads = 256;
+constexpr int kSTile = 128 * 64 * 2;  // bytes of one [128 x 64] bf16 tile
+
+struct SampledParams {
+  GemmParams g;          // A tensor map in g.tmA[0]; epilogue fields; M, N, m_tiles, n_tiles
+  CUtensorMap tmMu;      // [N, K] bf16 mean, box 128 x 64
+  CUtensorMap tmSig;     // [N, K] bf16 sigma = exp(lgstd), box 128 x 64
+  const float* eps;      // [N, K] dense fp32 (BLM_EPS_PTR) or null
+  int eps_mode;
+  unsigned long long seed, stream_id;
+  int K, kblocks, m_groups;
+};
+
+struct SampledSmem {
+  static constexpr int kAOff = 0;
+  static constexpr int kWOff = kSAStages * kSTile;
+  static constexpr int kBarOff = kWOff + kSWStages * 2 * kSTile;
+  // a_full[6] a_empty[6] w_full[3] w_ready[3] w_empty[3] t_full t_empty + tmem slot
+  static constexpr int kBytes = kBarOff + (2 * kSAStages + 3 * kSWStages + 2) * 8 + 16;
+  static constexpr int kDynBytes = kBytes + 1024;
+};
+
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+template <int ACT>
+__global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid_constant__ SampledParams p) {
+  using L = SampledSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* a_empty = a_full + kSAStages;
+  uint64_t* w_full = a_empty + kSAStages;    // TMA landed mu | sigma
+  uint64_t* w_ready = w_full + kSWStages;    // generators wrote W~ over mu
+  uint64_t* w_empty = w_ready + kSWStages;   // MMAs that read W~ retired
+  uint64_t* t_full = w_empty + kSWStages;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_works = p.g.n_tiles * p.m_groups;
+  const bool sampling = p.eps_mode != BLM_EPS_NONE;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.g.tmA[0]);
+    tma_prefetch_desc(&p.tmMu);
+    tma_prefetch_desc(&p.tmSig);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kSWStages; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_ready[s], kSGenThreads / 32);  // one arrive per generator warp
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA: mu | sigma tiles, A tiles
+    if (lane == 0) {
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      for (int w = blockIdx.x; w < num_works; w += gridDim.x) {
+        const int m_group = w / p.g.n_tiles;
+        const int n_tile = w - m_group * p.g.n_tiles;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&w_empty[sw], pw ^ 1u);
+          uint8_t* wt = smem + L::kWOff + sw * 2 * kSTile;
+          mbar_arrive_expect_tx(&w_full[sw], sampling ? 2 * kSTile : kSTile);
+          tma_load_2d(wt, &p.tmMu, &w_full[sw], kb * kBK, n_tile * kSBN, kEvictLast);
+          if (sampling) tma_load_2d(wt + kSTile, &p.tmSig, &w_full[sw], kb * kBK, n_tile * kSBN, kEvictLast);
+          if (++sw == kSWStages) {
+            sw = 0;
+            pw ^= 1u;
+          }
+          for (int mt = 0; mt < kSMT; ++mt) {
+            mbar_wait(&a_empty[sa], pa ^ 1u);
+            mbar_arrive_expect_tx(&a_full[sa], kSTile);
+            tma_load_2d(smem + L::kAOff + sa * kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK,
+                        (m_group * kSMT + mt) * kBM, kEvictNormal);
+            if (++sa == kSAStages) {
+              sa = 0;
+              pa ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kSBN);
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0, pt = 0;
+      for (int w = blockIdx.x; w < num_works; w += gridDim.x) {
+        mbar_wait(t_empty, pt ^ 1u);  // epilogue has drained all four accumulators
+        tcgen05_fence_after();
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&w_ready[sw], pw);
+          tcgen05_fence_after();
+          const uint64_t db = umma_desc_sw128(smem_u32(smem + L::kWOff + sw * 2 * kSTile));
+          for (int mt = 0; mt < kSMT; ++mt) {
+            mbar_wait(&a_full[sa], pa);
+            tcgen05_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + L::kAOff + sa * kSTile));
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kSBN);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&a_empty[sa]);
+            if (++sa == kSAStages) {
+              sa = 0;
+              pa ^= 1u;
+            }
+          }
+          umma_commit(&w_empty[sw]);  // the generated tile may be overwritten once these MMAs retire
+          if (++sw == kSWStages) {
+            sw = 0;
+            pw ^= 1u;
+          }
+        }
+        umma_commit(t_full);
+        pt ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ---------------------------------------------------------------- epilogue
+    const int lane_grp = warp & 3;
+    uint32_t pt = 0;
+    for (int w = blockIdx.x; w < num_works; w += gridDim.x) {
+      const int m_group = w / p.g.n_tiles;
+      const int n_tile = w - m_group * p.g.n_tiles;
+      mbar_wait(t_full, pt);
+      pt ^= 1u;
+      tcgen05_fence_after();
+      constexpr int kChunks = kSMT * kSBN / 32;  // 16 chunks of 32 columns over the 512 TMEM columns
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+      float va[32], vb[32];
+      __syncwarp();
+      tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; c += 2) {
+        tmem_ld_wait();
+        __syncwarp();
+        tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 1) * 32), vb);
+        {
+          const int mt = c / (kSBN / 32), cc = c % (kSBN / 32);
+          const int m = (m_group * kSMT + mt) * kBM + lane_grp * 32 + lane;
+          const int col0 = n_tile * kSBN + cc * 32;
+          if (m < p.g.M && col0 < p.g.N) store_chunk<ACT>(p.g, va, m, col0);
+        }
+        tmem_ld_wait();
+        __syncwarp();
+        if (c + 2 < kChunks) {
+          tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), va);
+        } else {
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(t_empty);
+        }
+        {
+          const int mt = (c + 1) / (kSBN / 32), cc = (c + 1) % (kSBN / 32);
+          const int m = (m_group * kSMT + mt) * kBM + lane_grp * 32 + lane;
+          const int col0 = n_tile * kSBN + cc * 32;
+          if (m < p.g.M && col0 < p.g.N) store_chunk<ACT>(p.g, vb, m, col0);
+        }
+      }
+    }
+  } else if (warp >= kSGenWarp0) {
+    // ---------------------------------------------------------------- W~ generators
+    const int gt = threadIdx.x - kSGenWarp0 * 32;  // 0..255
+    const int r = gt >> 1;                          // row of the B tile (output column n)
+    const int half = gt & 1;                        // 16-byte chunks [4*half, 4*half + 4) of the row
+    int sw = 0;
+    uint32_t pw = 0;
+    for (int w = blockIdx.x; w < num_works; w += gridDim.x) {
+      const int m_group = w / p.g.n_tiles;
+      const int n_tile = w - m_group * p.g.n_tiles;
+      const int n = n_tile * kSBN + r;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&w_full[sw], pw);
+        if (sampling) {
+          uint8_t* mu_row = smem + L::kWOff + sw * 2 * kSTile + r * 128;
+          const uint8_t* sg_row = mu_row + kSTile;
+          // rows / columns past the tensor edge were zero-filled by TMA (mu = sigma = 0 -> W~ = 0)
+          const long long dense0 = static_cast<long long>(n) * p.K + kb * kBK + half * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int pos = ((half * 4 + q) ^ (r & 7)) * 16;  // TMA SWIZZLE_128B: chunk index XOR (row % 8)
+            const uint4 m = *reinterpret_cast<const uint4*>(mu_row + pos);
+            const uint4 s = *reinterpret_cast<const uint4*>(sg_row + pos);
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, sw4[4] = {s.x, s.y, s.z, s.w};
+            float e[8];
+            if (p.eps_mode == BLM_EPS_PHILOX) {
+              const float4 z0 = philox_normal4(p.seed, p.stream_id, static_cast<uint64_t>(dense0 / 4 + 2 * q));
+              const float4 z1 = philox_normal4(p.seed, p.stream_id, static_cast<uint64_t>(dense0 / 4 + 2 * q + 1));
+              e[0] = z0.x; e[1] = z0.y; e[2] = z0.z; e[3] = z0.w;
+              e[4] = z1.x; e[5] = z1.y; e[6] = z1.z; e[7] = z1.w;
+            } else {
+              const bool ok = n < p.g.N && kb * kBK + half * 32 + 8 * q + 8 <= p.K;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) e[j] = ok ? __ldg(p.eps + dense0 + 8 * q + j) : 0.0f;
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float w0 = fmaf(bf16lo_to_f32(sw4[j]), e[2 * j], bf16lo_to_f32(mw[j]));
+              const float w1 = fmaf(bf16hi_to_f32(sw4[j]), e[2 * j + 1], bf16hi_to_f32(mw[j]));
+              o[j] = pack_bf16x2(w0, w1);
+            }
+            *reinterpret_cast<uint4*>(mu_row + pos) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_ready[sw]);
+        if (++sw == kSWStages) {
+          sw = 0;
+          pw ^= 1u;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int gemm_sampled_init() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_kernel<BLM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SampledSmem::kDynBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_kernel<BLM_ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SampledSmem::kDynBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_kernel<BLM_ACT_GPMIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SampledSmem::kDynBytes));
+  return BLM_OK;
+}
+
+}  // namespace blm
+
+extern "C" int blm_gemm_sampled(const blm_gemm_sampled_desc* d, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(d != nullptr, BLM_ERR_ARG, "null descriptor");
+  BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
+  BLM_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->M < (1ll << 31) && d->N < (1ll << 31), BLM_ERR_SHAPE,
+              "bad shape M=%lld N=%lld K=%lld", (long long)d->M, (long long)d->N, (long long)d->K);
+  BLM_REQUIRE(d->A && d->mu, BLM_ERR_ARG, "null A / mu");
+  BLM_REQUIRE(d->N % 1 == 0, BLM_ERR_SHAPE, "N");
+  BLM_REQUIRE((d->K % 8) == 0, BLM_ERR_SHAPE, "K=%lld must be a multiple of 8", (long long)d->K);
+  BLM_REQUIRE(d->eps_mode >= BLM_EPS_NONE && d->eps_mode <= BLM_EPS_PHILOX, BLM_ERR_ARG, "bad eps_mode %d", d->eps_mode);
+  BLM_REQUIRE(d->eps_mode == BLM_EPS_NONE || d->sigma, BLM_ERR_ARG, "sampling needs sigma");
+  BLM_REQUIRE(d->eps_mode != BLM_EPS_PTR || d->eps, BLM_ERR_ARG, "BLM_EPS_PTR needs eps");
+  BLM_REQUIRE(aligned16(d->eps), BLM_ERR_ALIGN, "eps must be 16-byte aligned");
+  BLM_REQUIRE(d->eps_mode != BLM_EPS_PTR || ((d->K % 8) == 0), BLM_ERR_SHAPE, "K");
+  BLM_REQUIRE(d->out_f32 || d->out_hi, BLM_ERR_ARG, "no output buffer");
+  BLM_REQUIRE(!d->out_lo || d->out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
+  BLM_REQUIRE((d->ldc % 8) == 0 && d->ldc >= d->N, BLM_ERR_ALIGN, "ldc=%lld", (long long)d->ldc);
+  BLM_REQUIRE(aligned16(d->out_f32) && aligned16(d->out_hi) && aligned16(d->out_lo) && aligned16(d->resid),
+              BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
+  BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld", (long long)d->ldr);
+  BLM_REQUIRE(d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX, BLM_ERR_ARG,
+              "unknown activation %d", d->act);
+  BLM_REQUIRE(d->act != BLM_ACT_GPMIX || d->coef, BLM_ERR_ARG, "GP-mix epilogue needs coef");
+
+  SampledParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = encode_tmap_bf16(&p.g.tmA[0], d->A, d->M, d->K, d->lda, kBM);
+  if (rc != BLM_OK) return rc;
+  rc = encode_tmap_bf16(&p.tmMu, d->mu, d->N, d->K, d->ldmu, kSBN);
+  if (rc != BLM_OK) return rc;
+  rc = encode_tmap_bf16(&p.tmSig, d->sigma ? d->sigma : d->mu, d->N, d->K, d->sigma ? d->K : d->ldmu, kSBN);
+  if (rc != BLM_OK) return rc;
+  p.g.M = static_cast<int>(d->M);
+  p.g.N = static_cast<int>(d->N);
+  p.g.m_tiles = static_cast<int>((d->M + kBM - 1) / kBM);
+  p.g.n_tiles = static_cast<int>((d->N + kSBN - 1) / kSBN);
+  p.g.bias = d->bias;
+  p.g.coef = d->coef;
+  p.g.col_scale = 1.0f;
+  p.g.col_scale_cols = 0;
+  p.g.resid = d->resid;
+  p.g.ldr = d->ldr;
+  p.g.out_f32 = d->out_f32;
+  p.g.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
+  p.g.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
+  p.g.ldc = d->ldc;
+  p.eps = d->eps;
+  p.eps_mode = d->eps_mode;
+  p.seed = d->seed;
+  p.stream_id = d->stream_id;
+  p.K = static_cast<int>(d->K);
+  p.kblocks = static_cast<int>((d->K + kBK - 1) / kBK);
+  p.m_groups = (p.g.m_tiles + kSMT - 1) / kSMT;
+  const int works = p.g.n_tiles * p.m_groups;
+  const int grid = works < num_sms() ? works : num_sms();
+  cudaStream_t st = as_stream(stream);
+  switch (d->act) {
+    case BLM_ACT_NONE:
+      gemm_sampled_kernel<BLM_ACT_NONE><<<grid, kSThreads, SampledSmem::kDynBytes, st>>>(p);
+      break;
+    case BLM_ACT_GELU:
+      gemm_sampled_kernel<BLM_ACT_GELU><<<grid, kSThreads, SampledSmem::kDynBytes, st>>>(p);
+      break;
+    default:
+      gemm_sampled_kernel<BLM_ACT_GPMIX><<<grid, kSThreads, SampledSmem::kDynBytes, st>>>(p);
+  }
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}

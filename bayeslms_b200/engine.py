@@ -115,6 +115,7 @@ class _Plan:
             if layer.kind == "bayes_ffn":
                 L["w2"], L["b2"] = sp(layer.linear2.weight_mean), None
                 L["w2_mu"], L["w2_ls"] = layer.linear2.weight_mean.detach(), layer.linear2.weight_lgstd.detach()
+                L["w2_sigma"] = ops.sigma_bf16(layer.linear2.weight_lgstd)  # sample-independent, cached
             else:
                 L["w2"], L["b2"] = sp(layer.linear2.weight), layer.linear2.bias.detach().float().contiguous()
             for n in ("norm1", "norm2"):
@@ -183,6 +184,7 @@ class _TmRun:
         self.nhead = model.nhead
         self.M = batch.n_tokens
         self.dev = plan.device
+        self.fused_sampling = False
 
     def f32(self, cols):
         return torch.empty(self.M, cols, dtype=torch.float32, device=self.dev)
@@ -214,6 +216,18 @@ class _TmRun:
     def part_d(self, L, x1_32, h: Split, w2: Split):
         y = self.f32(self.d)
         ops.gemm(h, w2, prec=self.prec, bias=L["b2"], resid=x1_32, out_f32=y, tag="ffn2")
+        g, b, eps = L["norm2"]
+        return ops.layernorm(y, g, b, eps, prec=self.prec)
+
+    # part D with the tile-fused sampled GEMM: W~ is generated inside the kernel, never stored
+    def part_d_fused(self, L, x1_32, h: Split, sample: Sample, eps_value, seed):
+        y = self.f32(self.d)
+        if isinstance(sample, dict):
+            ops.gemm_sampled(h, L["w2"].hi, L["w2_sigma"], eps=eps_value.to(self.dev).float(), resid=x1_32, out_f32=y,
+                             tag="ffn2")
+        else:
+            ops.gemm_sampled(h, L["w2"].hi, L["w2_sigma"], seed=seed, stream_id=_stream_id(_TID["ffn_w2"], int(sample)),
+                             resid=x1_32, out_f32=y, tag="ffn2")
         g, b, eps = L["norm2"]
         return ops.layernorm(y, g, b, eps, prec=self.prec)
 
@@ -261,6 +275,8 @@ class _TmRun:
         w2 = L["w2"]
         if kind == "bayes_ffn" and sample is not None:
             e = sample.get("layer0") if isinstance(sample, dict) else None
+            if self.fused_sampling and self.prec == "bf16":
+                return self.part_d_fused(L, x1_32, h, sample, e, seed)
             _, w2 = _sampled(L["w2_mu"], L["w2_ls"], _TID["ffn_w2"], sample, e, seed, self.prec)
         return self.part_d(L, x1_32, h, w2)
 
@@ -321,12 +337,15 @@ def _normalise_samples(K, seed, eps_list) -> Optional[List[Sample]]:
 @torch.no_grad()
 def transformer_score(model, batch: PackedBatch, *, K: int = 0, seed: Optional[int] = None,
                       eps_list: Optional[Sequence[dict]] = None, prec: str = "bf16",
-                      return_token_nll: bool = False):
+                      return_token_nll: bool = False, fused_sampling: bool = False):
     """Per-hypothesis NLL [n_hyp] (fp32, device).  Posterior mean unless ``eps_list`` (injected noise)
     or ``K`` + ``seed`` (device Philox noise) ask for sampling; K samples are combined per token as
     the Monte-Carlo predictive -log(1/K sum_k p_k)."""
     plan = plan_for(model, prec)
     run = _TmRun(model, plan, batch)
+    # fused_sampling: build the sampled FFN weight tile by tile inside the GEMM (blm_gemm_sampled, bf16
+    # mode) instead of materialising it with blm_reparam -- same noise, measured slower on B200 (DESIGN.md)
+    run.fused_sampling = fused_sampling
     samples = _normalise_samples(K, seed, eps_list)
     upto = _first_sampled_part(model) if samples else None
     carry = run.prefix(upto)

@@ -16,7 +16,8 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_GPMIX, ACT_NONE, EPS_NONE, EPS_PHILOX, EPS_PTR, GemmDesc, VocabNllDesc,
+from ._lib import (ACT_GELU, ACT_GPMIX, ACT_NONE, EPS_NONE, EPS_PHILOX, EPS_PTR, GemmDesc, GemmSampledDesc,
+                   VocabNllDesc,
                    check, lib)
 
 PRECISIONS = ("bf16", "bf16x3")
@@ -142,6 +143,55 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     d.ldc = ldc if ldc is not None else N
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
+
+
+def sigma_bf16(lgstd: torch.Tensor) -> torch.Tensor:
+    """bf16(exp(lgstd)), the cached sample-independent scale of the fused sampled GEMM."""
+    lgstd = lgstd.detach().contiguous().float()
+    out = torch.empty(lgstd.shape, dtype=torch.bfloat16, device=lgstd.device)
+    with _op("sigma_bf16", 1):
+        check(lib().blm_sigma_bf16(_ptr(lgstd), _ptr(out), lgstd.numel(), _stream()), "blm_sigma_bf16")
+    return out
+
+
+def gemm_sampled(a: Split, mu: torch.Tensor, sigma: Optional[torch.Tensor], *, eps: Optional[torch.Tensor] = None,
+                 seed: Optional[int] = None, stream_id: int = 0, bias: Optional[torch.Tensor] = None,
+                 act: int = ACT_NONE, coef: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+                 out_f32: Optional[torch.Tensor] = None, out: Optional[Split] = None, tag: str = "sampled"):
+    """``epilogue(a @ bf16(mu + sigma * eps).T)`` with the sampled weight built tile by tile inside the
+    kernel.  mu / sigma: bf16 [N, K] (sigma dense).  eps: explicit fp32 tensor, Philox(seed, stream_id),
+    or none (mean)."""
+    x = a.hi
+    M, K = x.shape
+    N = mu.shape[0]
+    assert mu.shape[1] == K and mu.stride(1) == 1 and mu.dtype == torch.bfloat16
+    mode = EPS_PTR if eps is not None else (EPS_PHILOX if seed is not None else EPS_NONE)
+    d = GemmSampledDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda = x.data_ptr(), x.stride(0)
+    d.mu, d.ldmu = mu.data_ptr(), mu.stride(0)
+    if sigma is not None:
+        assert sigma.dtype == torch.bfloat16 and sigma.is_contiguous() and sigma.shape == mu.shape
+        d.sigma = sigma.data_ptr()
+    if eps is not None:
+        eps = eps.contiguous().float()
+        d.eps = eps.data_ptr()
+    d.eps_mode, d.act, d.seed, d.stream_id = mode, act, int(seed or 0), int(stream_id)
+    d.bias, d.coef = _ptr(bias), _ptr(coef)
+    if resid is not None:
+        assert resid.dtype == torch.float32 and resid.stride(1) == 1
+        d.resid, d.ldr = _ptr(resid), resid.stride(0)
+    ldc = None
+    for t in (out_f32, None if out is None else out.hi, None if out is None else out.lo):
+        if t is not None:
+            assert t.stride(1) == 1 and (ldc is None or ldc == t.stride(0))
+            ldc = t.stride(0)
+    d.out_f32 = _ptr(out_f32)
+    d.out_hi = _ptr(None if out is None else out.hi)
+    d.out_lo = _ptr(None if out is None else out.lo)
+    d.ldc = ldc if ldc is not None else N
+    with _op("gemm_sampled:" + tag, 1, 2.0 * M * N * K):
+        check(lib().blm_gemm_sampled(C.byref(d), _stream()), "blm_gemm_sampled")
 
 
 _nll_ws = {}

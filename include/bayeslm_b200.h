@@ -108,6 +108,43 @@ typedef struct blm_gemm_desc {
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
 
+/* ------------------------------------------------- tile-fused sampled GEMM (a)
+ * C[M,N] = epilogue( A[M,K] * W~[N,K]^T ),  W~ = bf16( mu + sigma * eps ),  sigma = exp(lgstd)
+ * built tile by tile in shared memory: TMA stages the bf16 mu and sigma tiles, generator warps
+ * draw eps (Philox4x32-10 in registers, or an explicit tensor), overwrite the mu tile with W~
+ * in place and hand it to tcgen05.mma; W~ never reaches HBM.  Noise indexing is identical to
+ * blm_reparam(seed, stream_id) on the dense [N, K] tensor.  bf16 operands, fp32 accumulation.
+ * BLM_EPS_NONE degenerates to a GEMM on mu.  Epilogue as blm_gemm (no q-scale).
+ * mu / sigma are the bf16 copies the caller caches once per checkpoint (blm_split_bf16,
+ * blm_sigma_bf16): both are sample-independent.
+ * replaces: BayesLinear.forward model.py:1098-1129; GPNN weights model.py:1882-1885;
+ *           Bayesian embedding model.py:1286-1290.
+ * needs:    K % 8 == 0, lda / ldmu / ldc % 8 == 0, sigma dense [N, K], 16-B aligned pointers. */
+typedef struct blm_gemm_sampled_desc {
+  int64_t M, N, K;
+  const blm_bf16* A;     /* [M, K] bf16, leading dimension lda                  */
+  int64_t lda;
+  const blm_bf16* mu;    /* [N, K] bf16 mean, leading dimension ldmu            */
+  int64_t ldmu;
+  const blm_bf16* sigma; /* [N, K] bf16 exp(lgstd), dense (null with EPS_NONE)  */
+  const float* eps;      /* [N, K] fp32 dense (BLM_EPS_PTR)                     */
+  int32_t eps_mode;      /* BLM_EPS_*                                           */
+  int32_t act;           /* BLM_ACT_*                                           */
+  uint64_t seed, stream_id;
+  const float* bias;     /* [N] or null                                         */
+  const float* coef;     /* [4, N] (BLM_ACT_GPMIX)                              */
+  const float* resid;    /* [M, N] fp32 or null                                 */
+  int64_t ldr;
+  float* out_f32;
+  blm_bf16* out_hi;
+  blm_bf16* out_lo;
+  int64_t ldc;
+} blm_gemm_sampled_desc;
+
+/* sigma[i] = bf16(exp(lgstd[i])): the sample-independent scale the fused GEMM multiplies eps by. */
+int blm_sigma_bf16(const float* lgstd, blm_bf16* sigma, int64_t n, blm_stream stream);
+int blm_gemm_sampled(const blm_gemm_sampled_desc* d, blm_stream stream);
+
 /* ------------------------------------------- output projection + NLL (d)
  * nll[m] = logsumexp_v( h[m,:] . E[v,:] + b[v] ) - ( h[m,:] . E[t_m,:] + b[t_m] )
  * with the [M, V] logits living only in tensor memory: the vocabulary is

@@ -149,3 +149,32 @@ def test_scorer_files_end_to_end(golden, tmp_path):
     assert keys[:4] == ["utt-a_0-1", "utt-a_0-2", "utt-a_0-3", "utt-a_1-1"]
     got = [float(l.split()[1]) for l in lines]
     assert max(abs(a - b) for a, b in zip(got, rec["tm_scores"])) < 1e-3 + 5e-5
+
+
+def test_fused_sampled_gemm_bit_exact_and_model_level(golden):
+    """blm_gemm_sampled: (i) kernel level, bit-identical to bf16(mu + sigma*eps) fed to the plain GEMM, for
+    injected eps and for device Philox noise; (ii) model level, same scores as the materialised path."""
+    from bayeslms_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 700, 136, 200
+    a = torch.randn(M, K, device=DEV) * 0.5
+    mu = (torch.randn(N, K, device=DEV) * 0.05)
+    ls = torch.rand(N, K, device=DEV) * -3.0 - 2.0
+    A, mu_b, sg_b = ops.split(a, "bf16"), ops.split(mu, "bf16").hi, ops.sigma_bf16(ls)
+    assert torch.equal(sg_b, torch.exp(ls).to(torch.bfloat16))
+    bias = torch.randn(N, device=DEV)
+    for mode in ("ptr", "philox"):
+        eps = torch.randn(N, K, device=DEV) if mode == "ptr" else ops.philox_normal(11, 4, N * K, DEV).view(N, K)
+        out = torch.empty(M, N, device=DEV)
+        ops.gemm_sampled(A, mu_b, sg_b, eps=eps if mode == "ptr" else None, seed=None if mode == "ptr" else 11,
+                         stream_id=4, bias=bias, out_f32=out)
+        wt = torch.addcmul(mu_b.float(), sg_b.float(), eps).to(torch.bfloat16)
+        ref = torch.empty(M, N, device=DEV)
+        ops.gemm(A, ops.Split(wt), prec="bf16", bias=bias, out_f32=ref)
+        assert torch.equal(out, ref), mode
+    rec = golden("bayes_tm_FFN.pt")
+    net = load_golden_model(rec, DEV)
+    batch, ins, tgts = _batch_from_tb(rec["x"], DEV)
+    a1 = net.score(batch, K=2, seed=5, prec="bf16").cpu()
+    a2 = net.score(batch, K=2, seed=5, prec="bf16", fused_sampling=True).cpu()
+    assert (a1 - a2).abs().max().item() < 2e-2   # differ only by bf16 rounding of mu before the noise is added
