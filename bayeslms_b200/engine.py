@@ -138,6 +138,16 @@ class _Plan:
             })
 
 
+def _scaled_decoder(plan: _Plan, model, scale: float):
+    """(split(scale * E), scale * b) for logit interpolation, cached per scale."""
+    cache = plan.__dict__.setdefault("_scaled", {})
+    if scale not in cache:
+        with torch.no_grad():
+            cache[scale] = (ops.split(model.decoder.weight.detach().float() * scale, plan.prec),
+                            (model.decoder.bias.detach().float() * scale).contiguous())
+    return cache[scale]
+
+
 def plan_for(model, prec: str) -> _Plan:
     cache = model.__dict__.setdefault("_blm_plans", {})
     p = cache.get(prec)
@@ -337,7 +347,8 @@ def _normalise_samples(K, seed, eps_list) -> Optional[List[Sample]]:
 @torch.no_grad()
 def transformer_score(model, batch: PackedBatch, *, K: int = 0, seed: Optional[int] = None,
                       eps_list: Optional[Sequence[dict]] = None, prec: str = "bf16",
-                      return_token_nll: bool = False, fused_sampling: bool = False):
+                      return_token_nll: bool = False, fused_sampling: bool = False,
+                      inter_model=None, inter_alpha: float = 0.8):
     """Per-hypothesis NLL [n_hyp] (fp32, device).  Posterior mean unless ``eps_list`` (injected noise)
     or ``K`` + ``seed`` (device Philox noise) ask for sampling; K samples are combined per token as
     the Monte-Carlo predictive -log(1/K sum_k p_k)."""
@@ -349,14 +360,27 @@ def transformer_score(model, batch: PackedBatch, *, K: int = 0, seed: Optional[i
     samples = _normalise_samples(K, seed, eps_list)
     upto = _first_sampled_part(model) if samples else None
     carry = run.prefix(upto)
+    E, dec_b, extra = plan.E, plan.dec_b, ()
+    if inter_model is not None:
+        # logits = alpha * o1 + (1 - alpha) * o2 (score.py:157-163) as ONE vocabulary sweep: the second
+        # model's hidden states and (1-alpha)-scaled embedding are extra K segments of the same GEMM
+        plan2 = plan_for(inter_model, prec)
+        run2 = _TmRun(inter_model, plan2, batch)
+        xs2 = run2.hidden(run2.prefix(None), None, None, None)
+        E, b1 = _scaled_decoder(plan, model, float(inter_alpha))
+        E2, b2 = _scaled_decoder(plan2, inter_model, 1.0 - float(inter_alpha))
+        bkey = ("bias", id(plan2), float(inter_alpha))
+        if bkey not in plan.__dict__.setdefault("_scaled", {}):
+            plan._scaled[bkey] = (b1 + b2).contiguous()
+        dec_b, extra = plan._scaled[bkey], ((xs2, E2),)
     if not samples:
         xs = run.hidden(carry, None, None, None)
-        tok_nll = ops.vocab_nll(xs, plan.E, plan.dec_b, batch.targets, prec=prec)
+        tok_nll = ops.vocab_nll(xs, E, dec_b, batch.targets, prec=prec, extra=extra)
     else:
         per = torch.empty(len(samples), batch.n_tokens, dtype=torch.float32, device=plan.device)
         for k, s in enumerate(samples):
             xs = run.hidden(carry, upto, s if upto else None, seed)
-            ops.vocab_nll(xs, plan.E, plan.dec_b, batch.targets, prec=prec, out=per[k])
+            ops.vocab_nll(xs, E, dec_b, batch.targets, prec=prec, out=per[k], extra=extra)
             if upto is None:  # deterministic model: all samples identical
                 per[1:] = per[0]
                 break

@@ -113,15 +113,24 @@ class Rescorer:
     """Scores tokenised n-best lists with one model replica on one GPU."""
 
     def __init__(self, model, *, prec: str = "bf16", K: int = 0, seed: Optional[int] = None,
-                 max_tokens: int = 65536, eps_list=None):
+                 max_tokens: int = 65536, eps_list=None, inter_model=None, inter_alpha: float = 0.8):
         self.model, self.prec, self.K, self.seed, self.max_tokens = model, prec, K, seed, max_tokens
         self.eps_list = eps_list
+        self.inter_model, self.inter_alpha = inter_model, inter_alpha
+        if inter_model is not None and model.family.endswith("lstm"):
+            raise NotImplementedError("logit interpolation is wired for the Transformer families only")
         self.device = next(model.parameters()).device
         self.is_rnn = model.family.endswith("lstm")
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._stage = None   # pinned int32 staging for ids (grown on demand, reused across calls)
         self._out = None     # pinned fp32 landing buffer for the scores
+
+    def _score(self, batch):
+        kw = dict(K=self.K, seed=self.seed, eps_list=self.eps_list, prec=self.prec)
+        if self.inter_model is not None:
+            kw.update(inter_model=self.inter_model, inter_alpha=self.inter_alpha)
+        return self.model.score(batch, **kw)
 
     # hyps: list of (input_ids, target_ids); returns fp32 numpy [n_hyp]
     def score_transformer(self, hyps: Sequence[Tuple[Sequence[int], Sequence[int]]]) -> np.ndarray:
@@ -130,7 +139,7 @@ class Rescorer:
         for a, b in _chunks_by_tokens(lengths, self.max_tokens):
             batch = PackedBatch.from_lists([h[0] for h in hyps[a:b]], [h[1] for h in hyps[a:b]], self.device)
             self.h2d_bytes += batch.h2d_bytes
-            outs.append(self.model.score(batch, K=self.K, seed=self.seed, eps_list=self.eps_list, prec=self.prec))
+            outs.append(self._score(batch))
         res = torch.cat(outs) if outs else torch.empty(0, device=self.device)
         host = res.cpu()
         self.d2h_bytes += host.numel() * 4
@@ -159,7 +168,7 @@ class Rescorer:
             at += n
             batch = PackedBatch(dev[:M], dev[M:2 * M], dev[2 * M:3 * M], dev[3 * M:], int(lengths[a:b].max()), M, b - a)
             self.h2d_bytes += batch.h2d_bytes
-            outs.append(self.model.score(batch, K=self.K, seed=self.seed, eps_list=self.eps_list, prec=self.prec))
+            outs.append(self._score(batch))
         res = torch.cat(outs) if outs else torch.empty(0, device=self.device)
         if self._out is None or self._out.numel() < n_hyp:
             self._out = torch.empty(max(n_hyp, 1 << 12), dtype=torch.float32, pin_memory=True)
@@ -176,14 +185,15 @@ class Rescorer:
 def score_nbest(model, nbest: "OrderedDict[str, List[str]]", vocab: Dict[str, int], *, prec: str = "bf16",
                 K: int = 0, seed: Optional[int] = None, max_tokens: int = 65536, eps_list=None,
                 session_size: Optional[int] = None, rank: int = 0, world: int = 1, group=None,
-                rescorer: Optional[Rescorer] = None):
+                rescorer: Optional[Rescorer] = None, inter_model=None, inter_alpha: float = 0.8):
     """Score every hypothesis; returns {utt: [(hyp, score), ...]} in input order (score.py:206-280).
 
     With ``world > 1`` each rank scores its shard and the full result is assembled on every rank
     by one all-gather of the fp32 score vector.  ``session_size`` groups consecutive utterances
     into LSTM sessions (None = the whole list is one session, like one reference JOB).
     """
-    rs = rescorer or Rescorer(model, prec=prec, K=K, seed=seed, max_tokens=max_tokens, eps_list=eps_list)
+    rs = rescorer or Rescorer(model, prec=prec, K=K, seed=seed, max_tokens=max_tokens, eps_list=eps_list,
+                              inter_model=inter_model, inter_alpha=inter_alpha)
     keys = list(nbest.keys())
     tokenised = [[ids_for(h, vocab) for h in nbest[k]] for k in keys]
     counts = [len(u) for u in tokenised]
@@ -264,8 +274,9 @@ def main(argv=None) -> int:
     for pth in (args.nbest_list, args.vocabulary, args.model_path):
         if not os.path.exists(pth):
             raise FileNotFoundError(pth)
-    if args.interpolation_flag == 1:
-        raise NotImplementedError("logit interpolation (--interpolation_flag 1) is listed as next in SURVEY.md 8f")
+    if args.interpolation_flag == 1 and (args.model != "Transformer" or not args.inter_path):
+        raise NotImplementedError("--interpolation_flag 1 needs --model Transformer and an explicit --inter_path "
+                                  "(the reference overwrites the flag with a cluster path, score.py:451-455)")
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
@@ -276,10 +287,18 @@ def main(argv=None) -> int:
     net = models.build_model(args, len(vocab))
     load_checkpoint(net, args.model_path)
     net = net.cuda().eval()
+    net2 = None
+    if args.interpolation_flag == 1:
+        # the second model is the standard Transformer, tied, same sizes (score.py:385-410)
+        net2 = models.BayesTransformerModel(len(vocab), args.emsize, args.nhead, args.nhid, args.nlayers, 0.5, True,
+                                            "none")
+        load_checkpoint(net2, args.inter_path)
+        net2 = net2.cuda().eval()
     nbest = load_nbest(args.nbest_list)
     res = score_nbest(net, nbest, vocab, prec=args.precision, K=args.num_samples,
                       seed=args.seed if args.num_samples else None, max_tokens=args.max_tokens,
-                      session_size=args.session_size or None, rank=rank, world=world)
+                      session_size=args.session_size or None, rank=rank, world=world, inter_model=net2,
+                      inter_alpha=args.inter_alpha)
     if rank == 0:
         write_scores(res, args.outfile)
     if world > 1:

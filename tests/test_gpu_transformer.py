@@ -178,3 +178,22 @@ def test_fused_sampled_gemm_bit_exact_and_model_level(golden):
     a1 = net.score(batch, K=2, seed=5, prec="bf16").cpu()
     a2 = net.score(batch, K=2, seed=5, prec="bf16", fused_sampling=True).cpu()
     assert (a1 - a2).abs().max().item() < 2e-2   # differ only by bf16 rounding of mu before the noise is added
+
+
+def test_logit_interpolation_matches_oracle(golden):
+    """score.py:157-163: logits = alpha * o1 + (1 - alpha) * o2 with a second (standard) model, done here as
+    extra K segments of one vocabulary sweep."""
+    from collections import OrderedDict
+    rec, rec2 = golden("gauss_tm_3.pt"), golden("bayes_tm_none.pt")
+    net, net2 = load_golden_model(rec, DEV), load_golden_model(rec2, DEV)
+    batch, ins, tgts = _batch_from_tb(rec["x"], DEV)
+    for alpha in (0.8, 0.3):
+        got = net.score(batch, prec="bf16x3", inter_model=net2, inter_alpha=alpha).cpu()
+        want = []
+        with torch.no_grad():
+            for i, t in zip(ins, tgts):
+                x = torch.tensor(i).view(-1, 1)
+                lg = alpha * O.transformer_forward(rec["state_dict"], x, O.Config(rec["cfg"])) + \
+                    (1. - alpha) * O.transformer_forward(rec2["state_dict"], x, O.Config(rec2["cfg"]))
+                want.append(O.sentence_nll(lg, torch.tensor(t)))
+        assert (got - torch.tensor(want)).abs().max().item() < 1e-3, alpha
