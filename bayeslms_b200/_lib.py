@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbayeslm_b200.so")
 BLM_OK = 0
 ERR_NAMES = {-1: "BLM_ERR_SHAPE", -2: "BLM_ERR_ALIGN", -3: "BLM_ERR_ARCH", -4: "BLM_ERR_CUDA", -5: "BLM_ERR_ARG"}
 
-ACT_NONE, ACT_GELU, ACT_GPMIX = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD = 0, 1, 2, 3
 EPS_NONE, EPS_PTR, EPS_PHILOX = 0, 1, 2
 MAX_SEG = 6
 
@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("col_scale", C.c_float), ("col_scale_cols", C.c_int32),
         ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
+        ("lse", C.c_void_p), ("targets", C.c_void_p), ("grad_scale", C.c_float), ("reserved", C.c_int32),
     ]
 
 
@@ -55,7 +56,7 @@ class VocabNllDesc(C.Structure):
         ("H", C.c_void_p * MAX_SEG), ("E", C.c_void_p * MAX_SEG),
         ("K", C.c_int64 * MAX_SEG), ("ldh", C.c_int64 * MAX_SEG), ("lde", C.c_int64 * MAX_SEG),
         ("bias", C.c_void_p), ("targets", C.c_void_p), ("nll", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("lse", C.c_void_p),
     ]
 
 

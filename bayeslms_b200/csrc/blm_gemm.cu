@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 // nll[m] = ln2 * (gmax2 + log2(sum_g sum_g * 2^(max2_g - gmax2))) - target logit
 __global__ void nll_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                                  const float* __restrict__ part_tgt, int groups, int M,
-                                 float* __restrict__ nll) {
+                                 float* __restrict__ nll, float* __restrict__ lse) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float gmax = -INFINITY, tgt = -INFINITY;
@@ -324,7 +324,9 @@ __global__ void nll_merge_kernel(const float* __restrict__ part_max, const float
   for (int g = 0; g < groups; ++g)
     s += part_sum[static_cast<long long>(g) * M + m] * exp2f(part_max[static_cast<long long>(g) * M + m] - gmax);
   constexpr float kLn2 = 0.6931471805599453f;
-  nll[m] = kLn2 * (gmax + log2f(s)) - tgt;  // partial maxima are in the log2 domain
+  const float l = kLn2 * (gmax + log2f(s));  // partial maxima are in the log2 domain
+  nll[m] = l - tgt;
+  if (lse) lse[m] = l;
 }
 
 __global__ void segment_sum_kernel(const float* __restrict__ x, const int* __restrict__ offs,
@@ -361,6 +363,8 @@ int gemm_init() {
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_NLL, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kNllAresStages, EPI_NLL, BLM_ACT_NONE, kNllAres>()) != BLM_OK) return rc;
   return BLM_OK;
@@ -382,8 +386,7 @@ static int fill_segments(GemmParams& p, int nseg, const blm_bf16* const* A, cons
   p.nseg = nseg;
   for (int s = 0; s < nseg; ++s) {
     BLM_REQUIRE(A[s] && B[s], BLM_ERR_ARG, "segment %d has a null operand", s);
-    BLM_REQUIRE(K[s] > 0 && (K[s] % 8) == 0, BLM_ERR_SHAPE, "K[%d]=%lld must be a positive multiple of 8",
-                s, (long long)K[s]);
+    BLM_REQUIRE(K[s] > 0, BLM_ERR_SHAPE, "K[%d]=%lld must be positive", s, (long long)K[s]);
     int rc = encode_tmap_bf16(&p.tmA[s], A[s], M, K[s], lda[s], kBM);
     if (rc != BLM_OK) return rc;
     rc = encode_tmap_bf16(&p.tmB[s], B[s], N, K[s], ldb[s], BN);
@@ -410,8 +413,10 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
               BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
   BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld",
               (long long)d->ldr);
-  BLM_REQUIRE(d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX,
-              BLM_ERR_ARG, "unknown activation %d", d->act);
+  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_SOFTMAX_GRAD, BLM_ERR_ARG, "unknown activation %d",
+              d->act);
+  BLM_REQUIRE(d->act != BLM_ACT_SOFTMAX_GRAD || (d->lse && d->targets), BLM_ERR_ARG,
+              "softmax-grad epilogue needs lse and targets");
   BLM_REQUIRE(d->act != BLM_ACT_GPMIX || d->coef, BLM_ERR_ARG, "GP-mix epilogue needs coef");
 
   // Tile choice: 128x256 tiles unless that leaves most SMs idle, then 128x128.
@@ -441,18 +446,23 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(d->out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(d->out_lo);
   p.ldc = d->ldc;
+  p.lse = d->lse;
+  p.targets = d->targets;
+  p.grad_scale = d->grad_scale;
   cudaStream_t st = as_stream(stream);
   if (BN == 256) {
     switch (d->act) {
       case BLM_ACT_NONE: return launch<256, kStages256, EPI_STORE, BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU>(p, st);
-      default: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+      case BLM_ACT_GPMIX: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+      default: return launch<256, kStages256, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>(p, st);
     }
   }
   switch (d->act) {
     case BLM_ACT_NONE: return launch<128, kStages128, EPI_STORE, BLM_ACT_NONE>(p, st);
     case BLM_ACT_GELU: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU>(p, st);
-    default: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+    case BLM_ACT_GPMIX: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+    default: return launch<128, kStages128, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>(p, st);
   }
 }
 
@@ -519,7 +529,7 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   const int threads = 256;
   const int blocks = static_cast<int>((d->M + threads - 1) / threads);
   nll_merge_kernel<<<blocks, threads, 0, st>>>(p.part_max, p.part_sum, p.part_tgt, used_groups, p.M,
-                                               d->nll);
+                                               d->nll, d->lse);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

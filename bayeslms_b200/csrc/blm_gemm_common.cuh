@@ -34,7 +34,10 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldc;
-  // EPI_NLL
+  // BLM_ACT_SOFTMAX_GRAD: dZ = (softmax - onehot) * grad_scale, softmax = exp(z - lse[m])
+  const float* lse;
+  float grad_scale;
+  // EPI_NLL (and the softmax-grad epilogue)
   const int* targets;
   float* part_max;  // [n_groups, M]
   float* part_sum;
@@ -115,7 +118,13 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.col_scale_cols) v[j] *= p.col_scale;
     }
-    if constexpr (ACT != BLM_ACT_NONE) {
+    if constexpr (ACT == BLM_ACT_SOFTMAX_GRAD) {
+      const float nl = -__ldg(p.lse + m) * 1.4426950408889634f;
+      const int rel = __ldg(p.targets + m) - col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = (ex2_approx(fmaf(v[j], 1.4426950408889634f, nl)) - (j == rel ? 1.0f : 0.0f)) * p.grad_scale;
+    } else if constexpr (ACT != BLM_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
     }
@@ -168,7 +177,12 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       float z = v[j];
       if (p.bias) z += __ldg(p.bias + col);
       if (col < p.col_scale_cols) z *= p.col_scale;
-      z = apply_act<ACT>(z, p.coef, p.N, col);
+      if constexpr (ACT == BLM_ACT_SOFTMAX_GRAD) {
+        z = (ex2_approx((z - __ldg(p.lse + m)) * 1.4426950408889634f) - (col == __ldg(p.targets + m) ? 1.0f : 0.0f)) *
+            p.grad_scale;
+      } else {
+        z = apply_act<ACT>(z, p.coef, p.N, col);
+      }
       if (p.resid) z += __ldg(p.resid + static_cast<long long>(m) * p.ldr + col);
       if (p.out_f32) p.out_f32[off + j] = z;
       if (p.out_hi) {

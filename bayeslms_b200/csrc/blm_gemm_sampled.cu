@@ -310,7 +310,7 @@ extern "C" int blm_gemm_sampled(const blm_gemm_sampled_desc* d, blm_stream strea
               BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
   BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld", (long long)d->ldr);
   BLM_REQUIRE(d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX, BLM_ERR_ARG,
-              "unknown activation %d", d->act);
+              "unsupported activation %d", d->act);
   BLM_REQUIRE(d->act != BLM_ACT_GPMIX || d->coef, BLM_ERR_ARG, "GP-mix epilogue needs coef");
 
   SampledParams p;

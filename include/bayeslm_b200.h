@@ -47,8 +47,11 @@ enum {
 enum {
   BLM_ACT_NONE = 0,
   BLM_ACT_GELU = 1,  /* exact erf GELU, model.py:1035                          */
-  BLM_ACT_GPMIX = 2  /* sum_i coef[i,n]*act_i(z), acts tanh,sigmoid,relu,gelu;
+  BLM_ACT_GPMIX = 2, /* sum_i coef[i,n]*act_i(z), acts tanh,sigmoid,relu,gelu;
                         model.py:1893-1899 with act_set of model.py:2263       */
+  BLM_ACT_SOFTMAX_GRAD = 3 /* (exp(z - lse[m]) - [n == target[m]]) * grad_scale: the gradient of
+                        the mean cross-entropy w.r.t. the logits (train.py:332,412),
+                        written as bf16 (hi, lo) so the logits themselves never exist */
 };
 
 /* where the N(0,1) noise of a reparameterised tensor comes from */
@@ -80,8 +83,8 @@ int blm_num_sms(void);
  *
  * replaces: F.linear / nn.Linear at model.py:850,855,876,921,1026,1028,1043,
  *           1129,1290,1303,1885 (cuBLAS behind ATen in the reference).
- * needs:    K_s % 8 == 0, lda/ldb/ldc % 8 == 0, ldr % 4 == 0, 16-B aligned pointers
- *           (M and N are arbitrary: ragged edges are masked).
+ * needs:    lda/ldb/ldc % 8 == 0, ldr % 4 == 0, 16-B aligned pointers
+ *           (M, N and K_s are arbitrary: ragged edges are zero-filled / masked).
  */
 #define BLM_MAX_SEG 6
 
@@ -104,6 +107,10 @@ typedef struct blm_gemm_desc {
   blm_bf16* out_hi;
   blm_bf16* out_lo;
   int64_t ldc;         /* shared by the three outputs                          */
+  const float* lse;    /* [M] log-sum-exp per row      (BLM_ACT_SOFTMAX_GRAD)  */
+  const int32_t* targets; /* [M] target column per row (BLM_ACT_SOFTMAX_GRAD)  */
+  float grad_scale;    /* e.g. 1 / M                   (BLM_ACT_SOFTMAX_GRAD)  */
+  int32_t reserved;
 } blm_gemm_desc;
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
@@ -171,6 +178,7 @@ typedef struct blm_vocab_nll_desc {
   float* nll;             /* [M] out                                           */
   void* workspace;
   int64_t workspace_bytes;
+  float* lse;             /* [M] optional out: log-sum-exp of the row (backward) */
 } blm_vocab_nll_desc;
 
 int64_t blm_vocab_nll_workspace_bytes(int64_t M, int64_t V);
