@@ -3,13 +3,18 @@
 //   blm_gemm       C = epilogue(sum_s A_s B_s^T)        (a),(c): linear layers
 //   blm_vocab_nll  nll = LSE(h E^T + b) - (h E^T + b)[t]  (d): logits stay in TMEM
 //
-// One persistent CTA per SM, 256 threads:
+// One persistent CTA per SM, (4 + EW) warps:
 //   warp 0   TMA producer   (lane 0): A/B tiles -> 128B-swizzled smem ring
 //   warp 1   MMA issuer     (lane 0): tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
 //   warp 2   TMEM allocator
-//   warp 4-7 epilogue: tcgen05.ld one accumulator row per thread, fused
-//            bias / scale / GELU / GP-mix / residual / (hi,lo) split, or the
-//            online log-sum-exp + target gather of the vocabulary sweep.
+//   warp 4.. EW epilogue warps (8 or 16): warp w reads TMEM lanes [32 (w % 4), +32) -- one
+//            accumulator row per thread -- and owns column group (w - 4) / 4 of the tile: fused
+//            bias / scale / GELU / GP-mix / residual / (hi,lo) split, or the online
+//            log-sum-exp + target gather of the vocabulary sweep.  Two or four epilogue warps per
+//            scheduler hide each other's TMEM-load, MUFU and dependency latencies (with one, the
+//            epilogue issued 1 instruction in 5 cycles and ran 2.5x longer than the MMAs, r01d
+//            profile); the tile's bias is staged once in shared memory instead of being fetched
+//            from L2 by every thread for every chunk.
 // Two TMEM accumulator stages let the MMA of tile i+1 overlap the epilogue of
 // tile i.  Ragged M/N/K edges rely on TMA zero fill; the epilogue masks rows
 // >= M and columns >= N.
@@ -27,25 +32,24 @@ struct NllState {
 };
 
 // online log-sum-exp over one 32-column chunk of logits (natural-log units; exponentials via ex2)
-__device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], int col0, NllState& st) {
+// sb: the chunk's 32 bias values in shared memory (zero where there is no bias / past column N)
+__device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], int col0, NllState& st,
+                                          const float* sb) {
   constexpr float kLog2e = 1.4426950408889634f;
-  if (col0 + 32 <= p.N) {
-    if (p.bias) {
+  if (p.bias) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += bb.x;
-        v[j + 1] += bb.y;
-        v[j + 2] += bb.z;
-        v[j + 3] += bb.w;
-      }
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(sb + j);
+      v[j] += bb.x;
+      v[j + 1] += bb.y;
+      v[j + 2] += bb.z;
+      v[j + 3] += bb.w;
     }
-  } else {
+  }
+  if (col0 + 32 > p.N) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      v[j] = col < p.N ? v[j] + (p.bias ? __ldg(p.bias + col) : 0.0f) : -INFINITY;
-    }
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j >= p.N) v[j] = -INFINITY;
   }
   const unsigned int rel = static_cast<unsigned int>(st.tgt - col0);
   if (rel < 32u) {  // the target column lives in this chunk: once per row per sweep
@@ -77,17 +81,25 @@ __device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], i
   st.run_max = new_m2;
 }
 
-template <int BN, int STAGES, int EPI, int ACT, int ARES>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+template <int BN, int STAGES, int EPI, int ACT, int ARES, int EW>
+__global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   using L = SmemLayout<BN, STAGES, ARES>;
+  static_assert(EW == 8 || EW == 16, "epilogue warps");
+  constexpr int kColGroups = EW / 4;                 // column groups of the tile, one per 4 warps
+  constexpr int kChunks = BN / 32 / kColGroups;      // 32-column chunks per epilogue warp
+  static_assert(kChunks >= 2 && (kChunks % 2) == 0, "the chunk loop is unrolled by two");
   constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                             : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {  // SWIZZLE_128B tiles need 1024-B aligned bases
+    if (threadIdx.x == 0) printf("blm: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* ring = smem + L::kResBytes;
+  float* sbias = reinterpret_cast<float*>(smem + L::kBiasOffset);  // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], EW);  // one arrive per epilogue warp
     }
     mbar_init(afull_bar, 1);
     mbar_init(aempty_bar, 1);
@@ -224,8 +236,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   } else if (warp >= kEpiWarp0) {
     // ---------------------------------------------------------- epilogue
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) belong to this warp
+    const int col_grp = (warp - kEpiWarp0) >> 2;
+    const int etid = threadIdx.x - kEpiWarp0 * 32;
     const int row_in_tile = lane_grp * 32 + lane;
-    constexpr int kChunks = BN / 32;
+    const int c0 = col_grp * kChunks;  // first chunk of this warp inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
@@ -242,10 +256,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
 
       for (int n = n0; n < n1; ++n) {
+        // this tile's bias: fetched while the MMAs still run, staged in shared memory for all rows
+        float breg[(BN + EW * 32 - 1) / (EW * 32)];
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < (BN + EW * 32 - 1) / (EW * 32); ++i) {
+            const int col = n * BN + etid + i * EW * 32;
+            breg[i] = (etid + i * EW * 32 < BN && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+          }
+        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tcgen05_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        float* sb = sbias + acc * BN;
+        if (p.bias) {
+          // sbias[acc] was last read for tile n-2, which every epilogue warp finished before it
+          // passed the barrier of tile n-1
+#pragma unroll
+          for (int i = 0; i < (BN + EW * 32 - 1) / (EW * 32); ++i)
+            if (etid + i * EW * 32 < BN) sb[etid + i * EW * 32] = breg[i];
+          epi_bar_sync(EW * 32);
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN + c0 * 32);
         // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
         float va[32], vb[32];
         __syncwarp();
@@ -256,12 +288,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           __syncwarp();
           tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 1) * 32), vb);
           {
-            const int col0 = n * BN + c * 32;
+            const int col0 = n * BN + (c0 + c) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (row_ok) store_chunk<ACT>(p, va, m, col0);
+                if (row_ok) store_chunk<ACT>(p, va, m, col0, sb + (c0 + c) * 32);
               } else {
-                nll_chunk(p, va, col0, st);
+                nll_chunk(p, va, col0, st, sb + (c0 + c) * 32);
               }
             }
           }
@@ -270,17 +302,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           if (c + 2 < kChunks) {
             tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), va);
           } else {
-            // every column of this accumulator stage is in registers: hand it back to the MMA warp
+            // every column this warp owns is in registers: hand the stage back to the MMA warp
             tcgen05_fence_before();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
           {
-            const int col0 = n * BN + (c + 1) * 32;
+            const int col0 = n * BN + (c0 + c + 1) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (row_ok) store_chunk<ACT>(p, vb, m, col0);
+                if (row_ok) store_chunk<ACT>(p, vb, m, col0, sb + (c0 + c + 1) * 32);
               } else {
-                nll_chunk(p, vb, col0, st);
+                nll_chunk(p, vb, col0, st, sb + (c0 + c + 1) * 32);
               }
             }
           }
@@ -292,7 +324,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
       if constexpr (EPI == EPI_NLL) {
         if (row_ok) {
-          const long long o = static_cast<long long>(grp) * p.M + m;
+          // one partial per (vocabulary group, column group); nll_merge_kernel folds them
+          const long long o = static_cast<long long>(grp * kColGroups + col_grp) * p.M + m;
           p.part_max[o] = st.run_max;
           p.part_sum[o] = st.run_sum;
           p.part_tgt[o] = st.tgt_logit;
@@ -342,18 +375,36 @@ __global__ void segment_sum_kernel(const float* __restrict__ x, const int* __res
 }
 
 // ------------------------------------------------------------------ host
-template <int BN, int STAGES, int EPI, int ACT, int ARES = 0>
-static int set_smem_attr() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI, ACT, ARES>,
+constexpr int kStages256 = 4;
+constexpr int kStages128 = 6;
+constexpr int kNllAres = 8;        // resident A: 8 K blocks = K <= 512 (128 KB)
+constexpr int kNllAresStages = 3;  // + 3 x 32 KB of streamed vocabulary tiles
+
+// epilogue warps for the 128 x 256 tiles: 8 (default) or 16 (BLM_EPI_WARPS=16, A/B switch for profiling)
+static int epi_warps256() {
+  static const int ew = [] {
+    const char* e = getenv("BLM_EPI_WARPS");
+    return (e && atoi(e) == 16) ? 16 : 8;
+  }();
+  return ew;
+}
+
+template <int BN, int STAGES, int EPI, int ACT, int ARES, int EW>
+static int set_smem_attr1() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI, ACT, ARES, EW>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SmemLayout<BN, STAGES, ARES>::kDynBytes));
   return BLM_OK;
 }
 
-constexpr int kStages256 = 4;
-constexpr int kStages128 = 6;
-constexpr int kNllAres = 8;        // resident A: 8 K blocks = K <= 512 (128 KB)
-constexpr int kNllAresStages = 3;  // + 3 x 32 KB of streamed vocabulary tiles
+template <int BN, int STAGES, int EPI, int ACT, int ARES = 0>
+static int set_smem_attr() {
+  int rc = set_smem_attr1<BN, STAGES, EPI, ACT, ARES, 8>();
+  if constexpr (BN == 256) {
+    if (rc == BLM_OK) rc = set_smem_attr1<BN, STAGES, EPI, ACT, ARES, 16>();
+  }
+  return rc;
+}
 
 int gemm_init() {
   int rc;
@@ -373,8 +424,15 @@ int gemm_init() {
 template <int BN, int STAGES, int EPI, int ACT, int ARES = 0>
 static int launch(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<BN, STAGES, EPI, ACT, ARES>
-      <<<grid, kThreads, SmemLayout<BN, STAGES, ARES>::kDynBytes, st>>>(p);
+  constexpr int smem = SmemLayout<BN, STAGES, ARES>::kDynBytes;
+  if constexpr (BN == 256) {
+    if (epi_warps256() == 16) {
+      gemm_kernel<BN, STAGES, EPI, ACT, ARES, 16><<<grid, (4 + 16) * 32, smem, st>>>(p);
+      BLM_CHECK_CUDA(cudaGetLastError());
+      return BLM_OK;
+    }
+  }
+  gemm_kernel<BN, STAGES, EPI, ACT, ARES, 8><<<grid, (4 + 8) * 32, smem, st>>>(p);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }
@@ -479,10 +537,8 @@ static int nll_groups(int64_t M, int64_t V) {
 }
 
 int64_t blm_vocab_nll_workspace_bytes(int64_t M, int64_t V) {
-  // worst case: one group per N tile
-  const int64_t n_tiles = (V + 255) / 256;
-  const int64_t g = n_tiles < 148 ? n_tiles : 148;
-  return 3 * g * M * static_cast<int64_t>(sizeof(float)) + 64;
+  // one (max, sum, target) partial per row, vocabulary group and epilogue column group (<= 4)
+  return 3 * 4 * static_cast<int64_t>(nll_groups(M, V)) * M * static_cast<int64_t>(sizeof(float)) + 64;
 }
 
 int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
@@ -494,7 +550,8 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   BLM_REQUIRE(d->targets && d->nll && d->workspace, BLM_ERR_ARG, "null targets / nll / workspace");
   BLM_REQUIRE(aligned16(d->workspace), BLM_ERR_ALIGN, "workspace must be 16-byte aligned");
   const int groups = nll_groups(d->M, d->V);
-  BLM_REQUIRE(d->workspace_bytes >= 3ll * groups * d->M * (int64_t)sizeof(float), BLM_ERR_ARG,
+  const int col_groups = epi_warps256() / 4;
+  BLM_REQUIRE(d->workspace_bytes >= 3ll * col_groups * groups * d->M * (int64_t)sizeof(float), BLM_ERR_ARG,
               "workspace too small: %lld bytes", (long long)d->workspace_bytes);
 
   GemmParams p;
@@ -513,8 +570,9 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   p.targets = d->targets;
   float* ws = reinterpret_cast<float*>(d->workspace);
   p.part_max = ws;
-  p.part_sum = ws + static_cast<int64_t>(used_groups) * d->M;
-  p.part_tgt = ws + 2 * static_cast<int64_t>(used_groups) * d->M;
+  const int parts = used_groups * col_groups;
+  p.part_sum = ws + static_cast<int64_t>(parts) * d->M;
+  p.part_tgt = ws + 2 * static_cast<int64_t>(parts) * d->M;
   cudaStream_t st = as_stream(stream);
   int total_kb = 0;
   for (int i = 0; i < p.nseg; ++i) total_kb += p.kblocks[i];
@@ -528,7 +586,7 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   if (rc != BLM_OK) return rc;
   const int threads = 256;
   const int blocks = static_cast<int>((d->M + threads - 1) / threads);
-  nll_merge_kernel<<<blocks, threads, 0, st>>>(p.part_max, p.part_sum, p.part_tgt, used_groups, p.M,
+  nll_merge_kernel<<<blocks, threads, 0, st>>>(p.part_max, p.part_sum, p.part_tgt, parts, p.M,
                                                d->nll, d->lse);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;

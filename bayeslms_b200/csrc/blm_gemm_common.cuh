@@ -8,8 +8,7 @@ namespace blm {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 4;  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
 
 enum { EPI_STORE = 0, EPI_NLL = 1 };
 
@@ -52,11 +51,20 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kResBytes = ARES * kABytes;
   static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
-  static constexpr int kBarOffset = kResBytes + STAGES * kStageBytes;
+  static constexpr int kBiasOffset = kResBytes + STAGES * kStageBytes;  // fp32 bias[2][BN], one per accumulator stage
+  static constexpr int kBarOffset = kBiasOffset + 2 * BN * 4;
   // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] a_full a_empty + tmem ptr
   static constexpr int kBytes = kBarOffset + (2 * STAGES + 6) * 8 + 16;
-  static constexpr int kDynBytes = kBytes + 1024;  // slack for manual 1024-B alignment
+  // the dynamic shared-memory window of a kernel without static shared memory starts 1024-B aligned
+  // (checked at kernel entry), so no alignment slack is reserved: the A-resident NLL variant needs
+  // 224 KB of tiles and would not fit with it
+  static constexpr int kDynBytes = kBytes;
 };
+
+// barrier among the epilogue warps only (named barrier 1; barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync(int threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -96,14 +104,17 @@ __device__ __forceinline__ float apply_act(float z, const float* __restrict__ co
 // ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
 
 // bias / q-scale / activation / residual / (hi, lo) split / stores for one 32-column chunk
+// sb: this chunk's 32 bias values staged in shared memory (null: read p.bias from global)
 template <int ACT>
-__device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, int col0) {
+__device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, int col0,
+                                            const float* sb = nullptr) {
   const bool full = (col0 + 32 <= p.N);
   if (full) {
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        const float4 bb = sb ? *reinterpret_cast<const float4*>(sb + j)
+                             : __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
         v[j] += bb.x;
         v[j + 1] += bb.y;
         v[j + 2] += bb.z;
