@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbayeslm_b200.so")
 BLM_OK = 0
 ERR_NAMES = {-1: "BLM_ERR_SHAPE", -2: "BLM_ERR_ALIGN", -3: "BLM_ERR_ARCH", -4: "BLM_ERR_CUDA", -5: "BLM_ERR_ARG"}
 
-ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD, ACT_GELU_GRAD, ACT_GPMIX_GRAD = 0, 1, 2, 3, 4, 5
 EPS_NONE, EPS_PTR, EPS_PHILOX = 0, 1, 2
 MAX_SEG = 6
 
@@ -35,7 +35,8 @@ class GemmDesc(C.Structure):
         ("col_scale", C.c_float), ("col_scale_cols", C.c_int32),
         ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
-        ("lse", C.c_void_p), ("targets", C.c_void_p), ("grad_scale", C.c_float), ("reserved", C.c_int32),
+        ("lse", C.c_void_p), ("targets", C.c_void_p), ("grad_scale", C.c_float), ("k_chunk", C.c_int32),
+        ("out_pre", C.c_void_p), ("aux", C.c_void_p), ("ldaux", C.c_int64),
     ]
 
 
@@ -81,8 +82,25 @@ SIGNATURES = {
     "blm_reparam": (C.c_int, [_p, _i64, _p, _p, _i32, _u64, _u64, _i64, _i64, _p, _p, _p, _p]),
     "blm_philox_normal": (C.c_int, [_u64, _u64, _i64, _p, _p]),
     "blm_mha_causal": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "blm_mha_causal_bf16": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "blm_kl_workspace_bytes": (_i64, []),
     "blm_kl_gauss": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _f, _i32, _p, _p, _p]),
+    "blm_transpose_split": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "blm_transpose_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "blm_colsum": (C.c_int, [_p, _i64, _i64, _i64, _f, _i32, _p, _p]),
+    "blm_colsum_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i32, _p, _p]),
+    "blm_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),
+    "blm_layernorm_bwd": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
+    "blm_mha_causal_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p]),
+    "blm_gpmix_dcoef": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p]),
+    "blm_vnoise_fwd": (C.c_int, [_p, _p, _p, _i32, _u64, _u64, _f, _i64, _i32, _i32, _p, _p]),
+    "blm_vnoise_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _u64, _u64, _f, _i64, _i32, _i32, _f, _p, _p, _p, _p, _p]),
+    "blm_embed_bwd": (C.c_int, [_p, _p, _f, _i64, _i32, _p, _p]),
+    "blm_kl_gauss_bwd": (C.c_int, [_p, _i64, _p, _i64, _i64, _f, _p, _i64, _p, _p]),
+    "blm_reparam_bwd": (C.c_int, [_p, _i64, _p, _p, _i32, _u64, _u64, _i64, _i64, _i32, _p, _i64, _p, _p]),
+    "blm_reduce_workspace_bytes": (_i64, []),
+    "blm_reduce": (C.c_int, [_p, _i64, _i32, _f, _i32, _p, _p, _p]),
+    "blm_sgd_momentum": (C.c_int, [_p, _p, _p, _i64, _f, _f, _p, _f, _f, _p]),
     "blm_lstm_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_lstm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
 }

@@ -213,6 +213,279 @@ __global__ void __launch_bounds__(kWarpAttnWarps * 32) mha_causal_warp_kernel(
   }
 }
 
+// ---- tensor-core attention over bf16 (hi[, lo]) q/k/v ------------------------------------------
+// The QKV projection writes its output as bf16 (hi[, lo]) pairs; this kernel stages the [T x 64]
+// q, k, v blocks of each (hypothesis, head) with cp.async (16-byte chunks, XOR-swizzled rows, zero
+// fill past the hypothesis end), and runs S = Q K^T and O = P V on mma.sync m16n8k16 (bf16 in, fp32
+// accumulate) with the flash-attention register pipeline: the S accumulator fragments are masked,
+// soft-maxed (online, log2 domain) and re-used in place as the A fragments of P V; V is read through
+// ldmatrix.trans.  PRECISE carries every operand as hi + lo and issues hi*hi + hi*lo + lo*hi.
+// Hypotheses are 6..26 tokens (rescoring) or 100 (fine-tuning): a tcgen05 128-row tile would be
+// mostly padding and the kernel is bound by the q/k/v read anyway (4 KB per token), so the warp-level
+// MMA is the right atom here.
+//   KV_ROWS = 32 : one warp per (hypothesis, head), four pairs per CTA          (max_len <= 32)
+//   KV_ROWS = 128: one CTA per (hypothesis, head), warp w owns query rows [32w, 32w + 32)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2f_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int kMmaAttnHd = 64;
+constexpr int kMmaAttnRowBytes = kMmaAttnHd * 2;  // one q/k/v row of a head: 128 B = 8 chunks of 16 B
+
+template <bool PRECISE, int KV_ROWS>
+__global__ void __launch_bounds__(128) mha_causal_mma_kernel(
+    const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, long long ld,
+    const int* __restrict__ seq_offsets, long long n_pairs, int nhead, float* __restrict__ out_f32,
+    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
+  constexpr int PARTS = PRECISE ? 2 : 1;
+  constexpr int WPP = KV_ROWS / 32;  // warps per (hypothesis, head) pair
+  constexpr int PPC = 4 / WPP;       // pairs per CTA
+  extern __shared__ __align__(128) uint8_t attn_sm[];
+  // [matrix q,k,v][part hi,lo][128 rows][128 B]
+  const uint32_t sm_base = smem_u32(attn_sm);
+  auto tile = [&](int mat, int part) -> uint32_t { return sm_base + static_cast<uint32_t>((mat * PARTS + part) * 128 * 128); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pair = static_cast<long long>(blockIdx.x) * PPC + warp / WPP;
+  const int qt = warp % WPP;
+  int row0 = 0, T = 0, head = 0;
+  if (pair < n_pairs) {
+    const int seq = static_cast<int>(pair / nhead);
+    head = static_cast<int>(pair - static_cast<long long>(seq) * nhead);
+    row0 = __ldg(seq_offsets + seq);
+    T = __ldg(seq_offsets + seq + 1) - row0;
+    if (T > KV_ROWS) {
+      if (lane == 0) printf("blm: sequence %d has %d tokens > %d\n", seq, T, KV_ROWS);
+      __trap();
+    }
+  }
+  const int d = nhead * kMmaAttnHd;
+  const int pb = (warp / WPP) * KV_ROWS;  // first shared-memory row of this pair
+  // ---- stage rows [32 qt, 32 qt + 32) of q, k and v of this pair (zero fill past T)
+#pragma unroll
+  for (int mat = 0; mat < 3; ++mat) {
+#pragma unroll
+    for (int part = 0; part < PARTS; ++part) {
+      const __nv_bfloat16* src_base = (part == 0 ? qkv_hi : qkv_lo) + mat * d + head * kMmaAttnHd;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int c = it * 32 + lane;
+        const int r = c >> 3, ch = c & 7;
+        const int tr = qt * 32 + r;
+        const bool ok = tr < T;
+        const __nv_bfloat16* src = ok ? src_base + static_cast<long long>(row0 + tr) * ld + ch * 8 : src_base;
+        const uint32_t dst = tile(mat, part) + static_cast<uint32_t>((pb + tr) * kMmaAttnRowBytes + ((ch ^ (r & 7)) << 4));
+        cp_async16(dst, src, ok ? 16u : 0u);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (qt * 32 >= T) return;
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int i_hi = min(T, qt * 32 + 32) - 1;      // last valid query row of this warp
+  const int nmt = (i_hi - qt * 32) / 16 + 1;      // m16 tiles in use (1 or 2)
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  float o[2][8][4];
+  float mrow[2][2], lrow[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    mrow[mt][0] = mrow[mt][1] = -INFINITY;
+    lrow[mt][0] = lrow[mt][1] = 0.0f;
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][ct][e] = 0.0f;
+  }
+  // swizzled address of (row, 16-byte chunk) inside a tile
+  auto addr = [&](uint32_t base, int row, int chunk) -> uint32_t {
+    return base + static_cast<uint32_t>(row * kMmaAttnRowBytes + ((chunk ^ (row & 7)) << 4));
+  };
+
+  for (int kb = 0; kb <= qt; ++kb) {
+    const int jmax = min(i_hi, kb * 32 + 31);
+    const int nnt = (jmax - kb * 32) / 8 + 1;  // n8 key tiles in use (1..4)
+    float s[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.0f;
+    // ---- S = Q K^T over the 64 head dimensions
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t aq[2][PARTS][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < nmt) {
+          const int row = pb + qt * 32 + mt * 16 + (lane & 15);
+#pragma unroll
+          for (int part = 0; part < PARTS; ++part) ldsm_x4(addr(tile(0, part), row, ks * 2 + (lane >> 4)), aq[mt][part]);
+        }
+      }
+#pragma unroll
+      for (int ntp = 0; ntp < 2; ++ntp) {
+        if (ntp * 2 < nnt) {
+          uint32_t bk[PARTS][4];
+          const int row = pb + kb * 32 + ntp * 16 + (lane & 7) + ((lane >> 4) << 3);
+#pragma unroll
+          for (int part = 0; part < PARTS; ++part) ldsm_x4(addr(tile(1, part), row, ks * 2 + ((lane >> 3) & 1)), bk[part]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt < nmt) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                mma_bf16(s[mt][ntp * 2 + u], aq[mt][0], bk[0][2 * u], bk[0][2 * u + 1]);
+                if constexpr (PRECISE) {
+                  mma_bf16(s[mt][ntp * 2 + u], aq[mt][0], bk[1][2 * u], bk[1][2 * u + 1]);
+                  mma_bf16(s[mt][ntp * 2 + u], aq[mt][1], bk[0][2 * u], bk[0][2 * u + 1]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // ---- causal mask + online softmax (log2 domain), P re-packed as the A fragments of P V
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt < nmt) {
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = qt * 32 + mt * 16 + g + ((e >> 1) << 3);
+            const int j = kb * 32 + nt * 8 + 2 * t4 + (e & 1);
+            const float v = (j <= i && nt < nnt) ? s[mt][nt][e] * kLog2e : -INFINITY;
+            s[mt][nt][e] = v;
+            mx[e >> 1] = fmaxf(mx[e >> 1], v);
+          }
+        float alpha[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+          mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+          const float mnew = fmaxf(mrow[mt][h], mx[h]);  // finite: key kb*32 <= every row of this warp
+          alpha[h] = ex2f_(mrow[mt][h] - mnew);
+          mrow[mt][h] = mnew;
+          lrow[mt][h] *= alpha[h];
+        }
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) {
+          o[mt][ct][0] *= alpha[0];
+          o[mt][ct][1] *= alpha[0];
+          o[mt][ct][2] *= alpha[1];
+          o[mt][ct][3] *= alpha[1];
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pv = ex2f_(s[mt][nt][e] - mrow[mt][e >> 1]);
+            s[mt][nt][e] = pv;
+            lrow[mt][e >> 1] += pv;
+          }
+      }
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      if (kk * 2 < nnt) {
+        uint32_t ap[2][PARTS][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < nmt) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float x0 = s[mt][2 * kk + (q >> 1)][(q & 1) * 2], x1 = s[mt][2 * kk + (q >> 1)][(q & 1) * 2 + 1];
+              const uint32_t hi = pack_bf16x2(x0, x1);
+              ap[mt][0][q] = hi;
+              if constexpr (PRECISE)
+                ap[mt][1][q] = pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+            }
+          }
+        }
+#pragma unroll
+        for (int ctp = 0; ctp < 4; ++ctp) {
+          uint32_t bv[PARTS][4];
+          const int row = pb + kb * 32 + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+          for (int part = 0; part < PARTS; ++part) ldsm_x4_trans(addr(tile(2, part), row, ctp * 2 + (lane >> 4)), bv[part]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt < nmt) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                mma_bf16(o[mt][ctp * 2 + u], ap[mt][0], bv[0][2 * u], bv[0][2 * u + 1]);
+                if constexpr (PRECISE) {
+                  mma_bf16(o[mt][ctp * 2 + u], ap[mt][0], bv[1][2 * u], bv[1][2 * u + 1]);
+                  mma_bf16(o[mt][ctp * 2 + u], ap[mt][1], bv[0][2 * u], bv[0][2 * u + 1]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- normalise and store: thread holds rows g, g + 8 of each m tile, columns 8 ct + 2 t4 + {0, 1}
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    if (mt < nmt) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float l = lrow[mt][h];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = 1.0f / l;
+        const int i = qt * 32 + mt * 16 + g + 8 * h;
+        if (i < T) {
+          const long long off = static_cast<long long>(row0 + i) * ldo + head * kMmaAttnHd + 2 * t4;
+#pragma unroll
+          for (int ct = 0; ct < 8; ++ct) {
+            const float x0 = o[mt][ct][2 * h] * inv, x1 = o[mt][ct][2 * h + 1] * inv;
+            if (out_f32) *reinterpret_cast<float2*>(out_f32 + off + ct * 8) = make_float2(x0, x1);
+            if (out_hi) {
+              const uint32_t hi = pack_bf16x2(x0, x1);
+              *reinterpret_cast<uint32_t*>(out_hi + off + ct * 8) = hi;
+              if (out_lo)
+                *reinterpret_cast<uint32_t*>(out_lo + off + ct * 8) =
+                    pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool PRECISE>
+static constexpr int mma_attn_smem_bytes() { return 3 * (PRECISE ? 2 : 1) * 128 * 128; }
+
 static size_t warp_attn_smem_bytes(int max_len, int hd) {
   const size_t per_warp = (static_cast<size_t>(max_len) * (3 * hd + 1) + 4 * 32 + 3) & ~static_cast<size_t>(3);
   return sizeof(float) * kWarpAttnWarps * per_warp;
@@ -227,6 +500,14 @@ int attention_init() {
                                       static_cast<int>(attn_smem_bytes(kAttnMaxLen, kAttnMaxHd))));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_warp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(warp_attn_smem_bytes(32, 64))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<false>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<false>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<true>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<true>()));
   return BLM_OK;
 }
 
@@ -262,6 +543,55 @@ extern "C" int blm_mha_causal(const float* qkv, const int32_t* seq_offsets, int6
                       as_stream(stream)>>>(qkv, seq_offsets, nhead, head_dim, max_len, out_f32,
                                            reinterpret_cast<__nv_bfloat16*>(out_hi),
                                            reinterpret_cast<__nv_bfloat16*>(out_lo));
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+
+extern "C" int blm_mha_causal_bf16(const blm_bf16* qkv_hi, const blm_bf16* qkv_lo, int64_t ld,
+                                   const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                                   int32_t max_len, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, int64_t ldo,
+                                   blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(qkv_hi && seq_offsets && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention arguments");
+  BLM_REQUIRE(head_dim == kMmaAttnHd, BLM_ERR_SHAPE, "the tensor-core attention kernel needs head_dim 64, got %d", head_dim);
+  BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
+  BLM_REQUIRE(out_f32 || out_hi, BLM_ERR_ARG, "no output buffer");
+  BLM_REQUIRE(!out_lo || out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
+  BLM_REQUIRE((ld % 8) == 0 && ld >= 3ll * nhead * head_dim && (ldo % 2) == 0 && ldo >= (int64_t)nhead * head_dim,
+              BLM_ERR_ALIGN, "bad leading dimensions ld=%lld ldo=%lld", (long long)ld, (long long)ldo);
+  BLM_REQUIRE(aligned16(qkv_hi) && aligned16(qkv_lo) && aligned16(out_f32) && aligned16(out_hi) && aligned16(out_lo),
+              BLM_ERR_ALIGN, "attention pointers must be 16-byte aligned");
+  BLM_REQUIRE(nseq * nhead < (1ll << 31), BLM_ERR_SHAPE, "too many (sequence, head) pairs");
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = attention_init();
+    if (rc != BLM_OK) return rc;
+    attr_set = true;
+  }
+  const long long pairs = nseq * nhead;
+  const __nv_bfloat16* qh = reinterpret_cast<const __nv_bfloat16*>(qkv_hi);
+  const __nv_bfloat16* ql = reinterpret_cast<const __nv_bfloat16*>(qkv_lo);
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  cudaStream_t st = as_stream(stream);
+  if (max_len <= 32) {
+    const unsigned blocks = static_cast<unsigned>((pairs + 3) / 4);
+    if (ql)
+      mha_causal_mma_kernel<true, 32><<<blocks, 128, mma_attn_smem_bytes<true>(), st>>>(qh, ql, ld, seq_offsets, pairs, nhead,
+                                                                                    out_f32, oh, ol, ldo);
+    else
+      mha_causal_mma_kernel<false, 32><<<blocks, 128, mma_attn_smem_bytes<false>(), st>>>(qh, ql, ld, seq_offsets, pairs,
+                                                                                      nhead, out_f32, oh, ol, ldo);
+  } else {
+    const unsigned blocks = static_cast<unsigned>(pairs);
+    if (ql)
+      mha_causal_mma_kernel<true, 128><<<blocks, 128, mma_attn_smem_bytes<true>(), st>>>(qh, ql, ld, seq_offsets, pairs, nhead,
+                                                                                     out_f32, oh, ol, ldo);
+    else
+      mha_causal_mma_kernel<false, 128><<<blocks, 128, mma_attn_smem_bytes<false>(), st>>>(qh, ql, ld, seq_offsets, pairs,
+                                                                                       nhead, out_f32, oh, ol, ldo);
+  }
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

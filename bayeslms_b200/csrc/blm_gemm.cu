@@ -81,10 +81,17 @@ __device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], i
   st.run_max = new_m2;
 }
 
-template <int BN, int STAGES, int EPI, int ACT, int ARES, int EW>
+// CHUNK: the tensor core adds into its fp32 accumulator with truncation, one truncation per
+// 16-wide K step, which shrinks every output by ~2e-8 x (K steps) relative (measured: -2e-5 at
+// K = 3 x 4096).  With CHUNK the MMA warp closes the TMEM accumulator every p.chunk_kb K blocks and
+// the epilogue warps sum the chunks in fp32 registers (round to nearest), so the bias is bounded by
+// the chunk length, not by K (the precise bf16x3 mode uses chunks of 128 K elements).
+template <int BN, int STAGES, int EPI, int ACT, int ARES, int EW, int CHUNK = 0>
 __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   using L = SmemLayout<BN, STAGES, ARES>;
   static_assert(EW == 8 || EW == 16, "epilogue warps");
+  static_assert(!CHUNK || (BN == 128 && EW == 8 && EPI == EPI_STORE && ARES == 0),
+                "chunked accumulation keeps a 128 x 128 tile in the registers of 8 epilogue warps");
   constexpr int kColGroups = EW / 4;                 // column groups of the tile, one per 4 warps
   constexpr int kChunks = BN / 32 / kColGroups;      // 32-column chunks per epilogue warp
   static_assert(kChunks >= 2 && (kChunks % 2) == 0, "the chunk loop is unrolled by two");
@@ -200,33 +207,37 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
           a_phase ^= 1u;
         }
         for (int n = n0; n < n1; ++n) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-          tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-          for (int kb = 0; kb < total_kb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+          const int chunk_kb = CHUNK ? p.chunk_kb : total_kb;
+          for (int kb0 = 0; kb0 < total_kb; kb0 += chunk_kb) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tcgen05_fence_after();
-            const uint32_t st = smem_u32(ring + stage * L::kStageBytes);
-            const uint32_t sa = ARES > 0 ? smem_u32(smem + kb * L::kABytes) : st;
-            const uint32_t sb = ARES > 0 ? st : st + L::kABytes;
-            const uint64_t da = umma_desc_sw128(sa);
-            const uint64_t db = umma_desc_sw128(sb);
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+            const int kb1 = min(total_kb, kb0 + chunk_kb);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const uint32_t st = smem_u32(ring + stage * L::kStageBytes);
+              const uint32_t sa = ARES > 0 ? smem_u32(smem + kb * L::kABytes) : st;
+              const uint32_t sb = ARES > 0 ? st : st + L::kABytes;
+              const uint64_t da = umma_desc_sw128(sa);
+              const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              // +32 bytes per 16-element K step inside the 128-byte swizzle row
-              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                           idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBK / 16; ++k) {
+                // +32 bytes per 16-element K step inside the 128-byte swizzle row
+                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                             idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
             }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1u;
+            umma_commit(&tfull_bar[acc]);  // accumulator (chunk) complete
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1u;
             }
-          }
-          umma_commit(&tfull_bar[acc]);  // accumulator complete
-          if (++acc == 2) {
-            acc = 0;
-            acc_phase ^= 1u;
           }
         }
         if constexpr (ARES > 0) umma_commit(aempty_bar);  // resident A free once this work's MMAs retire
@@ -264,6 +275,48 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
             const int col = n * BN + etid + i * EW * 32;
             breg[i] = (etid + i * EW * 32 < BN && col < p.N) ? __ldg(p.bias + col) : 0.0f;
           }
+        }
+        if constexpr (CHUNK) {
+          // sum the K chunks of this tile in registers: this warp owns 64 columns of its 32 rows
+          float accr[2][32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) accr[0][j] = accr[1][j] = 0.0f;
+          float* sbc = sbias;  // one bias buffer: a tile's bias is staged once, at its first chunk
+          for (int kb0 = 0; kb0 < total_kb; kb0 += p.chunk_kb) {
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + c0 * 32);
+            float va[32], vb[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr, va);
+            tmem_ld_32x32(taddr + 32u, vb);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              accr[0][j] += va[j];
+              accr[1][j] += vb[j];
+            }
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1u;
+            }
+          }
+          if (p.bias) {
+            epi_bar_sync(EW * 32);  // every warp is done with the previous tile's bias
+#pragma unroll
+            for (int i = 0; i < (BN + EW * 32 - 1) / (EW * 32); ++i)
+              if (etid + i * EW * 32 < BN) sbc[etid + i * EW * 32] = breg[i];
+            epi_bar_sync(EW * 32);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int col0 = n * BN + (c0 + c) * 32;
+            if (col0 < p.N && row_ok) store_chunk<ACT>(p, accr[c], m, col0, sbc + (c0 + c) * 32);
+          }
+          continue;
         }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tcgen05_fence_after();
@@ -406,8 +459,31 @@ static int set_smem_attr() {
   return rc;
 }
 
+template <int ACT>
+static int set_smem_attr_chunk() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<128, kStages128, EPI_STORE, ACT, 0, 8, 1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SmemLayout<128, kStages128, 0>::kDynBytes));
+  return BLM_OK;
+}
+
+template <int ACT>
+static int launch_chunk(const GemmParams& p, cudaStream_t st) {
+  const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
+  gemm_kernel<128, kStages128, EPI_STORE, ACT, 0, 8, 1>
+      <<<grid, (4 + 8) * 32, SmemLayout<128, kStages128, 0>::kDynBytes, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 int gemm_init() {
   int rc;
+  if ((rc = set_smem_attr_chunk<BLM_ACT_NONE>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_chunk<BLM_ACT_GELU>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_chunk<BLM_ACT_GPMIX>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_chunk<BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_chunk<BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_chunk<BLM_ACT_GPMIX_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
@@ -416,6 +492,10 @@ int gemm_init() {
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GPMIX_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_NLL, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kNllAresStages, EPI_NLL, BLM_ACT_NONE, kNllAres>()) != BLM_OK) return rc;
   return BLM_OK;
@@ -471,16 +551,26 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
               BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
   BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld",
               (long long)d->ldr);
-  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_SOFTMAX_GRAD, BLM_ERR_ARG, "unknown activation %d",
+  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_GPMIX_GRAD, BLM_ERR_ARG, "unknown activation %d",
               d->act);
+  const bool grad_act = d->act == BLM_ACT_GELU_GRAD || d->act == BLM_ACT_GPMIX_GRAD;
+  BLM_REQUIRE(!grad_act || (d->aux && (d->ldaux % 4) == 0 && d->ldaux >= d->N && aligned16(d->aux)), BLM_ERR_ARG,
+              "the activation-gradient epilogues need aux (16-byte aligned, ldaux %% 4 == 0)");
+  BLM_REQUIRE(aligned16(d->out_pre), BLM_ERR_ALIGN, "out_pre must be 16-byte aligned");
   BLM_REQUIRE(d->act != BLM_ACT_SOFTMAX_GRAD || (d->lse && d->targets), BLM_ERR_ARG,
               "softmax-grad epilogue needs lse and targets");
-  BLM_REQUIRE(d->act != BLM_ACT_GPMIX || d->coef, BLM_ERR_ARG, "GP-mix epilogue needs coef");
+  BLM_REQUIRE((d->act != BLM_ACT_GPMIX && d->act != BLM_ACT_GPMIX_GRAD) || d->coef, BLM_ERR_ARG,
+              "GP-mix epilogue needs coef");
 
   // Tile choice: 128x256 tiles unless that leaves most SMs idle, then 128x128.
   const int m_tiles = static_cast<int>((d->M + kBM - 1) / kBM);
   const int n_tiles256 = static_cast<int>((d->N + 255) / 256);
-  const bool use256 = (d->N >= 256) && (static_cast<long long>(m_tiles) * n_tiles256 >= num_sms());
+  BLM_REQUIRE(d->k_chunk >= 0 && (d->k_chunk % kBK) == 0, BLM_ERR_ARG, "k_chunk=%d must be a multiple of %d",
+              d->k_chunk, kBK);
+  long long total_k = 0;
+  for (int s = 0; s < d->nseg && s < BLM_MAX_SEG; ++s) total_k += (d->K[s] + kBK - 1) / kBK * kBK;
+  const bool chunked = d->k_chunk > 0 && total_k > d->k_chunk;
+  const bool use256 = !chunked && (d->N >= 256) && (static_cast<long long>(m_tiles) * n_tiles256 >= num_sms());
   const int BN = use256 ? 256 : 128;
 
   GemmParams p;
@@ -507,12 +597,28 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   p.lse = d->lse;
   p.targets = d->targets;
   p.grad_scale = d->grad_scale;
+  p.out_pre = d->out_pre;
+  p.aux = d->aux;
+  p.ldaux = d->ldaux;
   cudaStream_t st = as_stream(stream);
+  if (chunked) {
+    p.chunk_kb = d->k_chunk / kBK;
+    switch (d->act) {
+      case BLM_ACT_NONE: return launch_chunk<BLM_ACT_NONE>(p, st);
+      case BLM_ACT_GELU: return launch_chunk<BLM_ACT_GELU>(p, st);
+      case BLM_ACT_GPMIX: return launch_chunk<BLM_ACT_GPMIX>(p, st);
+      case BLM_ACT_GELU_GRAD: return launch_chunk<BLM_ACT_GELU_GRAD>(p, st);
+      case BLM_ACT_GPMIX_GRAD: return launch_chunk<BLM_ACT_GPMIX_GRAD>(p, st);
+      default: return launch_chunk<BLM_ACT_SOFTMAX_GRAD>(p, st);
+    }
+  }
   if (BN == 256) {
     switch (d->act) {
       case BLM_ACT_NONE: return launch<256, kStages256, EPI_STORE, BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU>(p, st);
       case BLM_ACT_GPMIX: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+      case BLM_ACT_GELU_GRAD: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU_GRAD>(p, st);
+      case BLM_ACT_GPMIX_GRAD: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX_GRAD>(p, st);
       default: return launch<256, kStages256, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>(p, st);
     }
   }
@@ -520,6 +626,8 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
     case BLM_ACT_NONE: return launch<128, kStages128, EPI_STORE, BLM_ACT_NONE>(p, st);
     case BLM_ACT_GELU: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU>(p, st);
     case BLM_ACT_GPMIX: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>(p, st);
+    case BLM_ACT_GELU_GRAD: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU_GRAD>(p, st);
+    case BLM_ACT_GPMIX_GRAD: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX_GRAD>(p, st);
     default: return launch<128, kStages128, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>(p, st);
   }
 }

@@ -33,6 +33,10 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldc;
+  int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk
+  float* out_pre;       // fp32 copy of the value BEFORE the activation (training: saved pre-activation)
+  const float* aux;     // [M, N] fp32, leading dimension ldaux: the pre-activation the *_GRAD epilogues differentiate at
+  long long ldaux;
   // BLM_ACT_SOFTMAX_GRAD: dZ = (softmax - onehot) * grad_scale, softmax = exp(z - lse[m])
   const float* lse;
   float grad_scale;
@@ -88,6 +92,28 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x >= 0.0f ? x - w : w;
 }
 
+// d/dz of the exact-erf GELU: Phi(z) + z phi(z), with erfc from the same fit as gelu_fast
+__device__ __forceinline__ float gelu_grad(float z) {
+  const float t = fminf(fabsf(z) * 0.70710678118654752440f, 4.0f);
+  float q = fmaf(t, -1.002195230e-04f, 4.615629764e-04f);
+  q = fmaf(q, t, 2.302262028e-03f);
+  q = fmaf(q, t, -2.945254180e-02f);
+  q = fmaf(q, t, 1.489636837e-01f);
+  q = fmaf(q, t, 9.183286407e-01f);
+  q = fmaf(q, t, 1.627913732e+00f);
+  const float half_erfc = 0.5f * ex2_approx(-(q * t));
+  const float Phi = z >= 0.0f ? 1.0f - half_erfc : half_erfc;
+  const float phi = 0.3989422804014327f * ex2_approx(z * z * -0.7213475204444817f);
+  return fmaf(z, phi, Phi);
+}
+
+// d/dz of sum_i coef[i, n] act_i(z), acts tanh, sigmoid, relu, gelu (model.py:1893-1899)
+__device__ __forceinline__ float gpmix_grad(float z, const float* __restrict__ coef, int N, int n) {
+  const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n), c3 = __ldg(coef + 3 * N + n);
+  const float th = tanhf(z), sg = 1.0f / (1.0f + expf(-z));
+  return c0 * (1.0f - th * th) + c1 * sg * (1.0f - sg) + (z > 0.0f ? c2 : 0.0f) + c3 * gelu_grad(z);
+}
+
 template <int ACT>
 __device__ __forceinline__ float apply_act(float z, const float* __restrict__ coef, int N, int n) {
   if constexpr (ACT == BLM_ACT_GELU) {
@@ -129,12 +155,28 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.col_scale_cols) v[j] *= p.col_scale;
     }
+    if (p.out_pre) {
+      float* o = p.out_pre + static_cast<long long>(m) * p.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
     if constexpr (ACT == BLM_ACT_SOFTMAX_GRAD) {
       const float nl = -__ldg(p.lse + m) * 1.4426950408889634f;
       const int rel = __ldg(p.targets + m) - col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         v[j] = (ex2_approx(fmaf(v[j], 1.4426950408889634f, nl)) - (j == rel ? 1.0f : 0.0f)) * p.grad_scale;
+    } else if constexpr (ACT == BLM_ACT_GELU_GRAD || ACT == BLM_ACT_GPMIX_GRAD) {
+      const float* a = p.aux + static_cast<long long>(m) * p.ldaux + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 z = __ldg(reinterpret_cast<const float4*>(a + j));
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          v[j + q] *= (ACT == BLM_ACT_GELU_GRAD) ? gelu_grad(zz[q]) : gpmix_grad(zz[q], p.coef, p.N, col0 + j + q);
+      }
     } else if constexpr (ACT != BLM_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
@@ -188,9 +230,14 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       float z = v[j];
       if (p.bias) z += __ldg(p.bias + col);
       if (col < p.col_scale_cols) z *= p.col_scale;
+      if (p.out_pre) p.out_pre[off + j] = z;
       if constexpr (ACT == BLM_ACT_SOFTMAX_GRAD) {
         z = (ex2_approx((z - __ldg(p.lse + m)) * 1.4426950408889634f) - (col == __ldg(p.targets + m) ? 1.0f : 0.0f)) *
             p.grad_scale;
+      } else if constexpr (ACT == BLM_ACT_GELU_GRAD) {
+        z *= gelu_grad(__ldg(p.aux + static_cast<long long>(m) * p.ldaux + col));
+      } else if constexpr (ACT == BLM_ACT_GPMIX_GRAD) {
+        z *= gpmix_grad(__ldg(p.aux + static_cast<long long>(m) * p.ldaux + col), p.coef, p.N, col);
       } else {
         z = apply_act<ACT>(z, p.coef, p.N, col);
       }

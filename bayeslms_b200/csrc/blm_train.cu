@@ -1,0 +1,767 @@
+// Backward twins and the optimiser of the fine-tune step (reference train.py:306-438; SURVEY.md 8
+// row a19).  The contractions of the backward pass (dgrad, wgrad) run on the tcgen05 GEMM of
+// blm_gemm.cu with transposed bf16 operand copies made here; everything in this file is the
+// HBM-bound glue around them: transposes, column sums, LayerNorm / attention / activation
+// backward, the variational hidden-noise layer, reparameterisation and KL gradients, the embedding
+// scatter, the global gradient norm and the SGD-momentum update.  All reductions have a fixed
+// order (deterministic) except the embedding scatter (fp32 atomics).
+#include "blm_host.h"
+#include "blm_ptx.cuh"
+#include "blm_philox.cuh"
+
+namespace blm {
+
+static int tgrid(long long items, int threads, int per_sm) {
+  long long blocks = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------ transposes
+// out[c, r] = bf16 split of x[r, c]; 32 x 32 tiles through shared memory, both sides coalesced.
+template <typename Src>
+__global__ void __launch_bounds__(256) transpose_kernel(const Src* __restrict__ x_hi, const Src* __restrict__ x_lo,
+                                                        long long ldx, long long R, long long C,
+                                                        __nv_bfloat16* __restrict__ out_hi,
+                                                        __nv_bfloat16* __restrict__ out_lo, long long ldo) {
+  __shared__ float tile[32][33];
+  const long long tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long long t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long r = r0 + ty + 8 * k, c = c0 + tx;
+      float v = 0.0f;
+      if (r < R && c < C) {
+        if constexpr (sizeof(Src) == 4) {
+          v = reinterpret_cast<const float*>(x_hi)[r * ldx + c];
+        } else {
+          v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_hi)[r * ldx + c]);
+          if (x_lo) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_lo)[r * ldx + c]);
+        }
+      }
+      tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long c = c0 + ty + 8 * k, r = r0 + tx;
+      if (c < C && r < R) {
+        const float v = tile[tx][ty + 8 * k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out_hi[c * ldo + r] = h;
+        if (out_lo) out_lo[c * ldo + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ column sums
+// out[n] (+)= scale * sum_m x[m, n]: CTA = 32 columns x 8 row lanes, fixed summation order.
+template <typename Src>
+__global__ void __launch_bounds__(256) colsum_kernel(const Src* __restrict__ x_hi, const Src* __restrict__ x_lo,
+                                                     long long ldx, long long M, long long N, float scale,
+                                                     int accumulate, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long n0 = static_cast<long long>(blockIdx.x) * 32; n0 < N; n0 += static_cast<long long>(gridDim.x) * 32) {
+    const long long n = n0 + tx;
+    float s = 0.0f;
+    if (n < N) {
+      for (long long m = ty; m < M; m += 8) {
+        if constexpr (sizeof(Src) == 4) {
+          s += reinterpret_cast<const float*>(x_hi)[m * ldx + n];
+        } else {
+          float v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_hi)[m * ldx + n]);
+          if (x_lo) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_lo)[m * ldx + n]);
+          s += v;
+        }
+      }
+    }
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+      float t = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += part[k][tx];
+      t *= scale;
+      out[n] = accumulate ? out[n] + t : t;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// One warp per row: recompute mean / rstd of the LayerNorm input x, then
+//   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat;  dbeta += dy.
+// Per-CTA partial (dgamma, dbeta) go to the workspace; the second kernel folds them in block order.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, float eps, long long M,
+                                                            int d, float* __restrict__ dx,
+                                                            float* __restrict__ partial /* [grid, 2, d] */) {
+  extern __shared__ float sred[];  // [8 warps][2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * 8;
+  const float inv_d = 1.0f / static_cast<float>(d);
+  float4 ag[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long m = static_cast<long long>(blockIdx.x) * 8 + warp; m < M; m += warps) {
+    const float* xr = x + m * d;
+    const float* dr = dy + m * d;
+    float4 v[MAXV], g[MAXV], w[MAXV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        v[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
+        w[i] = __ldg(reinterpret_cast<const float4*>(dr + c));
+        g[i] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+        ag[i].x += w[i].x * v[i].x; ag[i].y += w[i].y * v[i].y; ag[i].z += w[i].z * v[i].z; ag[i].w += w[i].w * v[i].w;
+        ab[i].x += w[i].x; ab[i].y += w[i].y; ab[i].z += w[i].z; ab[i].w += w[i].w;
+        w[i].x *= g[i].x; w[i].y *= g[i].y; w[i].z *= g[i].z; w[i].w *= g[i].w;  // g * dy
+        s1 += (w[i].x + w[i].y) + (w[i].z + w[i].w);
+        s2 += (w[i].x * v[i].x + w[i].y * v[i].y) + (w[i].z * v[i].z + w[i].w * v[i].w);
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_d, m2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 o;
+        o.x = rstd * (w[i].x - m1 - v[i].x * m2);
+        o.y = rstd * (w[i].y - m1 - v[i].y * m2);
+        o.z = rstd * (w[i].z - m1 - v[i].z * m2);
+        o.w = rstd * (w[i].w - m1 - v[i].w * m2);
+        *reinterpret_cast<float4*>(dx + m * d + c) = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      *reinterpret_cast<float4*>(sred + (warp * 2 + 0) * d + c) = ag[i];
+      *reinterpret_cast<float4*>(sred + (warp * 2 + 1) * d + c) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * d; c += 256) {
+    const int which = c / d, col = c - which * d;
+    float t = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += sred[(wv * 2 + which) * d + col];
+    partial[(static_cast<long long>(blockIdx.x) * 2 + which) * d + col] = t;
+  }
+}
+
+__global__ void layernorm_bwd_fold_kernel(const float* __restrict__ partial, int blocks, int d, int accumulate,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * d) return;
+  const int which = c / d, col = c - which * d;
+  float t = 0.0f;
+  for (int b = 0; b < blocks; ++b) t += partial[(static_cast<long long>(b) * 2 + which) * d + col];
+  float* out = which == 0 ? dgamma : dbeta;
+  out[col] = accumulate ? out[col] + t : t;
+}
+
+// ------------------------------------------------------------------ attention backward
+// One CTA per (sequence, head), T <= 128, head_dim 64, fp32.  q, k, v, dO of the head are staged in
+// shared memory (rows padded to 65 floats).  Phase 1 (warp per query row i): recompute the softmax
+// statistics (m_i, l_i), D_i = sum_j p_ij dP_ij, and dq_i = sum_j dS_ij k_j.  Phase 2 (warp per key
+// row j): dk_j = sum_{i >= j} dS_ij q_i, dv_j = sum_{i >= j} p_ij dO_i, with p and dS recomputed from
+// the stored row statistics -- no T x T matrix is kept.  dq is multiplied by q_scale (the forward
+// scaled q after the projection, model.py:877).
+constexpr int kBwdHd = 64;
+__global__ void __launch_bounds__(256) mha_causal_bwd_kernel(const float* __restrict__ qkv, long long ld,
+                                                             const float* __restrict__ dout, long long ldo,
+                                                             const int* __restrict__ seq_offsets, int nhead,
+                                                             int max_len, float q_scale, float* __restrict__ dqkv,
+                                                             long long ldd) {
+  extern __shared__ float sm[];
+  constexpr int HP = kBwdHd + 1;
+  const int seq = blockIdx.x / nhead, head = blockIdx.x - seq * nhead;
+  const int row0 = seq_offsets[seq];
+  const int T = seq_offsets[seq + 1] - row0;
+  if (T > max_len) {
+    if (threadIdx.x == 0) printf("blm: sequence %d has %d tokens > max_len %d\n", seq, T, max_len);
+    __trap();
+  }
+  const int d = nhead * kBwdHd;
+  float* sQ = sm;
+  float* sK = sQ + max_len * HP;
+  float* sV = sK + max_len * HP;
+  float* sG = sV + max_len * HP;          // dO
+  float* sM = sG + max_len * HP;          // row max
+  float* sL = sM + max_len;               // row sum
+  float* sD = sL + max_len;               // D_i
+  float* sP = sD + max_len;               // [8 warps][max_len] scratch
+  for (int idx = threadIdx.x; idx < T * kBwdHd; idx += 256) {
+    const int t = idx / kBwdHd, c = idx - t * kBwdHd;
+    const float* base = qkv + static_cast<long long>(row0 + t) * ld + head * kBwdHd + c;
+    sQ[t * HP + c] = __ldg(base);
+    sK[t * HP + c] = __ldg(base + d);
+    sV[t * HP + c] = __ldg(base + 2 * d);
+    sG[t * HP + c] = __ldg(dout + static_cast<long long>(row0 + t) * ldo + head * kBwdHd + c);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = sP + warp * max_len;
+  // ---- phase 1: per query row
+  for (int i = warp; i < T; i += 8) {
+    const float* q = sQ + i * HP;
+    const float* go = sG + i * HP;
+    float mx = -INFINITY;
+    for (int j = lane; j <= i; j += 32) {
+      const float* k = sK + j * HP;
+      float s = 0.0f;
+#pragma unroll 16
+      for (int c = 0; c < kBwdHd; ++c) s = fmaf(q[c], k[c], s);
+      pr[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j <= i; j += 32) sum += expf(pr[j] - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float dsum = 0.0f;
+    for (int j = lane; j <= i; j += 32) {
+      const float* v = sV + j * HP;
+      float dp = 0.0f;
+#pragma unroll 16
+      for (int c = 0; c < kBwdHd; ++c) dp = fmaf(go[c], v[c], dp);
+      const float p = expf(pr[j] - mx) * inv;
+      pr[j] = p * dp;      // p_ij dP_ij, finished below once D_i is known
+      dsum += p * dp;
+      // keep p in the upper half of the scratch row? not needed: dS = p dP - p D
+      sP[8 * max_len + warp * max_len + j] = p;
+    }
+    const float D = warp_sum(dsum);
+    if (lane == 0) {
+      sM[i] = mx;
+      sL[i] = inv;
+      sD[i] = D;
+    }
+    __syncwarp();
+    // dq_i[c] = sum_j (p dP - p D)_j k_j[c]; lanes split the 64 columns
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int j = 0; j <= i; ++j) {
+      const float ds = pr[j] - sP[8 * max_len + warp * max_len + j] * D;
+      a0 = fmaf(ds, sK[j * HP + lane], a0);
+      a1 = fmaf(ds, sK[j * HP + lane + 32], a1);
+    }
+    float* o = dqkv + static_cast<long long>(row0 + i) * ldd + head * kBwdHd;
+    o[lane] = a0 * q_scale;
+    o[lane + 32] = a1 * q_scale;
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- phase 2: per key row
+  for (int j = warp; j < T; j += 8) {
+    const float* k = sK + j * HP;
+    const float* v = sV + j * HP;
+    float* ps = sP + warp * max_len;                 // p_ij for i >= j
+    float* dss = sP + 8 * max_len + warp * max_len;  // dS_ij
+    for (int i = j + lane; i < T; i += 32) {
+      const float* q = sQ + i * HP;
+      const float* go = sG + i * HP;
+      float s = 0.0f, dp = 0.0f;
+#pragma unroll 16
+      for (int c = 0; c < kBwdHd; ++c) {
+        s = fmaf(q[c], k[c], s);
+        dp = fmaf(go[c], v[c], dp);
+      }
+      const float p = expf(s - sM[i]) * sL[i];
+      ps[i] = p;
+      dss[i] = p * (dp - sD[i]);
+    }
+    __syncwarp();
+    float k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
+    for (int i = j; i < T; ++i) {
+      const float p = ps[i], ds = dss[i];
+      k0 = fmaf(ds, sQ[i * HP + lane], k0);
+      k1 = fmaf(ds, sQ[i * HP + lane + 32], k1);
+      v0 = fmaf(p, sG[i * HP + lane], v0);
+      v1 = fmaf(p, sG[i * HP + lane + 32], v1);
+    }
+    float* o = dqkv + static_cast<long long>(row0 + j) * ldd + head * kBwdHd;
+    o[d + lane] = k0;
+    o[d + lane + 32] = k1;
+    o[2 * d + lane] = v0;
+    o[2 * d + lane + 32] = v1;
+    __syncwarp();
+  }
+}
+
+static size_t mha_bwd_smem_bytes(int max_len) {
+  return sizeof(float) * (4ull * max_len * (kBwdHd + 1) + 3ull * max_len + 16ull * max_len);
+}
+
+// ------------------------------------------------------------------ activation column gradients
+// GP mixture: dcoef[i, n] (+)= sum_m dh[m, n] * act_i(z[m, n])   (acts tanh, sigmoid, relu, gelu)
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(256) gpmix_dcoef_kernel(const float* __restrict__ z, const float* __restrict__ dh,
+                                                          long long ld, long long M, long long N, int accumulate,
+                                                          float* __restrict__ dcoef) {
+  __shared__ float part[8][4][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long n0 = static_cast<long long>(blockIdx.x) * 32; n0 < N; n0 += static_cast<long long>(gridDim.x) * 32) {
+    const long long n = n0 + tx;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+      for (long long m = ty; m < M; m += 8) {
+        const float zz = z[m * ld + n], g = dh[m * ld + n];
+        s[0] += g * tanhf(zz);
+        s[1] += g * (1.0f / (1.0f + expf(-zz)));
+        s[2] += g * fmaxf(zz, 0.0f);
+        s[3] += g * gelu_exact(zz);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part[ty][i][tx] = s[i];
+    __syncthreads();
+    if (ty < 4 && n < N) {
+      float t = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += part[k][ty][tx];
+      float* o = dcoef + ty * N + n;
+      *o = accumulate ? *o + t : t;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ variational hidden noise
+// forward:  fp = f + e * exp(f * rho[t]),  e = explicit noise or noise_std * Philox normal; row m = b*T + t
+__global__ void vnoise_fwd_kernel(const float* __restrict__ f, const float* __restrict__ rho,
+                                  const float* __restrict__ eps, int eps_mode, uint64_t seed, uint64_t stream,
+                                  float noise_std, long long M, int T, int d, float* __restrict__ fp) {
+  const long long n4 = M * d / 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long m = (i * 4) / d;
+    const int c = static_cast<int>(i * 4 - m * d);
+    const int t = static_cast<int>(m % T);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(f) + i);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(rho + static_cast<long long>(t) * d + c));
+    float4 e;
+    if (eps_mode == BLM_EPS_PTR) {
+      e = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    } else {
+      e = philox_normal4(seed, stream, static_cast<uint64_t>(i));
+      e.x *= noise_std; e.y *= noise_std; e.z *= noise_std; e.w *= noise_std;
+    }
+    float4 o;
+    o.x = fmaf(e.x, expf(x.x * r.x), x.x);
+    o.y = fmaf(e.y, expf(x.y * r.y), x.y);
+    o.z = fmaf(e.z, expf(x.z * r.z), x.z);
+    o.w = fmaf(e.w, expf(x.w * r.w), x.w);
+    *(reinterpret_cast<float4*>(fp) + i) = o;
+  }
+}
+
+// backward + KL: thread per (t, c), fixed-order loop over the B sequences.
+//   KL = 0.5 * mean_{T,B,d}( ((1 - mp) fp)^2 - 2 rho + exp(2 rho) ),  klc = kl_scale / (T*B*d)
+//   g  = dfp + klc * (1 - mp)^2 fp            (loss gradient w.r.t. fp, KL term included)
+//   df = g * (1 + e rho E),  E = exp(f rho);  drho = sum_b g e f E + klc * B * (exp(2 rho) - 1)
+//   dmp = -klc * sum_b (1 - mp) fp^2;         klpart[t, c] = sum_b ((1-mp) fp)^2 + B (exp(2 rho) - 2 rho)
+__global__ void vnoise_bwd_kernel(const float* __restrict__ dfp, const float* __restrict__ f,
+                                  const float* __restrict__ rho, const float* __restrict__ mean_p,
+                                  const float* __restrict__ eps, int eps_mode, uint64_t seed, uint64_t stream,
+                                  float noise_std, int B, int T, int d, float klc, float* __restrict__ df,
+                                  float* __restrict__ drho, float* __restrict__ dmean_p, float* __restrict__ klpart) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * d) return;
+  const int t = idx / d, c = idx - t * d;
+  const float r = rho[idx], mp = mean_p[idx];
+  const float om = 1.0f - mp;
+  float a_rho = 0.0f, a_mp = 0.0f, a_kl = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const long long o = (static_cast<long long>(b) * T + t) * d + c;
+    const float x = f[o];
+    float e;
+    if (eps_mode == BLM_EPS_PTR) {
+      e = eps[o];
+    } else {
+      const float4 z = philox_normal4(seed, stream, static_cast<uint64_t>(o >> 2));
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+      e = zz[o & 3] * noise_std;
+    }
+    const float E = expf(x * r);
+    const float y = fmaf(e, E, x);  // fp
+    const float g = (dfp ? dfp[o] : 0.0f) + klc * om * om * y;
+    df[o] = g * (1.0f + e * r * E);
+    a_rho = fmaf(g * e, x * E, a_rho);
+    a_mp = fmaf(om * y, y, a_mp);
+    a_kl = fmaf(om * y, om * y, a_kl);
+  }
+  const float e2 = expf(2.0f * r);
+  drho[idx] = a_rho + klc * static_cast<float>(B) * (e2 - 1.0f);
+  dmean_p[idx] = -klc * a_mp;
+  klpart[idx] = a_kl + static_cast<float>(B) * (e2 - 2.0f * r);
+}
+
+// ------------------------------------------------------------------ embedding scatter
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ tok, float scale, long long M,
+                                 int d, float* __restrict__ dE) {
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+    float* e = dE + static_cast<long long>(__ldg(tok + m)) * d;
+    for (int c = lane; c < d; c += 32) atomicAdd(e + c, dx[m * d + c] * scale);
+  }
+}
+
+// ------------------------------------------------------------------ KL / reparameterisation gradients
+// dmu += coef * mu;  dlgstd += coef * (exp(2 lgstd) - 1)
+__global__ void kl_bwd_kernel(const float* __restrict__ mu, long long ldmu, const float* __restrict__ lgstd,
+                              long long rows, long long cols, float coef, float* __restrict__ dmu, long long lddmu,
+                              float* __restrict__ dlgstd) {
+  const long long n = rows * cols;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long r = i / cols, c = i - r * cols;
+    dmu[r * lddmu + c] += coef * mu[r * ldmu + c];
+    dlgstd[i] += coef * (expf(2.0f * lgstd[i]) - 1.0f);
+  }
+}
+
+// G = dL/dW~ : dmu (+)= G ; dlgstd (+)= G * eps * exp(lgstd)
+__global__ void reparam_bwd_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ lgstd,
+                                   const float* __restrict__ eps, int eps_mode, uint64_t seed, uint64_t stream,
+                                   long long rows, long long cols, int accumulate, float* __restrict__ dmu,
+                                   long long lddmu, float* __restrict__ dlgstd) {
+  const long long c4 = cols / 4, n4 = rows * c4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long r = i / c4, c = (i - r * c4) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(G + r * ldg + c);
+    const float4 ls = __ldg(reinterpret_cast<const float4*>(lgstd + r * cols + c));
+    float4 e;
+    if (eps_mode == BLM_EPS_PTR)
+      e = __ldg(reinterpret_cast<const float4*>(eps + r * cols + c));
+    else
+      e = philox_normal4(seed, stream, static_cast<uint64_t>(i));
+    float4* pm = reinterpret_cast<float4*>(dmu + r * lddmu + c);
+    float4* ps = reinterpret_cast<float4*>(dlgstd + r * cols + c);
+    float4 m = accumulate ? *pm : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s = accumulate ? *ps : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dmu != G || accumulate) {
+      m.x += g.x; m.y += g.y; m.z += g.z; m.w += g.w;
+      *pm = m;
+    }
+    s.x += g.x * e.x * __expf(ls.x);
+    s.y += g.y * e.y * __expf(ls.y);
+    s.z += g.z * e.z * __expf(ls.z);
+    s.w += g.w * e.w * __expf(ls.w);
+    *ps = s;
+  }
+}
+
+// ------------------------------------------------------------------ reductions + optimiser
+struct ReduceWs {
+  unsigned int counter;
+  unsigned int pad;
+  double partial[1024];
+};
+
+// out[0] (+)= scale * sum x   (mode 0)   or   scale * sum x^2   (mode 1)
+__global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ x, long long n, int mode, float scale,
+                                                     int accumulate, float* __restrict__ out,
+                                                     ReduceWs* __restrict__ ws) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  double acc = 0.0;
+  float a = 0.0f;
+  int cnt = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    a += mode ? v * v : v;
+    if (++cnt == 64) {  // bound the fp32 run length
+      acc += static_cast<double>(a);
+      a = 0.0f;
+      cnt = 0;
+    }
+  }
+  acc += static_cast<double>(a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double wsum[8];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) wsum[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+    for (int w = 0; w < 8; ++w) b += wsum[w];
+    ws->partial[blockIdx.x] = b;
+    __threadfence();
+    is_last = (atomicAdd(&ws->counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) t += ws->partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      const float r = static_cast<float>(t * static_cast<double>(scale));
+      out[0] = accumulate ? out[0] + r : r;
+      ws->counter = 0;
+    }
+  }
+}
+
+// torch.nn.utils.clip_grad_norm_ + SGD(momentum) of train.py:419,466:
+//   c = min(1, max_norm / (sqrt(norm_sq) * grad_scale + 1e-6));  g' = c * grad_scale * g
+//   v = momentum * v + g';  p -= lr * v
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
+                                    long long n, float lr, float momentum, const float* __restrict__ norm_sq,
+                                    float max_norm, float grad_scale) {
+  float c = grad_scale;
+  if (norm_sq && max_norm > 0.0f) {
+    const float norm = sqrtf(norm_sq[0]) * grad_scale;
+    c *= fminf(1.0f, max_norm / (norm + 1e-6f));
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float nv = fmaf(momentum, v[i], c * g[i]);
+    v[i] = nv;
+    p[i] = fmaf(-lr, nv, p[i]);
+  }
+}
+
+int train_init() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(mha_bwd_smem_bytes(128))));
+  return BLM_OK;
+}
+
+}  // namespace blm
+
+extern "C" {
+
+int blm_transpose_split(const float* x, int64_t ldx, int64_t R, int64_t C, blm_bf16* out_hi, blm_bf16* out_lo,
+                        int64_t ldo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(x && out_hi && R > 0 && C > 0 && ldx >= C && ldo >= R, BLM_ERR_ARG, "bad transpose arguments");
+  transpose_kernel<float><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
+      x, nullptr, ldx, R, C, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_transpose_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t R, int64_t C, blm_bf16* out_hi,
+                       blm_bf16* out_lo, int64_t ldo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(hi && out_hi && R > 0 && C > 0 && ld >= C && ldo >= R, BLM_ERR_ARG, "bad transpose arguments");
+  transpose_kernel<__nv_bfloat16><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), ld, R, C,
+      reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_colsum(const float* x, int64_t ldx, int64_t M, int64_t N, float scale, int32_t accumulate, float* out,
+               blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(x && out && M > 0 && N > 0 && ldx >= N, BLM_ERR_ARG, "bad colsum arguments");
+  colsum_kernel<float><<<tgrid((N + 31) / 32, 1, 8), 256, 0, as_stream(stream)>>>(x, nullptr, ldx, M, N, scale,
+                                                                                accumulate, out);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_colsum_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t M, int64_t N, float scale,
+                    int32_t accumulate, float* out, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(hi && out && M > 0 && N > 0 && ld >= N, BLM_ERR_ARG, "bad colsum arguments");
+  colsum_kernel<__nv_bfloat16><<<tgrid((N + 31) / 32, 1, 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), ld, M, N, scale,
+      accumulate, out);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+static int ln_bwd_blocks(int64_t M) {
+  const int cap = (blm::num_sms() > 0 ? blm::num_sms() : 148) * 2;
+  const int64_t need = (M + 7) / 8;
+  return static_cast<int>(need < cap ? need : cap);
+}
+
+int64_t blm_layernorm_bwd_workspace_bytes(int64_t M, int32_t d) {
+  (void)M;
+  return static_cast<int64_t>(148 * 2 * 2) * d * static_cast<int64_t>(sizeof(float)) * 2;
+}
+
+int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t M, int32_t d,
+                      float* dx, float* dgamma, float* dbeta, int32_t accumulate, void* workspace,
+                      blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && workspace && M > 0, BLM_ERR_ARG, "bad layernorm_bwd arguments");
+  BLM_REQUIRE((d % 4) == 0 && d > 0 && d <= 1024, BLM_ERR_SHAPE, "layernorm_bwd width %d must be a multiple of 4 and <= 1024", d);
+  BLM_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx) && aligned16(workspace), BLM_ERR_ALIGN,
+              "layernorm_bwd pointers must be 16-byte aligned");
+  const int blocks = ln_bwd_blocks(M);
+  float* partial = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = sizeof(float) * 8 * 2 * d;
+  if (d <= 512) {
+    BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    layernorm_bwd_kernel<4><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
+  } else {
+    BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    layernorm_bwd_kernel<8><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
+  }
+  BLM_CHECK_CUDA(cudaGetLastError());
+  layernorm_bwd_fold_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>(partial, blocks, d, accumulate, dgamma, dbeta);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_mha_causal_bwd(const float* qkv, int64_t ld, const float* dout, int64_t ldo, const int32_t* seq_offsets,
+                       int64_t nseq, int32_t nhead, int32_t head_dim, int32_t max_len, float q_scale, float* dqkv,
+                       int64_t ldd, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(qkv && dout && seq_offsets && dqkv && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention-backward arguments");
+  BLM_REQUIRE(head_dim == kBwdHd, BLM_ERR_SHAPE, "attention backward needs head_dim 64, got %d", head_dim);
+  BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
+  static bool attr = false;
+  if (!attr) {
+    int rc = train_init();
+    if (rc != BLM_OK) return rc;
+    attr = true;
+  }
+  mha_causal_bwd_kernel<<<static_cast<unsigned>(nseq * nhead), 256, mha_bwd_smem_bytes(max_len), as_stream(stream)>>>(
+      qkv, ld, dout, ldo, seq_offsets, nhead, max_len, q_scale, dqkv, ldd);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_gpmix_dcoef(const float* z, const float* dh, int64_t ld, int64_t M, int64_t N, int32_t accumulate,
+                    float* dcoef, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(z && dh && dcoef && M > 0 && N > 0 && ld >= N, BLM_ERR_ARG, "bad gpmix_dcoef arguments");
+  gpmix_dcoef_kernel<<<tgrid((N + 31) / 32, 1, 8), 256, 0, as_stream(stream)>>>(z, dh, ld, M, N, accumulate, dcoef);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_vnoise_fwd(const float* f, const float* rho, const float* eps, int32_t eps_mode, uint64_t seed,
+                   uint64_t stream_id, float noise_std, int64_t B, int32_t T, int32_t d, float* fp,
+                   blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(f && rho && fp && B > 0 && T > 0 && d > 0 && (d % 4) == 0, BLM_ERR_ARG, "bad vnoise arguments");
+  BLM_REQUIRE(eps_mode == BLM_EPS_PHILOX || (eps_mode == BLM_EPS_PTR && eps), BLM_ERR_ARG, "bad eps_mode %d", eps_mode);
+  vnoise_fwd_kernel<<<tgrid(B * T * d / 4, 256, 8), 256, 0, as_stream(stream)>>>(f, rho, eps, eps_mode, seed, stream_id,
+                                                                              noise_std, B * T, T, d, fp);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_vnoise_bwd(const float* dfp, const float* f, const float* rho, const float* mean_p, const float* eps,
+                   int32_t eps_mode, uint64_t seed, uint64_t stream_id, float noise_std, int64_t B, int32_t T,
+                   int32_t d, float kl_scale, float* df, float* drho, float* dmean_p, float* klpart,
+                   blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(f && rho && mean_p && df && drho && dmean_p && klpart && B > 0 && T > 0 && d > 0, BLM_ERR_ARG,
+              "bad vnoise_bwd arguments");
+  BLM_REQUIRE(eps_mode == BLM_EPS_PHILOX || (eps_mode == BLM_EPS_PTR && eps), BLM_ERR_ARG, "bad eps_mode %d", eps_mode);
+  const float klc = kl_scale / (static_cast<float>(B) * static_cast<float>(T) * static_cast<float>(d));
+  vnoise_bwd_kernel<<<(T * d + 127) / 128, 128, 0, as_stream(stream)>>>(dfp, f, rho, mean_p, eps, eps_mode, seed, stream_id,
+                                                                      noise_std, static_cast<int>(B), T, d, klc, df, drho,
+                                                                      dmean_p, klpart);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_embed_bwd(const float* dx, const int32_t* tokens, float scale, int64_t M, int32_t d, float* dE,
+                  blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(dx && tokens && dE && M > 0 && d > 0, BLM_ERR_ARG, "bad embed_bwd arguments");
+  embed_bwd_kernel<<<tgrid(M * 32, 256, 8), 256, 0, as_stream(stream)>>>(dx, tokens, scale, M, d, dE);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_kl_gauss_bwd(const float* mu, int64_t ldmu, const float* lgstd, int64_t rows, int64_t cols, float scale,
+                     float* dmu, int64_t lddmu, float* dlgstd, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(mu && lgstd && dmu && dlgstd && rows > 0 && cols > 0, BLM_ERR_ARG, "bad kl_bwd arguments");
+  const float coef = scale / (static_cast<float>(rows) * static_cast<float>(cols));
+  kl_bwd_kernel<<<tgrid(rows * cols, 256, 8), 256, 0, as_stream(stream)>>>(mu, ldmu, lgstd, rows, cols, coef, dmu, lddmu,
+                                                                        dlgstd);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_reparam_bwd(const float* G, int64_t ldg, const float* lgstd, const float* eps, int32_t eps_mode,
+                    uint64_t seed, uint64_t stream_id, int64_t rows, int64_t cols, int32_t accumulate, float* dmu,
+                    int64_t lddmu, float* dlgstd, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(G && lgstd && dmu && dlgstd && rows > 0 && cols > 0, BLM_ERR_ARG, "bad reparam_bwd arguments");
+  BLM_REQUIRE(eps_mode == BLM_EPS_PHILOX || (eps_mode == BLM_EPS_PTR && eps), BLM_ERR_ARG, "bad eps_mode %d", eps_mode);
+  BLM_REQUIRE((cols % 4) == 0 && (ldg % 4) == 0 && (lddmu % 4) == 0, BLM_ERR_SHAPE, "reparam_bwd needs cols, ld %% 4 == 0");
+  BLM_REQUIRE(aligned16(G) && aligned16(lgstd) && aligned16(eps) && aligned16(dmu) && aligned16(dlgstd), BLM_ERR_ALIGN,
+              "reparam_bwd pointers must be 16-byte aligned");
+  reparam_bwd_kernel<<<tgrid(rows * cols / 4, 256, 8), 256, 0, as_stream(stream)>>>(
+      G, ldg, lgstd, eps, eps_mode, seed, stream_id, rows, cols, accumulate, dmu, lddmu, dlgstd);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int64_t blm_reduce_workspace_bytes(void) { return static_cast<int64_t>(sizeof(blm::ReduceWs)); }
+
+int blm_reduce(const float* x, int64_t n, int32_t squares, float scale, int32_t accumulate, float* out,
+               void* workspace, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(x && out && workspace && n > 0, BLM_ERR_ARG, "bad reduce arguments");
+  int grid = tgrid(n / 4 + 1, 256, 4);
+  if (grid > 1024) grid = 1024;
+  reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, n, squares, scale, accumulate, out,
+                                                     reinterpret_cast<ReduceWs*>(workspace));
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_sgd_momentum(float* p, const float* g, float* v, int64_t n, float lr, float momentum, const float* norm_sq,
+                     float max_norm, float grad_scale, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(p && g && v && n > 0, BLM_ERR_ARG, "bad sgd arguments");
+  sgd_momentum_kernel<<<tgrid(n, 256, 8), 256, 0, as_stream(stream)>>>(p, g, v, n, lr, momentum, norm_sq, max_norm,
+                                                                      grad_scale);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+}  // extern "C"

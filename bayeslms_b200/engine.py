@@ -202,9 +202,15 @@ class _TmRun:
     # part A: fused QKV projection (q scaled by head_dim^-1/2 after the bias) + causal attention
     def part_a(self, L, xs: Split) -> Split:
         d = self.d
+        scale = float(d // self.nhead) ** -0.5
+        if d // self.nhead == 64:
+            # q, k, v leave the projection as bf16 (hi[, lo]) and feed the tensor-core attention kernel
+            qkv = ops.empty_split(self.M, 3 * d, self.prec, self.dev)
+            ops.gemm(xs, L["qkv"], prec=self.prec, bias=L["qkv_b"], col_scale=scale, col_scale_cols=d, out=qkv, tag="qkv")
+            _, att = ops.mha_causal_bf16(qkv, self.b.offsets, self.nhead, self.b.max_len, prec=self.prec)
+            return att
         qkv = self.f32(3 * d)
-        ops.gemm(xs, L["qkv"], prec=self.prec, bias=L["qkv_b"], col_scale=float(d // self.nhead) ** -0.5,
-                 col_scale_cols=d, out_f32=qkv, tag="qkv")
+        ops.gemm(xs, L["qkv"], prec=self.prec, bias=L["qkv_b"], col_scale=scale, col_scale_cols=d, out_f32=qkv, tag="qkv")
         _, att = ops.mha_causal(qkv, self.b.offsets, self.nhead, self.b.max_len, prec=self.prec)
         return att
 

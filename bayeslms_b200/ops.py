@@ -16,11 +16,13 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_GPMIX, ACT_NONE, EPS_NONE, EPS_PHILOX, EPS_PTR, GemmDesc, GemmSampledDesc,
+from ._lib import (ACT_GELU, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
+                   EPS_PTR, GemmDesc, GemmSampledDesc,
                    VocabNllDesc,
                    check, lib)
 
 PRECISIONS = ("bf16", "bf16x3")
+PRECISE_K_CHUNK = 128   # K elements per tensor-core accumulation in bf16x3 mode (blm_gemm_desc.k_chunk)
 
 
 class _Stats:
@@ -105,16 +107,23 @@ def _segments(a: Split, b: Split, prec: str):
     if prec == "bf16x3":
         if a.lo is None or b.lo is None:
             raise _lib.BlmError("bf16x3 needs (hi, lo) operands")
-        return [(a.hi, b.hi), (a.hi, b.lo), (a.lo, b.hi)]
+        # small cross terms first, hi*hi last: the tensor core truncates on every accumulate, and the
+        # truncation is relative to the running sum
+        return [(a.hi, b.lo), (a.lo, b.hi), (a.hi, b.hi)]
     raise _lib.BlmError(f"unknown precision {prec!r}")
 
 
 def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          coef: Optional[torch.Tensor] = None, col_scale: float = 1.0, col_scale_cols: int = 0,
          resid: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
-         out: Optional[Split] = None, extra: Sequence = (), tag: str = ""):
+         out: Optional[Split] = None, extra: Sequence = (), tag: str = "", out_pre: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
+         targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
-    accumulated into the same output (K-concatenation)."""
+    accumulated into the same output (K-concatenation).  ``out_pre`` receives the fp32 value before
+    the activation; ``aux`` is the saved pre-activation of the ``*_GRAD`` epilogues; ``lse`` /
+    ``targets`` / ``grad_scale`` feed ``ACT_SOFTMAX_GRAD``.  ``k_chunk`` (default: 128 in bf16x3 mode)
+    bounds the length of one tensor-core accumulation (see ``blm_gemm_desc.k_chunk``)."""
     segs = _segments(a, b, prec)
     for (a2, b2) in extra:
         segs += _segments(a2, b2, prec)
@@ -141,6 +150,15 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     d.out_hi = _ptr(None if out is None else out.hi)
     d.out_lo = _ptr(None if out is None else out.lo)
     d.ldc = ldc if ldc is not None else N
+    if out_pre is not None:
+        assert out_pre.dtype == torch.float32 and out_pre.stride(1) == 1 and out_pre.stride(0) == d.ldc
+        d.out_pre = _ptr(out_pre)
+    if aux is not None:
+        assert aux.dtype == torch.float32 and aux.stride(1) == 1
+        d.aux, d.ldaux = _ptr(aux), aux.stride(0)
+    if lse is not None:
+        d.lse, d.targets, d.grad_scale = _ptr(lse), _ptr(targets), grad_scale
+    d.k_chunk = (PRECISE_K_CHUNK if prec == "bf16x3" else 0) if k_chunk is None else k_chunk
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
 
@@ -198,8 +216,9 @@ _nll_ws = {}
 
 
 def vocab_nll(h: Split, e: Split, bias: Optional[torch.Tensor], targets: torch.Tensor, *, prec: str = "bf16",
-              extra: Sequence = (), out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Per-row ``-log softmax(h @ e.T + bias)[target]`` without materialising the logits."""
+              extra: Sequence = (), out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-row ``-log softmax(h @ e.T + bias)[target]`` without materialising the logits.
+    ``lse`` [M] optionally receives the row log-sum-exp (saved for the backward pass)."""
     segs = _segments(h, e, prec)
     for (h2, e2) in extra:
         segs += _segments(h2, e2, prec)
@@ -222,6 +241,7 @@ def vocab_nll(h: Split, e: Split, bias: Optional[torch.Tensor], targets: torch.T
         d.K[i], d.ldh[i], d.lde[i] = x.shape[1], x.stride(0), w.stride(0)
     d.bias, d.targets, d.nll = _ptr(bias), _ptr(targets), _ptr(out)
     d.workspace, d.workspace_bytes = _ptr(ws), ws.numel()
+    d.lse = _ptr(lse)
     with _op("vocab_nll", 2, 2.0 * M * V * sum(x.shape[1] for x, _ in segs)):
         check(lib().blm_vocab_nll(C.byref(d), _stream()), "blm_vocab_nll")
     return out
@@ -328,6 +348,25 @@ def mha_causal(qkv: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len
     return o, s
 
 
+def mha_causal_bf16(qkv: Split, seq_offsets: torch.Tensor, nhead: int, max_len: int, *, prec: str = "bf16",
+                    want_f32: bool = False):
+    """Causal attention on the bf16 (hi[, lo]) output of the QKV projection (tensor-core kernel)."""
+    M, d3 = qkv.hi.shape
+    d = d3 // 3
+    nseq = seq_offsets.numel() - 1
+    lo = qkv.lo if prec == "bf16x3" else None
+    if prec == "bf16x3" and lo is None:
+        raise _lib.BlmError("bf16x3 attention needs the lo part of qkv")
+    assert qkv.hi.stride(1) == 1 and (lo is None or lo.stride() == qkv.hi.stride())
+    o = torch.empty(M, d, dtype=torch.float32, device=qkv.hi.device) if want_f32 else None
+    s = empty_split(M, d, prec, qkv.hi.device)
+    with _op("mha_causal", 1, 0.0):
+        check(lib().blm_mha_causal_bf16(_ptr(qkv.hi), _ptr(lo), qkv.hi.stride(0), _ptr(seq_offsets), nseq, nhead,
+                                        d // nhead, max_len, _ptr(o), _ptr(s.hi), _ptr(s.lo), d, _stream()),
+              "blm_mha_causal_bf16")
+    return o, s
+
+
 _kl_ws = {}
 
 
@@ -374,3 +413,184 @@ def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.T
                                    _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),
                                    _ptr(hT), _ptr(cT), _ptr(ws), _stream()), "blm_lstm_layer")
     return out32, outs, hT, cT
+
+
+# ------------------------------------------------------------------ fine-tune step (backward twins)
+def _ld8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def transpose_split(x: torch.Tensor, prec: str = "bf16x3") -> Split:
+    """fp32 [R, C] -> Split [C, R] (row stride rounded up to 8 elements; use ``[:, :R]`` views)."""
+    R, C = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    ld = _ld8(R)
+    hi = torch.empty(C, ld, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(C, ld, dtype=torch.bfloat16, device=x.device) if prec == "bf16x3" else None
+    with _op("transpose", 1):
+        check(lib().blm_transpose_split(_ptr(x), x.stride(0), R, C, _ptr(hi), _ptr(lo), ld, _stream()), "blm_transpose_split")
+    return Split(hi[:, :R], None if lo is None else lo[:, :R])
+
+
+def transpose_bf16(x: Split, prec: str = "bf16x3") -> Split:
+    """Split [R, C] -> Split [C, R]."""
+    R, C = x.hi.shape
+    assert x.hi.stride(1) == 1
+    ld = _ld8(R)
+    hi = torch.empty(C, ld, dtype=torch.bfloat16, device=x.hi.device)
+    want_lo = prec == "bf16x3" and x.lo is not None
+    lo = torch.empty(C, ld, dtype=torch.bfloat16, device=x.hi.device) if want_lo else None
+    with _op("transpose", 1):
+        check(lib().blm_transpose_bf16(_ptr(x.hi), _ptr(x.lo if want_lo else None), x.hi.stride(0), R, C, _ptr(hi), _ptr(lo),
+                                       ld, _stream()), "blm_transpose_bf16")
+    return Split(hi[:, :R], None if lo is None else lo[:, :R])
+
+
+def colsum(x, out: torch.Tensor, *, scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+    """out[n] (+)= scale * sum_m x[m, n]; x fp32 [M, N] or a Split."""
+    if isinstance(x, Split):
+        M, N = x.hi.shape
+        with _op("colsum", 1):
+            check(lib().blm_colsum_bf16(_ptr(x.hi), _ptr(x.lo), x.hi.stride(0), M, N, scale, int(accumulate), _ptr(out),
+                                        _stream()), "blm_colsum_bf16")
+    else:
+        M, N = x.shape
+        with _op("colsum", 1):
+            check(lib().blm_colsum(_ptr(x), x.stride(0), M, N, scale, int(accumulate), _ptr(out), _stream()), "blm_colsum")
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(kind: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
+    key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, dgamma: torch.Tensor,
+                  dbeta: torch.Tensor, *, accumulate: bool = False) -> torch.Tensor:
+    """Returns dx; x is the LayerNorm input.  dgamma / dbeta are written (or accumulated) in place."""
+    M, d = x.shape
+    assert dy.is_contiguous() and x.is_contiguous()
+    dx = torch.empty_like(x)
+    ws = _workspace("ln_bwd", lib().blm_layernorm_bwd_workspace_bytes(M, d), x.device)
+    with _op("layernorm_bwd", 2):
+        check(lib().blm_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), eps, M, d, _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                      int(accumulate), _ptr(ws), _stream()), "blm_layernorm_bwd")
+    return dx
+
+
+def mha_causal_bwd(qkv: torch.Tensor, dout: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len: int,
+                   q_scale: float) -> torch.Tensor:
+    M, d3 = qkv.shape
+    d = d3 // 3
+    dqkv = torch.empty_like(qkv)
+    with _op("mha_causal_bwd", 1):
+        check(lib().blm_mha_causal_bwd(_ptr(qkv), qkv.stride(0), _ptr(dout), dout.stride(0), _ptr(seq_offsets),
+                                       seq_offsets.numel() - 1, nhead, d // nhead, max_len, q_scale, _ptr(dqkv),
+                                       dqkv.stride(0), _stream()), "blm_mha_causal_bwd")
+    return dqkv
+
+
+def gpmix_dcoef(z: torch.Tensor, dh: torch.Tensor, dcoef: torch.Tensor, *, accumulate: bool = False) -> torch.Tensor:
+    M, N = z.shape
+    assert z.stride() == dh.stride() and dcoef.is_contiguous()
+    with _op("gpmix_dcoef", 1):
+        check(lib().blm_gpmix_dcoef(_ptr(z), _ptr(dh), z.stride(0), M, N, int(accumulate), _ptr(dcoef), _stream()),
+              "blm_gpmix_dcoef")
+    return dcoef
+
+
+def _eps_args(eps, seed):
+    if eps is not None:
+        return _ptr(eps), EPS_PTR, 0
+    if seed is None:
+        raise _lib.BlmError("noise needs an explicit tensor or a Philox seed")
+    return None, EPS_PHILOX, int(seed)
+
+
+def vnoise_fwd(f: torch.Tensor, rho: torch.Tensor, B: int, T: int, *, eps: Optional[torch.Tensor] = None,
+               seed: Optional[int] = None, stream_id: int = 0, noise_std: float = 0.1) -> torch.Tensor:
+    """fp = f + e * exp(f * rho[t]) for sequence-major rows (row = b*T + t); rho [T, d]."""
+    d = f.shape[1]
+    assert f.is_contiguous() and rho.is_contiguous() and f.shape[0] == B * T
+    fp = torch.empty_like(f)
+    e, mode, sd = _eps_args(eps, seed)
+    with _op("vnoise_fwd", 1):
+        check(lib().blm_vnoise_fwd(_ptr(f), _ptr(rho), e, mode, sd, int(stream_id), noise_std, B, T, d, _ptr(fp), _stream()),
+              "blm_vnoise_fwd")
+    return fp
+
+
+def vnoise_bwd(dfp: Optional[torch.Tensor], f: torch.Tensor, rho: torch.Tensor, mean_p: torch.Tensor, B: int, T: int,
+               kl_scale: float, drho: torch.Tensor, dmean_p: torch.Tensor, *, eps: Optional[torch.Tensor] = None,
+               seed: Optional[int] = None, stream_id: int = 0, noise_std: float = 0.1):
+    """Returns (df, klpart [T, d]); writes drho / dmean_p."""
+    d = f.shape[1]
+    df = torch.empty_like(f)
+    klpart = torch.empty(T, d, dtype=torch.float32, device=f.device)
+    e, mode, sd = _eps_args(eps, seed)
+    with _op("vnoise_bwd", 1):
+        check(lib().blm_vnoise_bwd(_ptr(dfp), _ptr(f), _ptr(rho), _ptr(mean_p), e, mode, sd, int(stream_id), noise_std, B, T,
+                                   d, kl_scale, _ptr(df), _ptr(drho), _ptr(dmean_p), _ptr(klpart), _stream()),
+              "blm_vnoise_bwd")
+    return df, klpart
+
+
+def embed_bwd(dx: torch.Tensor, tokens: torch.Tensor, scale: float, dE: torch.Tensor) -> None:
+    M, d = dx.shape
+    assert dx.is_contiguous() and dE.is_contiguous() and tokens.dtype == torch.int32
+    with _op("embed_bwd", 1):
+        check(lib().blm_embed_bwd(_ptr(dx), _ptr(tokens), scale, M, d, _ptr(dE), _stream()), "blm_embed_bwd")
+
+
+def kl_gauss_bwd(mu: torch.Tensor, lgstd: torch.Tensor, scale: float, dmu: torch.Tensor, dlgstd: torch.Tensor) -> None:
+    """dmu += c mu, dlgstd += c (exp(2 lgstd) - 1), c = scale / numel; mu / dmu may be row-slice views."""
+    if mu.dim() == 1:
+        mu, lgstd, dmu, dlgstd = mu.view(1, -1), lgstd.view(1, -1), dmu.view(1, -1), dlgstd.view(1, -1)
+    rows, cols = mu.shape
+    assert lgstd.is_contiguous() and dlgstd.is_contiguous() and mu.stride(1) == 1 and dmu.stride(1) == 1
+    with _op("kl_gauss_bwd", 1):
+        check(lib().blm_kl_gauss_bwd(_ptr(mu), mu.stride(0), _ptr(lgstd), rows, cols, scale, _ptr(dmu), dmu.stride(0),
+                                     _ptr(dlgstd), _stream()), "blm_kl_gauss_bwd")
+
+
+def reparam_bwd(G: torch.Tensor, lgstd: torch.Tensor, dmu: torch.Tensor, dlgstd: torch.Tensor, *,
+                eps: Optional[torch.Tensor] = None, seed: Optional[int] = None, stream_id: int = 0,
+                accumulate: bool = False) -> None:
+    """dmu (+)= G, dlgstd (+)= G * eps * exp(lgstd); G may alias dmu."""
+    if G.dim() == 1:
+        G, lgstd, dmu, dlgstd = G.view(1, -1), lgstd.view(1, -1), dmu.view(1, -1), dlgstd.view(1, -1)
+        eps = None if eps is None else eps.view(1, -1)
+    rows, cols = G.shape
+    assert lgstd.is_contiguous() and dlgstd.is_contiguous() and G.stride(1) == 1 and dmu.stride(1) == 1
+    if eps is not None:
+        eps = eps.contiguous().float()
+    e, mode, sd = _eps_args(eps, seed)
+    with _op("reparam_bwd", 1):
+        check(lib().blm_reparam_bwd(_ptr(G), G.stride(0), _ptr(lgstd), e, mode, sd, int(stream_id), rows, cols,
+                                    int(accumulate), _ptr(dmu), dmu.stride(0), _ptr(dlgstd), _stream()), "blm_reparam_bwd")
+
+
+def reduce_sum(x: torch.Tensor, out: torch.Tensor, *, squares: bool = False, scale: float = 1.0,
+               accumulate: bool = False) -> torch.Tensor:
+    """out[0] (+)= scale * sum(x) or scale * sum(x^2), deterministic."""
+    assert x.is_contiguous() and x.dtype == torch.float32
+    ws = _workspace("reduce", lib().blm_reduce_workspace_bytes(), x.device, zero=True)
+    with _op("reduce", 1):
+        check(lib().blm_reduce(_ptr(x), x.numel(), int(squares), scale, int(accumulate), _ptr(out), _ptr(ws), _stream()),
+              "blm_reduce")
+    return out
+
+
+def sgd_momentum(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr: float, momentum: float,
+                 norm_sq: Optional[torch.Tensor], max_norm: float, grad_scale: float = 1.0) -> None:
+    assert p.is_contiguous() and g.is_contiguous() and v.is_contiguous() and p.numel() == g.numel() == v.numel()
+    with _op("sgd_momentum", 1):
+        check(lib().blm_sgd_momentum(_ptr(p), _ptr(g), _ptr(v), p.numel(), lr, momentum, _ptr(norm_sq), max_norm,
+                                     grad_scale, _stream()), "blm_sgd_momentum")

@@ -49,9 +49,12 @@ enum {
   BLM_ACT_GELU = 1,  /* exact erf GELU, model.py:1035                          */
   BLM_ACT_GPMIX = 2, /* sum_i coef[i,n]*act_i(z), acts tanh,sigmoid,relu,gelu;
                         model.py:1893-1899 with act_set of model.py:2263       */
-  BLM_ACT_SOFTMAX_GRAD = 3 /* (exp(z - lse[m]) - [n == target[m]]) * grad_scale: the gradient of
+  BLM_ACT_SOFTMAX_GRAD = 3, /* (exp(z - lse[m]) - [n == target[m]]) * grad_scale: the gradient of
                         the mean cross-entropy w.r.t. the logits (train.py:332,412),
                         written as bf16 (hi, lo) so the logits themselves never exist */
+  BLM_ACT_GELU_GRAD = 4,  /* z * gelu'(aux[m,n]): backward of BLM_ACT_GELU at the saved
+                        pre-activation aux                                       */
+  BLM_ACT_GPMIX_GRAD = 5  /* z * sum_i coef[i,n] act_i'(aux[m,n]): backward of BLM_ACT_GPMIX */
 };
 
 /* where the N(0,1) noise of a reparameterised tensor comes from */
@@ -110,7 +113,15 @@ typedef struct blm_gemm_desc {
   const float* lse;    /* [M] log-sum-exp per row      (BLM_ACT_SOFTMAX_GRAD)  */
   const int32_t* targets; /* [M] target column per row (BLM_ACT_SOFTMAX_GRAD)  */
   float grad_scale;    /* e.g. 1 / M                   (BLM_ACT_SOFTMAX_GRAD)  */
-  int32_t reserved;
+  int32_t k_chunk;     /* > 0: close the tensor-core accumulator every k_chunk K elements
+                          (multiple of 64, counted over the concatenated segments) and
+                          sum the chunks in fp32 registers with round-to-nearest.  The
+                          tensor core truncates on every accumulate, a bias proportional
+                          to K; the precise (bf16x3) mode uses 128.  0: one accumulation. */
+  float* out_pre;      /* optional fp32 [M, N] (ldc): the value before the activation,
+                          i.e. after bias and q-scale (saved for the backward pass)   */
+  const float* aux;    /* [M, N] fp32, leading dimension ldaux (BLM_ACT_*_GRAD)  */
+  int64_t ldaux;
 } blm_gemm_desc;
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
@@ -234,6 +245,16 @@ int blm_mha_causal(const float* qkv, const int32_t* seq_offsets, int64_t nseq, i
                    int32_t head_dim, int32_t max_len, float* out_f32, blm_bf16* out_hi,
                    blm_bf16* out_lo, blm_stream stream);
 
+/* Same attention on bf16 operands and tensor cores (the production path): qkv is the [M, 3*d]
+ * output of the QKV projection written as bf16 hi (+ optional lo: the precise hi*hi + hi*lo + lo*hi
+ * product), leading dimension ld; q, k, v blocks are staged with cp.async and multiplied with
+ * mma.sync m16n8k16 (fp32 accumulate), online softmax in registers.  out_* have leading dimension ldo.
+ * needs:    head_dim == 64, sequence length <= 128.                            */
+int blm_mha_causal_bf16(const blm_bf16* qkv_hi, const blm_bf16* qkv_lo, int64_t ld,
+                        const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                        int32_t max_len, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo,
+                        int64_t ldo, blm_stream stream);
+
 /* ------------------------------------------------------------------ KL (e)
  * out[0] (+)= scale * 0.5 * mean_{rows x cols}( mu^2 - 2 lgstd + exp(2 lgstd) [- 1] )
  * (model.py:762-765 without the -1; 1115; 1255; 1821-1825 with it).
@@ -264,6 +285,82 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
                    const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
                    int64_t H, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, float* hT,
                    float* cT, void* workspace, blm_stream stream);
+
+/* ------------------------------------------------- fine-tune step (train.py:306-438)
+ * Backward twins of the kernels above and the optimiser.  The contractions of the backward pass
+ * (dgrad dX = dY W, wgrad dW = dY^T X) are blm_gemm calls on transposed bf16 operand copies
+ * (blm_transpose_*), with the activation derivative fused as BLM_ACT_*_GRAD and the softmax
+ * gradient as BLM_ACT_SOFTMAX_GRAD; what follows is the HBM-bound rest.  Gradient buffers are
+ * fp32; "accumulate" adds to the destination instead of overwriting it.                        */
+
+/* out[c, r] = bf16 hi (+ lo) of x[r, c]: x fp32 [R, C] (ldx), out [C, R] (ldo, multiple of 8).  */
+int blm_transpose_split(const float* x, int64_t ldx, int64_t R, int64_t C, blm_bf16* out_hi,
+                        blm_bf16* out_lo, int64_t ldo, blm_stream stream);
+/* same from a bf16 (hi[, lo]) source.                                                          */
+int blm_transpose_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t R, int64_t C,
+                       blm_bf16* out_hi, blm_bf16* out_lo, int64_t ldo, blm_stream stream);
+/* out[n] (+)= scale * sum_m x[m, n]   (bias gradients).                                        */
+int blm_colsum(const float* x, int64_t ldx, int64_t M, int64_t N, float scale, int32_t accumulate,
+               float* out, blm_stream stream);
+int blm_colsum_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t M, int64_t N,
+                    float scale, int32_t accumulate, float* out, blm_stream stream);
+
+/* LayerNorm backward (nn.LayerNorm, model.py:1030-1031): x is the LayerNorm INPUT.
+ * dx = rstd (g dy - mean(g dy) - xhat mean(g dy xhat)); dgamma (+)= sum dy xhat; dbeta (+)= sum dy. */
+int64_t blm_layernorm_bwd_workspace_bytes(int64_t M, int32_t d);
+int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t M,
+                      int32_t d, float* dx, float* dgamma, float* dbeta, int32_t accumulate,
+                      void* workspace, blm_stream stream);
+
+/* Backward of blm_mha_causal: qkv fp32 [M, 3d] (q already scaled), dout [M, d] -> dqkv [M, 3d];
+ * the q block of dqkv is multiplied by q_scale (gradient w.r.t. the unscaled projection,
+ * model.py:877).  Softmax is recomputed, nothing of size T x T is stored.
+ * needs: head_dim == 64, sequence length <= 128.                                               */
+int blm_mha_causal_bwd(const float* qkv, int64_t ld, const float* dout, int64_t ldo,
+                       const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                       int32_t max_len, float q_scale, float* dqkv, int64_t ldd, blm_stream stream);
+
+/* GP mixture (model.py:1893-1899): dcoef[i, n] (+)= sum_m dh[m, n] act_i(z[m, n]).              */
+int blm_gpmix_dcoef(const float* z, const float* dh, int64_t ld, int64_t M, int64_t N,
+                    int32_t accumulate, float* dcoef, blm_stream stream);
+
+/* Variational hidden noise of VTransformerEncoderLayer (model.py:2785-2801, training, T == 100):
+ *   fp = f + e exp(f rho[t]),  e = eps (BLM_EPS_PTR, already N(0, noise_std^2)) or
+ *   noise_std * Philox normal.  Rows are sequence-major: row = b*T + t; rho, mean_p are [T, d].
+ * Backward also differentiates the layer's KL (model.py:2770-2781)
+ *   KL = 0.5 mean_{T,B,d}( ((1 - mean_p) fp)^2 - 2 rho + exp(2 rho) )
+ * scaled by kl_scale: dfp (may be null) is the downstream gradient w.r.t. fp; outputs df,
+ * drho, dmean_p and klpart[T, d] with KL = 0.5 sum(klpart) / (T B d).                          */
+int blm_vnoise_fwd(const float* f, const float* rho, const float* eps, int32_t eps_mode, uint64_t seed,
+                   uint64_t stream_id, float noise_std, int64_t B, int32_t T, int32_t d, float* fp,
+                   blm_stream stream);
+int blm_vnoise_bwd(const float* dfp, const float* f, const float* rho, const float* mean_p,
+                   const float* eps, int32_t eps_mode, uint64_t seed, uint64_t stream_id,
+                   float noise_std, int64_t B, int32_t T, int32_t d, float kl_scale, float* df,
+                   float* drho, float* dmean_p, float* klpart, blm_stream stream);
+
+/* dE[tokens[m], :] += scale * dx[m, :]   (nn.Embedding backward, fp32 atomics).                 */
+int blm_embed_bwd(const float* dx, const int32_t* tokens, float scale, int64_t M, int32_t d, float* dE,
+                  blm_stream stream);
+
+/* Gradient of scale * blm_kl_gauss: dmu += c mu, dlgstd += c (exp(2 lgstd) - 1), c = scale/(rows cols). */
+int blm_kl_gauss_bwd(const float* mu, int64_t ldmu, const float* lgstd, int64_t rows, int64_t cols,
+                     float scale, float* dmu, int64_t lddmu, float* dlgstd, blm_stream stream);
+/* Backward of blm_reparam: G = dL/dw [rows, cols] (ldg): dmu (+)= G, dlgstd (+)= G eps exp(lgstd). */
+int blm_reparam_bwd(const float* G, int64_t ldg, const float* lgstd, const float* eps, int32_t eps_mode,
+                    uint64_t seed, uint64_t stream_id, int64_t rows, int64_t cols, int32_t accumulate,
+                    float* dmu, int64_t lddmu, float* dlgstd, blm_stream stream);
+
+/* out[0] (+)= scale * sum x (squares == 0) or scale * sum x^2 (squares == 1); deterministic.
+ * workspace: blm_reduce_workspace_bytes(), zeroed once by the caller.                           */
+int64_t blm_reduce_workspace_bytes(void);
+int blm_reduce(const float* x, int64_t n, int32_t squares, float scale, int32_t accumulate, float* out,
+               void* workspace, blm_stream stream);
+/* clip_grad_norm_(max_norm) + SGD momentum (train.py:419,466) over one flat buffer:
+ *   c = min(1, max_norm / (sqrt(norm_sq[0]) grad_scale + 1e-6)) (1 if norm_sq is null);
+ *   v = momentum v + c grad_scale g;  p -= lr v.                                               */
+int blm_sgd_momentum(float* p, const float* g, float* v, int64_t n, float lr, float momentum,
+                     const float* norm_sq, float max_norm, float grad_scale, blm_stream stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,187 @@
+"""Kernel-level GPU parity: every C-ABI kernel against a float64 restatement of the same
+operation (torch ops on the device, test-only), at the shapes of the BASELINE configs and at
+ragged / edge shapes.  Tolerances: relative to the largest reference magnitude."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from bayeslms_b200 import _lib, ops as _ops
+    _lib.init(0)
+    torch.manual_seed(0)
+    return _ops
+
+
+def _close(got, ref, tol):
+    assert torch.isfinite(got).all()
+    err = (got.double() - ref.double()).abs().max().item()
+    scale = max(ref.double().abs().max().item(), 1e-6)
+    assert err <= tol * scale, (err, scale, tol)
+
+
+def _gp_mix(z, c):
+    return c[0] * torch.tanh(z) + c[1] * torch.sigmoid(z) + c[2] * torch.relu(z) + c[3] * torch.nn.functional.gelu(z)
+
+
+@pytest.mark.parametrize("M,N,K,prec,act,bias,resid,cs", [
+    (128, 128, 64, "bf16", 0, False, False, False),
+    (300, 520, 200, "bf16", 0, True, False, False),         # ragged M, N, K
+    (1000, 1536, 512, "bf16x3", 0, True, False, True),      # QKV projection, q scaled
+    (20000, 4096, 512, "bf16", 1, True, False, False),      # FFN1 + GELU
+    (20000, 512, 4096, "bf16x3", 0, True, True, False),     # FFN2 + residual
+    (5000, 4096, 512, "bf16x3", 2, True, False, False),     # GP mixture epilogue
+    (77, 64, 64, "bf16x3", 1, True, False, False),
+    (1, 8, 8, "bf16x3", 0, True, True, False),              # a single row
+])
+def test_gemm_epilogues(ops, M, N, K, prec, act, bias, resid, cs):
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    A, B = ops.split(a, prec), ops.split(b, prec)
+    bi = torch.randn(N, device=DEV) if bias else None
+    r = torch.randn(M, N, device=DEV) if resid else None
+    coef = torch.rand(4, N, device=DEV) if act == ops.ACT_GPMIX else None
+    out32 = torch.empty(M, N, device=DEV)
+    out = ops.empty_split(M, N, "bf16x3", DEV)
+    ops.gemm(A, B, prec=prec, bias=bi, act=act, coef=coef, col_scale=0.125 if cs else 1.0,
+             col_scale_cols=(N // 2) if cs else 0, resid=r, out_f32=out32, out=out)
+    z = (A.hi.double() @ B.hi.double().T) if prec == "bf16" else (a.double() @ b.double().T)
+    if bias:
+        z = z + bi.double()
+    if cs:
+        z[:, : N // 2] *= 0.125
+    if act == ops.ACT_GELU:
+        z = torch.nn.functional.gelu(z)
+    if act == ops.ACT_GPMIX:
+        z = _gp_mix(z, coef.double())
+    if resid:
+        z = z + r.double()
+    _close(out32, z, 4e-5 if prec == "bf16x3" else 2e-5)
+    _close(out.float(), z, 6e-5)
+
+
+@pytest.mark.parametrize("M,V,K,prec", [(100, 1000, 64, "bf16"), (100, 1000, 64, "bf16x3"), (3000, 30000, 512, "bf16"),
+                                        (3000, 30000, 512, "bf16x3"), (40000, 30000, 512, "bf16"),
+                                        (257, 30000, 1024, "bf16x3"), (5, 33, 8, "bf16x3")])
+def test_vocab_nll(ops, M, V, K, prec):
+    h = torch.randn(M, K, device=DEV)
+    e = (torch.rand(V, K, device=DEV) - 0.5) * 0.2
+    b = (torch.rand(V, device=DEV) - 0.5) * 0.2
+    t = torch.randint(0, V, (M,), device=DEV, dtype=torch.int32)
+    H, E = ops.split(h, prec), ops.split(e, prec)
+    nll = ops.vocab_nll(H, E, b, t, prec=prec)
+    nll_nb = ops.vocab_nll(H, E, None, t, prec=prec)
+    logits = (H.hi.double() @ E.hi.double().T) if prec == "bf16" else (h.double() @ e.double().T)
+    for got, lg in ((nll, logits + b.double()), (nll_nb, logits)):
+        ref = torch.logsumexp(lg, -1) - lg.gather(1, t.long().view(-1, 1)).squeeze(1)
+        _close(got, ref, 6e-6)
+
+
+def _attention_ref(qkv, offs, nhead):
+    M, d3 = qkv.shape
+    d = d3 // 3
+    hd = d // nhead
+    ref = torch.zeros(M, d, dtype=torch.float64, device=qkv.device)
+    offs = offs.tolist()
+    for i in range(len(offs) - 1):
+        r0, T = offs[i], offs[i + 1] - offs[i]
+        if T == 0:
+            continue
+        blk = qkv[r0:r0 + T].double()
+        q, k, v = (blk[:, j * d:(j + 1) * d].view(T, nhead, hd) for j in range(3))
+        sc = torch.einsum("ihc,jhc->hij", q, k)
+        sc = sc.masked_fill(torch.triu(torch.ones(T, T, device=qkv.device, dtype=torch.bool), 1), float("-inf"))
+        ref[r0:r0 + T] = torch.einsum("hij,jhc->ihc", torch.softmax(sc, -1), v).reshape(T, d)
+    return ref
+
+
+ATTN_LENS = [[1, 5, 17, 26, 32, 2], [100, 100, 7], [1, 2, 7, 8, 9, 15, 16, 17, 26, 31, 32, 5, 5, 5, 11, 13, 3],
+             list(range(1, 27)) * 3, [33, 64, 65, 96, 97, 128, 1]]
+
+
+@pytest.mark.parametrize("lens", ATTN_LENS)
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_attention_tensor_core(ops, lens, prec):
+    """blm_mha_causal_bf16 (mma.sync on bf16 hi[, lo]) at head_dim 64: short and long variants."""
+    nhead, hd = 8, 64
+    d = nhead * hd
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=DEV)
+    M = int(offs[-1])
+    qkv = torch.randn(M, 3 * d, device=DEV)
+    qkv[:, :d] *= hd ** -0.5
+    qs = ops.split(qkv, prec)
+    o32, osplit = ops.mha_causal_bf16(qs, offs, nhead, max(lens), prec=prec, want_f32=True)
+    src = qkv if prec == "bf16x3" else qs.hi.float()
+    ref = _attention_ref(src, offs, nhead)
+    # bf16 mode additionally rounds the softmax weights to bf16 (2^-9 relative)
+    _close(o32, ref, 3e-5 if prec == "bf16x3" else 6e-3)
+    _close(osplit.float(), ref, 5e-5 if prec == "bf16x3" else 1e-2)
+
+
+@pytest.mark.parametrize("lens,nhead,hd", [([1, 5, 17, 26, 33, 64], 8, 64), ([100, 100, 7], 8, 64), ([3, 9, 128], 4, 16),
+                                            ([1, 2, 3, 4, 26, 32], 4, 8)])
+def test_attention_fp32(ops, lens, nhead, hd):
+    d = nhead * hd
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=DEV)
+    qkv = torch.randn(int(offs[-1]), 3 * d, device=DEV)
+    o, _ = ops.mha_causal(qkv, offs, nhead, max(lens), prec="bf16x3", want_f32=True)
+    _close(o, _attention_ref(qkv, offs, nhead), 1e-5)
+
+
+def test_layernorm_embed_split(ops):
+    x = torch.randn(3000, 512, device=DEV) * 3 + 1
+    g, bb = torch.randn(512, device=DEV), torch.randn(512, device=DEV)
+    y, ys = ops.layernorm(x, g, bb, 1e-5, prec="bf16x3")
+    _close(y, torch.nn.functional.layer_norm(x.double(), (512,), g.double(), bb.double(), 1e-5), 1e-5)
+    _close(ys.float(), y, 2e-5)
+    V, d = 1000, 512
+    emb, pe = torch.randn(V, d, device=DEV), torch.randn(200, d, device=DEV)
+    tok = torch.randint(0, V, (777,), device=DEV, dtype=torch.int32)
+    pos = torch.randint(0, 200, (777,), device=DEV, dtype=torch.int32)
+    xf, _ = ops.embed(tok, pos, emb, pe, 22.627, prec="bf16x3")
+    _close(xf, emb[tok.long()] * 22.627 + pe[pos.long()], 1e-6)
+    s = ops.split(x, "bf16x3")
+    _close(s.float(), x, 2e-5)
+
+
+def test_kl_and_reparam(ops):
+    mu = torch.randn(4096, 1024, device=DEV) * 0.03
+    ls = torch.rand(1024, 1024, device=DEV) * -3.4 - 3.4
+    out = torch.zeros(1, device=DEV)
+    ops.kl_gauss(mu[2048:3072], ls, out)
+    ref = (mu[2048:3072].double() ** 2 - 2 * ls.double() + torch.exp(2 * ls.double())).mean() / 2
+    assert abs(out.item() - ref.item()) <= 1e-6 * abs(ref.item())      # north_star: KL within 1e-4 relative
+    ops.kl_gauss(mu[2048:3072], ls, out, minus_one=True, scale=0.5, accumulate=True)
+    ref2 = ref + 0.5 * ((mu[2048:3072].double() ** 2 - 2 * ls.double() + torch.exp(2 * ls.double()) - 1).mean() / 2)
+    assert abs(out.item() - ref2.item()) <= 1e-6 * abs(ref2.item())
+    eps = torch.randn(1024, 1024, device=DEV)
+    w, _ = ops.reparam(mu[2048:3072], ls, eps=eps, prec="bf16x3", want_f32=True)
+    _close(w, mu[2048:3072] + torch.exp(ls) * eps, 1e-6)
+    z = ops.philox_normal(1234, 7, 4_000_000, DEV)
+    assert abs(z.mean().item()) < 3e-3 and abs(z.std().item() - 1) < 3e-3
+    kurt = ((z - z.mean()) ** 4).mean().item() / z.var().item() ** 2
+    assert abs(kurt - 3) < 0.05
+    w2, _ = ops.reparam(mu[2048:3072], ls, seed=1234, stream_id=7, prec="bf16", want_f32=True)
+    _close(w2, mu[2048:3072] + torch.exp(ls) * z[: 1024 * 1024].view(1024, 1024), 1e-6)
+
+
+def test_precise_gemm_truncation_bias_is_bounded(ops):
+    """The tensor core truncates on every fp32 accumulate (a shrink of ~2e-8 per 16-wide K step).
+    Chunked accumulation (k_chunk, the bf16x3 default) keeps the systematic error of a K = 4096
+    product of same-sign operands below 5e-7 relative; one long accumulation does not."""
+    M, N, K = 512, 512, 4096
+    a = torch.rand(M, K, device=DEV) + 0.5
+    b = torch.rand(N, K, device=DEV) + 0.5
+    A, B = ops.split(a, "bf16x3"), ops.split(b, "bf16x3")
+    ref = a.double() @ b.double().T
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, prec="bf16x3", out_f32=out)
+    bias_chunked = ((out.double() - ref) / ref).mean().item()
+    ops.gemm(A, B, prec="bf16x3", out_f32=out, k_chunk=0)
+    bias_single = ((out.double() - ref) / ref).mean().item()
+    assert abs(bias_chunked) < 5e-7, (bias_chunked, bias_single)
+    assert abs(bias_single) > 4 * abs(bias_chunked), (bias_chunked, bias_single)

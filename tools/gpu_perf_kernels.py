@@ -77,6 +77,12 @@ offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, d
 Ma = int(offs[-1])
 qa = torch.randn(Ma, 3 * d, device=dev)
 line(f"mha_causal rescoring lens 6..26 ({Ma} tok)", timeit(lambda: ops.mha_causal(qa, offs, 8, 26)), bytes_=Ma * (3 * d * 4 + d * 2))
+qs = ops.split(qa, "bf16"); qs3 = ops.split(qa, "bf16x3")
+line(f"mha_causal_bf16 (mma) bf16   ({Ma} tok)", timeit(lambda: ops.mha_causal_bf16(qs, offs, 8, 26)), bytes_=Ma * (3 * d * 2 + d * 2))
+line(f"mha_causal_bf16 (mma) bf16x3 ({Ma} tok)", timeit(lambda: ops.mha_causal_bf16(qs3, offs, 8, 26, prec="bf16x3")), bytes_=Ma * (3 * d * 4 + d * 4))
+offs100 = torch.arange(0, 32 * 100 + 1, 100, dtype=torch.int32, device=dev)
+q100 = ops.split(torch.randn(3200, 3 * d, device=dev), "bf16x3")
+line("mha_causal_bf16 (mma) bf16x3 32 x T=100", timeit(lambda: ops.mha_causal_bf16(q100, offs100, 8, 100, prec="bf16x3")), bytes_=3200 * (3 * d * 4 + d * 4))
 g = torch.ones(d, device=dev); bt = torch.zeros(d, device=dev)
 line("layernorm [M,512] f32 -> f32 + bf16", timeit(lambda: ops.layernorm(x32, g, bt, 1e-5)), bytes_=M * d * (4 + 4 + 2))
 tok = torch.randint(0, V, (M,), device=dev, dtype=torch.int32)
