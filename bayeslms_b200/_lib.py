@@ -81,6 +81,7 @@ SIGNATURES = {
     "blm_layernorm": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _p]),
     "blm_reparam": (C.c_int, [_p, _i64, _p, _p, _i32, _u64, _u64, _i64, _i64, _p, _p, _p, _p]),
     "blm_philox_normal": (C.c_int, [_u64, _u64, _i64, _p, _p]),
+    "blm_philox_normal_scaled": (C.c_int, [_u64, _u64, _i64, _f, _p, _p]),
     "blm_mha_causal": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "blm_mha_causal_bf16": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "blm_kl_workspace_bytes": (_i64, []),
@@ -93,7 +94,7 @@ SIGNATURES = {
     "blm_layernorm_bwd": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "blm_mha_causal_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p]),
     "blm_gpmix_dcoef": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p]),
-    "blm_vnoise_fwd": (C.c_int, [_p, _p, _p, _i32, _u64, _u64, _f, _i64, _i32, _i32, _p, _p]),
+    "blm_vnoise_fwd": (C.c_int, [_p, _p, _p, _i32, _u64, _u64, _f, _p, _i64, _i32, _i32, _p, _p]),
     "blm_vnoise_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _u64, _u64, _f, _i64, _i32, _i32, _f, _p, _p, _p, _p, _p]),
     "blm_embed_bwd": (C.c_int, [_p, _p, _f, _i64, _i32, _p, _p]),
     "blm_kl_gauss_bwd": (C.c_int, [_p, _i64, _p, _i64, _i64, _f, _p, _i64, _p, _p]),

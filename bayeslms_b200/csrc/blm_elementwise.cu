@@ -123,14 +123,14 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
-__global__ void philox_normal_kernel(uint64_t seed, uint64_t stream, long long n, float* __restrict__ out) {
+__global__ void philox_normal_kernel(uint64_t seed, uint64_t stream, long long n, float scale, float* __restrict__ out) {
   const long long n4 = (n + 3) / 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 z = philox_normal4(seed, stream, static_cast<uint64_t>(i));
     const float zz[4] = {z.x, z.y, z.z, z.w};
     for (int j = 0; j < 4; ++j)
-      if (i * 4 + j < n) out[i * 4 + j] = zz[j];
+      if (i * 4 + j < n) out[i * 4 + j] = zz[j] * scale;
   }
 }
 
@@ -336,12 +336,16 @@ int blm_reparam(const float* mu, int64_t ldmu, const float* lgstd, const float* 
   return BLM_OK;
 }
 
-int blm_philox_normal(uint64_t seed, uint64_t stream_id, int64_t n, float* out, blm_stream stream) {
+int blm_philox_normal_scaled(uint64_t seed, uint64_t stream_id, int64_t n, float scale, float* out, blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(out && n > 0, BLM_ERR_ARG, "bad philox arguments");
-  philox_normal_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, as_stream(stream)>>>(seed, stream_id, n, out);
+  philox_normal_kernel<<<grid_for((n + 3) / 4, 256, 8), 256, 0, as_stream(stream)>>>(seed, stream_id, n, scale, out);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
+}
+
+int blm_philox_normal(uint64_t seed, uint64_t stream_id, int64_t n, float* out, blm_stream stream) {
+  return blm_philox_normal_scaled(seed, stream_id, n, 1.0f, out, stream);
 }
 
 int blm_mc_combine(const float* nll, int64_t K, int64_t M, float* out, blm_stream stream) {

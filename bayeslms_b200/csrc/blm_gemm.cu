@@ -86,7 +86,7 @@ __device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], i
 // K = 3 x 4096).  With CHUNK the MMA warp closes the TMEM accumulator every p.chunk_kb K blocks and
 // the epilogue warps sum the chunks in fp32 registers (round to nearest), so the bias is bounded by
 // the chunk length, not by K (the precise bf16x3 mode uses chunks of 128 K elements).
-template <int BN, int STAGES, int EPI, int ACT, int ARES, int EW, int CHUNK = 0>
+template <int BN, int STAGES, int EPI, int ACT, int ARES, int EW, int CHUNK = 0, int STG = 0>
 __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   using L = SmemLayout<BN, STAGES, ARES>;
   static_assert(EW == 8 || EW == 16, "epilogue warps");
@@ -251,6 +251,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     const int etid = threadIdx.x - kEpiWarp0 * 32;
     const int row_in_tile = lane_grp * 32 + lane;
     const int c0 = col_grp * kChunks;  // first chunk of this warp inside the tile
+    static_assert(!STG || (ARES == 0 && EW == 8 && EPI == EPI_STORE), "store staging: 8 warps x 4 KB");
+    float4* stg = STG ? reinterpret_cast<float4*>(smem + L::kStgOffset + (warp - kEpiWarp0) * 4096)
+                      : nullptr;  // store-transpose staging of this warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
@@ -260,6 +263,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
       const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
       const int m = m_tile * kBM + row_in_tile;
       const bool row_ok = m < p.M;
+      const bool warp_rows_ok = m_tile * kBM + lane_grp * 32 < p.M;  // warp-uniform: any valid row in this warp
+      (void)warp_rows_ok;
 
       NllState st{-INFINITY, 0.0f, -INFINITY, -1};
       if constexpr (EPI == EPI_NLL) {
@@ -314,7 +319,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int col0 = n * BN + (c0 + c) * 32;
-            if (col0 < p.N && row_ok) store_chunk<ACT>(p, accr[c], m, col0, sbc + (c0 + c) * 32);
+            if (col0 < p.N && m_tile * kBM + lane_grp * 32 < p.M)
+              store_chunk<ACT, STG>(p, accr[c], m, row_ok, lane, col0, sbc + (c0 + c) * 32, stg);
           }
           continue;
         }
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
             const int col0 = n * BN + (c0 + c) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (row_ok) store_chunk<ACT>(p, va, m, col0, sb + (c0 + c) * 32);
+                if (warp_rows_ok) store_chunk<ACT, STG>(p, va, m, row_ok, lane, col0, sb + (c0 + c) * 32, stg);
               } else {
                 nll_chunk(p, va, col0, st, sb + (c0 + c) * 32);
               }
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
             const int col0 = n * BN + (c0 + c + 1) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (row_ok) store_chunk<ACT>(p, vb, m, col0, sb + (c0 + c + 1) * 32);
+                if (warp_rows_ok) store_chunk<ACT, STG>(p, vb, m, row_ok, lane, col0, sb + (c0 + c + 1) * 32, stg);
               } else {
                 nll_chunk(p, vb, col0, st, sb + (c0 + c + 1) * 32);
               }
@@ -476,8 +482,29 @@ static int launch_chunk(const GemmParams& p, cudaStream_t st) {
   return BLM_OK;
 }
 
+// transposed-store (STG) variants: ACT_NONE only -- the fp32-output GEMMs (QKV in training, o_net, FFN2)
+template <int BN, int STAGES, int CHUNK>
+static int set_smem_attr_stg() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI_STORE, BLM_ACT_NONE, 0, 8, CHUNK, 1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SmemLayout<BN, STAGES, 0>::kDynBytes));
+  return BLM_OK;
+}
+
+template <int BN, int STAGES, int CHUNK>
+static int launch_stg(const GemmParams& p, cudaStream_t st) {
+  const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
+  gemm_kernel<BN, STAGES, EPI_STORE, BLM_ACT_NONE, 0, 8, CHUNK, 1>
+      <<<grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 int gemm_init() {
   int rc;
+  if ((rc = set_smem_attr_stg<256, kStages256, 0>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<128, kStages128, 0>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<128, kStages128, 1>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_GPMIX>()) != BLM_OK) return rc;
@@ -498,6 +525,9 @@ int gemm_init() {
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_NLL, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kNllAresStages, EPI_NLL, BLM_ACT_NONE, kNllAres>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kNllAresStages, EPI_STORE, BLM_ACT_NONE, kNllAres>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kNllAresStages, EPI_STORE, BLM_ACT_GELU, kNllAres>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kNllAresStages, EPI_STORE, BLM_ACT_GPMIX, kNllAres>()) != BLM_OK) return rc;
   return BLM_OK;
 }
 
@@ -597,12 +627,18 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   p.lse = d->lse;
   p.targets = d->targets;
   p.grad_scale = d->grad_scale;
+  // store transpose: pays for fp32 outputs (QKV fp32 228 -> 149 us at M = 65536); for bf16-only outputs the
+  // extra shared-memory round trip costs more issue slots than the wider stores save (FFN1 479 -> 536 us)
+  static const char* stg_env = getenv("BLM_STG");  // A/B switch for profiling: 0 = never, 1 = always
+  p.use_stg = stg_env ? atoi(stg_env) : (d->out_f32 != nullptr);
   p.out_pre = d->out_pre;
   p.aux = d->aux;
   p.ldaux = d->ldaux;
   cudaStream_t st = as_stream(stream);
+  const bool stg = p.use_stg && d->act == BLM_ACT_NONE;
   if (chunked) {
     p.chunk_kb = d->k_chunk / kBK;
+    if (stg) return launch_stg<128, kStages128, 1>(p, st);
     switch (d->act) {
       case BLM_ACT_NONE: return launch_chunk<BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch_chunk<BLM_ACT_GELU>(p, st);
@@ -612,6 +648,24 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
       default: return launch_chunk<BLM_ACT_SOFTMAX_GRAD>(p, st);
     }
   }
+  // Opt-in experiment (BLM_GEMM_ARES=1): keep the A tile resident in shared memory while the CTA sweeps
+  // all N tiles of its rows, as the NLL kernel does.  Measured SLOWER for the storing GEMMs (QKV 267 vs
+  // 218 us, FFN1 525 vs 432 us at M = 65536, profiles/r01g): the tile loads were not the bound, the
+  // row-per-thread stores were (fixed by the store transpose), and a single resident A buffer stalls
+  // every work boundary.
+  static const bool no_ares = getenv("BLM_GEMM_ARES") == nullptr;
+  if (BN == 256 && !no_ares && d->nseg == 1 && p.kblocks[0] <= kNllAres && p.n_tiles >= 4 && p.m_tiles >= num_sms() &&
+      (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX)) {
+    p.n_groups = 1;
+    p.tiles_per_group = p.n_tiles;
+    p.num_works = p.m_tiles;
+    switch (d->act) {
+      case BLM_ACT_NONE: return launch<256, kNllAresStages, EPI_STORE, BLM_ACT_NONE, kNllAres>(p, st);
+      case BLM_ACT_GELU: return launch<256, kNllAresStages, EPI_STORE, BLM_ACT_GELU, kNllAres>(p, st);
+      default: return launch<256, kNllAresStages, EPI_STORE, BLM_ACT_GPMIX, kNllAres>(p, st);
+    }
+  }
+  if (stg) return BN == 256 ? launch_stg<256, kStages256, 0>(p, st) : launch_stg<128, kStages128, 0>(p, st);
   if (BN == 256) {
     switch (d->act) {
       case BLM_ACT_NONE: return launch<256, kStages256, EPI_STORE, BLM_ACT_NONE>(p, st);

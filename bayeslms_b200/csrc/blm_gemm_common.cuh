@@ -33,6 +33,7 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldc;
+  int use_stg;          // 1: transpose finished chunks through shared memory for row-coalesced stores
   int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk
   float* out_pre;       // fp32 copy of the value BEFORE the activation (training: saved pre-activation)
   const float* aux;     // [M, N] fp32, leading dimension ldaux: the pre-activation the *_GRAD epilogues differentiate at
@@ -56,7 +57,10 @@ struct SmemLayout {
   static constexpr int kResBytes = ARES * kABytes;
   static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
   static constexpr int kBiasOffset = kResBytes + STAGES * kStageBytes;  // fp32 bias[2][BN], one per accumulator stage
-  static constexpr int kBarOffset = kBiasOffset + 2 * BN * 4;
+  // 4 KB per epilogue warp (8 warps) for the store transpose; the A-resident kernels (NLL) store nothing
+  static constexpr int kStgOffset = kBiasOffset + 2 * BN * 4;
+  static constexpr int kStgBytes = ARES ? 0 : 8 * 4096;
+  static constexpr int kBarOffset = kStgOffset + kStgBytes;
   // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] a_full a_empty + tmem ptr
   static constexpr int kBytes = kBarOffset + (2 * STAGES + 6) * 8 + 16;
   // the dynamic shared-memory window of a kernel without static shared memory starts 1024-B aligned
@@ -76,11 +80,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exact-erf GELU to 4e-7 absolute: erf(t) = 1 - 2^(-t q(t)) with q a degree-6 fit of -log2(erfc(t))/t
 // on [0, 4] (erfc(4) = 1.5e-8, so t is clamped there); one MUFU.EX2 and nine FMAs per element
 // instead of libdevice erff -- the FFN1 epilogue has ~16 issue slots per element before it, not
 // the tensor pipe, becomes the bound at K = 512.
 __device__ __forceinline__ float gelu_fast(float x) {
+  // GELU(x) = relu(x) - |x|/2 * erfc(|x|/sqrt 2): one formula for both signs, no select
   const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
   float q = fmaf(t, -1.002195230e-04f, 4.615629764e-04f);
   q = fmaf(q, t, 2.302262028e-03f);
@@ -88,8 +99,8 @@ __device__ __forceinline__ float gelu_fast(float x) {
   q = fmaf(q, t, 1.489636837e-01f);
   q = fmaf(q, t, 9.183286407e-01f);
   q = fmaf(q, t, 1.627913732e+00f);
-  const float w = 0.5f * x * ex2_approx(-(q * t));
-  return x >= 0.0f ? x - w : w;
+  const float e = ex2_approx(-(q * t));  // erfc(t)
+  return fmaf(fabsf(x) * -0.5f, e, fmaxf(x, 0.0f));
 }
 
 // d/dz of the exact-erf GELU: Phi(z) + z phi(z), with erfc from the same fit as gelu_fast
@@ -121,7 +132,14 @@ __device__ __forceinline__ float apply_act(float z, const float* __restrict__ co
   } else if constexpr (ACT == BLM_ACT_GPMIX) {
     const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n),
                 c3 = __ldg(coef + 3 * N + n);
-    return c0 * tanhf(z) + c1 * (1.0f / (1.0f + expf(-z))) + c2 * fmaxf(z, 0.0f) + c3 * gelu_fast(z);
+    // sigmoid and tanh from ONE exponential: e = exp(-z) (z clamped to +-15, where both have saturated to
+    // 3e-7), sigmoid = 1/(1+e), tanh = (1-e^2)/(1+e^2); ex2 / rcp are MUFU approximations (<= 2 ulp)
+    const float zc = fminf(fmaxf(z, -15.0f), 15.0f);
+    const float e1 = ex2_approx(zc * -1.4426950408889634f);
+    const float e2 = e1 * e1;
+    const float sg = rcp_approx(1.0f + e1);
+    const float th = (1.0f - e2) * rcp_approx(1.0f + e2);
+    return fmaf(c0, th, fmaf(c1, sg, fmaf(c2, fmaxf(z, 0.0f), c3 * gelu_fast(z))));
   } else {
     return z;
   }
@@ -129,11 +147,20 @@ __device__ __forceinline__ float apply_act(float z, const float* __restrict__ co
 
 // ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
 
-// bias / q-scale / activation / residual / (hi, lo) split / stores for one 32-column chunk
-// sb: this chunk's 32 bias values staged in shared memory (null: read p.bias from global)
-template <int ACT>
-__device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, int col0,
-                                            const float* sb = nullptr) {
+// bias / q-scale / activation / residual / (hi, lo) split / stores for one 32-column chunk.
+// Called by all 32 lanes of an epilogue warp; thread `lane` holds row m = m0 + lane (row_ok = m < M).
+//   sb : this chunk's 32 bias values staged in shared memory (null: read p.bias from global)
+//   stg: 4 KB of shared memory private to the warp.  The tcgen05.ld layout gives every thread one
+//        ROW, so direct stores touch 32 different 128-byte lines per instruction (16 bytes each) and
+//        the LSU / L2 request rate, not bandwidth, bounds the epilogue.  With stg the finished chunk
+//        is transposed through shared memory (16-byte slots XOR-swizzled by row, conflict free both
+//        ways) so that 8 lanes cover one row: every global access -- residual load, fp32 / bf16 hi /
+//        bf16 lo stores -- is a full 128-byte (64-byte for bf16) row segment, 4 rows per instruction.
+// STG selects the transposed-store path at compile time (one path per kernel keeps the epilogue
+// under the register cap: with both inlined every storing kernel spilled its loop state).
+template <int ACT, int STG = 0>
+__device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, bool row_ok, int lane,
+                                            int col0, const float* sb = nullptr, float4* stg = nullptr) {
   const bool full = (col0 + 32 <= p.N);
   if (full) {
     if (p.bias) {
@@ -155,32 +182,86 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.col_scale_cols) v[j] *= p.col_scale;
     }
-    if (p.out_pre) {
+    if (p.out_pre && row_ok) {
       float* o = p.out_pre + static_cast<long long>(m) * p.ldc + col0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     if constexpr (ACT == BLM_ACT_SOFTMAX_GRAD) {
-      const float nl = -__ldg(p.lse + m) * 1.4426950408889634f;
-      const int rel = __ldg(p.targets + m) - col0;
+      const float nl = row_ok ? -__ldg(p.lse + m) * 1.4426950408889634f : 0.0f;
+      const int rel = row_ok ? __ldg(p.targets + m) - col0 : -1;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         v[j] = (ex2_approx(fmaf(v[j], 1.4426950408889634f, nl)) - (j == rel ? 1.0f : 0.0f)) * p.grad_scale;
     } else if constexpr (ACT == BLM_ACT_GELU_GRAD || ACT == BLM_ACT_GPMIX_GRAD) {
-      const float* a = p.aux + static_cast<long long>(m) * p.ldaux + col0;
+      if (row_ok) {
+        const float* a = p.aux + static_cast<long long>(m) * p.ldaux + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 z = __ldg(reinterpret_cast<const float4*>(a + j));
-        const float zz[4] = {z.x, z.y, z.z, z.w};
+        for (int j = 0; j < 32; j += 4) {
+          const float4 z = __ldg(reinterpret_cast<const float4*>(a + j));
+          const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          v[j + q] *= (ACT == BLM_ACT_GELU_GRAD) ? gelu_grad(zz[q]) : gpmix_grad(zz[q], p.coef, p.N, col0 + j + q);
+          for (int q = 0; q < 4; ++q)
+            v[j + q] *= (ACT == BLM_ACT_GELU_GRAD) ? gelu_grad(zz[q]) : gpmix_grad(zz[q], p.coef, p.N, col0 + j + q);
+        }
       }
     } else if constexpr (ACT != BLM_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
     }
+    if constexpr (STG) {
+      // ---- transpose through shared memory, then row-coalesced residual + stores
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+      const int c4 = lane & 7, rsub = lane >> 3;
+      const int m0 = m - lane;
+      const int col = col0 + c4 * 4;
+      // residual loads are issued four rows ahead of their use (4 x 128 bit in flight per lane)
+#pragma unroll
+      for (int k0 = 0; k0 < 8; k0 += 4) {
+        float4 rr[4];
+        if (p.resid) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int mr = m0 + rsub + 4 * (k0 + k);
+            rr[k] = mr < p.M ? __ldg(reinterpret_cast<const float4*>(p.resid + static_cast<long long>(mr) * p.ldr + col))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = rsub + 4 * (k0 + k);
+          const int mr = m0 + row;
+          float4 x = stg[row * 8 + (c4 ^ (row & 7))];
+          if (p.resid) {
+            x.x += rr[k].x;
+            x.y += rr[k].y;
+            x.z += rr[k].z;
+            x.w += rr[k].w;
+          }
+          if (mr < p.M) {
+            const long long off = static_cast<long long>(mr) * p.ldc + col;
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = x;
+            if (p.out_hi) {
+              const uint32_t h0 = pack_bf16x2(x.x, x.y), h1 = pack_bf16x2(x.z, x.w);
+              *reinterpret_cast<uint2*>(p.out_hi + off) = make_uint2(h0, h1);
+              if (p.out_lo) {
+                const uint32_t l0 = pack_bf16x2(x.x - __uint_as_float(h0 << 16), x.y - __uint_as_float(h0 & 0xffff0000u));
+                const uint32_t l1 = pack_bf16x2(x.z - __uint_as_float(h1 << 16), x.w - __uint_as_float(h1 & 0xffff0000u));
+                *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(l0, l1);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();  // the staging buffer is reused by the next chunk
+      return;
+    }
+    if (!row_ok) return;
+    if constexpr (STG) return;  // (not reached: the staged path returned above)
     if (p.resid) {
       const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
 #pragma unroll
@@ -222,13 +303,14 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
     }
   } else {
     // ragged right edge (N not a multiple of 32): scalar path, only the last chunk of a row
+    if (!row_ok) return;
     const long long off = static_cast<long long>(m) * p.ldc + col0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {  // static register indices: v must not fall into local memory
       const int col = col0 + j;
       if (col >= p.N) continue;
       float z = v[j];
-      if (p.bias) z += __ldg(p.bias + col);
+      if (p.bias) z += sb ? sb[j] : __ldg(p.bias + col);
       if (col < p.col_scale_cols) z *= p.col_scale;
       if (p.out_pre) p.out_pre[off + j] = z;
       if constexpr (ACT == BLM_ACT_SOFTMAX_GRAD) {

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
           const int mt = c / (kSBN / 32), cc = c % (kSBN / 32);
           const int m = (m_group * kSMT + mt) * kBM + lane_grp * 32 + lane;
           const int col0 = n_tile * kSBN + cc * 32;
-          if (m < p.g.M && col0 < p.g.N) store_chunk<ACT>(p.g, va, m, col0);
+          if ((m - lane) < p.g.M && col0 < p.g.N) store_chunk<ACT, 0>(p.g, va, m, m < p.g.M, lane, col0);
         }
         tmem_ld_wait();
         __syncwarp();
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
           const int mt = (c + 1) / (kSBN / 32), cc = (c + 1) % (kSBN / 32);
           const int m = (m_group * kSMT + mt) * kBM + lane_grp * 32 + lane;
           const int col0 = n_tile * kSBN + cc * 32;
-          if (m < p.g.M && col0 < p.g.N) store_chunk<ACT>(p.g, vb, m, col0);
+          if ((m - lane) < p.g.M && col0 < p.g.N) store_chunk<ACT, 0>(p.g, vb, m, m < p.g.M, lane, col0);
         }
       }
     }

@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(256) gpmix_dcoef_kernel(const float* __restric
 // forward:  fp = f + e * exp(f * rho[t]),  e = explicit noise or noise_std * Philox normal; row m = b*T + t
 __global__ void vnoise_fwd_kernel(const float* __restrict__ f, const float* __restrict__ rho,
                                   const float* __restrict__ eps, int eps_mode, uint64_t seed, uint64_t stream,
-                                  float noise_std, long long M, int T, int d, float* __restrict__ fp) {
+                                  float noise_std, const float* __restrict__ resid, long long M, int T, int d,
+                                  float* __restrict__ fp) {
   const long long n4 = M * d / 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -386,6 +387,10 @@ __global__ void vnoise_fwd_kernel(const float* __restrict__ f, const float* __re
     o.y = fmaf(e.y, expf(x.y * r.y), x.y);
     o.z = fmaf(e.z, expf(x.z * r.z), x.z);
     o.w = fmaf(e.w, expf(x.w * r.w), x.w);
+    if (resid) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(resid) + i);
+      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+    }
     *(reinterpret_cast<float4*>(fp) + i) = o;
   }
 }
@@ -636,13 +641,16 @@ int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
   float* partial = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
   const size_t smem = sizeof(float) * 8 * 2 * d;
-  if (d <= 512) {
+  static bool attr = false;
+  if (!attr) {
     BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    layernorm_bwd_kernel<4><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
-  } else {
     BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    layernorm_bwd_kernel<8><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
+    attr = true;
   }
+  if (d <= 512)
+    layernorm_bwd_kernel<4><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
+  else
+    layernorm_bwd_kernel<8><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
   BLM_CHECK_CUDA(cudaGetLastError());
   layernorm_bwd_fold_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>(partial, blocks, d, accumulate, dgamma, dbeta);
   BLM_CHECK_CUDA(cudaGetLastError());
@@ -678,13 +686,13 @@ int blm_gpmix_dcoef(const float* z, const float* dh, int64_t ld, int64_t M, int6
 }
 
 int blm_vnoise_fwd(const float* f, const float* rho, const float* eps, int32_t eps_mode, uint64_t seed,
-                   uint64_t stream_id, float noise_std, int64_t B, int32_t T, int32_t d, float* fp,
-                   blm_stream stream) {
+                   uint64_t stream_id, float noise_std, const float* resid, int64_t B, int32_t T, int32_t d,
+                   float* fp, blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(f && rho && fp && B > 0 && T > 0 && d > 0 && (d % 4) == 0, BLM_ERR_ARG, "bad vnoise arguments");
   BLM_REQUIRE(eps_mode == BLM_EPS_PHILOX || (eps_mode == BLM_EPS_PTR && eps), BLM_ERR_ARG, "bad eps_mode %d", eps_mode);
   vnoise_fwd_kernel<<<tgrid(B * T * d / 4, 256, 8), 256, 0, as_stream(stream)>>>(f, rho, eps, eps_mode, seed, stream_id,
-                                                                              noise_std, B * T, T, d, fp);
+                                                                              noise_std, resid, B * T, T, d, fp);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

@@ -328,10 +328,15 @@ def reparam(mu: torch.Tensor, lgstd: Optional[torch.Tensor], *, eps: Optional[to
     return w, s
 
 
-def philox_normal(seed: int, stream_id: int, n: int, device) -> torch.Tensor:
-    out = torch.empty(n, dtype=torch.float32, device=device)
+def philox_normal(seed: int, stream_id: int, n: int, device, *, out: Optional[torch.Tensor] = None,
+                  scale: float = 1.0) -> torch.Tensor:
+    """scale * N(0,1) from the library's Philox stream (seed, stream_id): element i = counter i/4, lane i%4."""
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=device)
+    assert out.is_contiguous() and out.numel() == n
     with _op("philox_normal", 1):
-        check(lib().blm_philox_normal(int(seed), int(stream_id), n, _ptr(out), _stream()), "blm_philox_normal")
+        check(lib().blm_philox_normal_scaled(int(seed), int(stream_id), n, scale, _ptr(out), _stream()),
+              "blm_philox_normal_scaled")
     return out
 
 
@@ -515,15 +520,16 @@ def _eps_args(eps, seed):
 
 
 def vnoise_fwd(f: torch.Tensor, rho: torch.Tensor, B: int, T: int, *, eps: Optional[torch.Tensor] = None,
-               seed: Optional[int] = None, stream_id: int = 0, noise_std: float = 0.1) -> torch.Tensor:
-    """fp = f + e * exp(f * rho[t]) for sequence-major rows (row = b*T + t); rho [T, d]."""
+               seed: Optional[int] = None, stream_id: int = 0, noise_std: float = 0.1,
+               resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp = f + e * exp(f * rho[t]) (+ resid) for sequence-major rows (row = b*T + t); rho [T, d]."""
     d = f.shape[1]
     assert f.is_contiguous() and rho.is_contiguous() and f.shape[0] == B * T
     fp = torch.empty_like(f)
     e, mode, sd = _eps_args(eps, seed)
     with _op("vnoise_fwd", 1):
-        check(lib().blm_vnoise_fwd(_ptr(f), _ptr(rho), e, mode, sd, int(stream_id), noise_std, B, T, d, _ptr(fp), _stream()),
-              "blm_vnoise_fwd")
+        check(lib().blm_vnoise_fwd(_ptr(f), _ptr(rho), e, mode, sd, int(stream_id), noise_std, _ptr(resid), B, T, d,
+                                   _ptr(fp), _stream()), "blm_vnoise_fwd")
     return fp
 
 

@@ -1,0 +1,407 @@
+"""Fine-tune step: the B200 counterpart of one iteration of the reference's ``train()`` loop
+(``steps/pytorchnn/train.py:306-438``; ``train.py`` below) for the Transformer families.
+
+    loss = CE(mean over the batch's tokens) + KL * kl_scale,  kl_scale = seq_len / len(train_data)
+    clip_grad_norm_(parameters, clip);  SGD(lr, momentum=0.9, weight_decay=0)       (train.py:412-420, 466)
+
+Which KL is added follows train.py:335-399: Bayes-FFN -> layer 0 ``linear2``; Bayes-MHA -> layer 0
+``self_attn.o_net``; GP -> layer 0 ``gpnn`` (gauss_pos 1..3); Variational -> the V layers of ``T_v_pos``.
+
+How the work is laid out on the GPU
+  * the batch (T, B) is packed sequence-major ([M = B*T, width] activations, row = b*T + t), so the
+    forward pass is the rescoring pass of :mod:`bayeslms_b200.engine` with the activations kept;
+  * every contraction of the backward pass (dgrad dX = dY W, wgrad dW = dY^T X) is a ``blm_gemm`` call on
+    bf16 (hi[, lo]) operands -- transposed copies come from ``blm_transpose_*`` -- with the activation
+    derivative (GELU / GP mixture) fused into the dgrad epilogue and the softmax gradient fused into the
+    decoder product (the [M, V] logits never exist; dZ = softmax - onehot is produced directly as bf16);
+  * parameters, gradients and momentum live in three flat fp32 buffers: one reduction gives the global
+    gradient norm, one kernel applies clip + momentum + update, and data-parallel training needs a single
+    NCCL all-reduce of the gradient buffer (replicated weights, batch sharded over ranks).
+Dropout: the reference trains with dropout; masks are not reproduced here -- the step is the p = 0 step
+(what the parity tests compare against).  Noise is injected (``eps``) or Philox (``seed``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, engine, ops
+from .ops import (ACT_GELU, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, Split)
+
+_TID = engine._TID
+V_NOISE_STD = 0.1          # model.py:2786: normal_(0, 0.1)
+_TID_VNOISE = 32           # Philox stream ids of the V-layer noise: 32 + layer index
+
+
+class FineTuner:
+    """Owns the flat parameter / gradient / momentum buffers of ``model`` and runs training steps."""
+
+    def __init__(self, model, lr: float, *, momentum: float = 0.9, clip: float = 0.25, prec: str = "bf16x3",
+                 group=None):
+        if model.family not in ("bayes_tm", "gauss_tm", "v_tm"):
+            raise NotImplementedError("the fine-tune step is implemented for the Transformer families")
+        if getattr(model, "bayes_embed", False) or getattr(model, "bayes_pos", None) == "MHA":
+            raise NotImplementedError("fine-tuning the EMB / MHA Bayesian variants is not implemented yet")
+        self.model, self.lr, self.momentum, self.clip, self.prec = model, float(lr), float(momentum), float(clip), prec
+        self.group = group
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+        named = list(model.named_parameters())          # tied encoder / decoder weight appears once
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise _lib.BlmError("the model must live on a CUDA device: bayeslms_b200 has no CPU path")
+        _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.device = dev
+        offs, total = {}, 0
+        for name, p in named:
+            offs[name] = total
+            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned views
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.g: Dict[str, torch.Tensor] = {}
+        with torch.no_grad():
+            for name, p in named:
+                o, n = offs[name], p.numel()
+                self.flat_p[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[o:o + n].view(p.shape)
+                self.g[name] = self.flat_g[o:o + n].view(p.shape)
+        if model.decoder.weight is model.encoder.weight:
+            self.g["decoder.weight"] = self.g["encoder.weight"]
+        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_buf = torch.zeros(3, dtype=torch.float32, device=dev)   # ce, kl, loss
+
+    # ------------------------------------------------------------------ helpers
+    def _w(self, w: torch.Tensor) -> Split:
+        return ops.split(w.detach(), self.prec)
+
+    def _wt(self, w: torch.Tensor) -> Split:
+        """[N, K] fp32 weight -> Split of its transpose [K, N] (B operand of the dgrad product)."""
+        return ops.transpose_split(w.detach().float().contiguous(), self.prec)
+
+    def _reparam32(self, mu, lgstd, tid, eps_t, seed):
+        """fp32 sample mu + exp(lgstd) * eps of one tensor (injected eps or Philox stream (tid, 0))."""
+        if eps_t is not None:
+            w, _ = ops.reparam(mu, lgstd, eps=eps_t.to(self.device).float(), prec="bf16", want_f32=True)
+        else:
+            w, _ = ops.reparam(mu, lgstd, seed=seed, stream_id=engine._stream_id(tid, 0), prec="bf16", want_f32=True)
+        return w.view(mu.shape)
+
+    def _f32(self, rows, cols):
+        return torch.empty(rows, cols, dtype=torch.float32, device=self.device)
+
+    def _wgrad(self, dy_t: Split, x_t: Split, out: torch.Tensor, tag: str):
+        """out[N, K] = dY^T X, both operands given transposed ([N, M] and [K, M])."""
+        ops.gemm(dy_t, x_t, prec=self.prec, out_f32=out, tag="wgrad:" + tag)
+
+    # ------------------------------------------------------------------ one step
+    def forward_backward(self, tokens_tb: torch.Tensor, targets_tb: torch.Tensor, kl_scale: float, *,
+                         eps: Optional[dict] = None, seed: Optional[int] = None):
+        """Fills the gradient buffer for the batch (T, B); returns (loss, ce, kl) as 0-dim device tensors.
+        ``eps``: injected noise in the oracle's layout ({'layer<i>': ...}; V layers: (T, B, d) tensors
+        already scaled by 0.1); ``seed``: Philox noise instead."""
+        m, prec, dev = self.model, self.prec, self.device
+        T, B = tokens_tb.shape
+        M, d, nhead = T * B, m.ninp, m.nhead
+        V = m.decoder.weight.shape[0]
+        if d // nhead != 64:
+            raise NotImplementedError("the training attention kernels need head_dim 64")
+        eps = _to_device(eps or {}, dev)
+        tok = tokens_tb.t().contiguous().view(-1).to(torch.int32)
+        tgt = targets_tb.view(T, B).t().contiguous().view(-1).to(torch.int32)
+        pos = torch.arange(T, dtype=torch.int32, device=dev).repeat(B)
+        offs = torch.arange(0, (B + 1) * T, T, dtype=torch.int32, device=dev)
+        scale_q = float(d // nhead) ** -0.5
+        self.flat_g.zero_()
+        g = self.g
+
+        # ---------------------------------------------------------------- forward, activations kept
+        pe = m.pos_encoder.pe.detach()[:, 0, :].float().contiguous()
+        x32, xs = ops.embed(tok, pos, m.encoder.weight.detach().float(), pe, math.sqrt(d), prec=prec)
+        saved = []
+        for li, layer in enumerate(m.transformerlayers):
+            kind, pre = layer.kind, f"transformerlayers.{li}."
+            a = layer.self_attn
+            S = {"kind": kind, "x32": x32, "xs": xs}
+            qkv32 = self._f32(M, 3 * d)
+            qkvs = ops.empty_split(M, 3 * d, prec, dev)
+            ops.gemm(xs, self._w(a.qkv_net.weight), prec=prec, bias=a.qkv_net.bias.detach(), col_scale=scale_q,
+                     col_scale_cols=d, out_f32=qkv32, out=qkvs, tag="qkv")
+            _, atts = ops.mha_causal_bf16(qkvs, offs, nhead, T, prec=prec)
+            y1 = self._f32(M, d)
+            ops.gemm(atts, self._w(a.o_net.weight), prec=prec, bias=a.o_net.bias.detach(), resid=x32, out_f32=y1, tag="o_net")
+            x1_32, x1s = ops.layernorm(y1, layer.norm1.weight.detach(), layer.norm1.bias.detach(), layer.norm1.eps, prec=prec)
+            S.update(qkv32=qkv32, atts=atts, y1=y1, x1_32=x1_32, x1s=x1s)
+            # first FFN projection (+ GELU or the GP mixture), pre-activation kept
+            F = layer.linear2.in_features
+            z1 = self._f32(M, F)
+            hs = ops.empty_split(M, F, prec, dev)
+            if kind == "gauss":
+                gp = layer.gpnn
+                le = eps.get(f"layer{li}") if gp.sample else None
+                use_noise = gp.sample and (le is not None or seed is not None)
+                w1_32, b1, coef = gp.weights_mean.detach(), gp.bias_mean.detach(), gp.coef_mean.detach()
+                S["gp_noise"] = use_noise
+                if use_noise:
+                    ge = (lambda k: None) if le is None else le.get
+                    if gp.gpnn_type in (1, 3):
+                        coef = self._reparam32(gp.coef_mean.detach(), gp.coef_lgstd.detach(), _TID["gp_coef"], ge("coef"), seed)
+                    if gp.gpnn_type in (2, 3):
+                        w1_32 = self._reparam32(gp.weights_mean.detach(), gp.weights_lgstd.detach(), _TID["gp_w"],
+                                                ge("weights"), seed)
+                        b1 = self._reparam32(gp.bias_mean.detach(), gp.bias_lgstd.detach(), _TID["gp_b"], ge("bias"), seed)
+                coef = coef.contiguous()
+                ops.gemm(x1s, self._w(w1_32), prec=prec, bias=b1, act=ACT_GPMIX, coef=coef, out=hs, out_pre=z1, tag="ffn1")
+                S.update(w1_32=w1_32, coef=coef)
+            else:
+                w1_32 = layer.linear1.weight.detach()
+                ops.gemm(x1s, self._w(w1_32), prec=prec, bias=layer.linear1.bias.detach(), act=ACT_GELU, out=hs, out_pre=z1,
+                         tag="ffn1")
+                S["w1_32"] = w1_32
+            S.update(z1=z1, hs=hs)
+            # second FFN projection
+            if kind == "bayes_ffn":
+                le = eps.get(f"layer{li}")
+                S["w2_eps"] = le
+                if le is not None or seed is not None:
+                    w2_32 = self._reparam32(layer.linear2.weight_mean.detach(), layer.linear2.weight_lgstd.detach(),
+                                            _TID["ffn_w2"], le, seed)
+                    S["w2_sampled"] = True
+                else:
+                    w2_32, S["w2_sampled"] = layer.linear2.weight_mean.detach(), False
+                b2 = None
+            else:
+                w2_32, b2 = layer.linear2.weight.detach(), layer.linear2.bias.detach()
+            S["w2_32"] = w2_32
+            y2 = self._f32(M, d)
+            v_active = kind == "v"
+            if v_active:
+                if T != 100:
+                    raise _lib.BlmError("the variational layer is defined for sequence length 100 only "
+                                        "(its parameters are (100, 1, d), model.py:2754-2761)")
+                f = self._f32(M, d)
+                ops.gemm(hs, self._w(w2_32), prec=prec, bias=b2, out_f32=f, tag="ffn2")
+                le = eps.get(f"layer{li}")
+                e_bt = None if le is None else le.to(dev).float().permute(1, 0, 2).contiguous().view(M, d)
+                rho = layer.hiddens_lgstd.detach().view(T, d)
+                y2 = ops.vnoise_fwd(f, rho, B, T, eps=e_bt, seed=seed, stream_id=engine._stream_id(_TID_VNOISE + li, 0),
+                                    noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
+                S.update(f=f, v_eps=e_bt)
+            else:
+                ops.gemm(hs, self._w(w2_32), prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
+            x32, xs = ops.layernorm(y2, layer.norm2.weight.detach(), layer.norm2.bias.detach(), layer.norm2.eps, prec=prec)
+            S["y2"] = y2
+            saved.append(S)
+
+        # ---------------------------------------------------------------- loss
+        E32 = m.decoder.weight.detach().float()
+        Es = self._w(E32)
+        dec_b = m.decoder.bias.detach()
+        lse = torch.empty(M, dtype=torch.float32, device=dev)
+        nll = ops.vocab_nll(xs, Es, dec_b, tgt, prec=prec, lse=lse)
+        ce, kl, loss = self.loss_buf[0:1], self.loss_buf[1:2], self.loss_buf[2:3]
+        ops.reduce_sum(nll, ce, scale=1.0 / M)
+        kl.zero_()
+
+        # ---------------------------------------------------------------- backward: decoder
+        ldv = ops._ld8(V)
+        dZ = Split(torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V],
+                   torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V] if prec == "bf16x3" else None)
+        ops.gemm(xs, Es, prec=prec, bias=dec_b, act=ACT_SOFTMAX_GRAD, lse=lse, targets=tgt, grad_scale=1.0 / M, out=dZ,
+                 tag="dlogits")
+        dx = self._f32(M, d)
+        ops.gemm(dZ, self._wt(E32), prec=prec, out_f32=dx, tag="dgrad:decoder")
+        self._wgrad(ops.transpose_bf16(dZ, prec), ops.transpose_bf16(xs, prec), g["decoder.weight"], "decoder")
+        ops.colsum(dZ, g["decoder.bias"])
+
+        # ---------------------------------------------------------------- backward: layers
+        for li in range(len(saved) - 1, -1, -1):
+            S, layer, pre = saved[li], m.transformerlayers[li], f"transformerlayers.{li}."
+            kind, a = S["kind"], layer.self_attn
+            dy2 = ops.layernorm_bwd(dx, S["y2"], layer.norm2.weight.detach(), layer.norm2.eps, g[pre + "norm2.weight"],
+                                    g[pre + "norm2.bias"])
+            if kind == "v":
+                df, klpart = ops.vnoise_bwd(dy2, S["f"], layer.hiddens_lgstd.detach().view(T, d),
+                                            layer.hiddens_mean_p.detach().view(T, d), B, T, kl_scale,
+                                            g[pre + "hiddens_lgstd"].view(T, d), g[pre + "hiddens_mean_p"].view(T, d),
+                                            eps=S["v_eps"], seed=seed, stream_id=engine._stream_id(_TID_VNOISE + li, 0),
+                                            noise_std=V_NOISE_STD)
+                ops.reduce_sum(klpart.view(-1), kl, scale=0.5 / (M * d), accumulate=True)
+            else:
+                df = dy2
+            dfs = ops.split(df, prec)
+            # FFN2: dgrad fused with the activation derivative, wgrad, bias
+            dz1 = self._f32(M, S["z1"].shape[1])
+            dz1s = ops.empty_split(M, S["z1"].shape[1], prec, dev)
+            if kind == "gauss":
+                dh = torch.empty_like(dz1)
+                ops.gemm(dfs, self._wt(S["w2_32"]), prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,
+                         out=dz1s, out_pre=dh, tag="dgrad:ffn2")
+            else:
+                ops.gemm(dfs, self._wt(S["w2_32"]), prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
+                         tag="dgrad:ffn2")
+            dft, ht = ops.transpose_split(df, prec), ops.transpose_bf16(S["hs"], prec)
+            if kind == "bayes_ffn":
+                G = g[pre + "linear2.weight_mean"]
+                self._wgrad(dft, ht, G, "ffn2")
+                lin = layer.linear2
+                if S["w2_sampled"]:
+                    ops.reparam_bwd(G, lin.weight_lgstd.detach(), G, g[pre + "linear2.weight_lgstd"], eps=S["w2_eps"],
+                                    seed=seed, stream_id=engine._stream_id(_TID["ffn_w2"], 0))
+                ops.kl_gauss(lin.weight_mean.detach(), lin.weight_lgstd.detach(), kl, accumulate=True)
+                ops.kl_gauss_bwd(lin.weight_mean.detach(), lin.weight_lgstd.detach(), kl_scale, G,
+                                 g[pre + "linear2.weight_lgstd"])
+            else:
+                self._wgrad(dft, ht, g[pre + "linear2.weight"], "ffn2")
+                ops.colsum(df, g[pre + "linear2.bias"])
+            # FFN1
+            dx1 = self._f32(M, d)
+            ops.gemm(dz1s, self._wt(S["w1_32"]), prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
+            dz1t, x1t = ops.transpose_split(dz1, prec), ops.transpose_bf16(S["x1s"], prec)
+            if kind == "gauss":
+                self._gp_backward(layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, eps.get(f"layer{li}"), seed)
+            else:
+                self._wgrad(dz1t, x1t, g[pre + "linear1.weight"], "ffn1")
+                ops.colsum(dz1, g[pre + "linear1.bias"])
+            # LayerNorm 1, output projection, attention, QKV projection
+            dy1 = ops.layernorm_bwd(dx1, S["y1"], layer.norm1.weight.detach(), layer.norm1.eps, g[pre + "norm1.weight"],
+                                    g[pre + "norm1.bias"])
+            dy1s = ops.split(dy1, prec)
+            datt = self._f32(M, d)
+            ops.gemm(dy1s, self._wt(a.o_net.weight), prec=prec, out_f32=datt, tag="dgrad:o_net")
+            self._wgrad(ops.transpose_split(dy1, prec), ops.transpose_bf16(S["atts"], prec), g[pre + "self_attn.o_net.weight"],
+                        "o_net")
+            ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
+            dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q)
+            dx = self._f32(M, d)
+            ops.gemm(ops.split(dqkv, prec), self._wt(a.qkv_net.weight), prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
+            self._wgrad(ops.transpose_split(dqkv, prec), ops.transpose_bf16(S["xs"], prec), g[pre + "self_attn.qkv_net.weight"],
+                        "qkv")
+            ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
+        # embedding: scatter-add on top of the decoder's weight gradient when the weights are tied
+        ops.embed_bwd(dx, tok, math.sqrt(d), g["encoder.weight"])
+        # loss = ce + kl * kl_scale
+        ops.reduce_sum(ce, loss)
+        ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
+        return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
+
+    def _gp_backward(self, layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, le, seed):
+        """Gradients of the GP unit (model.py:1780-1902): weights / bias / coef means, their log-sigmas
+        through the reparameterisation when the unit samples, and the unit's KL (the '-1' variant)."""
+        g, gp = self.g, layer.gpnn
+        t = gp.gpnn_type
+        gw, gb, gc = g[pre + "gpnn.weights_mean"], g[pre + "gpnn.bias_mean"], g[pre + "gpnn.coef_mean"]
+        self._wgrad(dz1t, x1t, gw, "gpnn")
+        ops.colsum(dz1, gb)
+        ops.gpmix_dcoef(S["z1"], dh, gc)
+        noise = S["gp_noise"]
+        sid = lambda name: engine._stream_id(_TID[name], 0)  # noqa: E731
+        if t in (1, 3):
+            if noise:
+                ops.reparam_bwd(gc, gp.coef_lgstd.detach(), gc, g[pre + "gpnn.coef_lgstd"],
+                                eps=None if le is None else le.get("coef"), seed=seed, stream_id=sid("gp_coef"))
+            ops.kl_gauss(gp.coef_mean.detach(), gp.coef_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.coef_mean.detach(), gp.coef_lgstd.detach(), kl_scale, gc, g[pre + "gpnn.coef_lgstd"])
+        if t in (2, 3):
+            if noise:
+                ops.reparam_bwd(gw, gp.weights_lgstd.detach(), gw, g[pre + "gpnn.weights_lgstd"],
+                                eps=None if le is None else le.get("weights"), seed=seed, stream_id=sid("gp_w"))
+                ops.reparam_bwd(gb, gp.bias_lgstd.detach(), gb, g[pre + "gpnn.bias_lgstd"],
+                                eps=None if le is None else le.get("bias"), seed=seed, stream_id=sid("gp_b"))
+            ops.kl_gauss(gp.weights_mean.detach(), gp.weights_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.weights_mean.detach(), gp.weights_lgstd.detach(), kl_scale, gw, g[pre + "gpnn.weights_lgstd"])
+            ops.kl_gauss(gp.bias_mean.detach(), gp.bias_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.bias_mean.detach(), gp.bias_lgstd.detach(), kl_scale, gb, g[pre + "gpnn.bias_lgstd"])
+
+    def apply_gradients(self):
+        """All-reduce (data parallel), global-norm clip, SGD momentum; invalidates the cached weight copies."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+        ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)
+        ops.sgd_momentum(self.flat_p, self.flat_g, self.flat_v, self.lr, self.momentum, self.norm_sq, self.clip,
+                         1.0 / self.world)
+        self.model.__dict__.pop("_blm_plans", None)
+
+    def step(self, tokens_tb, targets_tb, kl_scale, *, eps=None, seed=None):
+        out = self.forward_backward(tokens_tb, targets_tb, kl_scale, eps=eps, seed=seed)
+        self.apply_gradients()
+        return out
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def capture(self, T: int, B: int, kl_scale: float):
+        """Capture forward + backward (graph 1) and norm + clip + SGD (graph 2) for batches of shape
+        (T, B).  A step is ~250 small launches; replaying them as two graphs removes the host-side launch
+        cost that otherwise dominates a 3200-token step.  The noise of the step lives in static device
+        buffers that :meth:`step_captured` refills (Philox, outside the graph) before every replay, so the
+        graph itself only ever sees injected noise.  The all-reduce stays outside, between the graphs."""
+        m, dev = self.model, self.device
+        d = m.ninp
+        self._cap = {"T": T, "B": B, "kl_scale": float(kl_scale),
+                     "x": torch.zeros(T, B, dtype=torch.int64, device=dev),
+                     "y": torch.zeros(T, B, dtype=torch.int64, device=dev), "eps": {}, "fill": []}
+        cap = self._cap
+        for li, layer in enumerate(m.transformerlayers):
+            if layer.kind == "v":
+                buf = torch.zeros(T, B, d, dtype=torch.float32, device=dev)
+                cap["eps"][f"layer{li}"] = buf
+                cap["fill"].append((buf, _TID_VNOISE + li, V_NOISE_STD))
+            elif layer.kind == "bayes_ffn":
+                buf = torch.zeros_like(layer.linear2.weight_lgstd)
+                cap["eps"][f"layer{li}"] = buf
+                cap["fill"].append((buf, _TID["ffn_w2"], 1.0))
+            elif layer.kind == "gauss" and layer.gpnn.sample:
+                e, gp = {}, layer.gpnn
+                if gp.gpnn_type in (1, 3):
+                    e["coef"] = torch.zeros_like(gp.coef_lgstd)
+                    cap["fill"].append((e["coef"], _TID["gp_coef"], 1.0))
+                if gp.gpnn_type in (2, 3):
+                    e["weights"], e["bias"] = torch.zeros_like(gp.weights_lgstd), torch.zeros_like(gp.bias_lgstd)
+                    cap["fill"] += [(e["weights"], _TID["gp_w"], 1.0), (e["bias"], _TID["gp_b"], 1.0)]
+                cap["eps"][f"layer{li}"] = e
+        self._refill_noise(0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, lazy attributes)
+            for _ in range(2):
+                self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        cap["g1"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cap["g1"]):
+            cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"])
+        cap["g2"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cap["g2"]):
+            ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)
+            ops.sgd_momentum(self.flat_p, self.flat_g, self.flat_v, self.lr, self.momentum, self.norm_sq, self.clip,
+                             1.0 / self.world)
+        return self
+
+    def _refill_noise(self, seed: int):
+        for buf, tid, std in self._cap["fill"]:
+            ops.philox_normal(seed, engine._stream_id(tid, 0), buf.numel(), self.device, out=buf.view(-1), scale=std)
+
+    def step_captured(self, tokens_tb, targets_tb, seed: int):
+        """One step through the captured graphs; (loss, ce, kl) are 0-dim device tensors valid until the
+        next replay."""
+        cap = self._cap
+        cap["x"].copy_(tokens_tb, non_blocking=True)
+        cap["y"].copy_(targets_tb.view(cap["T"], cap["B"]), non_blocking=True)
+        self._refill_noise(seed)
+        cap["g1"].replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+        cap["g2"].replay()
+        self.model.__dict__.pop("_blm_plans", None)
+        return cap["out"]
+
+
+def _to_device(obj, dev):
+    """Injected noise arrives as (nested dicts of) CPU tensors in the oracle's layout."""
+    if isinstance(obj, dict):
+        return {k: _to_device(v, dev) for k, v in obj.items()}
+    if torch.is_tensor(obj):
+        return obj.to(dev, non_blocking=True).float().contiguous()
+    return obj

@@ -101,6 +101,41 @@ def build_model(device):
     return net.to(device).eval()
 
 
+def bench_finetune(dev, world, steps, warmup=3):
+    """BASELINE config 4: Variational Transformer (T_v_pos=11 -> both first layers variational, 5 layers),
+    d=512, FFN=4096, V=30000; one fine-tune step = CE + KL, backward, clip, SGD momentum on a per-GPU
+    batch of 32 x 100 tokens (train.py step), data parallel with one NCCL all-reduce of the gradients."""
+    import torch.distributed as dist
+    from bayeslms_b200 import model as M
+    from bayeslms_b200.trainer import FineTuner
+    torch.manual_seed(1111)
+    net = M.VTransformerModel(V, D, NHEAD, FF, NLAYERS, 0.0, True, "11").to(dev).train()
+    ft = FineTuner(net, 0.01, clip=0.25, prec="bf16")
+    g = torch.Generator().manual_seed(1111 + int(os.environ.get("RANK", 0)))
+    T, B = 100, 32
+    x = torch.randint(0, V, (T, B), generator=g).to(dev)
+    y = torch.randint(0, V, (T, B), generator=g).to(dev)
+    losses = [float(ft.step(x, y, 1e-3, seed=7 + i)[0]) for i in range(warmup)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ft.step(x, y, 1e-3, seed=100 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    losses.append(float(ft.step(x, y, 1e-3, seed=999)[0]))
+    return {"workload": "Variational Transformer LM (T_v_pos=11) 5L d512 FFN4096 V30000 fine-tune step, "
+                        "32 x 100 tokens per GPU, CE + KL, clip, SGD momentum", "dtype": "bf16",
+            "tokens_per_s": T * B * world / (ms.item() / 1e3), "ms_per_step": ms.item(),
+            "parallelism": f"dp{world}: replicated weights, one NCCL all-reduce of the flat gradient buffer per step",
+            "loss_first": losses[0], "loss_last": losses[-1], "dropout": 0.0}
+
+
 def cpu_port_tokens_per_s(data, n_utts, state_dict):
     """The reference algorithm on the host: one hypothesis at a time, batch 1, fp32 torch CPU."""
     from oracle import bayeslm_oracle as O
@@ -275,6 +310,8 @@ def main():
     _, picks_f = synth.wer(data, per_utt(fast), lo=lo)
     wer_p, picks_p = synth.wer(data, per_utt(precise), lo=lo)
 
+    finetune = bench_finetune(dev, world, max(2, args.steps))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
@@ -310,6 +347,7 @@ def main():
                         "max_abs_score_diff_vs_bf16": float(np.abs(fast - precise).max()),
                         "one_best_agreement": float(np.mean(np.asarray(picks_f) == np.asarray(picks_p))),
                         "synthetic_wer": wer_p},
+            "finetune_step": finetune,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -233,6 +233,9 @@ int blm_reparam(const float* mu, int64_t ldmu, const float* lgstd, const float* 
 /* The N(0,1) stream blm_reparam uses, exposed so tests can inject it into the
  * oracle. */
 int blm_philox_normal(uint64_t seed, uint64_t stream_id, int64_t n, float* out, blm_stream stream);
+/* out[i] = scale * that stream (the N(0, 0.1^2) hidden noise of model.py:2786 uses scale 0.1). */
+int blm_philox_normal_scaled(uint64_t seed, uint64_t stream_id, int64_t n, float scale, float* out,
+                             blm_stream stream);
 
 /* ------------------------------------------------------------ attention (c)
  * Causal multi-head self-attention over packed variable-length hypotheses.
@@ -332,8 +335,8 @@ int blm_gpmix_dcoef(const float* z, const float* dh, int64_t ld, int64_t M, int6
  * scaled by kl_scale: dfp (may be null) is the downstream gradient w.r.t. fp; outputs df,
  * drho, dmean_p and klpart[T, d] with KL = 0.5 sum(klpart) / (T B d).                          */
 int blm_vnoise_fwd(const float* f, const float* rho, const float* eps, int32_t eps_mode, uint64_t seed,
-                   uint64_t stream_id, float noise_std, int64_t B, int32_t T, int32_t d, float* fp,
-                   blm_stream stream);
+                   uint64_t stream_id, float noise_std, const float* resid /* optional: out = resid + fp */,
+                   int64_t B, int32_t T, int32_t d, float* fp, blm_stream stream);
 int blm_vnoise_bwd(const float* dfp, const float* f, const float* rho, const float* mean_p,
                    const float* eps, int32_t eps_mode, uint64_t seed, uint64_t stream_id,
                    float noise_std, int64_t B, int32_t T, int32_t d, float kl_scale, float* df,

@@ -103,3 +103,19 @@ def mat():
     _, w = ops.reparam(mu, ls, seed=1, stream_id=5, prec="bf16")
     ops.gemm(h, w, resid=x32, out_f32=y)
 line("reparam + gemm ffn2 [M,512,4096] philox", timeit(mat), 2.0 * M * d * F)
+
+# ---- LSTM recurrence (one layer, all T steps in one cooperative launch)
+H = 1024
+for (T_, B_) in ((20, 2048), (26, 1024), (20, 256)):
+    gx = torch.randn(T_ * B_, 4 * H, device=dev) * 0.1
+    whh = ops.split(torch.randn(4 * H, H, device=dev) * 0.03, "bf16")
+    h0 = torch.zeros(B_, H, device=dev); c0 = torch.zeros(B_, H, device=dev)
+    lens = torch.full((B_,), T_, dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ops.lstm_layer(gx, whh, h0, c0, lens, T_, B_, H, prec="bf16", want_f32=False, want_split=True), 10)
+    # algorithmic bytes per step: W_hh re-read 4H*H*2 + gates_x B*4H*4 + h,c write 2*B*H*4
+    byt = T_ * (4 * H * H * 2 + B_ * 4 * H * 4 + 2 * B_ * H * 4)
+    line(f"lstm_layer T={T_} B={B_} H=1024 bf16", ms, 2.0 * T_ * B_ * 4 * H * H, byt)
+    print(f"    per step {ms*1e3/T_:.1f} us", flush=True)
+whh3 = ops.split(torch.randn(4 * H, H, device=dev) * 0.03, "bf16x3")
+ms = timeit(lambda: ops.lstm_layer(gx, whh3, h0, c0, lens, T_, B_, H, prec="bf16x3", want_f32=False, want_split=True), 10)
+line(f"lstm_layer T={T_} B={B_} H=1024 bf16x3", ms, 2.0 * T_ * B_ * 4 * H * H)
