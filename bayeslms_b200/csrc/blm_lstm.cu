@@ -1,12 +1,16 @@
 // Persistent LSTM recurrence for sm_100a  (SURVEY.md 8 row a6 / north_star (b)).
 //
 // One cooperative launch runs all T steps of one layer for a batch of B sequences advanced in
-// lock step.  CTA j owns hidden units [8j, 8j+8): its 32 rows of W_hh (4 gates x 8 units, bf16
-// hi [+ lo]) are TMA-loaded ONCE into 128B-swizzled shared memory and stay resident for every
-// timestep -- HBM never sees W_hh again.  Per step each CTA
-//   * streams h_{t-1} [B, H] (bf16 hi [+ lo], double-buffered in global, L2 resident) through a
-//     TMA ring and issues tcgen05.mma  D[128 x 32] += h_tile[128 x 64] . W_slice[32 x 64]^T into
-//     one 32-column TMEM accumulator per 128-row batch tile;
+// lock step.  CTA (j, bi) owns hidden units [U j, U j + U) and batch rows block bi: its 4U rows of
+// W_hh (4 gates x U units, bf16 hi [+ lo]) are TMA-loaded ONCE into 128B-swizzled shared memory
+// and stay resident for every timestep -- HBM never sees W_hh again.  U = 16 (128 KB of W) with the
+// batch split in two in bf16 mode, U = 8 (hi + lo = 128 KB) and no split in the precise mode: what a
+// CTA must ingest per step is h_{t-1} of its batch block, so the 2-D split halves the L2 -> SM
+// traffic that bounds the step (every CTA reading all of h: 101 us per step at B = 2048, r01k).
+// Per step each CTA
+//   * streams h_{t-1} [rows, H] (bf16 hi [+ lo], double-buffered in global, L2 resident) through a
+//     TMA ring and issues tcgen05.mma  D[128 x 4U] += h_tile[128 x 64] . W_slice[4U x 64]^T into
+//     one 4U-column TMEM accumulator per 128-row batch tile;
 //   * epilogue warps read the accumulator (one batch row per thread), add the hoisted input
 //     projection gates_x[t], apply the four gate nonlinearities (i, f, o = sigmoid, g = tanh),
 //     update c and h for their 8 units, and publish h_t (fp32 state, layer output, bf16 operand
@@ -14,6 +18,7 @@
 //   * a grid-wide barrier (one atomic per CTA, bounded spin) separates the steps.
 // Rows past their own length (right padding) keep (h, c) untouched, so the final state is the
 // state after each row's last valid token (the hidden carry of score.py:271-274).
+#include <stdlib.h>
 #include <string.h>
 
 #include "blm_host.h"
@@ -21,17 +26,16 @@
 
 namespace blm {
 
-constexpr int kU = 8;            // hidden units per CTA
-constexpr int kLN = 4 * kU;      // MMA N: 4 gates x 8 units
 constexpr int kLStages = 5;      // h-tile ring depth
 constexpr int kLThreads = 256;
-constexpr int kLMaxTiles = 16;   // 16 x 32 TMEM columns = 512
+constexpr int kLMaxTiles = 16;   // per CTA: 16 x 32 (U = 8) or 8 x 64 (U = 16) TMEM columns = 512
 constexpr int kLABytes = 128 * 64 * 2;
-constexpr int kLWTile = kLN * 64 * 2;  // one K block of the W slice: 4096 B
 
 struct LstmParams {
   CUtensorMap tmH[2][2];  // [buffer][hi, lo] : h state [B, H] bf16, box 128 x 64
-  CUtensorMap tmW[2];     // [hi, lo]         : W_hh [4H, H] bf16, box 8 x 64
+  CUtensorMap tmW[2];     // [hi, lo]         : W_hh [4H, H] bf16, box U x 64
+  int unit_blocks;        // H / U
+  int tiles_per_cta;      // 128-row batch tiles per CTA (batch split)
   const float* gates_x;   // [T, B, 4H]
   const float* h0;
   const float* c0;
@@ -87,7 +91,10 @@ __device__ __forceinline__ void store_h8(__nv_bfloat16* hi, __nv_bfloat16* lo, c
   if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
+template <int kU>
 __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_constant__ LstmParams p) {
+  constexpr int kLN = 4 * kU;            // MMA N: 4 gates x U units
+  constexpr int kLWTile = kLN * 64 * 2;  // one K block of the W slice
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
@@ -101,8 +108,12 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x;  // unit block
+  const int j = blockIdx.x % p.unit_blocks;   // unit block
+  const int bi = blockIdx.x / p.unit_blocks;  // batch block
   const int H = p.H, B = p.B;
+  const int mt0 = bi * p.tiles_per_cta;                           // first 128-row tile of this CTA
+  const int n_mt = min(p.tiles_per_cta, p.m_tiles - mt0);         // its tile count
+  const int row_lo = mt0 * 128, row_hi = min(B, (mt0 + n_mt) * 128);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kLStages; ++s) {
@@ -126,13 +137,14 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
     for (int part = 0; part < parts; ++part)
       for (int kb = 0; kb < p.kblocks; ++kb)
         for (int g = 0; g < 4; ++g)
-          tma_load_2d(sW[part] + kb * kLWTile + g * 1024, &p.tmW[part], w_bar, kb * 64, g * H + j * kU,
+          tma_load_2d(sW[part] + kb * kLWTile + g * (kU * 128), &p.tmW[part], w_bar, kb * 64, g * H + j * kU,
                       kEvictFirst);
   }
 
   // prologue: publish h_{-1} = h0 as the bf16 operand and seed the running (h, c) state, own columns
-  for (int b = threadIdx.x; b < B; b += kLThreads) {
-    const long long o = static_cast<long long>(b) * H + j * kU;
+  for (int idx = threadIdx.x; idx < (row_hi - row_lo) * (kU / 8); idx += kLThreads) {
+    const int b = row_lo + idx / (kU / 8);
+    const long long o = static_cast<long long>(b) * H + j * kU + (idx % (kU / 8)) * 8;
     float h[8], c[8];
     *reinterpret_cast<float4*>(h) = __ldg(reinterpret_cast<const float4*>(p.h0 + o));
     *reinterpret_cast<float4*>(h + 4) = __ldg(reinterpret_cast<const float4*>(p.h0 + o + 4));
@@ -158,12 +170,12 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
     if (warp == 0) {
       if (lane == 0) {
         fence_proxy_async_all();  // h_{t-1} was written with generic stores by other SMs
-        for (int mt = 0; mt < p.m_tiles; ++mt)
+        for (int mt = 0; mt < n_mt; ++mt)
           for (int part = 0; part < a_parts; ++part)
             for (int kb = 0; kb < p.kblocks; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&full_bar[stage], kLABytes);
-              tma_load_2d(sA + stage * kLABytes, &p.tmH[cur][part], &full_bar[stage], kb * 64, mt * 128,
+              tma_load_2d(sA + stage * kLABytes, &p.tmH[cur][part], &full_bar[stage], kb * 64, (mt0 + mt) * 128,
                           kEvictNormal);
               if (++stage == kLStages) {
                 stage = 0;
@@ -174,9 +186,9 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
       __syncwarp();
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, kLN);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, kLN);  // N = 32 or 64
         tcgen05_fence_after();
-        for (int mt = 0; mt < p.m_tiles; ++mt) {
+        for (int mt = 0; mt < n_mt; ++mt) {
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kLN);
           uint32_t accum = 0;
           for (int part = 0; part < a_parts; ++part)
@@ -208,61 +220,70 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
       __syncwarp();
     } else if (warp >= 4) {
       const int lane_grp = warp & 3;
-      for (int mt = 0; mt < p.m_tiles; ++mt) {
+      for (int mt = 0; mt < n_mt; ++mt) {
         mbar_wait(&tfull_bar[mt], static_cast<uint32_t>(t & 1));
         tcgen05_fence_after();
-        float v[32];
+        float v[kLN];
         __syncwarp();
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(mt * kLN), v);
+#pragma unroll
+        for (int q = 0; q < kLN / 32; ++q)
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(mt * kLN + q * 32),
+                        *reinterpret_cast<float(*)[32]>(v + q * 32));
         tmem_ld_wait();
-        const int b = mt * 128 + lane_grp * 32 + lane;
+        const int b = (mt0 + mt) * 128 + lane_grp * 32 + lane;
         if (b < B) {
-          const long long o = static_cast<long long>(b) * H + j * kU;
-          const long long ot = (static_cast<long long>(t) * B + b) * H + j * kU;
-          __nv_bfloat16* nh = p.hbuf[nxt][0] + o;
-          __nv_bfloat16* nl = p.nsplit == 3 ? p.hbuf[nxt][1] + o : nullptr;
-          if (t < __ldg(p.lengths + b)) {
-            const float* gx = p.gates_x + (static_cast<long long>(t) * B + b) * 4 * H + j * kU;
+          const bool live = t < __ldg(p.lengths + b);
+          const float* gx = p.gates_x + (static_cast<long long>(t) * B + b) * 4 * H + j * kU;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 x0 = __ldg(reinterpret_cast<const float4*>(gx + g * H));
-              const float4 x1 = __ldg(reinterpret_cast<const float4*>(gx + g * H + 4));
-              v[g * 8 + 0] += x0.x; v[g * 8 + 1] += x0.y; v[g * 8 + 2] += x0.z; v[g * 8 + 3] += x0.w;
-              v[g * 8 + 4] += x1.x; v[g * 8 + 5] += x1.y; v[g * 8 + 6] += x1.z; v[g * 8 + 7] += x1.w;
-            }
-            float c[8], h[8];
-            *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(p.cT + o);
-            *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(p.cT + o + 4);
+          for (int u8 = 0; u8 < kU; u8 += 8) {   // groups of 8 units: 16-byte bf16 stores
+            const long long o = static_cast<long long>(b) * H + j * kU + u8;
+            const long long ot = (static_cast<long long>(t) * B + b) * H + j * kU + u8;
+            __nv_bfloat16* nh = p.hbuf[nxt][0] + o;
+            __nv_bfloat16* nl = p.nsplit == 3 ? p.hbuf[nxt][1] + o : nullptr;
+            if (live) {
+              float a[4][8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float ig = 1.0f / (1.0f + expf(-v[u]));
-              const float fg = 1.0f / (1.0f + expf(-v[8 + u]));
-              const float gg = tanhf(v[16 + u]);
-              const float og = 1.0f / (1.0f + expf(-v[24 + u]));
-              c[u] = fg * c[u] + ig * gg;
-              h[u] = og * tanhf(c[u]);
-            }
-            *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
-            *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
-            *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
-            *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
-            store_h8(nh, nl, h);
-            if (p.out_f32) {
-              *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
-              *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
-            }
-            if (p.out_hi) store_h8(p.out_hi + ot, p.out_lo ? p.out_lo + ot : nullptr, h);
-          } else {
-            // padded step: state unchanged; carry the bf16 operand into the other buffer
-            *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(p.hbuf[cur][0] + o);
-            if (nl) *reinterpret_cast<uint4*>(nl) = *reinterpret_cast<const uint4*>(p.hbuf[cur][1] + o);
-            if (p.out_f32) {
-              *reinterpret_cast<float4*>(p.out_f32 + ot) = make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (p.out_hi) {
-              *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
-              if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + ot) = make_uint4(0, 0, 0, 0);
+              for (int g = 0; g < 4; ++g) {
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(gx + g * H + u8));
+                const float4 x1 = __ldg(reinterpret_cast<const float4*>(gx + g * H + u8 + 4));
+                const float* vv = v + g * kU + u8;
+                a[g][0] = vv[0] + x0.x; a[g][1] = vv[1] + x0.y; a[g][2] = vv[2] + x0.z; a[g][3] = vv[3] + x0.w;
+                a[g][4] = vv[4] + x1.x; a[g][5] = vv[5] + x1.y; a[g][6] = vv[6] + x1.z; a[g][7] = vv[7] + x1.w;
+              }
+              float c[8], h[8];
+              *reinterpret_cast<float4*>(c) = *reinterpret_cast<const float4*>(p.cT + o);
+              *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(p.cT + o + 4);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float ig = 1.0f / (1.0f + expf(-a[0][u]));
+                const float fg = 1.0f / (1.0f + expf(-a[1][u]));
+                const float gg = tanhf(a[2][u]);
+                const float og = 1.0f / (1.0f + expf(-a[3][u]));
+                c[u] = fg * c[u] + ig * gg;
+                h[u] = og * tanhf(c[u]);
+              }
+              *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
+              *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
+              *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
+              *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
+              store_h8(nh, nl, h);
+              if (p.out_f32) {
+                *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
+                *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
+              }
+              if (p.out_hi) store_h8(p.out_hi + ot, p.out_lo ? p.out_lo + ot : nullptr, h);
+            } else {
+              // padded step: state unchanged; carry the bf16 operand into the other buffer
+              *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(p.hbuf[cur][0] + o);
+              if (nl) *reinterpret_cast<uint4*>(nl) = *reinterpret_cast<const uint4*>(p.hbuf[cur][1] + o);
+              if (p.out_f32) {
+                *reinterpret_cast<float4*>(p.out_f32 + ot) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (p.out_hi) {
+                *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
+                if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + ot) = make_uint4(0, 0, 0, 0);
+              }
             }
           }
         }
@@ -281,14 +302,16 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-static size_t lstm_smem_bytes(int kblocks, int nsplit) {
-  return static_cast<size_t>((nsplit == 3 ? 2 : 1) * kblocks * kLWTile + kLStages * kLABytes +
+static size_t lstm_smem_bytes(int kblocks, int nsplit, int U) {
+  return static_cast<size_t>((nsplit == 3 ? 2 : 1) * kblocks * (4 * U * 128) + kLStages * kLABytes +
                              (2 * kLStages + kLMaxTiles + 1) * 8 + 16 + 1024);
 }
 
 int lstm_init() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(lstm_smem_bytes(16, 3))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 3, 8))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 1, 16))));
   return BLM_OK;
 }
 
@@ -310,10 +333,10 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
               "null LSTM argument");
   BLM_REQUIRE(T >= 1 && B >= 1 && T < (1 << 20), BLM_ERR_SHAPE, "bad LSTM shape T=%lld B=%lld", (long long)T,
               (long long)B);
-  BLM_REQUIRE(H >= kU && (H % kU) == 0 && H <= 1024, BLM_ERR_SHAPE,
+  BLM_REQUIRE(H >= 8 && (H % 8) == 0 && H <= 1024, BLM_ERR_SHAPE,
               "hidden size %lld must be a multiple of 8 and <= 1024 (W_hh slice must fit in shared memory)",
               (long long)H);
-  BLM_REQUIRE(H / kU <= num_sms(), BLM_ERR_SHAPE, "hidden size %lld needs more CTAs than SMs", (long long)H);
+  BLM_REQUIRE(H / 8 <= num_sms(), BLM_ERR_SHAPE, "hidden size %lld needs more CTAs than SMs", (long long)H);
   BLM_REQUIRE(B <= 128 * kLMaxTiles, BLM_ERR_SHAPE, "batch %lld exceeds %d rows per launch", (long long)B,
               128 * kLMaxTiles);
   BLM_REQUIRE(!out_lo || out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
@@ -347,17 +370,26 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
       int rc = encode_tmap_bf16(&p.tmH[buf][part], p.hbuf[buf][part], B, H, H, 128);
       if (rc != BLM_OK) return rc;
     }
-  int rc = encode_tmap_bf16(&p.tmW[0], w_hh_hi, 4 * H, H, H, 8);
+  // bf16 mode: 16 units per CTA and the batch split over two CTA rows (halves the per-step h ingest);
+  // precise mode keeps 8 units per CTA (hi + lo slices fill the same 128 KB) and no batch split
+  static const bool force_u8 = getenv("BLM_LSTM_U8") != nullptr;  // A/B switch for profiling
+  const int U = (!w_hh_lo && (H % 16) == 0 && !force_u8) ? 16 : 8;
+  const int nb = (U == 16 && p.m_tiles >= 2 && 2 * (H / U) <= num_sms()) ? 2 : 1;
+  p.unit_blocks = static_cast<int>(H / U);
+  p.tiles_per_cta = (p.m_tiles + nb - 1) / nb;
+  BLM_REQUIRE(p.tiles_per_cta * 4 * U <= 512, BLM_ERR_SHAPE, "batch %lld exceeds the TMEM accumulators of one launch",
+              (long long)B);
+  int rc = encode_tmap_bf16(&p.tmW[0], w_hh_hi, 4 * H, H, H, U);
   if (rc != BLM_OK) return rc;
-  rc = encode_tmap_bf16(&p.tmW[1], w_hh_lo ? w_hh_lo : w_hh_hi, 4 * H, H, H, 8);
+  rc = encode_tmap_bf16(&p.tmW[1], w_hh_lo ? w_hh_lo : w_hh_hi, 4 * H, H, H, U);
   if (rc != BLM_OK) return rc;
 
   cudaStream_t st = as_stream(stream);
   BLM_CHECK_CUDA(cudaMemsetAsync(p.barrier, 0, 256, st));
   void* args[] = {&p};
-  const dim3 grid(static_cast<unsigned>(H / kU)), block(kLThreads);
-  BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_layer_kernel), grid, block, args,
-                                             lstm_smem_bytes(p.kblocks, p.nsplit), st));
+  const dim3 grid(static_cast<unsigned>(p.unit_blocks * nb)), block(kLThreads);
+  void* fn = U == 16 ? reinterpret_cast<void*>(lstm_layer_kernel<16>) : reinterpret_cast<void*>(lstm_layer_kernel<8>);
+  BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, lstm_smem_bytes(p.kblocks, p.nsplit, U), st));
   return BLM_OK;
 }
 

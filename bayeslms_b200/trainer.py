@@ -99,10 +99,10 @@ class FineTuner:
 
     # ------------------------------------------------------------------ one step
     def forward_backward(self, tokens_tb: torch.Tensor, targets_tb: torch.Tensor, kl_scale: float, *,
-                         eps: Optional[dict] = None, seed: Optional[int] = None):
+                         eps: Optional[dict] = None, seed: Optional[int] = None, v_eps_layout: str = "tbd"):
         """Fills the gradient buffer for the batch (T, B); returns (loss, ce, kl) as 0-dim device tensors.
         ``eps``: injected noise in the oracle's layout ({'layer<i>': ...}; V layers: (T, B, d) tensors
-        already scaled by 0.1); ``seed``: Philox noise instead."""
+        already scaled by 0.1, or (B, T, d) with ``v_eps_layout="btd"``); ``seed``: Philox noise instead."""
         m, prec, dev = self.model, self.prec, self.device
         T, B = tokens_tb.shape
         M, d, nhead = T * B, m.ninp, m.nhead
@@ -185,7 +185,12 @@ class FineTuner:
                 f = self._f32(M, d)
                 ops.gemm(hs, self._w(w2_32), prec=prec, bias=b2, out_f32=f, tag="ffn2")
                 le = eps.get(f"layer{li}")
-                e_bt = None if le is None else le.to(dev).float().permute(1, 0, 2).contiguous().view(M, d)
+                if le is None:
+                    e_bt = None
+                elif v_eps_layout == "btd":
+                    e_bt = le.view(M, d)
+                else:
+                    e_bt = le.permute(1, 0, 2).contiguous().view(M, d)
                 rho = layer.hiddens_lgstd.detach().view(T, d)
                 y2 = ops.vnoise_fwd(f, rho, B, T, eps=e_bt, seed=seed, stream_id=engine._stream_id(_TID_VNOISE + li, 0),
                                     noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
@@ -345,7 +350,7 @@ class FineTuner:
         cap = self._cap
         for li, layer in enumerate(m.transformerlayers):
             if layer.kind == "v":
-                buf = torch.zeros(T, B, d, dtype=torch.float32, device=dev)
+                buf = torch.zeros(B, T, d, dtype=torch.float32, device=dev)   # the kernel's own (sequence-major) layout
                 cap["eps"][f"layer{li}"] = buf
                 cap["fill"].append((buf, _TID_VNOISE + li, V_NOISE_STD))
             elif layer.kind == "bayes_ffn":
@@ -366,12 +371,12 @@ class FineTuner:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, lazy attributes)
             for _ in range(2):
-                self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"])
+                self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         cap["g1"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cap["g1"]):
-            cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"])
+            cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
         cap["g2"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cap["g2"]):
             ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)

@@ -115,20 +115,21 @@ def bench_finetune(dev, world, steps, warmup=3):
     T, B = 100, 32
     x = torch.randint(0, V, (T, B), generator=g).to(dev)
     y = torch.randint(0, V, (T, B), generator=g).to(dev)
-    losses = [float(ft.step(x, y, 1e-3, seed=7 + i)[0]) for i in range(warmup)]
+    ft.capture(T, B, 1e-3)           # forward+backward and optimiser as two CUDA graphs; noise refreshed per step
+    losses = [float(ft.step_captured(x, y, 7 + i)[0]) for i in range(warmup)]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        ft.step(x, y, 1e-3, seed=100 + i)
+        ft.step_captured(x, y, 100 + i)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    losses.append(float(ft.step(x, y, 1e-3, seed=999)[0]))
+    losses.append(float(ft.step_captured(x, y, 999)[0]))
     return {"workload": "Variational Transformer LM (T_v_pos=11) 5L d512 FFN4096 V30000 fine-tune step, "
                         "32 x 100 tokens per GPU, CE + KL, clip, SGD momentum", "dtype": "bf16",
             "tokens_per_s": T * B * world / (ms.item() / 1e3), "ms_per_step": ms.item(),
@@ -310,7 +311,7 @@ def main():
     _, picks_f = synth.wer(data, per_utt(fast), lo=lo)
     wer_p, picks_p = synth.wer(data, per_utt(precise), lo=lo)
 
-    finetune = bench_finetune(dev, world, max(2, args.steps))
+    finetune = bench_finetune(dev, world, max(10, args.steps))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -149,3 +149,26 @@ def test_finetune_reduces_the_loss_and_philox_noise_is_reproducible():
     net.eval()
     s = net.score(PackedBatch.from_lists([x[:, 0].tolist()], [y[:, 0].tolist()], DEV), prec="bf16x3")
     assert torch.isfinite(s).all()
+
+
+def test_captured_step_equals_eager_step():
+    """The CUDA-graph replay (noise refreshed outside the graph with the same Philox streams) takes the
+    same steps as the eager path with seed-driven noise."""
+    from bayeslms_b200.trainer import FineTuner
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, V, (100, 4), generator=g).to(DEV)
+    y = torch.randint(0, V, (100, 4), generator=g).to(DEV)
+    outs = []
+    for captured in (False, True):
+        net, _, _ = _build("v_tm", 4, v_pos=3)
+        ft = FineTuner(net.to(DEV).train(), 0.05, clip=0.25, prec="bf16x3")
+        if captured:
+            ft.capture(100, 4, 0.01)
+        losses = []
+        for i in range(3):
+            out = ft.step_captured(x, y, 5 + i) if captured else ft.step(x, y, 0.01, seed=5 + i)
+            losses.append(float(out[0]))
+        outs.append((losses, ft.flat_p.clone()))
+    (l0, p0), (l1, p1) = outs
+    assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-5, (l0, l1)
+    assert (p0 - p1).abs().max().item() < 1e-6
