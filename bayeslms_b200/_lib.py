@@ -87,9 +87,11 @@ SIGNATURES = {
     "blm_kl_workspace_bytes": (_i64, []),
     "blm_kl_gauss": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _f, _i32, _p, _p, _p]),
     "blm_transpose_split": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "blm_split_transpose": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _p]),
     "blm_transpose_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _p]),
-    "blm_colsum": (C.c_int, [_p, _i64, _i64, _i64, _f, _i32, _p, _p]),
-    "blm_colsum_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i32, _p, _p]),
+    "blm_colsum_workspace_bytes": (_i64, [_i64, _i64]),
+    "blm_colsum": (C.c_int, [_p, _i64, _i64, _i64, _f, _i32, _p, _p, _p]),
+    "blm_colsum_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i32, _p, _p, _p]),
     "blm_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),
     "blm_layernorm_bwd": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "blm_mha_causal_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p]),

@@ -25,7 +25,10 @@ template <typename Src>
 __global__ void __launch_bounds__(256) transpose_kernel(const Src* __restrict__ x_hi, const Src* __restrict__ x_lo,
                                                         long long ldx, long long R, long long C,
                                                         __nv_bfloat16* __restrict__ out_hi,
-                                                        __nv_bfloat16* __restrict__ out_lo, long long ldo) {
+                                                        __nv_bfloat16* __restrict__ out_lo, long long ldo,
+                                                        __nv_bfloat16* __restrict__ dir_hi = nullptr,
+                                                        __nv_bfloat16* __restrict__ dir_lo = nullptr,
+                                                        long long ldd = 0) {
   __shared__ float tile[32][33];
   const long long tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -44,6 +47,11 @@ __global__ void __launch_bounds__(256) transpose_kernel(const Src* __restrict__ 
         }
       }
       tile[ty + 8 * k][tx] = v;
+      if (dir_hi && r < R && c < C) {  // the untransposed bf16 split of the same element, for free
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        dir_hi[r * ldd + c] = h;
+        if (dir_lo) dir_lo[r * ldd + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -61,37 +69,92 @@ __global__ void __launch_bounds__(256) transpose_kernel(const Src* __restrict__ 
 }
 
 // ------------------------------------------------------------------ column sums
-// out[n] (+)= scale * sum_m x[m, n]: CTA = 32 columns x 8 row lanes, fixed summation order.
+// out[n] (+)= scale * sum_m x[m, n].  Grid = (column blocks of 128) x (row splits): a thread owns 4
+// adjacent columns (one 128-bit fp32 / 64-bit bf16 load per row), the 8 warps of a CTA take rows
+// round-robin inside the CTA's row range, partial sums go to the workspace [row_splits, N] and the
+// last CTA of each column block (atomic ticket) folds them in split order -- deterministic, and
+// enough CTAs to fill the chip even for N = 512.
+struct ColsumWs {
+  unsigned int tickets[1024];  // one per column block
+};
+
 template <typename Src>
 __global__ void __launch_bounds__(256) colsum_kernel(const Src* __restrict__ x_hi, const Src* __restrict__ x_lo,
                                                      long long ldx, long long M, long long N, float scale,
-                                                     int accumulate, float* __restrict__ out) {
-  __shared__ float part[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (long long n0 = static_cast<long long>(blockIdx.x) * 32; n0 < N; n0 += static_cast<long long>(gridDim.x) * 32) {
-    const long long n = n0 + tx;
-    float s = 0.0f;
-    if (n < N) {
-      for (long long m = ty; m < M; m += 8) {
-        if constexpr (sizeof(Src) == 4) {
-          s += reinterpret_cast<const float*>(x_hi)[m * ldx + n];
+                                                     int accumulate, float* __restrict__ out,
+                                                     float* __restrict__ partial, unsigned int* __restrict__ tickets) {
+  __shared__ float4 part[8][32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n = (static_cast<long long>(blockIdx.x) * 32 + lane) * 4;
+  const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    const bool vec = (n + 4 <= N);
+    for (long long m = r0 + warp; m < r1; m += 8) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (sizeof(Src) == 4) {
+        const float* p = reinterpret_cast<const float*>(x_hi) + m * ldx + n;
+        if (vec && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         } else {
-          float v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_hi)[m * ldx + n]);
-          if (x_lo) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_lo)[m * ldx + n]);
-          s += v;
+          for (int k = 0; k < 4; ++k)
+            if (n + k < N) v[k] = p[k];
+        }
+      } else {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(x_hi) + m * ldx + n;
+        const __nv_bfloat16* pl = x_lo ? reinterpret_cast<const __nv_bfloat16*>(x_lo) + m * ldx + n : nullptr;
+        if (vec && ((reinterpret_cast<uintptr_t>(p) & 7u) == 0)) {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+          v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+          v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+          if (pl) {
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>(pl));
+            v[0] += __uint_as_float(l.x << 16); v[1] += __uint_as_float(l.x & 0xffff0000u);
+            v[2] += __uint_as_float(l.y << 16); v[3] += __uint_as_float(l.y & 0xffff0000u);
+          }
+        } else {
+          for (int k = 0; k < 4; ++k)
+            if (n + k < N) v[k] = __bfloat162float(p[k]) + (pl ? __bfloat162float(pl[k]) : 0.0f);
         }
       }
+      s.x += v[0]; s.y += v[1]; s.z += v[2]; s.w += v[3];
     }
-    part[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0 && n < N) {
-      float t = 0.0f;
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float4 t = part[0][lane];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t += part[k][tx];
-      t *= scale;
-      out[n] = accumulate ? out[n] + t : t;
+    for (int k = 1; k < 8; ++k) {
+      t.x += part[k][lane].x; t.y += part[k][lane].y; t.z += part[k][lane].z; t.w += part[k][lane].w;
     }
-    __syncthreads();
+    if (n < N) {
+      float* dst = partial + static_cast<long long>(blockIdx.y) * N + n;
+      dst[0] = t.x;
+      if (n + 1 < N) dst[1] = t.y;
+      if (n + 2 < N) dst[2] = t.z;
+      if (n + 3 < N) dst[3] = t.w;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) is_last = (atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < 128; c += 256) {
+      const long long col = static_cast<long long>(blockIdx.x) * 128 + c;
+      if (col < N) {
+        float t = 0.0f;
+        for (unsigned int r = 0; r < gridDim.y; ++r) t += partial[static_cast<long long>(r) * N + col];
+        t *= scale;
+        out[col] = accumulate ? out[col] + t : t;
+      }
+    }
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0;  // ready for the next launch
   }
 }
 
@@ -574,6 +637,30 @@ int train_init() {
 
 }  // namespace blm
 
+static int colsum_row_splits(int64_t M, int64_t N) {
+  const int64_t col_blocks = (N + 127) / 128;
+  int64_t splits = (2 * (blm::num_sms() > 0 ? blm::num_sms() : 148) + col_blocks - 1) / col_blocks;
+  const int64_t max_by_rows = (M + 31) / 32;  // at least 32 rows per CTA
+  if (splits > max_by_rows) splits = max_by_rows;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  return static_cast<int>(splits);
+}
+
+template <typename Src>
+static int colsum_launch(const Src* hi, const Src* lo, int64_t ld, int64_t M, int64_t N, float scale, int32_t accumulate,
+                         float* out, void* workspace, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(hi && out && workspace && M > 0 && N > 0 && ld >= N, BLM_ERR_ARG, "bad colsum arguments");
+  BLM_REQUIRE((N + 127) / 128 <= 1024, BLM_ERR_SHAPE, "colsum: N=%lld too wide", (long long)N);
+  ColsumWs* ws = reinterpret_cast<ColsumWs*>(workspace);
+  float* partial = reinterpret_cast<float*>(ws + 1);
+  const dim3 grid(static_cast<unsigned>((N + 127) / 128), static_cast<unsigned>(colsum_row_splits(M, N)));
+  colsum_kernel<Src><<<grid, 256, 0, as_stream(stream)>>>(hi, lo, ld, M, N, scale, accumulate, out, partial, ws->tickets);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 extern "C" {
 
 int blm_transpose_split(const float* x, int64_t ldx, int64_t R, int64_t C, blm_bf16* out_hi, blm_bf16* out_lo,
@@ -582,6 +669,18 @@ int blm_transpose_split(const float* x, int64_t ldx, int64_t R, int64_t C, blm_b
   BLM_REQUIRE(x && out_hi && R > 0 && C > 0 && ldx >= C && ldo >= R, BLM_ERR_ARG, "bad transpose arguments");
   transpose_kernel<float><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
       x, nullptr, ldx, R, C, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_split_transpose(const float* x, int64_t ldx, int64_t R, int64_t C, blm_bf16* hi, blm_bf16* lo, int64_t ld,
+                        blm_bf16* t_hi, blm_bf16* t_lo, int64_t ldt, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(x && hi && t_hi && R > 0 && C > 0 && ldx >= C && ld >= C && ldt >= R, BLM_ERR_ARG,
+              "bad split_transpose arguments");
+  transpose_kernel<float><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
+      x, nullptr, ldx, R, C, reinterpret_cast<__nv_bfloat16*>(t_hi), reinterpret_cast<__nv_bfloat16*>(t_lo), ldt,
+      reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }
@@ -597,25 +696,20 @@ int blm_transpose_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64
   return BLM_OK;
 }
 
+int64_t blm_colsum_workspace_bytes(int64_t M, int64_t N) {
+  (void)M;
+  return static_cast<int64_t>(sizeof(blm::ColsumWs)) + 64 * N * static_cast<int64_t>(sizeof(float));
+}
+
 int blm_colsum(const float* x, int64_t ldx, int64_t M, int64_t N, float scale, int32_t accumulate, float* out,
-               blm_stream stream) {
-  using namespace blm;
-  BLM_REQUIRE(x && out && M > 0 && N > 0 && ldx >= N, BLM_ERR_ARG, "bad colsum arguments");
-  colsum_kernel<float><<<tgrid((N + 31) / 32, 1, 8), 256, 0, as_stream(stream)>>>(x, nullptr, ldx, M, N, scale,
-                                                                                accumulate, out);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+               void* workspace, blm_stream stream) {
+  return colsum_launch<float>(x, nullptr, ldx, M, N, scale, accumulate, out, workspace, stream);
 }
 
 int blm_colsum_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t M, int64_t N, float scale,
-                    int32_t accumulate, float* out, blm_stream stream) {
-  using namespace blm;
-  BLM_REQUIRE(hi && out && M > 0 && N > 0 && ld >= N, BLM_ERR_ARG, "bad colsum arguments");
-  colsum_kernel<__nv_bfloat16><<<tgrid((N + 31) / 32, 1, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), ld, M, N, scale,
-      accumulate, out);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+                    int32_t accumulate, float* out, void* workspace, blm_stream stream) {
+  return colsum_launch<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo),
+                                      ld, M, N, scale, accumulate, out, workspace, stream);
 }
 
 static int ln_bwd_blocks(int64_t M) {

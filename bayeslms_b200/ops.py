@@ -437,6 +437,22 @@ def transpose_split(x: torch.Tensor, prec: str = "bf16x3") -> Split:
     return Split(hi[:, :R], None if lo is None else lo[:, :R])
 
 
+def split_transpose(x: torch.Tensor, prec: str = "bf16x3"):
+    """fp32 [R, C] -> (Split [R, C], Split [C, R]) in one pass over x."""
+    x = x.detach()
+    R, C = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    ld, ldt = _ld8(C), _ld8(R)
+    two = prec == "bf16x3"
+    mk = lambda r, l: torch.empty(r, l, dtype=torch.bfloat16, device=x.device)  # noqa: E731
+    hi, lo = mk(R, ld), (mk(R, ld) if two else None)
+    thi, tlo = mk(C, ldt), (mk(C, ldt) if two else None)
+    with _op("split_transpose", 1):
+        check(lib().blm_split_transpose(_ptr(x), x.stride(0), R, C, _ptr(hi), _ptr(lo), ld, _ptr(thi), _ptr(tlo), ldt,
+                                        _stream()), "blm_split_transpose")
+    return (Split(hi[:, :C], None if lo is None else lo[:, :C]), Split(thi[:, :R], None if tlo is None else tlo[:, :R]))
+
+
 def transpose_bf16(x: Split, prec: str = "bf16x3") -> Split:
     """Split [R, C] -> Split [C, R]."""
     R, C = x.hi.shape
@@ -453,15 +469,16 @@ def transpose_bf16(x: Split, prec: str = "bf16x3") -> Split:
 
 def colsum(x, out: torch.Tensor, *, scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
     """out[n] (+)= scale * sum_m x[m, n]; x fp32 [M, N] or a Split."""
-    if isinstance(x, Split):
-        M, N = x.hi.shape
-        with _op("colsum", 1):
+    first = x.hi if isinstance(x, Split) else x
+    M, N = first.shape
+    ws = _workspace("colsum", lib().blm_colsum_workspace_bytes(M, N), first.device, zero=True)
+    with _op("colsum", 1):
+        if isinstance(x, Split):
             check(lib().blm_colsum_bf16(_ptr(x.hi), _ptr(x.lo), x.hi.stride(0), M, N, scale, int(accumulate), _ptr(out),
-                                        _stream()), "blm_colsum_bf16")
-    else:
-        M, N = x.shape
-        with _op("colsum", 1):
-            check(lib().blm_colsum(_ptr(x), x.stride(0), M, N, scale, int(accumulate), _ptr(out), _stream()), "blm_colsum")
+                                        _ptr(ws), _stream()), "blm_colsum_bf16")
+        else:
+            check(lib().blm_colsum(_ptr(x), x.stride(0), M, N, scale, int(accumulate), _ptr(out), _ptr(ws), _stream()),
+                  "blm_colsum")
     return out
 
 

@@ -78,6 +78,10 @@ class FineTuner:
     def _w(self, w: torch.Tensor) -> Split:
         return ops.split(w.detach(), self.prec)
 
+    def _w2(self, w: torch.Tensor):
+        """(Split [N, K], Split [K, N]) of an fp32 weight: forward B operand and dgrad B operand, one pass."""
+        return ops.split_transpose(w.detach().float().contiguous(), self.prec)
+
     def _wt(self, w: torch.Tensor) -> Split:
         """[N, K] fp32 weight -> Split of its transpose [K, N] (B operand of the dgrad product)."""
         return ops.transpose_split(w.detach().float().contiguous(), self.prec)
@@ -128,11 +132,13 @@ class FineTuner:
             S = {"kind": kind, "x32": x32, "xs": xs}
             qkv32 = self._f32(M, 3 * d)
             qkvs = ops.empty_split(M, 3 * d, prec, dev)
-            ops.gemm(xs, self._w(a.qkv_net.weight), prec=prec, bias=a.qkv_net.bias.detach(), col_scale=scale_q,
+            wqkv, S["wqkv_t"] = self._w2(a.qkv_net.weight)
+            ops.gemm(xs, wqkv, prec=prec, bias=a.qkv_net.bias.detach(), col_scale=scale_q,
                      col_scale_cols=d, out_f32=qkv32, out=qkvs, tag="qkv")
             _, atts = ops.mha_causal_bf16(qkvs, offs, nhead, T, prec=prec)
             y1 = self._f32(M, d)
-            ops.gemm(atts, self._w(a.o_net.weight), prec=prec, bias=a.o_net.bias.detach(), resid=x32, out_f32=y1, tag="o_net")
+            wo, S["wo_t"] = self._w2(a.o_net.weight)
+            ops.gemm(atts, wo, prec=prec, bias=a.o_net.bias.detach(), resid=x32, out_f32=y1, tag="o_net")
             x1_32, x1s = ops.layernorm(y1, layer.norm1.weight.detach(), layer.norm1.bias.detach(), layer.norm1.eps, prec=prec)
             S.update(qkv32=qkv32, atts=atts, y1=y1, x1_32=x1_32, x1s=x1s)
             # first FFN projection (+ GELU or the GP mixture), pre-activation kept
@@ -154,13 +160,14 @@ class FineTuner:
                                                 ge("weights"), seed)
                         b1 = self._reparam32(gp.bias_mean.detach(), gp.bias_lgstd.detach(), _TID["gp_b"], ge("bias"), seed)
                 coef = coef.contiguous()
-                ops.gemm(x1s, self._w(w1_32), prec=prec, bias=b1, act=ACT_GPMIX, coef=coef, out=hs, out_pre=z1, tag="ffn1")
-                S.update(w1_32=w1_32, coef=coef)
+                w1, S["w1_t"] = self._w2(w1_32)
+                ops.gemm(x1s, w1, prec=prec, bias=b1, act=ACT_GPMIX, coef=coef, out=hs, out_pre=z1, tag="ffn1")
+                S["coef"] = coef
             else:
                 w1_32 = layer.linear1.weight.detach()
-                ops.gemm(x1s, self._w(w1_32), prec=prec, bias=layer.linear1.bias.detach(), act=ACT_GELU, out=hs, out_pre=z1,
+                w1, S["w1_t"] = self._w2(w1_32)
+                ops.gemm(x1s, w1, prec=prec, bias=layer.linear1.bias.detach(), act=ACT_GELU, out=hs, out_pre=z1,
                          tag="ffn1")
-                S["w1_32"] = w1_32
             S.update(z1=z1, hs=hs)
             # second FFN projection
             if kind == "bayes_ffn":
@@ -175,7 +182,7 @@ class FineTuner:
                 b2 = None
             else:
                 w2_32, b2 = layer.linear2.weight.detach(), layer.linear2.bias.detach()
-            S["w2_32"] = w2_32
+            w2, S["w2_t"] = self._w2(w2_32)
             y2 = self._f32(M, d)
             v_active = kind == "v"
             if v_active:
@@ -183,7 +190,7 @@ class FineTuner:
                     raise _lib.BlmError("the variational layer is defined for sequence length 100 only "
                                         "(its parameters are (100, 1, d), model.py:2754-2761)")
                 f = self._f32(M, d)
-                ops.gemm(hs, self._w(w2_32), prec=prec, bias=b2, out_f32=f, tag="ffn2")
+                ops.gemm(hs, w2, prec=prec, bias=b2, out_f32=f, tag="ffn2")
                 le = eps.get(f"layer{li}")
                 if le is None:
                     e_bt = None
@@ -196,14 +203,14 @@ class FineTuner:
                                     noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
                 S.update(f=f, v_eps=e_bt)
             else:
-                ops.gemm(hs, self._w(w2_32), prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
+                ops.gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
             x32, xs = ops.layernorm(y2, layer.norm2.weight.detach(), layer.norm2.bias.detach(), layer.norm2.eps, prec=prec)
             S["y2"] = y2
             saved.append(S)
 
         # ---------------------------------------------------------------- loss
         E32 = m.decoder.weight.detach().float()
-        Es = self._w(E32)
+        Es, Et = self._w2(E32)
         dec_b = m.decoder.bias.detach()
         lse = torch.empty(M, dtype=torch.float32, device=dev)
         nll = ops.vocab_nll(xs, Es, dec_b, tgt, prec=prec, lse=lse)
@@ -218,7 +225,7 @@ class FineTuner:
         ops.gemm(xs, Es, prec=prec, bias=dec_b, act=ACT_SOFTMAX_GRAD, lse=lse, targets=tgt, grad_scale=1.0 / M, out=dZ,
                  tag="dlogits")
         dx = self._f32(M, d)
-        ops.gemm(dZ, self._wt(E32), prec=prec, out_f32=dx, tag="dgrad:decoder")
+        ops.gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
         self._wgrad(ops.transpose_bf16(dZ, prec), ops.transpose_bf16(xs, prec), g["decoder.weight"], "decoder")
         ops.colsum(dZ, g["decoder.bias"])
 
@@ -243,10 +250,10 @@ class FineTuner:
             dz1s = ops.empty_split(M, S["z1"].shape[1], prec, dev)
             if kind == "gauss":
                 dh = torch.empty_like(dz1)
-                ops.gemm(dfs, self._wt(S["w2_32"]), prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,
+                ops.gemm(dfs, S["w2_t"], prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,
                          out=dz1s, out_pre=dh, tag="dgrad:ffn2")
             else:
-                ops.gemm(dfs, self._wt(S["w2_32"]), prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
+                ops.gemm(dfs, S["w2_t"], prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
                          tag="dgrad:ffn2")
             dft, ht = ops.transpose_split(df, prec), ops.transpose_bf16(S["hs"], prec)
             if kind == "bayes_ffn":
@@ -264,7 +271,7 @@ class FineTuner:
                 ops.colsum(df, g[pre + "linear2.bias"])
             # FFN1
             dx1 = self._f32(M, d)
-            ops.gemm(dz1s, self._wt(S["w1_32"]), prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
+            ops.gemm(dz1s, S["w1_t"], prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
             dz1t, x1t = ops.transpose_split(dz1, prec), ops.transpose_bf16(S["x1s"], prec)
             if kind == "gauss":
                 self._gp_backward(layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, eps.get(f"layer{li}"), seed)
@@ -276,13 +283,13 @@ class FineTuner:
                                     g[pre + "norm1.bias"])
             dy1s = ops.split(dy1, prec)
             datt = self._f32(M, d)
-            ops.gemm(dy1s, self._wt(a.o_net.weight), prec=prec, out_f32=datt, tag="dgrad:o_net")
+            ops.gemm(dy1s, S["wo_t"], prec=prec, out_f32=datt, tag="dgrad:o_net")
             self._wgrad(ops.transpose_split(dy1, prec), ops.transpose_bf16(S["atts"], prec), g[pre + "self_attn.o_net.weight"],
                         "o_net")
             ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
             dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q)
             dx = self._f32(M, d)
-            ops.gemm(ops.split(dqkv, prec), self._wt(a.qkv_net.weight), prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
+            ops.gemm(ops.split(dqkv, prec), S["wqkv_t"], prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
             self._wgrad(ops.transpose_split(dqkv, prec), ops.transpose_bf16(S["xs"], prec), g[pre + "self_attn.qkv_net.weight"],
                         "qkv")
             ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])

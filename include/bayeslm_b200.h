@@ -299,14 +299,20 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
 /* out[c, r] = bf16 hi (+ lo) of x[r, c]: x fp32 [R, C] (ldx), out [C, R] (ldo, multiple of 8).  */
 int blm_transpose_split(const float* x, int64_t ldx, int64_t R, int64_t C, blm_bf16* out_hi,
                         blm_bf16* out_lo, int64_t ldo, blm_stream stream);
+/* both bf16 copies of an fp32 weight in one pass: hi/lo [R, C] (ld) and its transpose t_hi/t_lo
+ * [C, R] (ldt) -- the B operands of the forward product and of its dgrad.                       */
+int blm_split_transpose(const float* x, int64_t ldx, int64_t R, int64_t C, blm_bf16* hi, blm_bf16* lo,
+                        int64_t ld, blm_bf16* t_hi, blm_bf16* t_lo, int64_t ldt, blm_stream stream);
 /* same from a bf16 (hi[, lo]) source.                                                          */
 int blm_transpose_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t R, int64_t C,
                        blm_bf16* out_hi, blm_bf16* out_lo, int64_t ldo, blm_stream stream);
-/* out[n] (+)= scale * sum_m x[m, n]   (bias gradients).                                        */
+/* out[n] (+)= scale * sum_m x[m, n]   (bias gradients); fixed summation order.
+ * workspace: blm_colsum_workspace_bytes(M, N) bytes, zeroed once by the caller.                 */
+int64_t blm_colsum_workspace_bytes(int64_t M, int64_t N);
 int blm_colsum(const float* x, int64_t ldx, int64_t M, int64_t N, float scale, int32_t accumulate,
-               float* out, blm_stream stream);
+               float* out, void* workspace, blm_stream stream);
 int blm_colsum_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64_t M, int64_t N,
-                    float scale, int32_t accumulate, float* out, blm_stream stream);
+                    float scale, int32_t accumulate, float* out, void* workspace, blm_stream stream);
 
 /* LayerNorm backward (nn.LayerNorm, model.py:1030-1031): x is the LayerNorm INPUT.
  * dx = rstd (g dy - mean(g dy) - xhat mean(g dy xhat)); dgamma (+)= sum dy xhat; dbeta (+)= sum dy. */
