@@ -20,7 +20,9 @@ static int tgrid(long long items, int threads, int per_sm) {
 }
 
 // ------------------------------------------------------------------ transposes
-// out[c, r] = bf16 split of x[r, c]; 32 x 32 tiles through shared memory, both sides coalesced.
+// out[c, r] = bf16 split of x[r, c]; 64 x 64 tiles through shared memory.  Loads: 128 B per warp row
+// (fp32: two 4-byte columns per lane, bf16: one bf16x2 per lane); stores: one bf16x2 per lane = 128 B per
+// warp row.  dir_hi / dir_lo optionally receive the untransposed bf16 split of the same elements.
 template <typename Src>
 __global__ void __launch_bounds__(256) transpose_kernel(const Src* __restrict__ x_hi, const Src* __restrict__ x_lo,
                                                         long long ldx, long long R, long long C,
@@ -29,39 +31,84 @@ __global__ void __launch_bounds__(256) transpose_kernel(const Src* __restrict__ 
                                                         __nv_bfloat16* __restrict__ dir_hi = nullptr,
                                                         __nv_bfloat16* __restrict__ dir_lo = nullptr,
                                                         long long ldd = 0) {
-  __shared__ float tile[32][33];
-  const long long tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  __shared__ float tile[64][65];
+  const long long tiles_c = (C + 63) / 64, tiles_r = (R + 63) / 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (long long t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
-    const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    const long long r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long r = r0 + ty + 8 * k, c = c0 + tx;
-      float v = 0.0f;
-      if (r < R && c < C) {
-        if constexpr (sizeof(Src) == 4) {
-          v = reinterpret_cast<const float*>(x_hi)[r * ldx + c];
-        } else {
-          v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_hi)[r * ldx + c]);
-          if (x_lo) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_lo)[r * ldx + c]);
+    for (int k = 0; k < 8; ++k) {
+      const int rr = ty + 8 * k;
+      const long long r = r0 + rr;
+      float v0 = 0.0f, v1 = 0.0f;
+      int cc0, cc1;
+      if constexpr (sizeof(Src) == 4) {
+        cc0 = tx;
+        cc1 = tx + 32;
+        if (r < R) {
+          const float* p = reinterpret_cast<const float*>(x_hi) + r * ldx + c0;
+          if (c0 + cc0 < C) v0 = p[cc0];
+          if (c0 + cc1 < C) v1 = p[cc1];
+        }
+      } else {
+        cc0 = 2 * tx;
+        cc1 = 2 * tx + 1;
+        if (r < R) {
+          const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(x_hi) + r * ldx + c0 + cc0;
+          const __nv_bfloat16* pl = x_lo ? reinterpret_cast<const __nv_bfloat16*>(x_lo) + r * ldx + c0 + cc0 : nullptr;
+          if (c0 + cc1 < C && ((reinterpret_cast<uintptr_t>(p) & 3u) == 0)) {
+            const uint32_t q = *reinterpret_cast<const uint32_t*>(p);
+            v0 = __uint_as_float(q << 16);
+            v1 = __uint_as_float(q & 0xffff0000u);
+            if (pl) {
+              const uint32_t l = *reinterpret_cast<const uint32_t*>(pl);
+              v0 += __uint_as_float(l << 16);
+              v1 += __uint_as_float(l & 0xffff0000u);
+            }
+          } else {
+            if (c0 + cc0 < C) v0 = __bfloat162float(p[0]) + (pl ? __bfloat162float(pl[0]) : 0.0f);
+            if (c0 + cc1 < C) v1 = __bfloat162float(p[1]) + (pl ? __bfloat162float(pl[1]) : 0.0f);
+          }
         }
       }
-      tile[ty + 8 * k][tx] = v;
-      if (dir_hi && r < R && c < C) {  // the untransposed bf16 split of the same element, for free
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        dir_hi[r * ldd + c] = h;
-        if (dir_lo) dir_lo[r * ldd + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+      tile[rr][cc0] = v0;
+      tile[rr][cc1] = v1;
+      if (dir_hi && r < R) {  // the untransposed bf16 split of the same elements, for free
+        if (c0 + cc0 < C) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v0);
+          dir_hi[r * ldd + c0 + cc0] = h;
+          if (dir_lo) dir_lo[r * ldd + c0 + cc0] = __float2bfloat16_rn(v0 - __bfloat162float(h));
+        }
+        if (c0 + cc1 < C) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v1);
+          dir_hi[r * ldd + c0 + cc1] = h;
+          if (dir_lo) dir_lo[r * ldd + c0 + cc1] = __float2bfloat16_rn(v1 - __bfloat162float(h));
+        }
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long c = c0 + ty + 8 * k, r = r0 + tx;
+    for (int k = 0; k < 8; ++k) {
+      const int cc = ty + 8 * k;
+      const long long c = c0 + cc, r = r0 + 2 * tx;
       if (c < C && r < R) {
-        const float v = tile[tx][ty + 8 * k];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        out_hi[c * ldo + r] = h;
-        if (out_lo) out_lo[c * ldo + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const float a = tile[2 * tx][cc], bq = tile[2 * tx + 1][cc];
+        __nv_bfloat16* oh = out_hi + c * ldo + r;
+        __nv_bfloat16* ol = out_lo ? out_lo + c * ldo + r : nullptr;
+        if (r + 1 < R && ((reinterpret_cast<uintptr_t>(oh) & 3u) == 0)) {
+          const uint32_t h = pack_bf16x2(a, bq);
+          *reinterpret_cast<uint32_t*>(oh) = h;
+          if (ol) *reinterpret_cast<uint32_t*>(ol) = pack_bf16x2(a - __uint_as_float(h << 16), bq - __uint_as_float(h & 0xffff0000u));
+        } else {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(a);
+          oh[0] = h0;
+          if (ol) ol[0] = __float2bfloat16_rn(a - __bfloat162float(h0));
+          if (r + 1 < R) {
+            const __nv_bfloat16 h1 = __float2bfloat16_rn(bq);
+            oh[1] = h1;
+            if (ol) ol[1] = __float2bfloat16_rn(bq - __bfloat162float(h1));
+          }
+        }
       }
     }
     __syncthreads();
@@ -667,7 +714,7 @@ int blm_transpose_split(const float* x, int64_t ldx, int64_t R, int64_t C, blm_b
                         int64_t ldo, blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(x && out_hi && R > 0 && C > 0 && ldx >= C && ldo >= R, BLM_ERR_ARG, "bad transpose arguments");
-  transpose_kernel<float><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
+  transpose_kernel<float><<<tgrid(((R + 63) / 64) * ((C + 63) / 64), 1, 8), 256, 0, as_stream(stream)>>>(
       x, nullptr, ldx, R, C, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
@@ -678,7 +725,7 @@ int blm_split_transpose(const float* x, int64_t ldx, int64_t R, int64_t C, blm_b
   using namespace blm;
   BLM_REQUIRE(x && hi && t_hi && R > 0 && C > 0 && ldx >= C && ld >= C && ldt >= R, BLM_ERR_ARG,
               "bad split_transpose arguments");
-  transpose_kernel<float><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
+  transpose_kernel<float><<<tgrid(((R + 63) / 64) * ((C + 63) / 64), 1, 8), 256, 0, as_stream(stream)>>>(
       x, nullptr, ldx, R, C, reinterpret_cast<__nv_bfloat16*>(t_hi), reinterpret_cast<__nv_bfloat16*>(t_lo), ldt,
       reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ld);
   BLM_CHECK_CUDA(cudaGetLastError());
@@ -689,7 +736,7 @@ int blm_transpose_bf16(const blm_bf16* hi, const blm_bf16* lo, int64_t ld, int64
                        blm_bf16* out_lo, int64_t ldo, blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(hi && out_hi && R > 0 && C > 0 && ld >= C && ldo >= R, BLM_ERR_ARG, "bad transpose arguments");
-  transpose_kernel<__nv_bfloat16><<<tgrid(((R + 31) / 32) * ((C + 31) / 32), 1, 8), 256, 0, as_stream(stream)>>>(
+  transpose_kernel<__nv_bfloat16><<<tgrid(((R + 63) / 64) * ((C + 63) / 64), 1, 8), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), ld, R, C,
       reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
   BLM_CHECK_CUDA(cudaGetLastError());

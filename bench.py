@@ -137,6 +137,35 @@ def bench_finetune(dev, world, steps, warmup=3):
             "loss_first": losses[0], "loss_last": losses[-1], "dropout": 0.0}
 
 
+def bench_lstm(dev, steps=2):
+    """BASELINE configs 1 / 5 shape: Bayesian LSTM 2x1024 (emb 1024, L_bayes_pos=3), V=30000, 100-best lists in
+    sessions of 16 utterances (hidden carry through hypothesis #0, score.py:271-274).  End to end: host id lists ->
+    lock-step batches -> persistent recurrence kernel -> vocabulary NLL -> scores on the host."""
+    from bayeslms_b200 import model as M, synth
+    from bayeslms_b200.scorer import Rescorer
+    torch.manual_seed(1111)
+    net = M.BayesRNNModel("LSTM", V, 1024, 1024, 2, 0.5, True, 3).to(dev).eval()
+    n_sess, per_sess, nbest = 8, 16, 100
+    data = synth.make_nbest(n_sess * per_sess, nbest, V, seed=1112)
+    utts = data.tokenised()
+    sessions = [utts[s * per_sess:(s + 1) * per_sess] for s in range(n_sess)]
+    n_tok = data.n_tokens()
+    out = {}
+    for name, kw in (("mean", {}), ("sampled_k8", {"K": 8, "seed": 1111})):
+        rs = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS, **kw)
+        rs.score_sessions(sessions)                      # warm-up (plans, workspaces)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rs.score_sessions(sessions)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        out[name] = {"tokens_per_s": n_tok / dt, "ms": dt * 1e3}
+    out["workload"] = (f"Bayesian LSTM 2x1024 L_bayes_pos=3 V30000, {nbest}-best, {n_sess} sessions x {per_sess} utterances "
+                       f"({n_tok} tokens), end to end incl. host packing (wall clock)")
+    return out
+
+
 def cpu_port_tokens_per_s(data, n_utts, state_dict):
     """The reference algorithm on the host: one hypothesis at a time, batch 1, fp32 torch CPU."""
     from oracle import bayeslm_oracle as O
@@ -312,11 +341,12 @@ def main():
     wer_p, picks_p = synth.wer(data, per_utt(precise), lo=lo)
 
     finetune = bench_finetune(dev, world, max(10, args.steps))
+    lstm = bench_lstm(dev) if (rank == 0 and world == 1) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-        n_cpu = 8
+        n_cpu = 40                                      # ~30 k tokens: 8-15 s on the box's host cores
         v_cpu, t_cpu, dt_cpu, cores = cpu_port_tokens_per_s(data, n_cpu, sd)
         cpu = {"value": v_cpu, "unit": "tokens/s", "cores": cores, "kind": "port",
                "sample": f"first {n_cpu} utterances x {NBEST}-best of the same lists ({t_cpu} tokens, {dt_cpu:.1f} s), "
@@ -337,7 +367,10 @@ def main():
             "clocks": clk.summary(),
             "roofline": {"kernel": "gemm_kernel<256,4,EPI_NLL> (vocab projection + online LSE + target gather)",
                          "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tensor"] if pk["tensor"] else None, "traffic": None,
+                         "frac": achieved / pk["tensor"] if pk["tensor"] else None,
+                         # dram__bytes_read + write of one launch at M = 52950 rows, ncu --set full
+                         # (profiles/r01g_nll_ew8_ncu_summary.txt); algorithmic bytes at that M: 85.0 MB
+                         "traffic": 90875648, "traffic_unit": "bytes/launch at M=52950",
                          "peak_source": pk["src"] + " bf16_tflops_sustained", "launches": nll_n,
                          "avg_launch_ms": nll_ms / nll_n if nll_n else None,
                          "share_of_step": nll_ms / tot},
@@ -349,6 +382,7 @@ def main():
                         "one_best_agreement": float(np.mean(np.asarray(picks_f) == np.asarray(picks_p))),
                         "synthetic_wer": wer_p},
             "finetune_step": finetune,
+            "lstm_rescoring": lstm,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

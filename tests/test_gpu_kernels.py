@@ -185,3 +185,20 @@ def test_precise_gemm_truncation_bias_is_bounded(ops):
     bias_single = ((out.double() - ref) / ref).mean().item()
     assert abs(bias_chunked) < 5e-7, (bias_chunked, bias_single)
     assert abs(bias_single) > 4 * abs(bias_chunked), (bias_chunked, bias_single)
+
+
+@pytest.mark.parametrize("R,C", [(3200, 512), (100, 30000), (77, 130), (1, 8), (64, 64), (65, 63)])
+def test_transposes_and_colsum(ops, R, C):
+    x = torch.randn(R, C, device=DEV)
+    t = ops.transpose_split(x, "bf16x3")
+    _close(t.float(), x.t(), 2e-5)
+    s, st = ops.split_transpose(x, "bf16x3")
+    _close(s.float(), x, 2e-5)
+    _close(st.float(), x.t(), 2e-5)
+    t2 = ops.transpose_bf16(s, "bf16x3")
+    _close(t2.float(), x.t(), 2e-5)
+    out = torch.zeros(C, device=DEV)
+    ops.colsum(x, out, scale=0.5)
+    _close(out, 0.5 * x.double().sum(0), 1e-5)
+    ops.colsum(s, out, accumulate=True)
+    _close(out, 1.5 * x.double().sum(0), 3e-5)
