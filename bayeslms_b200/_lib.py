@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbayeslm_b200.so")
 BLM_OK = 0
 ERR_NAMES = {-1: "BLM_ERR_SHAPE", -2: "BLM_ERR_ALIGN", -3: "BLM_ERR_ARCH", -4: "BLM_ERR_CUDA", -5: "BLM_ERR_ARG"}
 
-ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD, ACT_GELU_GRAD, ACT_GPMIX_GRAD = 0, 1, 2, 3, 4, 5
+ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD, ACT_GELU_GRAD, ACT_GPMIX_GRAD, ACT_GELU_FAST = 0, 1, 2, 3, 4, 5, 6
 EPS_NONE, EPS_PTR, EPS_PHILOX = 0, 1, 2
 MAX_SEG = 6
 
@@ -86,6 +86,7 @@ SIGNATURES = {
     "blm_mha_causal_bf16": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "blm_kl_workspace_bytes": (_i64, []),
     "blm_kl_gauss": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _f, _i32, _p, _p, _p]),
+    "blm_gp_lstm_cell": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "blm_transpose_split": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "blm_split_transpose": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _p]),
     "blm_transpose_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _p]),

@@ -243,6 +243,52 @@ __global__ void mc_combine_kernel(const float* __restrict__ nll, long long K, lo
   }
 }
 
+// GP-LSTM cell update (GPLSTMCell.Gplstm, model.py:1743-1777, gpnn_type <= 3, gate_type 1..4):
+// acc5 [B, 5H] holds the four pre-activations i, f, g, o (W_ih x + b_ih + W_hh h + b_ih -- bias_ih twice, the
+// reference's quirk) and, in the fifth block, the GP unit's pre-activation z = W_g [x; h] + b_g.  The gate
+// `gate_type` is REPLACED by gp = sum_i coef[i, u] act_i(z), acts = (sigmoid, tanh, relu)[:n_act]
+// (model.py:1692-1697); the others keep sigmoid / tanh.  Rows past their length keep (h, c).
+__global__ void gp_lstm_cell_kernel(const float* __restrict__ acc5, long long ld, const float* __restrict__ coef,
+                                    int n_act, int gate_type, const int* __restrict__ lengths, int t, long long B,
+                                    int H, float* __restrict__ c, float* __restrict__ h,
+                                    __nv_bfloat16* __restrict__ h_hi, __nv_bfloat16* __restrict__ h_lo,
+                                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                                    __nv_bfloat16* __restrict__ out_lo) {
+  const long long n = B * H;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long b = i / H;
+    const int u = static_cast<int>(i - b * H);
+    const bool live = t < __ldg(lengths + b);
+    float hv = h[i];
+    if (live) {
+      const float* a = acc5 + b * ld + u;
+      const float z = a[4ll * H];
+      float gp = __ldg(coef + u) * (1.0f / (1.0f + expf(-z)));
+      if (n_act > 1) gp += __ldg(coef + H + u) * tanhf(z);
+      if (n_act > 2) gp += __ldg(coef + 2 * H + u) * fmaxf(z, 0.0f);
+      const float ig = gate_type == 1 ? gp : 1.0f / (1.0f + expf(-a[0]));
+      const float fg = gate_type == 2 ? gp : 1.0f / (1.0f + expf(-a[H]));
+      const float gg = gate_type == 3 ? gp : tanhf(a[2ll * H]);
+      const float og = gate_type == 4 ? gp : 1.0f / (1.0f + expf(-a[3ll * H]));
+      const float cv = fg * c[i] + ig * gg;
+      hv = og * tanhf(cv);
+      c[i] = cv;
+      h[i] = hv;
+    }
+    const __nv_bfloat16 hh = __float2bfloat16_rn(hv);
+    h_hi[i] = hh;
+    if (h_lo) h_lo[i] = __float2bfloat16_rn(hv - __bfloat162float(hh));
+    const float ov = live ? hv : 0.0f;
+    if (out_f32) out_f32[i] = ov;
+    if (out_hi) {
+      const __nv_bfloat16 oh = __float2bfloat16_rn(ov);
+      out_hi[i] = oh;
+      if (out_lo) out_lo[i] = __float2bfloat16_rn(ov - __bfloat162float(oh));
+    }
+  }
+}
+
 static int grid_for(long long work_items, int threads, int per_sm) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms() > 0 ? num_sms() : 148) * per_sm;
@@ -373,6 +419,22 @@ int blm_kl_gauss(const float* mu, int64_t ldmu, const float* lgstd, int64_t rows
   if (grid > 1024) grid = 1024;
   kl_kernel<<<grid, 256, 0, as_stream(stream)>>>(mu, ldmu, lgstd, rows, cols, minus_one, scale, accumulate,
                                                 out, reinterpret_cast<KlWorkspace*>(workspace));
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_gp_lstm_cell(const float* acc5, int64_t ld, const float* coef, int32_t n_act, int32_t gate_type,
+                     const int32_t* lengths, int32_t t, int64_t B, int32_t H, float* c, float* h, blm_bf16* h_hi,
+                     blm_bf16* h_lo, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(acc5 && coef && lengths && c && h && h_hi && B > 0 && H > 0 && ld >= 5ll * H, BLM_ERR_ARG,
+              "bad gp_lstm_cell arguments");
+  BLM_REQUIRE(n_act >= 1 && n_act <= 3 && gate_type >= 1 && gate_type <= 4, BLM_ERR_ARG,
+              "gp_lstm_cell: n_act=%d gate_type=%d out of range", n_act, gate_type);
+  gp_lstm_cell_kernel<<<grid_for(B * H, 256, 8), 256, 0, as_stream(stream)>>>(
+      acc5, ld, coef, n_act, gate_type, lengths, t, B, H, c, h, reinterpret_cast<__nv_bfloat16*>(h_hi),
+      reinterpret_cast<__nv_bfloat16*>(h_lo), out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      reinterpret_cast<__nv_bfloat16*>(out_lo));
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

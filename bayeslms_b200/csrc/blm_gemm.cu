@@ -519,6 +519,8 @@ int gemm_init() {
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<128, kStages128, EPI_STORE, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr<256, kStages256, EPI_STORE, BLM_ACT_GPMIX_GRAD>()) != BLM_OK) return rc;
@@ -581,8 +583,10 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
               BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
   BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld",
               (long long)d->ldr);
-  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_GPMIX_GRAD, BLM_ERR_ARG, "unknown activation %d",
+  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_GELU_FAST, BLM_ERR_ARG, "unknown activation %d",
               d->act);
+  BLM_REQUIRE(d->act != BLM_ACT_GELU_FAST || (d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && d->k_chunk == 0),
+              BLM_ERR_ARG, "BLM_ACT_GELU_FAST is for bf16-hi-only outputs of the fast mode");
   const bool grad_act = d->act == BLM_ACT_GELU_GRAD || d->act == BLM_ACT_GPMIX_GRAD;
   BLM_REQUIRE(!grad_act || (d->aux && (d->ldaux % 4) == 0 && d->ldaux >= d->N && aligned16(d->aux)), BLM_ERR_ARG,
               "the activation-gradient epilogues need aux (16-byte aligned, ldaux %% 4 == 0)");
@@ -670,6 +674,7 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
     switch (d->act) {
       case BLM_ACT_NONE: return launch<256, kStages256, EPI_STORE, BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU>(p, st);
+      case BLM_ACT_GELU_FAST: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU_FAST>(p, st);
       case BLM_ACT_GPMIX: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX>(p, st);
       case BLM_ACT_GELU_GRAD: return launch<256, kStages256, EPI_STORE, BLM_ACT_GELU_GRAD>(p, st);
       case BLM_ACT_GPMIX_GRAD: return launch<256, kStages256, EPI_STORE, BLM_ACT_GPMIX_GRAD>(p, st);
@@ -679,6 +684,7 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   switch (d->act) {
     case BLM_ACT_NONE: return launch<128, kStages128, EPI_STORE, BLM_ACT_NONE>(p, st);
     case BLM_ACT_GELU: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU>(p, st);
+    case BLM_ACT_GELU_FAST: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU_FAST>(p, st);
     case BLM_ACT_GPMIX: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX>(p, st);
     case BLM_ACT_GELU_GRAD: return launch<128, kStages128, EPI_STORE, BLM_ACT_GELU_GRAD>(p, st);
     case BLM_ACT_GPMIX_GRAD: return launch<128, kStages128, EPI_STORE, BLM_ACT_GPMIX_GRAD>(p, st);

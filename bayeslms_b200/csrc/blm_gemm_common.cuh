@@ -1,6 +1,8 @@
 // Pieces shared by the tcgen05 GEMM kernels: tile constants, kernel parameters, the fused
 // epilogue math (bias / q-scale / GELU / GP mixture / residual / hi-lo split) and its helpers.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "blm_host.h"
 #include "blm_ptx.cuh"
 
@@ -103,6 +105,27 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(fabsf(x) * -0.5f, e, fmaxf(x, 0.0f));
 }
 
+// The same formula on two elements at a time in packed fp16 (HFMA2 / HMNMX2 / ex2.approx.f16x2): ~8 issue
+// slots per element instead of ~15.  fp16's 11-bit mantissa costs <= 5e-4 relative on the result -- below the
+// bf16 rounding (4e-3) of the only output this variant is used for (BLM_ACT_GELU_FAST: bf16-hi output of the
+// fast mode), where the fp32 GELU made the FFN1 epilogue, not the tensor pipe, the bound.
+__device__ __forceinline__ void gelu_fast_h2(float& a, float& b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 ax = __habs2(x);
+  const __half2 t = __hmin2(__hmul2(ax, __float2half2_rn(0.70710678118654752440f)), __float2half2_rn(4.0f));
+  __half2 q = __hfma2(t, __float2half2_rn(-1.002195230e-04f), __float2half2_rn(4.615629764e-04f));
+  q = __hfma2(q, t, __float2half2_rn(2.302262028e-03f));
+  q = __hfma2(q, t, __float2half2_rn(-2.945254180e-02f));
+  q = __hfma2(q, t, __float2half2_rn(1.489636837e-01f));
+  q = __hfma2(q, t, __float2half2_rn(9.183286407e-01f));
+  q = __hfma2(q, t, __float2half2_rn(1.627913732e+00f));
+  const __half2 e = h2exp2(__hneg2(__hmul2(q, t)));  // erfc(t)
+  const __half2 r = __hfma2(__hmul2(ax, __float2half2_rn(-0.5f)), e, __hmax2(x, __float2half2_rn(0.0f)));
+  const float2 f = __half22float2(r);
+  a = f.x;
+  b = f.y;
+}
+
 // d/dz of the exact-erf GELU: Phi(z) + z phi(z), with erfc from the same fit as gelu_fast
 __device__ __forceinline__ float gelu_grad(float z) {
   const float t = fminf(fabsf(z) * 0.70710678118654752440f, 4.0f);
@@ -127,8 +150,8 @@ __device__ __forceinline__ float gpmix_grad(float z, const float* __restrict__ c
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float z, const float* __restrict__ coef, int N, int n) {
-  if constexpr (ACT == BLM_ACT_GELU) {
-    return gelu_fast(z);
+  if constexpr (ACT == BLM_ACT_GELU || ACT == BLM_ACT_GELU_FAST) {
+    return gelu_fast(z);   // (the packed-fp16 variant is applied pairwise in store_chunk; this is its ragged-edge path)
   } else if constexpr (ACT == BLM_ACT_GPMIX) {
     const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n),
                 c3 = __ldg(coef + 3 * N + n);
@@ -206,6 +229,9 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
             v[j + q] *= (ACT == BLM_ACT_GELU_GRAD) ? gelu_grad(zz[q]) : gpmix_grad(zz[q], p.coef, p.N, col0 + j + q);
         }
       }
+    } else if constexpr (ACT == BLM_ACT_GELU_FAST) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) gelu_fast_h2(v[j], v[j + 1]);
     } else if constexpr (ACT != BLM_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);

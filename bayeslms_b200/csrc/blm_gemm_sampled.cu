@@ -18,6 +18,7 @@
 // Noise indexing matches blm_reparam: element (n, k) of the [N, K] tensor uses Philox counter
 // (n*K + k) / 4, lane (n*K + k) % 4 of stream `stream_id`: every rank, batch shape and code path draws
 // the same eps for the same (seed, stream).
+#include <stdlib.h>
 #include <string.h>
 
 #include "blm_gemm_common.cuh"
@@ -239,10 +240,9 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
             const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, sw4[4] = {s.x, s.y, s.z, s.w};
             float e[8];
             if (p.eps_mode == BLM_EPS_PHILOX) {
-              const float4 z0 = philox_normal4(p.seed, p.stream_id, static_cast<uint64_t>(dense0 / 4 + 2 * q));
-              const float4 z1 = philox_normal4(p.seed, p.stream_id, static_cast<uint64_t>(dense0 / 4 + 2 * q + 1));
-              e[0] = z0.x; e[1] = z0.y; e[2] = z0.z; e[3] = z0.w;
-              e[4] = z1.x; e[5] = z1.y; e[6] = z1.z; e[7] = z1.w;
+              const Normal8 z = philox_normal8(p.seed, p.stream_id, static_cast<uint64_t>(dense0 / 8 + q));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) e[j] = z.v[j];
             } else {
               const bool ok = n < p.g.N && kb * kBK + half * 32 + 8 * q + 8 <= p.K;
 #pragma unroll
@@ -277,6 +277,272 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
   }
 }
 
+// ---- cluster variant: the generated tile is shared by four CTAs -------------------------------
+// A generated element costs ~22 issue slots (Philox4x32-10 + 16-bit Box-Muller); with every CTA
+// generating its own [128 x 64] tile per K block the generator warps need ~4x the time the tensor
+// pipe spends on the four 128 x 128 x 64 products that consume it.  Here a cluster of kCL = 4 CTAs
+// works on the SAME N tile and four different M groups: CTA r TMA-loads only rows [32 r, 32 r + 32)
+// of the mu / sigma tiles, its generator warps build that quarter of W~, and one thread pushes the
+// 4 KB quarter into the W ring of all four CTAs with cp.async.bulk (shared::cta -> shared::cluster),
+// completion counted on each destination's w_ready mbarrier (4 x 4 KB = one tile).  A ring slot is
+// released cluster-wide: every MMA warp commits with .multicast::cluster onto the w_empty barrier
+// (count 4) of all four CTAs, which gates both the next quarter load and the next push.
+constexpr int kCL = 4;
+constexpr int kCWStages = 5;  // W~ ring and scratch ring depth: TMA -> generate -> DSMEM push is ~3 us deep
+constexpr int kCQRows = kSBN / kCL;       // 32 rows of W~ per CTA
+constexpr int kCQBytes = kCQRows * 128;   // 4 KB
+
+struct ClusterSmem {
+  static constexpr int kAOff = 0;
+  static constexpr int kWOff = kSAStages * kSTile;
+  static constexpr int kGOff = kWOff + kCWStages * kSTile;           // scratch: mu quarter | sigma quarter
+  static constexpr int kBarOff = kGOff + kCWStages * 2 * kCQBytes;
+  // a_full[6] a_empty[6] g_full[3] w_ready[3] w_empty[3] t_full t_empty + tmem slot
+  static constexpr int kBytes = kBarOff + (2 * kSAStages + 3 * kCWStages + 2) * 8 + 16;
+  static constexpr int kDynBytes = kBytes + 1024;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_cluster_kernel(const __grid_constant__ SampledParams p) {
+  using L = ClusterSmem;
+  extern __shared__ uint8_t smem_raw[];
+  // every CTA of the cluster must use the same offsets: the dynamic window starts at the same (1024-aligned
+  // after rounding) address in all of them
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* a_empty = a_full + kSAStages;
+  uint64_t* g_full = a_empty + kSAStages;    // TMA landed this CTA's mu | sigma quarter
+  uint64_t* w_ready = g_full + kCWStages;    // all four W~ quarters landed in this CTA's ring slot
+  uint64_t* w_empty = w_ready + kCWStages;   // all four CTAs' MMAs retired their reads of the slot
+  uint64_t* t_full = w_empty + kCWStages;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / kCL, n_clusters = gridDim.x / kCL;
+  const int m_quads = (p.m_groups + kCL - 1) / kCL;
+  const int num_works = p.g.n_tiles * m_quads;
+  const bool sampling = p.eps_mode != BLM_EPS_NONE;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.g.tmA[0]);
+    tma_prefetch_desc(&p.tmMu);
+    tma_prefetch_desc(&p.tmSig);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kCWStages; ++s) {
+      mbar_init(&g_full[s], 1);
+      mbar_init(&w_ready[s], 1);
+      mbar_init(&w_empty[s], kCL);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers exist before anyone arrives on / copies into a peer
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA: own A tiles (never gated by the W~ ring)
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int w = cluster_id; w < num_works; w += n_clusters) {
+        const int m_group = (w / p.g.n_tiles) * kCL + static_cast<int>(rank);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          for (int mt = 0; mt < kSMT; ++mt) {
+            mbar_wait(&a_empty[sa], pa ^ 1u);
+            mbar_arrive_expect_tx(&a_full[sa], kSTile);
+            tma_load_2d(smem + L::kAOff + sa * kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK, (m_group * kSMT + mt) * kBM,
+                        kEvictNormal);
+            if (++sa == kSAStages) {
+              sa = 0;
+              pa ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------------------------ TMA: this CTA's mu | sigma quarter
+    if (lane == 0) {
+      int sw = 0;
+      uint32_t pw = 0;
+      for (int w = cluster_id; w < num_works; w += n_clusters) {
+        const int n_tile = w % p.g.n_tiles;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&w_empty[sw], pw ^ 1u);  // slot sw (and the scratch that fed it) is free cluster-wide
+          uint8_t* g = smem + L::kGOff + sw * 2 * kCQBytes;
+          mbar_arrive_expect_tx(&g_full[sw], sampling ? 2 * kCQBytes : kCQBytes);
+          tma_load_2d(g, &p.tmMu, &g_full[sw], kb * kBK, n_tile * kSBN + static_cast<int>(rank) * kCQRows, kEvictLast);
+          if (sampling)
+            tma_load_2d(g + kCQBytes, &p.tmSig, &g_full[sw], kb * kBK, n_tile * kSBN + static_cast<int>(rank) * kCQRows,
+                        kEvictLast);
+          if (++sw == kCWStages) {
+            sw = 0;
+            pw ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kSBN);
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0, pt = 0;
+      for (int w = cluster_id; w < num_works; w += n_clusters) {
+        mbar_wait(t_empty, pt ^ 1u);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&w_ready[sw], pw);
+          tcgen05_fence_after();
+          const uint64_t db = umma_desc_sw128(smem_u32(smem + L::kWOff + sw * kSTile));
+          for (int mt = 0; mt < kSMT; ++mt) {
+            mbar_wait(&a_full[sa], pa);
+            tcgen05_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + L::kAOff + sa * kSTile));
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kSBN);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&a_empty[sa]);
+            if (++sa == kSAStages) {
+              sa = 0;
+              pa ^= 1u;
+            }
+          }
+          umma_commit_multicast(&w_empty[sw], static_cast<uint16_t>((1u << kCL) - 1u));
+          if (++sw == kCWStages) {
+            sw = 0;
+            pw ^= 1u;
+          }
+        }
+        umma_commit(t_full);
+        pt ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------ epilogue (as in the single-CTA kernel)
+    const int lane_grp = warp & 3;
+    uint32_t pt = 0;
+    for (int w = cluster_id; w < num_works; w += n_clusters) {
+      const int m_group = (w / p.g.n_tiles) * kCL + static_cast<int>(rank);
+      const int n_tile = w % p.g.n_tiles;
+      mbar_wait(t_full, pt);
+      pt ^= 1u;
+      tcgen05_fence_after();
+      constexpr int kChunks = kSMT * kSBN / 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+      float va[32], vb[32];
+      __syncwarp();
+      tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; c += 2) {
+        tmem_ld_wait();
+        __syncwarp();
+        tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 1) * 32), vb);
+        {
+          const int mt = c / (kSBN / 32), cc = c % (kSBN / 32);
+          const int m = (m_group * kSMT + mt) * kBM + lane_grp * 32 + lane;
+          const int col0 = n_tile * kSBN + cc * 32;
+          if ((m - lane) < p.g.M && col0 < p.g.N) store_chunk<ACT, 0>(p.g, va, m, m < p.g.M, lane, col0);
+        }
+        tmem_ld_wait();
+        __syncwarp();
+        if (c + 2 < kChunks) {
+          tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * 32), va);
+        } else {
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(t_empty);
+        }
+        {
+          const int mt = (c + 1) / (kSBN / 32), cc = (c + 1) % (kSBN / 32);
+          const int m = (m_group * kSMT + mt) * kBM + lane_grp * 32 + lane;
+          const int col0 = n_tile * kSBN + cc * 32;
+          if ((m - lane) < p.g.M && col0 < p.g.N) store_chunk<ACT, 0>(p.g, vb, m, m < p.g.M, lane, col0);
+        }
+      }
+    }
+  } else if (warp >= kSGenWarp0) {
+    // ------------------------------------------------ W~ generators: this CTA's quarter, then the push
+    const int gt = threadIdx.x - kSGenWarp0 * 32;  // 0..255: row gt / 8 of the quarter, 16-byte chunk gt % 8
+    const int row = gt >> 3, chunk = gt & 7;
+    const uint32_t pos = static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+    int sw = 0;
+    uint32_t pw = 0;
+    for (int w = cluster_id; w < num_works; w += n_clusters) {
+      const int n_tile = w % p.g.n_tiles;
+      const int n = n_tile * kSBN + static_cast<int>(rank) * kCQRows + row;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&g_full[sw], pw);
+        uint8_t* g = smem + L::kGOff + sw * 2 * kCQBytes;
+        if (sampling) {
+          const uint4 mq = *reinterpret_cast<const uint4*>(g + pos);
+          const uint4 sq = *reinterpret_cast<const uint4*>(g + kCQBytes + pos);
+          const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w}, sg[4] = {sq.x, sq.y, sq.z, sq.w};
+          const int k0 = kb * kBK + chunk * 8;
+          const long long dense = static_cast<long long>(n) * p.K + k0;
+          float e[8];
+          if (p.eps_mode == BLM_EPS_PHILOX) {
+            const Normal8 z = philox_normal8(p.seed, p.stream_id, static_cast<uint64_t>(dense >> 3));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = z.v[j];
+          } else {
+            const bool ok = n < p.g.N && k0 + 8 <= p.K;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = ok ? __ldg(p.eps + dense + j) : 0.0f;
+          }
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float w0 = fmaf(bf16lo_to_f32(sg[j]), e[2 * j], bf16lo_to_f32(mw[j]));
+            const float w1 = fmaf(bf16hi_to_f32(sg[j]), e[2 * j + 1], bf16hi_to_f32(mw[j]));
+            o[j] = pack_bf16x2(w0, w1);
+          }
+          *reinterpret_cast<uint4*>(g + pos) = make_uint4(o[0], o[1], o[2], o[3]);
+          fence_proxy_async_smem();  // generic stores -> visible to the bulk copy (async proxy)
+        }
+        asm volatile("bar.sync 2, %0;" ::"r"(kSGenThreads) : "memory");
+        if (gt == 0) {
+          mbar_arrive_expect_tx(&w_ready[sw], kSTile);  // this CTA's slot: four quarters of 4 KB
+          const uint32_t src = smem_u32(g);
+          const uint32_t dst = smem_u32(smem + L::kWOff + sw * kSTile) + rank * kCQBytes;
+          const uint32_t bar = smem_u32(&w_ready[sw]);
+#pragma unroll
+          for (uint32_t q = 0; q < kCL; ++q) bulk_copy_s2s(mapa_shared(dst, q), src, kCQBytes, mapa_shared(bar, q));
+        }
+        if (++sw == kCWStages) {
+          sw = 0;
+          pw ^= 1u;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no peer may still push into, or arrive on, a CTA that has exited
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 int gemm_sampled_init() {
   BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_kernel<BLM_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SampledSmem::kDynBytes));
@@ -284,6 +550,12 @@ int gemm_sampled_init() {
                                       SampledSmem::kDynBytes));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_kernel<BLM_ACT_GPMIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SampledSmem::kDynBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_cluster_kernel<BLM_ACT_NONE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ClusterSmem::kDynBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_cluster_kernel<BLM_ACT_GELU>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ClusterSmem::kDynBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_sampled_cluster_kernel<BLM_ACT_GPMIX>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ClusterSmem::kDynBytes));
   return BLM_OK;
 }
 
@@ -342,9 +614,46 @@ extern "C" int blm_gemm_sampled(const blm_gemm_sampled_desc* d, blm_stream strea
   p.K = static_cast<int>(d->K);
   p.kblocks = static_cast<int>((d->K + kBK - 1) / kBK);
   p.m_groups = (p.g.m_tiles + kSMT - 1) / kSMT;
+  cudaStream_t st = as_stream(stream);
+  // Cluster variant (BLM_SAMPLED_CLUSTER=1; exercised by the tests through the same entry point when the
+  // switch is set): correct and bit-identical, but MEASURED SLOWER than every CTA generating its own tile
+  // (591 vs 541 us at 65536 x 512 x 4096, profiles/r01s): with the 16-bit Box-Muller the generation is no
+  // longer the bound -- the W-stationary loop itself is (mean mode, no generation at all: 372 us) -- and
+  // the per-K-block cluster handshake costs more than the 3/4 of the generation it saves.
+  static const bool use_cluster = getenv("BLM_SAMPLED_CLUSTER") != nullptr;
+  if (use_cluster && d->eps_mode != BLM_EPS_NONE && p.m_groups >= kCL) {
+    CUtensorMap tq;
+    rc = encode_tmap_bf16(&tq, d->mu, d->N, d->K, d->ldmu, kCQRows);
+    if (rc != BLM_OK) return rc;
+    p.tmMu = tq;
+    rc = encode_tmap_bf16(&tq, d->sigma, d->N, d->K, d->K, kCQRows);
+    if (rc != BLM_OK) return rc;
+    p.tmSig = tq;
+    const int cworks = p.g.n_tiles * ((p.m_groups + kCL - 1) / kCL);
+    int n_clusters = num_sms() / kCL;
+    if (n_clusters > cworks) n_clusters = cworks;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * kCL));
+    cfg.blockDim = dim3(kSThreads);
+    cfg.dynamicSmemBytes = ClusterSmem::kDynBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    switch (d->act) {
+      case BLM_ACT_NONE: BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_sampled_cluster_kernel<BLM_ACT_NONE>, p)); break;
+      case BLM_ACT_GELU: BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_sampled_cluster_kernel<BLM_ACT_GELU>, p)); break;
+      default: BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_sampled_cluster_kernel<BLM_ACT_GPMIX>, p));
+    }
+    return BLM_OK;
+  }
   const int works = p.g.n_tiles * p.m_groups;
   const int grid = works < num_sms() ? works : num_sms();
-  cudaStream_t st = as_stream(stream);
   switch (d->act) {
     case BLM_ACT_NONE:
       gemm_sampled_kernel<BLM_ACT_NONE><<<grid, kSThreads, SampledSmem::kDynBytes, st>>>(p);

@@ -27,13 +27,14 @@
 namespace blm {
 
 constexpr int kLStages = 5;      // h-tile ring depth
-constexpr int kLThreads = 256;
+constexpr int kLThreads = 384;   // 4 control warps + 8 epilogue warps (two per scheduler, alternate tiles)
 constexpr int kLMaxTiles = 16;   // per CTA: 16 x 32 (U = 8) or 8 x 64 (U = 16) TMEM columns = 512
 constexpr int kLABytes = 128 * 64 * 2;
 
 struct LstmParams {
-  CUtensorMap tmH[2][2];  // [buffer][hi, lo] : h state [B, H] bf16, box 128 x 64
+  CUtensorMap tmH[2][2];  // [buffer][hi, lo] : h state [B, H] bf16, box 128 x 64 (box 32 x 64 in the cluster kernel)
   CUtensorMap tmW[2];     // [hi, lo]         : W_hh [4H, H] bf16, box U x 64
+  int kb_stagger;         // 1: stagger the K-block order per CTA (A/B switch BLM_LSTM_NO_STAGGER)
   int unit_blocks;        // H / U
   int tiles_per_cta;      // 128-row batch tiles per CTA (batch split)
   const float* gates_x;   // [T, B, 4H]
@@ -77,6 +78,22 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
   __syncthreads();
 }
 
+// sigmoid / tanh on the MUFU pipe: ex2.approx (2 ulp) + rcp.approx (1 ulp); |x| is clamped where both have
+// saturated in fp32.  The libdevice expf / tanhf / IEEE division of the first version cost ~150 issue slots per
+// hidden unit and made the single-warp-per-scheduler epilogue, not the recurrent product, the step's bound.
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(fmaxf(x, -30.0f), 30.0f) * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(fmaxf(x, -15.0f), 15.0f) * -2.8853900817779268f));  // exp(-2x)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return (1.0f - e) * r;
+}
+
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ void store_h8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&h)[8]) {
@@ -91,7 +108,11 @@ __device__ __forceinline__ void store_h8(__nv_bfloat16* hi, __nv_bfloat16* lo, c
   if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
-template <int kU>
+// kCL > 1: kCL CTAs with the same batch block (consecutive unit blocks) form a cluster; every h tile is
+// fetched ONCE per cluster -- CTA r loads rows [32 r, 32 r + 32) of the 128-row tile with TMA multicast
+// into all kCL CTAs -- and a ring slot is released by multicast tcgen05.commit from all kCL MMA warps.
+// The L2 -> SM traffic of the step (every CTA needs all of h_{t-1} of its batch block) drops kCL-fold.
+template <int kU, int kCL>
 __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_constant__ LstmParams p) {
   constexpr int kLN = 4 * kU;            // MMA N: 4 gates x U units
   constexpr int kLWTile = kLN * 64 * 2;  // one K block of the W slice
@@ -118,7 +139,7 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kLStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kCL);
     }
     for (int s = 0; s < kLMaxTiles; ++s) mbar_init(&tfull_bar[s], 1);
     mbar_init(w_bar, 1);
@@ -127,8 +148,10 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (kCL > 1) cluster_sync_all();  // peers' barriers exist before any multicast lands
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = kCL > 1 ? cluster_ctarank() : 0u;
 
   // resident W slice: rows {g*H + 8j + u}, one 8-row TMA box per (gate, K block) = one swizzle atom
   if (warp == 0 && lane == 0) {
@@ -161,6 +184,9 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   grid_barrier(p.barrier, (++bar_n) * gridDim.x);
   mbar_wait(w_bar, 0);
 
+  // every CTA (cluster) walks the K blocks of a tile from a different starting block: in lock step all
+  // CTAs of a batch block would otherwise request the same 16 KB of h from the same L2 slices at once
+  const int kb_rot = p.kb_stagger ? ((j / kCL) % p.kblocks) : 0;
   int stage = 0;
   uint32_t phase = 0;  // ring position, advanced identically by producer and MMA threads
   const int a_parts = p.nsplit == 3 ? 2 : 1;
@@ -172,11 +198,19 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
         fence_proxy_async_all();  // h_{t-1} was written with generic stores by other SMs
         for (int mt = 0; mt < n_mt; ++mt)
           for (int part = 0; part < a_parts; ++part)
-            for (int kb = 0; kb < p.kblocks; ++kb) {
+            for (int kbi = 0; kbi < p.kblocks; ++kbi) {
+              const int kb = (kbi + kb_rot) % p.kblocks;  // staggered K order: CTAs do not hit the same lines at once
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&full_bar[stage], kLABytes);
-              tma_load_2d(sA + stage * kLABytes, &p.tmH[cur][part], &full_bar[stage], kb * 64, (mt0 + mt) * 128,
-                          kEvictNormal);
+              if constexpr (kCL > 1) {
+                constexpr int kQ = 128 / kCL;  // rows of the tile this CTA fetches for the whole cluster
+                tma_load_2d_multicast(sA + stage * kLABytes + crank * (kQ * 128), &p.tmH[cur][part], &full_bar[stage],
+                                      kb * 64, (mt0 + mt) * 128 + static_cast<int>(crank) * kQ,
+                                      static_cast<uint16_t>((1u << kCL) - 1u), kEvictNormal);
+              } else {
+                tma_load_2d(sA + stage * kLABytes, &p.tmH[cur][part], &full_bar[stage], kb * 64, (mt0 + mt) * 128,
+                            kEvictNormal);
+              }
               if (++stage == kLStages) {
                 stage = 0;
                 phase ^= 1u;
@@ -192,7 +226,8 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kLN);
           uint32_t accum = 0;
           for (int part = 0; part < a_parts; ++part)
-            for (int kb = 0; kb < p.kblocks; ++kb) {
+            for (int kbi = 0; kbi < p.kblocks; ++kbi) {
+              const int kb = (kbi + kb_rot) % p.kblocks;
               mbar_wait(&full_bar[stage], phase);
               tcgen05_fence_after();
               const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kLABytes));
@@ -208,7 +243,10 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
                 for (int k = 0; k < 4; ++k)
                   umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
               }
-              umma_commit(&empty_bar[stage]);
+              if constexpr (kCL > 1)
+                umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << kCL) - 1u));
+              else
+                umma_commit(&empty_bar[stage]);
               if (++stage == kLStages) {
                 stage = 0;
                 phase ^= 1u;
@@ -220,7 +258,7 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
       __syncwarp();
     } else if (warp >= 4) {
       const int lane_grp = warp & 3;
-      for (int mt = 0; mt < n_mt; ++mt) {
+      for (int mt = (warp - 4) >> 2; mt < n_mt; mt += 2) {
         mbar_wait(&tfull_bar[mt], static_cast<uint32_t>(t & 1));
         tcgen05_fence_after();
         float v[kLN];
@@ -255,12 +293,12 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
               *reinterpret_cast<float4*>(c + 4) = *reinterpret_cast<const float4*>(p.cT + o + 4);
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const float ig = 1.0f / (1.0f + expf(-a[0][u]));
-                const float fg = 1.0f / (1.0f + expf(-a[1][u]));
-                const float gg = tanhf(a[2][u]);
-                const float og = 1.0f / (1.0f + expf(-a[3][u]));
-                c[u] = fg * c[u] + ig * gg;
-                h[u] = og * tanhf(c[u]);
+                const float ig = fast_sigmoid(a[0][u]);
+                const float fg = fast_sigmoid(a[1][u]);
+                const float gg = fast_tanh(a[2][u]);
+                const float og = fast_sigmoid(a[3][u]);
+                c[u] = fmaf(fg, c[u], ig * gg);
+                h[u] = og * fast_tanh(c[u]);
               }
               *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
               *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
@@ -299,6 +337,7 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
     tcgen05_fence_after();
   }
 
+  if constexpr (kCL > 1) cluster_sync_all();  // no multicast / remote arrive may target a CTA that has exited
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
@@ -308,9 +347,11 @@ static size_t lstm_smem_bytes(int kblocks, int nsplit, int U) {
 }
 
 int lstm_init() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 3, 8))));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 1, 16))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16))));
   return BLM_OK;
 }
@@ -364,17 +405,27 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   p.barrier = reinterpret_cast<unsigned int*>(ws);
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(ws + 256);
+  // bf16 mode: 16 units per CTA and the batch split over two CTA rows (halves the per-step h ingest);
+  // precise mode keeps 8 units per CTA (hi + lo slices fill the same 128 KB) and no batch split
+  static const bool force_u8 = getenv("BLM_LSTM_U8") != nullptr;          // A/B switches for profiling
+  // Two experiments kept behind switches because they measured as exact no-ops (67.7 us per step at B = 2048
+  // in all four combinations, profiles/r01v): TMA multicast of the h tiles inside 4-CTA clusters and a
+  // staggered K-block order.  The step is therefore NOT bound by L2 bandwidth or hot lines but by latency:
+  // 80 KB of h in flight per SM (5-stage ring next to the 128 KB resident W slice) over a ~2 us
+  // TMA + MMA + commit round trip = ~40 GB/s per SM.  The fix is structural (cta_group::2 pairs sharing the
+  // resident slice so that each CTA needs half the rows), not a different load path.
+  static const bool no_cluster = getenv("BLM_LSTM_CLUSTER") == nullptr;
+  static const bool no_stagger = getenv("BLM_LSTM_STAGGER") == nullptr;
+  p.kb_stagger = no_stagger ? 0 : 1;
+  const int U = (!w_hh_lo && (H % 16) == 0 && !force_u8) ? 16 : 8;
+  const int nb = (U == 16 && p.m_tiles >= 2 && 2 * (H / U) <= num_sms()) ? 2 : 1;
+  const int CL = (U == 16 && !no_cluster && ((H / U) % 4) == 0 && p.m_tiles >= 2) ? 4 : 1;
   for (int buf = 0; buf < 2; ++buf)
     for (int part = 0; part < 2; ++part) {
       p.hbuf[buf][part] = hb + (static_cast<int64_t>(buf) * 2 + part) * B * H;
-      int rc = encode_tmap_bf16(&p.tmH[buf][part], p.hbuf[buf][part], B, H, H, 128);
+      int rc = encode_tmap_bf16(&p.tmH[buf][part], p.hbuf[buf][part], B, H, H, 128 / CL);
       if (rc != BLM_OK) return rc;
     }
-  // bf16 mode: 16 units per CTA and the batch split over two CTA rows (halves the per-step h ingest);
-  // precise mode keeps 8 units per CTA (hi + lo slices fill the same 128 KB) and no batch split
-  static const bool force_u8 = getenv("BLM_LSTM_U8") != nullptr;  // A/B switch for profiling
-  const int U = (!w_hh_lo && (H % 16) == 0 && !force_u8) ? 16 : 8;
-  const int nb = (U == 16 && p.m_tiles >= 2 && 2 * (H / U) <= num_sms()) ? 2 : 1;
   p.unit_blocks = static_cast<int>(H / U);
   p.tiles_per_cta = (p.m_tiles + nb - 1) / nb;
   BLM_REQUIRE(p.tiles_per_cta * 4 * U <= 512, BLM_ERR_SHAPE, "batch %lld exceeds the TMEM accumulators of one launch",
@@ -388,7 +439,26 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
   BLM_CHECK_CUDA(cudaMemsetAsync(p.barrier, 0, 256, st));
   void* args[] = {&p};
   const dim3 grid(static_cast<unsigned>(p.unit_blocks * nb)), block(kLThreads);
-  void* fn = U == 16 ? reinterpret_cast<void*>(lstm_layer_kernel<16>) : reinterpret_cast<void*>(lstm_layer_kernel<8>);
+  if (CL > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = lstm_smem_bytes(p.kblocks, p.nsplit, U);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;  // the per-step grid barrier needs every CTA resident
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_layer_kernel<16, 4>, p));
+    return BLM_OK;
+  }
+  void* fn = U == 16 ? reinterpret_cast<void*>(lstm_layer_kernel<16, 1>) : reinterpret_cast<void*>(lstm_layer_kernel<8, 1>);
   BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, lstm_smem_bytes(p.kblocks, p.nsplit, U), st));
   return BLM_OK;
 }

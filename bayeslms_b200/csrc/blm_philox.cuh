@@ -9,9 +9,9 @@ namespace blm {
 // ------------------------------------------------------------------ Philox
 // Philox4x32-10 (Salmon et al., SC'11).  counter = (idx_lo, idx_hi, stream_lo,
 // stream_hi), key = (seed_lo, seed_hi).  One call yields four uniform words ->
-// four N(0,1) values by two Box-Muller pairs, so element i of a tensor uses
-// counter i/4, lane i%4: the noise is a pure function of (seed, stream, i) and
-// therefore identical on every rank and for every launch geometry.
+// eight N(0,1) values (below), so element i of a tensor uses counter i/8, lane
+// i%8: the noise is a pure function of (seed, stream, i) and therefore identical
+// on every rank and for every launch geometry.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
 #pragma unroll
@@ -25,32 +25,58 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-__device__ __forceinline__ float u32_to_unit_open(uint32_t u) {
-  // (0, 1]: never 0 so the log below is finite
-  return (static_cast<float>(u >> 8) + 1.0f) * (1.0f / 16777216.0f);
+// Eight N(0,1) values from ONE Philox call: each 32-bit word is split into two 16-bit uniforms that
+// drive one Box-Muller pair -- radius from u1 = (k + 0.5) / 65536 (|z| <= 4.66, P(|z| > 4.66) = 3e-6),
+// angle from (j + 0.5) / 65536 of a turn.  Four MUFU ops (lg2, sqrt, sin, cos) and ~12 ALU ops per pair;
+// halving the Philox rounds per normal is what lets the tile-fused sampled GEMM keep its generator
+// warps below the tensor pipe's time per K block.  Element i of a tensor uses counter i/8, lane i%8.
+struct Normal8 {
+  float v[8];
+};
+
+__device__ __forceinline__ void box_muller16(uint32_t w, float& z0, float& z1) {
+  constexpr float kInv = 1.0f / 65536.0f;
+  const float u1 = (static_cast<float>(w & 0xffffu) + 0.5f) * kInv;   // (0, 1)
+  const float turn = (static_cast<float>(w >> 16) + 0.5f) * kInv;     // (0, 1) of a full turn
+  float r, sn, cs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r * -1.3862943611198906f));  // sqrt(-2 ln u1)
+  const float ang = turn * 6.283185307179586f;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+  z0 = r * cs;
+  z1 = r * sn;
 }
 
-__device__ __forceinline__ float sqrt_approx(float x) {
-  float y;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Four N(0,1) values from one Philox call: two Box-Muller pairs on MUFU intrinsics (lg2, sqrt, sin,
-// cos = 2 special-function ops per normal -- the budget that bounds the tile-fused sampled GEMM).
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream, uint64_t idx4) {
+__device__ __forceinline__ Normal8 philox_normal8(uint64_t seed, uint64_t stream, uint64_t idx8) {
   const uint4 r = philox4x32_10(
-      make_uint4(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32),
+      make_uint4(static_cast<uint32_t>(idx8), static_cast<uint32_t>(idx8 >> 32),
                  static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32)),
       make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-  constexpr float kTwoPi = 6.283185307179586f;
-  constexpr float kNeg2Ln2 = -1.3862943611198906f;
-  const float r0 = sqrt_approx(kNeg2Ln2 * __log2f(u32_to_unit_open(r.x)));
-  const float r1 = sqrt_approx(kNeg2Ln2 * __log2f(u32_to_unit_open(r.z)));
-  float s0, c0, s1, c1;
-  __sincosf(kTwoPi * u32_to_unit_open(r.y), &s0, &c0);
-  __sincosf(kTwoPi * u32_to_unit_open(r.w), &s1, &c1);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+  Normal8 o;
+  box_muller16(r.x, o.v[0], o.v[1]);
+  box_muller16(r.y, o.v[2], o.v[3]);
+  box_muller16(r.z, o.v[4], o.v[5]);
+  box_muller16(r.w, o.v[6], o.v[7]);
+  return o;
+}
+
+// Four consecutive normals of the stream: elements [4 idx4, 4 idx4 + 4) = half of counter idx4 / 2.
+// (The elementwise kernels walk tensors four elements at a time.)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream, uint64_t idx4) {
+  const uint4 r = philox4x32_10(
+      make_uint4(static_cast<uint32_t>(idx4 >> 1), static_cast<uint32_t>(idx4 >> 33),
+                 static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32)),
+      make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  float4 o;
+  if (idx4 & 1u) {
+    box_muller16(r.z, o.x, o.y);
+    box_muller16(r.w, o.z, o.w);
+  } else {
+    box_muller16(r.x, o.x, o.y);
+    box_muller16(r.y, o.z, o.w);
+  }
+  return o;
 }
 
 // w = mu + sigma * eps with sigma = exp(lgstd): one definition so the fused and the materialising

@@ -305,19 +305,38 @@ __global__ void layernorm_bwd_fold_kernel(const float* __restrict__ partial, int
 
 // ------------------------------------------------------------------ attention backward
 // One CTA per (sequence, head), T <= 128, head_dim 64, fp32.  q, k, v, dO of the head are staged in
-// shared memory (rows padded to 65 floats).  Phase 1 (warp per query row i): recompute the softmax
-// statistics (m_i, l_i), D_i = sum_j p_ij dP_ij, and dq_i = sum_j dS_ij k_j.  Phase 2 (warp per key
-// row j): dk_j = sum_{i >= j} dS_ij q_i, dv_j = sum_{i >= j} p_ij dO_i, with p and dS recomputed from
-// the stored row statistics -- no T x T matrix is kept.  dq is multiplied by q_scale (the forward
-// scaled q after the projection, model.py:877).
+// shared memory with a row pitch of 68 floats (16-byte aligned rows; a quarter-warp reading the same
+// 16-byte column chunk of eight consecutive rows touches 32 distinct banks).
+// Phase 1 (warp per query row i): q_i and dO_i live in registers; lane j reads k_j / v_j with 128-bit
+// loads and forms s_ij and dP_ij; softmax statistics (m_i, 1/l_i), D_i = sum_j p_ij dP_ij and
+// dS_ij = p_ij (dP_ij - D_i) follow; dq_i = sum_j dS_ij k_j is accumulated by two half-warps (even / odd
+// j, four columns per lane) and combined with one shuffle.
+// Phase 2 (warp per key row j): k_j and v_j live in registers; lane i recomputes p_ij and dS_ij from the
+// stored statistics, then dk_j = sum_i dS_ij q_i and dv_j = sum_i p_ij dO_i the same half-warp way.
+// Nothing of size T x T is kept.  dq is multiplied by q_scale (model.py:877 scales q after the projection).
 constexpr int kBwdHd = 64;
+constexpr int kBwdHP = 68;
+
+__device__ __forceinline__ float dot64(const float4 (&a)[16], const float* __restrict__ row) {
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float4 b = *reinterpret_cast<const float4*>(row + 4 * c);
+    s0 = fmaf(a[c].x, b.x, s0);
+    s1 = fmaf(a[c].y, b.y, s1);
+    s0 = fmaf(a[c].z, b.z, s0);
+    s1 = fmaf(a[c].w, b.w, s1);
+  }
+  return s0 + s1;
+}
+
 __global__ void __launch_bounds__(256) mha_causal_bwd_kernel(const float* __restrict__ qkv, long long ld,
                                                              const float* __restrict__ dout, long long ldo,
                                                              const int* __restrict__ seq_offsets, int nhead,
                                                              int max_len, float q_scale, float* __restrict__ dqkv,
                                                              long long ldd) {
-  extern __shared__ float sm[];
-  constexpr int HP = kBwdHd + 1;
+  extern __shared__ __align__(16) float sm[];
+  constexpr int HP = kBwdHP;
   const int seq = blockIdx.x / nhead, head = blockIdx.x - seq * nhead;
   const int row0 = seq_offsets[seq];
   const int T = seq_offsets[seq + 1] - row0;
@@ -331,109 +350,116 @@ __global__ void __launch_bounds__(256) mha_causal_bwd_kernel(const float* __rest
   float* sV = sK + max_len * HP;
   float* sG = sV + max_len * HP;          // dO
   float* sM = sG + max_len * HP;          // row max
-  float* sL = sM + max_len;               // row sum
+  float* sL = sM + max_len;               // 1 / row sum
   float* sD = sL + max_len;               // D_i
-  float* sP = sD + max_len;               // [8 warps][max_len] scratch
-  for (int idx = threadIdx.x; idx < T * kBwdHd; idx += 256) {
-    const int t = idx / kBwdHd, c = idx - t * kBwdHd;
+  float* sP = sD + max_len;               // [8 warps][2][max_len] scratch
+  for (int idx = threadIdx.x; idx < T * (kBwdHd / 4); idx += 256) {
+    const int t = idx / (kBwdHd / 4), c = (idx - t * (kBwdHd / 4)) * 4;
     const float* base = qkv + static_cast<long long>(row0 + t) * ld + head * kBwdHd + c;
-    sQ[t * HP + c] = __ldg(base);
-    sK[t * HP + c] = __ldg(base + d);
-    sV[t * HP + c] = __ldg(base + 2 * d);
-    sG[t * HP + c] = __ldg(dout + static_cast<long long>(row0 + t) * ldo + head * kBwdHd + c);
+    *reinterpret_cast<float4*>(sQ + t * HP + c) = __ldg(reinterpret_cast<const float4*>(base));
+    *reinterpret_cast<float4*>(sK + t * HP + c) = __ldg(reinterpret_cast<const float4*>(base + d));
+    *reinterpret_cast<float4*>(sV + t * HP + c) = __ldg(reinterpret_cast<const float4*>(base + 2 * d));
+    *reinterpret_cast<float4*>(sG + t * HP + c) =
+        __ldg(reinterpret_cast<const float4*>(dout + static_cast<long long>(row0 + t) * ldo + head * kBwdHd + c));
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* pr = sP + warp * max_len;
+  const int half = lane >> 4, cl = lane & 15;
+  float* pa = sP + (warp * 2) * max_len;      // per-warp scratch rows
+  float* pb = pa + max_len;
   // ---- phase 1: per query row
   for (int i = warp; i < T; i += 8) {
-    const float* q = sQ + i * HP;
-    const float* go = sG + i * HP;
+    float4 q4[16], g4[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      q4[c] = *reinterpret_cast<const float4*>(sQ + i * HP + 4 * c);
+      g4[c] = *reinterpret_cast<const float4*>(sG + i * HP + 4 * c);
+    }
     float mx = -INFINITY;
     for (int j = lane; j <= i; j += 32) {
-      const float* k = sK + j * HP;
-      float s = 0.0f;
-#pragma unroll 16
-      for (int c = 0; c < kBwdHd; ++c) s = fmaf(q[c], k[c], s);
-      pr[j] = s;
+      const float s = dot64(q4, sK + j * HP);
+      pa[j] = s;
+      pb[j] = dot64(g4, sV + j * HP);
       mx = fmaxf(mx, s);
     }
     mx = warp_max(mx);
     float sum = 0.0f;
-    for (int j = lane; j <= i; j += 32) sum += expf(pr[j] - mx);
+    for (int j = lane; j <= i; j += 32) sum += expf(pa[j] - mx);
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     float dsum = 0.0f;
     for (int j = lane; j <= i; j += 32) {
-      const float* v = sV + j * HP;
-      float dp = 0.0f;
-#pragma unroll 16
-      for (int c = 0; c < kBwdHd; ++c) dp = fmaf(go[c], v[c], dp);
-      const float p = expf(pr[j] - mx) * inv;
-      pr[j] = p * dp;      // p_ij dP_ij, finished below once D_i is known
-      dsum += p * dp;
-      // keep p in the upper half of the scratch row? not needed: dS = p dP - p D
-      sP[8 * max_len + warp * max_len + j] = p;
+      const float p = expf(pa[j] - mx) * inv;
+      pa[j] = p;
+      dsum = fmaf(p, pb[j], dsum);
     }
     const float D = warp_sum(dsum);
+    for (int j = lane; j <= i; j += 32) pa[j] = pa[j] * (pb[j] - D);  // dS_ij
     if (lane == 0) {
       sM[i] = mx;
       sL[i] = inv;
       sD[i] = D;
     }
     __syncwarp();
-    // dq_i[c] = sum_j (p dP - p D)_j k_j[c]; lanes split the 64 columns
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int j = 0; j <= i; ++j) {
-      const float ds = pr[j] - sP[8 * max_len + warp * max_len + j] * D;
-      a0 = fmaf(ds, sK[j * HP + lane], a0);
-      a1 = fmaf(ds, sK[j * HP + lane + 32], a1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = half; j <= i; j += 2) {
+      const float ds = pa[j];
+      const float4 k4 = *reinterpret_cast<const float4*>(sK + j * HP + 4 * cl);
+      acc.x = fmaf(ds, k4.x, acc.x);
+      acc.y = fmaf(ds, k4.y, acc.y);
+      acc.z = fmaf(ds, k4.z, acc.z);
+      acc.w = fmaf(ds, k4.w, acc.w);
     }
-    float* o = dqkv + static_cast<long long>(row0 + i) * ldd + head * kBwdHd;
-    o[lane] = a0 * q_scale;
-    o[lane + 32] = a1 * q_scale;
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    if (half == 0) {
+      float* o = dqkv + static_cast<long long>(row0 + i) * ldd + head * kBwdHd + 4 * cl;
+      *reinterpret_cast<float4*>(o) = make_float4(acc.x * q_scale, acc.y * q_scale, acc.z * q_scale, acc.w * q_scale);
+    }
     __syncwarp();
   }
   __syncthreads();
   // ---- phase 2: per key row
   for (int j = warp; j < T; j += 8) {
-    const float* k = sK + j * HP;
-    const float* v = sV + j * HP;
-    float* ps = sP + warp * max_len;                 // p_ij for i >= j
-    float* dss = sP + 8 * max_len + warp * max_len;  // dS_ij
+    float4 k4[16], v4[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      k4[c] = *reinterpret_cast<const float4*>(sK + j * HP + 4 * c);
+      v4[c] = *reinterpret_cast<const float4*>(sV + j * HP + 4 * c);
+    }
     for (int i = j + lane; i < T; i += 32) {
-      const float* q = sQ + i * HP;
-      const float* go = sG + i * HP;
-      float s = 0.0f, dp = 0.0f;
-#pragma unroll 16
-      for (int c = 0; c < kBwdHd; ++c) {
-        s = fmaf(q[c], k[c], s);
-        dp = fmaf(go[c], v[c], dp);
-      }
+      const float s = dot64(k4, sQ + i * HP);
+      const float dp = dot64(v4, sG + i * HP);
       const float p = expf(s - sM[i]) * sL[i];
-      ps[i] = p;
-      dss[i] = p * (dp - sD[i]);
+      pa[i] = p;
+      pb[i] = p * (dp - sD[i]);
     }
     __syncwarp();
-    float k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
-    for (int i = j; i < T; ++i) {
-      const float p = ps[i], ds = dss[i];
-      k0 = fmaf(ds, sQ[i * HP + lane], k0);
-      k1 = fmaf(ds, sQ[i * HP + lane + 32], k1);
-      v0 = fmaf(p, sG[i * HP + lane], v0);
-      v1 = fmaf(p, sG[i * HP + lane + 32], v1);
+    float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = j + half; i < T; i += 2) {
+      const float p = pa[i], ds = pb[i];
+      const float4 qq = *reinterpret_cast<const float4*>(sQ + i * HP + 4 * cl);
+      const float4 gg = *reinterpret_cast<const float4*>(sG + i * HP + 4 * cl);
+      ak.x = fmaf(ds, qq.x, ak.x); ak.y = fmaf(ds, qq.y, ak.y); ak.z = fmaf(ds, qq.z, ak.z); ak.w = fmaf(ds, qq.w, ak.w);
+      av.x = fmaf(p, gg.x, av.x); av.y = fmaf(p, gg.y, av.y); av.z = fmaf(p, gg.z, av.z); av.w = fmaf(p, gg.w, av.w);
     }
-    float* o = dqkv + static_cast<long long>(row0 + j) * ldd + head * kBwdHd;
-    o[d + lane] = k0;
-    o[d + lane + 32] = k1;
-    o[2 * d + lane] = v0;
-    o[2 * d + lane + 32] = v1;
+    ak.x += __shfl_xor_sync(0xffffffffu, ak.x, 16); ak.y += __shfl_xor_sync(0xffffffffu, ak.y, 16);
+    ak.z += __shfl_xor_sync(0xffffffffu, ak.z, 16); ak.w += __shfl_xor_sync(0xffffffffu, ak.w, 16);
+    av.x += __shfl_xor_sync(0xffffffffu, av.x, 16); av.y += __shfl_xor_sync(0xffffffffu, av.y, 16);
+    av.z += __shfl_xor_sync(0xffffffffu, av.z, 16); av.w += __shfl_xor_sync(0xffffffffu, av.w, 16);
+    if (half == 0) {
+      float* o = dqkv + static_cast<long long>(row0 + j) * ldd + head * kBwdHd + 4 * cl;
+      *reinterpret_cast<float4*>(o + d) = ak;
+      *reinterpret_cast<float4*>(o + 2 * d) = av;
+    }
     __syncwarp();
   }
 }
 
 static size_t mha_bwd_smem_bytes(int max_len) {
-  return sizeof(float) * (4ull * max_len * (kBwdHd + 1) + 3ull * max_len + 16ull * max_len);
+  return sizeof(float) * (4ull * max_len * kBwdHP + 3ull * max_len + 16ull * max_len);
 }
 
 // ------------------------------------------------------------------ activation column gradients
@@ -805,6 +831,8 @@ int blm_mha_causal_bwd(const float* qkv, int64_t ld, const float* dout, int64_t 
   BLM_REQUIRE(qkv && dout && seq_offsets && dqkv && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention-backward arguments");
   BLM_REQUIRE(head_dim == kBwdHd, BLM_ERR_SHAPE, "attention backward needs head_dim 64, got %d", head_dim);
   BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
+  BLM_REQUIRE((ld % 4) == 0 && (ldo % 4) == 0 && (ldd % 4) == 0 && aligned16(qkv) && aligned16(dout) && aligned16(dqkv),
+              BLM_ERR_ALIGN, "attention-backward operands must be 16-byte aligned with leading dimensions %% 4 == 0");
   static bool attr = false;
   if (!attr) {
     int rc = train_init();

@@ -17,6 +17,7 @@ operator) is done once and shared by all K samples.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Union
 
@@ -24,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .ops import ACT_GELU, ACT_GPMIX, ACT_NONE, Split
+from .ops import ACT_GELU, ACT_GELU_FAST, ACT_GPMIX, ACT_NONE, Split
 
 Sample = Union[int, dict]
 
@@ -86,6 +87,8 @@ class _Plan:
             self.dec_b = model.decoder.bias.detach().float().contiguous()
             if model.family == "bayes_lstm":
                 self._lstm(model)
+            elif model.family in ("gauss_lstm", "v_lstm"):
+                self._cell_lstm(model)
             else:
                 self._transformer(model)
 
@@ -136,6 +139,33 @@ class _Plan:
                 "w_hh": self.split(getattr(r, f"weight_hh_mean_{layer}")),
                 "bias": (getattr(r, f"bias_ih_mean_{layer}") + getattr(r, f"bias_hh_mean_{layer}")).detach().float().contiguous(),
             })
+
+
+def _cell_lstm_plan(self, m):
+    """Layer list of GaussRNNModel / VariationalRNNModel.  Plain layers (nn.LSTM members, VLSTMCells with their
+    doubled bias_ih) go to the persistent recurrence kernel; a GP cell layer carries the concatenated weights
+    [W_ih; W_g(x part)] (input side, hoisted) and [W_hh; W_g(h part)] (recurrent side, one product per step)."""
+    self.lstm = []
+    for member in m.rnn.rnn:
+        if isinstance(member, torch.nn.LSTM):
+            for l in range(member.num_layers):
+                g = lambda n: getattr(member, f"{n}_l{l}").detach().float()  # noqa: E731
+                self.lstm.append({"w_ih": self.split(g("weight_ih")), "w_hh": self.split(g("weight_hh")),
+                                  "bias": (g("bias_ih") + g("bias_hh")).contiguous()})
+        elif getattr(member, "kind", "") == "gp":
+            gp, nin = member.gpnn, member.input_size
+            wg = gp.weights_mean.detach().float()
+            w_in = torch.cat([member.weights_ih.detach().float(), wg[:, :nin]], 0).contiguous()     # [5H, in]
+            w_rec = torch.cat([member.weights_hh.detach().float(), wg[:, nin:]], 0).contiguous()    # [5H, H]
+            bias = torch.cat([2.0 * member.bias_ih.detach().float(), gp.bias_mean.detach().float()], 0).contiguous()
+            self.lstm.append({"w_ih": self.split(w_in), "w_hh": self.split(w_rec), "bias": bias,
+                              "gp": {"coef": gp.coef_mean.detach().float().contiguous(), "gate": member.gate_type}})
+        else:   # VLSTMCell: gates = W_ih x + b_ih + W_hh h + b_ih (model.py:2519)
+            self.lstm.append({"w_ih": self.split(member.weights_ih), "w_hh": self.split(member.weights_hh),
+                              "bias": (2.0 * member.bias_ih.detach().float()).contiguous()})
+
+
+_Plan._cell_lstm = _cell_lstm_plan
 
 
 def _scaled_decoder(plan: _Plan, model, scale: float):
@@ -195,6 +225,7 @@ class _TmRun:
         self.M = batch.n_tokens
         self.dev = plan.device
         self.fused_sampling = False
+        self.fast_gelu = os.environ.get("BLM_NO_FAST_GELU") is None   # A/B switch for profiling
 
     def f32(self, cols):
         return torch.empty(self.M, cols, dtype=torch.float32, device=self.dev)
@@ -224,7 +255,9 @@ class _TmRun:
     # part C: first FFN projection with the activation fused (GELU, or the GP mixture)
     def part_c(self, L, x1s: Split, w1: Split, b1, coef) -> Split:
         h = ops.empty_split(self.M, w1.hi.shape[0], self.prec, self.dev)
-        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=ACT_GPMIX if coef is not None else ACT_GELU, coef=coef, out=h,
+        # fast mode: the hidden is stored as bf16 only, so GELU runs in packed fp16 (half the epilogue's issue slots)
+        gelu = ACT_GELU_FAST if (self.prec == "bf16" and self.fast_gelu) else ACT_GELU
+        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=ACT_GPMIX if coef is not None else gelu, coef=coef, out=h,
                  tag="ffn1")
         return h
 
@@ -448,8 +481,8 @@ def _lstm_weights(model, plan: _Plan, sample: Optional[Sample], seed):
     """Per-layer (w_ih, w_hh, bias) for one posterior sample: copies of the mean matrices whose
     gate-row block [(p-1)H, pH) is overwritten with mu + exp(lgstd) * eps (model.py:716-725)."""
     r = model.rnn
-    if sample is None or not 1 <= r.position <= 4:
-        return plan.lstm
+    if model.family != "bayes_lstm" or sample is None or not 1 <= r.position <= 4:
+        return plan.lstm   # GP / V cells score with their posterior means (eval semantics of the reference)
     rows = r.gate_rows()
     out = []
     for li, layer in enumerate((1, 2)):
@@ -498,18 +531,44 @@ def _lstm_forward(model, plan: _Plan, weights, tokens_tb: torch.Tensor, lengths:
     out32 = None
     for li in range(2):
         W = weights[li]
-        gates = torch.empty(T * B, 4 * H, dtype=torch.float32, device=plan.device)
-        ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
         last = li == 1
-        out32, x, hT, cT = ops.lstm_layer(gates, W["w_hh"], h0[li], c0[li], lengths, T, B, H, prec=prec,
-                                          want_f32=last and want_f32, want_split=(not last) or want_split)
+        if "gp" in W:
+            out32, x, hT, cT = _gp_lstm_layer(plan, W, x, h0[li], c0[li], lengths, T, B, H, last and want_f32,
+                                              (not last) or want_split)
+        else:
+            gates = torch.empty(T * B, 4 * H, dtype=torch.float32, device=plan.device)
+            ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+            out32, x, hT, cT = ops.lstm_layer(gates, W["w_hh"], h0[li], c0[li], lengths, T, B, H, prec=prec,
+                                              want_f32=last and want_f32, want_split=(not last) or want_split)
         hs.append(hT)
         cs.append(cT)
     return out32, x, torch.stack(hs), torch.stack(cs)
 
 
+def _gp_lstm_layer(plan: _Plan, W, x: Split, h0, c0, lengths, T, B, H, want_f32, want_split):
+    """GP-LSTM cell layer (model.py:1720-1777).  The input side of all five blocks (four gates + GP unit) is
+    hoisted into one GEMM over all timesteps; each step is one [B, 5H] product on the recurrent weights with the
+    hoisted rows as the residual operand, then the fused cell update."""
+    prec, dev = plan.prec, plan.device
+    pre = torch.empty(T * B, 5 * H, dtype=torch.float32, device=dev)
+    ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=pre, tag="gplstm_in")
+    h = h0.detach().float().contiguous().clone()
+    c = c0.detach().float().contiguous().clone()
+    h_op = ops.split(h, prec)
+    out32 = torch.empty(T * B, H, dtype=torch.float32, device=dev) if want_f32 else None
+    outs = ops.empty_split(T * B, H, prec, dev) if want_split else None
+    acc = torch.empty(B, 5 * H, dtype=torch.float32, device=dev)
+    for t in range(T):
+        rows = slice(t * B, (t + 1) * B)
+        ops.gemm(h_op, W["w_hh"], prec=prec, resid=pre[rows], out_f32=acc, tag="gplstm_rec")
+        ops.gp_lstm_cell(acc, W["gp"]["coef"], W["gp"]["gate"], lengths, t, c, h, h_op,
+                         None if out32 is None else out32[rows],
+                         None if outs is None else Split(outs.hi[rows], None if outs.lo is None else outs.lo[rows]))
+    return out32, outs, h, c
+
+
 def _fresh_train_sample(model):
-    if model.training and 1 <= model.rnn.position <= 4:
+    if model.family == "bayes_lstm" and model.training and 1 <= model.rnn.position <= 4:
         return 0, int(torch.randint(0, 2 ** 62, (1,)).item())
     return None, None
 

@@ -137,18 +137,24 @@ class GPNN(nn.Module):
     """Gaussian-process activation unit: z = x W^T + b, out = sum_i coef[i] * act_i(z) with
     acts (tanh, sigmoid, relu, gelu); type 1/3 Bayesian coef, 2/3 Bayesian W,b (model.py:1780-1902)."""
 
-    def __init__(self, input_size, output_size, act_set=("tanh", "sigmoid", "relu", "gelu"), gpnn_type=0):
+    ACT_SETS = (("tanh", "sigmoid", "relu", "gelu"),      # Transformer GP layer, model.py:2263
+                ("sigmoid", "tanh", "relu"),              # GP-LSTM gates i, g, o (GPNN default, model.py:1787,1693-1695)
+                ("sigmoid",))                             # GP-LSTM forget gate, model.py:1697
+
+    def __init__(self, input_size, output_size, act_set=("sigmoid", "tanh", "relu"), gpnn_type=0):
         super().__init__()
-        if tuple(act_set) != ("tanh", "sigmoid", "relu", "gelu"):
-            raise NotImplementedError("only the Transformer activation set of model.py:2263 is fused")
+        if tuple(act_set) not in self.ACT_SETS:
+            raise NotImplementedError(f"activation set {tuple(act_set)} is not one the reference builds")
+        self.act_set = tuple(act_set)
         self.input_size, self.output_size, self.gpnn_type = input_size, output_size, gpnn_type
         self.sample = False  # as shipped (model.py:1799); train.py never flips it
         s = 1.0 / math.sqrt(output_size)
+        n_act = len(self.act_set)
         self.weights_mean = _uniform((output_size, input_size), -s, s)
         self.bias_mean = nn.Parameter(torch.zeros(output_size))
-        self.coef_mean = _uniform((4, output_size), 0.0, 1.0)
+        self.coef_mean = _uniform((n_act, output_size), 0.0, 1.0)
         if gpnn_type in (1, 3):
-            self.coef_lgstd = _lgstd_like((4, output_size), s)
+            self.coef_lgstd = _lgstd_like((n_act, output_size), s)
         if gpnn_type in (2, 3):
             self.weights_lgstd = _lgstd_like((output_size, input_size), s)
             self.bias_lgstd = _lgstd_like((output_size,), s)
@@ -175,7 +181,7 @@ class GaussTransformerEncoderLayer(_EncoderLayer):
         self.gauss_pos = self.gpnn_type = gauss_pos
         if not 0 <= gauss_pos <= 3:
             raise NotImplementedError("GPNN2 (gauss_pos=4) is broken in the reference (SURVEY.md a16)")
-        self.gpnn = GPNN(d_model, dim_feedforward, gpnn_type=gauss_pos)
+        self.gpnn = GPNN(d_model, dim_feedforward, act_set=("tanh", "sigmoid", "relu", "gelu"), gpnn_type=gauss_pos)
 
 
 class VTransformerEncoderLayer(_EncoderLayer):
@@ -373,6 +379,136 @@ class BayesRNNModel(nn.Module):
         return _engine.lstm_score(self, batch, hidden, **kw)
 
 
+class GPLSTMCell(nn.Module):
+    """LSTM cell whose gate ``gate_type`` (1=i, 2=f, 3=g, 4=o) is a GP unit over cat[x, h]
+    (model.py:1674-1777).  Keeps the reference's bias quirk: ``bias_ih`` is added twice and ``bias_hh``
+    never (model.py:1748-1752).  gate types 5-7 and GPNN2 (gpnn_type 4) are not on the hot path."""
+    kind = "gp"
+
+    def __init__(self, input_size, hidden_size, gate_type=0, gpnn_type=0):
+        super().__init__()
+        if not (1 <= gate_type <= 4 and 0 <= gpnn_type <= 3):
+            raise NotImplementedError(f"GP-LSTM gate_type {gate_type} / gpnn_type {gpnn_type} is outside the B200 hot path "
+                                      "(gates 1-4 with GPNN types 0-3 are)")
+        self.input_size, self.hidden_size, self.gate_type, self.gpnn_type = input_size, hidden_size, gate_type, gpnn_type
+        act_set = ("sigmoid",) if gate_type == 2 else ("sigmoid", "tanh", "relu")
+        self.gpnn = GPNN(hidden_size + input_size, hidden_size, act_set=act_set, gpnn_type=gpnn_type)
+        s = 1.0 / math.sqrt(hidden_size)
+        self.weights_ih = _uniform((4 * hidden_size, input_size), -s, s)
+        self.bias_ih = nn.Parameter(torch.zeros(4 * hidden_size))
+        self.weights_hh = _uniform((4 * hidden_size, hidden_size), -s, s)
+        self.bias_hh = nn.Parameter(torch.zeros(4 * hidden_size))
+
+
+class GPLSTM(nn.Module):
+    """``gpnn_type`` string (the ``--L_gauss_pos`` flag): '<gate><type>' -> GP cell + nn.LSTM; three characters ->
+    nn.LSTM + GP cell; four -> two GP cells (gates [0] and [2], GPNN type [1]); '0x' -> plain nn.LSTM
+    (model.py:1609-1636).  The nn.LSTM members only hold parameters (keys weight_ih_l0, ...)."""
+
+    def __init__(self, input_size, hidden_size, num_layers=1, bias=True, dropout=0.0, gpnn_type="00"):
+        super().__init__()
+        if num_layers != 2:
+            raise NotImplementedError("the GP-LSTM of the reference recipes has two layers")
+        self.input_size, self.hidden_size, self.num_layers, self.gpnn_type = input_size, hidden_size, num_layers, gpnn_type
+        t = gpnn_type
+        cell = lambda gate: GPLSTMCell(input_size, hidden_size, gate_type=int(gate), gpnn_type=int(t[1]))  # noqa: E731
+        plain = lambda n: nn.LSTM(input_size=hidden_size, hidden_size=hidden_size, num_layers=n)  # noqa: E731
+        if int(t[0]) == 0:
+            members = [plain(num_layers)]
+        elif len(t) == 2:
+            members = [cell(t[0]), plain(num_layers - 1)]
+        elif len(t) == 3:
+            members = [plain(num_layers - 1), cell(t[0])]
+        else:
+            members = [cell(t[0]), cell(t[2])]
+        self.rnn = nn.ModuleList(members)
+
+
+class VNN(nn.Module):
+    """hidden_lgstd (1, input_size); noise only in training (model.py:2534-2579)."""
+
+    def __init__(self, input_size):
+        super().__init__()
+        s = 1.0 / math.sqrt(input_size)
+        self.sample = True
+        self.hidden_lgstd = _lgstd_like((1, input_size), s)
+
+
+class VLSTMCell(nn.Module):
+    """LSTM cell with the doubled ``bias_ih`` (model.py:2519) and a VNN that perturbs h in training."""
+    kind = "plain"
+
+    def __init__(self, input_size, hidden_size, vnn_type=0):
+        super().__init__()
+        self.input_size, self.hidden_size, self.vnn_type = input_size, hidden_size, vnn_type
+        self.vnn = VNN(input_size)
+        s = 1.0 / math.sqrt(hidden_size)
+        self.weights_ih = _uniform((4 * hidden_size, input_size), -s, s)
+        self.bias_ih = nn.Parameter(torch.zeros(4 * hidden_size))
+        self.weights_hh = _uniform((4 * hidden_size, hidden_size), -s, s)
+        self.bias_hh = nn.Parameter(torch.zeros(4 * hidden_size))
+
+
+class VariationalLSTM(nn.Module):
+    """Two VLSTMCells; ``vlstm_type`` = the ``--L_v_pos`` bit string (model.py:2426-2468)."""
+
+    def __init__(self, input_size, hidden_size, num_layers=1, bias=True, dropout=0.0, vlstm_type="00"):
+        super().__init__()
+        self.input_size, self.hidden_size, self.num_layers, self.vlstm_type = input_size, hidden_size, num_layers, vlstm_type
+        self.rnn = nn.ModuleList([VLSTMCell(input_size, hidden_size, vnn_type=int(vlstm_type[0])),
+                                  VLSTMCell(input_size, hidden_size, vnn_type=int(vlstm_type[1]))])
+
+
+class _CellRNNModel(nn.Module):
+    """Shared container of GaussRNNModel / VariationalRNNModel: encoder, rnn, decoder (tied)."""
+
+    def _finish(self, rnn_type, ntoken, ninp, nhid, nlayers, dropout, tie_weights):
+        if rnn_type != "LSTM":
+            raise NotImplementedError("only --model LSTM is on the rescoring path")
+        self.rnn_type, self.nhid, self.nlayers, self.p_drop = rnn_type, nhid, nlayers, float(dropout)
+        self.encoder = nn.Embedding(ntoken, ninp)
+        self.decoder = nn.Linear(nhid, ntoken)
+        if tie_weights:
+            if nhid != ninp:
+                raise ValueError("When using the tied flag, nhid must be equal to emsize.")
+            self.decoder.weight = self.encoder.weight
+        nn.init.uniform_(self.encoder.weight, -0.1, 0.1)
+        nn.init.zeros_(self.decoder.bias)
+        nn.init.uniform_(self.decoder.weight, -0.1, 0.1)
+
+    def init_hidden(self, bsz):
+        w = self.encoder.weight
+        return (w.new_zeros(self.nlayers, bsz, self.nhid), w.new_zeros(self.nlayers, bsz, self.nhid))
+
+    def forward(self, x, hidden):
+        """(T, B) int64, (h, c) each (2, B, H) -> logits (T, B, V), (h, c); eval semantics (posterior means)."""
+        return _engine.lstm_logits(self, x, hidden)
+
+
+class GaussRNNModel(_CellRNNModel):
+    """GaussRNNModel(rnn_type, ntoken, ninp, nhid, nlayers, dropout, tie_weights, gauss_pos:str) (model.py:1317-1366)."""
+    family = "gauss_lstm"
+
+    def __init__(self, rnn_type, ntoken, ninp, nhid, nlayers, dropout=0.5, tie_weights=False, gauss_pos="00"):
+        super().__init__()
+        self.gauss_pos = gauss_pos
+        self.rnn = GPLSTM(ninp, nhid, nlayers, dropout=dropout, gpnn_type=gauss_pos)
+        self._finish(rnn_type, ntoken, ninp, nhid, nlayers, dropout, tie_weights)
+
+
+class VariationalRNNModel(_CellRNNModel):
+    """VariationalRNNModel(..., tie_weights, v_pos:str) (model.py:2373-2423)."""
+    family = "v_lstm"
+
+    def __init__(self, rnn_type, ntoken, ninp, nhid, nlayers, dropout=0.5, tie_weights=False, v_pos="00"):
+        super().__init__()
+        self.v_pos = v_pos
+        if nlayers != 2:
+            raise NotImplementedError("VariationalLSTM is hard-wired to two cells in the reference")
+        self.rnn = VariationalLSTM(ninp, nhid, nlayers, dropout=dropout, vlstm_type=v_pos)
+        self._finish(rnn_type, ntoken, ninp, nhid, nlayers, dropout, tie_weights)
+
+
 def build_model(args, ntokens):
     """The model-selection switch of the scorer / trainer (score.py:374-448, train.py:193-224),
     for the families on the hot path."""
@@ -393,5 +529,8 @@ def build_model(args, ntokens):
             return BayesRNNModel(*common, args.L_bayes_pos)
         if unc == "none":
             return BayesRNNModel(*common, 0)
-    raise NotImplementedError(f"--model {args.model} --uncertainty {unc} is outside the B200 hot path "
-                              "(GP / Variational LSTM cells are listed as 'next' in SURVEY.md 8f)")
+        if unc == "Gaussian":   # the scorer builds this family untied (score.py:428)
+            return GaussRNNModel(*common[:-1], False, args.L_gauss_pos)
+        if unc == "Variational":
+            return VariationalRNNModel(*common, args.L_v_pos)
+    raise NotImplementedError(f"--model {args.model} --uncertainty {unc} is outside the B200 hot path")

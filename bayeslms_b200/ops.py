@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
+from ._lib import (ACT_GELU, ACT_GELU_FAST, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
                    EPS_PTR, GemmDesc, GemmSampledDesc,
                    VocabNllDesc,
                    check, lib)
@@ -418,6 +418,18 @@ def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.T
                                    _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),
                                    _ptr(hT), _ptr(cT), _ptr(ws), _stream()), "blm_lstm_layer")
     return out32, outs, hT, cT
+
+
+def gp_lstm_cell(acc5: torch.Tensor, coef: torch.Tensor, gate_type: int, lengths: torch.Tensor, t: int, c: torch.Tensor,
+                 h: torch.Tensor, h_op: Split, out_f32: Optional[torch.Tensor], out: Optional[Split]) -> None:
+    """One timestep of the GP-LSTM cell (see ``blm_gp_lstm_cell``); c, h updated in place."""
+    B, H = h.shape
+    assert acc5.stride(1) == 1 and coef.is_contiguous() and c.is_contiguous() and h.is_contiguous()
+    with _op("gp_lstm_cell", 1):
+        check(lib().blm_gp_lstm_cell(_ptr(acc5), acc5.stride(0), _ptr(coef), coef.shape[0], gate_type, _ptr(lengths), t, B, H,
+                                     _ptr(c), _ptr(h), _ptr(h_op.hi), _ptr(h_op.lo), _ptr(out_f32),
+                                     _ptr(None if out is None else out.hi), _ptr(None if out is None else out.lo),
+                                     _stream()), "blm_gp_lstm_cell")
 
 
 # ------------------------------------------------------------------ fine-tune step (backward twins)

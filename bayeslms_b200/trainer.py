@@ -42,8 +42,6 @@ class FineTuner:
                  group=None):
         if model.family not in ("bayes_tm", "gauss_tm", "v_tm"):
             raise NotImplementedError("the fine-tune step is implemented for the Transformer families")
-        if getattr(model, "bayes_embed", False) or getattr(model, "bayes_pos", None) == "MHA":
-            raise NotImplementedError("fine-tuning the EMB / MHA Bayesian variants is not implemented yet")
         self.model, self.lr, self.momentum, self.clip, self.prec = model, float(lr), float(momentum), float(clip), prec
         self.group = group
         self.world = 1
@@ -124,7 +122,23 @@ class FineTuner:
 
         # ---------------------------------------------------------------- forward, activations kept
         pe = m.pos_encoder.pe.detach()[:, 0, :].float().contiguous()
-        x32, xs = ops.embed(tok, pos, m.encoder.weight.detach().float(), pe, math.sqrt(d), prec=prec)
+        emb_variant = getattr(m, "bayes_embed", False)
+        E_in = {}
+        if emb_variant:
+            # x = (E[tok] sqrt(d)) W~^T + pe with W~ = embed_mean + exp(embed_lgstd) eps (model.py:1284-1293)
+            _, x0s = ops.embed(tok, None, m.encoder.weight.detach().float(), None, math.sqrt(d), prec=prec, want_f32=False)
+            pe_rows, _ = ops.embed(pos, None, pe, None, 1.0, prec="bf16", want_f32=True)
+            ee = eps.get("embed")
+            sampled = ee is not None or seed is not None
+            w_in32 = (self._reparam32(m.embed_mean.detach(), m.embed_lgstd.detach(), _TID["embed"], ee, seed)
+                      if sampled else m.embed_mean.detach())
+            w_in, w_in_t = self._w2(w_in32)
+            x32 = self._f32(M, d)
+            xs = ops.empty_split(M, d, prec, dev)
+            ops.gemm(x0s, w_in, prec=prec, resid=pe_rows, out_f32=x32, out=xs, tag="embed_in")
+            E_in = {"x0s": x0s, "w_in_t": w_in_t, "eps": ee, "sampled": sampled}
+        else:
+            x32, xs = ops.embed(tok, pos, m.encoder.weight.detach().float(), pe, math.sqrt(d), prec=prec)
         saved = []
         for li, layer in enumerate(m.transformerlayers):
             kind, pre = layer.kind, f"transformerlayers.{li}."
@@ -132,13 +146,23 @@ class FineTuner:
             S = {"kind": kind, "x32": x32, "xs": xs}
             qkv32 = self._f32(M, 3 * d)
             qkvs = ops.empty_split(M, 3 * d, prec, dev)
-            wqkv, S["wqkv_t"] = self._w2(a.qkv_net.weight)
-            ops.gemm(xs, wqkv, prec=prec, bias=a.qkv_net.bias.detach(), col_scale=scale_q,
+            if kind == "bayes_mha":   # separate q / k / v projections, Bayesian bias-free o_net (model.py:931-1019)
+                wqkv32 = torch.cat([a.q_net.weight.detach(), a.k_net.weight.detach(), a.v_net.weight.detach()], 0)
+                bqkv = torch.cat([a.q_net.bias.detach(), a.k_net.bias.detach(), a.v_net.bias.detach()], 0)
+                le = eps.get(f"layer{li}")
+                S["wo_eps"], S["wo_sampled"] = le, (le is not None or seed is not None)
+                wo32 = (self._reparam32(a.o_net.weight_mean.detach(), a.o_net.weight_lgstd.detach(), _TID["mha_o"], le, seed)
+                        if S["wo_sampled"] else a.o_net.weight_mean.detach())
+                bo = None
+            else:
+                wqkv32, bqkv, wo32, bo = a.qkv_net.weight, a.qkv_net.bias.detach(), a.o_net.weight, a.o_net.bias.detach()
+            wqkv, S["wqkv_t"] = self._w2(wqkv32)
+            ops.gemm(xs, wqkv, prec=prec, bias=bqkv, col_scale=scale_q,
                      col_scale_cols=d, out_f32=qkv32, out=qkvs, tag="qkv")
             _, atts = ops.mha_causal_bf16(qkvs, offs, nhead, T, prec=prec)
             y1 = self._f32(M, d)
-            wo, S["wo_t"] = self._w2(a.o_net.weight)
-            ops.gemm(atts, wo, prec=prec, bias=a.o_net.bias.detach(), resid=x32, out_f32=y1, tag="o_net")
+            wo, S["wo_t"] = self._w2(wo32)
+            ops.gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net")
             x1_32, x1s = ops.layernorm(y1, layer.norm1.weight.detach(), layer.norm1.bias.detach(), layer.norm1.eps, prec=prec)
             S.update(qkv32=qkv32, atts=atts, y1=y1, x1_32=x1_32, x1s=x1s)
             # first FFN projection (+ GELU or the GP mixture), pre-activation kept
@@ -208,6 +232,12 @@ class FineTuner:
             S["y2"] = y2
             saved.append(S)
 
+        if emb_variant:   # F.linear(x, embed_mean.t()): mean only (model.py:1303)
+            xs_pre = xs
+            em, em_t = self._w2(m.embed_mean.detach())            # em [k, n] (dgrad operand), em_t = embed_mean^T (forward)
+            xs = ops.empty_split(M, d, prec, dev)
+            ops.gemm(xs_pre, em_t, prec=prec, out=xs, tag="embed_out")
+
         # ---------------------------------------------------------------- loss
         E32 = m.decoder.weight.detach().float()
         Es, Et = self._w2(E32)
@@ -228,6 +258,11 @@ class FineTuner:
         ops.gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
         self._wgrad(ops.transpose_bf16(dZ, prec), ops.transpose_bf16(xs, prec), g["decoder.weight"], "decoder")
         ops.colsum(dZ, g["decoder.bias"])
+        if emb_variant:   # back through x @ embed_mean: d embed_mean += x^T dout, dx = dout @ embed_mean^T
+            dout = dx
+            self._wgrad(ops.transpose_bf16(xs_pre, prec), ops.transpose_split(dout, prec), g["embed_mean"], "embed_out")
+            dx = self._f32(M, d)
+            ops.gemm(ops.split(dout, prec), em, prec=prec, out_f32=dx, tag="dgrad:embed_out")
 
         # ---------------------------------------------------------------- backward: layers
         for li in range(len(saved) - 1, -1, -1):
@@ -284,15 +319,46 @@ class FineTuner:
             dy1s = ops.split(dy1, prec)
             datt = self._f32(M, d)
             ops.gemm(dy1s, S["wo_t"], prec=prec, out_f32=datt, tag="dgrad:o_net")
-            self._wgrad(ops.transpose_split(dy1, prec), ops.transpose_bf16(S["atts"], prec), g[pre + "self_attn.o_net.weight"],
-                        "o_net")
-            ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
+            dy1t, attt = ops.transpose_split(dy1, prec), ops.transpose_bf16(S["atts"], prec)
+            if kind == "bayes_mha":
+                G, lin = g[pre + "self_attn.o_net.weight_mean"], a.o_net
+                self._wgrad(dy1t, attt, G, "o_net")
+                if S["wo_sampled"]:
+                    ops.reparam_bwd(G, lin.weight_lgstd.detach(), G, g[pre + "self_attn.o_net.weight_lgstd"], eps=S["wo_eps"],
+                                    seed=seed, stream_id=engine._stream_id(_TID["mha_o"], 0))
+                ops.kl_gauss(lin.weight_mean.detach(), lin.weight_lgstd.detach(), kl, accumulate=True)
+                ops.kl_gauss_bwd(lin.weight_mean.detach(), lin.weight_lgstd.detach(), kl_scale, G,
+                                 g[pre + "self_attn.o_net.weight_lgstd"])
+            else:
+                self._wgrad(dy1t, attt, g[pre + "self_attn.o_net.weight"], "o_net")
+                ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
             dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q)
             dx = self._f32(M, d)
             ops.gemm(ops.split(dqkv, prec), S["wqkv_t"], prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
-            self._wgrad(ops.transpose_split(dqkv, prec), ops.transpose_bf16(S["xs"], prec), g[pre + "self_attn.qkv_net.weight"],
-                        "qkv")
-            ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
+            dqkvt, xst = ops.transpose_split(dqkv, prec), ops.transpose_bf16(S["xs"], prec)
+            if kind == "bayes_mha":
+                for k, nm in enumerate(("q_net", "k_net", "v_net")):
+                    rows = slice(k * d, (k + 1) * d)
+                    part = Split(dqkvt.hi[rows], None if dqkvt.lo is None else dqkvt.lo[rows])
+                    self._wgrad(part, xst, g[pre + f"self_attn.{nm}.weight"], nm)
+                    ops.colsum(dqkv[:, rows], g[pre + f"self_attn.{nm}.bias"])
+            else:
+                self._wgrad(dqkvt, xst, g[pre + "self_attn.qkv_net.weight"], "qkv")
+                ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
+        if emb_variant:   # back through x0 W~^T: G = dx^T x0 (-> embed_mean, embed_lgstd), dx0 = dx W~
+            dxt, x0t = ops.transpose_split(dx, prec), ops.transpose_bf16(E_in["x0s"], prec)
+            if E_in["sampled"]:
+                G = self._f32(d, d)
+                self._wgrad(dxt, x0t, G, "embed_in")
+                ops.reparam_bwd(G, m.embed_lgstd.detach(), g["embed_mean"], g["embed_lgstd"], eps=E_in["eps"], seed=seed,
+                                stream_id=engine._stream_id(_TID["embed"], 0), accumulate=True)
+            else:   # added onto the output-side gradient already in place (residual operand = output)
+                ops.gemm(dxt, x0t, prec=prec, resid=g["embed_mean"], out_f32=g["embed_mean"], tag="wgrad:embed_in")
+            ops.kl_gauss(m.embed_mean.detach(), m.embed_lgstd.detach(), kl, accumulate=True)
+            ops.kl_gauss_bwd(m.embed_mean.detach(), m.embed_lgstd.detach(), kl_scale, g["embed_mean"], g["embed_lgstd"])
+            dx0 = self._f32(M, d)
+            ops.gemm(ops.split(dx, prec), E_in["w_in_t"], prec=prec, out_f32=dx0, tag="dgrad:embed_in")
+            dx = dx0
         # embedding: scatter-add on top of the decoder's weight gradient when the weights are tied
         ops.embed_bwd(dx, tok, math.sqrt(d), g["encoder.weight"])
         # loss = ce + kl * kl_scale

@@ -62,7 +62,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:

@@ -54,7 +54,10 @@ enum {
                         written as bf16 (hi, lo) so the logits themselves never exist */
   BLM_ACT_GELU_GRAD = 4,  /* z * gelu'(aux[m,n]): backward of BLM_ACT_GELU at the saved
                         pre-activation aux                                       */
-  BLM_ACT_GPMIX_GRAD = 5  /* z * sum_i coef[i,n] act_i'(aux[m,n]): backward of BLM_ACT_GPMIX */
+  BLM_ACT_GPMIX_GRAD = 5, /* z * sum_i coef[i,n] act_i'(aux[m,n]): backward of BLM_ACT_GPMIX */
+  BLM_ACT_GELU_FAST = 6   /* the same erf GELU evaluated in packed fp16 (two elements per
+                        instruction, <= 5e-4 relative): for bf16-hi-only outputs (fast mode),
+                        where the fp32 evaluation bounds the FFN1 epilogue            */
 };
 
 /* where the N(0,1) noise of a reparameterised tensor comes from */
@@ -288,6 +291,18 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
                    const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
                    int64_t H, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, float* hT,
                    float* cT, void* workspace, blm_stream stream);
+
+/* GP-LSTM cell update for one timestep (GPLSTMCell.Gplstm, model.py:1743-1777; gpnn_type <= 3,
+ * gate_type 1..4 = i, f, g, o).  acc5 [B, 5H] (ld): the four gate pre-activations followed by the GP
+ * unit's pre-activation z = W_g [x; h] + b_g, all produced by one blm_gemm on the concatenated weights
+ * [W_hh; W_g(h part)] with the hoisted input part as residual.  The chosen gate is replaced by
+ * sum_i coef[i, u] act_i(z), acts (sigmoid, tanh, relu)[:n_act] (model.py:1692-1697).  Updates c, h (fp32,
+ * in place, rows with t >= lengths[b] untouched), writes the bf16 operand copy of h for the next step and
+ * this step's output rows (zero where padded).                                                    */
+int blm_gp_lstm_cell(const float* acc5, int64_t ld, const float* coef, int32_t n_act, int32_t gate_type,
+                     const int32_t* lengths, int32_t t, int64_t B, int32_t H, float* c, float* h,
+                     blm_bf16* h_hi, blm_bf16* h_lo, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo,
+                     blm_stream stream);
 
 /* ------------------------------------------------- fine-tune step (train.py:306-438)
  * Backward twins of the kernels above and the optimiser.  The contractions of the backward pass

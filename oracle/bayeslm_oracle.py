@@ -45,7 +45,7 @@ SD = Dict[str, Tensor]
 
 # --------------------------------------------------------------------------- config
 class Config(dict):
-    """family: 'bayes_tm' | 'gauss_tm' | 'v_tm' | 'bayes_lstm'; plus ntoken, ninp, nhead,
+    """family: 'bayes_tm' | 'gauss_tm' | 'v_tm' | 'bayes_lstm' | 'gauss_lstm' | 'v_lstm'; plus ntoken, ninp, nhead,
     nhid, nlayers and the family's position flag (bayes_pos / gauss_pos / v_pos)."""
     __getattr__ = dict.__getitem__
 
@@ -253,7 +253,11 @@ def lstm_layer(x: Tensor, h: Tensor, c: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih
 def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Config,
                 eps: Optional[Dict[str, Tensor]] = None, return_hidden_states: bool = False):
     """BayesRNNModel.forward in eval / injected-noise mode, model.py:217-222 + 783-828.
-    tokens (T, B); hidden = (h, c) each (2, B, H).  Returns logits (T, B, V), (h, c)."""
+    tokens (T, B); hidden = (h, c) each (2, B, H).  Returns logits (T, B, V), (h, c).
+    The GP / Variational cell families (eval mode) are routed to ``cell_rnn_forward``."""
+    if cfg.family in ("gauss_lstm", "v_lstm"):
+        assert not return_hidden_states
+        return cell_rnn_forward(sd, tokens, hidden, cfg)
     p = lstm_flat_parameters(sd, cfg.bayes_pos, eps)
     x = F.embedding(tokens, sd["encoder.weight"])
     h0, c0 = hidden
@@ -267,6 +271,75 @@ def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Conf
     if return_hidden_states:
         return x, new_hidden
     return F.linear(x, sd["decoder.weight"], sd["decoder.bias"]), new_hidden
+
+
+# ---------------------------------------------------------------- GP-LSTM / Variational-LSTM cells
+LSTM_GP_ACTS = {1: ("sigmoid", "tanh", "relu"), 2: ("sigmoid",), 3: ("sigmoid", "tanh", "relu"),
+                4: ("sigmoid", "tanh", "relu")}   # act_set per gate_type, model.py:1690-1697 (+ GPNN default 1787)
+
+
+def gp_lstm_layout(gauss_pos: str) -> List[Tuple[str, int, int]]:
+    """Members of GPLSTM.rnn for the ``--L_gauss_pos`` string (model.py:1619-1636):
+    ('gp', gate_type, gpnn_type) or ('lstm', n_layers, 0)."""
+    t = gauss_pos
+    if int(t[0]) == 0:
+        return [("lstm", 2, 0)]
+    if len(t) == 2:
+        return [("gp", int(t[0]), int(t[1])), ("lstm", 1, 0)]
+    if len(t) == 3:
+        return [("lstm", 1, 0), ("gp", int(t[0]), int(t[1]))]
+    return [("gp", int(t[0]), int(t[1])), ("gp", int(t[2]), int(t[1]))]
+
+
+def gp_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, gate_type: int):
+    """GPLSTMCell.forward / Gplstm in eval mode (posterior means), model.py:1720-1777, gate_type 1..4:
+    gates = W_ih x + b_ih + W_hh h + b_ih (bias_ih twice, bias_hh never); the chosen gate is replaced by
+    GPNN(cat[x, h]) = sum_i coef[i] * act_i(W_g cat[x, h] + b_g)."""
+    acts = LSTM_GP_ACTS[gate_type]
+    outs = []
+    for t in range(x.shape[0]):
+        gates = F.linear(x[t], sd[pre + "weights_ih"], sd[pre + "bias_ih"]) + F.linear(h, sd[pre + "weights_hh"], sd[pre + "bias_ih"])
+        i, f, g, o = gates.chunk(4, 1)
+        z = F.linear(torch.cat([x[t], h], -1), sd[pre + "gpnn.weights_mean"], sd[pre + "gpnn.bias_mean"])
+        gp = sum(getattr(torch, a)(z) * sd[pre + "gpnn.coef_mean"][k] for k, a in enumerate(acts))
+        i = gp if gate_type == 1 else torch.sigmoid(i)
+        f = gp if gate_type == 2 else torch.sigmoid(f)
+        g = gp if gate_type == 3 else torch.tanh(g)
+        o = gp if gate_type == 4 else torch.sigmoid(o)
+        c = f * c + i * g
+        h = o * torch.tanh(c)
+        outs.append(h)
+    return torch.stack(outs), h, c
+
+
+def cell_rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Config):
+    """GaussRNNModel.forward (model.py:1354-1359, GPLSTM.forward 1638-1671) and VariationalRNNModel.forward
+    (model.py:2411-2416, VariationalLSTM.forward 2447-2468) in eval mode.  Returns logits (T, B, V), (h, c)."""
+    x = F.embedding(tokens, sd["encoder.weight"])
+    h0, c0 = hidden
+    hs, cs, li = [], [], 0
+    if cfg.family == "gauss_lstm":
+        for mi, (kind, a, _) in enumerate(gp_lstm_layout(cfg.gauss_pos)):
+            pre = f"rnn.rnn.{mi}."
+            if kind == "gp":
+                x, h, c = gp_lstm_cell_layer(x, h0[li], c0[li], sd, pre, a)
+                hs.append(h), cs.append(c)
+                li += 1
+            else:
+                for l in range(a):
+                    x, h, c = lstm_layer(x, h0[li], c0[li], sd[f"{pre}weight_ih_l{l}"], sd[f"{pre}weight_hh_l{l}"],
+                                         sd[f"{pre}bias_ih_l{l}"], sd[f"{pre}bias_hh_l{l}"])
+                    hs.append(h), cs.append(c)
+                    li += 1
+    elif cfg.family == "v_lstm":
+        for mi in range(2):   # VLSTMCell.lstmcell, model.py:2515-2531: bias_ih on both products
+            pre = f"rnn.rnn.{mi}."
+            x, h, c = lstm_layer(x, h0[mi], c0[mi], sd[pre + "weights_ih"], sd[pre + "weights_hh"], sd[pre + "bias_ih"],
+                                 sd[pre + "bias_ih"])
+            hs.append(h), cs.append(c)
+    else:
+        raise ValueError(cfg.family)
+    return F.linear(x, sd["decoder.weight"], sd["decoder.bias"]), (torch.stack(hs), torch.stack(cs))
 
 
 def init_hidden(cfg: Config, bsz: int) -> Tuple[Tensor, Tensor]:

@@ -202,3 +202,24 @@ def test_transposes_and_colsum(ops, R, C):
     _close(out, 0.5 * x.double().sum(0), 1e-5)
     ops.colsum(s, out, accumulate=True)
     _close(out, 1.5 * x.double().sum(0), 3e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(4500, 520, 328), (2048, 128, 64), (8192, 512, 4096)])
+def test_cluster_sampled_gemm_bit_exact(ops, M, N, K):
+    """The 4-CTA-cluster variant of blm_gemm_sampled (generated W~ quarters pushed through DSMEM):
+    bit-identical to bf16(mu + sigma * eps) fed to the plain GEMM, for injected and Philox noise,
+    with ragged M groups / N tiles / K blocks."""
+    a = torch.randn(M, K, device=DEV) * 0.5
+    mu = torch.randn(N, K, device=DEV) * 0.05
+    ls = torch.rand(N, K, device=DEV) * -3.0 - 2.0
+    A, mu_b, sg_b = ops.split(a, "bf16"), ops.split(mu, "bf16").hi, ops.sigma_bf16(ls)
+    resid = torch.randn(M, N, device=DEV)
+    for mode in ("ptr", "philox"):
+        eps = torch.randn(N, K, device=DEV) if mode == "ptr" else ops.philox_normal(11, 4, N * K, DEV).view(N, K)
+        out = torch.empty(M, N, device=DEV)
+        ops.gemm_sampled(A, mu_b, sg_b, eps=eps if mode == "ptr" else None, seed=None if mode == "ptr" else 11,
+                         stream_id=4, resid=resid, out_f32=out)
+        wt = torch.addcmul(mu_b.float(), sg_b.float(), eps).to(torch.bfloat16)
+        ref = torch.empty(M, N, device=DEV)
+        ops.gemm(A, ops.Split(wt), prec="bf16", resid=resid, out_f32=ref, k_chunk=0)
+        assert torch.equal(out, ref), mode

@@ -99,3 +99,46 @@ def test_many_rows_ragged_lengths_two_sessions():
     assert np.abs(got - want).max() < 1e-3
     got_fast = Rescorer(net, prec="bf16", max_tokens=3000).score_sessions(sessions)
     assert np.abs(got_fast - want).max() < 5e-2 + 2e-3 * np.abs(want).max()
+
+
+CELL_FIXTURES = ["gauss_lstm_31", "gauss_lstm_23", "gauss_lstm_13", "gauss_lstm_43", "gauss_lstm_333",
+                 "gauss_lstm_3330", "v_lstm_11", "v_lstm_01"]
+
+
+@pytest.mark.parametrize("name", CELL_FIXTURES)
+def test_gp_and_variational_cells_match_reference_golden(golden, name):
+    """GP-LSTM (gate replaced by the GP unit, doubled bias_ih) and Variational-LSTM cells,
+    eval mode, against the reference's own outputs."""
+    rec = golden(name + ".pt")
+    net = load_golden_model(rec, DEV)
+    h0 = tuple(t.to(DEV) for t in rec["h0"])
+    out, (h, c) = net(rec["x"].to(DEV), h0)
+    assert (out.cpu() - rec["logits_eval"]).abs().max().item() < 1e-3
+    assert (h.cpu() - rec["hidden_eval"][0]).abs().max().item() < 1e-4
+    assert (c.cpu() - rec["hidden_eval"][1]).abs().max().item() < 1e-4
+    if "kl" in rec and rec["kl"]:
+        cells = [m for m in net.rnn.rnn if hasattr(m, "gpnn")]
+        for cell, ref in zip(cells, rec["kl"]):
+            if ref:
+                assert abs(float(cell.gpnn.kl_divergence()) - ref) <= 1e-4 * abs(ref)
+
+
+@pytest.mark.parametrize("name", ["gauss_lstm_31", "gauss_lstm_3330", "v_lstm_11"])
+def test_cell_models_session_scoring_matches_oracle(golden, name):
+    """The session scheduler (hidden carry through hypothesis #0, ragged lock-step batches) with GP / V cells
+    against the oracle's restatement of the reference scoring loop."""
+    from bayeslms_b200.scorer import Rescorer, ids_for
+    rec = golden(name + ".pt")
+    loop = golden("scorer_loop.pt")
+    vocab = {w: i for i, w in enumerate(loop["vocab_words"])}
+    nbest = OrderedDict()
+    for line in loop["nbest_lines"]:
+        key, _, hyp = line.partition(" ")
+        nbest.setdefault(key.rsplit("-", 1)[0], []).append(hyp or " ")
+    cfg = O.Config(rec["cfg"])
+    want = O.compute_scores(nbest, vocab, rec["state_dict"], cfg)
+    want = np.asarray([s for items in want.values() for _, s in items])
+    net = load_golden_model(rec, DEV)
+    sessions = [[[ids_for(h, vocab) for h in hyps] for hyps in nbest.values()]]
+    got = Rescorer(net, prec="bf16x3").score_sessions(sessions)
+    assert np.abs(got - want).max() < 1e-3

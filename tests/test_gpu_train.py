@@ -53,6 +53,8 @@ def _oracle_step(sd, cfg, x, y, eps, kl_scale, lr, clip):
 
 CASES = [
     ("bayes_tm", 2, {"bayes_pos": "FFN"}, 12),
+    ("bayes_tm", 2, {"bayes_pos": "MHA"}, 12),
+    ("bayes_tm", 2, {"bayes_pos": "EMB"}, 12),
     ("gauss_tm", 2, {"gauss_pos": 3}, 12),
     ("gauss_tm", 2, {"gauss_pos": 1}, 12),
     ("v_tm", 4, {"v_pos": 3}, 100),

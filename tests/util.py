@@ -17,6 +17,10 @@ def build_from_cfg(cfg, device=None):
     elif fam == "bayes_lstm":
         net = M.BayesRNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, True,
                               cfg["bayes_pos"])
+    elif fam == "gauss_lstm":
+        net = M.GaussRNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, False, cfg["gauss_pos"])
+    elif fam == "v_lstm":
+        net = M.VariationalRNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, True, cfg["v_pos"])
     else:
         raise ValueError(fam)
     return net if device is None else net.to(device)
