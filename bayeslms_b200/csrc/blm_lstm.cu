@@ -26,7 +26,8 @@
 
 namespace blm {
 
-constexpr int kLStages = 5;      // h-tile ring depth
+constexpr int kLStages = 5;      // h-tile ring depth with one K block per stage (16 KB stages)
+constexpr int kLStages2 = 3;     // ... with two K blocks per stage (32 KB stages): fewer, larger round trips
 constexpr int kLThreads = 384;   // 4 control warps + 8 epilogue warps (two per scheduler, alternate tiles)
 constexpr int kLMaxTiles = 16;   // per CTA: 16 x 32 (U = 8) or 8 x 64 (U = 16) TMEM columns = 512
 constexpr int kLABytes = 128 * 64 * 2;
@@ -112,8 +113,14 @@ __device__ __forceinline__ void store_h8(__nv_bfloat16* hi, __nv_bfloat16* lo, c
 // fetched ONCE per cluster -- CTA r loads rows [32 r, 32 r + 32) of the 128-row tile with TMA multicast
 // into all kCL CTAs -- and a ring slot is released by multicast tcgen05.commit from all kCL MMA warps.
 // The L2 -> SM traffic of the step (every CTA needs all of h_{t-1} of its batch block) drops kCL-fold.
-template <int kU, int kCL>
+// kSub: K blocks per ring stage.  The ring's throughput is bytes in flight / round-trip time, and the round
+// trip (commit -> producer wake-up -> TMA issue -> L2 -> mbarrier -> MMA) is mostly fixed cost: 32 KB stages
+// move twice the bytes per trip in the same shared memory (3 x 32 KB instead of 5 x 16 KB).
+template <int kU, int kCL, int kSub>
 __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_constant__ LstmParams p) {
+  constexpr int kNStages = kSub == 2 ? kLStages2 : kLStages;
+  constexpr int kStageBytes = kSub * kLABytes;
+  static_assert(kSub == 1 || kCL == 1, "the cluster experiment keeps one K block per stage");
   constexpr int kLN = 4 * kU;            // MMA N: 4 gates x U units
   constexpr int kLWTile = kLN * 64 * 2;  // one K block of the W slice
   extern __shared__ uint8_t smem_raw[];
@@ -122,9 +129,9 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   const int w_bytes = p.kblocks * kLWTile;
   uint8_t* sW[2] = {smem, smem + w_bytes};
   uint8_t* sA = smem + (p.nsplit == 3 ? 2 : 1) * w_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kLStages * kLABytes);
-  uint64_t* empty_bar = full_bar + kLStages;
-  uint64_t* tfull_bar = empty_bar + kLStages;  // [kLMaxTiles]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kNStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kNStages;
+  uint64_t* tfull_bar = empty_bar + kNStages;  // [kLMaxTiles]
   uint64_t* w_bar = tfull_bar + kLMaxTiles;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   const int row_lo = mt0 * 128, row_hi = min(B, (mt0 + n_mt) * 128);
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kLStages; ++s) {
+    for (int s = 0; s < kNStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kCL);
     }
@@ -198,20 +205,22 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
         fence_proxy_async_all();  // h_{t-1} was written with generic stores by other SMs
         for (int mt = 0; mt < n_mt; ++mt)
           for (int part = 0; part < a_parts; ++part)
-            for (int kbi = 0; kbi < p.kblocks; ++kbi) {
-              const int kb = (kbi + kb_rot) % p.kblocks;  // staggered K order: CTAs do not hit the same lines at once
+            for (int kbi = 0; kbi < p.kblocks; kbi += kSub) {
+              const int kb = (kbi + kb_rot) % p.kblocks;  // staggered K order (experiment, kSub == 1 only)
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[stage], kLABytes);
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
               if constexpr (kCL > 1) {
                 constexpr int kQ = 128 / kCL;  // rows of the tile this CTA fetches for the whole cluster
-                tma_load_2d_multicast(sA + stage * kLABytes + crank * (kQ * 128), &p.tmH[cur][part], &full_bar[stage],
+                tma_load_2d_multicast(sA + stage * kStageBytes + crank * (kQ * 128), &p.tmH[cur][part], &full_bar[stage],
                                       kb * 64, (mt0 + mt) * 128 + static_cast<int>(crank) * kQ,
                                       static_cast<uint16_t>((1u << kCL) - 1u), kEvictNormal);
               } else {
-                tma_load_2d(sA + stage * kLABytes, &p.tmH[cur][part], &full_bar[stage], kb * 64, (mt0 + mt) * 128,
-                            kEvictNormal);
+#pragma unroll
+                for (int sub = 0; sub < kSub; ++sub)
+                  tma_load_2d(sA + stage * kStageBytes + sub * kLABytes, &p.tmH[cur][part], &full_bar[stage],
+                              (kb + sub) * 64, (mt0 + mt) * 128, kEvictNormal);
               }
-              if (++stage == kLStages) {
+              if (++stage == kNStages) {
                 stage = 0;
                 phase ^= 1u;
               }
@@ -226,28 +235,32 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kLN);
           uint32_t accum = 0;
           for (int part = 0; part < a_parts; ++part)
-            for (int kbi = 0; kbi < p.kblocks; ++kbi) {
-              const int kb = (kbi + kb_rot) % p.kblocks;
+            for (int kbi = 0; kbi < p.kblocks; kbi += kSub) {
+              const int kb0 = (kbi + kb_rot) % p.kblocks;
               mbar_wait(&full_bar[stage], phase);
               tcgen05_fence_after();
-              const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kLABytes));
-              const uint64_t dw_hi = umma_desc_sw128(smem_u32(sW[0] + kb * kLWTile));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_hi + static_cast<uint64_t>(2 * k), idesc, accum);
-                accum = 1;
-              }
-              if (part == 0 && p.nsplit == 3) {  // h_hi . W_lo
-                const uint64_t dw_lo = umma_desc_sw128(smem_u32(sW[1] + kb * kLWTile));
+              for (int sub = 0; sub < kSub; ++sub) {
+                const int kb = kb0 + sub;
+                const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kStageBytes + sub * kLABytes));
+                const uint64_t dw_hi = umma_desc_sw128(smem_u32(sW[0] + kb * kLWTile));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_hi + static_cast<uint64_t>(2 * k), idesc, accum);
+                  accum = 1;
+                }
+                if (part == 0 && p.nsplit == 3) {  // h_hi . W_lo
+                  const uint64_t dw_lo = umma_desc_sw128(smem_u32(sW[1] + kb * kLWTile));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), dw_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+                }
               }
               if constexpr (kCL > 1)
                 umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << kCL) - 1u));
               else
                 umma_commit(&empty_bar[stage]);
-              if (++stage == kLStages) {
+              if (++stage == kNStages) {
                 stage = 0;
                 phase ^= 1u;
               }
@@ -341,17 +354,22 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-static size_t lstm_smem_bytes(int kblocks, int nsplit, int U) {
-  return static_cast<size_t>((nsplit == 3 ? 2 : 1) * kblocks * (4 * U * 128) + kLStages * kLABytes +
-                             (2 * kLStages + kLMaxTiles + 1) * 8 + 16 + 1024);
+static size_t lstm_smem_bytes(int kblocks, int nsplit, int U, int sub = 1) {
+  const int stages = sub == 2 ? kLStages2 : kLStages;
+  return static_cast<size_t>((nsplit == 3 ? 2 : 1) * kblocks * (4 * U * 128) + stages * sub * kLABytes +
+                             (2 * stages + kLMaxTiles + 1) * 8 + 16 + 1024);
 }
 
 int lstm_init() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 3, 8))));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16))));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<8, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 3, 8, 2))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 1, 16, 2))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16))));
   return BLM_OK;
 }
@@ -455,11 +473,17 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_layer_kernel<16, 4>, p));
+    BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_layer_kernel<16, 4, 1>, p));
     return BLM_OK;
   }
-  void* fn = U == 16 ? reinterpret_cast<void*>(lstm_layer_kernel<16, 1>) : reinterpret_cast<void*>(lstm_layer_kernel<8, 1>);
-  BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, lstm_smem_bytes(p.kblocks, p.nsplit, U), st));
+  static const bool no_sub2 = getenv("BLM_LSTM_NO_SUB2") != nullptr;  // A/B switch for profiling
+  const int sub = (!no_sub2 && (p.kblocks % 2) == 0 && !p.kb_stagger) ? 2 : 1;
+  void* fn;
+  if (U == 16)
+    fn = sub == 2 ? reinterpret_cast<void*>(lstm_layer_kernel<16, 1, 2>) : reinterpret_cast<void*>(lstm_layer_kernel<16, 1, 1>);
+  else
+    fn = sub == 2 ? reinterpret_cast<void*>(lstm_layer_kernel<8, 1, 2>) : reinterpret_cast<void*>(lstm_layer_kernel<8, 1, 1>);
+  BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, lstm_smem_bytes(p.kblocks, p.nsplit, U, sub), st));
   return BLM_OK;
 }
 

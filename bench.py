@@ -333,6 +333,20 @@ def main():
     step(prec="bf16x3")
     px_ms = timed(lambda: step(prec="bf16x3"), k4_steps)
 
+    # ---- BASELINE config 3: GP Transformer (T_gauss_pos=3) on the same lists, posterior mean, bf16
+    from bayeslms_b200 import model as M
+    torch.manual_seed(1111)
+    gp_net = M.GaussTransformerModel(V, D, NHEAD, FF, NLAYERS, 0.5, True, 3).to(dev).eval()
+
+    def gp_step():
+        res = torch.cat([gp_net.score(b, prec="bf16") for b in batches])
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, res)
+
+    gp_step()
+    gp_ms = timed(gp_step, k4_steps)
+    del gp_net
+
     # ---- fast-vs-precise agreement on this step's lists (ranking evidence)
     fast = step().float().cpu().numpy()
     precise = step(prec="bf16x3").float().cpu().numpy()
@@ -381,6 +395,9 @@ def main():
                         "max_abs_score_diff_vs_bf16": float(np.abs(fast - precise).max()),
                         "one_best_agreement": float(np.mean(np.asarray(picks_f) == np.asarray(picks_p))),
                         "synthetic_wer": wer_p},
+            "gp_tm_rescoring": {"value": n_tokens * world * k4_steps / (gp_ms / 1e3), "unit": "tokens/s",
+                                "workload": "GP Transformer LM T_gauss_pos=3 (GP activation mixture in layer 0), same lists, "
+                                            "posterior mean, bf16"},
             "finetune_step": finetune,
             "lstm_rescoring": lstm,
             "cpu_baseline": cpu,

@@ -223,3 +223,24 @@ def test_cluster_sampled_gemm_bit_exact(ops, M, N, K):
         ref = torch.empty(M, N, device=DEV)
         ops.gemm(A, ops.Split(wt), prec="bf16", resid=resid, out_f32=ref, k_chunk=0)
         assert torch.equal(out, ref), mode
+
+
+def test_fast_gelu_epilogue(ops):
+    """BLM_ACT_GELU_FAST (packed fp16 evaluation, bf16-hi output): within bf16 rounding of the exact GELU."""
+    M, N, K = 3000, 4096, 512
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    bias = torch.randn(N, device=DEV)
+    A, B = ops.split(a, "bf16"), ops.split(b, "bf16")
+    out = ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm(A, B, prec="bf16", bias=bias, act=ops.ACT_GELU_FAST, out=out)
+    z = A.hi.double() @ B.hi.double().T + bias.double()
+    ref = torch.nn.functional.gelu(z)
+    err = (out.hi.double() - ref).abs()
+    assert (err <= 4.5e-3 * ref.abs() + 1.5e-3).all(), (err.max().item(),)        # bf16 ulp/2 + fp16 evaluation
+    exact = ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm(A, B, prec="bf16", bias=bias, act=ops.ACT_GELU, out=exact)
+    # the two variants agree to within one bf16 ulp almost everywhere
+    diff = (out.hi.float() - exact.hi.float()).abs()
+    assert (diff <= 8e-3 * exact.hi.float().abs() + 2e-3).all()
+    assert (diff == 0).float().mean().item() > 0.8
