@@ -28,7 +28,8 @@ namespace blm {
 
 constexpr int kSBN = 128;        // N tile
 constexpr int kSMT = 4;          // M tiles per work item (accumulators resident in TMEM)
-constexpr int kSAStages = 6;     // A ring: 6 x 16 KB
+constexpr int kSAPairStages = 3; // A ring: 3 x 32 KB (two M tiles per stage: the ring's throughput is bytes in
+                                 // flight per round trip, and the round trip is mostly fixed cost)
 constexpr int kSWStages = 3;     // (mu | sigma) ring: 3 x 32 KB
 constexpr int kSThreads = 512;
 constexpr int kSGenWarp0 = 8;
@@ -47,10 +48,10 @@ struct SampledParams {
 
 struct SampledSmem {
   static constexpr int kAOff = 0;
-  static constexpr int kWOff = kSAStages * kSTile;
+  static constexpr int kWOff = kSAPairStages * 2 * kSTile;
   static constexpr int kBarOff = kWOff + kSWStages * 2 * kSTile;
-  // a_full[6] a_empty[6] w_full[3] w_ready[3] w_empty[3] t_full t_empty + tmem slot
-  static constexpr int kBytes = kBarOff + (2 * kSAStages + 3 * kSWStages + 2) * 8 + 16;
+  // a_full[3] a_empty[3] w_full[3] w_ready[3] w_empty[3] t_full t_empty + tmem slot
+  static constexpr int kBytes = kBarOff + (2 * kSAPairStages + 3 * kSWStages + 2) * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;
 };
 
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* a_empty = a_full + kSAStages;
-  uint64_t* w_full = a_empty + kSAStages;    // TMA landed mu | sigma
+  uint64_t* a_empty = a_full + kSAPairStages;
+  uint64_t* w_full = a_empty + kSAPairStages;    // TMA landed mu | sigma
   uint64_t* w_ready = w_full + kSWStages;    // generators wrote W~ over mu
   uint64_t* w_empty = w_ready + kSWStages;   // MMAs that read W~ retired
   uint64_t* t_full = w_empty + kSWStages;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
     tma_prefetch_desc(&p.tmSig);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kSAStages; ++s) {
+    for (int s = 0; s < kSAPairStages; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
     }
@@ -102,13 +103,37 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA: mu | sigma tiles, A tiles
+    // ---------------------------------------------------------------- TMA: A tiles (two M tiles per stage)
     if (lane == 0) {
-      int sa = 0, sw = 0;
-      uint32_t pa = 0, pw = 0;
+      int sa = 0;
+      uint32_t pa = 0;
       for (int w = blockIdx.x; w < num_works; w += gridDim.x) {
         const int m_group = w / p.g.n_tiles;
-        const int n_tile = w - m_group * p.g.n_tiles;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          for (int mt = 0; mt < kSMT; mt += 2) {
+            mbar_wait(&a_empty[sa], pa ^ 1u);
+            mbar_arrive_expect_tx(&a_full[sa], 2 * kSTile);
+            tma_load_2d(smem + L::kAOff + sa * 2 * kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK,
+                        (m_group * kSMT + mt) * kBM, kEvictNormal);
+            tma_load_2d(smem + L::kAOff + sa * 2 * kSTile + kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK,
+                        (m_group * kSMT + mt + 1) * kBM, kEvictNormal);
+            if (++sa == kSAPairStages) {
+              sa = 0;
+              pa ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ---------------------------------------------------------------- TMA: mu | sigma tiles (own thread: the A
+    // stream must never wait for a W slot)
+    if (lane == 0) {
+      int sw = 0;
+      uint32_t pw = 0;
+      for (int w = blockIdx.x; w < num_works; w += gridDim.x) {
+        const int n_tile = w % p.g.n_tiles;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&w_empty[sw], pw ^ 1u);
           uint8_t* wt = smem + L::kWOff + sw * 2 * kSTile;
@@ -118,16 +143,6 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
           if (++sw == kSWStages) {
             sw = 0;
             pw ^= 1u;
-          }
-          for (int mt = 0; mt < kSMT; ++mt) {
-            mbar_wait(&a_empty[sa], pa ^ 1u);
-            mbar_arrive_expect_tx(&a_full[sa], kSTile);
-            tma_load_2d(smem + L::kAOff + sa * kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK,
-                        (m_group * kSMT + mt) * kBM, kEvictNormal);
-            if (++sa == kSAStages) {
-              sa = 0;
-              pa ^= 1u;
-            }
           }
         }
       }
@@ -146,17 +161,20 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_kernel(const __grid
           mbar_wait(&w_ready[sw], pw);
           tcgen05_fence_after();
           const uint64_t db = umma_desc_sw128(smem_u32(smem + L::kWOff + sw * 2 * kSTile));
-          for (int mt = 0; mt < kSMT; ++mt) {
+          for (int mt = 0; mt < kSMT; mt += 2) {
             mbar_wait(&a_full[sa], pa);
             tcgen05_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(smem + L::kAOff + sa * kSTile));
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kSBN);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const uint64_t da = umma_desc_sw128(smem_u32(smem + L::kAOff + sa * 2 * kSTile + h2 * kSTile));
+              const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((mt + h2) * kSBN);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit(&a_empty[sa]);
-            if (++sa == kSAStages) {
+            if (++sa == kSAPairStages) {
               sa = 0;
               pa ^= 1u;
             }
@@ -294,11 +312,11 @@ constexpr int kCQBytes = kCQRows * 128;   // 4 KB
 
 struct ClusterSmem {
   static constexpr int kAOff = 0;
-  static constexpr int kWOff = kSAStages * kSTile;
+  static constexpr int kWOff = kSAPairStages * 2 * kSTile;
   static constexpr int kGOff = kWOff + kCWStages * kSTile;           // scratch: mu quarter | sigma quarter
   static constexpr int kBarOff = kGOff + kCWStages * 2 * kCQBytes;
   // a_full[6] a_empty[6] g_full[3] w_ready[3] w_empty[3] t_full t_empty + tmem slot
-  static constexpr int kBytes = kBarOff + (2 * kSAStages + 3 * kCWStages + 2) * 8 + 16;
+  static constexpr int kBytes = kBarOff + (2 * kSAPairStages + 3 * kCWStages + 2) * 8 + 16;
   static constexpr int kDynBytes = kBytes + 1024;
 };
 
@@ -311,8 +329,8 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_cluster_kernel(cons
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* a_empty = a_full + kSAStages;
-  uint64_t* g_full = a_empty + kSAStages;    // TMA landed this CTA's mu | sigma quarter
+  uint64_t* a_empty = a_full + kSAPairStages;
+  uint64_t* g_full = a_empty + kSAPairStages;    // TMA landed this CTA's mu | sigma quarter
   uint64_t* w_ready = g_full + kCWStages;    // all four W~ quarters landed in this CTA's ring slot
   uint64_t* w_empty = w_ready + kCWStages;   // all four CTAs' MMAs retired their reads of the slot
   uint64_t* t_full = w_empty + kCWStages;
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_cluster_kernel(cons
     tma_prefetch_desc(&p.tmSig);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kSAStages; ++s) {
+    for (int s = 0; s < kSAPairStages; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
     }
@@ -360,12 +378,14 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_cluster_kernel(cons
       for (int w = cluster_id; w < num_works; w += n_clusters) {
         const int m_group = (w / p.g.n_tiles) * kCL + static_cast<int>(rank);
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          for (int mt = 0; mt < kSMT; ++mt) {
+          for (int mt = 0; mt < kSMT; mt += 2) {
             mbar_wait(&a_empty[sa], pa ^ 1u);
-            mbar_arrive_expect_tx(&a_full[sa], kSTile);
-            tma_load_2d(smem + L::kAOff + sa * kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK, (m_group * kSMT + mt) * kBM,
-                        kEvictNormal);
-            if (++sa == kSAStages) {
+            mbar_arrive_expect_tx(&a_full[sa], 2 * kSTile);
+            tma_load_2d(smem + L::kAOff + sa * 2 * kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK,
+                        (m_group * kSMT + mt) * kBM, kEvictNormal);
+            tma_load_2d(smem + L::kAOff + sa * 2 * kSTile + kSTile, &p.g.tmA[0], &a_full[sa], kb * kBK,
+                        (m_group * kSMT + mt + 1) * kBM, kEvictNormal);
+            if (++sa == kSAPairStages) {
               sa = 0;
               pa ^= 1u;
             }
@@ -410,17 +430,20 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_sampled_cluster_kernel(cons
           mbar_wait(&w_ready[sw], pw);
           tcgen05_fence_after();
           const uint64_t db = umma_desc_sw128(smem_u32(smem + L::kWOff + sw * kSTile));
-          for (int mt = 0; mt < kSMT; ++mt) {
+          for (int mt = 0; mt < kSMT; mt += 2) {
             mbar_wait(&a_full[sa], pa);
             tcgen05_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(smem + L::kAOff + sa * kSTile));
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kSBN);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const uint64_t da = umma_desc_sw128(smem_u32(smem + L::kAOff + sa * 2 * kSTile + h2 * kSTile));
+              const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((mt + h2) * kSBN);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit(&a_empty[sa]);
-            if (++sa == kSAStages) {
+            if (++sa == kSAPairStages) {
               sa = 0;
               pa ^= 1u;
             }
