@@ -25,62 +25,6 @@
 
 namespace blm {
 
-struct NllState {
-  float run_max;  // log2 domain: fl(max logit * log2 e)
-  float run_sum, tgt_logit;
-  int tgt;
-};
-
-// online log-sum-exp over one 32-column chunk of logits (natural-log units; exponentials via ex2)
-// sb: the chunk's 32 bias values in shared memory (zero where there is no bias / past column N)
-__device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], int col0, NllState& st,
-                                          const float* sb) {
-  constexpr float kLog2e = 1.4426950408889634f;
-  if (p.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(sb + j);
-      v[j] += bb.x;
-      v[j + 1] += bb.y;
-      v[j + 2] += bb.z;
-      v[j + 3] += bb.w;
-    }
-  }
-  if (col0 + 32 > p.N) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j >= p.N) v[j] = -INFINITY;
-  }
-  const unsigned int rel = static_cast<unsigned int>(st.tgt - col0);
-  if (rel < 32u) {  // the target column lives in this chunk: once per row per sweep
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (rel == static_cast<unsigned int>(j)) st.tgt_logit = v[j];
-  }
-  float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
-#pragma unroll
-  for (int j = 8; j < 32; j += 8) {
-    m0 = fmaxf(m0, fmaxf(v[j], v[j + 1]));
-    m1 = fmaxf(m1, fmaxf(v[j + 2], v[j + 3]));
-    m2 = fmaxf(m2, fmaxf(v[j + 4], v[j + 5]));
-    m3 = fmaxf(m3, fmaxf(v[j + 6], v[j + 7]));
-  }
-  // running maximum kept in the log2 domain as the ROUNDED product max * log2(e): every term and
-  // every rescale is then measured against exactly the same power of two (a rescale by the
-  // unchanged maximum is exactly 1, so nothing compounds over the ~1000 chunks of a row)
-  const float new_m2 = fmaxf(st.run_max, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * kLog2e);
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    s0 += ex2_approx(fmaf(v[j], kLog2e, -new_m2));
-    s1 += ex2_approx(fmaf(v[j + 1], kLog2e, -new_m2));
-    s2 += ex2_approx(fmaf(v[j + 2], kLog2e, -new_m2));
-    s3 += ex2_approx(fmaf(v[j + 3], kLog2e, -new_m2));
-  }
-  st.run_sum = st.run_sum * ex2_approx(st.run_max - new_m2) + ((s0 + s1) + (s2 + s3));
-  st.run_max = new_m2;
-}
-
 // CHUNK: the tensor core adds into its fp32 accumulator with truncation, one truncation per
 // 16-wide K step, which shrinks every output by ~2e-8 x (K steps) relative (measured: -2e-5 at
 // K = 3 x 4096).  With CHUNK the MMA warp closes the TMEM accumulator every p.chunk_kb K blocks and
@@ -253,7 +197,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     const int c0 = col_grp * kChunks;  // first chunk of this warp inside the tile
     static_assert(!STG || (ARES == 0 && EW == 8 && EPI == EPI_STORE), "store staging: 8 warps x 4 KB");
     float4* stg = STG ? reinterpret_cast<float4*>(smem + L::kStgOffset + (warp - kEpiWarp0) * 4096)
-                      : nullptr;  // store-transpose staging of this warp
+                      : nullptr;  // store-transpose / TMA-store staging of this warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
@@ -350,7 +294,15 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
             const int col0 = n * BN + (c0 + c) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (warp_rows_ok) store_chunk<ACT, STG>(p, va, m, row_ok, lane, col0, sb + (c0 + c) * 32, stg);
+                if (warp_rows_ok) {
+                  store_chunk<ACT, STG>(p, va, m, row_ok, lane, col0, sb + (c0 + c) * 32, stg);
+                  if constexpr (STG == 2) {
+                    // the previous TMA store of this warp has finished reading the staging tile
+                    if (lane == 0) bulk_wait_group_read0();
+                    __syncwarp();
+                    stage_chunk_bf16(va, reinterpret_cast<uint8_t*>(stg), lane, 0);
+                  }
+                }
               } else {
                 nll_chunk(p, va, col0, st, sb + (c0 + c) * 32);
               }
@@ -369,9 +321,23 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
             const int col0 = n * BN + (c0 + c + 1) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (warp_rows_ok) store_chunk<ACT, STG>(p, vb, m, row_ok, lane, col0, sb + (c0 + c + 1) * 32, stg);
+                if (warp_rows_ok) {
+                  store_chunk<ACT, STG>(p, vb, m, row_ok, lane, col0, sb + (c0 + c + 1) * 32, stg);
+                  if constexpr (STG == 2) stage_chunk_bf16(vb, reinterpret_cast<uint8_t*>(stg), lane, 1);
+                }
               } else {
                 nll_chunk(p, vb, col0, st, sb + (c0 + c + 1) * 32);
+              }
+            }
+            if constexpr (EPI == EPI_STORE && STG == 2) {
+              // one 32-row x 64-column bf16 tile per chunk pair leaves through the TMA store path
+              if (warp_rows_ok && n * BN + (c0 + c) * 32 < p.N) {
+                fence_proxy_async_smem();  // this lane's generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&p.tmC, stg, n * BN + (c0 + c) * 32, m - lane);
+                  bulk_commit_group();
+                }
               }
             }
           }
@@ -393,6 +359,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     }
   }
 
+  if constexpr (STG == 2) {
+    if (warp >= kEpiWarp0 && lane == 0) bulk_wait_group0();  // every committed TMA store has completed
+  }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -500,8 +469,34 @@ static int launch_stg(const GemmParams& p, cudaStream_t st) {
   return BLM_OK;
 }
 
+// TMA-store (STG == 2) variants: bf16-hi-only outputs of the forward GEMMs (QKV, FFN1)
+template <int BN, int STAGES, int ACT>
+static int set_smem_attr_tma() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, 0, 2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SmemLayout<BN, STAGES, 0>::kDynBytes));
+  return BLM_OK;
+}
+
+template <int BN, int STAGES, int ACT>
+static int launch_tma(const GemmParams& p, cudaStream_t st) {
+  const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
+  gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, 0, 2>
+      <<<grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 int gemm_init() {
   int rc;
+  if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_NONE>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GELU>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_NONE>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_GELU>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<256, kStages256, 0>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<128, kStages128, 0>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<128, kStages128, 1>()) != BLM_OK) return rc;
@@ -547,6 +542,18 @@ static int launch(const GemmParams& p, cudaStream_t st) {
   gemm_kernel<BN, STAGES, EPI, ACT, ARES, 8><<<grid, (4 + 8) * 32, smem, st>>>(p);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
+}
+
+int gemm2_store(GemmParams p, int act, cudaStream_t st);   // blm_gemm2.cu: CTA-pair (cta_group::2) kernels
+int gemm2_nll(GemmParams p, int groups, cudaStream_t st);
+
+// CTA-pair path switch: BLM_GEMM2=0 disables, =1 enables (default set below after measurement)
+static bool use_gemm2() {
+  static const bool on = [] {
+    const char* e = getenv("BLM_GEMM2");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
 }
 
 static int fill_segments(GemmParams& p, int nseg, const blm_bf16* const* A, const blm_bf16* const* B,
@@ -639,6 +646,40 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   p.aux = d->aux;
   p.ldaux = d->ldaux;
   cudaStream_t st = as_stream(stream);
+  // CTA-pair kernel: one bf16 segment, bf16-only output, forward activations, enough 256 x 256 tiles
+  if (use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
+      (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST) &&
+      static_cast<long long>((d->M + 255) / 256) * ((d->N + 255) / 256) >= num_sms() / 2) {
+    GemmParams p2 = p;
+    rc = fill_segments(p2, d->nseg, d->A, d->B, d->K, d->lda, d->ldb, d->M, d->N, 128);  // B boxes of 128 rows
+    if (rc != BLM_OK) return rc;
+    return gemm2_store(p2, d->act, st);
+  }
+  // bf16-hi-only output of a forward GEMM: the tile leaves through TMA stores (row-per-thread 16-byte stores to
+  // rows 8 KB apart back up the LSU / L2 request queues; BLM_TMA_STORE=0 is the A/B switch)
+  static const bool tma_store_on = [] {
+    const char* e = getenv("BLM_TMA_STORE");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (tma_store_on && !chunked && d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && !d->resid &&
+      (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_GPMIX)) {
+    rc = encode_tmap_bf16(&p.tmC, d->out_hi, d->M, d->N, d->ldc, 32);
+    if (rc != BLM_OK) return rc;
+    if (BN == 256) {
+      switch (d->act) {
+        case BLM_ACT_NONE: return launch_tma<256, kStages256, BLM_ACT_NONE>(p, st);
+        case BLM_ACT_GELU: return launch_tma<256, kStages256, BLM_ACT_GELU>(p, st);
+        case BLM_ACT_GPMIX: return launch_tma<256, kStages256, BLM_ACT_GPMIX>(p, st);
+        default: return launch_tma<256, kStages256, BLM_ACT_GELU_FAST>(p, st);
+      }
+    }
+    switch (d->act) {
+      case BLM_ACT_NONE: return launch_tma<128, kStages128, BLM_ACT_NONE>(p, st);
+      case BLM_ACT_GELU: return launch_tma<128, kStages128, BLM_ACT_GELU>(p, st);
+      case BLM_ACT_GPMIX: return launch_tma<128, kStages128, BLM_ACT_GPMIX>(p, st);
+      default: return launch_tma<128, kStages128, BLM_ACT_GELU_FAST>(p, st);
+    }
+  }
   const bool stg = p.use_stg && d->act == BLM_ACT_NONE;
   if (chunked) {
     p.chunk_kb = d->k_chunk / kBK;
@@ -747,6 +788,29 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   // K <= 512 in one segment (the bf16 Transformer case): keep the hidden-state tile resident in
   // shared memory for the whole vocabulary sweep, so only the embedding tiles stream from L2
   static const bool no_ares = getenv("BLM_NLL_NO_ARES") != nullptr;  // A/B switch for profiling
+  if (use_gemm2() && p.nseg == 1 && total_kb <= kNllAres && d->M >= 256 * 8) {
+    // CTA-pair kernel: each CTA streams only its half of every vocabulary tile
+    GemmParams p2 = p;
+    rc = fill_segments(p2, d->nseg, d->H, d->E, d->K, d->ldh, d->lde, d->M, d->V, 128);
+    if (rc != BLM_OK) return rc;
+    const int m_pairs = static_cast<int>((d->M + 255) / 256);
+    int g2 = (num_sms() / 2 + m_pairs - 1) / m_pairs;
+    if (g2 > p.n_tiles) g2 = p.n_tiles;
+    if (g2 > groups) g2 = groups;   // the workspace was sized for `groups`
+    if (g2 < 1) g2 = 1;
+    const int tpg = (p.n_tiles + g2 - 1) / g2;
+    const int used = (p.n_tiles + tpg - 1) / tpg;
+    const int parts2 = used * col_groups;
+    p2.part_max = ws;
+    p2.part_sum = ws + static_cast<int64_t>(parts2) * d->M;
+    p2.part_tgt = ws + 2 * static_cast<int64_t>(parts2) * d->M;
+    rc = gemm2_nll(p2, g2, st);
+    if (rc != BLM_OK) return rc;
+    nll_merge_kernel<<<static_cast<int>((d->M + 255) / 256), 256, 0, st>>>(p2.part_max, p2.part_sum, p2.part_tgt, parts2, p.M,
+                                                                         d->nll, d->lse);
+    BLM_CHECK_CUDA(cudaGetLastError());
+    return BLM_OK;
+  }
   if (total_kb <= kNllAres && !no_ares)
     rc = launch<256, kNllAresStages, EPI_NLL, BLM_ACT_NONE, kNllAres>(p, st);
   else

@@ -17,6 +17,7 @@ enum { EPI_STORE = 0, EPI_NLL = 1 };
 struct GemmParams {
   CUtensorMap tmA[BLM_MAX_SEG];
   CUtensorMap tmB[BLM_MAX_SEG];
+  CUtensorMap tmC;      // STG == 2: bf16 output [M, N], box 64 columns x 32 rows, 128B swizzle (TMA store)
   int kblocks[BLM_MAX_SEG];
   int nseg;
   int M, N;
@@ -153,6 +154,7 @@ __device__ __forceinline__ float apply_act(float z, const float* __restrict__ co
   if constexpr (ACT == BLM_ACT_GELU || ACT == BLM_ACT_GELU_FAST) {
     return gelu_fast(z);   // (the packed-fp16 variant is applied pairwise in store_chunk; this is its ragged-edge path)
   } else if constexpr (ACT == BLM_ACT_GPMIX) {
+    n = min(n, N - 1);  // the TMA-store path evaluates (and then clips) columns past the ragged edge
     const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n),
                 c3 = __ldg(coef + 3 * N + n);
     // sigmoid and tanh from ONE exponential: e = exp(-z) (z clamped to +-15, where both have saturated to
@@ -166,6 +168,63 @@ __device__ __forceinline__ float apply_act(float z, const float* __restrict__ co
   } else {
     return z;
   }
+}
+
+// ---- vocabulary NLL epilogue state (shared by the 1-CTA and 2-CTA kernels) -------------------------------
+struct NllState {
+  float run_max;  // log2 domain: fl(max logit * log2 e)
+  float run_sum, tgt_logit;
+  int tgt;
+};
+
+// online log-sum-exp over one 32-column chunk of logits (natural-log units; exponentials via ex2)
+// sb: the chunk's 32 bias values in shared memory (zero where there is no bias / past column N)
+__device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], int col0, NllState& st,
+                                          const float* sb) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(sb + j);
+      v[j] += bb.x;
+      v[j + 1] += bb.y;
+      v[j + 2] += bb.z;
+      v[j + 3] += bb.w;
+    }
+  }
+  if (col0 + 32 > p.N) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j >= p.N) v[j] = -INFINITY;
+  }
+  const unsigned int rel = static_cast<unsigned int>(st.tgt - col0);
+  if (rel < 32u) {  // the target column lives in this chunk: once per row per sweep
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (rel == static_cast<unsigned int>(j)) st.tgt_logit = v[j];
+  }
+  float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
+#pragma unroll
+  for (int j = 8; j < 32; j += 8) {
+    m0 = fmaxf(m0, fmaxf(v[j], v[j + 1]));
+    m1 = fmaxf(m1, fmaxf(v[j + 2], v[j + 3]));
+    m2 = fmaxf(m2, fmaxf(v[j + 4], v[j + 5]));
+    m3 = fmaxf(m3, fmaxf(v[j + 6], v[j + 7]));
+  }
+  // running maximum kept in the log2 domain as the ROUNDED product max * log2(e): every term and
+  // every rescale is then measured against exactly the same power of two (a rescale by the
+  // unchanged maximum is exactly 1, so nothing compounds over the ~1000 chunks of a row)
+  const float new_m2 = fmaxf(st.run_max, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * kLog2e);
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    s0 += ex2_approx(fmaf(v[j], kLog2e, -new_m2));
+    s1 += ex2_approx(fmaf(v[j + 1], kLog2e, -new_m2));
+    s2 += ex2_approx(fmaf(v[j + 2], kLog2e, -new_m2));
+    s3 += ex2_approx(fmaf(v[j + 3], kLog2e, -new_m2));
+  }
+  st.run_sum = st.run_sum * ex2_approx(st.run_max - new_m2) + ((s0 + s1) + (s2 + s3));
+  st.run_max = new_m2;
 }
 
 // ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
@@ -184,7 +243,9 @@ __device__ __forceinline__ float apply_act(float z, const float* __restrict__ co
 template <int ACT, int STG = 0>
 __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32], int m, bool row_ok, int lane,
                                             int col0, const float* sb = nullptr, float4* stg = nullptr) {
-  const bool full = (col0 + 32 <= p.N);
+  // STG == 2: arithmetic only -- the caller packs the chunk to bf16 and hands it to a TMA store, which clips
+  // the tensor edges itself, so every chunk takes the vector path (staged bias is zero past column N)
+  const bool full = (STG == 2) || (col0 + 32 <= p.N);
   if (full) {
     if (p.bias) {
 #pragma unroll
@@ -236,7 +297,8 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
     }
-    if constexpr (STG) {
+    if constexpr (STG == 2) return;
+    if constexpr (STG == 1) {
       // ---- transpose through shared memory, then row-coalesced residual + stores
 #pragma unroll
       for (int q = 0; q < 8; ++q)
@@ -287,7 +349,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       return;
     }
     if (!row_ok) return;
-    if constexpr (STG) return;  // (not reached: the staged path returned above)
+    if constexpr (STG != 0) return;  // (not reached: the staged paths returned above)
     if (p.resid) {
       const float* r = p.resid + static_cast<long long>(m) * p.ldr + col0;
 #pragma unroll
@@ -357,6 +419,20 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
         if (p.out_lo) p.out_lo[off + j] = __float2bfloat16_rn(z - __bfloat162float(hh));
       }
     }
+  }
+}
+
+// STG == 2: pack one finished 32-column chunk to bf16 and write it into this lane's 128-byte row of the
+// warp's [32 rows x 64 columns] staging tile (half = 0 / 1: columns [0, 32) / [32, 64)), in the 128B-swizzle
+// layout the output tensor map expects: 16-byte slot j of row r sits at slot j ^ (r & 7).
+__device__ __forceinline__ void stage_chunk_bf16(const float (&v)[32], uint8_t* stg, int lane, int half) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = pack_bf16x2(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+    const int slot = (half * 4 + q) ^ (lane & 7);
+    *reinterpret_cast<uint4*>(stg + lane * 128 + slot * 16) = make_uint4(h[0], h[1], h[2], h[3]);
   }
 }
 

@@ -114,6 +114,19 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void
       : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async-group completion); rows / columns past the tensor edge
+// are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t crd0, int32_t crd1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed bulk store has been read (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // createpolicy-encoded L2 hints (same constants CUTLASS ships as CacheHintSm90).
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;

@@ -68,6 +68,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t c
 int gemm_init();  // blm_gemm.cu: raise dynamic shared-memory limits
 int lstm_init();  // blm_lstm.cu
 int gemm_sampled_init();  // blm_gemm_sampled.cu
+int gemm2_init();         // blm_gemm2.cu
 
 }  // namespace blm
 
@@ -100,6 +101,8 @@ int blm_init(int device) {
   rc = lstm_init();
   if (rc != BLM_OK) return rc;
   rc = gemm_sampled_init();
+  if (rc != BLM_OK) return rc;
+  rc = gemm2_init();
   if (rc != BLM_OK) return rc;
   return BLM_OK;
 }

@@ -8,13 +8,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-# opt-in kernel variants that the suite must keep exercising (read once by the library):
-# the 4-CTA-cluster form of blm_gemm_sampled is used for M >= 2048 rows when this is set
-os.environ.setdefault("BLM_SAMPLED_CLUSTER", "1")
-# ... and the cluster-multicast / staggered form of the persistent LSTM kernel for batches >= 256 rows
-os.environ.setdefault("BLM_LSTM_CLUSTER", "1")
-os.environ.setdefault("BLM_LSTM_STAGGER", "1")
-
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")

@@ -244,3 +244,21 @@ def test_fast_gelu_epilogue(ops):
     diff = (out.hi.float() - exact.hi.float()).abs()
     assert (diff <= 8e-3 * exact.hi.float().abs() + 2e-3).all()
     assert (diff == 0).float().mean().item() > 0.8
+
+
+@pytest.mark.parametrize("M,N,K,act", [(4096, 1536, 512, 0), (3000, 4096, 512, 1), (2500, 696, 200, 0), (20000, 4096, 512, 6)])
+def test_bf16_output_gemm_shapes_of_the_pair_kernel(ops, M, N, K, act):
+    """bf16-only-output GEMMs at the shapes the CTA-pair (cta_group::2) kernel takes when BLM_GEMM2=1
+    (and the 1-CTA kernel otherwise): QKV, FFN1 + GELU, ragged edges."""
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    bias = torch.randn(N, device=DEV)
+    A, B = ops.split(a, "bf16"), ops.split(b, "bf16")
+    out = ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm(A, B, prec="bf16", bias=bias, act=act, col_scale=0.125, col_scale_cols=N // 3 // 8 * 8, out=out)
+    z = A.hi.double() @ B.hi.double().T + bias.double()
+    z[:, : N // 3 // 8 * 8] *= 0.125
+    if act:
+        z = torch.nn.functional.gelu(z)
+    err = (out.hi.double() - z).abs()
+    assert (err <= 4.5e-3 * z.abs() + (1.5e-3 if act == 6 else 1e-5)).all(), err.max().item()
