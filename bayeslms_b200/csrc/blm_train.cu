@@ -702,6 +702,61 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
   }
 }
 
+// ---------------------------------------------------------------- LSTM backward (BPTT)
+// The forward recurrence kernel (blm_lstm.cu) keeps no gate values.  For the fine-tune step the
+// pre-activations Z = gates_x + H_prev W_hh^T are rebuilt by ONE GEMM over all timesteps (H_prev is the
+// saved layer output shifted by a step), then this kernel turns Z into the activated gates in place and
+// recomputes the cell states: one thread per (row b, unit u) walks t = 0..T-1.
+__global__ void lstm_gates_act_kernel(float* __restrict__ gates, const float* __restrict__ c0, int T, int B, int H,
+                                      float* __restrict__ c_all) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * H) return;
+  const int b = static_cast<int>(idx / H), u = static_cast<int>(idx % H);
+  float c = c0[idx];
+  for (int t = 0; t < T; ++t) {
+    float* z = gates + (static_cast<long long>(t) * B + b) * 4 * H + u;
+    const float i = 1.0f / (1.0f + expf(-z[0]));
+    const float f = 1.0f / (1.0f + expf(-z[H]));
+    const float g = tanhf(z[2 * H]);
+    const float o = 1.0f / (1.0f + expf(-z[3 * H]));
+    c = fmaf(f, c, i * g);
+    z[0] = i, z[H] = f, z[2 * H] = g, z[3 * H] = o;
+    c_all[(static_cast<long long>(t) * B + b) * H + u] = c;
+  }
+}
+
+// One step of the backward recurrence (gate order i,f,g,o):
+//   dh = dout_t + dh_rec;  do = dh tanh(c_t) o(1-o);  dc' = dc + dh o (1 - tanh(c_t)^2)
+//   di = dc' g i(1-i);  df = dc' c_{t-1} f(1-f);  dg = dc' i (1-g^2);  dc <- dc' f
+// dgates leave as fp32 (for the weight gradients) and as bf16 hi[, lo] (A operand of dh_rec = dgates W_hh).
+__global__ void lstm_bwd_step_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                     const float* __restrict__ c_t, const float* __restrict__ dout,
+                                     const float* __restrict__ dh_rec, float* __restrict__ dc, int dc_is_zero, int B, int H,
+                                     float* __restrict__ dg32, __nv_bfloat16* __restrict__ dg_hi,
+                                     __nv_bfloat16* __restrict__ dg_lo) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * H) return;
+  const int b = static_cast<int>(idx / H), u = static_cast<int>(idx % H);
+  const long long row = static_cast<long long>(b) * 4 * H + u;
+  const float i = gates[row], f = gates[row + H], g = gates[row + 2 * H], o = gates[row + 3 * H];
+  const float dh = dout[idx] + (dh_rec ? dh_rec[idx] : 0.0f);
+  const float tc = tanhf(c_t[idx]);
+  const float dcp = (dc_is_zero ? 0.0f : dc[idx]) + dh * o * (1.0f - tc * tc);
+  float d[4];
+  d[0] = dcp * g * i * (1.0f - i);
+  d[1] = dcp * c_prev[idx] * f * (1.0f - f);
+  d[2] = dcp * i * (1.0f - g * g);
+  d[3] = dh * tc * o * (1.0f - o);
+  dc[idx] = dcp * f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    dg32[row + k * H] = d[k];
+    const __nv_bfloat16 h = __float2bfloat16_rn(d[k]);
+    dg_hi[row + k * H] = h;
+    if (dg_lo) dg_lo[row + k * H] = __float2bfloat16_rn(d[k] - __bfloat162float(h));
+  }
+}
+
 int train_init() {
   BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(mha_bwd_smem_bytes(128))));
@@ -937,6 +992,28 @@ int blm_sgd_momentum(float* p, const float* g, float* v, int64_t n, float lr, fl
   BLM_REQUIRE(p && g && v && n > 0, BLM_ERR_ARG, "bad sgd arguments");
   sgd_momentum_kernel<<<tgrid(n, 256, 8), 256, 0, as_stream(stream)>>>(p, g, v, n, lr, momentum, norm_sq, max_norm,
                                                                       grad_scale);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_lstm_gates_act(float* gates, const float* c0, int64_t T, int64_t B, int64_t H, float* c_all, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(gates && c0 && c_all && T > 0 && B > 0 && H > 0, BLM_ERR_ARG, "bad lstm_gates_act arguments");
+  lstm_gates_act_kernel<<<static_cast<unsigned>((B * H + 127) / 128), 128, 0, as_stream(stream)>>>(
+      gates, c0, static_cast<int>(T), static_cast<int>(B), static_cast<int>(H), c_all);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_lstm_bwd_step(const float* gates_t, const float* c_prev, const float* c_t, const float* dout_t,
+                      const float* dh_rec, float* dc, int32_t dc_is_zero, int64_t B, int64_t H, float* dgates_f32,
+                      blm_bf16* dgates_hi, blm_bf16* dgates_lo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(gates_t && c_prev && c_t && dout_t && dc && dgates_f32 && dgates_hi && B > 0 && H > 0, BLM_ERR_ARG,
+              "bad lstm_bwd_step arguments");
+  lstm_bwd_step_kernel<<<static_cast<unsigned>((B * H + 255) / 256), 256, 0, as_stream(stream)>>>(
+      gates_t, c_prev, c_t, dout_t, dh_rec, dc, dc_is_zero, static_cast<int>(B), static_cast<int>(H), dgates_f32,
+      reinterpret_cast<__nv_bfloat16*>(dgates_hi), reinterpret_cast<__nv_bfloat16*>(dgates_lo));
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

@@ -612,6 +612,26 @@ def reparam_bwd(G: torch.Tensor, lgstd: torch.Tensor, dmu: torch.Tensor, dlgstd:
                                     int(accumulate), _ptr(dmu), dmu.stride(0), _ptr(dlgstd), _stream()), "blm_reparam_bwd")
 
 
+def lstm_gates_act(gates: torch.Tensor, c0: torch.Tensor, T: int, B: int, H: int) -> torch.Tensor:
+    """Pre-activations [T*B, 4H] -> activated gates (in place); returns the cell states [T*B, H]."""
+    assert gates.is_contiguous() and gates.shape == (T * B, 4 * H) and c0.is_contiguous() and c0.shape == (B, H)
+    c_all = torch.empty(T * B, H, dtype=torch.float32, device=gates.device)
+    with _op("lstm_gates_act", 1):
+        check(lib().blm_lstm_gates_act(_ptr(gates), _ptr(c0), T, B, H, _ptr(c_all), _stream()), "blm_lstm_gates_act")
+    return c_all
+
+
+def lstm_bwd_step(gates_t, c_prev, c_t, dout_t, dh_rec, dc, dc_is_zero: bool, dg32_t, dg_t: Split) -> None:
+    """One step of the LSTM backward recurrence over rows [B] (see ``blm_lstm_bwd_step``)."""
+    B, H = c_t.shape
+    for x in (gates_t, c_prev, c_t, dout_t, dc, dg32_t, dg_t.hi):
+        assert x.is_contiguous()
+    with _op("lstm_bwd_step", 1):
+        check(lib().blm_lstm_bwd_step(_ptr(gates_t), _ptr(c_prev), _ptr(c_t), _ptr(dout_t), _ptr(dh_rec), _ptr(dc),
+                                      int(dc_is_zero), B, H, _ptr(dg32_t), _ptr(dg_t.hi), _ptr(dg_t.lo), _stream()),
+              "blm_lstm_bwd_step")
+
+
 def reduce_sum(x: torch.Tensor, out: torch.Tensor, *, squares: bool = False, scale: float = 1.0,
                accumulate: bool = False) -> torch.Tensor:
     """out[0] (+)= scale * sum(x) or scale * sum(x^2), deterministic."""

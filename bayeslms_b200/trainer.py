@@ -40,8 +40,10 @@ class FineTuner:
 
     def __init__(self, model, lr: float, *, momentum: float = 0.9, clip: float = 0.25, prec: str = "bf16x3",
                  group=None):
-        if model.family not in ("bayes_tm", "gauss_tm", "v_tm"):
-            raise NotImplementedError("the fine-tune step is implemented for the Transformer families")
+        if model.family not in ("bayes_tm", "gauss_tm", "v_tm", "bayes_lstm"):
+            raise NotImplementedError("the fine-tune step is implemented for the Transformer families and the "
+                                      "Bayesian / standard two-layer LSTM")
+        self.hidden = None
         self.model, self.lr, self.momentum, self.clip, self.prec = model, float(lr), float(momentum), float(clip), prec
         self.group = group
         self.world = 1
@@ -101,10 +103,15 @@ class FineTuner:
 
     # ------------------------------------------------------------------ one step
     def forward_backward(self, tokens_tb: torch.Tensor, targets_tb: torch.Tensor, kl_scale: float, *,
-                         eps: Optional[dict] = None, seed: Optional[int] = None, v_eps_layout: str = "tbd"):
+                         eps: Optional[dict] = None, seed: Optional[int] = None, v_eps_layout: str = "tbd",
+                         hidden=None):
         """Fills the gradient buffer for the batch (T, B); returns (loss, ce, kl) as 0-dim device tensors.
         ``eps``: injected noise in the oracle's layout ({'layer<i>': ...}; V layers: (T, B, d) tensors
-        already scaled by 0.1, or (B, T, d) with ``v_eps_layout="btd"``); ``seed``: Philox noise instead."""
+        already scaled by 0.1, or (B, T, d) with ``v_eps_layout="btd"``); ``seed``: Philox noise instead.
+        LSTM families: ``hidden`` = (h, c) carried in from the previous batch (zeros if None); the state
+        after the batch is left in ``self.hidden``."""
+        if self.model.family == "bayes_lstm":
+            return self._lstm_forward_backward(tokens_tb, targets_tb, kl_scale, hidden, eps, seed)
         m, prec, dev = self.model, self.prec, self.device
         T, B = tokens_tb.shape
         M, d, nhead = T * B, m.ninp, m.nhead
@@ -238,26 +245,7 @@ class FineTuner:
             xs = ops.empty_split(M, d, prec, dev)
             ops.gemm(xs_pre, em_t, prec=prec, out=xs, tag="embed_out")
 
-        # ---------------------------------------------------------------- loss
-        E32 = m.decoder.weight.detach().float()
-        Es, Et = self._w2(E32)
-        dec_b = m.decoder.bias.detach()
-        lse = torch.empty(M, dtype=torch.float32, device=dev)
-        nll = ops.vocab_nll(xs, Es, dec_b, tgt, prec=prec, lse=lse)
-        ce, kl, loss = self.loss_buf[0:1], self.loss_buf[1:2], self.loss_buf[2:3]
-        ops.reduce_sum(nll, ce, scale=1.0 / M)
-        kl.zero_()
-
-        # ---------------------------------------------------------------- backward: decoder
-        ldv = ops._ld8(V)
-        dZ = Split(torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V],
-                   torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V] if prec == "bf16x3" else None)
-        ops.gemm(xs, Es, prec=prec, bias=dec_b, act=ACT_SOFTMAX_GRAD, lse=lse, targets=tgt, grad_scale=1.0 / M, out=dZ,
-                 tag="dlogits")
-        dx = self._f32(M, d)
-        ops.gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
-        self._wgrad(ops.transpose_bf16(dZ, prec), ops.transpose_bf16(xs, prec), g["decoder.weight"], "decoder")
-        ops.colsum(dZ, g["decoder.bias"])
+        dx, ce, kl, loss = self._loss_and_decoder_grads(xs, tgt)
         if emb_variant:   # back through x @ embed_mean: d embed_mean += x^T dout, dx = dout @ embed_mean^T
             dout = dx
             self._wgrad(ops.transpose_bf16(xs_pre, prec), ops.transpose_split(dout, prec), g["embed_mean"], "embed_out")
@@ -366,6 +354,155 @@ class FineTuner:
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
         return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
 
+    def _loss_and_decoder_grads(self, xs: Split, tgt: torch.Tensor):
+        """Cross entropy (mean over the M rows) through the vocabulary-streaming kernel, then the decoder's
+        backward: dZ = (softmax - onehot) / M produced directly as bf16 by the fused product (the [M, V]
+        logits never exist), dx = dZ E, dE += dZ^T x, db = colsum(dZ).  Returns (dx fp32 [M, d], ce, kl, loss)
+        with kl zeroed."""
+        m, prec, dev, g = self.model, self.prec, self.device, self.g
+        M, d = xs.hi.shape
+        V = m.decoder.weight.shape[0]
+        E32 = m.decoder.weight.detach().float()
+        Es, Et = self._w2(E32)
+        dec_b = m.decoder.bias.detach()
+        lse = torch.empty(M, dtype=torch.float32, device=dev)
+        nll = ops.vocab_nll(xs, Es, dec_b, tgt, prec=prec, lse=lse)
+        ce, kl, loss = self.loss_buf[0:1], self.loss_buf[1:2], self.loss_buf[2:3]
+        ops.reduce_sum(nll, ce, scale=1.0 / M)
+        kl.zero_()
+        ldv = ops._ld8(V)
+        dZ = Split(torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V],
+                   torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V] if prec == "bf16x3" else None)
+        ops.gemm(xs, Es, prec=prec, bias=dec_b, act=ACT_SOFTMAX_GRAD, lse=lse, targets=tgt, grad_scale=1.0 / M, out=dZ,
+                 tag="dlogits")
+        dx = self._f32(M, d)
+        ops.gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
+        self._wgrad(ops.transpose_bf16(dZ, prec), ops.transpose_bf16(xs, prec), g["decoder.weight"], "decoder")
+        ops.colsum(dZ, g["decoder.bias"])
+        return dx, ce, kl, loss
+
+    # ------------------------------------------------------------------ LSTM families
+    def _lstm_layer_params(self, layer: int, eps: dict, seed, sampled: bool):
+        """fp32 (W_ih, W_hh, b_ih + b_hh) of one layer for this step: the means, with the Bayesian gate's
+        rows replaced by mu + exp(lgstd) eps when sampling (model.py:668-725)."""
+        r = self.model.rnn
+        rows = r.gate_rows() if sampled else None
+        out = {}
+        for name in ("ih", "hh"):
+            mu = getattr(r, f"weight_{name}_mean_{layer}").detach()
+            if sampled:
+                key = f"weight_{name}_{layer}"
+                w = mu.clone()
+                sub = self._reparam32(mu[rows], getattr(r, f"weight_{name}_lgstd_{layer}").detach(),
+                                      _TID["lstm"] + engine.LSTM_EPS_ORDER.index(key), eps.get(key), seed)
+                w[rows] = sub
+                mu = w
+            out["w_" + name] = mu
+        bias = getattr(r, f"bias_ih_mean_{layer}").detach() + getattr(r, f"bias_hh_mean_{layer}").detach()
+        if sampled:
+            cur = bias[rows].contiguous()
+            for name in ("ih", "hh"):
+                key = f"bias_{name}_{layer}"
+                cur = self._reparam32(cur, getattr(r, f"bias_{name}_lgstd_{layer}").detach(),
+                                      _TID["lstm"] + engine.LSTM_EPS_ORDER.index(key), eps.get(key), seed)
+            bias[rows] = cur
+        out["bias"] = bias
+        return out
+
+    def _lstm_forward_backward(self, tokens_tb, targets_tb, kl_scale, hidden, eps, seed):
+        """BayesRNNModel step (model.py:217-222, train.py:319-340): embedding -> two LSTM layers -> decoder.
+        Rows are time-major (row = t*B + b).  Forward keeps each layer's input and output; the backward pass
+        rebuilds the gate pre-activations with one GEMM per layer, walks the recurrence backwards (one small
+        kernel + one [B, 4H] x [4H, H] product per step) and finishes with three GEMMs per layer (input
+        gradient and the two weight gradients over all T*B rows at once).  The incoming hidden state is a
+        constant (train.py repackages it); the outgoing one is kept in ``self.hidden``."""
+        m, prec, dev, g = self.model, self.prec, self.device, self.g
+        r = m.rnn
+        T, B = tokens_tb.shape
+        M, H = T * B, m.nhid
+        eps = _to_device(eps or {}, dev)
+        if hidden is None:
+            hidden = m.init_hidden(B)
+        h0, c0 = hidden[0].detach().float().contiguous(), hidden[1].detach().float().contiguous()
+        bayes = 1 <= r.position <= 4
+        sampled = bayes and (len(eps) > 0 or seed is not None)
+        tok = tokens_tb.reshape(-1).to(torch.int32)
+        tgt = targets_tb.reshape(-1).to(torch.int32)
+        lengths = torch.full((B,), T, dtype=torch.int32, device=dev)
+        self.flat_g.zero_()
+
+        _, x = ops.embed(tok, None, m.encoder.weight.detach().float(), None, 1.0, prec=prec, want_f32=False)
+        saved, hT, cT = [], [], []
+        for li in range(2):
+            P = self._lstm_layer_params(li + 1, eps, seed, sampled)
+            w_ih, w_ih_t = self._w2(P["w_ih"])
+            w_hh, w_hh_t = self._w2(P["w_hh"])
+            gates = self._f32(M, 4 * H)
+            ops.gemm(x, w_ih, prec=prec, bias=P["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+            _, out, h_last, c_last = ops.lstm_layer(gates, w_hh, h0[li], c0[li], lengths, T, B, H, prec=prec,
+                                                    want_f32=False, want_split=True)
+            saved.append({"x": x, "out": out, "gates": gates, "w_ih_t": w_ih_t, "w_hh": w_hh, "w_hh_t": w_hh_t})
+            hT.append(h_last)
+            cT.append(c_last)
+            x = out
+        self.hidden = (torch.stack(hT), torch.stack(cT))
+
+        dout, ce, kl, loss = self._loss_and_decoder_grads(x, tgt)
+
+        for li in (1, 0):
+            S, layer = saved[li], li + 1
+            h0s = ops.split(h0[li], prec)
+            hprev = Split(torch.cat([h0s.hi, S["out"].hi[:M - B]], 0),
+                          None if h0s.lo is None else torch.cat([h0s.lo, S["out"].lo[:M - B]], 0))
+            gates = S["gates"]
+            ops.gemm(hprev, S["w_hh"], prec=prec, resid=gates, out_f32=gates, tag="lstm_rebuild")
+            c_all = ops.lstm_gates_act(gates, c0[li], T, B, H)
+            dG = self._f32(M, 4 * H)
+            dGs = ops.empty_split(M, 4 * H, prec, dev)
+            dc = self._f32(B, H)
+            dh = [self._f32(B, H), self._f32(B, H)]
+            rec = None
+            for t in range(T - 1, -1, -1):
+                sl = slice(t * B, (t + 1) * B)
+                c_prev = c0[li] if t == 0 else c_all[(t - 1) * B:t * B]
+                dGt = Split(dGs.hi[sl], None if dGs.lo is None else dGs.lo[sl])
+                ops.lstm_bwd_step(gates[sl], c_prev, c_all[sl], dout[sl], rec, dc, t == T - 1, dG[sl], dGt)
+                if t > 0:
+                    rec = dh[t & 1]
+                    ops.gemm(dGt, S["w_hh_t"], prec=prec, out_f32=rec, tag="lstm_dh")
+            # input gradient, weight gradients, biases
+            dGT = ops.transpose_split(dG, prec)
+            pre = "rnn."
+            G_ih, G_hh = g[f"{pre}weight_ih_mean_{layer}"], g[f"{pre}weight_hh_mean_{layer}"]
+            self._wgrad(dGT, ops.transpose_bf16(S["x"], prec), G_ih, f"lstm_ih{layer}")
+            self._wgrad(dGT, ops.transpose_bf16(hprev, prec), G_hh, f"lstm_hh{layer}")
+            gb_ih, gb_hh = g[f"{pre}bias_ih_mean_{layer}"], g[f"{pre}bias_hh_mean_{layer}"]
+            ops.colsum(dG, gb_ih)
+            ops.colsum(dG, gb_hh)
+            dx = self._f32(M, S["x"].hi.shape[1])
+            ops.gemm(dGs, S["w_ih_t"], prec=prec, out_f32=dx, tag="dgrad:lstm_in")
+            dout = dx
+            if bayes:
+                rows = r.gate_rows()
+                terms = [(f"weight_hh_{layer}", G_hh, H / float(H + r.input_size)),
+                         (f"weight_ih_{layer}", G_ih, r.input_size / float(H + r.input_size)),
+                         (f"bias_hh_{layer}", gb_hh, 0.5), (f"bias_ih_{layer}", gb_ih, 0.5)]
+                for key, G, frac in terms:
+                    name = key.rsplit("_", 1)[0]
+                    lg = getattr(r, f"{name}_lgstd_{layer}").detach()
+                    mu = getattr(r, f"{name}_mean_{layer}").detach()
+                    g_lg = g[f"{pre}{name}_lgstd_{layer}"]
+                    if sampled:
+                        ops.reparam_bwd(G[rows], lg, G[rows], g_lg, eps=eps.get(key), seed=seed,
+                                        stream_id=engine._stream_id(_TID["lstm"] + engine.LSTM_EPS_ORDER.index(key), 0))
+                    if layer == 1:   # the reference's KL only sees the layer-1 tensors (model.py:736-765)
+                        ops.kl_gauss(mu[rows], lg, kl, scale=frac, accumulate=True)
+                        ops.kl_gauss_bwd(mu[rows], lg, kl_scale * frac, G[rows], g_lg)
+        ops.embed_bwd(dout, tok, 1.0, g["encoder.weight"])
+        ops.reduce_sum(ce, loss)
+        ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
+        return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
+
     def _gp_backward(self, layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, le, seed):
         """Gradients of the GP unit (model.py:1780-1902): weights / bias / coef means, their log-sigmas
         through the reparameterisation when the unit samples, and the unit's KL (the '-1' variant)."""
@@ -403,8 +540,8 @@ class FineTuner:
                          1.0 / self.world)
         self.model.__dict__.pop("_blm_plans", None)
 
-    def step(self, tokens_tb, targets_tb, kl_scale, *, eps=None, seed=None):
-        out = self.forward_backward(tokens_tb, targets_tb, kl_scale, eps=eps, seed=seed)
+    def step(self, tokens_tb, targets_tb, kl_scale, *, eps=None, seed=None, hidden=None):
+        out = self.forward_backward(tokens_tb, targets_tb, kl_scale, eps=eps, seed=seed, hidden=hidden)
         self.apply_gradients()
         return out
 

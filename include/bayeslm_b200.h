@@ -375,6 +375,21 @@ int blm_reparam_bwd(const float* G, int64_t ldg, const float* lgstd, const float
                     uint64_t seed, uint64_t stream_id, int64_t rows, int64_t cols, int32_t accumulate,
                     float* dmu, int64_t lddmu, float* dlgstd, blm_stream stream);
 
+/* LSTM backward through time (the LSTM families' share of train.py:306-438; torch's LSTM backward
+ * behind model.py:812).  Row layout is time-major: row = t * B + b.
+ * blm_lstm_gates_act: gates [T, B, 4H] holds the pre-activations Z = x W_ih^T + b + h_{t-1} W_hh^T
+ *   (rebuilt by one blm_gemm over all steps); on return it holds sigmoid/tanh of them (i,f,g,o) and
+ *   c_all [T, B, H] the cell states, starting from c0 [B, H].
+ * blm_lstm_bwd_step: one step of the backward recurrence for rows [B] at time t:
+ *   dgates_t from (dout_t + dh_rec, dc); dc is updated in place (dc_is_zero: treat the carry as 0,
+ *   first step of the backward walk).  dh_rec (nullable) = dgates_{t+1} W_hh, a blm_gemm between steps.
+ *   dgates leave as fp32 and bf16 hi[, lo], all with leading dimension 4H.                      */
+int blm_lstm_gates_act(float* gates, const float* c0, int64_t T, int64_t B, int64_t H, float* c_all,
+                       blm_stream stream);
+int blm_lstm_bwd_step(const float* gates_t, const float* c_prev, const float* c_t, const float* dout_t,
+                      const float* dh_rec, float* dc, int32_t dc_is_zero, int64_t B, int64_t H,
+                      float* dgates_f32, blm_bf16* dgates_hi, blm_bf16* dgates_lo, blm_stream stream);
+
 /* out[0] (+)= scale * sum x (squares == 0) or scale * sum x^2 (squares == 1); deterministic.
  * workspace: blm_reduce_workspace_bytes(), zeroed once by the caller.                           */
 int64_t blm_reduce_workspace_bytes(void);

@@ -398,7 +398,9 @@ def model_kl(sd: SD, cfg: Config, aux: Optional[dict] = None) -> Tensor:
     """The KL term train.py adds for each family (train.py:335-399)."""
     fam = cfg.family
     if fam == "bayes_lstm":
-        return kl_bayes_lstm(sd, cfg.bayes_pos)
+        # pos 0 = plain LSTM: train.py only adds the KL under --uncertainty Bayesian, and the reference's
+        # kl_divergence raises for position 0 (model.py:757-775 falls into the prior branch with prior=None)
+        return kl_bayes_lstm(sd, cfg.bayes_pos) if 1 <= cfg.bayes_pos <= 4 else torch.zeros(())
     if fam == "bayes_tm":
         if cfg.bayes_pos == "FFN":
             return kl_bayes_linear(sd, "transformerlayers.0.linear2.")

@@ -174,3 +174,76 @@ def test_captured_step_equals_eager_step():
     (l0, p0), (l1, p1) = outs
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 1e-5, (l0, l1)
     assert (p0 - p1).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------ LSTM families
+def _build_lstm(pos, H=128):
+    from bayeslms_b200 import model as M
+    torch.manual_seed(7)
+    net = M.BayesRNNModel("LSTM", V, H, H, 2, 0.0, True, pos)
+    with torch.no_grad():
+        net.decoder.bias.uniform_(-0.1, 0.1)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.Config(family="bayes_lstm", ntoken=V, ninp=H, nhid=H, nlayers=2, bayes_pos=pos)
+    return net, sd, cfg
+
+
+def _oracle_lstm_step(sd, cfg, x, y, eps, kl_scale, hidden):
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v)
+            for k, v in sd.items() if k != "decoder.weight"}
+    leaf["decoder.weight"] = leaf["encoder.weight"]
+    loss, ce, kl = O.finetune_loss(leaf, x, y, cfg, eps, kl_scale, hidden=hidden)
+    loss.backward()
+    grads = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v))
+             for k, v in leaf.items() if k != "decoder.weight" and v.requires_grad}
+    with torch.no_grad():
+        _, new_hidden = O.rnn_forward(sd, x, hidden, cfg, eps)
+    return float(loss.detach()), float(ce.detach()), float(kl.detach()) if torch.is_tensor(kl) else float(kl), grads, new_hidden
+
+
+@pytest.mark.parametrize("pos,sampled", [(3, True), (1, True), (4, False), (0, False)])
+def test_lstm_finetune_step_matches_oracle_autograd(pos, sampled):
+    """Bayes-LSTM (train.py:319-340 with model.rnn.kl_divergence()): loss, KL, every gradient and the
+    carried-out hidden state against autograd through the oracle's LSTM, from a non-zero carried-in state.
+    Same tolerances as the Transformer cases."""
+    from bayeslms_b200.trainer import FineTuner
+    net, sd, cfg = _build_lstm(pos)
+    T, B, H, kl_scale = 9, 4, 128, 0.37
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, V, (T, B), generator=g)
+    y = torch.randint(0, V, (T, B), generator=g)
+    hidden = (torch.randn(2, B, H, generator=g) * 0.3, torch.randn(2, B, H, generator=g) * 0.3)
+    eps = O.draw_eps(sd, cfg, 99) if sampled else None
+    want_loss, want_ce, want_kl, want_g, want_hidden = _oracle_lstm_step(sd, cfg, x, y.view(-1), eps, kl_scale, hidden)
+
+    ft = FineTuner(net.to(DEV).train(), 0.05, clip=0.25, prec="bf16x3")
+    loss, ce, kl = ft.forward_backward(x.to(DEV), y.to(DEV), kl_scale, eps=eps,
+                                       hidden=(hidden[0].to(DEV), hidden[1].to(DEV)))
+    assert abs(float(ce) - want_ce) < 2e-4, (float(ce), want_ce)
+    assert abs(float(kl) - want_kl) <= 1e-4 * abs(want_kl) + 1e-7, (float(kl), want_kl)
+    assert abs(float(loss) - want_loss) < 2e-4 + 1e-4 * abs(want_loss), (float(loss), want_loss)
+    for got, want in zip(ft.hidden, want_hidden):
+        assert (got.cpu() - want).abs().max().item() < 1e-4
+    bad = []
+    for name, ref in want_g.items():
+        got = ft.g[name].detach().cpu()
+        tol = 2e-3 * ref.abs().max().item() + 1e-7
+        err = (got - ref).abs().max().item()
+        if not err <= tol:
+            bad.append((name, err, ref.abs().max().item()))
+    assert not bad, bad
+
+
+def test_lstm_finetune_reduces_the_loss_with_carried_state():
+    from bayeslms_b200.trainer import FineTuner
+    net, sd, cfg = _build_lstm(3)
+    ft = FineTuner(net.to(DEV).train(), 0.5, clip=0.25, prec="bf16")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, V, (20, 8), generator=g).to(DEV)
+    y = torch.randint(0, V, (20, 8), generator=g).to(DEV)
+    l0 = float(ft.step(x, y, 0.01, seed=1)[0])
+    hidden = None
+    for i in range(12):
+        last = float(ft.step(x, y, 0.01, seed=2 + i, hidden=hidden)[0])
+        hidden = ft.hidden
+    assert last < l0 - 0.05, (l0, last)

@@ -9,8 +9,12 @@ from bayeslms_b200.trainer import FineTuner
 _lib.init(0)
 dev = torch.device("cuda:0")
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+family = sys.argv[2] if len(sys.argv) > 2 else "v_tm"
 torch.manual_seed(1111)
-net = M.VTransformerModel(bench.V, bench.D, bench.NHEAD, bench.FF, bench.NLAYERS, 0.0, True, "11").to(dev).train()
+if family == "lstm":   # Bayes-LSTM 2 x 1024, gate 3 (BASELINE config 1 / 5 architecture), batch 32 x 100
+    net = M.BayesRNNModel("LSTM", bench.V, 1024, 1024, 2, 0.0, True, 3).to(dev).train()
+else:
+    net = M.VTransformerModel(bench.V, bench.D, bench.NHEAD, bench.FF, bench.NLAYERS, 0.0, True, "11").to(dev).train()
 ft = FineTuner(net, 0.01, clip=0.25, prec=prec)
 g = torch.Generator().manual_seed(1)
 x = torch.randint(0, bench.V, (100, 32), generator=g).to(dev)
