@@ -40,6 +40,16 @@ class GemmDesc(C.Structure):
     ]
 
 
+class GemmLnDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64),
+        ("bias", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("reserved", C.c_int32),
+        ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("ldc", C.c_int64),
+    ]
+
+
 class GemmSampledDesc(C.Structure):
     _fields_ = [
         ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
@@ -70,6 +80,7 @@ SIGNATURES = {
     "blm_init": (C.c_int, [C.c_int]),
     "blm_num_sms": (C.c_int, []),
     "blm_gemm": (C.c_int, [C.POINTER(GemmDesc), _p]),
+    "blm_gemm_ln": (C.c_int, [C.POINTER(GemmLnDesc), _p]),
     "blm_gemm_sampled": (C.c_int, [C.POINTER(GemmSampledDesc), _p]),
     "blm_sigma_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "blm_vocab_nll_workspace_bytes": (_i64, [_i64, _i64]),

@@ -544,7 +544,7 @@ static int launch(const GemmParams& p, cudaStream_t st) {
   return BLM_OK;
 }
 
-int gemm2_store(GemmParams p, int act, cudaStream_t st);   // blm_gemm2.cu: CTA-pair (cta_group::2) kernels
+int gemm2_store(GemmParams p, int act, cudaStream_t st, bool tma_store);   // blm_gemm2.cu: CTA-pair (cta_group::2) kernels
 int gemm2_nll(GemmParams p, int groups, cudaStream_t st);
 
 // CTA-pair path switch: BLM_GEMM2=0 disables, =1 enables (default set below after measurement)
@@ -653,7 +653,16 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
     GemmParams p2 = p;
     rc = fill_segments(p2, d->nseg, d->A, d->B, d->K, d->lda, d->ldb, d->M, d->N, 128);  // B boxes of 128 rows
     if (rc != BLM_OK) return rc;
-    return gemm2_store(p2, d->act, st);
+    static const bool tma2 = [] {
+      const char* e = getenv("BLM_GEMM2_TMA_STORE");
+      return e ? atoi(e) != 0 : true;
+    }();
+    const bool ts = tma2 && d->out_hi && !d->out_lo && !d->resid;
+    if (ts) {
+      rc = encode_tmap_bf16(&p2.tmC, d->out_hi, d->M, d->N, d->ldc, 32);
+      if (rc != BLM_OK) return rc;
+    }
+    return gemm2_store(p2, d->act, st, ts);
   }
   // bf16-hi-only output of a forward GEMM: the tile leaves through TMA stores (row-per-thread 16-byte stores to
   // rows 8 KB apart back up the LSU / L2 request queues; BLM_TMA_STORE=0 is the A/B switch)

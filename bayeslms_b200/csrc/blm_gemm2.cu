@@ -34,7 +34,9 @@ template <int STAGES, int ARES>
 struct Smem2 {
   static constexpr int kResBytes = ARES * k2AB;
   static constexpr int kStageBytes = (ARES ? 0 : k2AB) + k2AB;
-  static constexpr int kBiasOffset = kResBytes + STAGES * kStageBytes;
+  static constexpr int kStgOffset = kResBytes + STAGES * kStageBytes;   // 1024-B aligned: TMA-store staging, 4 KB per warp
+  static constexpr int kStgBytes = ARES ? 0 : k2EW * 4096;
+  static constexpr int kBiasOffset = kStgOffset + kStgBytes;
   static constexpr int kBarOffset = kBiasOffset + 2 * k2BN * 4;
   // full[STAGES] empty[STAGES] tfull[2] tempty[2] afull aempty + tmem slot
   static constexpr int kBytes = kBarOffset + (2 * STAGES + 6) * 8 + 16;
@@ -85,9 +87,12 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kCols) : "memory");
 }
 
-template <int STAGES, int EPI, int ACT, int ARES>
+// STG == 2: bf16-hi-only output leaves through TMA stores (as in the 1-CTA kernel, blm_gemm.cu): row-per-thread
+// 16-byte stores cost 32 LSU wavefronts per instruction and were the bound of the K = 512 shapes.
+template <int STAGES, int EPI, int ACT, int ARES, int STG = 0>
 __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_constant__ GemmParams p) {
   using L = Smem2<STAGES, ARES>;
+  static_assert(!STG || (EPI == EPI_STORE && ARES == 0), "TMA-store staging belongs to the storing kernels");
   constexpr int kChunks = k2BN / 32 / (k2EW / 4);  // 4 chunks of 32 columns per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -233,6 +238,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     const int row_in_tile = lane_grp * 32 + lane;
     const int c0 = col_grp * kChunks;
     const uint32_t tempty_leader[2] = {mapa_shared(smem_u32(&tempty_bar[0]), 0), mapa_shared(smem_u32(&tempty_bar[1]), 0)};
+    uint8_t* stg = STG ? smem + L::kStgOffset + (warp - kEpiWarp0) * 4096 : nullptr;
+    (void)stg;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = pair_id; w < p.num_works; w += n_pairs) {
@@ -276,7 +283,14 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             const int col0 = n * k2BN + (c0 + c) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (warp_rows_ok) store_chunk<ACT, 0>(p, va, m, row_ok, lane, col0, sb + (c0 + c) * 32);
+                if (warp_rows_ok) {
+                  store_chunk<ACT, STG>(p, va, m, row_ok, lane, col0, sb + (c0 + c) * 32);
+                  if constexpr (STG == 2) {
+                    if (lane == 0) bulk_wait_group_read0();  // the previous TMA store has left the staging tile
+                    __syncwarp();
+                    stage_chunk_bf16(va, stg, lane, 0);
+                  }
+                }
               } else {
                 nll_chunk(p, va, col0, st, sb + (c0 + c) * 32);
               }
@@ -294,9 +308,22 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             const int col0 = n * k2BN + (c0 + c + 1) * 32;
             if (col0 < p.N) {
               if constexpr (EPI == EPI_STORE) {
-                if (warp_rows_ok) store_chunk<ACT, 0>(p, vb, m, row_ok, lane, col0, sb + (c0 + c + 1) * 32);
+                if (warp_rows_ok) {
+                  store_chunk<ACT, STG>(p, vb, m, row_ok, lane, col0, sb + (c0 + c + 1) * 32);
+                  if constexpr (STG == 2) stage_chunk_bf16(vb, stg, lane, 1);
+                }
               } else {
                 nll_chunk(p, vb, col0, st, sb + (c0 + c + 1) * 32);
+              }
+            }
+            if constexpr (EPI == EPI_STORE && STG == 2) {
+              if (warp_rows_ok && n * k2BN + (c0 + c) * 32 < p.N) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&p.tmC, stg, n * k2BN + (c0 + c) * 32, m - lane);
+                  bulk_commit_group();
+                }
               }
             }
           }
@@ -317,6 +344,9 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     }
   }
 
+  if constexpr (STG == 2) {
+    if (warp >= kEpiWarp0 && lane == 0) bulk_wait_group0();
+  }
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -329,9 +359,9 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
 constexpr int k2Stages = 6;       // 6 x 32 KB (A tile + B half)
 constexpr int k2NllStages = 6;    // 128 KB resident A + 6 x 16 KB of B halves
 
-template <int STAGES, int EPI, int ACT, int ARES>
+template <int STAGES, int EPI, int ACT, int ARES, int STG = 0>
 static int set_attr2() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<STAGES, EPI, ACT, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<STAGES, EPI, ACT, ARES, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Smem2<STAGES, ARES>::kDynBytes));
   return BLM_OK;
 }
@@ -341,11 +371,14 @@ int gemm2_init() {
   if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_NONE, 0>()) != BLM_OK) return rc;
   if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU, 0>()) != BLM_OK) return rc;
   if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU_FAST, 0>()) != BLM_OK) return rc;
+  if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_NONE, 0, 2>()) != BLM_OK) return rc;
+  if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU, 0, 2>()) != BLM_OK) return rc;
+  if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU_FAST, 0, 2>()) != BLM_OK) return rc;
   if ((rc = set_attr2<k2NllStages, EPI_NLL, BLM_ACT_NONE, k2Ares>()) != BLM_OK) return rc;
   return BLM_OK;
 }
 
-template <int STAGES, int EPI, int ACT, int ARES>
+template <int STAGES, int EPI, int ACT, int ARES, int STG = 0>
 static int launch2(const GemmParams& p, cudaStream_t st) {
   int pairs = num_sms() / 2;
   if (pairs > p.num_works) pairs = p.num_works;
@@ -362,18 +395,25 @@ static int launch2(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<STAGES, EPI, ACT, ARES>, p));
+  BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<STAGES, EPI, ACT, ARES, STG>, p));
   return BLM_OK;
 }
 
 // Pair-tile launch of a storing GEMM (called by blm_gemm when the shape qualifies): p is filled for 128-row
 // tiles by the caller; only the tile bookkeeping changes here.
-int gemm2_store(GemmParams p, int act, cudaStream_t st) {
+int gemm2_store(GemmParams p, int act, cudaStream_t st, bool tma_store) {
   p.m_tiles = (p.M + 2 * kBM - 1) / (2 * kBM);
   p.n_tiles = (p.N + k2BN - 1) / k2BN;
   p.n_groups = p.n_tiles;
   p.tiles_per_group = 1;
   p.num_works = p.m_tiles * p.n_tiles;
+  if (tma_store) {   // p.tmC: bf16 [M, N], box 32 rows x 64 columns (encoded by the caller)
+    switch (act) {
+      case BLM_ACT_NONE: return launch2<k2Stages, EPI_STORE, BLM_ACT_NONE, 0, 2>(p, st);
+      case BLM_ACT_GELU: return launch2<k2Stages, EPI_STORE, BLM_ACT_GELU, 0, 2>(p, st);
+      default: return launch2<k2Stages, EPI_STORE, BLM_ACT_GELU_FAST, 0, 2>(p, st);
+    }
+  }
   switch (act) {
     case BLM_ACT_NONE: return launch2<k2Stages, EPI_STORE, BLM_ACT_NONE, 0>(p, st);
     case BLM_ACT_GELU: return launch2<k2Stages, EPI_STORE, BLM_ACT_GELU, 0>(p, st);

@@ -40,6 +40,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                      int box_rows);
 
+int encode_tmap_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
 inline cudaStream_t as_stream(blm_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace blm

@@ -65,10 +65,36 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t c
   return BLM_OK;
 }
 
+// fp32 row-major [rows, cols] tensor (leading dimension ld elements), [box_rows x 32] box = 128-byte inner
+// extent with 128-byte swizzle: the residual-in / fp32-out tiles of the LayerNorm-fused GEMM epilogue.
+int encode_tmap_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  int rc = load_encode();
+  if (rc != BLM_OK) return rc;
+  BLM_REQUIRE(aligned16(base), BLM_ERR_ALIGN, "tensor base %p is not 16-byte aligned", base);
+  BLM_REQUIRE((ld % 4) == 0 && ld >= cols, BLM_ERR_ALIGN,
+              "leading dimension %lld must be a multiple of 4 and >= cols %lld", (long long)ld, (long long)cols);
+  BLM_REQUIRE(rows > 0 && cols > 0 && box_rows > 0 && box_rows <= 256, BLM_ERR_SHAPE,
+              "bad tensor-map shape rows=%lld cols=%lld box_rows=%d", (long long)rows, (long long)cols, box_rows);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4u};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%d)", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return BLM_ERR_CUDA;
+  }
+  return BLM_OK;
+}
+
 int gemm_init();  // blm_gemm.cu: raise dynamic shared-memory limits
 int lstm_init();  // blm_lstm.cu
 int gemm_sampled_init();  // blm_gemm_sampled.cu
 int gemm2_init();         // blm_gemm2.cu
+int gemm_ln_init();       // blm_gemm_ln.cu
 
 }  // namespace blm
 
@@ -101,6 +127,8 @@ int blm_init(int device) {
   rc = lstm_init();
   if (rc != BLM_OK) return rc;
   rc = gemm_sampled_init();
+  if (rc != BLM_OK) return rc;
+  rc = gemm_ln_init();
   if (rc != BLM_OK) return rc;
   rc = gemm2_init();
   if (rc != BLM_OK) return rc;

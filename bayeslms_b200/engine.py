@@ -226,6 +226,9 @@ class _TmRun:
         self.dev = plan.device
         self.fused_sampling = False
         self.fast_gelu = os.environ.get("BLM_NO_FAST_GELU") is None   # A/B switch for profiling
+        # fast mode: projection + residual + LayerNorm in one kernel (BLM_NO_GEMM_LN=1 is the A/B switch)
+        self.fused_ln = (self.prec == "bf16" and self.d in ops.GEMM_LN_WIDTHS
+                         and os.environ.get("BLM_NO_GEMM_LN") is None)
 
     def f32(self, cols):
         return torch.empty(self.M, cols, dtype=torch.float32, device=self.dev)
@@ -247,6 +250,9 @@ class _TmRun:
 
     # part B: output projection + residual, LayerNorm 1
     def part_b(self, L, x32, att: Split, w_o: Split):
+        if self.fused_ln:
+            g, b, eps = L["norm1"]
+            return ops.gemm_ln(att, w_o, bias=L["o_b"], resid=x32, gamma=g, beta=b, eps=eps, tag="o_net")
         y = self.f32(self.d)
         ops.gemm(att, w_o, prec=self.prec, bias=L["o_b"], resid=x32, out_f32=y, tag="o_net")
         g, b, eps = L["norm1"]
@@ -263,6 +269,11 @@ class _TmRun:
 
     # part D: second FFN projection + residual, LayerNorm 2
     def part_d(self, L, x1_32, h: Split, w2: Split):
+        # K = 4096: the one-accumulator-stage kernel cannot hide its epilogue behind the next tile's MMAs and its
+        # ring holds two K blocks; measured 315 us fused vs 279 us for blm_gemm + blm_layernorm (BLM_GEMM_LN_FFN2=1)
+        if self.fused_ln and os.environ.get("BLM_GEMM_LN_FFN2") is not None:
+            g, b, eps = L["norm2"]
+            return ops.gemm_ln(h, w2, bias=L["b2"], resid=x1_32, gamma=g, beta=b, eps=eps, tag="ffn2")
         y = self.f32(self.d)
         ops.gemm(h, w2, prec=self.prec, bias=L["b2"], resid=x1_32, out_f32=y, tag="ffn2")
         g, b, eps = L["norm2"]

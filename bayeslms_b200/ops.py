@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_GELU_FAST, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
-                   EPS_PTR, GemmDesc, GemmSampledDesc,
+                   EPS_PTR, GemmDesc, GemmLnDesc, GemmSampledDesc,
                    VocabNllDesc,
                    check, lib)
 
@@ -161,6 +161,31 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     d.k_chunk = (PRECISE_K_CHUNK if prec == "bf16x3" else 0) if k_chunk is None else k_chunk
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
+
+
+GEMM_LN_WIDTHS = (128, 256, 384, 512)   # d_model values the LayerNorm-fused GEMM covers (blm_gemm_ln)
+
+
+def gemm_ln(a: Split, b: Split, *, bias: Optional[torch.Tensor], resid: torch.Tensor, gamma: torch.Tensor,
+            beta: torch.Tensor, eps: float, want_f32: bool = True, tag: str = ""):
+    """``LayerNorm(resid + a @ b.T + bias) * gamma + beta`` in one kernel (bf16 operands, fp32 statistics):
+    returns (fp32 [M, N] or None, Split(hi)).  Fast mode only; N must be one of GEMM_LN_WIDTHS."""
+    x, w = a.hi, b.hi
+    _require_cuda(x, w, resid, gamma, beta, bias)
+    M, N = x.shape[0], w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.shape[1] == w.shape[1]
+    assert x.stride(1) == 1 and w.stride(1) == 1 and resid.dtype == torch.float32 and resid.stride(1) == 1
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device) if want_f32 else None
+    s = empty_split(M, N, "bf16", x.device)
+    d = GemmLnDesc()
+    d.M, d.N, d.K = M, N, x.shape[1]
+    d.A, d.lda, d.B, d.ldb = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0)
+    d.bias, d.resid, d.ldr = _ptr(bias), _ptr(resid), resid.stride(0)
+    d.gamma, d.beta, d.eps = _ptr(gamma), _ptr(beta), eps
+    d.out_f32, d.out_hi, d.ldc = _ptr(y), _ptr(s.hi), N
+    with _op("gemm_ln:" + tag if tag else "gemm_ln", 1, 2.0 * M * N * x.shape[1]):
+        check(lib().blm_gemm_ln(C.byref(d), _stream()), "blm_gemm_ln")
+    return y, s
 
 
 def sigma_bf16(lgstd: torch.Tensor) -> torch.Tensor:

@@ -129,6 +129,40 @@ typedef struct blm_gemm_desc {
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
 
+/* --------------------------------------- GEMM + bias + residual + LayerNorm
+ * out[M,N] = LayerNorm( resid[M,N] + A[M,K] * B[N,K]^T + bias[N] ) * gamma + beta
+ *
+ * The post-LN sublayer tail of the Transformer block in ONE kernel (fast bf16 mode): a CTA owns a
+ * full 128 x N row block (N <= 512 = all 512 TMEM columns), so the row statistics are local to
+ * the epilogue thread that owns the row; the pre-LayerNorm sum never reaches HBM.  The residual
+ * arrives and both outputs (fp32 residual stream + bf16 operand copy) leave through TMA.
+ * Statistics: shifted one-pass mean / M2 per half row, merged with Chan's formula; eps inside the
+ * sqrt (nn.LayerNorm).
+ * replaces: `src = norm1(src + dropout1(self_attn(...)))` / `src = norm2(src + dropout2(linear2(...)))`
+ *           model.py:1040-1046, 1167-1175, 2283-2286 (eval mode: dropout is the identity).
+ * needs:    N in {128, 256, 384, 512}; lda / ldb % 8 == 0; resid / out_f32 / out_hi dense enough for
+ *           ldr % 4 == 0, ldc % 8 == 0; 16-B aligned pointers.  resid may alias out_f32.
+ * returns BLM_ERR_SHAPE for other N: the caller then runs blm_gemm + blm_layernorm.            */
+typedef struct blm_gemm_ln_desc {
+  int64_t M, N, K;
+  const blm_bf16* A;   /* [M, K] bf16, leading dimension lda                   */
+  int64_t lda;
+  const blm_bf16* B;   /* [N, K] bf16, leading dimension ldb                   */
+  int64_t ldb;
+  const float* bias;   /* [N] or null                                          */
+  const float* resid;  /* [M, N] fp32, leading dimension ldr                   */
+  int64_t ldr;
+  const float* gamma;  /* [N]                                                  */
+  const float* beta;   /* [N]                                                  */
+  float eps;
+  int32_t reserved;
+  float* out_f32;      /* [M, N] fp32, leading dimension ldc (may be null)     */
+  blm_bf16* out_hi;    /* [M, N] bf16, leading dimension ldc (may be null)     */
+  int64_t ldc;
+} blm_gemm_ln_desc;
+
+int blm_gemm_ln(const blm_gemm_ln_desc* d, blm_stream stream);
+
 /* ------------------------------------------------- tile-fused sampled GEMM (a)
  * C[M,N] = epilogue( A[M,K] * W~[N,K]^T ),  W~ = bf16( mu + sigma * eps ),  sigma = exp(lgstd)
  * built tile by tile in shared memory: TMA stages the bf16 mu and sigma tiles, generator warps

@@ -262,3 +262,50 @@ def test_bf16_output_gemm_shapes_of_the_pair_kernel(ops, M, N, K, act):
         z = torch.nn.functional.gelu(z)
     err = (out.hi.double() - z).abs()
     assert (err <= 4.5e-3 * z.abs() + (1.5e-3 if act == 6 else 1e-5)).all(), err.max().item()
+
+
+@pytest.mark.parametrize("M,N,K,bias,offset", [
+    (128, 128, 64, False, 0.0),
+    (300, 256, 200, True, 0.0),          # ragged M and K
+    (1000, 384, 512, True, 0.0),
+    (20000, 512, 512, True, 0.0),        # o_net + residual + norm1 at the BASELINE width
+    (65536 + 77, 512, 4096, True, 0.0),  # linear2 + residual + norm2, more tiles than SMs, ragged last tile
+    (4000, 512, 512, True, 300.0),       # |mean| >> std: the shifted statistics must not cancel
+])
+def test_gemm_ln_matches_float64(ops, M, N, K, bias, offset):
+    """blm_gemm_ln (projection + residual + LayerNorm in one kernel) against a float64 restatement on the
+    same bf16 operands: fp32 output within 2e-5 of the largest magnitude, bf16 copy = rounded fp32."""
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    A, B = ops.split(a, "bf16"), ops.split(b, "bf16")
+    bi = torch.randn(N, device=DEV) if bias else None
+    r = torch.randn(M, N, device=DEV) + offset
+    g = torch.rand(N, device=DEV) + 0.5
+    be = torch.randn(N, device=DEV)
+    y32, ys = ops.gemm_ln(A, B, bias=bi, resid=r, gamma=g, beta=be, eps=1e-5)
+    z = A.hi.double() @ B.hi.double().T + r.double()
+    if bias:
+        z = z + bi.double()
+    ref = torch.nn.functional.layer_norm(z, (N,), g.double(), be.double(), 1e-5)
+    # offset case: fp32 input rounding of a 300-sized value (3e-5 abs) is amplified by 1/std ~ 1
+    _close(y32, ref, 2e-5 if offset == 0.0 else 2e-4)
+    assert torch.equal(ys.hi, y32.to(torch.bfloat16))
+    # in place on the residual stream
+    r2 = r.clone()
+    from bayeslms_b200 import ops as O
+    d = O.GemmLnDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.B, d.ldb = A.hi.data_ptr(), A.hi.stride(0), B.hi.data_ptr(), B.hi.stride(0)
+    d.bias, d.resid, d.ldr = O._ptr(bi), O._ptr(r2), N
+    d.gamma, d.beta, d.eps = O._ptr(g), O._ptr(be), 1e-5
+    d.out_f32, d.out_hi, d.ldc = O._ptr(r2), None, N
+    O.check(O.lib().blm_gemm_ln(O.C.byref(d), O._stream()), "blm_gemm_ln")
+    assert torch.equal(r2, y32)
+
+
+def test_gemm_ln_rejects_other_widths(ops):
+    from bayeslms_b200 import _lib
+    a, b = ops.split(torch.randn(64, 64, device=DEV), "bf16"), ops.split(torch.randn(192, 64, device=DEV), "bf16")
+    with pytest.raises(_lib.BlmError):
+        ops.gemm_ln(a, b, bias=None, resid=torch.zeros(64, 192, device=DEV), gamma=torch.ones(192, device=DEV),
+                    beta=torch.zeros(192, device=DEV), eps=1e-5)
