@@ -58,6 +58,8 @@ class GemmSampledDesc(C.Structure):
         ("seed", C.c_uint64), ("stream_id", C.c_uint64),
         ("bias", C.c_void_p), ("coef", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("mu_f32", C.c_void_p), ("ldmu_f32", C.c_int64), ("lgstd_f32", C.c_void_p),
     ]
 
 
@@ -82,6 +84,7 @@ SIGNATURES = {
     "blm_gemm": (C.c_int, [C.POINTER(GemmDesc), _p]),
     "blm_gemm_ln": (C.c_int, [C.POINTER(GemmLnDesc), _p]),
     "blm_gemm_sampled": (C.c_int, [C.POINTER(GemmSampledDesc), _p]),
+    "blm_gemm_sampled_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_sigma_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "blm_vocab_nll_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_vocab_nll": (C.c_int, [C.POINTER(VocabNllDesc), _p]),

@@ -22,8 +22,84 @@
 #include <string.h>
 
 #include "blm_gemm_common.cuh"
+#include "blm_philox.cuh"
 
 namespace blm {
+
+// ---- generate-once sampled weights (blm_gemm_sampled): W~ is built INSIDE the GEMM launch, once ----------
+// A tile-stationary scheme regenerates every W~ tile for each group of M tiles that consumes it (128x for
+// the FFN weight at M = 65536: ~270 M normals, which makes the generator warps, not the tensor pipe, the
+// bound -- 0.37 of the tensor roofline).  The whole sampled weight is 4 MB: it fits the
+// 126 MB L2 thirty times over.  So each CTA of the persistent grid draws 1/grid of W~ exactly once (Philox
+// in registers, mu / sigma read once with 16-byte loads), writes it as bf16 to an L2-resident scratch
+// tensor, and a grid-wide arrival counter gates the first B-tile TMA load of every CTA; from there on the
+// kernel is the plain pipelined GEMM.  Same noise indexing and rounding as the tile-fused kernel:
+// element (n, k) is lane (nK + k) % 8 of Philox counter (nK + k) / 8; W~ = bf16(fma(sigma, eps, mu)).
+__device__ __forceinline__ void generate_weights(const GemmParams& p) {
+  const long long groups = static_cast<long long>(p.N) * p.gen_K / 8;  // gen_K % 8 == 0
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const long long e0 = g * 8;
+    const int n = static_cast<int>(e0 / p.gen_K), k = static_cast<int>(e0 - static_cast<long long>(n) * p.gen_K);
+    float e[8];
+    if (p.gen_eps) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.gen_eps + e0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.gen_eps + e0 + 4));
+      e[0] = a.x, e[1] = a.y, e[2] = a.z, e[3] = a.w, e[4] = b.x, e[5] = b.y, e[6] = b.z, e[7] = b.w;
+    } else {
+      const Normal8 z = philox_normal8(p.gen_seed, p.gen_stream, static_cast<uint64_t>(g));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e[j] = z.v[j];
+    }
+    uint32_t o[4];
+    if (p.gen_mu32) {
+      const float* mp = p.gen_mu32 + static_cast<long long>(n) * p.gen_ldmu32 + k;
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp)), m1 = __ldg(reinterpret_cast<const float4*>(mp + 4));
+      const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.gen_lgstd32 + e0));
+      const float4 l1 = __ldg(reinterpret_cast<const float4*>(p.gen_lgstd32 + e0 + 4));
+      o[0] = pack_bf16x2(reparam_value(m0.x, l0.x, e[0]), reparam_value(m0.y, l0.y, e[1]));
+      o[1] = pack_bf16x2(reparam_value(m0.z, l0.z, e[2]), reparam_value(m0.w, l0.w, e[3]));
+      o[2] = pack_bf16x2(reparam_value(m1.x, l1.x, e[4]), reparam_value(m1.y, l1.y, e[5]));
+      o[3] = pack_bf16x2(reparam_value(m1.z, l1.z, e[6]), reparam_value(m1.w, l1.w, e[7]));
+    } else {
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.gen_mu + static_cast<long long>(n) * p.gen_ldmu + k));
+      const uint4 sg = __ldg(reinterpret_cast<const uint4*>(p.gen_sigma + e0));
+      const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, sw[4] = {sg.x, sg.y, sg.z, sg.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w0 = fmaf(__uint_as_float(sw[j] << 16), e[2 * j], __uint_as_float(mw[j] << 16));
+        const float w1 = fmaf(__uint_as_float(sw[j] & 0xffff0000u), e[2 * j + 1], __uint_as_float(mw[j] & 0xffff0000u));
+        o[j] = pack_bf16x2(w0, w1);
+      }
+    }
+    *reinterpret_cast<uint4*>(p.gen_wt + e0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  // generic-proxy global writes -> visible to the TMA loads (async proxy) of every CTA
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p.gen_sync, 1u);
+}
+
+// TMA producer thread: wait until every CTA of the (co-resident, persistent) grid has published its share
+__device__ __forceinline__ void wait_generated(const GemmParams& p) {
+  unsigned int seen;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.gen_sync) : "memory");
+    if (seen < gridDim.x && (clock64() - t0) > 8000000000LL) {
+      printf("blm: generate-once barrier timed out (block %d, %u of %u)\n", (int)blockIdx.x, seen, gridDim.x);
+      __trap();
+    }
+  } while (seen < gridDim.x);
+  asm volatile("fence.proxy.async;" ::: "memory");
+  // the last CTA to leave re-arms the counters for the next launch (nobody is still polling by then)
+  if (atomicAdd(p.gen_sync + 1, 1u) == gridDim.x - 1) {
+    p.gen_sync[0] = 0u;
+    p.gen_sync[1] = 0u;
+    __threadfence();
+  }
+}
 
 // CHUNK: the tensor core adds into its fp32 accumulator with truncation, one truncation per
 // 16-wide K step, which shrinks every output by ~2e-8 x (K steps) relative (measured: -2e-5 at
@@ -62,6 +138,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (p.gen_wt) generate_weights(p);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
       tma_prefetch_desc(&p.tmA[s]);
@@ -95,6 +172,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
+      if (p.gen_wt) wait_generated(p);
       for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
         const int m_tile = w / p.n_groups;
         const int grp = w - m_tile * p.n_groups;
@@ -575,10 +653,10 @@ static int fill_segments(GemmParams& p, int nseg, const blm_bf16* const* A, cons
 
 }  // namespace blm
 
-extern "C" {
+namespace blm {
 
-int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
-  using namespace blm;
+// gen != null: generate-once sampled weights (see generate_weights); d->B[0] is then the scratch tensor
+int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   BLM_REQUIRE(d != nullptr, BLM_ERR_ARG, "null descriptor");
   BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
   BLM_REQUIRE(d->M > 0 && d->N > 0 && d->M < (1ll << 31) && d->N < (1ll << 31), BLM_ERR_SHAPE,
@@ -645,9 +723,23 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
   p.out_pre = d->out_pre;
   p.aux = d->aux;
   p.ldaux = d->ldaux;
+  if (gen) {
+    p.gen_mu = reinterpret_cast<const __nv_bfloat16*>(gen->mu);
+    p.gen_ldmu = gen->ldmu;
+    p.gen_sigma = reinterpret_cast<const __nv_bfloat16*>(gen->sigma);
+    p.gen_eps = gen->eps;
+    p.gen_mu32 = gen->mu32;
+    p.gen_ldmu32 = gen->ldmu32;
+    p.gen_lgstd32 = gen->lgstd32;
+    p.gen_seed = gen->seed;
+    p.gen_stream = gen->stream_id;
+    p.gen_K = static_cast<int>(d->K[0]);
+    p.gen_wt = reinterpret_cast<__nv_bfloat16*>(gen->wt);
+    p.gen_sync = gen->sync;
+  }
   cudaStream_t st = as_stream(stream);
   // CTA-pair kernel: one bf16 segment, bf16-only output, forward activations, enough 256 x 256 tiles
-  if (use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
+  if (!gen && use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
       (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST) &&
       static_cast<long long>((d->M + 255) / 256) * ((d->N + 255) / 256) >= num_sms() / 2) {
     GemmParams p2 = p;
@@ -741,6 +833,12 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) {
     default: return launch<128, kStages128, EPI_STORE, BLM_ACT_SOFTMAX_GRAD>(p, st);
   }
 }
+
+}  // namespace blm
+
+extern "C" {
+
+int blm_gemm(const blm_gemm_desc* d, blm_stream stream) { return blm::gemm_impl(d, nullptr, stream); }
 
 // vocabulary groups: enough (m_tile, group) work items to fill the chip, but no
 // more than needed -- each group costs one partial (max, sum, tgt) per row.

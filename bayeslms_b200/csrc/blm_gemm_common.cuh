@@ -49,6 +49,20 @@ struct GemmParams {
   float* part_max;  // [n_groups, M]
   float* part_sum;
   float* part_tgt;
+  // generate-once mode of blm_gemm_sampled (gen_wt != null): before the first B tile is loaded every CTA builds
+  // its share of W~ = bf16(mu + sigma eps) into gen_wt -- the dense [N, gen_K] bf16 tensor tmB[0] points at, 4 MB
+  // for the FFN weight, L2 resident -- and the TMA producers wait on a grid-wide arrival counter.
+  const __nv_bfloat16* gen_mu;     // [N, gen_K] bf16, leading dimension gen_ldmu
+  long long gen_ldmu;
+  const __nv_bfloat16* gen_sigma;  // [N, gen_K] bf16, dense
+  const float* gen_eps;            // [N, gen_K] fp32 dense (BLM_EPS_PTR) or null (Philox)
+  const float* gen_mu32;           // optional fp32 sources [N, gen_K] (ld gen_ldmu32) / lgstd dense: W~ is then
+  long long gen_ldmu32;            // bf16(mu + exp(lgstd) eps) from fp32, bit-identical to blm_reparam's bf16 output
+  const float* gen_lgstd32;
+  unsigned long long gen_seed, gen_stream;
+  int gen_K;
+  __nv_bfloat16* gen_wt;
+  unsigned int* gen_sync;          // [0] arrivals, [1] departures; zero between launches
 };
 
 // ARES > 0: the A operand of a work item (ARES K blocks of 128 x 64) stays resident in shared

@@ -584,17 +584,22 @@ int gemm_sampled_init() {
 
 }  // namespace blm
 
+extern "C" int64_t blm_gemm_sampled_workspace_bytes(int64_t N, int64_t K) {
+  return 256 + ((N * K * 2 + 255) / 256) * 256;   // two counters (own 256-byte line) + dense bf16 [N, K]
+}
+
 extern "C" int blm_gemm_sampled(const blm_gemm_sampled_desc* d, blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(d != nullptr, BLM_ERR_ARG, "null descriptor");
   BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
   BLM_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->M < (1ll << 31) && d->N < (1ll << 31), BLM_ERR_SHAPE,
               "bad shape M=%lld N=%lld K=%lld", (long long)d->M, (long long)d->N, (long long)d->K);
-  BLM_REQUIRE(d->A && d->mu, BLM_ERR_ARG, "null A / mu");
+  const bool gen32 = d->workspace && d->mu_f32 && d->lgstd_f32 && d->eps_mode != BLM_EPS_NONE;
+  BLM_REQUIRE(d->A && (d->mu || gen32), BLM_ERR_ARG, "null A / mu");
   BLM_REQUIRE(d->N % 1 == 0, BLM_ERR_SHAPE, "N");
   BLM_REQUIRE((d->K % 8) == 0, BLM_ERR_SHAPE, "K=%lld must be a multiple of 8", (long long)d->K);
   BLM_REQUIRE(d->eps_mode >= BLM_EPS_NONE && d->eps_mode <= BLM_EPS_PHILOX, BLM_ERR_ARG, "bad eps_mode %d", d->eps_mode);
-  BLM_REQUIRE(d->eps_mode == BLM_EPS_NONE || d->sigma, BLM_ERR_ARG, "sampling needs sigma");
+  BLM_REQUIRE(d->eps_mode == BLM_EPS_NONE || d->sigma || gen32, BLM_ERR_ARG, "sampling needs sigma");
   BLM_REQUIRE(d->eps_mode != BLM_EPS_PTR || d->eps, BLM_ERR_ARG, "BLM_EPS_PTR needs eps");
   BLM_REQUIRE(aligned16(d->eps), BLM_ERR_ALIGN, "eps must be 16-byte aligned");
   BLM_REQUIRE(d->eps_mode != BLM_EPS_PTR || ((d->K % 8) == 0), BLM_ERR_SHAPE, "K");
@@ -607,6 +612,39 @@ extern "C" int blm_gemm_sampled(const blm_gemm_sampled_desc* d, blm_stream strea
   BLM_REQUIRE(d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX, BLM_ERR_ARG,
               "unsupported activation %d", d->act);
   BLM_REQUIRE(d->act != BLM_ACT_GPMIX || d->coef, BLM_ERR_ARG, "GP-mix epilogue needs coef");
+
+  // generate-once mode: W~ built once per launch into the caller's L2-resident scratch, then the plain GEMM
+  static const bool force_tile = getenv("BLM_SAMPLED_TILE") != nullptr;   // A/B switch
+  if (d->workspace && d->eps_mode != BLM_EPS_NONE && !force_tile) {
+    BLM_REQUIRE(d->workspace_bytes >= blm_gemm_sampled_workspace_bytes(d->N, d->K), BLM_ERR_ARG,
+                "workspace too small: %lld bytes", (long long)d->workspace_bytes);
+    BLM_REQUIRE((reinterpret_cast<uintptr_t>(d->workspace) & 255u) == 0, BLM_ERR_ALIGN, "workspace must be 256-byte aligned");
+    BLM_REQUIRE(gen32 || ((d->ldmu % 8) == 0 && aligned16(d->mu) && aligned16(d->sigma)), BLM_ERR_ALIGN,
+                "mu / sigma alignment");
+    BLM_REQUIRE(!gen32 || ((d->ldmu_f32 % 4) == 0 && d->ldmu_f32 >= d->K && aligned16(d->mu_f32) && aligned16(d->lgstd_f32)),
+                BLM_ERR_ALIGN, "mu_f32 / lgstd_f32 alignment");
+    GemmGen gen;
+    gen.mu32 = gen32 ? d->mu_f32 : nullptr;
+    gen.ldmu32 = d->ldmu_f32;
+    gen.lgstd32 = gen32 ? d->lgstd_f32 : nullptr;
+    gen.mu = d->mu;
+    gen.ldmu = d->ldmu;
+    gen.sigma = d->sigma;
+    gen.eps = d->eps_mode == BLM_EPS_PTR ? d->eps : nullptr;
+    gen.seed = d->seed;
+    gen.stream_id = d->stream_id;
+    gen.sync = reinterpret_cast<unsigned int*>(d->workspace);
+    gen.wt = reinterpret_cast<uint8_t*>(d->workspace) + 256;
+    blm_gemm_desc g;
+    memset(&g, 0, sizeof(g));
+    g.M = d->M, g.N = d->N, g.nseg = 1, g.act = d->act;
+    g.A[0] = d->A, g.B[0] = reinterpret_cast<const blm_bf16*>(gen.wt);
+    g.K[0] = d->K, g.lda[0] = d->lda, g.ldb[0] = d->K;
+    g.bias = d->bias, g.coef = d->coef, g.col_scale = 1.0f;
+    g.resid = d->resid, g.ldr = d->ldr;
+    g.out_f32 = d->out_f32, g.out_hi = d->out_hi, g.out_lo = d->out_lo, g.ldc = d->ldc;
+    return gemm_impl(&g, &gen, stream);
+  }
 
   SampledParams p;
   memset(&p, 0, sizeof(p));

@@ -42,6 +42,21 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t c
 
 int encode_tmap_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
+// generate-once sampled weights inside a blm_gemm launch (blm_gemm.cu: generate_weights)
+struct GemmGen {
+  const void* mu;      // bf16 [N, K], leading dimension ldmu
+  int64_t ldmu;
+  const void* sigma;   // bf16 [N, K] dense
+  const float* eps;    // fp32 [N, K] dense, or null for Philox(seed, stream_id)
+  const float* mu32;   // optional fp32 mean [N, K] (ld ldmu32) + dense fp32 lgstd: replaces (mu, sigma)
+  int64_t ldmu32;
+  const float* lgstd32;
+  uint64_t seed, stream_id;
+  void* wt;            // bf16 [N, K] dense scratch = B operand of the GEMM
+  unsigned int* sync;  // two zeroed counters
+};
+int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream);
+
 inline cudaStream_t as_stream(blm_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace blm

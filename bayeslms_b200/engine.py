@@ -224,7 +224,10 @@ class _TmRun:
         self.nhead = model.nhead
         self.M = batch.n_tokens
         self.dev = plan.device
-        self.fused_sampling = False
+        self.fused_sampling = False    # True: tile-stationary blm_gemm_sampled (W~ never stored)
+        # fast mode default: the sampled FFN weight is drawn inside the GEMM launch (generate-once blm_gemm_sampled);
+        # BLM_NO_FUSED_SAMPLING=1 falls back to blm_reparam + blm_gemm (A/B switch, same bits)
+        self.once_sampling = os.environ.get("BLM_NO_FUSED_SAMPLING") is None
         self.fast_gelu = os.environ.get("BLM_NO_FAST_GELU") is None   # A/B switch for profiling
         # fast mode: projection + residual + LayerNorm in one kernel (BLM_NO_GEMM_LN=1 is the A/B switch)
         self.fused_ln = (self.prec == "bf16" and self.d in ops.GEMM_LN_WIDTHS
@@ -280,14 +283,18 @@ class _TmRun:
         return ops.layernorm(y, g, b, eps, prec=self.prec)
 
     # part D with the tile-fused sampled GEMM: W~ is generated inside the kernel, never stored
-    def part_d_fused(self, L, x1_32, h: Split, sample: Sample, eps_value, seed):
+    def part_d_fused(self, L, x1_32, h: Split, sample: Sample, eps_value, seed, how: str = "tile"):
         y = self.f32(self.d)
-        if isinstance(sample, dict):
-            ops.gemm_sampled(h, L["w2"].hi, L["w2_sigma"], eps=eps_value.to(self.dev).float(), resid=x1_32, out_f32=y,
-                             tag="ffn2")
+        if how == "once":
+            # generate-once kernel on the fp32 parameters: one launch, bit-identical to reparam + gemm
+            src = dict(mu=None, sigma=None, mu_f32=L["w2_mu"], lgstd_f32=L["w2_ls"], how="once")
         else:
-            ops.gemm_sampled(h, L["w2"].hi, L["w2_sigma"], seed=seed, stream_id=_stream_id(_TID["ffn_w2"], int(sample)),
-                             resid=x1_32, out_f32=y, tag="ffn2")
+            src = dict(mu=L["w2"].hi, sigma=L["w2_sigma"], how="tile")
+        if isinstance(sample, dict):
+            ops.gemm_sampled(h, eps=eps_value.to(self.dev).float(), resid=x1_32, out_f32=y, tag="ffn2", **src)
+        else:
+            ops.gemm_sampled(h, seed=seed, stream_id=_stream_id(_TID["ffn_w2"], int(sample)), resid=x1_32, out_f32=y,
+                             tag="ffn2", **src)
         g, b, eps = L["norm2"]
         return ops.layernorm(y, g, b, eps, prec=self.prec)
 
@@ -336,7 +343,9 @@ class _TmRun:
         if kind == "bayes_ffn" and sample is not None:
             e = sample.get("layer0") if isinstance(sample, dict) else None
             if self.fused_sampling and self.prec == "bf16":
-                return self.part_d_fused(L, x1_32, h, sample, e, seed)
+                return self.part_d_fused(L, x1_32, h, sample, e, seed, "tile")
+            if self.prec == "bf16" and self.once_sampling:
+                return self.part_d_fused(L, x1_32, h, sample, e, seed, "once")
             _, w2 = _sampled(L["w2_mu"], L["w2_ls"], _TID["ffn_w2"], sample, e, seed, self.prec)
         return self.part_d(L, x1_32, h, w2)
 
@@ -404,8 +413,9 @@ def transformer_score(model, batch: PackedBatch, *, K: int = 0, seed: Optional[i
     the Monte-Carlo predictive -log(1/K sum_k p_k)."""
     plan = plan_for(model, prec)
     run = _TmRun(model, plan, batch)
-    # fused_sampling: build the sampled FFN weight tile by tile inside the GEMM (blm_gemm_sampled, bf16
-    # mode) instead of materialising it with blm_reparam -- same noise, measured slower on B200 (DESIGN.md)
+    # fast mode: the sampled FFN weight is drawn inside the GEMM launch (generate-once blm_gemm_sampled).
+    # fused_sampling=True selects the tile-stationary kernel instead (W~ regenerated per group of M tiles and
+    # never stored) -- same noise, measured slower on B200 (DESIGN.md section 5)
     run.fused_sampling = fused_sampling
     samples = _normalise_samples(K, seed, eps_list)
     upto = _first_sampled_part(model) if samples else None

@@ -197,22 +197,35 @@ def sigma_bf16(lgstd: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gemm_sampled(a: Split, mu: torch.Tensor, sigma: Optional[torch.Tensor], *, eps: Optional[torch.Tensor] = None,
+def gemm_sampled(a: Split, mu: Optional[torch.Tensor], sigma: Optional[torch.Tensor], *, eps: Optional[torch.Tensor] = None,
+                 mu_f32: Optional[torch.Tensor] = None, lgstd_f32: Optional[torch.Tensor] = None,
                  seed: Optional[int] = None, stream_id: int = 0, bias: Optional[torch.Tensor] = None,
                  act: int = ACT_NONE, coef: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
-                 out_f32: Optional[torch.Tensor] = None, out: Optional[Split] = None, tag: str = "sampled"):
-    """``epilogue(a @ bf16(mu + sigma * eps).T)`` with the sampled weight built tile by tile inside the
-    kernel.  mu / sigma: bf16 [N, K] (sigma dense).  eps: explicit fp32 tensor, Philox(seed, stream_id),
-    or none (mean)."""
+                 out_f32: Optional[torch.Tensor] = None, out: Optional[Split] = None, tag: str = "sampled",
+                 how: str = "once"):
+    """``epilogue(a @ bf16(mu + sigma * eps).T)`` with the sampled weight built inside the GEMM launch.
+    mu / sigma: bf16 [N, K] (sigma dense).  eps: explicit fp32 tensor, Philox(seed, stream_id), or none (mean).
+    ``how="once"``: every CTA draws 1/grid of W~ once into an L2-resident scratch, then the pipelined GEMM
+    (default); ``how="tile"``: tile-stationary kernel, W~ regenerated per group of M tiles and never stored."""
     x = a.hi
     M, K = x.shape
-    N = mu.shape[0]
-    assert mu.shape[1] == K and mu.stride(1) == 1 and mu.dtype == torch.bfloat16
     mode = EPS_PTR if eps is not None else (EPS_PHILOX if seed is not None else EPS_NONE)
     d = GemmSampledDesc()
+    if mu_f32 is not None:
+        # fp32 parameters straight into the generate-once kernel: same rounding as reparam(prec="bf16")
+        assert how == "once" and mode != EPS_NONE and lgstd_f32 is not None
+        assert mu_f32.dtype == torch.float32 and mu_f32.stride(1) == 1 and mu_f32.shape[1] == K
+        assert lgstd_f32.dtype == torch.float32 and lgstd_f32.is_contiguous() and lgstd_f32.shape == mu_f32.shape
+        _require_cuda(mu_f32, lgstd_f32)
+        N = mu_f32.shape[0]
+        d.mu_f32, d.ldmu_f32, d.lgstd_f32 = mu_f32.data_ptr(), mu_f32.stride(0), lgstd_f32.data_ptr()
+    else:
+        N = mu.shape[0]
     d.M, d.N, d.K = M, N, K
     d.A, d.lda = x.data_ptr(), x.stride(0)
-    d.mu, d.ldmu = mu.data_ptr(), mu.stride(0)
+    if mu is not None:
+        assert mu.shape[1] == K and mu.stride(1) == 1 and mu.dtype == torch.bfloat16
+        d.mu, d.ldmu = mu.data_ptr(), mu.stride(0)
     if sigma is not None:
         assert sigma.dtype == torch.bfloat16 and sigma.is_contiguous() and sigma.shape == mu.shape
         d.sigma = sigma.data_ptr()
@@ -233,6 +246,10 @@ def gemm_sampled(a: Split, mu: torch.Tensor, sigma: Optional[torch.Tensor], *, e
     d.out_hi = _ptr(None if out is None else out.hi)
     d.out_lo = _ptr(None if out is None else out.lo)
     d.ldc = ldc if ldc is not None else N
+    if how == "once" and (eps is not None or seed is not None):
+        nbytes = lib().blm_gemm_sampled_workspace_bytes(N, K)
+        ws = _workspace("gemm_sampled", nbytes, x.device, zero=True)   # zeroed once, the kernel re-arms its counters
+        d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     with _op("gemm_sampled:" + tag, 1, 2.0 * M * N * K):
         check(lib().blm_gemm_sampled(C.byref(d), _stream()), "blm_gemm_sampled")
 

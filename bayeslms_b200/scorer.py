@@ -97,15 +97,25 @@ def shard_ranges(weights: Sequence[int], world: int) -> List[Tuple[int, int]]:
 
 
 def _chunks_by_tokens(lengths: Sequence[int], max_tokens: int) -> List[Tuple[int, int]]:
-    out, start, tot = [], 0, 0
-    for i, n in enumerate(lengths):
-        if tot and tot + n > max_tokens:
-            out.append((start, i))
-            start, tot = i, 0
-        tot += n
-    if start < len(lengths):
-        out.append((start, len(lengths)))
-    return out
+    """Contiguous hypothesis ranges of at most ``max_tokens`` tokens each, BALANCED: the fewest chunks that
+    fit, cut at equal shares of the token count (a greedy fill leaves a small tail batch whose GEMMs run on a
+    fraction of the SMs)."""
+    if not len(lengths):
+        return []
+    csum = np.cumsum(np.asarray(lengths, dtype=np.int64))
+    total = int(csum[-1])
+    n = max(1, -(-total // max_tokens))
+    while True:
+        cuts = [0]
+        for j in range(1, n):
+            i = int(np.searchsorted(csum, j * total / n, side="left")) + 1   # first prefix reaching the share
+            cuts.append(min(max(i, cuts[-1] + 1), len(lengths)))
+        cuts.append(len(lengths))
+        cuts = sorted(set(cuts))
+        sizes = [int(csum[b - 1] - (csum[a - 1] if a else 0)) for a, b in zip(cuts[:-1], cuts[1:])]
+        if max(sizes) <= max_tokens or n >= len(lengths):
+            return list(zip(cuts[:-1], cuts[1:]))
+        n += 1
 
 
 # -------------------------------------------------------------------------- scoring

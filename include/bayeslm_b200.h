@@ -194,7 +194,20 @@ typedef struct blm_gemm_sampled_desc {
   blm_bf16* out_hi;
   blm_bf16* out_lo;
   int64_t ldc;
+  void* workspace;        /* null: tile-stationary kernel (W~ regenerated per group of 4 M tiles, never stored).
+                             blm_gemm_sampled_workspace_bytes(N, K) bytes, ZEROED ONCE by the caller and then
+                             reusable by any number of launches on one stream: GENERATE-ONCE mode -- each CTA
+                             of the persistent grid draws 1/grid of W~ exactly once at kernel entry into this
+                             L2-resident scratch (4 MB for the FFN weight), a grid-wide arrival counter gates the
+                             first weight-tile TMA load, and the rest of the launch is the pipelined tcgen05
+                             GEMM of blm_gemm (all of its epilogues).  Bit-identical results.          */
+  int64_t workspace_bytes;
+  const float* mu_f32;    /* generate-once mode only, optional: fp32 mean [N, K] (leading dimension ldmu_f32) and  */
+  int64_t ldmu_f32;       /* dense fp32 lgstd [N, K]; W~ = bf16(mu + exp(lgstd) eps) is then formed from the fp32  */
+  const float* lgstd_f32; /* parameters, bit-identical to blm_reparam's bf16 output (mu / sigma may be null)       */
 } blm_gemm_sampled_desc;
+
+int64_t blm_gemm_sampled_workspace_bytes(int64_t N, int64_t K);
 
 /* sigma[i] = bf16(exp(lgstd[i])): the sample-independent scale the fused GEMM multiplies eps by. */
 int blm_sigma_bf16(const float* lgstd, blm_bf16* sigma, int64_t n, blm_stream stream);

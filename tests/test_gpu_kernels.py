@@ -218,11 +218,39 @@ def test_cluster_sampled_gemm_bit_exact(ops, M, N, K):
         eps = torch.randn(N, K, device=DEV) if mode == "ptr" else ops.philox_normal(11, 4, N * K, DEV).view(N, K)
         out = torch.empty(M, N, device=DEV)
         ops.gemm_sampled(A, mu_b, sg_b, eps=eps if mode == "ptr" else None, seed=None if mode == "ptr" else 11,
-                         stream_id=4, resid=resid, out_f32=out)
+                         stream_id=4, resid=resid, out_f32=out, how="tile")
         wt = torch.addcmul(mu_b.float(), sg_b.float(), eps).to(torch.bfloat16)
         ref = torch.empty(M, N, device=DEV)
         ops.gemm(A, ops.Split(wt), prec="bf16", resid=resid, out_f32=ref, k_chunk=0)
         assert torch.equal(out, ref), mode
+
+
+@pytest.mark.parametrize("M,N,K", [(4500, 520, 328), (2048, 128, 64), (65536, 512, 4096), (30000, 4096, 512)])
+def test_generate_once_sampled_gemm_bit_exact(ops, M, N, K):
+    """blm_gemm_sampled in generate-once mode (W~ drawn once per launch into the L2-resident scratch, grid-wide
+    arrival counter, then the pipelined GEMM): bit-identical to bf16(mu + sigma * eps) fed to the plain GEMM for
+    injected and Philox noise; repeated launches reuse the self-re-arming workspace; bf16 outputs + GELU too."""
+    a = torch.randn(M, K, device=DEV) * 0.5
+    mu = torch.randn(N, K, device=DEV) * 0.05
+    ls = torch.rand(N, K, device=DEV) * -3.0 - 2.0
+    A, mu_b, sg_b = ops.split(a, "bf16"), ops.split(mu, "bf16").hi, ops.sigma_bf16(ls)
+    resid = torch.randn(M, N, device=DEV)
+    for rep in range(2):
+        for mode in ("ptr", "philox"):
+            sid = 4 + rep
+            eps = torch.randn(N, K, device=DEV) if mode == "ptr" else ops.philox_normal(11, sid, N * K, DEV).view(N, K)
+            out = torch.empty(M, N, device=DEV)
+            ops.gemm_sampled(A, mu_b, sg_b, eps=eps if mode == "ptr" else None, seed=None if mode == "ptr" else 11,
+                             stream_id=sid, resid=resid, out_f32=out, how="once")
+            wt = torch.addcmul(mu_b.float(), sg_b.float(), eps).to(torch.bfloat16)
+            ref = torch.empty(M, N, device=DEV)
+            ops.gemm(A, ops.Split(wt), prec="bf16", resid=resid, out_f32=ref, k_chunk=0)
+            assert torch.equal(out, ref), (mode, rep)
+    bias = torch.randn(N, device=DEV)
+    o1, o2 = ops.empty_split(M, N, "bf16", DEV), ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm_sampled(A, mu_b, sg_b, seed=11, stream_id=5, bias=bias, act=ops.ACT_GELU, out=o1, how="once")
+    ops.gemm(A, ops.Split(wt), prec="bf16", bias=bias, act=ops.ACT_GELU, out=o2)
+    assert torch.equal(o1.hi, o2.hi)
 
 
 def test_fast_gelu_epilogue(ops):

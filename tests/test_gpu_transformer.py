@@ -163,11 +163,11 @@ def test_fused_sampled_gemm_bit_exact_and_model_level(golden):
     A, mu_b, sg_b = ops.split(a, "bf16"), ops.split(mu, "bf16").hi, ops.sigma_bf16(ls)
     assert torch.equal(sg_b, torch.exp(ls).to(torch.bfloat16))
     bias = torch.randn(N, device=DEV)
-    for mode in ("ptr", "philox"):
+    for mode, how in (("ptr", "tile"), ("philox", "tile"), ("ptr", "once"), ("philox", "once")):
         eps = torch.randn(N, K, device=DEV) if mode == "ptr" else ops.philox_normal(11, 4, N * K, DEV).view(N, K)
         out = torch.empty(M, N, device=DEV)
         ops.gemm_sampled(A, mu_b, sg_b, eps=eps if mode == "ptr" else None, seed=None if mode == "ptr" else 11,
-                         stream_id=4, bias=bias, out_f32=out)
+                         stream_id=4, bias=bias, out_f32=out, how=how)
         wt = torch.addcmul(mu_b.float(), sg_b.float(), eps).to(torch.bfloat16)
         ref = torch.empty(M, N, device=DEV)
         ops.gemm(A, ops.Split(wt), prec="bf16", bias=bias, out_f32=ref)
@@ -178,6 +178,17 @@ def test_fused_sampled_gemm_bit_exact_and_model_level(golden):
     a1 = net.score(batch, K=2, seed=5, prec="bf16").cpu()
     a2 = net.score(batch, K=2, seed=5, prec="bf16", fused_sampling=True).cpu()
     assert (a1 - a2).abs().max().item() < 2e-2   # differ only by bf16 rounding of mu before the noise is added
+    # the default fast-mode path (generate-once kernel on the fp32 parameters) has the bits of reparam + gemm
+    import os
+    os.environ["BLM_NO_FUSED_SAMPLING"] = "1"
+    try:
+        a3 = net.score(batch, K=2, seed=5, prec="bf16").cpu()
+        e = O.draw_eps(rec["state_dict"], O.Config(rec["cfg"]), 7)
+        b3 = net.score(batch, eps_list=[e], prec="bf16").cpu()
+    finally:
+        del os.environ["BLM_NO_FUSED_SAMPLING"]
+    assert torch.equal(a1, a3)
+    assert torch.equal(net.score(batch, eps_list=[e], prec="bf16").cpu(), b3)
 
 
 def test_logit_interpolation_matches_oracle(golden):

@@ -99,8 +99,11 @@ line("kl_gauss [4096,8192] (268 MB)", timeit(lambda: ops.kl_gauss(mu2, ls2, out)
 # sampled FFN2: fused vs materialise + plain GEMM
 sig = ops.sigma_bf16(ls)
 mub = ops.split(mu, "bf16")
-line("gemm_sampled ffn2 [M,512,4096] philox fused", timeit(lambda: ops.gemm_sampled(h, mub.hi, sig, seed=1, stream_id=5, resid=x32, out_f32=y)), 2.0 * M * d * F)
-line("gemm_sampled ffn2 [M,512,4096] mean", timeit(lambda: ops.gemm_sampled(h, mub.hi, None, resid=x32, out_f32=y)), 2.0 * M * d * F)
+line("gemm_sampled ffn2 [M,512,4096] philox generate-once", timeit(lambda: ops.gemm_sampled(h, mub.hi, sig, seed=1, stream_id=5, resid=x32, out_f32=y, how="once")), 2.0 * M * d * F)
+line("gemm_sampled ffn2 [M,512,4096] philox tile-stationary", timeit(lambda: ops.gemm_sampled(h, mub.hi, sig, seed=1, stream_id=5, resid=x32, out_f32=y, how="tile")), 2.0 * M * d * F)
+line("gemm_sampled ffn2 [M,512,4096] mean (tile kernel)", timeit(lambda: ops.gemm_sampled(h, mub.hi, None, resid=x32, out_f32=y)), 2.0 * M * d * F)
+sigT = ops.sigma_bf16(ls.t().contiguous()); muT = ops.split(mu.t().contiguous(), "bf16")
+line("gemm_sampled gpnn [M,4096,512] philox generate-once +GELU bf16", timeit(lambda: ops.gemm_sampled(x, muT.hi, sigT, seed=1, stream_id=6, bias=bF, act=ACT_GELU, out=hout, how="once")), 2.0 * M * d * F)
 def mat():
     _, w = ops.reparam(mu, ls, seed=1, stream_id=5, prec="bf16")
     ops.gemm(h, w, resid=x32, out_f32=y)
