@@ -21,6 +21,7 @@
 //     pass 3   the same y packed to bf16, [32 rows x 64 cols] tiles -> TMA store
 // All global traffic of the epilogue is TMA: a row-per-thread access pattern costs 32 LSU wavefronts per
 // instruction and was the measured bound of the fp32-output GEMM epilogues (r01 profiles).
+#include <stdlib.h>
 #include <string.h>
 
 #include "blm_gemm_common.cuh"
@@ -228,11 +229,6 @@ __global__ void __launch_bounds__(384, 1) gemm_ln_kernel(const __grid_constant__
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) r[q] = *reinterpret_cast<const float4*>(b + lane * 128 + ((q ^ sw) << 4));
-          __syncwarp();  // every lane has read its row: the buffer may be refilled
-          if (lane == 0 && c + 2 < nch) {
-            mbar_arrive_expect_tx(&rb[c & 1], 4096u);
-            tma_load_2d(b, &p.tmR, &rb[c & 1], col_base + (c + 2) * 32, m0, kEvictFirst);
-          }
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) r[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,6 +243,14 @@ __global__ void __launch_bounds__(384, 1) gemm_ln_kernel(const __grid_constant__
           v[4 * q + 1] += bb.y + r[q].y;
           v[4 * q + 2] += bb.z + r[q].z;
           v[4 * q + 3] += bb.w + r[q].w;
+        }
+        // refill only after every lane has consumed its loads (see the pair kernel below)
+        if (rows_ok) {
+          __syncwarp();
+          if (lane == 0 && c + 2 < nch) {
+            mbar_arrive_expect_tx(&rb[c & 1], 4096u);
+            tma_load_2d((c & 1) ? buf1 : buf0, &p.tmR, &rb[c & 1], col_base + (c + 2) * 32, m0, kEvictFirst);
+          }
         }
         if (c == 0) shift = v[0];
         float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -368,8 +372,416 @@ __global__ void __launch_bounds__(384, 1) gemm_ln_kernel(const __grid_constant__
   }
 }
 
+
+// ===================================================================================================
+// v2 (N = 512): a CTA PAIR splits the row block by columns -- CTA r of the 2-CTA cluster owns columns
+// [256 r, 256 r + 256) of the same 128 rows.  Each CTA then runs the plain GEMM pipeline on a 128 x 256 tile
+// (4-stage 48 KB ring, TWO 256-column TMEM accumulator stages), so the LayerNorm epilogue of tile i overlaps
+// the MMAs of tile i + 1 -- what the one-CTA kernel above cannot do with all 512 TMEM columns in one
+// accumulator (measured: 315 us fused vs 279 us unfused at K = 4096).  The price is one exchange per tile:
+// the two warps of a CTA that share a row merge their quarter-row (mean, M2) through shared memory, then
+// the pair swaps half-row statistics through DISTRIBUTED shared memory (st.shared::cluster + a remote
+// mbarrier arrive, 1 KB per tile), double buffered by tile parity.  The pair is otherwise uncoupled: each CTA
+// has its own TMA producer, MMA issuer (cta_group::1) and TMEM.
+namespace ln2 {
+constexpr int kNH = 256;                       // columns per CTA
+constexpr int kABytes = kBM * kBK * 2;         // 16 KB
+constexpr int kBBytes = kNH * kBK * 2;         // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+template <int STAGES, int NBUF>
+struct Smem {
+  static constexpr int kStgOff = STAGES * kStageBytes;        // 8 warps x NBUF x 4 KB, 1024-B aligned
+  static constexpr int kXchOff = kStgOff + 8 * NBUF * 4096;   // remote half-row statistics: float2 [2 parities][128]
+  static constexpr int kBarOff = kXchOff + 2 * 128 * 8;
+  // full[STAGES] empty[STAGES] tfull[2] tempty[2] rfull[8][2] xbar[2]
+  static constexpr int kNumBars = 2 * STAGES + 4 + 16 + 2;
+  static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
+  static_assert(kBytes <= 232448, "shared memory budget of one sm_100 CTA");
+};
+}  // namespace ln2
+
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t ok = 0, polls = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (((++polls) & 0x3fffu) == 0u && (clock64() - t0) > 8000000000LL) {
+      printf("blm: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+template <int STAGES, int NBUF>
+__global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant__ GemmLnParams p) {
+  using L = ln2::Smem<STAGES, NBUF>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("blm: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* rfull = tempty + 2;   // [8 warps][2]
+  uint64_t* xbar = rfull + 16;    // [2 parities]: 4 remote arrivals (the peer's column-group-0 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int ncol0 = static_cast<int>(rank) * ln2::kNH;   // first output column of this CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmR);
+    tma_prefetch_desc(&p.tmO);
+    tma_prefetch_desc(&p.tmH);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 8);
+      mbar_init(&xbar[s], 4);
+    }
+    for (int s = 0; s < 16; ++s) mbar_init(&rfull[s], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anyone arrives on them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair_id; t < p.m_tiles; t += n_pairs) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], ln2::kStageBytes);
+          uint8_t* st = smem + stage * ln2::kStageBytes;
+          tma_load_2d(st, &p.tmA, &full[stage], kb * kBK, t * kBM, kEvictNormal);
+          tma_load_2d(st + ln2::kABytes, &p.tmB, &full[stage], kb * kBK, ncol0, kEvictLast);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, ln2::kNH);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = pair_id; t < p.m_tiles; t += n_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * ln2::kNH);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + stage * ln2::kStageBytes);
+          const uint64_t da = umma_desc_sw128(st), db = umma_desc_sw128(st + ln2::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kEpiWarp0) {
+    // ---------------------------------------------------------- epilogue
+    constexpr int kCh = ln2::kNH / 64;              // 4 chunks of 32 columns per warp
+    const int ew = warp - kEpiWarp0;
+    const int lane_grp = warp & 3;
+    const int col_grp = ew >> 2;
+    const int col_base = ncol0 + col_grp * (ln2::kNH / 2);   // first global column of this warp
+    uint8_t* bufs = smem + L::kStgOff + ew * NBUF * 4096;
+    uint64_t* rb = rfull + ew * 2;
+    float2* xch = reinterpret_cast<float2*>(smem + L::kXchOff);
+    const uint32_t xch_peer = mapa_shared(smem_u32(xch), rank ^ 1u);
+    const uint32_t xbar_peer[2] = {mapa_shared(smem_u32(&xbar[0]), rank ^ 1u), mapa_shared(smem_u32(&xbar[1]), rank ^ 1u)};
+    // local exchange slot of this warp's rows: the first 256 bytes of the PARTNER-visible staging buffer
+    float2* lx_mine = reinterpret_cast<float2*>(bufs);
+    float2* lx_partner = reinterpret_cast<float2*>(smem + L::kStgOff + (ew ^ 4) * NBUF * 4096);
+    const int sw = lane & 7;
+    const int row = lane_grp * 32 + lane;
+    uint32_t rph[2] = {0u, 0u};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    constexpr float kInvQ = 1.0f / 128.0f;   // quarter row = 128 columns
+
+    for (int t = pair_id; t < p.m_tiles; t += n_pairs, ++it) {
+      const int m0 = t * kBM + lane_grp * 32;
+      const bool rows_ok = m0 < p.M;
+      const int par = it & 1;
+      const uint32_t xph = static_cast<uint32_t>(it >> 1) & 1u;
+      // prefetch the first residual chunk(s) while this tile's MMAs still run
+      if (rows_ok && lane == 0) {
+        bulk_wait_group_read0();
+#pragma unroll
+        for (int c = 0; c < NBUF; ++c) {
+          mbar_arrive_expect_tx(&rb[c], 4096u);
+          tma_load_2d(bufs + c * 4096, &p.tmR, &rb[c], col_base + c * 32, m0, kEvictFirst);
+        }
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                             static_cast<uint32_t>(acc * ln2::kNH + col_grp * (ln2::kNH / 2));
+
+      // ---- pass 1
+      float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < kCh; ++c) {
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32), v);
+        float4 r[8];
+        if (rows_ok) {
+          const int bi = c % NBUF;
+          uint8_t* b = bufs + bi * 4096;
+          mbar_wait(&rb[bi], rph[bi]);
+          rph[bi] ^= 1u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = *reinterpret_cast<const float4*>(b + lane * 128 + ((q ^ sw) << 4));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld_wait();
+        const int col0 = col_base + c * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+          v[4 * q] += bb.x + r[q].x;
+          v[4 * q + 1] += bb.y + r[q].y;
+          v[4 * q + 2] += bb.z + r[q].z;
+          v[4 * q + 3] += bb.w + r[q].w;
+        }
+        // The buffer is refilled only after every lane has CONSUMED its shared-memory loads (the adds above wait
+        // on their scoreboards).  Issuing the TMA right after the loads were merely issued raced: with the tensor
+        // core saturating shared-memory bandwidth under this epilogue (K = 4096 mainloop), queued LDS were
+        // overtaken by the next chunk's TMA write (sporadic wrong rows, found by the float64 parity test).
+        if (rows_ok) {
+          __syncwarp();
+          if (lane == 0 && c + NBUF < kCh) {
+            const int bi = c % NBUF;
+            mbar_arrive_expect_tx(&rb[bi], 4096u);
+            tma_load_2d(bufs + bi * 4096, &p.tmR, &rb[bi], col_base + (c + NBUF) * 32, m0, kEvictFirst);
+          }
+        }
+        if (c == 0) shift = v[0];
+        float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float d0 = v[j] - shift, d1 = v[j + 1] - shift;
+          a0 += d0;
+          a1 += d1;
+          q0 = fmaf(d0, d0, q0);
+          q1 = fmaf(d1, d1, q1);
+        }
+        s1 += a0 + a1;
+        s2 += q0 + q1;
+        tmem_st_32x32(tlane + static_cast<uint32_t>(c * 32), v);
+      }
+      tmem_st_wait();
+
+      // ---- quarter rows -> half row (the partner warp of this CTA), then half rows across the pair
+      const float mean_q = shift + s1 * kInvQ;
+      const float m2_q = fmaxf(s2 - s1 * s1 * kInvQ, 0.0f);
+      __syncwarp();   // every lane has consumed the residual chunk that shared this buffer
+      lx_mine[lane] = make_float2(mean_q, m2_q);
+      epi_bar_sync(256);
+      const float2 o = lx_partner[lane];
+      const float dq = o.x - mean_q;
+      const float mean_h = 0.5f * (mean_q + o.x);
+      const float m2_h = m2_q + o.y + dq * dq * 64.0f;            // n_a n_b / (n_a + n_b) = 128 * 128 / 256
+      if (col_grp == 0) {
+        st_cluster_f32x2(xch_peer + static_cast<uint32_t>((par * 128 + row) * 8), mean_h, m2_h);
+        fence_acq_rel_cluster();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(xbar_peer[par]);
+      }
+      mbar_wait_cluster(&xbar[par], xph);
+      const float2 oh = xch[par * 128 + row];
+      const float dh = oh.x - mean_h;
+      const float mean = 0.5f * (mean_h + oh.x);
+      const float var = (m2_h + oh.y + dh * dh * 128.0f) * (1.0f / 512.0f);   // 256 * 256 / 512
+      const float rstd = rsqrtf(var + p.eps);
+      const float nmr = -mean * rstd;
+      epi_bar_sync(256);   // both partners have read the local slots before they become staging again
+
+      // ---- pass 2: fp32 output chunks
+      if (p.has_f32) {
+#pragma unroll 1
+        for (int c = 0; c < kCh; ++c) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32), v);
+          const int col0 = col_base + c * 32;
+          uint8_t* b = bufs + (c % NBUF) * 4096;
+          if (lane == 0) {
+            if (NBUF == 1) bulk_wait_group_read0(); else bulk_wait_group_read1();
+          }
+          tmem_ld_wait();
+          __syncwarp();
+          if (rows_ok) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0) + q);
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + col0) + q);
+              float4 y;
+              y.x = fmaf(fmaf(v[4 * q], rstd, nmr), g.x, be.x);
+              y.y = fmaf(fmaf(v[4 * q + 1], rstd, nmr), g.y, be.y);
+              y.z = fmaf(fmaf(v[4 * q + 2], rstd, nmr), g.z, be.z);
+              y.w = fmaf(fmaf(v[4 * q + 3], rstd, nmr), g.w, be.w);
+              *reinterpret_cast<float4*>(b + lane * 128 + ((q ^ sw) << 4)) = y;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmO, b, col0, m0);
+              bulk_commit_group();
+            }
+          }
+        }
+      }
+      // ---- pass 3: bf16 output
+      if (p.has_hi) {
+#pragma unroll 1
+        for (int c = 0; c < kCh; c += 2) {
+          float va[32], vb[32];
+          __syncwarp();
+          tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32), va);
+          tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32 + 32), vb);
+          const int col0 = col_base + c * 32;
+          uint8_t* b = bufs + ((c >> 1) % NBUF) * 4096;
+          if (lane == 0) {
+            if (NBUF == 1) bulk_wait_group_read0(); else bulk_wait_group_read1();
+          }
+          tmem_ld_wait();
+          __syncwarp();
+          if (rows_ok) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0) + q);
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + col0) + q);
+              va[4 * q] = fmaf(fmaf(va[4 * q], rstd, nmr), g.x, be.x);
+              va[4 * q + 1] = fmaf(fmaf(va[4 * q + 1], rstd, nmr), g.y, be.y);
+              va[4 * q + 2] = fmaf(fmaf(va[4 * q + 2], rstd, nmr), g.z, be.z);
+              va[4 * q + 3] = fmaf(fmaf(va[4 * q + 3], rstd, nmr), g.w, be.w);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + 32) + q);
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + 32) + q);
+              vb[4 * q] = fmaf(fmaf(vb[4 * q], rstd, nmr), g.x, be.x);
+              vb[4 * q + 1] = fmaf(fmaf(vb[4 * q + 1], rstd, nmr), g.y, be.y);
+              vb[4 * q + 2] = fmaf(fmaf(vb[4 * q + 2], rstd, nmr), g.z, be.z);
+              vb[4 * q + 3] = fmaf(fmaf(vb[4 * q + 3], rstd, nmr), g.w, be.w);
+            }
+            stage_chunk_bf16(va, b, lane, 0);
+            stage_chunk_bf16(vb, b, lane, 1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmH, b, col0, m0);
+              bulk_commit_group();
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+    if (lane == 0) bulk_wait_group0();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be writing statistics into this CTA's shared memory
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int STAGES, int NBUF>
+static int launch_ln2(const GemmLnParams& p, cudaStream_t st) {
+  int pairs = num_sms() / 2;
+  if (pairs > p.m_tiles) pairs = p.m_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = ln2::Smem<STAGES, NBUF>::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln2_kernel<STAGES, NBUF>, p));
+  return BLM_OK;
+}
+
 int gemm_ln_init() {
   BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ln::kSmemBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln2_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ln2::Smem<4, 1>::kBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ln2::Smem<3, 2>::kBytes));
   return BLM_OK;
 }
 
@@ -416,6 +828,17 @@ extern "C" int blm_gemm_ln(const blm_gemm_ln_desc* d, blm_stream stream) {
   p.eps = d->eps;
   p.has_f32 = d->out_f32 != nullptr;
   p.has_hi = d->out_hi != nullptr;
+  // N = 512: CTA pairs split the columns (two TMEM stages, epilogue overlapped); BLM_GEMM_LN_V1=1 keeps the
+  // one-CTA full-row kernel for A/B
+  static const bool force_v1 = getenv("BLM_GEMM_LN_V1") != nullptr;
+  if (d->N == 512 && !force_v1 && num_sms() >= 2) {
+    rc = encode_tmap_bf16(&p.tmB, d->B, d->N, d->K, d->ldb, ln2::kNH);
+    if (rc != BLM_OK) return rc;
+    // deep ring + one staging buffer when the mainloop hides the epilogue (K = 4096), shallower ring + double
+    // buffered staging when the epilogue is the longer leg (K = 512)
+    if (p.kblocks > 16) return launch_ln2<4, 1>(p, as_stream(stream));
+    return launch_ln2<3, 2>(p, as_stream(stream));
+  }
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
   gemm_ln_kernel<<<grid, 384, ln::kSmemBytes, as_stream(stream)>>>(p);
   BLM_CHECK_CUDA(cudaGetLastError());

@@ -272,9 +272,10 @@ class _TmRun:
 
     # part D: second FFN projection + residual, LayerNorm 2
     def part_d(self, L, x1_32, h: Split, w2: Split):
-        # K = 4096: the one-accumulator-stage kernel cannot hide its epilogue behind the next tile's MMAs and its
-        # ring holds two K blocks; measured 315 us fused vs 279 us for blm_gemm + blm_layernorm (BLM_GEMM_LN_FFN2=1)
-        if self.fused_ln and os.environ.get("BLM_GEMM_LN_FFN2") is not None:
+        # d = 512 runs the CTA-pair kernel (two TMEM stages: the LayerNorm epilogue hides behind the next tile's
+        # MMAs).  Other widths use the one-accumulator-stage kernel, which loses to blm_gemm + blm_layernorm at
+        # K = 4096 (315 vs 279 us), so they stay unfused here.  BLM_NO_GEMM_LN_FFN2=1 is the A/B switch.
+        if self.fused_ln and self.d == 512 and os.environ.get("BLM_NO_GEMM_LN_FFN2") is None:
             g, b, eps = L["norm2"]
             return ops.gemm_ln(h, w2, bias=L["b2"], resid=x1_32, gamma=g, beta=b, eps=eps, tag="ffn2")
         y = self.f32(self.d)

@@ -6,7 +6,7 @@
 Workload at N=1 (BASELINE.json configs[1]): Bayesian Transformer LM, 6 layers, d=512, FFN=4096,
 8 heads, V=30000, T_bayes_pos=FFN, 50-best lists, random-init weights of that architecture,
 synthetic n-best lists (bayeslms_b200/synth.py).  One *step* scores UTTS_PER_STEP utterances x
-50 hypotheses (~0.2 M scored positions) in packed batches of <= 65536 tokens; with N ranks every
+50 hypotheses (~0.2 M scored positions) in balanced packed batches of <= 65536 tokens; with N ranks every
 rank scores its own UTTS_PER_STEP utterances (weak scaling, no data-path collective; one score
 gather per step).  Reported:
 
@@ -329,7 +329,12 @@ def main():
     # ---- K = 4 sampled and precise-mode numbers (same lists)
     k4_steps = max(1, args.steps // 2)
     step(K=4, seed=1111)
+    ops.STATS.timing = {}
     k4_ms = timed(lambda: step(K=4, seed=1111), k4_steps)
+    k4_timing, ops.STATS.timing = ops.STATS.timing, None
+    sg = k4_timing.get("gemm_sampled:ffn2", [])
+    sg_ms = sum(a.elapsed_time(b) for a, b, _ in sg)
+    sg_tf = (sum(w for _, _, w in sg) / (sg_ms / 1e3) / 1e12) if sg_ms else 0.0
     step(prec="bf16x3")
     px_ms = timed(lambda: step(prec="bf16x3"), k4_steps)
 
@@ -390,7 +395,15 @@ def main():
                          "share_of_step": nll_ms / tot},
             "kernel_time_shares": {k: round(v / tot, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
             "sampled_k4": {"value": n_tokens * world * k4_steps / (k4_ms / 1e3), "unit": "tokens/s", "K": 4,
-                           "noise": "Philox4x32-10 on device"},
+                           "noise": "Philox4x32-10 on device",
+                           # north_star (a): the reparameterised-weight GEMM of the sampled FFN (layer 0 linear2,
+                           # [M, 512] x [512, 4096]^T), W~ drawn inside the launch; 2*M*N*K FLOP per launch over the
+                           # CUDA-event time of its launches in this K = 4 run
+                           "sampled_gemm_roofline": {
+                               "kernel": "gemm_kernel + generate_weights (blm_gemm_sampled, generate-once)",
+                               "bound": "tensor", "achieved": sg_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
+                               "frac": sg_tf / pk["tensor"] if pk["tensor"] else None, "launches": len(sg),
+                               "avg_launch_ms": sg_ms / len(sg) if sg else None}},
             "precise": {"value": n_tokens * world * k4_steps / (px_ms / 1e3), "unit": "tokens/s", "dtype": "bf16x3",
                         "max_abs_score_diff_vs_bf16": float(np.abs(fast - precise).max()),
                         "one_best_agreement": float(np.mean(np.asarray(picks_f) == np.asarray(picks_p))),
