@@ -128,12 +128,11 @@ __device__ __forceinline__ void gelu_fast_h2(float& a, float& b) {
   const __half2 x = __floats2half2_rn(a, b);
   const __half2 ax = __habs2(x);
   const __half2 t = __hmin2(__hmul2(ax, __float2half2_rn(0.70710678118654752440f)), __float2half2_rn(4.0f));
-  __half2 q = __hfma2(t, __float2half2_rn(-1.002195230e-04f), __float2half2_rn(4.615629764e-04f));
-  q = __hfma2(q, t, __float2half2_rn(2.302262028e-03f));
-  q = __hfma2(q, t, __float2half2_rn(-2.945254180e-02f));
-  q = __hfma2(q, t, __float2half2_rn(1.489636837e-01f));
-  q = __hfma2(q, t, __float2half2_rn(9.183286407e-01f));
-  q = __hfma2(q, t, __float2half2_rn(1.627913732e+00f));
+  // degree-3 fit of q (weighted by the sensitivity |x|/2 erfc(t) ln2 t of the result): 1.2e-5 absolute on GELU in
+  // exact arithmetic, far below the fp16 evaluation itself -- three HFMA2 fewer per pair than the degree-6 fit
+  __half2 q = __hfma2(t, __float2half2_rn(-1.632555e-02f), __float2half2_rn(1.2818365e-01f));
+  q = __hfma2(q, t, __float2half2_rn(9.3115127e-01f));
+  q = __hfma2(q, t, __float2half2_rn(1.62531592e+00f));
   const __half2 e = h2exp2(__hneg2(__hmul2(q, t)));  // erfc(t)
   const __half2 r = __hfma2(__hmul2(ax, __float2half2_rn(-0.5f)), e, __hmax2(x, __float2half2_rn(0.0f)));
   const float2 f = __half22float2(r);

@@ -616,6 +616,22 @@ def lstm_logits(model, x: torch.Tensor, hidden):
     return logits[:, :V].reshape(T, B, V), (hT, cT)
 
 
+@torch.no_grad()
+def lstm_token_nll(model, x: torch.Tensor, targets: torch.Tensor, hidden, prec: str = "bf16x3"):
+    """Evaluation step of the training loop (train.py:440-457): (T, B) ids + carried (h, c) -> per-token NLL
+    [T * B] in the reference's (t, b) order and the state after the batch; posterior means, logits never stored."""
+    T, B = x.shape
+    if B > LSTM_MAX_ROWS:
+        raise _lib.BlmError(f"batch {B} exceeds {LSTM_MAX_ROWS} rows per recurrence launch")
+    plan = plan_for(model, prec)
+    W = _lstm_weights(model, plan, None, None)
+    lengths = torch.full((B,), T, dtype=torch.int32, device=x.device)
+    _, out, hT, cT = _lstm_forward(model, plan, W, x.to(torch.int32).contiguous(), lengths, hidden[0].float(),
+                                   hidden[1].float(), want_f32=False, want_split=True)
+    nll = ops.vocab_nll(out, plan.E, plan.dec_b, targets.reshape(-1).to(torch.int32).contiguous(), prec=prec)
+    return nll, (hT, cT)
+
+
 def _pad_time_major(seqs: Sequence[Sequence[int]], device):
     """list of id lists -> (int32 [T, B] time-major right-padded with 0, int32 lengths [B]) on device."""
     B = len(seqs)
