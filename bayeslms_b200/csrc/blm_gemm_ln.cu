@@ -74,6 +74,11 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[3
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // at most one committed bulk store of this thread may still be reading its shared-memory source
 __device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// at most N of this thread's most recent bulk stores may still be reading their shared-memory sources
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
 __global__ void __launch_bounds__(384, 1) gemm_ln_kernel(const __grid_constant__ GemmLnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -393,8 +398,8 @@ struct Smem {
   static constexpr int kStgOff = STAGES * kStageBytes;        // 8 warps x NBUF x 4 KB, 1024-B aligned
   static constexpr int kXchOff = kStgOff + 8 * NBUF * 4096;   // remote half-row statistics: float2 [2 parities][128]
   static constexpr int kBarOff = kXchOff + 2 * 128 * 8;
-  // full[STAGES] empty[STAGES] tfull[2] tempty[2] rfull[8][2] xbar[2]
-  static constexpr int kNumBars = 2 * STAGES + 4 + 16 + 2;
+  // full[STAGES] empty[STAGES] tfull[2] tempty[2] rfull[8][NBUF] xbar[2]
+  static constexpr int kNumBars = 2 * STAGES + 4 + 8 * NBUF + 2;
   static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
   static_assert(kBytes <= 232448, "shared memory budget of one sm_100 CTA");
 };
@@ -441,8 +446,8 @@ __global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant_
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* rfull = tempty + 2;   // [8 warps][2]
-  uint64_t* xbar = rfull + 16;    // [2 parities]: 4 remote arrivals (the peer's column-group-0 warps)
+  uint64_t* rfull = tempty + 2;          // [8 warps][NBUF]
+  uint64_t* xbar = rfull + 8 * NBUF;     // [2 parities]: 4 remote arrivals (the peer's column-group-0 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant_
       mbar_init(&tempty[s], 8);
       mbar_init(&xbar[s], 4);
     }
-    for (int s = 0; s < 16; ++s) mbar_init(&rfull[s], 1);
+    for (int s = 0; s < 8 * NBUF; ++s) mbar_init(&rfull[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant_
     const int col_grp = ew >> 2;
     const int col_base = ncol0 + col_grp * (ln2::kNH / 2);   // first global column of this warp
     uint8_t* bufs = smem + L::kStgOff + ew * NBUF * 4096;
-    uint64_t* rb = rfull + ew * 2;
+    uint64_t* rb = rfull + ew * NBUF;
     float2* xch = reinterpret_cast<float2*>(smem + L::kXchOff);
     const uint32_t xch_peer = mapa_shared(smem_u32(xch), rank ^ 1u);
     const uint32_t xbar_peer[2] = {mapa_shared(smem_u32(&xbar[0]), rank ^ 1u), mapa_shared(smem_u32(&xbar[1]), rank ^ 1u)};
@@ -547,7 +552,9 @@ __global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant_
     float2* lx_partner = reinterpret_cast<float2*>(smem + L::kStgOff + (ew ^ 4) * NBUF * 4096);
     const int sw = lane & 7;
     const int row = lane_grp * 32 + lane;
-    uint32_t rph[2] = {0u, 0u};
+    uint32_t rph[NBUF];
+#pragma unroll
+    for (int c = 0; c < NBUF; ++c) rph[c] = 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
@@ -664,9 +671,7 @@ __global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant_
           tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32), v);
           const int col0 = col_base + c * 32;
           uint8_t* b = bufs + (c % NBUF) * 4096;
-          if (lane == 0) {
-            if (NBUF == 1) bulk_wait_group_read0(); else bulk_wait_group_read1();
-          }
+          if (lane == 0) bulk_wait_group_read_n<NBUF - 1>();   // the store that last used this buffer has left it
           tmem_ld_wait();
           __syncwarp();
           if (rows_ok) {
@@ -700,9 +705,7 @@ __global__ void __launch_bounds__(384, 1) gemm_ln2_kernel(const __grid_constant_
           tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32 + 32), vb);
           const int col0 = col_base + c * 32;
           uint8_t* b = bufs + ((c >> 1) % NBUF) * 4096;
-          if (lane == 0) {
-            if (NBUF == 1) bulk_wait_group_read0(); else bulk_wait_group_read1();
-          }
+          if (lane == 0) bulk_wait_group_read_n<NBUF - 1>();   // the store that last used this buffer has left it
           tmem_ld_wait();
           __syncwarp();
           if (rows_ok) {
@@ -782,6 +785,8 @@ int gemm_ln_init() {
                                       ln2::Smem<4, 1>::kBytes));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ln2::Smem<3, 2>::kBytes));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ln2::Smem<2, 4>::kBytes));
   return BLM_OK;
 }
 
@@ -837,6 +842,10 @@ extern "C" int blm_gemm_ln(const blm_gemm_ln_desc* d, blm_stream stream) {
     // deep ring + one staging buffer when the mainloop hides the epilogue (K = 4096), shallower ring + double
     // buffered staging when the epilogue is the longer leg (K = 512)
     if (p.kblocks > 16) return launch_ln2<4, 1>(p, as_stream(stream));
+    // <2, 4> (every residual chunk of the tile prefetched, two ring stages) measured slower: 90.6 vs 85.0 us at
+    // M = 52833 -- the K = 512 mainloop needs the third ring stage more than the epilogue needs the buffers
+    static const bool deep_stg = getenv("BLM_GEMM_LN_24") != nullptr;   // A/B switch
+    if (deep_stg) return launch_ln2<2, 4>(p, as_stream(stream));
     return launch_ln2<3, 2>(p, as_stream(stream));
   }
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();

@@ -184,7 +184,7 @@ def cpu_port_tokens_per_s(data, n_utts, state_dict):
     return toks / dt, toks, dt, cores
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
     reference cannot travel to the GPU box), all host threads, bounded sample per step."""
     if rank != 0:
@@ -206,14 +206,14 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = tok * args.steps / dt
     sample = f"{n_utts} utterances x {NBEST}-best ({tok} tokens) per step, batch 1 per hypothesis"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "nbest_rescoring_tokens_per_sec", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():
@@ -227,8 +227,17 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    # stdout carries exactly ONE line, the JSON result: everything else that writes to fd 1 (NCCL's version banner,
+    # library chatter) is sent to stderr, and the result is written to the saved descriptor at the end
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return 0
 
     import torch.distributed as dist
@@ -239,8 +248,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner to stdout; the driver parses stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.init(local_rank)
     warmup = max(args.warmup, 3)
@@ -390,8 +397,9 @@ def main():
                          "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tensor"] if pk["tensor"] else None,
                          # dram__bytes_read + write of one launch at M = 52950 rows, ncu --set full
-                         # (profiles/r01g_nll_ew8_ncu_summary.txt); algorithmic bytes at that M: 85.0 MB
-                         "traffic": 90875648, "traffic_unit": "bytes/launch at M=52950",
+                         # (profiles/r01as_top_kernels_ncu_full.txt: 85.38 MB read + 3.35 MB written); algorithmic
+                         # bytes at that M: V*d*2 + M*d*2 + 12*M = 85.6 MB
+                         "traffic": 88725504, "traffic_unit": "bytes/launch at M=52950",
                          "peak_source": pk["src"] + " bf16_tflops_sustained", "launches": nll_n,
                          "avg_launch_ms": nll_ms / nll_n if nll_n else None,
                          "share_of_step": nll_ms / tot},
@@ -417,7 +425,7 @@ def main():
             "lstm_rescoring": lstm,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
