@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbayeslm_b200.so")
 BLM_OK = 0
 ERR_NAMES = {-1: "BLM_ERR_SHAPE", -2: "BLM_ERR_ALIGN", -3: "BLM_ERR_ARCH", -4: "BLM_ERR_CUDA", -5: "BLM_ERR_ARG"}
 
-ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD, ACT_GELU_GRAD, ACT_GPMIX_GRAD, ACT_GELU_FAST = 0, 1, 2, 3, 4, 5, 6
+ACT_NONE, ACT_GELU, ACT_GPMIX, ACT_SOFTMAX_GRAD, ACT_GELU_GRAD, ACT_GPMIX_GRAD, ACT_GELU_FAST, ACT_GPMIX_FAST = 0, 1, 2, 3, 4, 5, 6, 7
 EPS_NONE, EPS_PTR, EPS_PHILOX = 0, 1, 2
 MAX_SEG = 6
 
@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
         ("lse", C.c_void_p), ("targets", C.c_void_p), ("grad_scale", C.c_float), ("k_chunk", C.c_int32),
         ("out_pre", C.c_void_p), ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("a_f16", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -214,7 +214,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // -------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      // A / B formats (bits [7,10) / [10,13)): 1 = bf16, 0 = f16.  Mixed A = f16 with B = bf16 is an illegal
+      // instruction on sm_100a (tried), so the fp16 mode switches both operands
+      const uint32_t idesc = umma_idesc_bf16(kBM, BN) & ~(p.a_f16 ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       int acc = 0;
@@ -570,6 +572,8 @@ int gemm_init() {
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GPMIX_FAST>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_GPMIX_FAST>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<128, kStages128, BLM_ACT_NONE>()) != BLM_OK) return rc;
@@ -668,17 +672,21 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
               BLM_ERR_ALIGN, "output / residual pointers must be 16-byte aligned");
   BLM_REQUIRE(!d->resid || ((d->ldr % 4) == 0 && d->ldr >= d->N), BLM_ERR_ALIGN, "ldr=%lld",
               (long long)d->ldr);
-  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_GELU_FAST, BLM_ERR_ARG, "unknown activation %d",
+  BLM_REQUIRE(d->act >= BLM_ACT_NONE && d->act <= BLM_ACT_GPMIX_FAST, BLM_ERR_ARG, "unknown activation %d",
               d->act);
-  BLM_REQUIRE(d->act != BLM_ACT_GELU_FAST || (d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && d->k_chunk == 0),
-              BLM_ERR_ARG, "BLM_ACT_GELU_FAST is for bf16-hi-only outputs of the fast mode");
+  BLM_REQUIRE((d->act != BLM_ACT_GELU_FAST && d->act != BLM_ACT_GPMIX_FAST) ||
+                  (d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && d->k_chunk == 0),
+              BLM_ERR_ARG, "the packed-fp16 activations are for bf16-hi-only outputs of the fast mode");
+  BLM_REQUIRE(d->act != BLM_ACT_GPMIX_FAST || ((d->N % 2) == 0 && !d->resid && aligned16(d->coef)), BLM_ERR_ARG,
+              "BLM_ACT_GPMIX_FAST needs an even N, no residual and a 16-byte aligned coef");
+  BLM_REQUIRE(!d->a_f16 || (d->nseg == 1 && d->k_chunk == 0), BLM_ERR_ARG, "fp16 operands: one segment, no k_chunk");
   const bool grad_act = d->act == BLM_ACT_GELU_GRAD || d->act == BLM_ACT_GPMIX_GRAD;
   BLM_REQUIRE(!grad_act || (d->aux && (d->ldaux % 4) == 0 && d->ldaux >= d->N && aligned16(d->aux)), BLM_ERR_ARG,
               "the activation-gradient epilogues need aux (16-byte aligned, ldaux %% 4 == 0)");
   BLM_REQUIRE(aligned16(d->out_pre), BLM_ERR_ALIGN, "out_pre must be 16-byte aligned");
   BLM_REQUIRE(d->act != BLM_ACT_SOFTMAX_GRAD || (d->lse && d->targets), BLM_ERR_ARG,
               "softmax-grad epilogue needs lse and targets");
-  BLM_REQUIRE((d->act != BLM_ACT_GPMIX && d->act != BLM_ACT_GPMIX_GRAD) || d->coef, BLM_ERR_ARG,
+  BLM_REQUIRE((d->act != BLM_ACT_GPMIX && d->act != BLM_ACT_GPMIX_GRAD && d->act != BLM_ACT_GPMIX_FAST) || d->coef, BLM_ERR_ARG,
               "GP-mix epilogue needs coef");
 
   // Tile choice: 128x256 tiles unless that leaves most SMs idle, then 128x128.
@@ -723,6 +731,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   p.out_pre = d->out_pre;
   p.aux = d->aux;
   p.ldaux = d->ldaux;
+  p.a_f16 = d->a_f16;
   if (gen) {
     p.gen_mu = reinterpret_cast<const __nv_bfloat16*>(gen->mu);
     p.gen_ldmu = gen->ldmu;
@@ -739,7 +748,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   }
   cudaStream_t st = as_stream(stream);
   // CTA-pair kernel: one bf16 segment, bf16-only output, forward activations, enough 256 x 256 tiles
-  if (!gen && use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
+  if (!gen && !d->a_f16 && use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
       (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST) &&
       static_cast<long long>((d->M + 255) / 256) * ((d->N + 255) / 256) >= num_sms() / 2) {
     GemmParams p2 = p;
@@ -762,8 +771,16 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
     const char* e = getenv("BLM_TMA_STORE");
     return e ? atoi(e) != 0 : true;
   }();
-  if (tma_store_on && !chunked && d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && !d->resid &&
-      (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_GPMIX)) {
+  const bool tma_ok = tma_store_on && !chunked && d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && !d->resid;
+  blm_gemm_desc downgraded;
+  if (d->act == BLM_ACT_GPMIX_FAST && !tma_ok) {   // the packed variant only exists on the TMA-store path
+    downgraded = *d;
+    downgraded.act = BLM_ACT_GPMIX;
+    d = &downgraded;
+  }
+  if (tma_ok &&
+      (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_GPMIX ||
+       d->act == BLM_ACT_GPMIX_FAST)) {
     rc = encode_tmap_bf16(&p.tmC, d->out_hi, d->M, d->N, d->ldc, 32);
     if (rc != BLM_OK) return rc;
     if (BN == 256) {
@@ -771,6 +788,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
         case BLM_ACT_NONE: return launch_tma<256, kStages256, BLM_ACT_NONE>(p, st);
         case BLM_ACT_GELU: return launch_tma<256, kStages256, BLM_ACT_GELU>(p, st);
         case BLM_ACT_GPMIX: return launch_tma<256, kStages256, BLM_ACT_GPMIX>(p, st);
+        case BLM_ACT_GPMIX_FAST: return launch_tma<256, kStages256, BLM_ACT_GPMIX_FAST>(p, st);
         default: return launch_tma<256, kStages256, BLM_ACT_GELU_FAST>(p, st);
       }
     }
@@ -778,6 +796,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
       case BLM_ACT_NONE: return launch_tma<128, kStages128, BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch_tma<128, kStages128, BLM_ACT_GELU>(p, st);
       case BLM_ACT_GPMIX: return launch_tma<128, kStages128, BLM_ACT_GPMIX>(p, st);
+      case BLM_ACT_GPMIX_FAST: return launch_tma<128, kStages128, BLM_ACT_GPMIX_FAST>(p, st);
       default: return launch_tma<128, kStages128, BLM_ACT_GELU_FAST>(p, st);
     }
   }

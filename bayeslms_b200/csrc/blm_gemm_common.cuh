@@ -36,6 +36,7 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldc;
+  int a_f16;            // 1: A operands are fp16 (instruction descriptor A format F16, B stays BF16)
   int use_stg;          // 1: transpose finished chunks through shared memory for row-coalesced stores
   int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk
   float* out_pre;       // fp32 copy of the value BEFORE the activation (training: saved pre-activation)
@@ -124,17 +125,56 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // slots per element instead of ~15.  fp16's 11-bit mantissa costs <= 5e-4 relative on the result -- below the
 // bf16 rounding (4e-3) of the only output this variant is used for (BLM_ACT_GELU_FAST: bf16-hi output of the
 // fast mode), where the fp32 GELU made the FFN1 epilogue, not the tensor pipe, the bound.
+__device__ __forceinline__ __half2 gelu_fast_core_h2(__half2 x, __half2 relu_x) {
+  // GELU(x) = max(x, 0) - |x| 2^(-(p(s) s) - 1), s = min(|x|, 4 sqrt 2), p(s) = q(s / sqrt 2) / sqrt 2 with q the
+  // degree-3 fit of -log2(erfc(t)) / t (weighted by the sensitivity |x|/2 erfc(t) ln2 t of the result: 1.2e-5
+  // absolute on GELU in exact arithmetic, far below the fp16 evaluation itself).  The 1/sqrt 2 scaling and the
+  // factor 1/2 live in the coefficients / the exponent: 9 packed instructions per pair + 2 MUFU.
+  const __half2 s = __hmin2(__habs2(x), __float2half2_rn(5.65685f));
+  __half2 p = __hfma2(s, __float2half2_rn(-4.0813875e-03f), __float2half2_rn(4.5319763e-02f));
+  p = __hfma2(p, s, __float2half2_rn(4.6557564e-01f));
+  p = __hfma2(p, s, __float2half2_rn(1.1492719e+00f));
+  const __half2 ex = __hfma2(__hneg2(p), s, __float2half2_rn(-1.0f));   // -(p s) - 1
+  // ex2.approx.f16x2 straight from PTX: two MUFU.EX2.F16 + one PRMT.  The h2exp2() intrinsic expands to seven
+  // instructions (half -> float, MUFU.EX2, an FFMA rounding fix-up, float -> half) -- measured in the SASS
+  uint32_t e_bits;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e_bits) : "r"(*reinterpret_cast<const uint32_t*>(&ex)));
+  const __half2 e = *reinterpret_cast<const __half2*>(&e_bits);          // erfc(|x| / sqrt 2) / 2
+  return __hfma2(__hneg2(__habs2(x)), e, relu_x);
+}
+
 __device__ __forceinline__ void gelu_fast_h2(float& a, float& b) {
   const __half2 x = __floats2half2_rn(a, b);
-  const __half2 ax = __habs2(x);
-  const __half2 t = __hmin2(__hmul2(ax, __float2half2_rn(0.70710678118654752440f)), __float2half2_rn(4.0f));
-  // degree-3 fit of q (weighted by the sensitivity |x|/2 erfc(t) ln2 t of the result): 1.2e-5 absolute on GELU in
-  // exact arithmetic, far below the fp16 evaluation itself -- three HFMA2 fewer per pair than the degree-6 fit
-  __half2 q = __hfma2(t, __float2half2_rn(-1.632555e-02f), __float2half2_rn(1.2818365e-01f));
-  q = __hfma2(q, t, __float2half2_rn(9.3115127e-01f));
-  q = __hfma2(q, t, __float2half2_rn(1.62531592e+00f));
-  const __half2 e = h2exp2(__hneg2(__hmul2(q, t)));  // erfc(t)
-  const __half2 r = __hfma2(__hmul2(ax, __float2half2_rn(-0.5f)), e, __hmax2(x, __float2half2_rn(0.0f)));
+  const float2 f = __half22float2(gelu_fast_core_h2(x, __hmax2(x, __float2half2_rn(0.0f))));
+  a = f.x;
+  b = f.y;
+}
+
+__device__ __forceinline__ __half2 tanh_h2(__half2 x) {
+  uint32_t r;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&x)));   // 2 MUFU.TANH.F16 + PRMT
+  return *reinterpret_cast<const __half2*>(&r);
+}
+
+// GP activation mixture sum_i coef[i, n] act_i(z), acts tanh, sigmoid, relu, gelu (model.py:1893-1899, 2263), on
+// the column pair (n, n + 1) in packed fp16: sigmoid(z) = 0.5 tanh(z / 2) + 0.5, both tanh through MUFU.TANH.F16.
+// The fp32 evaluation costs ~45 issue slots per element (706 us for the GP layer's FFN1 vs 273 us with GELU).
+__device__ __forceinline__ void gpmix_fast_h2(float& a, float& b, const float* __restrict__ coef, int N, int n) {
+  n = min(n, N - 2);   // the TMA-store path evaluates (and then clips) columns past the ragged edge; N is even
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 half = __float2half2_rn(0.5f);
+  const __half2 th = tanh_h2(x);
+  const __half2 sg = __hfma2(tanh_h2(__hmul2(x, half)), half, half);
+  const __half2 rl = __hmax2(x, __float2half2_rn(0.0f));
+  const __half2 gl = gelu_fast_core_h2(x, rl);
+  const float2 c0 = __ldg(reinterpret_cast<const float2*>(coef + n));
+  const float2 c1 = __ldg(reinterpret_cast<const float2*>(coef + N + n));
+  const float2 c2 = __ldg(reinterpret_cast<const float2*>(coef + 2 * N + n));
+  const float2 c3 = __ldg(reinterpret_cast<const float2*>(coef + 3 * N + n));
+  __half2 r = __hmul2(__floats2half2_rn(c0.x, c0.y), th);
+  r = __hfma2(__floats2half2_rn(c1.x, c1.y), sg, r);
+  r = __hfma2(__floats2half2_rn(c2.x, c2.y), rl, r);
+  r = __hfma2(__floats2half2_rn(c3.x, c3.y), gl, r);
   const float2 f = __half22float2(r);
   a = f.x;
   b = f.y;
@@ -164,7 +204,9 @@ __device__ __forceinline__ float gpmix_grad(float z, const float* __restrict__ c
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float z, const float* __restrict__ coef, int N, int n) {
-  if constexpr (ACT == BLM_ACT_GELU || ACT == BLM_ACT_GELU_FAST) {
+  if constexpr (ACT == BLM_ACT_GPMIX_FAST) {
+    return z;   // (never reached: the packed variant only runs on the TMA-store path, which takes no ragged-edge branch)
+  } else if constexpr (ACT == BLM_ACT_GELU || ACT == BLM_ACT_GELU_FAST) {
     return gelu_fast(z);   // (the packed-fp16 variant is applied pairwise in store_chunk; this is its ragged-edge path)
   } else if constexpr (ACT == BLM_ACT_GPMIX) {
     n = min(n, N - 1);  // the TMA-store path evaluates (and then clips) columns past the ragged edge
@@ -306,6 +348,9 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
     } else if constexpr (ACT == BLM_ACT_GELU_FAST) {
 #pragma unroll
       for (int j = 0; j < 32; j += 2) gelu_fast_h2(v[j], v[j + 1]);
+    } else if constexpr (ACT == BLM_ACT_GPMIX_FAST) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) gpmix_fast_h2(v[j], v[j + 1], p.coef, p.N, col0 + j);
     } else if constexpr (ACT != BLM_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);

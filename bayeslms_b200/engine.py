@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .ops import ACT_GELU, ACT_GELU_FAST, ACT_GPMIX, ACT_NONE, Split
+from .ops import ACT_GELU, ACT_GELU_FAST, ACT_GPMIX, ACT_GPMIX_FAST, ACT_NONE, Split
 
 Sample = Union[int, dict]
 
@@ -266,7 +266,8 @@ class _TmRun:
         h = ops.empty_split(self.M, w1.hi.shape[0], self.prec, self.dev)
         # fast mode: the hidden is stored as bf16 only, so GELU runs in packed fp16 (half the epilogue's issue slots)
         gelu = ACT_GELU_FAST if (self.prec == "bf16" and self.fast_gelu) else ACT_GELU
-        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=ACT_GPMIX if coef is not None else gelu, coef=coef, out=h,
+        gpmix = ACT_GPMIX_FAST if (self.prec == "bf16" and self.fast_gelu and w1.hi.shape[0] % 2 == 0) else ACT_GPMIX
+        ops.gemm(x1s, w1, prec=self.prec, bias=b1, act=gpmix if coef is not None else gelu, coef=coef, out=h,
                  tag="ffn1")
         return h
 

@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_GELU_FAST, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
+from ._lib import (ACT_GELU, ACT_GELU_FAST, ACT_GPMIX_FAST, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
                    EPS_PTR, GemmDesc, GemmLnDesc, GemmSampledDesc,
                    VocabNllDesc,
                    check, lib)
@@ -118,7 +118,8 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
          resid: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
          out: Optional[Split] = None, extra: Sequence = (), tag: str = "", out_pre: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
-         targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None):
+         targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None,
+         a_f16: bool = False):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
     accumulated into the same output (K-concatenation).  ``out_pre`` receives the fp32 value before
     the activation; ``aux`` is the saved pre-activation of the ``*_GRAD`` epilogues; ``lse`` /
@@ -132,7 +133,8 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     d.M, d.N, d.nseg, d.act = M, N, len(segs), act
     for i, (x, w) in enumerate(segs):
         _require_cuda(x, w)
-        assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+        want = torch.float16 if a_f16 else torch.bfloat16     # fp16 mode: BOTH operands (mixed types are illegal on sm_100a)
+        assert x.dtype == want and w.dtype == want
         assert x.shape[1] == w.shape[1] and x.stride(1) == 1 and w.stride(1) == 1
         d.A[i], d.B[i] = x.data_ptr(), w.data_ptr()
         d.K[i], d.lda[i], d.ldb[i] = x.shape[1], x.stride(0), w.stride(0)
@@ -159,6 +161,7 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     if lse is not None:
         d.lse, d.targets, d.grad_scale = _ptr(lse), _ptr(targets), grad_scale
     d.k_chunk = (PRECISE_K_CHUNK if prec == "bf16x3" else 0) if k_chunk is None else k_chunk
+    d.a_f16 = int(a_f16)
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
 

@@ -55,9 +55,11 @@ enum {
   BLM_ACT_GELU_GRAD = 4,  /* z * gelu'(aux[m,n]): backward of BLM_ACT_GELU at the saved
                         pre-activation aux                                       */
   BLM_ACT_GPMIX_GRAD = 5, /* z * sum_i coef[i,n] act_i'(aux[m,n]): backward of BLM_ACT_GPMIX */
-  BLM_ACT_GELU_FAST = 6   /* the same erf GELU evaluated in packed fp16 (two elements per
+  BLM_ACT_GELU_FAST = 6,  /* the same erf GELU evaluated in packed fp16 (two elements per
                         instruction, <= 5e-4 relative): for bf16-hi-only outputs (fast mode),
                         where the fp32 evaluation bounds the FFN1 epilogue            */
+  BLM_ACT_GPMIX_FAST = 7  /* BLM_ACT_GPMIX in packed fp16 (tanh.approx.f16x2 for tanh and sigmoid):
+                        bf16-hi-only outputs of the fast mode, N even                  */
 };
 
 /* where the N(0,1) noise of a reparameterised tensor comes from */
@@ -125,6 +127,9 @@ typedef struct blm_gemm_desc {
                           i.e. after bias and q-scale (saved for the backward pass)   */
   const float* aux;    /* [M, N] fp32, leading dimension ldaux (BLM_ACT_*_GRAD)  */
   int64_t ldaux;
+  int32_t a_f16;       /* 1: A AND B operands hold IEEE fp16 bits instead of bf16 (tcgen05 kind::f16; mixing
+                          A = f16 with B = bf16 is an illegal instruction on sm_100a).  One segment, no k_chunk. */
+  int32_t reserved;
 } blm_gemm_desc;
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);

@@ -337,3 +337,37 @@ def test_gemm_ln_rejects_other_widths(ops):
     with pytest.raises(_lib.BlmError):
         ops.gemm_ln(a, b, bias=None, resid=torch.zeros(64, 192, device=DEV), gamma=torch.ones(192, device=DEV),
                     beta=torch.zeros(192, device=DEV), eps=1e-5)
+
+
+def test_fast_gpmix_epilogue(ops):
+    """BLM_ACT_GPMIX_FAST (GP activation mixture in packed fp16, tanh / sigmoid through MUFU.TANH.F16, bf16-hi
+    output): within bf16 rounding + the fp16 evaluation of the exact mixture (model.py:1893-1899)."""
+    M, N, K = 3000, 4096, 512
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    bias = torch.randn(N, device=DEV)
+    coef = torch.rand(4, N, device=DEV) - 0.3
+    A, B = ops.split(a, "bf16"), ops.split(b, "bf16")
+    out = ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm(A, B, prec="bf16", bias=bias, act=ops.ACT_GPMIX_FAST, coef=coef, out=out)
+    z = A.hi.double() @ B.hi.double().T + bias.double()
+    ref = _gp_mix(z, coef.double())
+    scale = (coef.double().abs().unsqueeze(1) * torch.stack([torch.tanh(z).abs(), torch.sigmoid(z), torch.relu(z),
+                                                               torch.nn.functional.gelu(z).abs()])).sum(0)
+    err = (out.hi.double() - ref).abs()
+    # bf16 ulp/2 of the result + fp16 evaluation of each term (relative to the terms' magnitudes: they can cancel)
+    assert (err <= 4.5e-3 * ref.abs() + 2.5e-3 * scale + 1e-3).all(), (err.max().item(),)
+    ref32 = ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm(A, B, prec="bf16", bias=bias, act=ops.ACT_GPMIX, coef=coef, out=ref32)
+    d = (out.hi.float() - ref32.hi.float()).abs()          # vs the fp32 evaluation: one bf16 ulp + the fp16 terms
+    assert (d <= 8e-3 * ref32.hi.float().abs() + 2.5e-3 * scale.float() + 1e-3).all(), d.max().item()
+
+
+def test_fp16_operands(ops):
+    """a_f16: both operands fp16 (tcgen05 kind::f16 with A = B = F16; mixed f16 x bf16 is an illegal instruction)."""
+    M, N, K = 1000, 512, 1024
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(torch.float16)
+    b = (torch.randn(N, K, device=DEV) * 0.1).to(torch.float16)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(ops.Split(a), ops.Split(b), prec="bf16", out_f32=out, a_f16=True)
+    _close(out, a.double() @ b.double().T, 1e-5)

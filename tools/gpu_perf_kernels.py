@@ -54,6 +54,8 @@ line("gemm ffn1  [M,4096,512] bias+GELU bf16", timeit(lambda: ops.gemm(x, w1, bi
 from bayeslms_b200.ops import ACT_GELU_FAST
 line("gemm ffn1  [M,4096,512] bias+GELU(f16x2) bf16", timeit(lambda: ops.gemm(x, w1, bias=bF, act=ACT_GELU_FAST, out=hout)), 2.0 * M * F * d)
 line("gemm ffn1  [M,4096,512] bias+GPMIX bf16", timeit(lambda: ops.gemm(x, w1, bias=bF, act=ACT_GPMIX, coef=coef, out=hout)), 2.0 * M * F * d)
+from bayeslms_b200.ops import ACT_GPMIX_FAST
+line("gemm ffn1  [M,4096,512] bias+GPMIX(f16x2) bf16", timeit(lambda: ops.gemm(x, w1, bias=bF, act=ACT_GPMIX_FAST, coef=coef, out=hout)), 2.0 * M * F * d)
 line("gemm ffn1  [M,4096,512] no epilogue bf16", timeit(lambda: ops.gemm(x, w1, out=hout)), 2.0 * M * F * d)
 line("gemm ffn2  [M,512,4096] resid f32", timeit(lambda: ops.gemm(h, w2, resid=x32, out_f32=y)), 2.0 * M * d * F)
 A8, B8 = ops.split(torch.randn(8192, 8192, device=dev), "bf16"), ops.split(torch.randn(8192, 8192, device=dev), "bf16")
