@@ -633,32 +633,69 @@ def lstm_token_nll(model, x: torch.Tensor, targets: torch.Tensor, hidden, prec: 
     return nll, (hT, cT)
 
 
-def _pad_time_major(seqs: Sequence[Sequence[int]], device):
-    """list of id lists -> (int32 [T, B] time-major right-padded with 0, int32 lengths [B]) on device."""
-    B = len(seqs)
-    lens = np.fromiter((len(s) for s in seqs), dtype=np.int32, count=B)
-    T = max(int(lens.max()) if B else 0, 1)
-    host = torch.zeros(T * B + B, dtype=torch.int32)
-    if torch.cuda.is_available():
-        host = host.pin_memory()
-    mat = host[:T * B].view(T, B).numpy()
-    for b, s in enumerate(seqs):
-        if len(s):
-            mat[:len(s), b] = s
-    host[T * B:] = torch.from_numpy(lens)
-    dev = host.to(device, non_blocking=True)
-    return dev[:T * B].view(T, B), dev[T * B:], lens
-
-
 @torch.no_grad()
 def lstm_score(model, batch, hidden, **kw):
     raise _lib.BlmError("use Rescorer.score_sessions / lstm_score_sessions for LSTM rescoring")
 
 
-@torch.no_grad()
+def _pin(host: torch.Tensor) -> torch.Tensor:
+    return host.pin_memory() if torch.cuda.is_available() else host
+
+
+def _pad_from_flat(flat: np.ndarray, starts: np.ndarray, lens: np.ndarray, device):
+    """Rows ``flat[starts[b] : starts[b] + lens[b]]`` -> (int32 [T, B] time-major right-padded with 0, int32
+    lengths [B]) on the device, plus the (t * B + b) index of every valid element in row-major (b, t) order.
+    Pure index arithmetic: no Python loop over hypotheses."""
+    B = len(lens)
+    T = max(int(lens.max()) if B else 0, 1)
+    offs = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    M = int(offs[-1])
+    b_of = np.repeat(np.arange(B, dtype=np.int64), lens)
+    t_of = np.arange(M, dtype=np.int64) - np.repeat(offs[:-1], lens)
+    host = _pin(torch.zeros(T * B + B, dtype=torch.int32))
+    buf = host.numpy()
+    where = t_of * B + b_of
+    buf[where] = flat[np.repeat(starts.astype(np.int64), lens) + t_of]
+    buf[T * B:] = lens
+    dev = host.to(device, non_blocking=True)
+    return dev[:T * B].view(T, B), dev[T * B:], where.astype(np.int32), offs
+
+
+def flatten_sessions(sessions):
+    """Nested [session][utterance][(input ids, target ids)] lists -> flat host arrays
+    (tok, tgt, offs [n_hyp + 1], sess_of [n_hyp], utt_of [n_hyp] = utterance index inside the session)."""
+    import itertools
+    lens, sess_of, utt_of = [], [], []
+    for si, sess in enumerate(sessions):
+        for ui, utt in enumerate(sess):
+            lens.extend(len(x) for x, _ in utt)
+            sess_of.extend([si] * len(utt))
+            utt_of.extend([ui] * len(utt))
+    lens = np.asarray(lens, dtype=np.int64)
+    offs = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    total = int(offs[-1])
+    tok = np.fromiter(itertools.chain.from_iterable(x for sess in sessions for utt in sess for x, _ in utt),
+                      dtype=np.int32, count=total)
+    tgt = np.fromiter(itertools.chain.from_iterable(y for sess in sessions for utt in sess for _, y in utt),
+                      dtype=np.int32, count=total)
+    return tok, tgt, offs, np.asarray(sess_of, dtype=np.int32), np.asarray(utt_of, dtype=np.int32)
+
+
 def lstm_score_sessions(rs, sessions):
-    """Score LSTM sessions (see scorer.py).  sessions[s][u] = [(input ids, target ids), ...].
-    Returns fp32 numpy scores in (session, utterance, hypothesis) order.
+    """Score LSTM sessions given as nested lists (see scorer.py): flattened once, then :func:`lstm_score_flat`."""
+    if not any(len(u) for s in sessions for u in s):
+        return np.zeros(0, dtype=np.float32)
+    return lstm_score_flat(rs, *flatten_sessions(sessions))
+
+
+@torch.no_grad()
+def lstm_score_flat(rs, tok: np.ndarray, tgt: np.ndarray, offs: np.ndarray, sess_of: np.ndarray, utt_of: np.ndarray):
+    """Score LSTM sessions from flat host arrays: hypothesis r has input ids ``tok[offs[r]:offs[r+1]]``, targets
+    ``tgt[...]`` and belongs to utterance ``utt_of[r]`` of session ``sess_of[r]``; rows are ordered (session,
+    utterance, hypothesis), so the first row of each (session, utterance) is hypothesis #0 (score.py:271-274).
+    Returns fp32 numpy scores in row order.
 
     Phase 1: the hypothesis-#0 chain.  For u = 0, 1, ...: hypothesis #0 of utterance u of EVERY session
     advances in lock step from that session's carried state; the state before each utterance is
@@ -667,16 +704,28 @@ def lstm_score_sessions(rs, sessions):
     starts from its utterance's recorded state; the last layer's hidden states of the valid
     positions are gathered hypothesis-major and go through the vocabulary-streaming NLL kernel.
     With K posterior samples both phases run once per sample (each sample carries its own chain)
-    and the per-token log-probabilities are combined as the Monte-Carlo predictive."""
+    and the per-token log-probabilities are combined as the Monte-Carlo predictive.
+    All host-side packing is numpy index arithmetic on the flat arrays (the per-hypothesis Python loops of
+    the first version left the GPU idle for a quarter of the wall clock)."""
     model, prec, dev = rs.model, rs.prec, rs.device
     plan = plan_for(model, prec)
     H = model.nhid
     samples = _normalise_samples(rs.K, rs.seed, rs.eps_list) or [None]
-    S = len(sessions)
-    U = max((len(s) for s in sessions), default=0)
-    rows = [(s, u, n) for s in range(S) for u in range(len(sessions[s])) for n in range(len(sessions[s][u]))]
-    if not rows:
+    n_rows = len(offs) - 1
+    if n_rows == 0:
         return np.zeros(0, dtype=np.float32)
+    offs = np.asarray(offs, dtype=np.int64)
+    lens_all = np.diff(offs)
+    sess_of = np.asarray(sess_of, dtype=np.int64)
+    utt_of = np.asarray(utt_of, dtype=np.int64)
+    S, U = int(sess_of.max()) + 1, int(utt_of.max()) + 1
+    # row of hypothesis #0 of every (session, utterance); -1 where the session has fewer utterances
+    first = np.full((S, U), -1, dtype=np.int64)
+    key = sess_of * U + utt_of
+    is_first = np.ones(n_rows, dtype=bool)
+    is_first[1:] = key[1:] != key[:-1]
+    fr = np.nonzero(is_first)[0]
+    first[sess_of[fr], utt_of[fr]] = fr
 
     # ---------------- phase 1 (per sample): init state of every (session, utterance)
     init_h = torch.zeros(len(samples), U, 2, S, H, dtype=torch.float32, device=dev)
@@ -684,22 +733,27 @@ def lstm_score_sessions(rs, sessions):
     weights = [_lstm_weights(model, plan, k, rs.seed) for k in samples]
     for s0 in range(0, S, LSTM_MAX_ROWS):
         s1 = min(S, s0 + LSTM_MAX_ROWS)
-        chain_in = [[sessions[s][u][0][0] if u < len(sessions[s]) else [] for s in range(s0, s1)] for u in range(U)]
-        padded = [_pad_time_major(c, dev) for c in chain_in[:-1]]   # the last utterance feeds nobody
-        rs.h2d_bytes += sum(4 * (t.numel() + l.numel()) for t, l, _ in padded)
+        padded = []
+        for u in range(U - 1):                                        # the last utterance feeds nobody
+            r0 = first[s0:s1, u]
+            ok = r0 >= 0
+            starts = np.where(ok, offs[np.maximum(r0, 0)], 0)
+            ln = np.where(ok, lens_all[np.maximum(r0, 0)], 0)
+            t_d, l_d, _, _ = _pad_from_flat(tok, starts, ln, dev)
+            padded.append((t_d, l_d))
+        rs.h2d_bytes += sum(4 * (t.numel() + l.numel()) for t, l in padded)
         for k in range(len(samples)):
             h = torch.zeros(2, s1 - s0, H, dtype=torch.float32, device=dev)
             c = torch.zeros_like(h)
             for u in range(U):
                 init_h[k, u, :, s0:s1], init_c[k, u, :, s0:s1] = h, c
                 if u + 1 < U:
-                    tok, lens, _ = padded[u]
-                    _, _, h, c = _lstm_forward(model, plan, weights[k], tok, lens, h, c, want_f32=False, want_split=False)
+                    t_d, l_d = padded[u]
+                    _, _, h, c = _lstm_forward(model, plan, weights[k], t_d, l_d, h, c, want_f32=False, want_split=False)
 
     # ---------------- phase 2: all hypotheses, longest first, in lock-step batches
-    lens_all = np.asarray([len(sessions[s][u][n][0]) for s, u, n in rows], dtype=np.int64)
     order = np.argsort(-lens_all, kind="stable")
-    scores = np.zeros(len(rows), dtype=np.float32)
+    scores = np.zeros(n_rows, dtype=np.float32)
     outs = []
     i = 0
     while i < len(order):
@@ -707,30 +761,30 @@ def lstm_score_sessions(rs, sessions):
         nb = int(min(LSTM_MAX_ROWS, max(1, rs.max_tokens // max(T, 1)), len(order) - i))
         idx = order[i:i + nb]
         i += nb
-        seqs = [sessions[rows[r][0]][rows[r][1]][rows[r][2]] for r in idx]
-        tok, lens_d, lens = _pad_time_major([x for x, _ in seqs], dev)
-        B = len(seqs)
-        # hypothesis-major gather list of the valid (t, b) rows + packed targets
-        offs = np.zeros(B + 1, dtype=np.int32)
-        np.cumsum(lens, out=offs[1:])
-        M = int(offs[-1])
-        b_of = np.repeat(np.arange(B, dtype=np.int32), lens)
-        t_of = (np.arange(M, dtype=np.int32) - np.repeat(offs[:-1], lens)).astype(np.int32)
-        meta = np.concatenate([t_of * B + b_of, np.concatenate([np.asarray(y, dtype=np.int32) for _, y in seqs]),
-                               offs, np.asarray([rows[r][0] for r in idx], dtype=np.int32),
-                               np.asarray([rows[r][1] for r in idx], dtype=np.int32)]).astype(np.int32)
-        meta_h = torch.from_numpy(meta)
-        meta_d = (meta_h.pin_memory() if torch.cuda.is_available() else meta_h).to(dev, non_blocking=True)
-        rs.h2d_bytes += 4 * (meta.size + tok.numel() + lens_d.numel())
-        gather, tgt, offs_d = meta_d[:M], meta_d[M:2 * M], meta_d[2 * M:2 * M + B + 1]
+        lens = lens_all[idx]
+        tok_d, lens_d, where, boffs = _pad_from_flat(tok, offs[idx], lens, dev)
+        B = len(idx)
+        M = int(boffs[-1])
+        # hypothesis-major gather list of the valid (t, b) rows + packed targets + (session, utterance) of every row
+        src = np.repeat(offs[idx], lens) + (np.arange(M, dtype=np.int64) - np.repeat(boffs[:-1], lens))
+        meta_h = _pin(torch.empty(2 * M + (B + 1) + 2 * B, dtype=torch.int32))
+        meta = meta_h.numpy()
+        meta[:M] = where
+        meta[M:2 * M] = tgt[src]
+        meta[2 * M:2 * M + B + 1] = boffs
+        meta[2 * M + B + 1:2 * M + 2 * B + 1] = sess_of[idx]
+        meta[2 * M + 2 * B + 1:] = utt_of[idx]
+        meta_d = meta_h.to(dev, non_blocking=True)
+        rs.h2d_bytes += 4 * (meta.size + tok_d.numel() + lens_d.numel())
+        gather, tgt_d, offs_d = meta_d[:M], meta_d[M:2 * M], meta_d[2 * M:2 * M + B + 1]
         s_idx, u_idx = meta_d[2 * M + B + 1:2 * M + 2 * B + 1].long(), meta_d[2 * M + 2 * B + 1:].long()
         per = torch.empty(len(samples), M, dtype=torch.float32, device=dev)
         for k in range(len(samples)):
             h0 = init_h[k, u_idx, :, s_idx].transpose(0, 1).contiguous()   # [2, B, H]
             c0 = init_c[k, u_idx, :, s_idx].transpose(0, 1).contiguous()
-            out32, _, _, _ = _lstm_forward(model, plan, weights[k], tok, lens_d, h0, c0, want_f32=True, want_split=False)
+            out32, _, _, _ = _lstm_forward(model, plan, weights[k], tok_d, lens_d, h0, c0, want_f32=True, want_split=False)
             _, hs = ops.embed(gather, None, out32, None, 1.0, prec=prec, want_f32=False)  # row gather + bf16 split
-            ops.vocab_nll(hs, plan.E, plan.dec_b, tgt, prec=prec, out=per[k])
+            ops.vocab_nll(hs, plan.E, plan.dec_b, tgt_d, prec=prec, out=per[k])
         tok_nll = per[0] if len(samples) == 1 else ops.mc_combine(per)
         outs.append((idx, ops.segment_sum(tok_nll, offs_d)))
     for idx, dev_scores in outs:

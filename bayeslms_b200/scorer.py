@@ -191,6 +191,11 @@ class Rescorer:
         """sessions: list of sessions, each a list of utterances, each a list of (input, target)."""
         return engine.lstm_score_sessions(self, sessions)
 
+    def score_sessions_flat(self, tok, tgt, offs, sess_of, utt_of):
+        """LSTM rescoring from flat host arrays (see :func:`bayeslms_b200.engine.lstm_score_flat`): rows ordered
+        (session, utterance, hypothesis); returns fp32 numpy scores in row order."""
+        return engine.lstm_score_flat(self, tok, tgt, offs, sess_of, utt_of)
+
 
 def score_nbest(model, nbest: "OrderedDict[str, List[str]]", vocab: Dict[str, int], *, prec: str = "bf16",
                 K: int = 0, seed: Optional[int] = None, max_tokens: int = 65536, eps_list=None,

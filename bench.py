@@ -147,22 +147,24 @@ def bench_lstm(dev, steps=2):
     net = M.BayesRNNModel("LSTM", V, 1024, 1024, 2, 0.5, True, 3).to(dev).eval()
     n_sess, per_sess, nbest = 8, 16, 100
     data = synth.make_nbest(n_sess * per_sess, nbest, V, seed=1112)
-    utts = data.tokenised()
-    sessions = [utts[s * per_sess:(s + 1) * per_sess] for s in range(n_sess)]
+    # flat host id arrays, rows ordered (session, utterance, hypothesis) -- the LSTM twin of flat_host() above
+    tok, tgt, _, offs = data.flat_host()
+    utt = np.repeat(np.arange(n_sess * per_sess), [len(u) for u in data.hyps])
+    sess_of, utt_of = (utt // per_sess).astype(np.int32), (utt % per_sess).astype(np.int32)
     n_tok = data.n_tokens()
     out = {}
     for name, kw in (("mean", {}), ("sampled_k8", {"K": 8, "seed": 1111})):
         rs = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS, **kw)
-        rs.score_sessions(sessions)                      # warm-up (plans, workspaces)
+        rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)       # warm-up (plans, workspaces)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            rs.score_sessions(sessions)
+            rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
         out[name] = {"tokens_per_s": n_tok / dt, "ms": dt * 1e3}
     out["workload"] = (f"Bayesian LSTM 2x1024 L_bayes_pos=3 V30000, {nbest}-best, {n_sess} sessions x {per_sess} utterances "
-                       f"({n_tok} tokens), end to end incl. host packing (wall clock)")
+                       f"({n_tok} tokens), end to end from flat host id arrays incl. batch packing (wall clock)")
     return out
 
 
