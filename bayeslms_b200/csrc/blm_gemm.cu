@@ -197,10 +197,22 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
               uint8_t* st = ring + stage * L::kStageBytes;
               // activations stream once; weights are re-read by every M tile and stay L2 resident
               if constexpr (ARES == 0) {
-                tma_load_2d(st, &p.tmA[s], &full_bar[stage], kb * kBK, m_tile * kBM, kEvictNormal);
+                if (!p.a_mn) {
+                  tma_load_2d(st, &p.tmA[s], &full_bar[stage], kb * kBK, m_tile * kBM, kEvictNormal);
+                } else {   // MN-major: [64 reduction rows x 64 elements] boxes, one per 64 rows of the tile
+#pragma unroll
+                  for (int j = 0; j < kBM / 64; ++j)
+                    tma_load_2d(st + j * 8192, &p.tmA[s], &full_bar[stage], m_tile * kBM + 64 * j, kb * kBK, kEvictNormal);
+                }
                 st += L::kABytes;
               }
-              tma_load_2d(st, &p.tmB[s], &full_bar[stage], kb * kBK, n * BN, kEvictLast);
+              if (!p.b_mn) {
+                tma_load_2d(st, &p.tmB[s], &full_bar[stage], kb * kBK, n * BN, kEvictLast);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(st + j * 8192, &p.tmB[s], &full_bar[stage], n * BN + 64 * j, kb * kBK, kEvictLast);
+              }
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -216,7 +228,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     if (lane == 0) {
       // A / B formats (bits [7,10) / [10,13)): 1 = bf16, 0 = f16.  Mixed A = f16 with B = bf16 is an illegal
       // instruction on sm_100a (tried), so the fp16 mode switches both operands
-      const uint32_t idesc = umma_idesc_bf16(kBM, BN) & ~(p.a_f16 ? ((1u << 7) | (1u << 10)) : 0u);
+      const uint32_t idesc = (umma_idesc_bf16(kBM, BN) & ~(p.a_f16 ? ((1u << 7) | (1u << 10)) : 0u)) |
+                             (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);   // bits 15 / 16: A / B MN-major
+      const uint64_t a_step = p.a_mn ? 128u : 2u, b_step = p.b_mn ? 128u : 2u;          // per K = 16 step, in 16-byte units
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       int acc = 0;
@@ -243,12 +257,12 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
               const uint32_t st = smem_u32(ring + stage * L::kStageBytes);
               const uint32_t sa = ARES > 0 ? smem_u32(smem + kb * L::kABytes) : st;
               const uint32_t sb = ARES > 0 ? st : st + L::kABytes;
-              const uint64_t da = umma_desc_sw128(sa);
-              const uint64_t db = umma_desc_sw128(sb);
+              const uint64_t da = p.a_mn ? umma_desc_sw128_mn(sa) : umma_desc_sw128(sa);
+              const uint64_t db = p.b_mn ? umma_desc_sw128_mn(sb) : umma_desc_sw128(sb);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k) {
-                // +32 bytes per 16-element K step inside the 128-byte swizzle row
-                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                // K-major: +32 bytes per 16-element K step inside the 128-byte swizzle row; MN-major: +2 atoms
+                umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k) * a_step, db + static_cast<uint64_t>(k) * b_step,
                              idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
               }
               umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
@@ -640,15 +654,16 @@ static bool use_gemm2() {
 
 static int fill_segments(GemmParams& p, int nseg, const blm_bf16* const* A, const blm_bf16* const* B,
                          const int64_t* K, const int64_t* lda, const int64_t* ldb, int64_t M,
-                         int64_t N, int BN) {
+                         int64_t N, int BN, bool a_mn = false, bool b_mn = false) {
   BLM_REQUIRE(nseg >= 1 && nseg <= BLM_MAX_SEG, BLM_ERR_ARG, "nseg=%d out of range", nseg);
   p.nseg = nseg;
   for (int s = 0; s < nseg; ++s) {
     BLM_REQUIRE(A[s] && B[s], BLM_ERR_ARG, "segment %d has a null operand", s);
     BLM_REQUIRE(K[s] > 0, BLM_ERR_SHAPE, "K[%d]=%lld must be positive", s, (long long)K[s]);
-    int rc = encode_tmap_bf16(&p.tmA[s], A[s], M, K[s], lda[s], kBM);
+    // MN-major operands are [K_s, M] / [K_s, N] row-major: boxes of 64 reduction rows x 64 contiguous elements
+    int rc = a_mn ? encode_tmap_bf16(&p.tmA[s], A[s], K[s], M, lda[s], 64) : encode_tmap_bf16(&p.tmA[s], A[s], M, K[s], lda[s], kBM);
     if (rc != BLM_OK) return rc;
-    rc = encode_tmap_bf16(&p.tmB[s], B[s], N, K[s], ldb[s], BN);
+    rc = b_mn ? encode_tmap_bf16(&p.tmB[s], B[s], K[s], N, ldb[s], 64) : encode_tmap_bf16(&p.tmB[s], B[s], N, K[s], ldb[s], BN);
     if (rc != BLM_OK) return rc;
     p.kblocks[s] = static_cast<int>((K[s] + kBK - 1) / kBK);
   }
@@ -702,8 +717,10 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  int rc = fill_segments(p, d->nseg, d->A, d->B, d->K, d->lda, d->ldb, d->M, d->N, BN);
+  int rc = fill_segments(p, d->nseg, d->A, d->B, d->K, d->lda, d->ldb, d->M, d->N, BN, d->a_mn != 0, d->b_mn != 0);
   if (rc != BLM_OK) return rc;
+  p.a_mn = d->a_mn != 0;
+  p.b_mn = d->b_mn != 0;
   p.M = static_cast<int>(d->M);
   p.N = static_cast<int>(d->N);
   p.m_tiles = m_tiles;
@@ -748,7 +765,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   }
   cudaStream_t st = as_stream(stream);
   // CTA-pair kernel: one bf16 segment, bf16-only output, forward activations, enough 256 x 256 tiles
-  if (!gen && !d->a_f16 && use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
+  if (!gen && !d->a_f16 && !d->a_mn && !d->b_mn && use_gemm2() && !chunked && d->nseg == 1 && !d->out_f32 && !d->out_pre && d->N >= 256 &&
       (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST) &&
       static_cast<long long>((d->M + 255) / 256) * ((d->N + 255) / 256) >= num_sms() / 2) {
     GemmParams p2 = p;
@@ -819,7 +836,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   // row-per-thread stores were (fixed by the store transpose), and a single resident A buffer stalls
   // every work boundary.
   static const bool no_ares = getenv("BLM_GEMM_ARES") == nullptr;
-  if (BN == 256 && !no_ares && d->nseg == 1 && p.kblocks[0] <= kNllAres && p.n_tiles >= 4 && p.m_tiles >= num_sms() &&
+  if (BN == 256 && !no_ares && !d->a_mn && !d->b_mn && d->nseg == 1 && p.kblocks[0] <= kNllAres && p.n_tiles >= 4 && p.m_tiles >= num_sms() &&
       (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GPMIX)) {
     p.n_groups = 1;
     p.tiles_per_group = p.n_tiles;

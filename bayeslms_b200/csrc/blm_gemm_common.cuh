@@ -36,6 +36,8 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ldc;
+  int a_mn, b_mn;       // 1: the operand is MN-major: A[s] is [K_s, M] / B[s] is [K_s, N] row-major (wgrad / dgrad
+                        // straight from the activations / weights, no transposed copies); boxes of 64 x 64
   int a_f16;            // 1: A operands are fp16 (instruction descriptor A format F16, B stays BF16)
   int use_stg;          // 1: transpose finished chunks through shared memory for row-coalesced stores
   int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk

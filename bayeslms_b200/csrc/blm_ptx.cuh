@@ -241,6 +241,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the MMA's M / N index is the contiguous one in memory, e.g. dY[m][n] used as the A = dY^T of a
+// weight gradient): TMA lands [64 reduction rows x 64 contiguous elements] boxes (8 KB, SWIZZLE_128B) back to back
+// along MN.  Canonical layout Swizzle<3,4,3> o ((8,8,mn),(8,k)):((1,8,LBO),(64,SBO)) in elements: a reduction row
+// is one 128-byte line, 8 rows form a 1024-byte swizzle atom (SBO), the next 64-wide MN block is the next box (LBO).
+// One K = 16 step covers two atoms: the start address advances by 2048 bytes per step.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;   // LBO: next 64-element block along MN
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;   // SBO: next group of 8 reduction rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10),
 // both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {

@@ -119,25 +119,29 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
          out: Optional[Split] = None, extra: Sequence = (), tag: str = "", out_pre: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
          targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None,
-         a_f16: bool = False):
+         a_f16: bool = False, a_mn: bool = False, b_mn: bool = False):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
     accumulated into the same output (K-concatenation).  ``out_pre`` receives the fp32 value before
     the activation; ``aux`` is the saved pre-activation of the ``*_GRAD`` epilogues; ``lse`` /
     ``targets`` / ``grad_scale`` feed ``ACT_SOFTMAX_GRAD``.  ``k_chunk`` (default: 128 in bf16x3 mode)
-    bounds the length of one tensor-core accumulation (see ``blm_gemm_desc.k_chunk``)."""
+    bounds the length of one tensor-core accumulation (see ``blm_gemm_desc.k_chunk``).
+    ``a_mn`` / ``b_mn``: the operand is given MN-major, a as [K, M] / b as [K, N] (e.g. ``dW = gemm(dY, X, a_mn=True,
+    b_mn=True)`` with dY [tokens, N], X [tokens, K]; ``dX = gemm(dY, W, b_mn=True)`` with W [N, K])."""
     segs = _segments(a, b, prec)
     for (a2, b2) in extra:
         segs += _segments(a2, b2, prec)
-    M, N = a.hi.shape[0], b.hi.shape[0]
+    M = a.hi.shape[1] if a_mn else a.hi.shape[0]
+    N = b.hi.shape[1] if b_mn else b.hi.shape[0]
     d = GemmDesc()
     d.M, d.N, d.nseg, d.act = M, N, len(segs), act
     for i, (x, w) in enumerate(segs):
         _require_cuda(x, w)
         want = torch.float16 if a_f16 else torch.bfloat16     # fp16 mode: BOTH operands (mixed types are illegal on sm_100a)
         assert x.dtype == want and w.dtype == want
-        assert x.shape[1] == w.shape[1] and x.stride(1) == 1 and w.stride(1) == 1
+        kx, kw = x.shape[0 if a_mn else 1], w.shape[0 if b_mn else 1]
+        assert kx == kw and x.stride(1) == 1 and w.stride(1) == 1
         d.A[i], d.B[i] = x.data_ptr(), w.data_ptr()
-        d.K[i], d.lda[i], d.ldb[i] = x.shape[1], x.stride(0), w.stride(0)
+        d.K[i], d.lda[i], d.ldb[i] = kx, x.stride(0), w.stride(0)
     d.bias, d.coef = _ptr(bias), _ptr(coef)
     d.col_scale, d.col_scale_cols = col_scale, col_scale_cols
     if resid is not None:
@@ -161,8 +165,8 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     if lse is not None:
         d.lse, d.targets, d.grad_scale = _ptr(lse), _ptr(targets), grad_scale
     d.k_chunk = (PRECISE_K_CHUNK if prec == "bf16x3" else 0) if k_chunk is None else k_chunk
-    d.a_f16 = int(a_f16)
-    with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[1] for x, _ in segs)):
+    d.a_f16, d.a_mn, d.b_mn = int(a_f16), int(a_mn), int(b_mn)
+    with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[0 if a_mn else 1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
 
 

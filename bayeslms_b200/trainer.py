@@ -23,12 +23,47 @@ Dropout: the reference trains with dropout; masks are not reproduced here -- the
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
 
 from . import _lib, engine, ops
 from .ops import (ACT_GELU, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, Split)
+
+# Weight gradients dW = dY^T X and input gradients dX = dY W consume their "transposed" operands MN-major straight
+# from the [tokens, features] activations / [N, K] weights (blm_gemm_desc.a_mn / b_mn, tcgen05 MN-major shared
+# memory descriptors): the 42 transpose + 21 split-transpose launches of a step (a sixth of its time) are gone.
+# BLM_TRAIN_TRANSPOSE=1 restores the materialised transposes (A/B switch).
+_MN = os.environ.get("BLM_TRAIN_TRANSPOSE") is None
+
+
+class _T:
+    """An operand that stands for the TRANSPOSE of the Split it holds."""
+    __slots__ = ("s",)
+
+    def __init__(self, s: Split):
+        self.s = s
+
+    def rows(self, sl: slice) -> "_T":
+        """Rows ``sl`` of the transpose = columns of the held tensor."""
+        return _T(Split(self.s.hi[:, sl], None if self.s.lo is None else self.s.lo[:, sl]))
+
+
+def _gemm(a, b, **kw):
+    a_mn, b_mn = isinstance(a, _T), isinstance(b, _T)
+    return ops.gemm(a.s if a_mn else a, b.s if b_mn else b, a_mn=a_mn, b_mn=b_mn, **kw)
+
+
+def _tsplit(x: torch.Tensor, prec: str, have: Optional[Split] = None):
+    """Transpose of an fp32 tensor as a GEMM operand (``have``: an existing Split of x to reuse)."""
+    if _MN:
+        return _T(have if have is not None else ops.split(x, prec))
+    return ops.transpose_split(x, prec)
+
+
+def _tbf16(s: Split, prec: str):
+    return _T(s) if _MN else ops.transpose_bf16(s, prec)
 
 _TID = engine._TID
 V_NOISE_STD = 0.1          # model.py:2786: normal_(0, 0.1)
@@ -80,11 +115,14 @@ class FineTuner:
 
     def _w2(self, w: torch.Tensor):
         """(Split [N, K], Split [K, N]) of an fp32 weight: forward B operand and dgrad B operand, one pass."""
+        if _MN:
+            sp = ops.split(w.detach().float().contiguous(), self.prec)
+            return sp, _T(sp)
         return ops.split_transpose(w.detach().float().contiguous(), self.prec)
 
     def _wt(self, w: torch.Tensor) -> Split:
         """[N, K] fp32 weight -> Split of its transpose [K, N] (B operand of the dgrad product)."""
-        return ops.transpose_split(w.detach().float().contiguous(), self.prec)
+        return _tsplit(w.detach().float().contiguous(), self.prec)
 
     def _reparam32(self, mu, lgstd, tid, eps_t, seed):
         """fp32 sample mu + exp(lgstd) * eps of one tensor (injected eps or Philox stream (tid, 0))."""
@@ -99,7 +137,7 @@ class FineTuner:
 
     def _wgrad(self, dy_t: Split, x_t: Split, out: torch.Tensor, tag: str):
         """out[N, K] = dY^T X, both operands given transposed ([N, M] and [K, M])."""
-        ops.gemm(dy_t, x_t, prec=self.prec, out_f32=out, tag="wgrad:" + tag)
+        _gemm(dy_t, x_t, prec=self.prec, out_f32=out, tag="wgrad:" + tag)
 
     # ------------------------------------------------------------------ one step
     def forward_backward(self, tokens_tb: torch.Tensor, targets_tb: torch.Tensor, kl_scale: float, *,
@@ -142,7 +180,7 @@ class FineTuner:
             w_in, w_in_t = self._w2(w_in32)
             x32 = self._f32(M, d)
             xs = ops.empty_split(M, d, prec, dev)
-            ops.gemm(x0s, w_in, prec=prec, resid=pe_rows, out_f32=x32, out=xs, tag="embed_in")
+            _gemm(x0s, w_in, prec=prec, resid=pe_rows, out_f32=x32, out=xs, tag="embed_in")
             E_in = {"x0s": x0s, "w_in_t": w_in_t, "eps": ee, "sampled": sampled}
         else:
             x32, xs = ops.embed(tok, pos, m.encoder.weight.detach().float(), pe, math.sqrt(d), prec=prec)
@@ -164,12 +202,12 @@ class FineTuner:
             else:
                 wqkv32, bqkv, wo32, bo = a.qkv_net.weight, a.qkv_net.bias.detach(), a.o_net.weight, a.o_net.bias.detach()
             wqkv, S["wqkv_t"] = self._w2(wqkv32)
-            ops.gemm(xs, wqkv, prec=prec, bias=bqkv, col_scale=scale_q,
+            _gemm(xs, wqkv, prec=prec, bias=bqkv, col_scale=scale_q,
                      col_scale_cols=d, out_f32=qkv32, out=qkvs, tag="qkv")
             _, atts = ops.mha_causal_bf16(qkvs, offs, nhead, T, prec=prec)
             y1 = self._f32(M, d)
             wo, S["wo_t"] = self._w2(wo32)
-            ops.gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net")
+            _gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net")
             x1_32, x1s = ops.layernorm(y1, layer.norm1.weight.detach(), layer.norm1.bias.detach(), layer.norm1.eps, prec=prec)
             S.update(qkv32=qkv32, atts=atts, y1=y1, x1_32=x1_32, x1s=x1s)
             # first FFN projection (+ GELU or the GP mixture), pre-activation kept
@@ -192,12 +230,12 @@ class FineTuner:
                         b1 = self._reparam32(gp.bias_mean.detach(), gp.bias_lgstd.detach(), _TID["gp_b"], ge("bias"), seed)
                 coef = coef.contiguous()
                 w1, S["w1_t"] = self._w2(w1_32)
-                ops.gemm(x1s, w1, prec=prec, bias=b1, act=ACT_GPMIX, coef=coef, out=hs, out_pre=z1, tag="ffn1")
+                _gemm(x1s, w1, prec=prec, bias=b1, act=ACT_GPMIX, coef=coef, out=hs, out_pre=z1, tag="ffn1")
                 S["coef"] = coef
             else:
                 w1_32 = layer.linear1.weight.detach()
                 w1, S["w1_t"] = self._w2(w1_32)
-                ops.gemm(x1s, w1, prec=prec, bias=layer.linear1.bias.detach(), act=ACT_GELU, out=hs, out_pre=z1,
+                _gemm(x1s, w1, prec=prec, bias=layer.linear1.bias.detach(), act=ACT_GELU, out=hs, out_pre=z1,
                          tag="ffn1")
             S.update(z1=z1, hs=hs)
             # second FFN projection
@@ -221,7 +259,7 @@ class FineTuner:
                     raise _lib.BlmError("the variational layer is defined for sequence length 100 only "
                                         "(its parameters are (100, 1, d), model.py:2754-2761)")
                 f = self._f32(M, d)
-                ops.gemm(hs, w2, prec=prec, bias=b2, out_f32=f, tag="ffn2")
+                _gemm(hs, w2, prec=prec, bias=b2, out_f32=f, tag="ffn2")
                 le = eps.get(f"layer{li}")
                 if le is None:
                     e_bt = None
@@ -234,7 +272,7 @@ class FineTuner:
                                     noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
                 S.update(f=f, v_eps=e_bt)
             else:
-                ops.gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
+                _gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
             x32, xs = ops.layernorm(y2, layer.norm2.weight.detach(), layer.norm2.bias.detach(), layer.norm2.eps, prec=prec)
             S["y2"] = y2
             saved.append(S)
@@ -243,14 +281,14 @@ class FineTuner:
             xs_pre = xs
             em, em_t = self._w2(m.embed_mean.detach())            # em [k, n] (dgrad operand), em_t = embed_mean^T (forward)
             xs = ops.empty_split(M, d, prec, dev)
-            ops.gemm(xs_pre, em_t, prec=prec, out=xs, tag="embed_out")
+            _gemm(xs_pre, em_t, prec=prec, out=xs, tag="embed_out")
 
         dx, ce, kl, loss = self._loss_and_decoder_grads(xs, tgt)
         if emb_variant:   # back through x @ embed_mean: d embed_mean += x^T dout, dx = dout @ embed_mean^T
             dout = dx
-            self._wgrad(ops.transpose_bf16(xs_pre, prec), ops.transpose_split(dout, prec), g["embed_mean"], "embed_out")
+            self._wgrad(_tbf16(xs_pre, prec), _tsplit(dout, prec), g["embed_mean"], "embed_out")
             dx = self._f32(M, d)
-            ops.gemm(ops.split(dout, prec), em, prec=prec, out_f32=dx, tag="dgrad:embed_out")
+            _gemm(ops.split(dout, prec), em, prec=prec, out_f32=dx, tag="dgrad:embed_out")
 
         # ---------------------------------------------------------------- backward: layers
         for li in range(len(saved) - 1, -1, -1):
@@ -273,12 +311,12 @@ class FineTuner:
             dz1s = ops.empty_split(M, S["z1"].shape[1], prec, dev)
             if kind == "gauss":
                 dh = torch.empty_like(dz1)
-                ops.gemm(dfs, S["w2_t"], prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,
+                _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,
                          out=dz1s, out_pre=dh, tag="dgrad:ffn2")
             else:
-                ops.gemm(dfs, S["w2_t"], prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
+                _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
                          tag="dgrad:ffn2")
-            dft, ht = ops.transpose_split(df, prec), ops.transpose_bf16(S["hs"], prec)
+            dft, ht = _tsplit(df, prec, dfs), _tbf16(S["hs"], prec)
             if kind == "bayes_ffn":
                 G = g[pre + "linear2.weight_mean"]
                 self._wgrad(dft, ht, G, "ffn2")
@@ -294,8 +332,8 @@ class FineTuner:
                 ops.colsum(df, g[pre + "linear2.bias"])
             # FFN1
             dx1 = self._f32(M, d)
-            ops.gemm(dz1s, S["w1_t"], prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
-            dz1t, x1t = ops.transpose_split(dz1, prec), ops.transpose_bf16(S["x1s"], prec)
+            _gemm(dz1s, S["w1_t"], prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
+            dz1t, x1t = _tsplit(dz1, prec, dz1s), _tbf16(S["x1s"], prec)
             if kind == "gauss":
                 self._gp_backward(layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, eps.get(f"layer{li}"), seed)
             else:
@@ -306,8 +344,8 @@ class FineTuner:
                                     g[pre + "norm1.bias"])
             dy1s = ops.split(dy1, prec)
             datt = self._f32(M, d)
-            ops.gemm(dy1s, S["wo_t"], prec=prec, out_f32=datt, tag="dgrad:o_net")
-            dy1t, attt = ops.transpose_split(dy1, prec), ops.transpose_bf16(S["atts"], prec)
+            _gemm(dy1s, S["wo_t"], prec=prec, out_f32=datt, tag="dgrad:o_net")
+            dy1t, attt = _tsplit(dy1, prec, dy1s), _tbf16(S["atts"], prec)
             if kind == "bayes_mha":
                 G, lin = g[pre + "self_attn.o_net.weight_mean"], a.o_net
                 self._wgrad(dy1t, attt, G, "o_net")
@@ -322,30 +360,31 @@ class FineTuner:
                 ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
             dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q)
             dx = self._f32(M, d)
-            ops.gemm(ops.split(dqkv, prec), S["wqkv_t"], prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
-            dqkvt, xst = ops.transpose_split(dqkv, prec), ops.transpose_bf16(S["xs"], prec)
+            dqkvs = ops.split(dqkv, prec)
+            _gemm(dqkvs, S["wqkv_t"], prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
+            dqkvt, xst = _tsplit(dqkv, prec, dqkvs), _tbf16(S["xs"], prec)
             if kind == "bayes_mha":
                 for k, nm in enumerate(("q_net", "k_net", "v_net")):
                     rows = slice(k * d, (k + 1) * d)
-                    part = Split(dqkvt.hi[rows], None if dqkvt.lo is None else dqkvt.lo[rows])
+                    part = dqkvt.rows(rows) if _MN else Split(dqkvt.hi[rows], None if dqkvt.lo is None else dqkvt.lo[rows])
                     self._wgrad(part, xst, g[pre + f"self_attn.{nm}.weight"], nm)
                     ops.colsum(dqkv[:, rows], g[pre + f"self_attn.{nm}.bias"])
             else:
                 self._wgrad(dqkvt, xst, g[pre + "self_attn.qkv_net.weight"], "qkv")
                 ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
         if emb_variant:   # back through x0 W~^T: G = dx^T x0 (-> embed_mean, embed_lgstd), dx0 = dx W~
-            dxt, x0t = ops.transpose_split(dx, prec), ops.transpose_bf16(E_in["x0s"], prec)
+            dxt, x0t = _tsplit(dx, prec), _tbf16(E_in["x0s"], prec)
             if E_in["sampled"]:
                 G = self._f32(d, d)
                 self._wgrad(dxt, x0t, G, "embed_in")
                 ops.reparam_bwd(G, m.embed_lgstd.detach(), g["embed_mean"], g["embed_lgstd"], eps=E_in["eps"], seed=seed,
                                 stream_id=engine._stream_id(_TID["embed"], 0), accumulate=True)
             else:   # added onto the output-side gradient already in place (residual operand = output)
-                ops.gemm(dxt, x0t, prec=prec, resid=g["embed_mean"], out_f32=g["embed_mean"], tag="wgrad:embed_in")
+                _gemm(dxt, x0t, prec=prec, resid=g["embed_mean"], out_f32=g["embed_mean"], tag="wgrad:embed_in")
             ops.kl_gauss(m.embed_mean.detach(), m.embed_lgstd.detach(), kl, accumulate=True)
             ops.kl_gauss_bwd(m.embed_mean.detach(), m.embed_lgstd.detach(), kl_scale, g["embed_mean"], g["embed_lgstd"])
             dx0 = self._f32(M, d)
-            ops.gemm(ops.split(dx, prec), E_in["w_in_t"], prec=prec, out_f32=dx0, tag="dgrad:embed_in")
+            _gemm(ops.split(dx, prec), E_in["w_in_t"], prec=prec, out_f32=dx0, tag="dgrad:embed_in")
             dx = dx0
         # embedding: scatter-add on top of the decoder's weight gradient when the weights are tied
         ops.embed_bwd(dx, tok, math.sqrt(d), g["encoder.weight"])
@@ -373,11 +412,11 @@ class FineTuner:
         ldv = ops._ld8(V)
         dZ = Split(torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V],
                    torch.empty(M, ldv, dtype=torch.bfloat16, device=dev)[:, :V] if prec == "bf16x3" else None)
-        ops.gemm(xs, Es, prec=prec, bias=dec_b, act=ACT_SOFTMAX_GRAD, lse=lse, targets=tgt, grad_scale=1.0 / M, out=dZ,
+        _gemm(xs, Es, prec=prec, bias=dec_b, act=ACT_SOFTMAX_GRAD, lse=lse, targets=tgt, grad_scale=1.0 / M, out=dZ,
                  tag="dlogits")
         dx = self._f32(M, d)
-        ops.gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
-        self._wgrad(ops.transpose_bf16(dZ, prec), ops.transpose_bf16(xs, prec), g["decoder.weight"], "decoder")
+        _gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
+        self._wgrad(_tbf16(dZ, prec), _tbf16(xs, prec), g["decoder.weight"], "decoder")
         ops.colsum(dZ, g["decoder.bias"])
         return dx, ce, kl, loss
 
@@ -438,7 +477,7 @@ class FineTuner:
             w_ih, w_ih_t = self._w2(P["w_ih"])
             w_hh, w_hh_t = self._w2(P["w_hh"])
             gates = self._f32(M, 4 * H)
-            ops.gemm(x, w_ih, prec=prec, bias=P["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+            _gemm(x, w_ih, prec=prec, bias=P["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
             _, out, h_last, c_last = ops.lstm_layer(gates, w_hh, h0[li], c0[li], lengths, T, B, H, prec=prec,
                                                     want_f32=False, want_split=True)
             saved.append({"x": x, "out": out, "gates": gates, "w_ih_t": w_ih_t, "w_hh": w_hh, "w_hh_t": w_hh_t})
@@ -455,7 +494,7 @@ class FineTuner:
             hprev = Split(torch.cat([h0s.hi, S["out"].hi[:M - B]], 0),
                           None if h0s.lo is None else torch.cat([h0s.lo, S["out"].lo[:M - B]], 0))
             gates = S["gates"]
-            ops.gemm(hprev, S["w_hh"], prec=prec, resid=gates, out_f32=gates, tag="lstm_rebuild")
+            _gemm(hprev, S["w_hh"], prec=prec, resid=gates, out_f32=gates, tag="lstm_rebuild")
             c_all = ops.lstm_gates_act(gates, c0[li], T, B, H)
             dG = self._f32(M, 4 * H)
             dGs = ops.empty_split(M, 4 * H, prec, dev)
@@ -469,18 +508,18 @@ class FineTuner:
                 ops.lstm_bwd_step(gates[sl], c_prev, c_all[sl], dout[sl], rec, dc, t == T - 1, dG[sl], dGt)
                 if t > 0:
                     rec = dh[t & 1]
-                    ops.gemm(dGt, S["w_hh_t"], prec=prec, out_f32=rec, tag="lstm_dh")
+                    _gemm(dGt, S["w_hh_t"], prec=prec, out_f32=rec, tag="lstm_dh")
             # input gradient, weight gradients, biases
-            dGT = ops.transpose_split(dG, prec)
+            dGT = _tsplit(dG, prec)
             pre = "rnn."
             G_ih, G_hh = g[f"{pre}weight_ih_mean_{layer}"], g[f"{pre}weight_hh_mean_{layer}"]
-            self._wgrad(dGT, ops.transpose_bf16(S["x"], prec), G_ih, f"lstm_ih{layer}")
-            self._wgrad(dGT, ops.transpose_bf16(hprev, prec), G_hh, f"lstm_hh{layer}")
+            self._wgrad(dGT, _tbf16(S["x"], prec), G_ih, f"lstm_ih{layer}")
+            self._wgrad(dGT, _tbf16(hprev, prec), G_hh, f"lstm_hh{layer}")
             gb_ih, gb_hh = g[f"{pre}bias_ih_mean_{layer}"], g[f"{pre}bias_hh_mean_{layer}"]
             ops.colsum(dG, gb_ih)
             ops.colsum(dG, gb_hh)
             dx = self._f32(M, S["x"].hi.shape[1])
-            ops.gemm(dGs, S["w_ih_t"], prec=prec, out_f32=dx, tag="dgrad:lstm_in")
+            _gemm(dGs, S["w_ih_t"], prec=prec, out_f32=dx, tag="dgrad:lstm_in")
             dout = dx
             if bayes:
                 rows = r.gate_rows()

@@ -129,6 +129,10 @@ typedef struct blm_gemm_desc {
   int64_t ldaux;
   int32_t a_f16;       /* 1: A AND B operands hold IEEE fp16 bits instead of bf16 (tcgen05 kind::f16; mixing
                           A = f16 with B = bf16 is an illegal instruction on sm_100a).  One segment, no k_chunk. */
+  int32_t a_mn;        /* 1: A[s] is given MN-major, i.e. as the row-major [K_s, M] tensor (leading dimension lda[s]):  */
+  int32_t b_mn;        /* 1: B[s] is the row-major [K_s, N] tensor.  Weight gradients dW = dY^T X take dY [tokens, N]
+                          and X [tokens, K] as they are (a_mn = b_mn = 1), input gradients dX = dY W take W [N, K]
+                          as it is (b_mn = 1): no transposed copies (tcgen05 MN-major shared-memory descriptors)  */
   int32_t reserved;
 } blm_gemm_desc;
 

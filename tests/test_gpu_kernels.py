@@ -371,3 +371,44 @@ def test_fp16_operands(ops):
     out = torch.empty(M, N, device=DEV)
     ops.gemm(ops.Split(a), ops.Split(b), prec="bf16", out_f32=out, a_f16=True)
     _close(out, a.double() @ b.double().T, 1e-5)
+
+
+@pytest.mark.parametrize("M,N,K,prec,a_mn,b_mn", [
+    (512, 256, 128, "bf16", True, True),
+    (4096, 512, 3200, "bf16", True, True),        # wgrad FFN1: dW[4096, 512] = dZ^T X over 3200 tokens
+    (512, 4096, 3200, "bf16x3", True, True),      # wgrad FFN2, precise (three segments)
+    (3200, 512, 4096, "bf16", False, True),       # dgrad FFN1: dX[3200, 512] = dZ[3200, 4096] W1[4096, 512]
+    (3200, 4096, 512, "bf16x3", False, True),     # dgrad FFN2
+    (1536, 520, 3203, "bf16x3", True, True),      # ragged reduction length and N
+    (300, 200, 80, "bf16", True, False),
+    (30000, 512, 3200, "bf16", True, True),       # decoder wgrad
+])
+def test_gemm_mn_major_operands(ops, M, N, K, prec, a_mn, b_mn):
+    """MN-major operands (no transposed copies for wgrad / dgrad): a given as [K, M] and / or b as [K, N]."""
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    pad8 = lambda n: (n + 7) // 8 * 8   # noqa: E731
+    if a_mn:
+        buf = torch.zeros(K, pad8(M), device=DEV)
+        buf[:, :M] = a.t()
+        A = ops.split(buf, prec)
+        A = ops.Split(A.hi[:, :M], None if A.lo is None else A.lo[:, :M])
+    else:
+        A = ops.split(a, prec)
+    if b_mn:
+        buf = torch.zeros(K, pad8(N), device=DEV)
+        buf[:, :N] = b.t()
+        B = ops.split(buf, prec)
+        B = ops.Split(B.hi[:, :N], None if B.lo is None else B.lo[:, :N])
+    else:
+        B = ops.split(b, prec)
+    out = torch.empty(M, pad8(N), device=DEV)[:, :N]
+    bias = torch.randn(N, device=DEV)
+    ops.gemm(A, B, prec=prec, bias=bias, out_f32=out, a_mn=a_mn, b_mn=b_mn)
+    if prec == "bf16":
+        af = A.hi.double().t() if a_mn else A.hi.double()
+        bf = B.hi.double().t() if b_mn else B.hi.double()
+        ref = af @ bf.T + bias.double()
+        _close(out, ref, 2e-5)
+    else:
+        _close(out, a.double() @ b.double().T + bias.double(), 2e-5)

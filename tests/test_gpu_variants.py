@@ -34,3 +34,8 @@ def test_cluster_sampled_gemm():
 
 def test_lstm_cluster_multicast_and_stagger():
     _run({"BLM_LSTM_CLUSTER": "1", "BLM_LSTM_STAGGER": "1"}, ["tests/test_gpu_lstm.py"])
+
+
+def test_training_with_materialised_transposes():
+    """BLM_TRAIN_TRANSPOSE=1: the fine-tune step with transposed operand copies instead of MN-major descriptors."""
+    _run({"BLM_TRAIN_TRANSPOSE": "1"}, ["tests/test_gpu_train.py", "-k", "bayes_tm or lstm_finetune_step"])
