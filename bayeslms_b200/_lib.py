@@ -120,6 +120,7 @@ SIGNATURES = {
     "blm_reduce_workspace_bytes": (_i64, []),
     "blm_reduce": (C.c_int, [_p, _i64, _i32, _f, _i32, _p, _p, _p]),
     "blm_sgd_momentum": (C.c_int, [_p, _p, _p, _i64, _f, _f, _p, _f, _f, _p]),
+    "blm_sgd_momentum_split": (C.c_int, [_p, _p, _p, _i64, _f, _f, _p, _f, _f, _p, _p, _p]),
     "blm_lstm_gates_act": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "blm_lstm_bwd_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p]),
     "blm_lstm_workspace_bytes": (_i64, [_i64, _i64]),

@@ -686,9 +686,12 @@ __global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ x
 // torch.nn.utils.clip_grad_norm_ + SGD(momentum) of train.py:419,466:
 //   c = min(1, max_norm / (sqrt(norm_sq) * grad_scale + 1e-6));  g' = c * grad_scale * g
 //   v = momentum * v + g';  p -= lr * v
+// out_hi / out_lo (optional): the bf16 (hi, lo) operand copies of the UPDATED parameters, so the next step's GEMMs
+// need no per-weight split launches.
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v,
                                     long long n, float lr, float momentum, const float* __restrict__ norm_sq,
-                                    float max_norm, float grad_scale) {
+                                    float max_norm, float grad_scale, __nv_bfloat16* __restrict__ out_hi,
+                                    __nv_bfloat16* __restrict__ out_lo) {
   float c = grad_scale;
   if (norm_sq && max_norm > 0.0f) {
     const float norm = sqrtf(norm_sq[0]) * grad_scale;
@@ -698,7 +701,13 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float nv = fmaf(momentum, v[i], c * g[i]);
     v[i] = nv;
-    p[i] = fmaf(-lr, nv, p[i]);
+    const float np_ = fmaf(-lr, nv, p[i]);
+    p[i] = np_;
+    if (out_hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(np_);
+      out_hi[i] = h;
+      if (out_lo) out_lo[i] = __float2bfloat16_rn(np_ - __bfloat162float(h));
+    }
   }
 }
 
@@ -991,7 +1000,18 @@ int blm_sgd_momentum(float* p, const float* g, float* v, int64_t n, float lr, fl
   using namespace blm;
   BLM_REQUIRE(p && g && v && n > 0, BLM_ERR_ARG, "bad sgd arguments");
   sgd_momentum_kernel<<<tgrid(n, 256, 8), 256, 0, as_stream(stream)>>>(p, g, v, n, lr, momentum, norm_sq, max_norm,
-                                                                      grad_scale);
+                                                                      grad_scale, nullptr, nullptr);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_sgd_momentum_split(float* p, const float* g, float* v, int64_t n, float lr, float momentum, const float* norm_sq,
+                           float max_norm, float grad_scale, blm_bf16* out_hi, blm_bf16* out_lo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(p && g && v && out_hi && n > 0, BLM_ERR_ARG, "bad sgd arguments");
+  sgd_momentum_kernel<<<tgrid(n, 256, 8), 256, 0, as_stream(stream)>>>(
+      p, g, v, n, lr, momentum, norm_sq, max_norm, grad_scale, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      reinterpret_cast<__nv_bfloat16*>(out_lo));
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

@@ -693,8 +693,16 @@ def reduce_sum(x: torch.Tensor, out: torch.Tensor, *, squares: bool = False, sca
 
 
 def sgd_momentum(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr: float, momentum: float,
-                 norm_sq: Optional[torch.Tensor], max_norm: float, grad_scale: float = 1.0) -> None:
+                 norm_sq: Optional[torch.Tensor], max_norm: float, grad_scale: float = 1.0,
+                 out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> None:
+    """clip + SGD momentum over flat buffers; ``out_hi`` / ``out_lo``: bf16 operand copies of the updated parameters."""
     assert p.is_contiguous() and g.is_contiguous() and v.is_contiguous() and p.numel() == g.numel() == v.numel()
+    if out_hi is not None:
+        assert out_hi.dtype == torch.bfloat16 and out_hi.numel() == p.numel() and out_hi.is_contiguous()
+        with _op("sgd_momentum", 1):
+            check(lib().blm_sgd_momentum_split(_ptr(p), _ptr(g), _ptr(v), p.numel(), lr, momentum, _ptr(norm_sq), max_norm,
+                                               grad_scale, _ptr(out_hi), _ptr(out_lo), _stream()), "blm_sgd_momentum_split")
+        return
     with _op("sgd_momentum", 1):
         check(lib().blm_sgd_momentum(_ptr(p), _ptr(g), _ptr(v), p.numel(), lr, momentum, _ptr(norm_sq), max_norm,
                                      grad_scale, _stream()), "blm_sgd_momentum")

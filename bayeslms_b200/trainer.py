@@ -36,6 +36,8 @@ from .ops import (ACT_GELU, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, 
 # memory descriptors): the 42 transpose + 21 split-transpose launches of a step (a sixth of its time) are gone.
 # BLM_TRAIN_TRANSPOSE=1 restores the materialised transposes (A/B switch).
 _MN = os.environ.get("BLM_TRAIN_TRANSPOSE") is None
+# the optimiser kernel writes the bf16 operand copies of the updated weights (BLM_TRAIN_NO_MIRROR=1: split per step)
+_MIRROR = os.environ.get("BLM_TRAIN_NO_MIRROR") is None
 
 
 class _T:
@@ -93,7 +95,7 @@ class FineTuner:
         offs, total = {}, 0
         for name, p in named:
             offs[name] = total
-            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned views
+            total += (p.numel() + 7) // 8 * 8          # 16-byte aligned views of the fp32 AND the bf16 mirror buffers
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -106,17 +108,44 @@ class FineTuner:
                 self.g[name] = self.flat_g[o:o + n].view(p.shape)
         if model.decoder.weight is model.encoder.weight:
             self.g["decoder.weight"] = self.g["encoder.weight"]
+        # bf16 (hi[, lo]) mirrors of the parameters: written by the optimiser kernel together with the update, so a
+        # step splits no weight (21 launches); re-made from scratch whenever a parameter was written from outside
+        self.flat_hi = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self.flat_lo = torch.zeros(total, dtype=torch.bfloat16, device=dev) if prec == "bf16x3" else None
+        self._params = [p for _, p in named]
+        self._seen_version = None
         self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss_buf = torch.zeros(3, dtype=torch.float32, device=dev)   # ce, kl, loss
 
     # ------------------------------------------------------------------ helpers
+    def refresh_weights(self) -> None:
+        """Re-make the bf16 mirrors from the fp32 parameters (after load_state_dict or any external write)."""
+        with torch.no_grad():
+            _lib.check(_lib.lib().blm_split_bf16(ops._ptr(self.flat_p), ops._ptr(self.flat_hi), ops._ptr(self.flat_lo),
+                                                 self.flat_p.numel(), ops._stream()), "blm_split_bf16")
+        self._seen_version = sum(p._version for p in self._params)
+
+    def _check_mirrors(self) -> None:
+        if self._seen_version != sum(p._version for p in self._params):
+            self.refresh_weights()
+
+    def _mirror(self, w: torch.Tensor) -> Optional[Split]:
+        """The (hi[, lo]) mirror views of a parameter tensor that lives in the flat buffer, else None."""
+        if w.dtype != torch.float32 or not w.is_contiguous() or not _MIRROR:
+            return None
+        off = w.data_ptr() - self.flat_p.data_ptr()
+        if off < 0 or off + 4 * w.numel() > 4 * self.flat_p.numel() or off % 32:
+            return None
+        o, n = off // 4, w.numel()
+        return Split(self.flat_hi[o:o + n].view(w.shape), None if self.flat_lo is None else self.flat_lo[o:o + n].view(w.shape))
+
     def _w(self, w: torch.Tensor) -> Split:
-        return ops.split(w.detach(), self.prec)
+        return self._mirror(w.detach()) or ops.split(w.detach(), self.prec)
 
     def _w2(self, w: torch.Tensor):
         """(Split [N, K], Split [K, N]) of an fp32 weight: forward B operand and dgrad B operand, one pass."""
         if _MN:
-            sp = ops.split(w.detach().float().contiguous(), self.prec)
+            sp = self._w(w.detach().float().contiguous())
             return sp, _T(sp)
         return ops.split_transpose(w.detach().float().contiguous(), self.prec)
 
@@ -148,6 +177,7 @@ class FineTuner:
         already scaled by 0.1, or (B, T, d) with ``v_eps_layout="btd"``); ``seed``: Philox noise instead.
         LSTM families: ``hidden`` = (h, c) carried in from the previous batch (zeros if None); the state
         after the batch is left in ``self.hidden``."""
+        self._check_mirrors()
         if self.model.family == "bayes_lstm":
             return self._lstm_forward_backward(tokens_tb, targets_tb, kl_scale, hidden, eps, seed)
         m, prec, dev = self.model, self.prec, self.device
@@ -576,7 +606,7 @@ class FineTuner:
             torch.distributed.all_reduce(self.flat_g, group=self.group)
         ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)
         ops.sgd_momentum(self.flat_p, self.flat_g, self.flat_v, self.lr, self.momentum, self.norm_sq, self.clip,
-                         1.0 / self.world)
+                         1.0 / self.world, out_hi=self.flat_hi if _MIRROR else None, out_lo=self.flat_lo if _MIRROR else None)
         self.model.__dict__.pop("_blm_plans", None)
 
     def step(self, tokens_tb, targets_tb, kl_scale, *, eps=None, seed=None, hidden=None):
@@ -593,6 +623,7 @@ class FineTuner:
         graph itself only ever sees injected noise.  The all-reduce stays outside, between the graphs."""
         m, dev = self.model, self.device
         d = m.ninp
+        self._check_mirrors()
         self._cap = {"T": T, "B": B, "kl_scale": float(kl_scale),
                      "x": torch.zeros(T, B, dtype=torch.int64, device=dev),
                      "y": torch.zeros(T, B, dtype=torch.int64, device=dev), "eps": {}, "fill": []}
@@ -630,7 +661,8 @@ class FineTuner:
         with torch.cuda.graph(cap["g2"]):
             ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)
             ops.sgd_momentum(self.flat_p, self.flat_g, self.flat_v, self.lr, self.momentum, self.norm_sq, self.clip,
-                             1.0 / self.world)
+                             1.0 / self.world, out_hi=self.flat_hi if _MIRROR else None,
+                             out_lo=self.flat_lo if _MIRROR else None)
         return self
 
     def _refill_noise(self, seed: int):
@@ -641,6 +673,7 @@ class FineTuner:
         """One step through the captured graphs; (loss, ce, kl) are 0-dim device tensors valid until the
         next replay."""
         cap = self._cap
+        self._check_mirrors()          # outside the graphs: a parameter written from outside re-makes the bf16 mirrors
         cap["x"].copy_(tokens_tb, non_blocking=True)
         cap["y"].copy_(targets_tb.view(cap["T"], cap["B"]), non_blocking=True)
         self._refill_noise(seed)

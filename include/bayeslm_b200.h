@@ -456,6 +456,11 @@ int blm_reduce(const float* x, int64_t n, int32_t squares, float scale, int32_t 
  *   v = momentum v + c grad_scale g;  p -= lr v.                                               */
 int blm_sgd_momentum(float* p, const float* g, float* v, int64_t n, float lr, float momentum,
                      const float* norm_sq, float max_norm, float grad_scale, blm_stream stream);
+/* The same update that also writes the bf16 (hi[, lo]) operand copies of the updated parameters (out_lo may be
+ * null): the next step's GEMMs read them directly instead of re-splitting every weight.          */
+int blm_sgd_momentum_split(float* p, const float* g, float* v, int64_t n, float lr, float momentum,
+                           const float* norm_sq, float max_norm, float grad_scale, blm_bf16* out_hi,
+                           blm_bf16* out_lo, blm_stream stream);
 
 #ifdef __cplusplus
 }
