@@ -114,7 +114,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
                 "chunked accumulation keeps a 128 x 128 tile in the registers of 8 epilogue warps");
   constexpr int kColGroups = EW / 4;                 // column groups of the tile, one per 4 warps
   constexpr int kChunks = BN / 32 / kColGroups;      // 32-column chunks per epilogue warp
-  static_assert(kChunks >= 2 && (kChunks % 2) == 0, "the chunk loop is unrolled by two");
+  static_assert(kChunks >= 2 && (kChunks % 2) == 0, "the chunk loop is unrolled by two");  // (EW = 16: 2 chunks)
   constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                             : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
@@ -289,8 +289,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     const int etid = threadIdx.x - kEpiWarp0 * 32;
     const int row_in_tile = lane_grp * 32 + lane;
     const int c0 = col_grp * kChunks;  // first chunk of this warp inside the tile
-    static_assert(!STG || (ARES == 0 && EW == 8 && EPI == EPI_STORE), "store staging: 8 warps x 4 KB");
-    float4* stg = STG ? reinterpret_cast<float4*>(smem + L::kStgOffset + (warp - kEpiWarp0) * 4096)
+    static_assert(!STG || (ARES == 0 && EPI == EPI_STORE && (EW == 8 || STG == 2)),
+                  "store staging: 8 warps x 4 KB, or 16 warps x 2 KB (TMA store only)");
+    float4* stg = STG ? reinterpret_cast<float4*>(smem + L::kStgOffset + (warp - kEpiWarp0) * (EW == 16 ? 2048 : 4096))
                       : nullptr;  // store-transpose / TMA-store staging of this warp
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -375,6 +376,42 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                                static_cast<uint32_t>(acc * BN + c0 * 32);
+        if constexpr (EW == 16 && STG == 2) {
+          // Sixteen epilogue warps (four per scheduler): the packed-fp16 activations are issue / latency bound on
+          // eight (273 us with GELU vs 246 us without an epilogue), so thread-level parallelism replaces the
+          // two-chunk register pipeline: one 32-column chunk in registers (96-register budget at 640 threads),
+          // 2 KB of staging per warp, [32 x 32] bf16 TMA stores (64B swizzle).
+          float v[32];
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c) {
+            __syncwarp();
+            tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+            tmem_ld_wait();
+            if (c + 1 == kChunks) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            const int col0 = n * BN + (c0 + c) * 32;
+            if (col0 < p.N && warp_rows_ok) {
+              store_chunk<ACT, STG>(p, v, m, row_ok, lane, col0, sb + (c0 + c) * 32, stg);
+              if (lane == 0) bulk_wait_group_read0();
+              __syncwarp();
+              stage_chunk_bf16_sw64(v, reinterpret_cast<uint8_t*>(stg), lane);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&p.tmC, stg, col0, m - lane);
+                bulk_commit_group();
+              }
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+          continue;
+        }
         // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
         float va[32], vb[32];
         __syncwarp();
@@ -572,6 +609,23 @@ static int set_smem_attr_tma() {
   return BLM_OK;
 }
 
+// 16 epilogue warps + [32 x 32] TMA stores: the packed-fp16 activation epilogues (p.tmC: 32 x 32 box, 64B swizzle)
+template <int ACT>
+static int set_smem_attr_tma16() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<256, kStages256, EPI_STORE, ACT, 0, 16, 0, 2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256, kStages256, 0>::kDynBytes));
+  return BLM_OK;
+}
+
+template <int ACT>
+static int launch_tma16(const GemmParams& p, cudaStream_t st) {
+  const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
+  gemm_kernel<256, kStages256, EPI_STORE, ACT, 0, 16, 0, 2>
+      <<<grid, (4 + 16) * 32, SmemLayout<256, kStages256, 0>::kDynBytes, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 template <int BN, int STAGES, int ACT>
 static int launch_tma(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
@@ -583,6 +637,8 @@ static int launch_tma(const GemmParams& p, cudaStream_t st) {
 
 int gemm_init() {
   int rc;
+  if ((rc = set_smem_attr_tma16<BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma16<BLM_ACT_GPMIX_FAST>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
@@ -798,6 +854,15 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   if (tma_ok &&
       (d->act == BLM_ACT_NONE || d->act == BLM_ACT_GELU || d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_GPMIX ||
        d->act == BLM_ACT_GPMIX_FAST)) {
+    static const bool ew16 = [] {
+      const char* e = getenv("BLM_EPI16");   // A/B switch: 0 keeps the packed-fp16 epilogues on 8 warps
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (ew16 && BN == 256 && (d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_GPMIX_FAST)) {
+      rc = encode_tmap_bf16_box32(&p.tmC, d->out_hi, d->M, d->N, d->ldc);
+      if (rc != BLM_OK) return rc;
+      return d->act == BLM_ACT_GELU_FAST ? launch_tma16<BLM_ACT_GELU_FAST>(p, st) : launch_tma16<BLM_ACT_GPMIX_FAST>(p, st);
+    }
     rc = encode_tmap_bf16(&p.tmC, d->out_hi, d->M, d->N, d->ldc, 32);
     if (rc != BLM_OK) return rc;
     if (BN == 256) {

@@ -496,4 +496,18 @@ __device__ __forceinline__ void stage_chunk_bf16(const float (&v)[32], uint8_t* 
   }
 }
 
+
+// 16-epilogue-warp variant: one 32-column chunk -> this lane's 64-byte row of the warp's [32 rows x 32 columns]
+// bf16 staging tile in the 64B-swizzle layout (16-byte slot j of row r sits at slot j ^ ((r >> 1) & 3)).
+__device__ __forceinline__ void stage_chunk_bf16_sw64(const float (&v)[32], uint8_t* stg, int lane) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = pack_bf16x2(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+    const int slot = q ^ ((lane >> 1) & 3);
+    *reinterpret_cast<uint4*>(stg + lane * 64 + slot * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+  }
+}
+
 }  // namespace blm

@@ -40,6 +40,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                      int box_rows);
 
+int encode_tmap_bf16_box32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld);
 int encode_tmap_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 // generate-once sampled weights inside a blm_gemm launch (blm_gemm.cu: generate_weights)

@@ -90,6 +90,27 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t co
   return BLM_OK;
 }
 
+// bf16 row-major [rows, cols] output tensor, [32 rows x 32 cols] box = 64-byte inner extent with 64-byte swizzle:
+// the 2 KB per-warp staging tiles of the 16-epilogue-warp GEMM variant.
+int encode_tmap_bf16_box32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  int rc = load_encode();
+  if (rc != BLM_OK) return rc;
+  BLM_REQUIRE(aligned16(base) && (ld % 8) == 0 && ld >= cols && rows > 0 && cols > 0, BLM_ERR_ALIGN,
+              "bad bf16 tensor for a 32 x 32 box map (ld=%lld cols=%lld)", (long long)ld, (long long)cols);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2u};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (32 x 32 bf16 box) failed with CUresult %d", (int)r);
+    return BLM_ERR_CUDA;
+  }
+  return BLM_OK;
+}
+
 int gemm_init();  // blm_gemm.cu: raise dynamic shared-memory limits
 int lstm_init();  // blm_lstm.cu
 int gemm_sampled_init();  // blm_gemm_sampled.cu
