@@ -696,7 +696,7 @@ static int launch(const GemmParams& p, cudaStream_t st) {
   return BLM_OK;
 }
 
-int gemm2_store(GemmParams p, int act, cudaStream_t st, bool tma_store);   // blm_gemm2.cu: CTA-pair (cta_group::2) kernels
+int gemm2_store(GemmParams p, int act, cudaStream_t st, int tma_store);   // blm_gemm2.cu: CTA-pair (cta_group::2) kernels
 int gemm2_nll(GemmParams p, int groups, cudaStream_t st);
 
 // CTA-pair path switch: BLM_GEMM2=0 disables, =1 enables (default set below after measurement)
@@ -832,11 +832,20 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
       return e ? atoi(e) != 0 : true;
     }();
     const bool ts = tma2 && d->out_hi && !d->out_lo && !d->resid;
+    static const bool pair16 = [] {
+      const char* e = getenv("BLM_EPI16");
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (ts && pair16 && d->act == BLM_ACT_GELU_FAST) {
+      rc = encode_tmap_bf16_box32(&p2.tmC, d->out_hi, d->M, d->N, d->ldc);
+      if (rc != BLM_OK) return rc;
+      return gemm2_store(p2, d->act, st, 2);
+    }
     if (ts) {
       rc = encode_tmap_bf16(&p2.tmC, d->out_hi, d->M, d->N, d->ldc, 32);
       if (rc != BLM_OK) return rc;
     }
-    return gemm2_store(p2, d->act, st, ts);
+    return gemm2_store(p2, d->act, st, ts ? 1 : 0);
   }
   // bf16-hi-only output of a forward GEMM: the tile leaves through TMA stores (row-per-thread 16-byte stores to
   // rows 8 KB apart back up the LSU / L2 request queues; BLM_TMA_STORE=0 is the A/B switch)

@@ -89,11 +89,12 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
 
 // STG == 2: bf16-hi-only output leaves through TMA stores (as in the 1-CTA kernel, blm_gemm.cu): row-per-thread
 // 16-byte stores cost 32 LSU wavefronts per instruction and were the bound of the K = 512 shapes.
-template <int STAGES, int EPI, int ACT, int ARES, int STG = 0>
-__global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_constant__ GemmParams p) {
+template <int STAGES, int EPI, int ACT, int ARES, int STG = 0, int EW = k2EW>
+__global__ void __launch_bounds__((4 + EW) * 32, 1) gemm2_kernel(const __grid_constant__ GemmParams p) {
   using L = Smem2<STAGES, ARES>;
   static_assert(!STG || (EPI == EPI_STORE && ARES == 0), "TMA-store staging belongs to the storing kernels");
-  constexpr int kChunks = k2BN / 32 / (k2EW / 4);  // 4 chunks of 32 columns per epilogue warp
+  static_assert(EW == 8 || (EW == 16 && STG == 2), "16 epilogue warps: TMA-store kernels only (2 KB staging per warp)");
+  constexpr int kChunks = k2BN / 32 / (EW / 4);  // 4 (EW = 8) or 2 (EW = 16) chunks of 32 columns per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) {
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * k2EW);  // epilogue warps of both CTAs
+      mbar_init(&tempty_bar[s], 2 * EW);  // epilogue warps of both CTAs
     }
     mbar_init(afull_bar, 1);
     mbar_init(aempty_bar, 1);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     const int row_in_tile = lane_grp * 32 + lane;
     const int c0 = col_grp * kChunks;
     const uint32_t tempty_leader[2] = {mapa_shared(smem_u32(&tempty_bar[0]), 0), mapa_shared(smem_u32(&tempty_bar[1]), 0)};
-    uint8_t* stg = STG ? smem + L::kStgOffset + (warp - kEpiWarp0) * 4096 : nullptr;
+    uint8_t* stg = STG ? smem + L::kStgOffset + (warp - kEpiWarp0) * (EW == 16 ? 2048 : 4096) : nullptr;
     (void)stg;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
       }
       for (int n = n0; n < n1; ++n) {
         float breg[1];
-        if (p.bias) {
+        if (p.bias && etid < k2BN) {
           const int col = n * k2BN + etid;
           breg[0] = col < p.N ? __ldg(p.bias + col) : 0.0f;
         }
@@ -266,11 +267,44 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
         tcgen05_fence_after();
         float* sb = sbias + acc * k2BN;
         if (p.bias) {
-          sb[etid] = breg[0];
-          epi_bar_sync(k2EW * 32);
+          if (etid < k2BN) sb[etid] = breg[0];
+          epi_bar_sync(EW * 32);
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                                static_cast<uint32_t>(acc * k2BN + c0 * 32);
+        if constexpr (EW == 16) {
+          // sixteen epilogue warps, one chunk in registers, [32 x 32] TMA stores (see blm_gemm.cu)
+          float v[32];
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c) {
+            __syncwarp();
+            tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+            tmem_ld_wait();
+            if (c + 1 == kChunks) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(tempty_leader[acc]);
+            }
+            const int col0 = n * k2BN + (c0 + c) * 32;
+            if (col0 < p.N && warp_rows_ok) {
+              store_chunk<ACT, STG>(p, v, m, row_ok, lane, col0, sb + (c0 + c) * 32);
+              if (lane == 0) bulk_wait_group_read0();
+              __syncwarp();
+              stage_chunk_bf16_sw64(v, stg, lane);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&p.tmC, stg, col0, m - lane);
+                bulk_commit_group();
+              }
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+          continue;
+        }
         float va[32], vb[32];
         __syncwarp();
         tmem_ld_32x32(taddr, va);
@@ -335,7 +369,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
       }
       if constexpr (EPI == EPI_NLL) {
         if (row_ok) {
-          const long long o = static_cast<long long>(grp * (k2EW / 4) + col_grp) * p.M + m;
+          const long long o = static_cast<long long>(grp * (EW / 4) + col_grp) * p.M + m;
           p.part_max[o] = st.run_max;
           p.part_sum[o] = st.run_sum;
           p.part_tgt[o] = st.tgt_logit;
@@ -359,9 +393,9 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
 constexpr int k2Stages = 6;       // 6 x 32 KB (A tile + B half)
 constexpr int k2NllStages = 6;    // 128 KB resident A + 6 x 16 KB of B halves
 
-template <int STAGES, int EPI, int ACT, int ARES, int STG = 0>
+template <int STAGES, int EPI, int ACT, int ARES, int STG = 0, int EW = k2EW>
 static int set_attr2() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<STAGES, EPI, ACT, ARES, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<STAGES, EPI, ACT, ARES, STG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Smem2<STAGES, ARES>::kDynBytes));
   return BLM_OK;
 }
@@ -374,18 +408,19 @@ int gemm2_init() {
   if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_NONE, 0, 2>()) != BLM_OK) return rc;
   if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU, 0, 2>()) != BLM_OK) return rc;
   if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU_FAST, 0, 2>()) != BLM_OK) return rc;
+  if ((rc = set_attr2<k2Stages, EPI_STORE, BLM_ACT_GELU_FAST, 0, 2, 16>()) != BLM_OK) return rc;
   if ((rc = set_attr2<k2NllStages, EPI_NLL, BLM_ACT_NONE, k2Ares>()) != BLM_OK) return rc;
   return BLM_OK;
 }
 
-template <int STAGES, int EPI, int ACT, int ARES, int STG = 0>
+template <int STAGES, int EPI, int ACT, int ARES, int STG = 0, int EW = k2EW>
 static int launch2(const GemmParams& p, cudaStream_t st) {
   int pairs = num_sms() / 2;
   if (pairs > p.num_works) pairs = p.num_works;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-  cfg.blockDim = dim3(k2Threads);
+  cfg.blockDim = dim3((4 + EW) * 32);
   cfg.dynamicSmemBytes = Smem2<STAGES, ARES>::kDynBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -395,18 +430,21 @@ static int launch2(const GemmParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<STAGES, EPI, ACT, ARES, STG>, p));
+  BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<STAGES, EPI, ACT, ARES, STG, EW>, p));
   return BLM_OK;
 }
 
 // Pair-tile launch of a storing GEMM (called by blm_gemm when the shape qualifies): p is filled for 128-row
 // tiles by the caller; only the tile bookkeeping changes here.
-int gemm2_store(GemmParams p, int act, cudaStream_t st, bool tma_store) {
+// tma_store: 0 = direct stores, 1 = [32 x 64] TMA stores on 8 epilogue warps (p.tmC box 64 x 32),
+//            2 = GELU_FAST on 16 epilogue warps with [32 x 32] TMA stores (p.tmC box 32 x 32, 64B swizzle)
+int gemm2_store(GemmParams p, int act, cudaStream_t st, int tma_store) {
   p.m_tiles = (p.M + 2 * kBM - 1) / (2 * kBM);
   p.n_tiles = (p.N + k2BN - 1) / k2BN;
   p.n_groups = p.n_tiles;
   p.tiles_per_group = 1;
   p.num_works = p.m_tiles * p.n_tiles;
+  if (tma_store == 2) return launch2<k2Stages, EPI_STORE, BLM_ACT_GELU_FAST, 0, 2, 16>(p, st);
   if (tma_store) {   // p.tmC: bf16 [M, N], box 32 rows x 64 columns (encoded by the caller)
     switch (act) {
       case BLM_ACT_NONE: return launch2<k2Stages, EPI_STORE, BLM_ACT_NONE, 0, 2>(p, st);
