@@ -111,6 +111,7 @@ SIGNATURES = {
     "blm_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),
     "blm_layernorm_bwd": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "blm_mha_causal_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p]),
+    "blm_mha_causal_bwd_tc": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _i32, _p, _i64, _p]),
     "blm_gpmix_dcoef": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p]),
     "blm_vnoise_fwd": (C.c_int, [_p, _p, _p, _i32, _u64, _u64, _f, _p, _i64, _i32, _i32, _p, _p]),
     "blm_vnoise_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _u64, _u64, _f, _i64, _i32, _i32, _f, _p, _p, _p, _p, _p]),

@@ -483,6 +483,346 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
   }
 }
 
+// ------------------------------------------------------------------ tensor-core attention backward
+// dqkv = d(causal MHA)/d(q, k, v) for one (sequence, head) per CTA, T <= 128, head_dim 64, on mma.sync m16n8k16
+// bf16 (hi[, lo] parts as in the forward kernel; PRECISE = three products per term).  q, k, v (q already scaled)
+// and dO arrive as fp32 and are split into swizzled bf16 tiles while they are staged.
+// Two phases, nothing of size T x T is stored and no fragment is transposed:
+//   A (warp w = query rows [32w, 32w+32)): pass 1 over the key blocks j <= i rebuilds S = Q K^T and dP = dO V^T
+//     and folds them into the row statistics m_i, l_i, D_i = sum_j P_ij dP_ij (online, log2 domain); pass 2
+//     rebuilds both again, forms dS = P (dP - D) in registers and accumulates dQ += dS K with dS re-packed from
+//     the accumulator layout into A fragments (the forward kernel's P V trick).
+//   B (warp w = key rows [32w, 32w+32)): for every 16-row query block i >= j, S^T = K Q^T and dP^T = V dO^T come out
+//     with the KEY index as the accumulator row, so P^T and dS^T re-pack into A fragments of
+//     dV += P^T dO and dK += dS^T Q; the statistics of phase A are read from shared memory per column.
+// Recomputing the two small products three times costs ~0.3 GFLOP per launch; the fp32 SIMT kernel it replaces
+// read 5 MB of shared memory per CTA and took 155 us per layer (19 % of the fine-tune step).
+template <bool PRECISE>
+__global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
+    const float* __restrict__ qkv, long long ld, const float* __restrict__ dout, long long ldo,
+    const int* __restrict__ seq_offsets, int nhead, float q_scale, float* __restrict__ dqkv, long long ldd) {
+  constexpr int PARTS = PRECISE ? 2 : 1;
+  extern __shared__ __align__(128) uint8_t attn_sm[];
+  const uint32_t sm_base = smem_u32(attn_sm);
+  // [matrix q,k,v,dO][part hi,lo][128 rows][128 B], then the row statistics
+  auto tile = [&](int mat, int part) -> uint32_t { return sm_base + static_cast<uint32_t>((mat * PARTS + part) * 128 * 128); };
+  float* sM = reinterpret_cast<float*>(attn_sm + 4 * PARTS * 128 * 128);
+  float* sL = sM + 128;
+  float* sD = sL + 128;
+  auto addr = [&](uint32_t base, int row, int chunk) -> uint32_t {
+    return base + static_cast<uint32_t>(row * kMmaAttnRowBytes + ((chunk ^ (row & 7)) << 4));
+  };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.x / nhead, head = blockIdx.x - seq * nhead;
+  const int row0 = __ldg(seq_offsets + seq);
+  const int T = __ldg(seq_offsets + seq + 1) - row0;
+  if (T > 128) {
+    if (threadIdx.x == 0) printf("blm: sequence %d has %d tokens > 128\n", seq, T);
+    __trap();
+  }
+  const int d = nhead * kMmaAttnHd;
+  const int Tpad = (T + 31) & ~31;
+  // ---- stage q, k, v, dO: fp32 -> bf16 hi (lo), zero rows up to the next multiple of 32
+  for (int idx = threadIdx.x; idx < 4 * Tpad * 8; idx += 128) {
+    const int mat = idx / (Tpad * 8), rem = idx - mat * (Tpad * 8);
+    const int r = rem >> 3, ch = rem & 7;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (r < T) {
+      const float* src = mat < 3 ? qkv + static_cast<long long>(row0 + r) * ld + mat * d + head * kMmaAttnHd + ch * 8
+                                 : dout + static_cast<long long>(row0 + r) * ldo + head * kMmaAttnHd + ch * 8;
+      a = __ldg(reinterpret_cast<const float4*>(src));
+      b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    }
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = pack_bf16x2(x[2 * e], x[2 * e + 1]);
+      lo[e] = pack_bf16x2(x[2 * e] - __uint_as_float(hi[e] << 16), x[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
+    }
+    const uint32_t off = static_cast<uint32_t>(r * kMmaAttnRowBytes + ((ch ^ (r & 7)) << 4));
+    *reinterpret_cast<uint4*>(attn_sm + (mat * PARTS) * 128 * 128 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if constexpr (PRECISE)
+      *reinterpret_cast<uint4*>(attn_sm + (mat * PARTS + 1) * 128 * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  constexpr float kLog2e = 1.4426950408889634f;
+  // C[16 x 8] += A(rows ra.., mat ma) B(rows rb.., mat mb)^T over the 64 head dimensions, for 2 m tiles x 4 n tiles
+  auto rows_product = [&](float (&c)[2][4][4], int ma, int ra, int mb, int rb, int nmt, int nnt) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[mt][nt][e] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t fa[2][PARTS][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < nmt) {
+          const int row = ra + mt * 16 + (lane & 15);
+#pragma unroll
+          for (int part = 0; part < PARTS; ++part) ldsm_x4(addr(tile(ma, part), row, ks * 2 + (lane >> 4)), fa[mt][part]);
+        }
+      }
+#pragma unroll
+      for (int ntp = 0; ntp < 2; ++ntp) {
+        if (ntp * 2 < nnt) {
+          uint32_t fb[PARTS][4];
+          const int row = rb + ntp * 16 + (lane & 7) + ((lane >> 4) << 3);
+#pragma unroll
+          for (int part = 0; part < PARTS; ++part) ldsm_x4(addr(tile(mb, part), row, ks * 2 + ((lane >> 3) & 1)), fb[part]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt < nmt) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                mma_bf16(c[mt][ntp * 2 + u], fa[mt][0], fb[0][2 * u], fb[0][2 * u + 1]);
+                if constexpr (PRECISE) {
+                  mma_bf16(c[mt][ntp * 2 + u], fa[mt][0], fb[1][2 * u], fb[1][2 * u + 1]);
+                  mma_bf16(c[mt][ntp * 2 + u], fa[mt][1], fb[0][2 * u], fb[0][2 * u + 1]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  };
+  // acc[2][8][4] += X (accumulator-layout [2 m tiles][4 n tiles], contraction over its 32 columns) . rows rb.. of mat mb
+  auto acc_product = [&](float (&acc)[2][8][4], const float (&x)[2][4][4], int mb, int rb, int nmt, int nnt) {
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      if (kk * 2 < nnt) {
+        uint32_t ap[2][PARTS][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < nmt) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float x0 = x[mt][2 * kk + (q >> 1)][(q & 1) * 2], x1 = x[mt][2 * kk + (q >> 1)][(q & 1) * 2 + 1];
+              const uint32_t hi = pack_bf16x2(x0, x1);
+              ap[mt][0][q] = hi;
+              if constexpr (PRECISE)
+                ap[mt][1][q] = pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+            }
+          }
+        }
+#pragma unroll
+        for (int ctp = 0; ctp < 4; ++ctp) {
+          uint32_t bv[PARTS][4];
+          const int row = rb + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+          for (int part = 0; part < PARTS; ++part) ldsm_x4_trans(addr(tile(mb, part), row, ctp * 2 + (lane >> 4)), bv[part]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt < nmt) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                mma_bf16(acc[mt][ctp * 2 + u], ap[mt][0], bv[0][2 * u], bv[0][2 * u + 1]);
+                if constexpr (PRECISE) {
+                  mma_bf16(acc[mt][ctp * 2 + u], ap[mt][0], bv[1][2 * u], bv[1][2 * u + 1]);
+                  mma_bf16(acc[mt][ctp * 2 + u], ap[mt][1], bv[0][2 * u], bv[0][2 * u + 1]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  };
+
+  // ================================================================= phase A: query rows of this warp
+  if (warp * 32 < T) {
+    const int qt = warp;
+    const int i_hi = min(T, qt * 32 + 32) - 1;
+    const int nmt = (i_hi - qt * 32) / 16 + 1;
+    float mrow[2][2], lrow[2][2], drow[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mrow[mt][h] = -INFINITY;
+        lrow[mt][h] = 0.0f;
+        drow[mt][h] = 0.0f;
+      }
+    float s[2][4][4], dp[2][4][4];
+    // ---- pass 1: statistics
+    for (int kb = 0; kb <= qt; ++kb) {
+      const int jmax = min(i_hi, kb * 32 + 31);
+      const int nnt = (jmax - kb * 32) / 8 + 1;
+      rows_product(s, 0, qt * 32, 1, kb * 32, nmt, nnt);
+      rows_product(dp, 3, qt * 32, 2, kb * 32, nmt, nnt);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < nmt) {
+          float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = qt * 32 + mt * 16 + g + ((e >> 1) << 3);
+              const int j = kb * 32 + nt * 8 + 2 * t4 + (e & 1);
+              const float v = (j <= i && nt < nnt) ? s[mt][nt][e] * kLog2e : -INFINITY;
+              s[mt][nt][e] = v;
+              mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+            const float mnew = fmaxf(mrow[mt][h], mx[h]);
+            const float alpha = ex2f_(mrow[mt][h] - mnew);
+            mrow[mt][h] = mnew;
+            lrow[mt][h] *= alpha;
+            drow[mt][h] *= alpha;
+          }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float pv = ex2f_(s[mt][nt][e] - mrow[mt][e >> 1]);   // 0 where masked
+              lrow[mt][e >> 1] += pv;
+              drow[mt][e >> 1] = fmaf(pv, (nt < nnt) ? dp[mt][nt][e] : 0.0f, drow[mt][e >> 1]);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float l = lrow[mt][h], dd = drow[mt][h];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+        const float inv = (mt < nmt && l > 0.0f) ? 1.0f / l : 0.0f;
+        lrow[mt][h] = inv;
+        drow[mt][h] = dd * inv;
+        if (t4 == 0) {
+          const int i = qt * 32 + mt * 16 + g + 8 * h;
+          sM[i] = mrow[mt][h];
+          sL[i] = inv;
+          sD[i] = dd * inv;
+        }
+      }
+    // ---- pass 2: dS and dQ
+    float dq[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ct = 0; ct < 8; ++ct)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dq[mt][ct][e] = 0.0f;
+    for (int kb = 0; kb <= qt; ++kb) {
+      const int jmax = min(i_hi, kb * 32 + 31);
+      const int nnt = (jmax - kb * 32) / 8 + 1;
+      rows_product(s, 0, qt * 32, 1, kb * 32, nmt, nnt);
+      rows_product(dp, 3, qt * 32, 2, kb * 32, nmt, nnt);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = qt * 32 + mt * 16 + g + ((e >> 1) << 3);
+            const int j = kb * 32 + nt * 8 + 2 * t4 + (e & 1);
+            const bool ok = j <= i && nt < nnt && mt < nmt;
+            const float pv = ok ? ex2f_(fmaf(s[mt][nt][e], kLog2e, -mrow[mt][e >> 1])) * lrow[mt][e >> 1] : 0.0f;
+            s[mt][nt][e] = ok ? pv * (dp[mt][nt][e] - drow[mt][e >> 1]) : 0.0f;   // dS
+          }
+      acc_product(dq, s, 1, kb * 32, nmt, nnt);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt < nmt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = qt * 32 + mt * 16 + g + 8 * h;
+          if (i < T) {
+            float* o = dqkv + static_cast<long long>(row0 + i) * ldd + head * kMmaAttnHd + 2 * t4;
+#pragma unroll
+            for (int ct = 0; ct < 8; ++ct)
+              *reinterpret_cast<float2*>(o + ct * 8) = make_float2(dq[mt][ct][2 * h] * q_scale, dq[mt][ct][2 * h + 1] * q_scale);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();   // statistics of every query row are in shared memory
+
+  // ================================================================= phase B: key rows of this warp
+  if (warp * 32 < T) {
+    const int jt = warp;
+    const int j_hi = min(T, jt * 32 + 32) - 1;
+    const int nmt = (j_hi - jt * 32) / 16 + 1;
+    float dk[2][8][4], dv[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ct = 0; ct < 8; ++ct)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dk[mt][ct][e] = dv[mt][ct][e] = 0.0f;
+    float st[2][4][4], dpt[2][4][4];
+    const int nblk = (T + 31) / 32;
+    for (int ib = jt; ib < nblk; ++ib) {
+      const int imax = min(T - 1, ib * 32 + 31);
+      const int nnt = (imax - ib * 32) / 8 + 1;   // n8 tiles of query columns in use
+      rows_product(st, 1, jt * 32, 0, ib * 32, nmt, nnt);    // S^T = K Q^T
+      rows_product(dpt, 2, jt * 32, 3, ib * 32, nmt, nnt);   // dP^T = V dO^T
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float cm[2], cl[2], cd[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = ib * 32 + nt * 8 + 2 * t4 + u;   // rows beyond T hold finite leftovers or zeros; masked below
+          cm[u] = sM[i & 127];
+          cl[u] = sL[i & 127];
+          cd[u] = sD[i & 127];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = jt * 32 + mt * 16 + g + ((e >> 1) << 3);
+            const int i = ib * 32 + nt * 8 + 2 * t4 + (e & 1);
+            const bool ok = j <= i && i < T && nt < nnt && mt < nmt;
+            const float pv = ok ? ex2f_(fmaf(st[mt][nt][e], kLog2e, -cm[e & 1])) * cl[e & 1] : 0.0f;
+            st[mt][nt][e] = pv;                                           // P^T
+            dpt[mt][nt][e] = ok ? pv * (dpt[mt][nt][e] - cd[e & 1]) : 0.0f;   // dS^T
+          }
+      }
+      acc_product(dv, st, 3, ib * 32, nmt, nnt);    // dV += P^T dO
+      acc_product(dk, dpt, 0, ib * 32, nmt, nnt);   // dK += dS^T Q
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt < nmt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = jt * 32 + mt * 16 + g + 8 * h;
+          if (j < T) {
+            float* o = dqkv + static_cast<long long>(row0 + j) * ldd + d + head * kMmaAttnHd + 2 * t4;
+#pragma unroll
+            for (int ct = 0; ct < 8; ++ct) {
+              *reinterpret_cast<float2*>(o + ct * 8) = make_float2(dk[mt][ct][2 * h], dk[mt][ct][2 * h + 1]);
+              *reinterpret_cast<float2*>(o + d + ct * 8) = make_float2(dv[mt][ct][2 * h], dv[mt][ct][2 * h + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool PRECISE>
+static constexpr int mma_attn_bwd_smem_bytes() { return 4 * (PRECISE ? 2 : 1) * 128 * 128 + 3 * 128 * 4; }
+
 template <bool PRECISE>
 static constexpr int mma_attn_smem_bytes() { return 3 * (PRECISE ? 2 : 1) * 128 * 128; }
 
@@ -508,6 +848,10 @@ int attention_init() {
                                       mma_attn_smem_bytes<true>()));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       mma_attn_smem_bytes<true>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_bwd_smem_bytes<false>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_bwd_smem_bytes<true>()));
   return BLM_OK;
 }
 
@@ -592,6 +936,32 @@ extern "C" int blm_mha_causal_bf16(const blm_bf16* qkv_hi, const blm_bf16* qkv_l
       mha_causal_mma_kernel<false, 128><<<blocks, 128, mma_attn_smem_bytes<false>(), st>>>(qh, ql, ld, seq_offsets, pairs,
                                                                                        nhead, out_f32, oh, ol, ldo);
   }
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+extern "C" int blm_mha_causal_bwd_tc(const float* qkv, int64_t ld, const float* dout, int64_t ldo, const int32_t* seq_offsets,
+                                     int64_t nseq, int32_t nhead, int32_t head_dim, int32_t max_len, float q_scale,
+                                     int32_t precise, float* dqkv, int64_t ldd, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(qkv && dout && seq_offsets && dqkv && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention-backward arguments");
+  BLM_REQUIRE(head_dim == kMmaAttnHd, BLM_ERR_SHAPE, "tensor-core attention backward needs head_dim 64, got %d", head_dim);
+  BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
+  BLM_REQUIRE((ld % 4) == 0 && (ldo % 4) == 0 && (ldd % 4) == 0 && aligned16(qkv) && aligned16(dout) && aligned16(dqkv),
+              BLM_ERR_ALIGN, "attention-backward operands must be 16-byte aligned with leading dimensions %% 4 == 0");
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = attention_init();
+    if (rc != BLM_OK) return rc;
+    attr_set = true;
+  }
+  const unsigned grid = static_cast<unsigned>(nseq * nhead);
+  if (precise)
+    mha_causal_bwd_mma_kernel<true><<<grid, 128, mma_attn_bwd_smem_bytes<true>(), as_stream(stream)>>>(
+        qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd);
+  else
+    mha_causal_bwd_mma_kernel<false><<<grid, 128, mma_attn_bwd_smem_bytes<false>(), as_stream(stream)>>>(
+        qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

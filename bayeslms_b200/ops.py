@@ -10,6 +10,7 @@ Precision modes (``prec``):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -569,10 +570,18 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: f
 
 
 def mha_causal_bwd(qkv: torch.Tensor, dout: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len: int,
-                   q_scale: float) -> torch.Tensor:
+                   q_scale: float, prec: Optional[str] = None) -> torch.Tensor:
+    """Gradient of the causal attention w.r.t. the (q-scaled) qkv projection.  ``prec`` = "bf16" / "bf16x3" selects
+    the tensor-core kernel (head_dim 64); None (or BLM_ATTN_BWD_SIMT=1) the fp32 SIMT kernel."""
     M, d3 = qkv.shape
     d = d3 // 3
     dqkv = torch.empty_like(qkv)
+    if prec is not None and d // nhead == 64 and max_len <= 128 and os.environ.get("BLM_ATTN_BWD_SIMT") is None:
+        with _op("mha_causal_bwd", 1):
+            check(lib().blm_mha_causal_bwd_tc(_ptr(qkv), qkv.stride(0), _ptr(dout), dout.stride(0), _ptr(seq_offsets),
+                                              seq_offsets.numel() - 1, nhead, 64, max_len, q_scale, int(prec == "bf16x3"),
+                                              _ptr(dqkv), dqkv.stride(0), _stream()), "blm_mha_causal_bwd_tc")
+        return dqkv
     with _op("mha_causal_bwd", 1):
         check(lib().blm_mha_causal_bwd(_ptr(qkv), qkv.stride(0), _ptr(dout), dout.stride(0), _ptr(seq_offsets),
                                        seq_offsets.numel() - 1, nhead, d // nhead, max_len, q_scale, _ptr(dqkv),

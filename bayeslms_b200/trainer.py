@@ -388,7 +388,7 @@ class FineTuner:
             else:
                 self._wgrad(dy1t, attt, g[pre + "self_attn.o_net.weight"], "o_net")
                 ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
-            dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q)
+            dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q, prec=prec)
             dx = self._f32(M, d)
             dqkvs = ops.split(dqkv, prec)
             _gemm(dqkvs, S["wqkv_t"], prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")

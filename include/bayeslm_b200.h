@@ -399,6 +399,13 @@ int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
 int blm_mha_causal_bwd(const float* qkv, int64_t ld, const float* dout, int64_t ldo,
                        const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
                        int32_t max_len, float q_scale, float* dqkv, int64_t ldd, blm_stream stream);
+/* The same gradient on tensor cores (mma.sync m16n8k16 bf16; precise = 1: hi/lo parts, three products per term):
+ * S, dP are rebuilt per block in registers, dS / P are re-packed from accumulator to A fragments, nothing T x T
+ * is stored.  head_dim 64, max_len <= 128.                                                                    */
+int blm_mha_causal_bwd_tc(const float* qkv, int64_t ld, const float* dout, int64_t ldo,
+                          const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                          int32_t max_len, float q_scale, int32_t precise, float* dqkv, int64_t ldd,
+                          blm_stream stream);
 
 /* GP mixture (model.py:1893-1899): dcoef[i, n] (+)= sum_m dh[m, n] act_i(z[m, n]).              */
 int blm_gpmix_dcoef(const float* z, const float* dh, int64_t ld, int64_t M, int64_t N,
