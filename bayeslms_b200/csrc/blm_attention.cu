@@ -497,11 +497,16 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
 //     dV += P^T dO and dK += dS^T Q; the statistics of phase A are read from shared memory per column.
 // Recomputing the two small products three times costs ~0.3 GFLOP per launch; the fp32 SIMT kernel it replaces
 // read 5 MB of shared memory per CTA and took 155 us per layer (19 % of the fine-tune step).
-template <bool PRECISE>
-__global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
+// MT = m16 tiles per warp: 1 -> eight warps of 16 rows (bf16 mode: <= 128 registers, two CTAs per SM; the precise
+// mode's 129 KB of tiles allow one CTA per SM anyway, so it keeps the full register file): the launch is one wave of
+// nseq * nhead latency-bound CTAs, so warps per CTA are what shortens it.  2 -> four warps of 32 rows.
+template <bool PRECISE, int MT>
+__global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 2 : 1) mha_causal_bwd_mma_kernel(
     const float* __restrict__ qkv, long long ld, const float* __restrict__ dout, long long ldo,
     const int* __restrict__ seq_offsets, int nhead, float q_scale, float* __restrict__ dqkv, long long ldd) {
   constexpr int PARTS = PRECISE ? 2 : 1;
+  constexpr int RB = 16 * MT;               // rows per warp
+  constexpr int NT = 128 / RB * 32;         // threads
   extern __shared__ __align__(128) uint8_t attn_sm[];
   const uint32_t sm_base = smem_u32(attn_sm);
   // [matrix q,k,v,dO][part hi,lo][128 rows][128 B], then the row statistics
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
   const int d = nhead * kMmaAttnHd;
   const int Tpad = (T + 31) & ~31;
   // ---- stage q, k, v, dO: fp32 -> bf16 hi (lo), zero rows up to the next multiple of 32
-  for (int idx = threadIdx.x; idx < 4 * Tpad * 8; idx += 128) {
+  for (int idx = threadIdx.x; idx < 4 * Tpad * 8; idx += NT) {
     const int mat = idx / (Tpad * 8), rem = idx - mat * (Tpad * 8);
     const int r = rem >> 3, ch = rem & 7;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -551,18 +556,18 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
   const int g = lane >> 2, t4 = lane & 3;
   constexpr float kLog2e = 1.4426950408889634f;
   // C[16 x 8] += A(rows ra.., mat ma) B(rows rb.., mat mb)^T over the 64 head dimensions, for 2 m tiles x 4 n tiles
-  auto rows_product = [&](float (&c)[2][4][4], int ma, int ra, int mb, int rb, int nmt, int nnt) {
+  auto rows_product = [&](float (&c)[MT][4][4], int ma, int ra, int mb, int rb, int nmt, int nnt) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) c[mt][nt][e] = 0.0f;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      uint32_t fa[2][PARTS][4];
+      uint32_t fa[MT][PARTS][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         if (mt < nmt) {
           const int row = ra + mt * 16 + (lane & 15);
 #pragma unroll
@@ -577,7 +582,7 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
 #pragma unroll
           for (int part = 0; part < PARTS; ++part) ldsm_x4(addr(tile(mb, part), row, ks * 2 + ((lane >> 3) & 1)), fb[part]);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
+          for (int mt = 0; mt < MT; ++mt) {
             if (mt < nmt) {
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
@@ -594,13 +599,13 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
     }
   };
   // acc[2][8][4] += X (accumulator-layout [2 m tiles][4 n tiles], contraction over its 32 columns) . rows rb.. of mat mb
-  auto acc_product = [&](float (&acc)[2][8][4], const float (&x)[2][4][4], int mb, int rb, int nmt, int nnt) {
+  auto acc_product = [&](float (&acc)[MT][8][4], const float (&x)[MT][4][4], int mb, int rb, int nmt, int nnt) {
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       if (kk * 2 < nnt) {
-        uint32_t ap[2][PARTS][4];
+        uint32_t ap[MT][PARTS][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
           if (mt < nmt) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -619,7 +624,7 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
 #pragma unroll
           for (int part = 0; part < PARTS; ++part) ldsm_x4_trans(addr(tile(mb, part), row, ctp * 2 + (lane >> 4)), bv[part]);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
+          for (int mt = 0; mt < MT; ++mt) {
             if (mt < nmt) {
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
@@ -637,35 +642,36 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
   };
 
   // ================================================================= phase A: query rows of this warp
-  if (warp * 32 < T) {
-    const int qt = warp;
-    const int i_hi = min(T, qt * 32 + 32) - 1;
-    const int nmt = (i_hi - qt * 32) / 16 + 1;
-    float mrow[2][2], lrow[2][2], drow[2][2];
+  const bool active = warp * RB < T;
+  const int qt = warp;
+  const int i_hi = min(T, qt * RB + RB) - 1;
+  const int nmt = active ? (i_hi - qt * RB) / 16 + 1 : 0;
+  float mrow[MT][2], lrow[MT][2], drow[MT][2];
+  float s[MT][4][4], dp[MT][4][4];
+  if (active) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         mrow[mt][h] = -INFINITY;
         lrow[mt][h] = 0.0f;
         drow[mt][h] = 0.0f;
       }
-    float s[2][4][4], dp[2][4][4];
     // ---- pass 1: statistics
-    for (int kb = 0; kb <= qt; ++kb) {
+    for (int kb = 0; kb * 32 <= i_hi; ++kb) {
       const int jmax = min(i_hi, kb * 32 + 31);
       const int nnt = (jmax - kb * 32) / 8 + 1;
-      rows_product(s, 0, qt * 32, 1, kb * 32, nmt, nnt);
-      rows_product(dp, 3, qt * 32, 2, kb * 32, nmt, nnt);
+      rows_product(s, 0, qt * RB, 1, kb * 32, nmt, nnt);
+      rows_product(dp, 3, qt * RB, 2, kb * 32, nmt, nnt);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         if (mt < nmt) {
           float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int i = qt * 32 + mt * 16 + g + ((e >> 1) << 3);
+              const int i = qt * RB + mt * 16 + g + ((e >> 1) << 3);
               const int j = kb * 32 + nt * 8 + 2 * t4 + (e & 1);
               const float v = (j <= i && nt < nnt) ? s[mt][nt][e] * kLog2e : -INFINITY;
               s[mt][nt][e] = v;
@@ -693,7 +699,7 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
       }
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float l = lrow[mt][h], dd = drow[mt][h];
@@ -705,32 +711,35 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
         lrow[mt][h] = inv;
         drow[mt][h] = dd * inv;
         if (t4 == 0) {
-          const int i = qt * 32 + mt * 16 + g + 8 * h;
+          const int i = qt * RB + mt * 16 + g + 8 * h;
           sM[i] = mrow[mt][h];
           sL[i] = inv;
           sD[i] = dd * inv;
         }
       }
+  }
+  __syncthreads();   // the statistics of every query row are in shared memory: pass 2 and phase B need no further sync
+  if (active) {
     // ---- pass 2: dS and dQ
-    float dq[2][8][4];
+    float dq[MT][8][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int ct = 0; ct < 8; ++ct)
 #pragma unroll
         for (int e = 0; e < 4; ++e) dq[mt][ct][e] = 0.0f;
-    for (int kb = 0; kb <= qt; ++kb) {
+    for (int kb = 0; kb * 32 <= i_hi; ++kb) {
       const int jmax = min(i_hi, kb * 32 + 31);
       const int nnt = (jmax - kb * 32) / 8 + 1;
-      rows_product(s, 0, qt * 32, 1, kb * 32, nmt, nnt);
-      rows_product(dp, 3, qt * 32, 2, kb * 32, nmt, nnt);
+      rows_product(s, 0, qt * RB, 1, kb * 32, nmt, nnt);
+      rows_product(dp, 3, qt * RB, 2, kb * 32, nmt, nnt);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int i = qt * 32 + mt * 16 + g + ((e >> 1) << 3);
+            const int i = qt * RB + mt * 16 + g + ((e >> 1) << 3);
             const int j = kb * 32 + nt * 8 + 2 * t4 + (e & 1);
             const bool ok = j <= i && nt < nnt && mt < nmt;
             const float pv = ok ? ex2f_(fmaf(s[mt][nt][e], kLog2e, -mrow[mt][e >> 1])) * lrow[mt][e >> 1] : 0.0f;
@@ -739,11 +748,11 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
       acc_product(dq, s, 1, kb * 32, nmt, nnt);
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       if (mt < nmt) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int i = qt * 32 + mt * 16 + g + 8 * h;
+          const int i = qt * RB + mt * 16 + g + 8 * h;
           if (i < T) {
             float* o = dqkv + static_cast<long long>(row0 + i) * ldd + head * kMmaAttnHd + 2 * t4;
 #pragma unroll
@@ -754,27 +763,25 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
       }
     }
   }
-  __syncthreads();   // statistics of every query row are in shared memory
 
   // ================================================================= phase B: key rows of this warp
-  if (warp * 32 < T) {
+  if (active) {
     const int jt = warp;
-    const int j_hi = min(T, jt * 32 + 32) - 1;
-    const int nmt = (j_hi - jt * 32) / 16 + 1;
-    float dk[2][8][4], dv[2][8][4];
+    float dk[MT][8][4], dv[MT][8][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int ct = 0; ct < 8; ++ct)
 #pragma unroll
         for (int e = 0; e < 4; ++e) dk[mt][ct][e] = dv[mt][ct][e] = 0.0f;
-    float st[2][4][4], dpt[2][4][4];
+    float (&st)[MT][4][4] = s;
+    float (&dpt)[MT][4][4] = dp;
     const int nblk = (T + 31) / 32;
-    for (int ib = jt; ib < nblk; ++ib) {
+    for (int ib = (jt * RB) / 32; ib < nblk; ++ib) {
       const int imax = min(T - 1, ib * 32 + 31);
       const int nnt = (imax - ib * 32) / 8 + 1;   // n8 tiles of query columns in use
-      rows_product(st, 1, jt * 32, 0, ib * 32, nmt, nnt);    // S^T = K Q^T
-      rows_product(dpt, 2, jt * 32, 3, ib * 32, nmt, nnt);   // dP^T = V dO^T
+      rows_product(st, 1, jt * RB, 0, ib * 32, nmt, nnt);    // S^T = K Q^T
+      rows_product(dpt, 2, jt * RB, 3, ib * 32, nmt, nnt);   // dP^T = V dO^T
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         float cm[2], cl[2], cd[2];
@@ -786,10 +793,10 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
           cd[u] = sD[i & 127];
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = jt * 32 + mt * 16 + g + ((e >> 1) << 3);
+            const int j = jt * RB + mt * 16 + g + ((e >> 1) << 3);
             const int i = ib * 32 + nt * 8 + 2 * t4 + (e & 1);
             const bool ok = j <= i && i < T && nt < nnt && mt < nmt;
             const float pv = ok ? ex2f_(fmaf(st[mt][nt][e], kLog2e, -cm[e & 1])) * cl[e & 1] : 0.0f;
@@ -801,11 +808,11 @@ __global__ void __launch_bounds__(128) mha_causal_bwd_mma_kernel(
       acc_product(dk, dpt, 0, ib * 32, nmt, nnt);   // dK += dS^T Q
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       if (mt < nmt) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int j = jt * 32 + mt * 16 + g + 8 * h;
+          const int j = jt * RB + mt * 16 + g + 8 * h;
           if (j < T) {
             float* o = dqkv + static_cast<long long>(row0 + j) * ldd + d + head * kMmaAttnHd + 2 * t4;
 #pragma unroll
@@ -848,9 +855,9 @@ int attention_init() {
                                       mma_attn_smem_bytes<true>()));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       mma_attn_smem_bytes<true>()));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       mma_attn_bwd_smem_bytes<false>()));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       mma_attn_bwd_smem_bytes<true>()));
   return BLM_OK;
 }
@@ -957,10 +964,10 @@ extern "C" int blm_mha_causal_bwd_tc(const float* qkv, int64_t ld, const float* 
   }
   const unsigned grid = static_cast<unsigned>(nseq * nhead);
   if (precise)
-    mha_causal_bwd_mma_kernel<true><<<grid, 128, mma_attn_bwd_smem_bytes<true>(), as_stream(stream)>>>(
+    mha_causal_bwd_mma_kernel<true, 1><<<grid, 256, mma_attn_bwd_smem_bytes<true>(), as_stream(stream)>>>(
         qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd);
   else
-    mha_causal_bwd_mma_kernel<false><<<grid, 128, mma_attn_bwd_smem_bytes<false>(), as_stream(stream)>>>(
+    mha_causal_bwd_mma_kernel<false, 1><<<grid, 256, mma_attn_bwd_smem_bytes<false>(), as_stream(stream)>>>(
         qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
