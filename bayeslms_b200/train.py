@@ -30,6 +30,8 @@ from . import engine
 from .engine import PackedBatch
 from .scorer import read_vocab
 
+_USE_GRAPHS = os.environ.get("BLM_TRAIN_NO_GRAPHS") is None     # A/B switch: plain launches instead of graph replay
+
 
 # ------------------------------------------------------------------ data (data.py:9-54, train.py:164-183,293-297)
 class Corpus:
@@ -109,6 +111,15 @@ def train_epoch(ft, train_data: torch.Tensor, seq_len: int, epoch: int, *, log_i
         if is_rnn:
             _, ce, _ = ft.step(data, targets, kl_scale, seed=step_seed, hidden=hidden)
             hidden = ft.hidden                           # detached by construction (train.py:320)
+        elif data.size(0) == seq_len and _USE_GRAPHS:
+            # full-size batches replay the step as two CUDA graphs (~250 small launches otherwise); the graphs bake
+            # in the shapes, the KL scale and the learning rate, so they are re-captured when any of them changes
+            cap = getattr(ft, "_cap", None)
+            key = (data.size(0), data.size(1), kl_scale, ft.lr)
+            if cap is None or cap.get("key") != key:
+                ft.capture(data.size(0), data.size(1), kl_scale)
+                ft._cap["key"] = key
+            _, ce, _ = ft.step_captured(data, targets, step_seed)
         else:
             _, ce, _ = ft.step(data, targets, kl_scale, seed=step_seed)
         tot += ce.double()

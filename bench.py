@@ -320,6 +320,13 @@ def main():
             nll_ms, nll_flops, nll_n = t, sum(w for _, _, w in evs), len(evs)
     tot = sum(shares.values()) or 1.0
     pk = peaks()
+    # achieved TFLOP/s of every tensor-bound kernel of the step (algorithmic FLOP of its launches / event time)
+    krf = {}
+    for name, evs in timing.items():
+        w = sum(x for _, _, x in evs)
+        if w > 0 and shares[name] > 0:
+            tf = w / (shares[name] / 1e3) / 1e12
+            krf[name] = {"achieved": round(tf, 1), "frac": round(tf / pk["tensor"], 3), "launches": len(evs)}
     achieved = (nll_flops / nll_n) / (nll_ms / nll_n / 1e3) / 1e12 if nll_n else 0.0
 
     # ---- e2e: host ids -> pinned staging -> device -> scores back on the host, every step
@@ -406,6 +413,7 @@ def main():
                          "avg_launch_ms": nll_ms / nll_n if nll_n else None,
                          "share_of_step": nll_ms / tot},
             "kernel_time_shares": {k: round(v / tot, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
+            "kernel_rooflines": {"unit": "TFLOP/s", "peak": pk["tensor"], **krf},
             "sampled_k4": {"value": n_tokens * world * k4_steps / (k4_ms / 1e3), "unit": "tokens/s", "K": 4,
                            "noise": "Philox4x32-10 on device",
                            # north_star (a): the reparameterised-weight GEMM of the sampled FFN (layer 0 linear2,
