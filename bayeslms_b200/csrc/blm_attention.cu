@@ -280,21 +280,32 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
   }
   const int d = nhead * kMmaAttnHd;
   const int pb = (warp / WPP) * KV_ROWS;  // first shared-memory row of this pair
-  // ---- stage rows [32 qt, 32 qt + 32) of q, k and v of this pair (zero fill past T)
+  // ---- stage rows [32 qt, 32 qt + 32) of q, k and v of this pair (zero fill past T).  Lane l copies 16-byte chunk
+  // l % 8 of rows l / 8 + 4 it: one pointer and one swizzled offset per (matrix, part), advanced by constants (the
+  // address arithmetic of the first version was 60 % of this kernel's instructions, ncu r01az).  Rows past the last
+  // 16-row tile that holds a valid token are never read by an MMA and are skipped.
+  {
+    const int r0 = lane >> 3, ch = lane & 7;
+    const int rows_used = min(32, ((T - qt * 32 + 15) & ~15));          // 16 or 32 (<= 0: nothing to stage)
+    const long long row_step = 4 * ld;                                   // elements between two iterations
+    // swizzled chunk position alternates with (row & 7) = r0 or r0 + 4
+    const uint32_t sw0 = static_cast<uint32_t>((ch ^ r0) << 4), sw1 = static_cast<uint32_t>((ch ^ (r0 + 4)) << 4);
+    const uint32_t dst_row = static_cast<uint32_t>((pb + qt * 32 + r0) * kMmaAttnRowBytes);
 #pragma unroll
-  for (int mat = 0; mat < 3; ++mat) {
+    for (int mat = 0; mat < 3; ++mat) {
 #pragma unroll
-    for (int part = 0; part < PARTS; ++part) {
-      const __nv_bfloat16* src_base = (part == 0 ? qkv_hi : qkv_lo) + mat * d + head * kMmaAttnHd;
+      for (int part = 0; part < PARTS; ++part) {
+        const __nv_bfloat16* src = (part == 0 ? qkv_hi : qkv_lo) + mat * d + head * kMmaAttnHd + ch * 8 +
+                                   static_cast<long long>(row0 + qt * 32 + r0) * ld;
+        const uint32_t dst = tile(mat, part) + dst_row;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int c = it * 32 + lane;
-        const int r = c >> 3, ch = c & 7;
-        const int tr = qt * 32 + r;
-        const bool ok = tr < T;
-        const __nv_bfloat16* src = ok ? src_base + static_cast<long long>(row0 + tr) * ld + ch * 8 : src_base;
-        const uint32_t dst = tile(mat, part) + static_cast<uint32_t>((pb + tr) * kMmaAttnRowBytes + ((ch ^ (r & 7)) << 4));
-        cp_async16(dst, src, ok ? 16u : 0u);
+        for (int it = 0; it < 8; ++it) {
+          if (it * 4 < rows_used) {
+            const bool ok = qt * 32 + r0 + it * 4 < T;
+            cp_async16(dst + static_cast<uint32_t>(it * 4 * kMmaAttnRowBytes) + ((it & 1) ? sw1 : sw0),
+                       ok ? src + it * row_step : src, ok ? 16u : 0u);
+          }
+        }
       }
     }
   }
