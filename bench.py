@@ -137,34 +137,44 @@ def bench_finetune(dev, world, steps, warmup=3):
             "loss_first": losses[0], "loss_last": losses[-1], "dropout": 0.0}
 
 
-def bench_lstm(dev, steps=2):
+def bench_lstm(dev, world=1, rank=0, steps=2):
     """BASELINE configs 1 / 5 shape: Bayesian LSTM 2x1024 (emb 1024, L_bayes_pos=3), V=30000, 100-best lists in
-    sessions of 16 utterances (hidden carry through hypothesis #0, score.py:271-274).  End to end: host id lists ->
-    lock-step batches -> persistent recurrence kernel -> vocabulary NLL -> scores on the host."""
+    sessions of 16 utterances (hidden carry through hypothesis #0, score.py:271-274).  End to end: flat host id
+    arrays -> lock-step batches -> persistent recurrence kernel -> vocabulary NLL -> scores on the host.  With N
+    ranks every rank scores its own 8 sessions (session-sharded, weak scaling, no data-path collective); the time is
+    the max over ranks between two barriers."""
+    import torch.distributed as dist
     from bayeslms_b200 import model as M, synth
     from bayeslms_b200.scorer import Rescorer
     torch.manual_seed(1111)
     net = M.BayesRNNModel("LSTM", V, 1024, 1024, 2, 0.5, True, 3).to(dev).eval()
     n_sess, per_sess, nbest = 8, 16, 100
-    data = synth.make_nbest(n_sess * per_sess, nbest, V, seed=1112)
+    data = synth.make_nbest(n_sess * per_sess, nbest, V, seed=1112 + rank)
     # flat host id arrays, rows ordered (session, utterance, hypothesis) -- the LSTM twin of flat_host() above
     tok, tgt, _, offs = data.flat_host()
     utt = np.repeat(np.arange(n_sess * per_sess), [len(u) for u in data.hyps])
     sess_of, utt_of = (utt // per_sess).astype(np.int32), (utt % per_sess).astype(np.int32)
-    n_tok = data.n_tokens()
+    n_tok = torch.tensor([float(data.n_tokens())], device=dev)
+    if world > 1:
+        dist.all_reduce(n_tok)
     out = {}
     for name, kw in (("mean", {}), ("sampled_k8", {"K": 8, "seed": 1111})):
         rs = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS, **kw)
         rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)       # warm-up (plans, workspaces)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / steps
-        out[name] = {"tokens_per_s": n_tok / dt, "ms": dt * 1e3}
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[name] = {"tokens_per_s": n_tok.item() / dt.item(), "ms": dt.item() * 1e3}
     out["workload"] = (f"Bayesian LSTM 2x1024 L_bayes_pos=3 V30000, {nbest}-best, {n_sess} sessions x {per_sess} utterances "
-                       f"({n_tok} tokens), end to end from flat host id arrays incl. batch packing (wall clock)")
+                       f"per GPU ({int(n_tok.item())} tokens over {world} GPU(s)), end to end from flat host id arrays incl. "
+                       "batch packing (wall clock, max over ranks)")
     return out
 
 
@@ -378,7 +388,7 @@ def main():
     wer_p, picks_p = synth.wer(data, per_utt(precise), lo=lo)
 
     finetune = bench_finetune(dev, world, max(10, args.steps))
-    lstm = bench_lstm(dev) if (rank == 0 and world == 1) else None
+    lstm = bench_lstm(dev, world, rank)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
