@@ -582,19 +582,20 @@ static int launch_chunk(const GemmParams& p, cudaStream_t st) {
   return BLM_OK;
 }
 
-// transposed-store (STG) variants: ACT_NONE only -- the fp32-output GEMMs (QKV in training, o_net, FFN2)
-template <int BN, int STAGES, int CHUNK>
+// transposed-store (STG) variants: the fp32-output GEMMs (QKV in training, o_net, FFN2) and the GELU-gradient
+// dgrad (dz1 = (dF W2) * gelu'(z1): fp32 + bf16 outputs and the saved pre-activation read, all row-coalesced)
+template <int BN, int STAGES, int CHUNK, int ACT = BLM_ACT_NONE>
 static int set_smem_attr_stg() {
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI_STORE, BLM_ACT_NONE, 0, 8, CHUNK, 1>,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, CHUNK, 1>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SmemLayout<BN, STAGES, 0>::kDynBytes));
   return BLM_OK;
 }
 
-template <int BN, int STAGES, int CHUNK>
+template <int BN, int STAGES, int CHUNK, int ACT = BLM_ACT_NONE>
 static int launch_stg(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<BN, STAGES, EPI_STORE, BLM_ACT_NONE, 0, 8, CHUNK, 1>
+  gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, CHUNK, 1>
       <<<grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st>>>(p);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
@@ -652,6 +653,9 @@ int gemm_init() {
   if ((rc = set_smem_attr_stg<256, kStages256, 0>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<128, kStages128, 0>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<128, kStages128, 1>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<256, kStages256, 0, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<128, kStages128, 0, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<128, kStages128, 1, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_GPMIX>()) != BLM_OK) return rc;
@@ -805,6 +809,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   p.aux = d->aux;
   p.ldaux = d->ldaux;
   p.a_f16 = d->a_f16;
+  p.fast_act = d->fast_act;
   if (gen) {
     p.gen_mu = reinterpret_cast<const __nv_bfloat16*>(gen->mu);
     p.gen_ldmu = gen->ldmu;
@@ -891,10 +896,12 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
       default: return launch_tma<128, kStages128, BLM_ACT_GELU_FAST>(p, st);
     }
   }
+  const bool gstg = p.use_stg && d->act == BLM_ACT_GELU_GRAD && !d->out_pre;
   const bool stg = p.use_stg && d->act == BLM_ACT_NONE;
   if (chunked) {
     p.chunk_kb = d->k_chunk / kBK;
     if (stg) return launch_stg<128, kStages128, 1>(p, st);
+    if (gstg) return launch_stg<128, kStages128, 1, BLM_ACT_GELU_GRAD>(p, st);
     switch (d->act) {
       case BLM_ACT_NONE: return launch_chunk<BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch_chunk<BLM_ACT_GELU>(p, st);
@@ -922,6 +929,9 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
     }
   }
   if (stg) return BN == 256 ? launch_stg<256, kStages256, 0>(p, st) : launch_stg<128, kStages128, 0>(p, st);
+  if (gstg)
+    return BN == 256 ? launch_stg<256, kStages256, 0, BLM_ACT_GELU_GRAD>(p, st)
+                     : launch_stg<128, kStages128, 0, BLM_ACT_GELU_GRAD>(p, st);
   if (BN == 256) {
     switch (d->act) {
       case BLM_ACT_NONE: return launch<256, kStages256, EPI_STORE, BLM_ACT_NONE>(p, st);

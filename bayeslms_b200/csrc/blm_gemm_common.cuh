@@ -38,6 +38,7 @@ struct GemmParams {
   long long ldc;
   int a_mn, b_mn;       // 1: the operand is MN-major: A[s] is [K_s, M] / B[s] is [K_s, N] row-major (wgrad / dgrad
                         // straight from the activations / weights, no transposed copies); boxes of 64 x 64
+  int fast_act;         // 1: packed-fp16 evaluation of the activation derivative (GELU_GRAD on the transposed path)
   int a_f16;            // 1: A operands are fp16 (instruction descriptor A format F16, B stays BF16)
   int use_stg;          // 1: transpose finished chunks through shared memory for row-coalesced stores
   int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk
@@ -197,6 +198,30 @@ __device__ __forceinline__ float gelu_grad(float z) {
   return fmaf(z, phi, Phi);
 }
 
+// The same derivative for two elements in packed fp16 (fast mode: <= 1e-3 absolute): E = erfc(|z| / sqrt 2) / 2 from
+// the exponent trick of gelu_fast_core_h2, Phi = 1/2 + copysign(1/2 - E, z), phi through a second ex2.approx.f16x2.
+__device__ __forceinline__ void gelu_grad_h2(float z0, float z1, float& g0, float& g1) {
+  const __half2 x = __floats2half2_rn(z0, z1);
+  const __half2 s = __hmin2(__habs2(x), __float2half2_rn(5.65685f));
+  __half2 p = __hfma2(s, __float2half2_rn(-4.0813875e-03f), __float2half2_rn(4.5319763e-02f));
+  p = __hfma2(p, s, __float2half2_rn(4.6557564e-01f));
+  p = __hfma2(p, s, __float2half2_rn(1.1492719e+00f));
+  const __half2 ex = __hfma2(__hneg2(p), s, __float2half2_rn(-1.0f));
+  const __half2 ex2 = __hmul2(__hmul2(x, x), __float2half2_rn(-0.7213475f));        // -z^2 / 2 in log2 units
+  uint32_t e_bits, f_bits;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e_bits) : "r"(*reinterpret_cast<const uint32_t*>(&ex)));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(f_bits) : "r"(*reinterpret_cast<const uint32_t*>(&ex2)));
+  const __half2 E = *reinterpret_cast<const __half2*>(&e_bits);
+  const __half2 half = __float2half2_rn(0.5f);
+  __half2 dlt = __hsub2(half, E);                                                   // >= 0
+  uint32_t d_bits = *reinterpret_cast<const uint32_t*>(&dlt) | (*reinterpret_cast<const uint32_t*>(&x) & 0x80008000u);
+  const __half2 Phi = __hadd2(half, *reinterpret_cast<const __half2*>(&d_bits));
+  const __half2 g = __hfma2(__hmul2(x, __float2half2_rn(0.3989423f)), *reinterpret_cast<const __half2*>(&f_bits), Phi);
+  const float2 f = __half22float2(g);
+  g0 = f.x;
+  g1 = f.y;
+}
+
 // d/dz of sum_i coef[i, n] act_i(z), acts tanh, sigmoid, relu, gelu (model.py:1893-1899)
 __device__ __forceinline__ float gpmix_grad(float z, const float* __restrict__ coef, int N, int n) {
   const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n), c3 = __ldg(coef + 3 * N + n);
@@ -335,6 +360,8 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         v[j] = (ex2_approx(fmaf(v[j], 1.4426950408889634f, nl)) - (j == rel ? 1.0f : 0.0f)) * p.grad_scale;
+    } else if constexpr (ACT == BLM_ACT_GELU_GRAD && STG == 1) {
+      // applied after the transpose below, where the saved pre-activation is read with row-coalesced loads
     } else if constexpr (ACT == BLM_ACT_GELU_GRAD || ACT == BLM_ACT_GPMIX_GRAD) {
       if (row_ok) {
         const float* a = p.aux + static_cast<long long>(m) * p.ldaux + col0;
@@ -379,11 +406,36 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
                              : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        float4 za[4];
+        if constexpr (ACT == BLM_ACT_GELU_GRAD) {   // the saved pre-activation of these four rows, coalesced
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int mr = m0 + rsub + 4 * (k0 + k);
+            za[k] = mr < p.M ? __ldg(reinterpret_cast<const float4*>(p.aux + static_cast<long long>(mr) * p.ldaux + col))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int row = rsub + 4 * (k0 + k);
           const int mr = m0 + row;
           float4 x = stg[row * 8 + (c4 ^ (row & 7))];
+          if constexpr (ACT == BLM_ACT_GELU_GRAD) {
+            if (p.fast_act) {
+              float g0, g1, g2, g3;
+              gelu_grad_h2(za[k].x, za[k].y, g0, g1);
+              gelu_grad_h2(za[k].z, za[k].w, g2, g3);
+              x.x *= g0;
+              x.y *= g1;
+              x.z *= g2;
+              x.w *= g3;
+            } else {
+              x.x *= gelu_grad(za[k].x);
+              x.y *= gelu_grad(za[k].y);
+              x.z *= gelu_grad(za[k].z);
+              x.w *= gelu_grad(za[k].w);
+            }
+          }
           if (p.resid) {
             x.x += rr[k].x;
             x.y += rr[k].y;

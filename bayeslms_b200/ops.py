@@ -120,7 +120,7 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
          out: Optional[Split] = None, extra: Sequence = (), tag: str = "", out_pre: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
          targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None,
-         a_f16: bool = False, a_mn: bool = False, b_mn: bool = False):
+         a_f16: bool = False, a_mn: bool = False, b_mn: bool = False, fast_act: bool = False):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
     accumulated into the same output (K-concatenation).  ``out_pre`` receives the fp32 value before
     the activation; ``aux`` is the saved pre-activation of the ``*_GRAD`` epilogues; ``lse`` /
@@ -166,7 +166,7 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     if lse is not None:
         d.lse, d.targets, d.grad_scale = _ptr(lse), _ptr(targets), grad_scale
     d.k_chunk = (PRECISE_K_CHUNK if prec == "bf16x3" else 0) if k_chunk is None else k_chunk
-    d.a_f16, d.a_mn, d.b_mn = int(a_f16), int(a_mn), int(b_mn)
+    d.a_f16, d.a_mn, d.b_mn, d.fast_act = int(a_f16), int(a_mn), int(b_mn), int(fast_act)
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[0 if a_mn else 1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
 

@@ -345,7 +345,7 @@ class FineTuner:
                          out=dz1s, out_pre=dh, tag="dgrad:ffn2")
             else:
                 _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
-                         tag="dgrad:ffn2")
+                      fast_act=(prec == "bf16"), tag="dgrad:ffn2")
             dft, ht = _tsplit(df, prec, dfs), _tbf16(S["hs"], prec)
             if kind == "bayes_ffn":
                 G = g[pre + "linear2.weight_mean"]

@@ -133,7 +133,7 @@ typedef struct blm_gemm_desc {
   int32_t b_mn;        /* 1: B[s] is the row-major [K_s, N] tensor.  Weight gradients dW = dY^T X take dY [tokens, N]
                           and X [tokens, K] as they are (a_mn = b_mn = 1), input gradients dX = dY W take W [N, K]
                           as it is (b_mn = 1): no transposed copies (tcgen05 MN-major shared-memory descriptors)  */
-  int32_t reserved;
+  int32_t fast_act;    /* 1: BLM_ACT_GELU_GRAD evaluates gelu' in packed fp16 (fast mode, <= 1e-3 absolute)            */
 } blm_gemm_desc;
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);

@@ -444,3 +444,24 @@ def test_attention_backward_tensor_core(ops, lens, prec, tol):
     ref[:, :d] *= 0.125                      # dq is returned w.r.t. the unscaled projection (model.py:877)
     _close(simt, ref, 1e-5)
     _close(got, ref, tol)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_gelu_grad_epilogue_coalesced(ops, fast):
+    """BLM_ACT_GELU_GRAD through the store-transpose path (fp32 + bf16 outputs, saved pre-activation read row
+    coalesced); ``fast_act``: gelu' in packed fp16 (fast mode)."""
+    M, N, K = 3200, 4096, 512
+    a = torch.randn(M, K, device=DEV) * 0.5
+    b = torch.randn(N, K, device=DEV) * 0.1
+    z = torch.randn(M, N, device=DEV) * 1.5
+    A, B = ops.split(a, "bf16"), ops.split(b, "bf16")
+    out32 = torch.empty(M, N, device=DEV)
+    out = ops.empty_split(M, N, "bf16", DEV)
+    ops.gemm(A, B, prec="bf16", act=ops.ACT_GELU_GRAD, aux=z, out_f32=out32, out=out, fast_act=fast)
+    zz = z.double().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    ref = (A.hi.double() @ B.hi.double().T) * zz.grad
+    err = (out32.double() - ref).abs()
+    acc = (A.hi.double() @ B.hi.double().T).abs()
+    assert (err <= (2e-3 if fast else 2e-6) * acc + 1e-6 * acc.max()).all(), err.max().item()
+    assert torch.equal(out.hi, out32.to(torch.bfloat16))
