@@ -102,10 +102,17 @@ def _chunks_by_tokens(lengths: Sequence[int], max_tokens: int) -> List[Tuple[int
     fraction of the SMs)."""
     if not len(lengths):
         return []
+    # greedy fill: the fewest-chunk reference (and the answer when single items are close to the limit)
+    greedy, start, tot = [], 0, 0
+    for i, n in enumerate(lengths):
+        if tot and tot + n > max_tokens:
+            greedy.append((start, i))
+            start, tot = i, 0
+        tot += n
+    greedy.append((start, len(lengths)))
     csum = np.cumsum(np.asarray(lengths, dtype=np.int64))
     total = int(csum[-1])
-    n = max(1, -(-total // max_tokens))
-    while True:
+    for n in range(max(1, -(-total // max_tokens)), len(greedy) + 1):
         cuts = [0]
         for j in range(1, n):
             i = int(np.searchsorted(csum, j * total / n, side="left")) + 1   # first prefix reaching the share
@@ -113,9 +120,9 @@ def _chunks_by_tokens(lengths: Sequence[int], max_tokens: int) -> List[Tuple[int
         cuts.append(len(lengths))
         cuts = sorted(set(cuts))
         sizes = [int(csum[b - 1] - (csum[a - 1] if a else 0)) for a, b in zip(cuts[:-1], cuts[1:])]
-        if max(sizes) <= max_tokens or n >= len(lengths):
+        if max(sizes) <= max_tokens:
             return list(zip(cuts[:-1], cuts[1:]))
-        n += 1
+    return greedy
 
 
 # -------------------------------------------------------------------------- scoring

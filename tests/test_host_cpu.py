@@ -146,3 +146,56 @@ def test_sharded_scoring_equals_single_rank_gloo():
     for p in procs:
         p.join(60)
     assert got == [(0, True), (1, True)]
+
+
+def test_balanced_chunks_cover_and_respect_the_limit():
+    """scorer._chunks_by_tokens: contiguous, complete, every chunk <= max_tokens, fewest chunks, balanced sizes."""
+    import numpy as np
+    from bayeslms_b200.scorer import _chunks_by_tokens
+    rng = np.random.default_rng(3)
+    for n, mx in ((12800, 65536), (1000, 500), (7, 30), (1, 5), (50, 27)):
+        lens = rng.integers(1, 27, size=n).tolist()
+        cuts = _chunks_by_tokens(lens, mx)
+        assert cuts[0][0] == 0 and cuts[-1][1] == n and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        sizes = [sum(lens[a:b]) for a, b in cuts]
+        assert max(sizes) <= max(mx, max(lens))
+        greedy, tot = 1, 0                      # never more chunks than a greedy fill
+        for x in lens:
+            if tot and tot + x > mx:
+                greedy, tot = greedy + 1, 0
+            tot += x
+        assert len(cuts) <= greedy
+        if len(sizes) > 1 and mx >= 500:        # balanced when items are small against the limit
+            assert max(sizes) - min(sizes) <= 2 * 26 + sum(lens) // len(sizes) // 10
+    assert _chunks_by_tokens([], 10) == []
+    assert [sum([10, 1, 1, 1, 10][a:b]) <= 11 for a, b in _chunks_by_tokens([10, 1, 1, 1, 10], 11)] == [True] * 3
+
+
+def test_flatten_sessions_layout():
+    """engine.flatten_sessions: nested [session][utterance][(input, target)] -> flat arrays in row order."""
+    import numpy as np
+    from bayeslms_b200.engine import flatten_sessions
+    sessions = [[[([0, 5, 6], [5, 6, 0]), ([0, 7], [7, 0])], [([0], [0])]], [[([0, 9, 9, 9], [9, 9, 9, 0])]]]
+    tok, tgt, offs, sess_of, utt_of = flatten_sessions(sessions)
+    assert tok.tolist() == [0, 5, 6, 0, 7, 0, 0, 9, 9, 9] and tgt.tolist() == [5, 6, 0, 7, 0, 0, 9, 9, 9, 0]
+    assert offs.tolist() == [0, 3, 5, 6, 10]
+    assert sess_of.tolist() == [0, 0, 0, 1] and utt_of.tolist() == [0, 0, 1, 0]
+    assert tok.dtype == np.int32 and tgt.dtype == np.int32
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference prints exactly one JSON line on stdout with the keys of the contract."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
