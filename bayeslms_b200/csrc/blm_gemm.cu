@@ -289,8 +289,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
     const int etid = threadIdx.x - kEpiWarp0 * 32;
     const int row_in_tile = lane_grp * 32 + lane;
     const int c0 = col_grp * kChunks;  // first chunk of this warp inside the tile
-    static_assert(!STG || (ARES == 0 && EPI == EPI_STORE && (EW == 8 || STG == 2)),
-                  "store staging: 8 warps x 4 KB, or 16 warps x 2 KB (TMA store only)");
+    static_assert(!STG || (EPI == EPI_STORE && ((ARES == 0 && (EW == 8 || STG == 2)) || (ARES > 0 && STG == 2 && EW == 16))),
+                  "store staging: 8 warps x 4 KB, or 16 warps x 2 KB (TMA store only; also the A-resident variant)");
     float4* stg = STG ? reinterpret_cast<float4*>(smem + L::kStgOffset + (warp - kEpiWarp0) * (EW == 16 ? 2048 : 4096))
                       : nullptr;  // store-transpose / TMA-store staging of this warp
     int acc = 0;
@@ -627,6 +627,26 @@ static int launch_tma16(const GemmParams& p, cudaStream_t st) {
   return BLM_OK;
 }
 
+// A-resident form of the 16-epilogue-warp TMA-store kernel for K <= 512 (QKV, FFN1): the 128 x 512 activation
+// tile stays in shared memory while the CTA sweeps a group of N tiles, only weight tiles stream (2 x 32 KB ring)
+constexpr int kAresStoreStages = 2;
+template <int ACT>
+static int set_smem_attr_tma16_ares() {
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<256, kAresStoreStages, EPI_STORE, ACT, kNllAres, 16, 0, 2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SmemLayout<256, kAresStoreStages, kNllAres>::kDynBytes));
+  return BLM_OK;
+}
+
+template <int ACT>
+static int launch_tma16_ares(const GemmParams& p, cudaStream_t st) {
+  const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
+  gemm_kernel<256, kAresStoreStages, EPI_STORE, ACT, kNllAres, 16, 0, 2>
+      <<<grid, (4 + 16) * 32, SmemLayout<256, kAresStoreStages, kNllAres>::kDynBytes, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 template <int BN, int STAGES, int ACT>
 static int launch_tma(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
@@ -638,6 +658,8 @@ static int launch_tma(const GemmParams& p, cudaStream_t st) {
 
 int gemm_init() {
   int rc;
+  if ((rc = set_smem_attr_tma16_ares<BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_tma16_ares<BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma16<BLM_ACT_GELU_FAST>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma16<BLM_ACT_GPMIX_FAST>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_tma<256, kStages256, BLM_ACT_NONE>()) != BLM_OK) return rc;
@@ -872,6 +894,27 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
       const char* e = getenv("BLM_EPI16");   // A/B switch: 0 keeps the packed-fp16 epilogues on 8 warps
       return e ? atoi(e) != 0 : true;
     }();
+    static const bool ares16 = getenv("BLM_GEMM_ARES16") != nullptr;   // A/B switch (opt-in experiment)
+    if (ares16 && ew16 && BN == 256 && d->nseg == 1 && p.kblocks[0] <= kNllAres && p.n_tiles >= 4 &&
+        (d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_NONE)) {
+      // groups of N tiles per work item: as few A reloads as possible at >= 95 % wave efficiency
+      int best_g = p.n_tiles;
+      for (int g = 1; g <= p.n_tiles; g *= 2) {
+        const long long works = static_cast<long long>(p.m_tiles) * g;
+        const long long rounds = (works + num_sms() - 1) / num_sms();
+        if (static_cast<double>(works) / (rounds * num_sms()) >= 0.95) {
+          best_g = g;
+          break;
+        }
+      }
+      p.n_groups = best_g;
+      p.tiles_per_group = (p.n_tiles + best_g - 1) / best_g;
+      p.n_groups = (p.n_tiles + p.tiles_per_group - 1) / p.tiles_per_group;
+      p.num_works = p.m_tiles * p.n_groups;
+      rc = encode_tmap_bf16_box32(&p.tmC, d->out_hi, d->M, d->N, d->ldc);
+      if (rc != BLM_OK) return rc;
+      return d->act == BLM_ACT_GELU_FAST ? launch_tma16_ares<BLM_ACT_GELU_FAST>(p, st) : launch_tma16_ares<BLM_ACT_NONE>(p, st);
+    }
     if (ew16 && BN == 256 && (d->act == BLM_ACT_GELU_FAST || d->act == BLM_ACT_GPMIX_FAST)) {
       rc = encode_tmap_bf16_box32(&p.tmC, d->out_hi, d->M, d->N, d->ldc);
       if (rc != BLM_OK) return rc;

@@ -80,7 +80,8 @@ struct SmemLayout {
   static constexpr int kBiasOffset = kResBytes + STAGES * kStageBytes;  // fp32 bias[2][BN], one per accumulator stage
   // 4 KB per epilogue warp (8 warps) for the store transpose; the A-resident kernels (NLL) store nothing
   static constexpr int kStgOffset = kBiasOffset + 2 * BN * 4;
-  static constexpr int kStgBytes = ARES ? 0 : 8 * 4096;
+  // (the A-resident storing variant with TWO ring stages keeps 32 KB of TMA-store staging; the three-stage NLL variant stores nothing)
+  static constexpr int kStgBytes = (ARES && STAGES > 2) ? 0 : 8 * 4096;
   static constexpr int kBarOffset = kStgOffset + kStgBytes;
   // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] a_full a_empty + tmem ptr
   static constexpr int kBytes = kBarOffset + (2 * STAGES + 6) * 8 + 16;

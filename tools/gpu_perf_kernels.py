@@ -49,6 +49,8 @@ y = torch.empty(M, d, device=dev)
 hout = ops.empty_split(M, F, "bf16", dev)
 
 line("gemm qkv   [M,1536,512] bias+qscale f32", timeit(lambda: ops.gemm(x, wqkv, bias=b3, col_scale=0.125, col_scale_cols=d, out_f32=qkv)), 2.0 * M * 3 * d * d)
+qkvs = ops.empty_split(M, 3 * d, "bf16", dev)
+line("gemm qkv   [M,1536,512] bias+qscale bf16", timeit(lambda: ops.gemm(x, wqkv, bias=b3, col_scale=0.125, col_scale_cols=d, out=qkvs)), 2.0 * M * 3 * d * d)
 line("gemm o_net [M,512,512] bias+resid f32", timeit(lambda: ops.gemm(x, wo, bias=bd, resid=x32, out_f32=y)), 2.0 * M * d * d)
 line("gemm ffn1  [M,4096,512] bias+GELU bf16", timeit(lambda: ops.gemm(x, w1, bias=bF, act=ACT_GELU, out=hout)), 2.0 * M * F * d)
 from bayeslms_b200.ops import ACT_GELU_FAST
