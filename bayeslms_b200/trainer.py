@@ -38,6 +38,11 @@ from .ops import (ACT_GELU, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, 
 _MN = os.environ.get("BLM_TRAIN_TRANSPOSE") is None
 # the optimiser kernel writes the bf16 operand copies of the updated weights (BLM_TRAIN_NO_MIRROR=1: split per step)
 _MIRROR = os.environ.get("BLM_TRAIN_NO_MIRROR") is None
+# Data parallel, opt-in (BLM_TRAIN_OVERLAP=1): all-reduce of the upper layers' gradients overlapped with the rest of
+# the backward pass (two CUDA graphs).  Correct (tools/ddp_train_check.py) but MEASURED SLOWER on 8 GPUs: 4.11 vs
+# 4.01 ms per step -- only 38 % of the bytes can start early (the tied embedding gradient completes last), the NCCL
+# kernel takes SMs from a backward pass made of 20-70 us kernels, and three small all-reduces pay three latencies.
+_OVERLAP = os.environ.get("BLM_TRAIN_OVERLAP") is not None
 
 
 class _T:
@@ -96,6 +101,7 @@ class FineTuner:
         for name, p in named:
             offs[name] = total
             total += (p.numel() + 7) // 8 * 8          # 16-byte aligned views of the fp32 AND the bf16 mirror buffers
+        self._offs = {name: (offs[name], (p.numel() + 7) // 8 * 8) for name, p in named}
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -171,7 +177,7 @@ class FineTuner:
     # ------------------------------------------------------------------ one step
     def forward_backward(self, tokens_tb: torch.Tensor, targets_tb: torch.Tensor, kl_scale: float, *,
                          eps: Optional[dict] = None, seed: Optional[int] = None, v_eps_layout: str = "tbd",
-                         hidden=None):
+                         hidden=None, on_layer_done=None):
         """Fills the gradient buffer for the batch (T, B); returns (loss, ce, kl) as 0-dim device tensors.
         ``eps``: injected noise in the oracle's layout ({'layer<i>': ...}; V layers: (T, B, d) tensors
         already scaled by 0.1, or (B, T, d) with ``v_eps_layout="btd"``); ``seed``: Philox noise instead.
@@ -402,6 +408,8 @@ class FineTuner:
             else:
                 self._wgrad(dqkvt, xst, g[pre + "self_attn.qkv_net.weight"], "qkv")
                 ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
+            if on_layer_done is not None:
+                on_layer_done(li)      # every gradient of layers >= li is final (capture() splits the graph here)
         if emb_variant:   # back through x0 W~^T: G = dx^T x0 (-> embed_mean, embed_lgstd), dx0 = dx W~
             dxt, x0t = _tsplit(dx, prec), _tbf16(E_in["x0s"], prec)
             if E_in["sampled"]:
@@ -654,9 +662,47 @@ class FineTuner:
                 self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        cap["g1"] = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cap["g1"]):
-            cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
+        nl = len(m.transformerlayers)
+        cap["split"] = None
+        if self.world > 1 and nl >= 2 and _OVERLAP:
+            # Data parallel: the backward pass is captured as TWO graphs, cut after layer `sl`.  The gradients of the
+            # layers >= sl are final there, so their all-reduce (one contiguous range of the flat buffer) runs on
+            # NCCL's stream while the second graph finishes the backward pass of the lower layers and the embedding.
+            sl = nl // 2
+            rng = [self._offs[n] for n in self._offs if n.startswith("transformerlayers.")
+                   and int(n.split(".")[1]) >= sl]
+            lo, hi = min(o for o, _ in rng), max(o + n for o, n in rng)
+            inside = [n for n, (o, _) in self._offs.items() if lo <= o < hi]
+            if all(n.startswith("transformerlayers.") and int(n.split(".")[1]) >= sl for n in inside):
+                cap["split"] = (sl, lo, hi)
+        if cap["split"] is None:
+            cap["g1"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cap["g1"]):
+                cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
+        else:
+            sl = cap["split"][0]
+            cap["g1"], cap["g1b"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            state = {"cut": False}
+
+            def cut(li):
+                if li == sl and not state["cut"]:
+                    cap["g1"].capture_end()
+                    cap["g1b"].capture_begin(pool=cap["g1"].pool())
+                    state["cut"] = True
+
+            cs = torch.cuda.Stream()
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")  # workspaces of this stream
+                torch.cuda.synchronize()
+                cap["g1"].capture_begin()
+                cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd",
+                                                   on_layer_done=cut)
+                (cap["g1b"] if state["cut"] else cap["g1"]).capture_end()
+            torch.cuda.current_stream().wait_stream(cs)
+            torch.cuda.synchronize()
+            if not state["cut"]:
+                cap["split"] = None
         cap["g2"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cap["g2"]):
             ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)
@@ -678,7 +724,17 @@ class FineTuner:
         cap["y"].copy_(targets_tb.view(cap["T"], cap["B"]), non_blocking=True)
         self._refill_noise(seed)
         cap["g1"].replay()
-        if self.world > 1:
+        if self.world > 1 and cap.get("split"):
+            _, lo, hi = cap["split"]
+            dist = torch.distributed
+            w1 = dist.all_reduce(self.flat_g[lo:hi], group=self.group, async_op=True)   # overlaps the second graph
+            cap["g1b"].replay()
+            works = [w1, dist.all_reduce(self.flat_g[:lo], group=self.group, async_op=True)]
+            if hi < self.flat_g.numel():
+                works.append(dist.all_reduce(self.flat_g[hi:], group=self.group, async_op=True))
+            for w in works:
+                w.wait()
+        elif self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.group)
         cap["g2"].replay()
         self.model.__dict__.pop("_blm_plans", None)
