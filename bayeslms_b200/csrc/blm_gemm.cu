@@ -1003,16 +1003,37 @@ extern "C" {
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream) { return blm::gemm_impl(d, nullptr, stream); }
 
-// vocabulary groups: enough (m_tile, group) work items to fill the chip, but no
-// more than needed -- each group costs one partial (max, sum, tgt) per row.
+// vocabulary groups: (m_tile, group) work items should fill WHOLE waves of the persistent grid.  One group per m
+// tile left 7 % of the chip idle at 413 m tiles (2.79 waves) and 13.5 % at 512 (3.46): the group count is the
+// smallest one (<= 8, or what it takes to have one work item per SM) whose last wave is at least 97 % full, else
+// the best found.  A group costs one (max, sum, target) partial per row and one reload of the resident 128 KB
+// hidden tile per work item -- noise next to the 256 KB vocabulary tiles it streams.
 static int nll_groups(int64_t M, int64_t V) {
   const int m_tiles = static_cast<int>((M + blm::kBM - 1) / blm::kBM);
   const int n_tiles = static_cast<int>((V + 255) / 256);
   int sms = blm::num_sms() > 0 ? blm::num_sms() : 148;
-  int g = (sms + m_tiles - 1) / m_tiles;
-  if (g > n_tiles) g = n_tiles;
-  if (g < 1) g = 1;
-  return g;
+  int g_min = (sms + m_tiles - 1) / m_tiles;
+  if (g_min > n_tiles) g_min = n_tiles;
+  if (g_min < 1) g_min = 1;
+  int g_max = g_min > 8 ? g_min : 8;
+  if (g_max > n_tiles) g_max = n_tiles;
+  static const bool no_balance = getenv("BLM_NLL_NO_BALANCE") != nullptr;   // A/B switch
+  if (no_balance) return g_min;
+  int best = g_min;
+  double best_eff = 0.0;
+  for (int g = g_min; g <= g_max; ++g) {
+    const int tpg = (n_tiles + g - 1) / g;
+    const int used = (n_tiles + tpg - 1) / tpg;
+    const long long works = static_cast<long long>(m_tiles) * used;
+    const long long waves = (works + sms - 1) / sms;
+    const double eff = static_cast<double>(works) / static_cast<double>(waves * sms);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = g;
+    }
+    if (eff >= 0.97) break;
+  }
+  return best;
 }
 
 int64_t blm_vocab_nll_workspace_bytes(int64_t M, int64_t V) {
