@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import engine
+from . import _lib, engine
 from .engine import PackedBatch
 
 
@@ -96,20 +96,54 @@ def shard_ranges(weights: Sequence[int], world: int) -> List[Tuple[int, int]]:
     return [(bounds[i], bounds[i + 1]) for i in range(world)]
 
 
-def _chunks_by_tokens(lengths: Sequence[int], max_tokens: int) -> List[Tuple[int, int]]:
+def wave_quantum() -> int:
+    """Tokens in one full wave of 128-row tiles over the CTA pairs of the LayerNorm-fused GEMM (128 * SMs / 2), or 0
+    before the library is initialised."""
+    try:
+        sms = _lib.lib().blm_num_sms()
+    except Exception:
+        return 0
+    return 128 * (sms // 2) if sms > 1 else 0
+
+
+def _greedy_fill(csum0: np.ndarray, limit: int) -> List[Tuple[int, int]]:
+    """Greedy contiguous fill (every chunk <= limit tokens, at least one item) on the prefix sums csum0 (csum0[0] = 0):
+    one searchsorted per chunk instead of a Python loop per hypothesis."""
+    out, start, n = [], 0, len(csum0) - 1
+    while start < n:
+        end = int(np.searchsorted(csum0, csum0[start] + limit, side="right")) - 1
+        end = min(max(end, start + 1), n)
+        out.append((start, end))
+        start = end
+    return out
+
+
+def _chunks_by_tokens(lengths: Sequence[int], max_tokens: int, quantum: int = 0) -> List[Tuple[int, int]]:
+    """Balanced cuts (see :func:`_balanced_chunks`); with ``quantum`` > 0 also tries chunks filled to the largest
+    multiple of ``quantum`` tokens that fits (whole waves of row tiles, remainder last) and keeps whichever needs
+    fewer waves in total."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    base = _balanced_chunks(lengths, max_tokens)
+    target = (max_tokens // quantum) * quantum if quantum > 0 else 0
+    if target <= 0 or len(base) <= 1:
+        return base
+    csum = np.concatenate([[0], np.cumsum(np.asarray(lengths, dtype=np.int64))])
+    alt = _greedy_fill(csum, target)
+
+    def waves(cuts):
+        return sum(-(-(-(-int(csum[b] - csum[a]) // 128)) // (quantum // 128)) for a, b in cuts)
+
+    return alt if (len(alt) <= len(base) and waves(alt) < waves(base)) else base
+
+
+def _balanced_chunks(lengths: Sequence[int], max_tokens: int) -> List[Tuple[int, int]]:
     """Contiguous hypothesis ranges of at most ``max_tokens`` tokens each, BALANCED: the fewest chunks that
     fit, cut at equal shares of the token count (a greedy fill leaves a small tail batch whose GEMMs run on a
     fraction of the SMs)."""
     if not len(lengths):
         return []
     # greedy fill: the fewest-chunk reference (and the answer when single items are close to the limit)
-    greedy, start, tot = [], 0, 0
-    for i, n in enumerate(lengths):
-        if tot and tot + n > max_tokens:
-            greedy.append((start, i))
-            start, tot = i, 0
-        tot += n
-    greedy.append((start, len(lengths)))
+    greedy = _greedy_fill(np.concatenate([[0], np.cumsum(np.asarray(lengths, dtype=np.int64))]), max_tokens)
     csum = np.cumsum(np.asarray(lengths, dtype=np.int64))
     total = int(csum[-1])
     for n in range(max(1, -(-total // max_tokens)), len(greedy) + 1):
@@ -153,7 +187,7 @@ class Rescorer:
     def score_transformer(self, hyps: Sequence[Tuple[Sequence[int], Sequence[int]]]) -> np.ndarray:
         lengths = [len(x) for x, _ in hyps]
         outs = []
-        for a, b in _chunks_by_tokens(lengths, self.max_tokens):
+        for a, b in _chunks_by_tokens(lengths, self.max_tokens, wave_quantum()):
             batch = PackedBatch.from_lists([h[0] for h in hyps[a:b]], [h[1] for h in hyps[a:b]], self.device)
             self.h2d_bytes += batch.h2d_bytes
             outs.append(self._score(batch))
@@ -169,7 +203,7 @@ class Rescorer:
         ``max_tokens`` tokens; each batch is one pinned H2D copy, and all scores return in one D2H."""
         n_hyp = len(offsets) - 1
         lengths = np.diff(offsets)
-        chunks = _chunks_by_tokens(lengths.tolist(), self.max_tokens)
+        chunks = _chunks_by_tokens(lengths, self.max_tokens, wave_quantum())
         need = 3 * int(offsets[-1]) + n_hyp + len(chunks)
         if self._stage is None or self._stage.numel() < need:
             self._stage = torch.empty(max(need, 1 << 16), dtype=torch.int32, pin_memory=True)

@@ -255,7 +255,7 @@ def main():
     import torch.distributed as dist
     from bayeslms_b200 import _lib, ops, synth
     from bayeslms_b200.engine import PackedBatch
-    from bayeslms_b200.scorer import Rescorer, _chunks_by_tokens
+    from bayeslms_b200.scorer import Rescorer, _chunks_by_tokens, wave_quantum
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -270,7 +270,7 @@ def main():
     tok, tgt, pos, offs = data.flat_host(lo, hi)
     n_tokens, n_hyp = int(offs[-1]), len(offs) - 1
     lengths = np.diff(offs)
-    chunks = _chunks_by_tokens(lengths.tolist(), MAX_TOKENS)
+    chunks = _chunks_by_tokens(lengths, MAX_TOKENS, wave_quantum())
 
     def device_batches():
         out = []

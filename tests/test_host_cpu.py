@@ -199,3 +199,20 @@ def test_bench_reference_arm_contract():
         assert key in line, key
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_wave_quantised_chunks():
+    """_chunks_by_tokens with a wave quantum: chunks filled to whole waves of 128-row tiles when that needs fewer
+    waves in total than the balanced cut, never more chunks, always complete and within the limit."""
+    import numpy as np
+    from bayeslms_b200.scorer import _chunks_by_tokens
+    rng = np.random.default_rng(0)
+    lens = rng.integers(7, 28, size=12800).tolist()
+    q = 128 * 74
+    base, alt = _chunks_by_tokens(lens, 65536), _chunks_by_tokens(lens, 65536, q)
+    waves = lambda cuts: sum(-(-(-(-sum(lens[a:b]) // 128)) // 74) for a, b in cuts)  # noqa: E731
+    assert alt[0][0] == 0 and alt[-1][1] == len(lens) and all(a[1] == b[0] for a, b in zip(alt, alt[1:]))
+    assert max(sum(lens[a:b]) for a, b in alt) <= 65536 and len(alt) <= len(base)
+    assert waves(alt) <= waves(base)
+    assert all(sum(lens[a:b]) > 6 * q - 28 for a, b in alt[:-1]) or alt == base
+    assert _chunks_by_tokens(lens[:100], 65536, q) == _chunks_by_tokens(lens[:100], 65536)
