@@ -85,7 +85,7 @@ class _Plan:
             self.emb = model.encoder.weight.detach().float().contiguous()
             self.E = self.split(model.decoder.weight)
             self.dec_b = model.decoder.bias.detach().float().contiguous()
-            if model.family == "bayes_lstm":
+            if model.family in ("bayes_lstm", "std_lstm"):
                 self._lstm(model)
             elif model.family in ("gauss_lstm", "v_lstm"):
                 self._cell_lstm(model)
@@ -98,7 +98,7 @@ class _Plan:
         self.layers = []
         for layer in m.transformerlayers:
             a = layer.self_attn
-            L = {"kind": layer.kind}
+            L = {"kind": layer.kind, "mod": layer, "index": len(self.layers)}
             if layer.kind == "bayes_mha":
                 w = torch.cat([a.q_net.weight, a.k_net.weight, a.v_net.weight], 0)
                 b = torch.cat([a.q_net.bias, a.k_net.bias, a.v_net.bias], 0)
@@ -188,6 +188,8 @@ def plan_for(model, prec: str) -> _Plan:
 
 # --------------------------------------------------------------------- sampling
 # tensor ids of the Philox streams (stream_id = tensor_id << 32 | sample index)
+V_NOISE_STD = 0.1          # model.py:2786: normal_(0, 0.1)
+V_NOISE_TID = 32           # Philox stream ids of the V-layer noise: 32 + layer index
 _TID = {"ffn_w2": 1, "mha_o": 2, "embed": 3, "gp_coef": 4, "gp_w": 5, "gp_b": 6,
         "lstm": 16}  # lstm tensors use 16 + index in the reference draw order
 
@@ -224,6 +226,7 @@ class _TmRun:
         self.nhead = model.nhead
         self.M = batch.n_tokens
         self.dev = plan.device
+        self.v_train = None            # (B, T, seed, 0) when the variational layers add their training noise
         self.fused_sampling = False    # True: tile-stationary blm_gemm_sampled (W~ never stored)
         # fast mode default: the sampled FFN weight is drawn inside the GEMM launch (generate-once blm_gemm_sampled);
         # BLM_NO_FUSED_SAMPLING=1 falls back to blm_reparam + blm_gemm (A/B switch, same bits)
@@ -300,6 +303,21 @@ class _TmRun:
         g, b, eps = L["norm2"]
         return ops.layernorm(y, g, b, eps, prec=self.prec)
 
+    def part_d_vnoise(self, L, x1_32, h: Split, w2: Split):
+        """Training-mode variational layer at T = 100 (model.py:2784-2801, oracle position SURVEY.md 8c-1): the FFN
+        output f gets e * exp(f * hiddens_lgstd[t]), e ~ N(0, 0.1^2), before the residual and LayerNorm 2; f and the
+        noise stream are kept on the module for ``kl_divergence()``."""
+        B, T, seed, _ = self.v_train
+        mod = L["mod"]
+        f = self.f32(self.d)
+        ops.gemm(h, w2, prec=self.prec, bias=L["b2"], out_f32=f, tag="ffn2")
+        rho = mod.hiddens_lgstd.detach().view(T, self.d)
+        sid = _stream_id(V_NOISE_TID + L["index"], 0)
+        y = ops.vnoise_fwd(f, rho, B, T, seed=seed, stream_id=sid, noise_std=V_NOISE_STD, resid=x1_32)
+        mod._v_state = {"f": f, "B": B, "T": T, "eps": None, "seed": seed, "stream_id": sid}
+        g, b, eps = L["norm2"]
+        return ops.layernorm(y, g, b, eps, prec=self.prec)
+
     def gp_weights(self, L, sample: Optional[Sample], seed):
         """(w1, b1, coef) of the GP layer for one posterior sample (None = mean)."""
         g = L["gp"]
@@ -342,6 +360,8 @@ class _TmRun:
         else:
             h = carry["h"]
         w2 = L["w2"]
+        if kind == "v" and self.v_train is not None:
+            return self.part_d_vnoise(L, x1_32, h, w2)
         if kind == "bayes_ffn" and sample is not None:
             e = sample.get("layer0") if isinstance(sample, dict) else None
             if self.fused_sampling and self.prec == "bf16":
@@ -472,6 +492,8 @@ def transformer_logits(model, src: torch.Tensor) -> torch.Tensor:
         if _first_sampled_part(model) and not gp_off:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             sample, upto = 0, _first_sampled_part(model)
+        if model.family == "v_tm" and T == 100:   # the variational noise only exists at T = 100 (model.py:2784)
+            run.v_train = (B, T, int(torch.randint(0, 2 ** 62, (1,)).item()), 0)
     xs = run.hidden(run.prefix(upto), upto, sample, seed)
     V = plan.E.hi.shape[0]
     ld = (V + 7) // 8 * 8
@@ -481,6 +503,21 @@ def transformer_logits(model, src: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- KL
+def v_layer_kl(layer) -> torch.Tensor:
+    """KL of one variational Transformer layer from the state its last training-mode forward left on the module
+    (0-dim device tensor)."""
+    st = layer._v_state
+    f, B, T = st["f"], st["B"], st["T"]
+    d = f.shape[1]
+    scratch = torch.empty(2, T, d, dtype=torch.float32, device=f.device)
+    _, klpart = ops.vnoise_bwd(None, f, layer.hiddens_lgstd.detach().view(T, d), layer.hiddens_mean_p.detach().view(T, d),
+                               B, T, 0.0, scratch[0], scratch[1], eps=st["eps"], seed=st["seed"], stream_id=st["stream_id"],
+                               noise_std=V_NOISE_STD)
+    out = torch.zeros(1, dtype=torch.float32, device=f.device)
+    ops.reduce_sum(klpart.view(-1), out, scale=0.5 / (B * T * d))
+    return out[0]
+
+
 def kl_sum(terms, minus_one: bool) -> torch.Tensor:
     """sum_i scale_i * 0.5 * mean(mu_i^2 - 2 rho_i + exp(2 rho_i) [- 1]) as a 0-dim device tensor."""
     dev = terms[0][0].device
@@ -504,7 +541,7 @@ def _lstm_weights(model, plan: _Plan, sample: Optional[Sample], seed):
     """Per-layer (w_ih, w_hh, bias) for one posterior sample: copies of the mean matrices whose
     gate-row block [(p-1)H, pH) is overwritten with mu + exp(lgstd) * eps (model.py:716-725)."""
     r = model.rnn
-    if model.family != "bayes_lstm" or sample is None or not 1 <= r.position <= 4:
+    if model.family != "bayes_lstm" or sample is None or not 1 <= r.position <= 4:   # std_lstm: nothing to sample
         return plan.lstm   # GP / V cells score with their posterior means (eval semantics of the reference)
     rows = r.gate_rows()
     out = []

@@ -5,6 +5,7 @@ only.  All arithmetic is done by :mod:`bayeslms_b200.engine` through the sm_100a
 ``libbayeslm_b200.so``; there is no PyTorch/CPU execution path.
 
 Reference call sites this mirrors (``model.py`` = reference steps/pytorchnn/model.py):
+  RNNModel 23-72; TransformerModel 120-171 (their nn.LSTM / nn.TransformerEncoder state_dict keys);
   BayesRNNModel 179-229 / Bayes2LSTM 585-828; MultiheadAttention 836-928;
   BayesMultiheadAttention 931-1019; StandardTransformerEncoderLayer 1022-1046;
   BayesLinear 1049-1134; BayesTransformerEncoderLayer 1137-1176; BayesTransformerModel
@@ -17,6 +18,7 @@ materialising logits -- which is what :mod:`bayeslms_b200.scorer` uses.
 from __future__ import annotations
 
 import math
+import re
 from typing import Optional
 
 import torch
@@ -193,6 +195,15 @@ class VTransformerEncoderLayer(_EncoderLayer):
         super().__init__(d_model, nhead, dim_feedforward, dropout)
         for name in ("hiddens_mean_p", "hiddens_lgstd_p", "hiddens_mean", "hiddens_lgstd"):
             setattr(self, name, nn.Parameter(torch.rand(100, 1, d_model)))
+        self._v_state = None     # FFN output + noise source of the last training-mode forward (the reference's self.hidden)
+
+    def kl_divergence(self):
+        """mean((h - h * mean_p)^2 - 2 lgstd + exp(2 lgstd)) / 2 on the noised FFN output h of the last training-mode
+        forward at sequence length 100 (model.py:2770-2781; called by train.py:380-395)."""
+        if self._v_state is None:
+            raise RuntimeError("VTransformerEncoderLayer.kl_divergence() needs a training-mode forward at sequence length "
+                               "100 first (the reference reads the hidden it stored there, model.py:2772)")
+        return _engine.v_layer_kl(self)
 
 
 class _TransformerLM(nn.Module):
@@ -298,6 +309,82 @@ class VTransformerModel(_TransformerLM):
         self._finish(ntoken, ninp, dropout, tie_weights)
 
 
+class _ParamView:
+    """(weight, bias) pair presented under the attribute names the engine reads."""
+    __slots__ = ("weight", "bias")
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class _TorchMultiheadAttention(nn.Module):
+    """Parameter container with ``nn.MultiheadAttention``'s keys (in_proj_weight, in_proj_bias, out_proj.*):
+    what ``nn.TransformerEncoderLayer`` puts in a reference ``TransformerModel`` checkpoint (model.py:131-133)."""
+    kind = "mha"
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0):
+        super().__init__()
+        assert embed_dim % num_heads == 0, "embed_dim must be divisible by num_heads"
+        self.embed_dim, self.num_heads, self.dropout = embed_dim, num_heads, float(dropout)
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+    @property
+    def qkv_net(self):
+        return _ParamView(self.in_proj_weight, self.in_proj_bias)
+
+    @property
+    def o_net(self):
+        return self.out_proj
+
+
+class _TorchEncoderLayer(_EncoderLayer):
+    """Post-LN layer with ``nn.TransformerEncoderLayer``'s keys (self_attn.in_proj_*, self_attn.out_proj.*,
+    linear1, linear2, norm1, norm2); activation = exact-erf GELU, the only one the callers pass
+    (score.py:377, train.py:198-201)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1):
+        super().__init__(d_model, nhead, dim_feedforward, dropout, attn_cls=_TorchMultiheadAttention)
+
+
+class _TorchEncoder(nn.Module):
+    """``nn.TransformerEncoder``'s layout: the layers live under ``.layers`` (keys transformerlayers.layers.<i>.*)."""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+    def __iter__(self):
+        return iter(self.layers)
+
+    def __len__(self):
+        return len(self.layers)
+
+    def __getitem__(self, i):
+        return self.layers[i]
+
+
+class TransformerModel(_TransformerLM):
+    """TransformerModel(ntoken, ninp, nhead, nhid, nlayers, dropout, activation, tie_weights) (model.py:120-171):
+    the baseline model of ``--uncertainty none`` (score.py:377, train.py:198-201), a stack of
+    ``nn.TransformerEncoderLayer``s in the reference -- so its checkpoints carry torch's key names, which this
+    container reproduces.  Runs on the same kernels as the standard layers of the Bayesian models."""
+    family = "std_tm"
+
+    def __init__(self, ntoken, ninp, nhead, nhid, nlayers, dropout=0.5, activation="relu", tie_weights=False):
+        super().__init__()
+        if activation != "gelu":
+            raise NotImplementedError("the scorer and the trainer build TransformerModel with activation='gelu' "
+                                      "(score.py:377, train.py:198); relu is not on the B200 path")
+        self.src_mask = None
+        self.pos_encoder = PositionalEncoding(ninp, dropout)
+        self.transformerlayers = _TorchEncoder([_TorchEncoderLayer(ninp, nhead, nhid, dropout) for _ in range(nlayers)])
+        self._finish(ntoken, ninp, dropout, tie_weights)
+
+
 class Bayes2LSTM(nn.Module):
     """Two-layer LSTM whose gate ``position`` (1=i, 2=f, 3=g, 4=o) has Gaussian weights in both layers
     (model.py:585-666).  ``weight_ih_mean_2`` is (4H, input_size) like the reference, i.e. only
@@ -377,6 +464,69 @@ class BayesRNNModel(nn.Module):
 
     def score(self, batch, hidden, **kw):
         return _engine.lstm_score(self, batch, hidden, **kw)
+
+
+class _TorchLSTMParams(nn.Module):
+    """Parameter container with ``nn.LSTM``'s keys (weight_ih_l<k>, weight_hh_l<k>, bias_ih_l<k>, bias_hh_l<k>).
+    The Bayes2LSTM-style names ``<w>_mean_<layer>`` (layer from 1) resolve to the same tensors, so the engine and
+    the trainer treat it as a Bayes2LSTM with no Bayesian gate."""
+    position = 0
+    _ALIAS = re.compile(r"(weight|bias)_(ih|hh)_mean_(\d+)")
+
+    def __init__(self, input_size, hidden_size, num_layers=1, dropout=0.0):
+        super().__init__()
+        self.input_size, self.hidden_size, self.num_layers, self.dropout = input_size, hidden_size, num_layers, float(dropout)
+        H, s = hidden_size, 1.0 / math.sqrt(hidden_size)
+        for l in range(num_layers):
+            setattr(self, f"weight_ih_l{l}", _uniform((4 * H, input_size if l == 0 else H), -s, s))
+            setattr(self, f"weight_hh_l{l}", _uniform((4 * H, H), -s, s))
+            setattr(self, f"bias_ih_l{l}", _uniform((4 * H,), -s, s))
+            setattr(self, f"bias_hh_l{l}", _uniform((4 * H,), -s, s))
+
+    def __getattr__(self, name):
+        m = self._ALIAS.fullmatch(name)
+        if m:
+            return super().__getattr__(f"{m[1]}_{m[2]}_l{int(m[3]) - 1}")
+        return super().__getattr__(name)
+
+    def gate_rows(self):
+        return slice(0, 0)
+
+    def kl_divergence(self, prior=None):
+        return 0
+
+
+class RNNModel(nn.Module):
+    """RNNModel(rnn_type, ntoken, ninp, nhid, nlayers, dropout, tie_weights) (model.py:23-72): the baseline LSTM LM of
+    ``--uncertainty none`` (score.py:413, train.py:204-207) with ``nn.LSTM``'s state_dict keys."""
+    family = "std_lstm"
+
+    def __init__(self, rnn_type, ntoken, ninp, nhid, nlayers, dropout=0.5, tie_weights=False):
+        super().__init__()
+        if rnn_type != "LSTM":
+            raise NotImplementedError("only --model LSTM is on the rescoring path (GRU / RNN_TANH / RNN_RELU are not)")
+        if nlayers != 2:
+            raise NotImplementedError("the recurrence path is laid out for the recipes' two-layer LSTM")
+        self.rnn_type, self.nhid, self.nlayers = rnn_type, nhid, nlayers
+        self.p_drop = float(dropout)
+        self.encoder = nn.Embedding(ntoken, ninp)
+        self.rnn = _TorchLSTMParams(ninp, nhid, nlayers, dropout=dropout)
+        self.decoder = nn.Linear(nhid, ntoken)
+        if tie_weights:
+            if nhid != ninp:
+                raise ValueError("When using the tied flag, nhid must be equal to emsize.")
+            self.decoder.weight = self.encoder.weight
+        nn.init.uniform_(self.encoder.weight, -0.1, 0.1)
+        nn.init.zeros_(self.decoder.bias)
+        nn.init.uniform_(self.decoder.weight, -0.1, 0.1)
+
+    def init_hidden(self, bsz):
+        w = self.encoder.weight
+        return (w.new_zeros(self.nlayers, bsz, self.nhid), w.new_zeros(self.nlayers, bsz, self.nhid))
+
+    def forward(self, x, hidden):
+        """(T, B) int64, (h, c) each (nlayers, B, H) -> logits (T, B, V), (h, c)."""
+        return _engine.lstm_logits(self, x, hidden)
 
 
 class GPLSTMCell(nn.Module):
@@ -513,24 +663,25 @@ def build_model(args, ntokens):
     """The model-selection switch of the scorer / trainer (score.py:374-448, train.py:193-224),
     for the families on the hot path."""
     unc = args.uncertainty
+    tied = getattr(args, "tied", True)     # the scorer ties every model_1 (score.py:377-440); the trainer passes --tied
     if args.model == "Transformer":
-        common = (ntokens, args.emsize, args.nhead, args.nhid, args.nlayers, getattr(args, "dropout", 0.5), True)
+        common = (ntokens, args.emsize, args.nhead, args.nhid, args.nlayers, getattr(args, "dropout", 0.5), tied)
         if unc == "Bayesian":
             return BayesTransformerModel(*common, args.T_bayes_pos)
-        if unc == "none":
-            return BayesTransformerModel(*common, "none")
+        if unc == "none":    # score.py:377, train.py:198: nn.TransformerEncoder keys
+            return TransformerModel(*common[:-1], "gelu", common[-1])
         if unc == "Gaussian":
             return GaussTransformerModel(*common, args.T_gauss_pos)
         if unc == "Variational":
             return VTransformerModel(*common, args.T_v_pos)
     elif args.model == "LSTM":
-        common = ("LSTM", ntokens, args.emsize, args.nhid, args.nlayers, getattr(args, "dropout", 0.5), True)
+        common = ("LSTM", ntokens, args.emsize, args.nhid, args.nlayers, getattr(args, "dropout", 0.5), tied)
         if unc == "Bayesian":
             return BayesRNNModel(*common, args.L_bayes_pos)
-        if unc == "none":
-            return BayesRNNModel(*common, 0)
-        if unc == "Gaussian":   # the scorer builds this family untied (score.py:428)
-            return GaussRNNModel(*common[:-1], False, args.L_gauss_pos)
+        if unc == "none":    # score.py:413, train.py:204: nn.LSTM keys
+            return RNNModel(*common)
+        if unc == "Gaussian":   # the scorer builds this family untied (score.py:428), the trainer with --tied (train.py:219)
+            return GaussRNNModel(*common[:-1], getattr(args, "tied", False), args.L_gauss_pos)
         if unc == "Variational":
             return VariationalRNNModel(*common, args.L_v_pos)
     raise NotImplementedError(f"--model {args.model} --uncertainty {unc} is outside the B200 hot path")

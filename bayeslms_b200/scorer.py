@@ -316,12 +316,37 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
-def load_checkpoint(model, path: str) -> None:
-    """Keep the checkpoint keys the model knows, load the rest from the initialisation (score.py:457-462)."""
+_DERIVED_KEYS = ("pos_encoder.pe",)     # deterministic buffer (model.py:97-103): rebuilt, may be absent from a checkpoint
+
+
+def load_checkpoint(model, path: str, *, partial: bool = False) -> dict:
+    """Load the checkpoint keys the model knows (score.py:457-462).
+
+    The reference intersects silently, which turns a checkpoint of the wrong architecture (e.g. a ``TransformerModel``
+    file given to ``BayesTransformerModel(..., 'none')``) into a randomly initialised model that scores garbage.  Here
+    that is an error: every parameter of the model must come from the file and every tensor of the file must have a
+    home, unless ``partial=True`` -- the deliberate intersect-and-keep-the-rest semantics of ``--prior True``
+    (train.py:239-258), which returns what was left out instead of raising.  Shape mismatches always raise."""
     ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    if not isinstance(ckpt, dict):
+        raise TypeError(f"{path}: expected a state_dict, got {type(ckpt).__name__}")
     own = model.state_dict()
+    missing = [k for k in own if k not in ckpt and k not in _DERIVED_KEYS]
+    unexpected = [k for k in ckpt if k not in own]
+    if (missing or unexpected) and not partial:
+        def show(keys):
+            return ", ".join(keys[:6]) + (f", ... ({len(keys)} in all)" if len(keys) > 6 else "")
+        raise KeyError(f"{path} does not match {type(model).__name__}: "
+                       + (f"the model's {show(missing)} are not in the file; " if missing else "")
+                       + (f"the file's {show(unexpected)} have no place in the model; " if unexpected else "")
+                       + "check --model / --uncertainty / --*_pos against the flags the checkpoint was trained with")
+    for k, v in ckpt.items():
+        if k in own and tuple(v.shape) != tuple(own[k].shape):
+            raise ValueError(f"{path}: {k} has shape {tuple(v.shape)}, the model expects {tuple(own[k].shape)}")
     own.update({k: v for k, v in ckpt.items() if k in own})
     model.load_state_dict(own)
+    model.__dict__.pop("_blm_plans", None)
+    return {"missing": missing, "unexpected": unexpected}
 
 
 def main(argv=None) -> int:

@@ -12,7 +12,9 @@ What is kept from the reference (file:line = steps/pytorchnn/train.py unless not
   * the schedule: save the state_dict when the validation loss improves, otherwise halve the learning rate,
     build a fresh optimiser (momentum reset) and reload the best checkpoint; stop after 8 such reloads
     (:470-512); finally reload the best checkpoint and report the test loss (:518-530);
-  * the CLI flags of :28-100 (``--prior*`` / ``--mark`` pruning are not part of the hot path).
+  * the CLI flags of :28-103, including ``--prior True --prior_path DIR`` (start from DIR/model.pt, keeping the
+    tensors both sides have, :239-258) and the ``--mark base-<frac>set`` corpus pruning (:151-165), so the stage-1
+    command lines of ``run_nnlm_ami_{tm,lstm}.sh`` parse and run unchanged.
 Dropout: the CUDA step has no dropout masks, so ``--dropout`` is accepted and ignored.
 There is no CPU path: the model must live on a B200.
 """
@@ -170,6 +172,14 @@ def fit(model, train_data, val_data, *, lr: float, epochs: int, seq_len: int, cl
     return best, history
 
 
+_MARK_FRACTIONS = {"base-0.5set": 2, "base-0.25set": 4, "base-0.1set": 10, "base-0.05set": 20}
+
+
+def pruned_length(train_len: int, mark: str) -> int:
+    """``--mark``: the data-size experiments train on the leading 1/2, 1/4, 1/10 or 1/20 of the corpus (train.py:151-165)."""
+    return int(train_len / _MARK_FRACTIONS.get(mark, 1))
+
+
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(description="Fine-tune a Bayesian / GP / Variational neural LM on B200.")
     p.add_argument("--data", type=str, default="./data/pytorchnn")
@@ -185,6 +195,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--L_v_pos", type=str, default="11")
     p.add_argument("--T_gauss_pos", type=int, default=3)
     p.add_argument("--T_v_pos", type=str, default="0", help="0..3, or the per-layer bit string 00/01/10/11")
+    p.add_argument("--mark", type=str, default="none",
+                   help="base-0.5set / -0.25set / -0.1set / -0.05set train on that leading fraction (train.py:151-165)")
     p.add_argument("--lr", type=float, default=0.1)
     p.add_argument("--batch-size", type=int, default=20)
     p.add_argument("--epochs", type=int, default=20)
@@ -192,11 +204,19 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--clip", type=float, default=0.25)
     p.add_argument("--dropout", type=float, default=0.2, help="accepted for compatibility; the CUDA step has no dropout")
     p.add_argument("--tied", action="store_true")
+    p.add_argument("--optimizer", type=str, default="SGD", help="parsed like the reference, which builds SGD regardless "
+                                                                 "(train.py:466)")
     p.add_argument("--log-interval", type=int, default=200)
     p.add_argument("--cuda", action="store_true", help="accepted for compatibility: there is no CPU path")
     p.add_argument("--save", type=str, default="model.pt")
     p.add_argument("--seed", type=int, default=1111)
     p.add_argument("--resume", type=str, default="", help="checkpoint to start from (the fine-tuning recipe, README)")
+    p.add_argument("--debug", action="store_true", help="parsed for compatibility (unused by the reference, train.py:94)")
+    p.add_argument("--work_dir", type=str, default="TFM", help="parsed for compatibility (unused, train.py:96)")
+    p.add_argument("--prior", type=str, default="False", help='"True": start from <prior_path>/model.pt (train.py:239-258)')
+    p.add_argument("--prior_path", type=str, default="steps/pytorchnn/prior")
+    p.add_argument("--prior2_path", type=str, default="steps/pytorchnn/prior/transformer2/",
+                   help="parsed for compatibility (unused, train.py:102)")
     p.add_argument("--precision", type=str, default="bf16x3", choices=["bf16", "bf16x3"])
     return p
 
@@ -211,9 +231,15 @@ def main(argv=None) -> int:
     corpus = Corpus(args.data)
     print("train set:", len(corpus.train), "\nvalid set:", len(corpus.valid), "\ntest set:", len(corpus.test),
           "\nnum tokens:", len(corpus))
-    train_data = batchify(corpus.train, args.batch_size, dev)
+    train_data = batchify(corpus.train[:pruned_length(len(corpus.train), args.mark)], args.batch_size, dev)
     val_data, test_data = batchify(corpus.valid, 20, dev), batchify(corpus.test, 20, dev)   # eval_batch_size = 20 (:178)
     net = models.build_model(args, len(corpus))
+    if args.prior == "True":
+        # pre-trained prior: keep the checkpoint tensors the model has, everything else stays as initialised
+        # (a baseline model's means under a Bayesian model's fresh log-sigmas; train.py:239-258)
+        left = load_checkpoint(net, os.path.join(args.prior_path, "model.pt"), partial=True)
+        print(f"prior: {len(left['missing'])} model tensors keep their initialisation, "
+              f"{len(left['unexpected'])} checkpoint tensors unused")
     if args.resume:
         load_checkpoint(net, args.resume)
     net = net.to(dev)

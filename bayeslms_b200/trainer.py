@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 from typing import Dict, Optional
 
 import torch
@@ -73,8 +74,8 @@ def _tbf16(s: Split, prec: str):
     return _T(s) if _MN else ops.transpose_bf16(s, prec)
 
 _TID = engine._TID
-V_NOISE_STD = 0.1          # model.py:2786: normal_(0, 0.1)
-_TID_VNOISE = 32           # Philox stream ids of the V-layer noise: 32 + layer index
+V_NOISE_STD = engine.V_NOISE_STD
+_TID_VNOISE = engine.V_NOISE_TID   # Philox stream ids of the V-layer noise: 32 + layer index
 
 
 class FineTuner:
@@ -82,7 +83,7 @@ class FineTuner:
 
     def __init__(self, model, lr: float, *, momentum: float = 0.9, clip: float = 0.25, prec: str = "bf16x3",
                  group=None):
-        if model.family not in ("bayes_tm", "gauss_tm", "v_tm", "bayes_lstm"):
+        if model.family not in ("bayes_tm", "gauss_tm", "v_tm", "std_tm", "bayes_lstm", "std_lstm"):
             raise NotImplementedError("the fine-tune step is implemented for the Transformer families and the "
                                       "Bayesian / standard two-layer LSTM")
         self.hidden = None
@@ -114,6 +115,12 @@ class FineTuner:
                 self.g[name] = self.flat_g[o:o + n].view(p.shape)
         if model.decoder.weight is model.encoder.weight:
             self.g["decoder.weight"] = self.g["encoder.weight"]
+        # the baseline models keep torch's key names (model.py:23-171); the step addresses gradients by the names of
+        # the Bayesian containers, so alias them
+        for name, t in list(self.g.items()):
+            alias = _engine_name(name)
+            if alias != name:
+                self.g[alias] = t
         # bf16 (hi[, lo]) mirrors of the parameters: written by the optimiser kernel together with the update, so a
         # step splits no weight (21 launches); re-made from scratch whenever a parameter was written from outside
         self.flat_hi = torch.zeros(total, dtype=torch.bfloat16, device=dev)
@@ -184,7 +191,7 @@ class FineTuner:
         LSTM families: ``hidden`` = (h, c) carried in from the previous batch (zeros if None); the state
         after the batch is left in ``self.hidden``."""
         self._check_mirrors()
-        if self.model.family == "bayes_lstm":
+        if self.model.family in ("bayes_lstm", "std_lstm"):
             return self._lstm_forward_backward(tokens_tb, targets_tb, kl_scale, hidden, eps, seed)
         m, prec, dev = self.model, self.prec, self.device
         T, B = tokens_tb.shape
@@ -307,6 +314,8 @@ class FineTuner:
                 y2 = ops.vnoise_fwd(f, rho, B, T, eps=e_bt, seed=seed, stream_id=engine._stream_id(_TID_VNOISE + li, 0),
                                     noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
                 S.update(f=f, v_eps=e_bt)
+                layer._v_state = {"f": f, "B": B, "T": T, "eps": e_bt, "seed": seed,
+                                  "stream_id": engine._stream_id(_TID_VNOISE + li, 0)}
             else:
                 _gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
             x32, xs = ops.layernorm(y2, layer.norm2.weight.detach(), layer.norm2.bias.detach(), layer.norm2.eps, prec=prec)
@@ -739,6 +748,22 @@ class FineTuner:
         cap["g2"].replay()
         self.model.__dict__.pop("_blm_plans", None)
         return cap["out"]
+
+
+_TORCH_TM_KEYS = {"self_attn.in_proj_weight": "self_attn.qkv_net.weight", "self_attn.in_proj_bias": "self_attn.qkv_net.bias",
+                  "self_attn.out_proj.weight": "self_attn.o_net.weight", "self_attn.out_proj.bias": "self_attn.o_net.bias"}
+
+
+def _engine_name(name: str) -> str:
+    """Parameter name of a TransformerModel / RNNModel (torch's nn.TransformerEncoder / nn.LSTM keys) -> the name the
+    same tensor has in the Bayesian containers; other names pass through."""
+    m = re.fullmatch(r"transformerlayers\.layers\.(\d+)\.(.*)", name)
+    if m:
+        return f"transformerlayers.{m[1]}.{_TORCH_TM_KEYS.get(m[2], m[2])}"
+    m = re.fullmatch(r"rnn\.(weight|bias)_(ih|hh)_l(\d+)", name)
+    if m:
+        return f"rnn.{m[1]}_{m[2]}_mean_{int(m[3]) + 1}"
+    return name
 
 
 def _to_device(obj, dev):

@@ -45,9 +45,40 @@ SD = Dict[str, Tensor]
 
 # --------------------------------------------------------------------------- config
 class Config(dict):
-    """family: 'bayes_tm' | 'gauss_tm' | 'v_tm' | 'bayes_lstm' | 'gauss_lstm' | 'v_lstm'; plus ntoken, ninp, nhead,
-    nhid, nlayers and the family's position flag (bayes_pos / gauss_pos / v_pos)."""
+    """family: 'bayes_tm' | 'gauss_tm' | 'v_tm' | 'bayes_lstm' | 'gauss_lstm' | 'v_lstm' | 'std_tm' | 'std_lstm'; plus
+    ntoken, ninp, nhead, nhid, nlayers and the family's position flag (bayes_pos / gauss_pos / v_pos)."""
     __getattr__ = dict.__getitem__
+
+
+_TORCH_TM_KEYS = {"self_attn.in_proj_weight": "self_attn.qkv_net.weight", "self_attn.in_proj_bias": "self_attn.qkv_net.bias",
+                  "self_attn.out_proj.weight": "self_attn.o_net.weight", "self_attn.out_proj.bias": "self_attn.o_net.bias"}
+
+
+def canonical(sd: SD, cfg: Config) -> Tuple[SD, Config]:
+    """The baseline models of ``--uncertainty none`` are torch library modules in the reference: ``TransformerModel``
+    = nn.TransformerEncoder of post-LN nn.TransformerEncoderLayer(activation='gelu') (model.py:131-133),
+    ``RNNModel`` = nn.LSTM (model.py:35).  Their published arithmetic is the one restated below for the reference's
+    own StandardTransformerEncoderLayer (fused in_proj = qkv_net, q scaled by head_dim^-1/2, additive causal mask,
+    softmax, out_proj = o_net, erf GELU, LayerNorm eps 1e-5) and for the Bayesian LSTM at position 0 (gate order
+    i, f, g, o, two biases), so they are evaluated by renaming their keys; pinned by tests/golden/std_{tm,lstm}.pt."""
+    fam = cfg.family
+    if fam == "std_tm":
+        out = {}
+        for k, v in sd.items():
+            if k.startswith("transformerlayers.layers."):
+                i, rest = k[len("transformerlayers.layers."):].split(".", 1)
+                k = f"transformerlayers.{i}.{_TORCH_TM_KEYS.get(rest, rest)}"
+            out[k] = v
+        return out, Config(cfg, family="bayes_tm", bayes_pos="none")
+    if fam == "std_lstm":
+        out = {}
+        for k, v in sd.items():
+            if k.startswith("rnn.") and "_l" in k:
+                name, l = k[4:].rsplit("_l", 1)
+                k = f"rnn.{name}_mean_{int(l) + 1}"
+            out[k] = v
+        return out, Config(cfg, family="bayes_lstm", bayes_pos=0)
+    return sd, cfg
 
 
 def tm_layer_kinds(cfg: Config) -> List[str]:
@@ -194,6 +225,7 @@ def transformer_hidden(sd: SD, tokens: Tensor, cfg: Config, eps: Optional[dict] 
     """Everything of {Bayes,Gauss,V}TransformerModel.forward before the decoder
     (model.py:1274-1304, 2341-2360, 2871-2891).  tokens: (T, B) int64.
     eps: {'layer<i>': noise for layer i, 'embed': noise for the EMB variant}."""
+    sd, cfg = canonical(sd, cfg)
     eps = eps or {}
     T = tokens.shape[0]
     d = cfg.ninp
@@ -258,6 +290,7 @@ def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Conf
     if cfg.family in ("gauss_lstm", "v_lstm"):
         assert not return_hidden_states
         return cell_rnn_forward(sd, tokens, hidden, cfg)
+    sd, cfg = canonical(sd, cfg)
     p = lstm_flat_parameters(sd, cfg.bayes_pos, eps)
     x = F.embedding(tokens, sd["encoder.weight"])
     h0, c0 = hidden
@@ -397,6 +430,8 @@ def kl_v_layer(sd: SD, pre: str, hidden: Tensor) -> Tensor:
 def model_kl(sd: SD, cfg: Config, aux: Optional[dict] = None) -> Tensor:
     """The KL term train.py adds for each family (train.py:335-399)."""
     fam = cfg.family
+    if fam in ("std_tm", "std_lstm"):
+        return torch.zeros(())
     if fam == "bayes_lstm":
         # pos 0 = plain LSTM: train.py only adds the KL under --uncertainty Bayesian, and the reference's
         # kl_divergence raises for position 0 (model.py:757-775 falls into the prior branch with prior=None)

@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("pos", [0, 1, 3, 4])
+@pytest.mark.parametrize("pos", [0, 1, 3, 4, "std"])
 def test_forward_matches_reference_golden(golden, pos):
-    rec = golden(f"bayes_lstm_{pos}.pt")
+    rec = golden("std_lstm.pt" if pos == "std" else f"bayes_lstm_{pos}.pt")   # std = RNNModel (nn.LSTM keys)
     net = load_golden_model(rec, DEV)
     h0 = tuple(t.to(DEV) for t in rec["h0"])
     out, (h, c) = net(rec["x"].to(DEV), h0)

@@ -46,7 +46,7 @@ def test_product_never_imports_oracle():
 
 @pytest.mark.parametrize("name", ["bayes_tm_FFN", "bayes_tm_MHA", "bayes_tm_EMB", "bayes_tm_none", "gauss_tm_0",
                                   "gauss_tm_3", "v_tm_0", "v_tm_1", "v_tm_2", "v_tm_3", "bayes_lstm_0",
-                                  "bayes_lstm_3"])
+                                  "bayes_lstm_3", "std_tm", "std_lstm"])
 def test_state_dict_layout_matches_reference(golden, name):
     from tests.util import build_from_cfg
     rec = golden(name + ".pt")
@@ -57,6 +57,120 @@ def test_state_dict_layout_matches_reference(golden, name):
         assert mine.pop("pos_encoder.pe")[1:] == (1, rec["cfg"]["ninp"])
     assert mine == ref
     net.load_state_dict(rec["state_dict"], strict=False)
+
+
+def test_load_checkpoint_fails_loudly_on_the_wrong_architecture(golden, tmp_path):
+    """A reference TransformerModel checkpoint given to BayesTransformerModel(..., 'none') (different key names) used to
+    load as random init; now it raises, and so does a Bayesian checkpoint given to the wrong --T_bayes_pos."""
+    from bayeslms_b200 import model as M, scorer as S
+    rec = golden("std_tm.pt")
+    c = rec["cfg"]
+    path = str(tmp_path / "std_tm.pt")
+    torch.save(rec["state_dict"], path)
+    good = M.TransformerModel(c["ntoken"], c["ninp"], c["nhead"], c["nhid"], c["nlayers"], 0.5, "gelu", True)
+    assert S.load_checkpoint(good, path) == {"missing": [], "unexpected": []}
+    assert torch.equal(good.transformerlayers[1].self_attn.in_proj_weight,
+                       rec["state_dict"]["transformerlayers.layers.1.self_attn.in_proj_weight"])
+    wrong = M.BayesTransformerModel(c["ntoken"], c["ninp"], c["nhead"], c["nhid"], c["nlayers"], 0.5, True, "none")
+    with pytest.raises(KeyError, match="does not match BayesTransformerModel"):
+        S.load_checkpoint(wrong, path)
+    left = S.load_checkpoint(wrong, path, partial=True)      # --prior semantics: intersect, report the rest
+    assert "transformerlayers.0.linear1.weight" in left["missing"] and left["unexpected"]
+    rec = golden("bayes_tm_FFN.pt")
+    path = str(tmp_path / "ffn.pt")
+    torch.save(rec["state_dict"], path)
+    c = rec["cfg"]
+    with pytest.raises(KeyError):
+        S.load_checkpoint(M.BayesTransformerModel(c["ntoken"], c["ninp"], c["nhead"], c["nhid"], c["nlayers"], 0.5, True, "MHA"), path)
+    bad = dict(rec["state_dict"])
+    bad["decoder.bias"] = bad["decoder.bias"][:-1]
+    torch.save(bad, path)
+    with pytest.raises(ValueError, match="decoder.bias"):
+        S.load_checkpoint(M.BayesTransformerModel(c["ntoken"], c["ninp"], c["nhead"], c["nhid"], c["nlayers"], 0.5, True, "FFN"), path)
+
+
+def _recipe_train_args(script, **env):
+    """The stage-1 ``python steps/pytorchnn/train.py ...`` command line of a run_nnlm_*.sh recipe, with the shell
+    variables it declares at the top (plus ``env``) substituted -- what the reference pipeline really passes."""
+    text = open(script).read()
+    cmd = re.search(r"python steps/pytorchnn/train\.py(.*?)> \$pytorch_path/train\.log", text, flags=re.S).group(1)
+    variables = dict(re.findall(r"^([A-Za-z_0-9]+)=([^\s#]*)", text, flags=re.M))
+    variables.update(env)
+    words = cmd.replace("\\\n", " ").split()
+    out = []
+    for w in words:
+        m = re.fullmatch(r"\$\{?([A-Za-z_0-9]+)\}?", w)
+        out.append(variables.get(m.group(1), "x").strip('"') if m else w)
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/run_nnlm_ami_tm.sh"), reason="needs the reference checkout")
+@pytest.mark.parametrize("script", ["run_nnlm_ami_tm.sh", "run_nnlm_ami_lstm.sh", "run_nnlm_lrs2_tm.sh", "run_nnlm_lrs2_lstm.sh"])
+def test_train_cli_parses_the_recipe_command_lines(script):
+    """run_nnlm_ami_tm.sh:89-110 / run_nnlm_ami_lstm.sh stage 1 pass --prior, --prior_path, --mark, --epoch (a prefix of
+    --epochs), --cuda: the trainer must accept exactly that line."""
+    from bayeslms_b200 import train as T
+    argv = _recipe_train_args(os.path.join("/root/reference", script), data_dir="d", nn_model="m.pt", prior_path="p")
+    assert "--prior" in argv and "--prior_path" in argv and "--tied" in argv
+    args = T.build_parser().parse_args(argv)
+    assert args.epochs == 32 and args.batch_size == 32 and args.clip == 1.0 and args.tied and args.cuda
+    assert args.prior in ("True", "False") and args.prior_path == "p"
+
+
+def test_train_cli_recipe_line_verbatim():
+    """The same check without the reference checkout: the argv of run_nnlm_ami_tm.sh:89-110 with its default variables."""
+    from bayeslms_b200 import train as T
+    argv = ("--data data/pytorchnn_ami+fisher --model Transformer --emsize 512 --nhid 4096 --nlayers 6 --nhead 8 --lr 0.1 "
+            "--dropout 0.2 --seq_len 100 --clip 1.0 --batch-size 32 --epoch 32 --seed 1111 --save exp/m/model.pt "
+            "--prior False --prior_path steps/pytorchnn/prior/transformer --uncertainty Bayesian --T_bayes_pos FFN "
+            "--T_gauss_pos 3 --T_v_pos 0 --tied --cuda").split()
+    a = T.build_parser().parse_args(argv)
+    assert (a.epochs, a.prior, a.prior_path, a.dropout, a.T_bayes_pos) == (32, "False", "steps/pytorchnn/prior/transformer", 0.2, "FFN")
+    argv = ("--data d --model LSTM --emsize 1024 --nhid 1024 --nlayers 2 --nhead 8 --lr 5 --dropout 0.2 --seq_len 100 "
+            "--clip 1.0 --batch-size 32 --epoch 32 --seed 1111 --save m.pt --uncertainty Bayesian --L_bayes_pos 3 "
+            "--L_gauss_pos 00 --L_v_pos 00 --prior True --prior_path steps/pytorchnn/prior/lstm --tied --mark no --cuda").split()
+    a = T.build_parser().parse_args(argv)
+    assert (a.mark, a.prior, a.L_bayes_pos, a.optimizer, a.debug, a.work_dir) == ("no", "True", 3, "SGD", False, "TFM")
+    assert T.pruned_length(1000, "base-0.25set") == 250 and T.pruned_length(1000, "no") == 1000
+
+
+def test_build_model_follows_the_reference_switch():
+    """score.py:374-448 / train.py:193-224: --uncertainty none builds TransformerModel / RNNModel (torch key names)."""
+    import argparse
+    from bayeslms_b200 import model as M
+    ns = argparse.Namespace(model="Transformer", uncertainty="none", emsize=32, nhead=4, nhid=64, nlayers=2)
+    m = M.build_model(ns, 40)
+    assert isinstance(m, M.TransformerModel) and "transformerlayers.layers.1.self_attn.in_proj_weight" in m.state_dict()
+    assert m.decoder.weight is m.encoder.weight          # the scorer ties (score.py:377)
+    ns = argparse.Namespace(model="LSTM", uncertainty="none", emsize=32, nhid=32, nlayers=2, tied=False)
+    m = M.build_model(ns, 40)
+    assert isinstance(m, M.RNNModel) and "rnn.weight_hh_l1" in m.state_dict() and m.decoder.weight is not m.encoder.weight
+    with pytest.raises(NotImplementedError):
+        M.TransformerModel(40, 32, 4, 64, 2, 0.5, "relu", True)
+    with pytest.raises(NotImplementedError):
+        M.RNNModel("GRU", 40, 32, 32, 2)
+
+
+def test_import_model_shim_exposes_the_reference_classes():
+    """with shim/steps/pytorchnn first on the path, ``import model`` gives the reference's
+    class names with their positional constructors (score.py:377-440) -- checked in a fresh interpreter."""
+    import subprocess
+    code = (
+        "import model, torch\n"
+        "m = model.BayesTransformerModel(40, 32, 4, 64, 2, 0.5, True, 'FFN')\n"
+        "assert 'transformerlayers.0.linear2.weight_lgstd' in m.state_dict()\n"
+        "model.TransformerModel(40, 32, 4, 64, 2, 0.5, 'gelu', True); model.RNNModel('LSTM', 40, 32, 32, 2, 0.5, True)\n"
+        "model.BayesRNNModel('LSTM', 40, 32, 32, 2, 0.5, True, 3); model.GaussRNNModel('LSTM', 40, 32, 32, 2, 0.5, False, '31')\n"
+        "model.GaussTransformerModel(40, 32, 4, 64, 2, 0.5, True, 3); model.VTransformerModel(40, 32, 4, 64, 6, 0.5, True, 3)\n"
+        "model.VariationalRNNModel('LSTM', 40, 32, 32, 2, 0.5, True, '11')\n"
+        "assert model.__file__.endswith('shim/steps/pytorchnn/model.py'); print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "shim", "steps", "pytorchnn"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/")
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+    for script in ("compute_sentence_scores_bayes_jianwei.py", "train.py"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "shim", "steps", "pytorchnn", script), "--help"],
+                           capture_output=True, text=True, cwd="/")
+        assert r.returncode == 0 and "--uncertainty" in r.stdout, r.stderr
 
 
 def test_v_pos_normalisation():

@@ -21,6 +21,10 @@ def build_from_cfg(cfg, device=None):
         net = M.GaussRNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, False, cfg["gauss_pos"])
     elif fam == "v_lstm":
         net = M.VariationalRNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, True, cfg["v_pos"])
+    elif fam == "std_tm":
+        net = M.TransformerModel(cfg["ntoken"], cfg["ninp"], cfg["nhead"], cfg["nhid"], cfg["nlayers"], 0.5, "gelu", True)
+    elif fam == "std_lstm":
+        net = M.RNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, True)
     else:
         raise ValueError(fam)
     return net if device is None else net.to(device)
