@@ -74,6 +74,11 @@ class VocabNllDesc(C.Structure):
     ]
 
 
+class DropoutDesc(C.Structure):
+    _fields_ = [("mask", C.c_void_p), ("p", C.c_float), ("reserved", C.c_int32), ("seed", C.c_uint64),
+                ("seed_dev", C.c_void_p), ("stream_id", C.c_uint64)]
+
+
 _p, _i32, _i64, _u64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/bayeslm_b200.h declares
@@ -112,6 +117,11 @@ SIGNATURES = {
     "blm_layernorm_bwd": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
     "blm_mha_causal_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p]),
     "blm_mha_causal_bwd_tc": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _i32, _p, _i64, _p]),
+    "blm_dropout": (C.c_int, [_p, _i64, C.POINTER(DropoutDesc), _p, _p, _p, _p, _p]),
+    "blm_mha_causal_bf16_dropout": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _i32, _i32, C.POINTER(DropoutDesc), _p, _p, _p,
+                                              _i64, _p]),
+    "blm_mha_causal_bwd_tc_dropout": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _i32,
+                                                C.POINTER(DropoutDesc), _p, _i64, _p]),
     "blm_gpmix_dcoef": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p]),
     "blm_vnoise_fwd": (C.c_int, [_p, _p, _p, _i32, _u64, _u64, _f, _p, _i64, _i32, _i32, _p, _p]),
     "blm_vnoise_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _u64, _u64, _f, _i64, _i32, _i32, _f, _p, _p, _p, _p, _p]),

@@ -10,6 +10,7 @@
 // (model.py:906-912) is realised by simply not visiting j > i.
 #include "blm_host.h"
 #include "blm_ptx.cuh"
+#include "blm_philox.cuh"
 
 namespace blm {
 
@@ -251,11 +252,14 @@ __device__ __forceinline__ float ex2f_(float x) {
 constexpr int kMmaAttnHd = 64;
 constexpr int kMmaAttnRowBytes = kMmaAttnHd * 2;  // one q/k/v row of a head: 128 B = 8 chunks of 16 B
 
-template <bool PRECISE, int KV_ROWS>
+// DROP: dropout on the attention probabilities (training, model.py:912-913): P is multiplied by the keep multipliers
+// AFTER the row sum l_i has been taken, so O = (m . P) V with P the full softmax.
+template <bool PRECISE, int KV_ROWS, bool DROP = false>
 __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
     const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, long long ld,
     const int* __restrict__ seq_offsets, long long n_pairs, int nhead, float* __restrict__ out_f32,
-    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
+    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo,
+    DropParams dparams = DropParams{}, int ldm = 0) {
   constexpr int PARTS = PRECISE ? 2 : 1;
   constexpr int WPP = KV_ROWS / 32;  // warps per (hypothesis, head) pair
   constexpr int PPC = 4 / WPP;       // pairs per CTA
@@ -420,6 +424,22 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
             s[mt][nt][e] = pv;
             lrow[mt][e >> 1] += pv;
           }
+        if constexpr (DROP) {
+          const DropParams dr = drop_resolve(dparams);
+          const long long mbase = pair * ldm * ldm;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = qt * 32 + mt * 16 + g + 8 * h;
+              const int j0 = kb * 32 + nt * 8 + 2 * t4;
+              if (nt < nnt && i < T && j0 <= i) {   // (elements with j > i are already zero)
+                const float2 dm = drop_mult2(dr, mbase + static_cast<long long>(i) * ldm + j0);
+                s[mt][nt][2 * h] *= dm.x;
+                s[mt][nt][2 * h + 1] *= dm.y;
+              }
+            }
+        }
       }
     }
     // ---- O += P V
@@ -511,10 +531,13 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
 // MT = m16 tiles per warp: 1 -> eight warps of 16 rows (bf16 mode: <= 128 registers, two CTAs per SM; the precise
 // mode's 129 KB of tiles allow one CTA per SM anyway, so it keeps the full register file): the launch is one wave of
 // nseq * nhead latency-bound CTAs, so warps per CTA are what shortens it.  2 -> four warps of 32 rows.
-template <bool PRECISE, int MT>
-__global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 2 : 1) mha_causal_bwd_mma_kernel(
+// DROP (attention-probability dropout, P' = m . P): dV = P'^T dO, dP = m . (dO V^T), D_i = sum_j P_ij dP_ij,
+// dS = P (dP - D): the multipliers are re-derived from the same mask tensor / Philox stream as in the forward kernel.
+template <bool PRECISE, int MT, bool DROP = false>
+__global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE && !DROP) ? 2 : 1) mha_causal_bwd_mma_kernel(
     const float* __restrict__ qkv, long long ld, const float* __restrict__ dout, long long ldo,
-    const int* __restrict__ seq_offsets, int nhead, float q_scale, float* __restrict__ dqkv, long long ldd) {
+    const int* __restrict__ seq_offsets, int nhead, float q_scale, float* __restrict__ dqkv, long long ldd,
+    DropParams dparams = DropParams{}, int ldm = 0) {
   constexpr int PARTS = PRECISE ? 2 : 1;
   constexpr int RB = 16 * MT;               // rows per warp
   constexpr int NT = 128 / RB * 32;         // threads
@@ -652,6 +675,25 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 
     }
   };
 
+  const DropParams dr = DROP ? drop_resolve(dparams) : dparams;
+  const long long mbase = static_cast<long long>(blockIdx.x) * ldm * ldm;
+  // dP' -> dP = m . dP' on an accumulator block whose rows are queries r0.. and columns keys c0..
+  auto drop_rows = [&](float (&x)[MT][4][4], int r0, int c0, int nmt_, int nnt_) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = r0 + mt * 16 + g + 8 * h;
+          const int j0 = c0 + nt * 8 + 2 * t4;
+          if (mt < nmt_ && nt < nnt_ && i < T && j0 <= i) {
+            const float2 dm = drop_mult2(dr, mbase + static_cast<long long>(i) * ldm + j0);
+            x[mt][nt][2 * h] *= dm.x;
+            x[mt][nt][2 * h + 1] *= dm.y;
+          }
+        }
+  };
   // ================================================================= phase A: query rows of this warp
   const bool active = warp * RB < T;
   const int qt = warp;
@@ -674,6 +716,7 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 
       const int nnt = (jmax - kb * 32) / 8 + 1;
       rows_product(s, 0, qt * RB, 1, kb * 32, nmt, nnt);
       rows_product(dp, 3, qt * RB, 2, kb * 32, nmt, nnt);
+      if constexpr (DROP) drop_rows(dp, qt * RB, kb * 32, nmt, nnt);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         if (mt < nmt) {
@@ -744,6 +787,7 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 
       const int nnt = (jmax - kb * 32) / 8 + 1;
       rows_product(s, 0, qt * RB, 1, kb * 32, nmt, nnt);
       rows_product(dp, 3, qt * RB, 2, kb * 32, nmt, nnt);
+      if constexpr (DROP) drop_rows(dp, qt * RB, kb * 32, nmt, nnt);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -811,8 +855,10 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 
             const int i = ib * 32 + nt * 8 + 2 * t4 + (e & 1);
             const bool ok = j <= i && i < T && nt < nnt && mt < nmt;
             const float pv = ok ? ex2f_(fmaf(st[mt][nt][e], kLog2e, -cm[e & 1])) * cl[e & 1] : 0.0f;
-            st[mt][nt][e] = pv;                                           // P^T
-            dpt[mt][nt][e] = ok ? pv * (dpt[mt][nt][e] - cd[e & 1]) : 0.0f;   // dS^T
+            float dm = 1.0f;
+            if constexpr (DROP) dm = ok ? drop_mult1(dr, mbase + static_cast<long long>(i) * ldm + j) : 0.0f;
+            st[mt][nt][e] = pv * dm;                                           // P'^T = (m . P)^T
+            dpt[mt][nt][e] = ok ? pv * (dm * dpt[mt][nt][e] - cd[e & 1]) : 0.0f;   // dS^T
           }
       }
       acc_product(dv, st, 3, ib * 32, nmt, nnt);    // dV += P^T dO
@@ -870,6 +916,18 @@ int attention_init() {
                                       mma_attn_bwd_smem_bytes<false>()));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       mma_attn_bwd_smem_bytes<true>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<false, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<false>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<false>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<true, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<true>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_mma_kernel<true, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_smem_bytes<true>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_bwd_smem_bytes<false>()));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(mha_causal_bwd_mma_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      mma_attn_bwd_smem_bytes<true>()));
   return BLM_OK;
 }
 
@@ -914,7 +972,25 @@ extern "C" int blm_mha_causal_bf16(const blm_bf16* qkv_hi, const blm_bf16* qkv_l
                                    const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
                                    int32_t max_len, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, int64_t ldo,
                                    blm_stream stream) {
+  return blm_mha_causal_bf16_dropout(qkv_hi, qkv_lo, ld, seq_offsets, nseq, nhead, head_dim, max_len, nullptr, out_f32,
+                                     out_hi, out_lo, ldo, stream);
+}
+
+static bool drop_active(const blm_dropout_desc* d) { return d && (d->mask || d->p > 0.0f); }
+
+extern "C" int blm_mha_causal_bf16_dropout(const blm_bf16* qkv_hi, const blm_bf16* qkv_lo, int64_t ld,
+                                           const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                                           int32_t max_len, const blm_dropout_desc* drop, float* out_f32,
+                                           blm_bf16* out_hi, blm_bf16* out_lo, int64_t ldo, blm_stream stream) {
   using namespace blm;
+  const bool dropping = drop_active(drop);
+  if (dropping) {
+    BLM_REQUIRE(drop->p >= 0.0f && drop->p < 1.0f, BLM_ERR_ARG, "dropout probability %g not in [0, 1)", drop->p);
+    BLM_REQUIRE((reinterpret_cast<uintptr_t>(drop->mask) & 7u) == 0, BLM_ERR_ALIGN, "attention dropout mask must be 8-byte aligned");
+  }
+  const DropParams dpar = dropping ? make_drop_params(drop->mask, drop->p, drop->seed, drop->seed_dev, drop->stream_id)
+                                   : DropParams{};
+  const int ldm = (max_len + 3) & ~3;
   BLM_REQUIRE(qkv_hi && seq_offsets && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention arguments");
   BLM_REQUIRE(head_dim == kMmaAttnHd, BLM_ERR_SHAPE, "the tensor-core attention kernel needs head_dim 64, got %d", head_dim);
   BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
@@ -937,6 +1013,27 @@ extern "C" int blm_mha_causal_bf16(const blm_bf16* qkv_hi, const blm_bf16* qkv_l
   __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
   cudaStream_t st = as_stream(stream);
+  if (dropping) {
+    if (max_len <= 32) {
+      const unsigned blocks = static_cast<unsigned>((pairs + 3) / 4);
+      if (ql)
+        mha_causal_mma_kernel<true, 32, true><<<blocks, 128, mma_attn_smem_bytes<true>(), st>>>(
+            qh, ql, ld, seq_offsets, pairs, nhead, out_f32, oh, ol, ldo, dpar, ldm);
+      else
+        mha_causal_mma_kernel<false, 32, true><<<blocks, 128, mma_attn_smem_bytes<false>(), st>>>(
+            qh, ql, ld, seq_offsets, pairs, nhead, out_f32, oh, ol, ldo, dpar, ldm);
+    } else {
+      const unsigned blocks = static_cast<unsigned>(pairs);
+      if (ql)
+        mha_causal_mma_kernel<true, 128, true><<<blocks, 128, mma_attn_smem_bytes<true>(), st>>>(
+            qh, ql, ld, seq_offsets, pairs, nhead, out_f32, oh, ol, ldo, dpar, ldm);
+      else
+        mha_causal_mma_kernel<false, 128, true><<<blocks, 128, mma_attn_smem_bytes<false>(), st>>>(
+            qh, ql, ld, seq_offsets, pairs, nhead, out_f32, oh, ol, ldo, dpar, ldm);
+    }
+    BLM_CHECK_CUDA(cudaGetLastError());
+    return BLM_OK;
+  }
   if (max_len <= 32) {
     const unsigned blocks = static_cast<unsigned>((pairs + 3) / 4);
     if (ql)
@@ -961,7 +1058,23 @@ extern "C" int blm_mha_causal_bf16(const blm_bf16* qkv_hi, const blm_bf16* qkv_l
 extern "C" int blm_mha_causal_bwd_tc(const float* qkv, int64_t ld, const float* dout, int64_t ldo, const int32_t* seq_offsets,
                                      int64_t nseq, int32_t nhead, int32_t head_dim, int32_t max_len, float q_scale,
                                      int32_t precise, float* dqkv, int64_t ldd, blm_stream stream) {
+  return blm_mha_causal_bwd_tc_dropout(qkv, ld, dout, ldo, seq_offsets, nseq, nhead, head_dim, max_len, q_scale, precise,
+                                       nullptr, dqkv, ldd, stream);
+}
+
+extern "C" int blm_mha_causal_bwd_tc_dropout(const float* qkv, int64_t ld, const float* dout, int64_t ldo,
+                                             const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                                             int32_t max_len, float q_scale, int32_t precise, const blm_dropout_desc* drop,
+                                             float* dqkv, int64_t ldd, blm_stream stream) {
   using namespace blm;
+  const bool dropping = drop_active(drop);
+  if (dropping) {
+    BLM_REQUIRE(drop->p >= 0.0f && drop->p < 1.0f, BLM_ERR_ARG, "dropout probability %g not in [0, 1)", drop->p);
+    BLM_REQUIRE((reinterpret_cast<uintptr_t>(drop->mask) & 7u) == 0, BLM_ERR_ALIGN, "attention dropout mask must be 8-byte aligned");
+  }
+  const DropParams dpar = dropping ? make_drop_params(drop->mask, drop->p, drop->seed, drop->seed_dev, drop->stream_id)
+                                   : DropParams{};
+  const int ldm = (max_len + 3) & ~3;
   BLM_REQUIRE(qkv && dout && seq_offsets && dqkv && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention-backward arguments");
   BLM_REQUIRE(head_dim == kMmaAttnHd, BLM_ERR_SHAPE, "tensor-core attention backward needs head_dim 64, got %d", head_dim);
   BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
@@ -974,6 +1087,16 @@ extern "C" int blm_mha_causal_bwd_tc(const float* qkv, int64_t ld, const float* 
     attr_set = true;
   }
   const unsigned grid = static_cast<unsigned>(nseq * nhead);
+  if (dropping) {
+    if (precise)
+      mha_causal_bwd_mma_kernel<true, 1, true><<<grid, 256, mma_attn_bwd_smem_bytes<true>(), as_stream(stream)>>>(
+          qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd, dpar, ldm);
+    else
+      mha_causal_bwd_mma_kernel<false, 1, true><<<grid, 256, mma_attn_bwd_smem_bytes<false>(), as_stream(stream)>>>(
+          qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd, dpar, ldm);
+    BLM_CHECK_CUDA(cudaGetLastError());
+    return BLM_OK;
+  }
   if (precise)
     mha_causal_bwd_mma_kernel<true, 1><<<grid, 256, mma_attn_bwd_smem_bytes<true>(), as_stream(stream)>>>(
         qkv, ld, dout, ldo, seq_offsets, nhead, q_scale, dqkv, ldd);

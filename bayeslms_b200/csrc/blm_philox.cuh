@@ -79,6 +79,55 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream,
   return o;
 }
 
+// ------------------------------------------------------------------ dropout multipliers
+// Element i: word (i & 3) of Philox counter (i >> 2); kept (multiplier 1/(1-p)) iff word >= thresh = floor(p 2^32).
+struct DropParams {
+  const float* mask;          // explicit multipliers (parity), or null
+  const uint64_t* seed_dev;   // device word added to the key at kernel entry (CUDA-graph replays), or null
+  uint64_t seed, stream;
+  uint32_t thresh;
+  float scale;                // 1 / (1 - p)
+};
+
+// host: C-ABI descriptor -> kernel parameters
+inline DropParams make_drop_params(const float* mask, float p, uint64_t seed, const uint64_t* seed_dev, uint64_t stream) {
+  DropParams d;
+  d.mask = mask;
+  d.seed_dev = seed_dev;
+  d.seed = seed;
+  d.stream = stream;
+  const double t = static_cast<double>(p) * 4294967296.0;
+  d.thresh = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+  d.scale = 1.0f / (1.0f - p);
+  return d;
+}
+
+__device__ __forceinline__ DropParams drop_resolve(DropParams d) {
+  if (d.seed_dev) d.seed += *d.seed_dev;
+  return d;
+}
+
+__device__ __forceinline__ uint4 philox_words4(uint64_t seed, uint64_t stream, uint64_t idx4) {
+  return philox4x32_10(make_uint4(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32),
+                                  static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32)),
+                       make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+}
+
+// multipliers of elements idx, idx + 1 (idx even, both valid) / of element idx
+__device__ __forceinline__ float2 drop_mult2(const DropParams& d, long long idx) {
+  if (d.mask) return make_float2(__ldg(d.mask + idx), __ldg(d.mask + idx + 1));
+  const uint4 w = philox_words4(d.seed, d.stream, static_cast<uint64_t>(idx) >> 2);
+  const uint32_t a = (idx & 2) ? w.z : w.x, b = (idx & 2) ? w.w : w.y;
+  return make_float2(a >= d.thresh ? d.scale : 0.0f, b >= d.thresh ? d.scale : 0.0f);
+}
+__device__ __forceinline__ float drop_mult1(const DropParams& d, long long idx) {
+  if (d.mask) return __ldg(d.mask + idx);
+  const uint4 w = philox_words4(d.seed, d.stream, static_cast<uint64_t>(idx) >> 2);
+  const uint32_t q = static_cast<uint32_t>(idx) & 3u;
+  const uint32_t a = q == 0 ? w.x : q == 1 ? w.y : q == 2 ? w.z : w.w;
+  return a >= d.thresh ? d.scale : 0.0f;
+}
+
 // w = mu + sigma * eps with sigma = exp(lgstd): one definition so the fused and the materialising
 // kernels round identically.
 __device__ __forceinline__ float reparam_value(float mu, float lgstd, float eps) {

@@ -572,6 +572,41 @@ __global__ void vnoise_bwd_kernel(const float* __restrict__ dfp, const float* __
   klpart[idx] = a_kl + static_cast<float>(B) * (e2 - 2.0f * r);
 }
 
+// ------------------------------------------------------------------ dropout (model.py:116, 1039-1045, 218-221)
+// out = x * m (+ resid); m from an explicit multiplier tensor or Philox (blm_philox.cuh: drop_mult*)
+__global__ void dropout_kernel(const float* x, long long n4, DropParams dp, const float* __restrict__ resid,
+                               float* out_f32 /* may alias x */, __nv_bfloat16* __restrict__ out_hi,
+                               __nv_bfloat16* __restrict__ out_lo) {
+  const DropParams d = drop_resolve(dp);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = x ? *(reinterpret_cast<const float4*>(x) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 m;
+    if (d.mask) {
+      m = __ldg(reinterpret_cast<const float4*>(d.mask) + i);
+    } else {
+      const uint4 w = philox_words4(d.seed, d.stream, static_cast<uint64_t>(i));
+      m = make_float4(w.x >= d.thresh ? d.scale : 0.f, w.y >= d.thresh ? d.scale : 0.f,
+                      w.z >= d.thresh ? d.scale : 0.f, w.w >= d.thresh ? d.scale : 0.f);
+    }
+    v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    if (resid) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(resid) + i);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (out_f32) *(reinterpret_cast<float4*>(out_f32) + i) = v;
+    if (out_hi) {
+      const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+      *(reinterpret_cast<uint2*>(out_hi) + i) = make_uint2(h0, h1);
+      if (out_lo) {
+        const uint32_t l0 = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
+        const uint32_t l1 = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
+        *(reinterpret_cast<uint2*>(out_lo) + i) = make_uint2(l0, l1);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ embedding scatter
 __global__ void embed_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ tok, float scale, long long M,
                                  int d, float* __restrict__ dE) {
@@ -942,6 +977,22 @@ int blm_vnoise_bwd(const float* dfp, const float* f, const float* rho, const flo
   vnoise_bwd_kernel<<<(T * d + 127) / 128, 128, 0, as_stream(stream)>>>(dfp, f, rho, mean_p, eps, eps_mode, seed, stream_id,
                                                                       noise_std, static_cast<int>(B), T, d, klc, df, drho,
                                                                       dmean_p, klpart);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_dropout(const float* x, int64_t n, const blm_dropout_desc* drop, const float* resid, float* out_f32,
+                blm_bf16* out_hi, blm_bf16* out_lo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(drop && n > 0 && (n % 4) == 0 && (out_f32 || out_hi), BLM_ERR_ARG, "bad dropout arguments");
+  BLM_REQUIRE(drop->p >= 0.0f && drop->p < 1.0f, BLM_ERR_ARG, "dropout probability %g not in [0, 1)", drop->p);
+  BLM_REQUIRE(!out_lo || out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
+  BLM_REQUIRE(aligned16(x) && aligned16(drop->mask) && aligned16(resid) && aligned16(out_f32) && aligned16(out_hi) &&
+                  aligned16(out_lo), BLM_ERR_ALIGN, "dropout pointers must be 16-byte aligned");
+  const DropParams dp = make_drop_params(drop->mask, drop->p, drop->seed, drop->seed_dev, drop->stream_id);
+  dropout_kernel<<<tgrid(n / 4, 256, 8), 256, 0, as_stream(stream)>>>(x, n / 4, dp, resid, out_f32,
+                                                                       reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                                       reinterpret_cast<__nv_bfloat16*>(out_lo));
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_GELU_FAST, ACT_GPMIX_FAST, ACT_GELU_GRAD, ACT_GPMIX, ACT_GPMIX_GRAD, ACT_NONE, ACT_SOFTMAX_GRAD, EPS_NONE, EPS_PHILOX,
-                   EPS_PTR, GemmDesc, GemmLnDesc, GemmSampledDesc,
+                   EPS_PTR, DropoutDesc, GemmDesc, GemmLnDesc, GemmSampledDesc,
                    VocabNllDesc,
                    check, lib)
 
@@ -403,9 +403,59 @@ def mha_causal(qkv: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len
     return o, s
 
 
+@dataclass
+class Drop:
+    """One dropout site of the fine-tune step: drop probability ``p`` and where the keep multipliers (0 or 1/(1-p)) come
+    from -- an explicit fp32 tensor ``mask`` (parity with masks injected into the oracle) or Philox(seed + *seed_dev,
+    stream_id) on the device.  ``seed_dev``: a device int64 [1] added to the key, so captured graphs replay with fresh
+    masks."""
+    p: float
+    mask: Optional[torch.Tensor] = None
+    seed: int = 0
+    stream_id: int = 0
+    seed_dev: Optional[torch.Tensor] = None
+
+    def desc(self) -> DropoutDesc:
+        d = DropoutDesc()
+        if self.mask is not None:
+            assert self.mask.dtype == torch.float32 and self.mask.is_contiguous() and self.mask.is_cuda
+            d.mask = self.mask.data_ptr()
+        d.p, d.seed, d.stream_id = float(self.p), int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(self.stream_id)
+        if self.seed_dev is not None:
+            assert self.seed_dev.dtype == torch.int64 and self.seed_dev.is_cuda
+            d.seed_dev = self.seed_dev.data_ptr()
+        return d
+
+
+def dropout(x: Optional[torch.Tensor], drop: Drop, *, resid: Optional[torch.Tensor] = None, prec: Optional[str] = None,
+            want_f32: bool = True, out_f32: Optional[torch.Tensor] = None, n: Optional[int] = None, device=None):
+    """``x * m (+ resid)`` with the multipliers of ``drop``; returns (fp32 or None, Split or None).  ``prec`` asks for
+    the bf16 (hi[, lo]) copy as well; ``x=None`` with ``n`` exports the multipliers themselves."""
+    if x is not None:
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        n, device, shape = x.numel(), x.device, x.shape
+    else:
+        shape = (n,)
+    if drop.mask is not None:
+        assert drop.mask.numel() == n
+    if resid is not None:
+        assert resid.dtype == torch.float32 and resid.is_contiguous() and resid.numel() == n
+    y = out_f32 if out_f32 is not None else (torch.empty(shape, dtype=torch.float32, device=device) if want_f32 else None)
+    sp = None
+    if prec is not None:
+        sp = Split(torch.empty(shape, dtype=torch.bfloat16, device=device),
+                   torch.empty(shape, dtype=torch.bfloat16, device=device) if prec == "bf16x3" else None)
+    d = drop.desc()
+    with _op("dropout", 1):
+        check(lib().blm_dropout(_ptr(x), n, C.byref(d), _ptr(resid), _ptr(y), _ptr(None if sp is None else sp.hi),
+                                _ptr(None if sp is None else sp.lo), _stream()), "blm_dropout")
+    return y, sp
+
+
 def mha_causal_bf16(qkv: Split, seq_offsets: torch.Tensor, nhead: int, max_len: int, *, prec: str = "bf16",
-                    want_f32: bool = False):
-    """Causal attention on the bf16 (hi[, lo]) output of the QKV projection (tensor-core kernel)."""
+                    want_f32: bool = False, drop: Optional[Drop] = None):
+    """Causal attention on the bf16 (hi[, lo]) output of the QKV projection (tensor-core kernel).  ``drop``: dropout
+    on the attention probabilities (mask layout [n_seq * nhead, L, L], L = max_len rounded up to 4)."""
     M, d3 = qkv.hi.shape
     d = d3 // 3
     nseq = seq_offsets.numel() - 1
@@ -416,9 +466,15 @@ def mha_causal_bf16(qkv: Split, seq_offsets: torch.Tensor, nhead: int, max_len: 
     o = torch.empty(M, d, dtype=torch.float32, device=qkv.hi.device) if want_f32 else None
     s = empty_split(M, d, prec, qkv.hi.device)
     with _op("mha_causal", 1, 0.0):
-        check(lib().blm_mha_causal_bf16(_ptr(qkv.hi), _ptr(lo), qkv.hi.stride(0), _ptr(seq_offsets), nseq, nhead,
-                                        d // nhead, max_len, _ptr(o), _ptr(s.hi), _ptr(s.lo), d, _stream()),
-              "blm_mha_causal_bf16")
+        if drop is not None:
+            dd = drop.desc()
+            check(lib().blm_mha_causal_bf16_dropout(_ptr(qkv.hi), _ptr(lo), qkv.hi.stride(0), _ptr(seq_offsets), nseq, nhead,
+                                                    d // nhead, max_len, C.byref(dd), _ptr(o), _ptr(s.hi), _ptr(s.lo), d,
+                                                    _stream()), "blm_mha_causal_bf16_dropout")
+        else:
+            check(lib().blm_mha_causal_bf16(_ptr(qkv.hi), _ptr(lo), qkv.hi.stride(0), _ptr(seq_offsets), nseq, nhead,
+                                            d // nhead, max_len, _ptr(o), _ptr(s.hi), _ptr(s.lo), d, _stream()),
+                  "blm_mha_causal_bf16")
     return o, s
 
 
@@ -570,12 +626,22 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: f
 
 
 def mha_causal_bwd(qkv: torch.Tensor, dout: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len: int,
-                   q_scale: float, prec: Optional[str] = None) -> torch.Tensor:
+                   q_scale: float, prec: Optional[str] = None, drop: Optional[Drop] = None) -> torch.Tensor:
     """Gradient of the causal attention w.r.t. the (q-scaled) qkv projection.  ``prec`` = "bf16" / "bf16x3" selects
     the tensor-core kernel (head_dim 64); None (or BLM_ATTN_BWD_SIMT=1) the fp32 SIMT kernel."""
     M, d3 = qkv.shape
     d = d3 // 3
     dqkv = torch.empty_like(qkv)
+    if drop is not None:
+        if prec is None or d // nhead != 64 or max_len > 128:
+            raise _lib.BlmError("attention dropout runs on the tensor-core kernels (head_dim 64, length <= 128)")
+        dd = drop.desc()
+        with _op("mha_causal_bwd", 1):
+            check(lib().blm_mha_causal_bwd_tc_dropout(_ptr(qkv), qkv.stride(0), _ptr(dout), dout.stride(0), _ptr(seq_offsets),
+                                                      seq_offsets.numel() - 1, nhead, 64, max_len, q_scale,
+                                                      int(prec == "bf16x3"), C.byref(dd), _ptr(dqkv), dqkv.stride(0),
+                                                      _stream()), "blm_mha_causal_bwd_tc_dropout")
+        return dqkv
     if prec is not None and d // nhead == 64 and max_len <= 128 and os.environ.get("BLM_ATTN_BWD_SIMT") is None:
         with _op("mha_causal_bwd", 1):
             check(lib().blm_mha_causal_bwd_tc(_ptr(qkv), qkv.stride(0), _ptr(dout), dout.stride(0), _ptr(seq_offsets),

@@ -15,7 +15,8 @@ What is kept from the reference (file:line = steps/pytorchnn/train.py unless not
   * the CLI flags of :28-103, including ``--prior True --prior_path DIR`` (start from DIR/model.pt, keeping the
     tensors both sides have, :239-258) and the ``--mark base-<frac>set`` corpus pruning (:151-165), so the stage-1
     command lines of ``run_nnlm_ami_{tm,lstm}.sh`` parse and run unchanged.
-Dropout: the CUDA step has no dropout masks, so ``--dropout`` is accepted and ignored.
+  * ``--dropout`` is the reference's: the step draws Philox keep masks at every nn.Dropout site of the training
+    forward (bayeslms_b200.trainer), seeded per (seed, epoch, batch).
 There is no CPU path: the model must live on a B200.
 """
 from __future__ import annotations
@@ -97,21 +98,26 @@ def evaluate(model, source: torch.Tensor, seq_len: int, prec: str = "bf16x3") ->
 # ------------------------------------------------------------------ one epoch (train.py:306-438)
 def train_epoch(ft, train_data: torch.Tensor, seq_len: int, epoch: int, *, log_interval: int = 200,
                 seed: int = 1111, log=print) -> float:
-    """One pass over ``train_data`` with the CUDA fine-tune step; returns the mean CE of the epoch."""
+    """One pass over ``train_data`` with the CUDA fine-tune step; returns the mean loss (CE + scaled KL, the quantity
+    train.py:422-431 accumulates and logs) of the epoch."""
     model = ft.model
     model.train()
     kl_scale = float(seq_len) / len(train_data)          # kl / len(train_data) * seq_len, train.py:338
     is_rnn = model.family.endswith("lstm")
+    if model.family == "v_tm" and getattr(model, "v_pos", 0) and seq_len != 100:
+        raise ValueError(f"--seq_len {seq_len}: the variational Transformer layers carry (100, 1, d) parameters and only "
+                         "exist at sequence length 100 (model.py:2754-2761, 2784); the reference's KL raises here too")
     hidden = None                                        # zeros at the start of every epoch (train.py:314)
     tot = torch.zeros((), dtype=torch.float64, device=train_data.device)
+    tot_kl = torch.zeros((), dtype=torch.float64, device=train_data.device)
     n_since, n_batches, t0 = 0, 0, time.time()
     for batch, i in enumerate(range(0, train_data.size(0) - 1, seq_len)):
         data, targets = get_batch(train_data, i, seq_len)
-        if model.family == "v_tm" and data.size(0) != 100:
-            continue     # the variational layers only exist at T = 100 (model.py:2784; the reference's KL raises here)
+        if model.family == "v_tm" and getattr(model, "v_pos", 0) and data.size(0) != 100:
+            continue     # ragged last batch: the variational layers only exist at T = 100 (model.py:2784)
         step_seed = (seed * 1000003 + epoch * 100003 + batch) & 0x7FFFFFFFFFFF
         if is_rnn:
-            _, ce, _ = ft.step(data, targets, kl_scale, seed=step_seed, hidden=hidden)
+            loss, _, kl = ft.step(data, targets, kl_scale, seed=step_seed, hidden=hidden)
             hidden = ft.hidden                           # detached by construction (train.py:320)
         elif data.size(0) == seq_len and _USE_GRAPHS:
             # full-size batches replay the step as two CUDA graphs (~250 small launches otherwise); the graphs bake
@@ -121,18 +127,22 @@ def train_epoch(ft, train_data: torch.Tensor, seq_len: int, epoch: int, *, log_i
             if cap is None or cap.get("key") != key:
                 ft.capture(data.size(0), data.size(1), kl_scale)
                 ft._cap["key"] = key
-            _, ce, _ = ft.step_captured(data, targets, step_seed)
+            loss, _, kl = ft.step_captured(data, targets, step_seed)
         else:
-            _, ce, _ = ft.step(data, targets, kl_scale, seed=step_seed)
-        tot += ce.double()
+            loss, _, kl = ft.step(data, targets, kl_scale, seed=step_seed)
+        tot += loss.double()
+        tot_kl += kl.double() * kl_scale
         n_since += 1
         n_batches += 1
         if log_interval and batch % log_interval == 0 and batch > 0:
             cur = float(tot) / n_batches
             log(f"| epoch {epoch:3d} | {batch:5d}/{len(train_data) // seq_len:5d} batches | lr {ft.lr:02.4f} | "
-                f"ms/batch {(time.time() - t0) * 1000 / n_since:5.2f} | loss {cur:5.2f} | ppl {math.exp(min(cur, 50)):8.2f}")
+                f"ms/batch {(time.time() - t0) * 1000 / n_since:5.2f} | loss {cur:5.2f} | "
+                f"kl_loss {float(tot_kl) / n_batches:5.4f} | ppl {math.exp(min(cur, 50)):8.2f}")
             n_since, t0 = 0, time.time()
-    return float(tot) / max(n_batches, 1)
+    if n_batches == 0:
+        raise RuntimeError(f"the epoch ran no step: {train_data.size(0)} rows of training data at --seq_len {seq_len}")
+    return float(tot) / n_batches
 
 
 # ------------------------------------------------------------------ schedule (train.py:464-512)
@@ -202,7 +212,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--epochs", type=int, default=20)
     p.add_argument("--seq_len", type=int, default=35)
     p.add_argument("--clip", type=float, default=0.25)
-    p.add_argument("--dropout", type=float, default=0.2, help="accepted for compatibility; the CUDA step has no dropout")
+    p.add_argument("--dropout", type=float, default=0.2, help="dropout applied to layers (train.py:75)")
     p.add_argument("--tied", action="store_true")
     p.add_argument("--optimizer", type=str, default="SGD", help="parsed like the reference, which builds SGD regardless "
                                                                  "(train.py:466)")

@@ -17,8 +17,12 @@ How the work is laid out on the GPU
   * parameters, gradients and momentum live in three flat fp32 buffers: one reduction gives the global
     gradient norm, one kernel applies clip + momentum + update, and data-parallel training needs a single
     NCCL all-reduce of the gradient buffer (replicated weights, batch sharded over ranks).
-Dropout: the reference trains with dropout; masks are not reproduced here -- the step is the p = 0 step
-(what the parity tests compare against).  Noise is injected (``eps``) or Philox (``seed``).
+Dropout (train.py:75, model.py:116,913,1039-1045,218-221): every nn.Dropout of the reference's training forward is
+applied -- embedding + positional output, attention probabilities (inside the attention kernels, forward and
+backward), the two residual branches and the FFN activation of every layer (layer 0 of the Bayesian FFN / MHA models
+with the hard-coded 0.2 of model.py:1202,1207), and the LSTM's input / output.  Keep masks are Philox(seed, site,
+element) on the device, re-derived in the backward pass, or injected multiplier tensors (``masks``, the oracle's
+layout) for parity.  Noise is injected (``eps``) or Philox (``seed``).
 """
 from __future__ import annotations
 
@@ -74,6 +78,9 @@ def _tbf16(s: Split, prec: str):
     return _T(s) if _MN else ops.transpose_bf16(s, prec)
 
 _TID = engine._TID
+# Philox streams of the dropout sites: embedding / positional output, LSTM input and output, then four per layer
+_TID_DROP_PE, _TID_DROP_EMB, _TID_DROP_OUT, _TID_DROP_LAYER = 48, 49, 50, 64
+_DROP_SITES = {"attn": 0, "d1": 1, "ffn": 2, "d2": 3}
 V_NOISE_STD = engine.V_NOISE_STD
 _TID_VNOISE = engine.V_NOISE_TID   # Philox stream ids of the V-layer noise: 32 + layer index
 
@@ -82,16 +89,24 @@ class FineTuner:
     """Owns the flat parameter / gradient / momentum buffers of ``model`` and runs training steps."""
 
     def __init__(self, model, lr: float, *, momentum: float = 0.9, clip: float = 0.25, prec: str = "bf16x3",
-                 group=None):
+                 group=None, data_parallel: Optional[bool] = None):
         if model.family not in ("bayes_tm", "gauss_tm", "v_tm", "std_tm", "bayes_lstm", "std_lstm"):
             raise NotImplementedError("the fine-tune step is implemented for the Transformer families and the "
                                       "Bayesian / standard two-layer LSTM")
         self.hidden = None
         self.model, self.lr, self.momentum, self.clip, self.prec = model, float(lr), float(momentum), float(clip), prec
         self.group = group
-        self.world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        self.world, self.rank = 1, 0
+        dist_up = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if data_parallel is None:
+            data_parallel = group is not None or dist_up     # default: data parallel whenever a process group exists
+        if data_parallel:
+            if not dist_up:
+                raise _lib.BlmError("data_parallel=True needs an initialised torch.distributed process group")
             self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+        self._drop = None          # per-step dropout state, see _begin_dropout
+        self._seed_dev = None      # device int64 [1] added to the dropout key inside captured graphs
         named = list(model.named_parameters())          # tied encoder / decoder weight appears once
         dev = named[0][1].device
         if dev.type != "cuda":
@@ -181,16 +196,69 @@ class FineTuner:
         """out[N, K] = dY^T X, both operands given transposed ([N, M] and [K, M])."""
         _gemm(dy_t, x_t, prec=self.prec, out_f32=out, tag="wgrad:" + tag)
 
+    def _static_noise(self, e, what: str):
+        """While a CUDA graph is being captured every sampled tensor must read its noise from a static buffer that
+        step_captured() refills: a missing one would silently train on the posterior mean."""
+        if e is None and getattr(self, "_capturing", False):
+            raise _lib.BlmError(f"capture(): no static noise buffer for the sampled tensor {what}")
+        return e
+
+    # ------------------------------------------------------------------ dropout sites
+    def _begin_dropout(self, masks, seed, layout: str = "tbd"):
+        """Dropout of this step: injected multiplier tensors (``masks``, oracle layout), else Philox keyed by ``seed``
+        (or by the device seed word while a graph is being captured); off when neither is given."""
+        if masks is not None:
+            self._drop = {"masks": _to_device(masks, self.device), "seed": None, "layout": layout}
+        elif getattr(self, "_capturing", False):
+            self._drop = {"masks": None, "seed": 0, "seed_dev": self._seed_dev}
+        elif seed is not None:
+            self._drop = {"masks": None, "seed": int(seed), "seed_dev": None}
+        else:
+            self._drop = None
+
+    def _site(self, p: float, tid: int, key=None, rows=None) -> Optional[ops.Drop]:
+        """The dropout of one site, or None when it is the identity.  ``key``: path into the injected masks;
+        ``rows`` = (T, B) re-orders an injected (T, B, w) mask to this step's sequence-major rows."""
+        st = self._drop
+        if st is None:
+            return None
+        if st["masks"] is not None:
+            m = st["masks"]
+            for k in key:
+                m = m.get(k) if isinstance(m, dict) else None
+                if m is None:
+                    return None
+            if rows is not None and st["layout"] == "tbd":
+                T, B = rows
+                m = m.view(T, B, -1).permute(1, 0, 2)
+            return ops.Drop(p, mask=m.contiguous())
+        if p <= 0.0:
+            return None
+        # per-activation noise: the rank is part of the stream, so data-parallel shards draw different masks
+        return ops.Drop(p, seed=st["seed"], stream_id=engine._stream_id(tid, self.rank), seed_dev=st.get("seed_dev"))
+
+    def _layer_site(self, layer, li: int, name: str, rows=None) -> Optional[ops.Drop]:
+        dr = self._site(layer.p_drop, _TID_DROP_LAYER + 4 * li + _DROP_SITES[name], (f"layer{li}", name), rows)
+        if name == "attn" and dr is not None and dr.mask is not None and dr.mask.shape[-1] % 4:
+            # the attention kernels index their [pairs, L, L] multipliers with L = T rounded up to a multiple of 4
+            pad = -dr.mask.shape[-1] % 4
+            dr.mask = torch.nn.functional.pad(dr.mask, (0, pad, 0, pad)).contiguous()
+        return dr
+
     # ------------------------------------------------------------------ one step
     def forward_backward(self, tokens_tb: torch.Tensor, targets_tb: torch.Tensor, kl_scale: float, *,
                          eps: Optional[dict] = None, seed: Optional[int] = None, v_eps_layout: str = "tbd",
-                         hidden=None, on_layer_done=None):
+                         hidden=None, on_layer_done=None, masks: Optional[dict] = None):
         """Fills the gradient buffer for the batch (T, B); returns (loss, ce, kl) as 0-dim device tensors.
         ``eps``: injected noise in the oracle's layout ({'layer<i>': ...}; V layers: (T, B, d) tensors
         already scaled by 0.1, or (B, T, d) with ``v_eps_layout="btd"``); ``seed``: Philox noise instead.
         LSTM families: ``hidden`` = (h, c) carried in from the previous batch (zeros if None); the state
-        after the batch is left in ``self.hidden``."""
+        after the batch is left in ``self.hidden``.
+        Dropout follows the modules' probabilities: Philox masks keyed by ``seed``, or ``masks`` = injected multiplier
+        tensors in the oracle's layout ({'pe': (T,B,d), 'layer<i>': {'attn': (B*nhead,T,T), 'd1','ffn','d2': (T,B,.)}};
+        LSTM: {'emb','out'}); with neither (``eps``-only parity calls) the step runs without dropout."""
         self._check_mirrors()
+        self._begin_dropout(masks, seed)
         if self.model.family in ("bayes_lstm", "std_lstm"):
             return self._lstm_forward_backward(tokens_tb, targets_tb, kl_scale, hidden, eps, seed)
         m, prec, dev = self.model, self.prec, self.device
@@ -216,7 +284,7 @@ class FineTuner:
             # x = (E[tok] sqrt(d)) W~^T + pe with W~ = embed_mean + exp(embed_lgstd) eps (model.py:1284-1293)
             _, x0s = ops.embed(tok, None, m.encoder.weight.detach().float(), None, math.sqrt(d), prec=prec, want_f32=False)
             pe_rows, _ = ops.embed(pos, None, pe, None, 1.0, prec="bf16", want_f32=True)
-            ee = eps.get("embed")
+            ee = self._static_noise(eps.get("embed"), "embed_mean")
             sampled = ee is not None or seed is not None
             w_in32 = (self._reparam32(m.embed_mean.detach(), m.embed_lgstd.detach(), _TID["embed"], ee, seed)
                       if sampled else m.embed_mean.detach())
@@ -227,6 +295,9 @@ class FineTuner:
             E_in = {"x0s": x0s, "w_in_t": w_in_t, "eps": ee, "sampled": sampled}
         else:
             x32, xs = ops.embed(tok, pos, m.encoder.weight.detach().float(), pe, math.sqrt(d), prec=prec)
+        drop_pe = self._site(m.pos_encoder.p, _TID_DROP_PE, ("pe",), (T, B))      # PositionalEncoding.dropout, model.py:116
+        if drop_pe is not None:
+            x32, xs = ops.dropout(x32, drop_pe, prec=prec, out_f32=x32)
         saved = []
         for li, layer in enumerate(m.transformerlayers):
             kind, pre = layer.kind, f"transformerlayers.{li}."
@@ -237,7 +308,7 @@ class FineTuner:
             if kind == "bayes_mha":   # separate q / k / v projections, Bayesian bias-free o_net (model.py:931-1019)
                 wqkv32 = torch.cat([a.q_net.weight.detach(), a.k_net.weight.detach(), a.v_net.weight.detach()], 0)
                 bqkv = torch.cat([a.q_net.bias.detach(), a.k_net.bias.detach(), a.v_net.bias.detach()], 0)
-                le = eps.get(f"layer{li}")
+                le = self._static_noise(eps.get(f"layer{li}"), pre + "self_attn.o_net.weight")
                 S["wo_eps"], S["wo_sampled"] = le, (le is not None or seed is not None)
                 wo32 = (self._reparam32(a.o_net.weight_mean.detach(), a.o_net.weight_lgstd.detach(), _TID["mha_o"], le, seed)
                         if S["wo_sampled"] else a.o_net.weight_mean.detach())
@@ -247,10 +318,17 @@ class FineTuner:
             wqkv, S["wqkv_t"] = self._w2(wqkv32)
             _gemm(xs, wqkv, prec=prec, bias=bqkv, col_scale=scale_q,
                      col_scale_cols=d, out_f32=qkv32, out=qkvs, tag="qkv")
-            _, atts = ops.mha_causal_bf16(qkvs, offs, nhead, T, prec=prec)
+            S["drop_attn"] = self._layer_site(layer, li, "attn")                 # on the probabilities, model.py:913
+            _, atts = ops.mha_causal_bf16(qkvs, offs, nhead, T, prec=prec, drop=S["drop_attn"])
             y1 = self._f32(M, d)
             wo, S["wo_t"] = self._w2(wo32)
-            _gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net")
+            S["drop_d1"] = self._layer_site(layer, li, "d1", (T, B))              # dropout1, model.py:1039
+            if S["drop_d1"] is not None:
+                o32 = self._f32(M, d)
+                _gemm(atts, wo, prec=prec, bias=bo, out_f32=o32, tag="o_net")
+                ops.dropout(o32, S["drop_d1"], resid=x32, out_f32=y1)
+            else:
+                _gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net")
             x1_32, x1s = ops.layernorm(y1, layer.norm1.weight.detach(), layer.norm1.bias.detach(), layer.norm1.eps, prec=prec)
             S.update(qkv32=qkv32, atts=atts, y1=y1, x1_32=x1_32, x1s=x1s)
             # first FFN projection (+ GELU or the GP mixture), pre-activation kept
@@ -259,7 +337,7 @@ class FineTuner:
             hs = ops.empty_split(M, F, prec, dev)
             if kind == "gauss":
                 gp = layer.gpnn
-                le = eps.get(f"layer{li}") if gp.sample else None
+                le = self._static_noise(eps.get(f"layer{li}"), pre + "gpnn") if gp.sample else None
                 use_noise = gp.sample and (le is not None or seed is not None)
                 w1_32, b1, coef = gp.weights_mean.detach(), gp.bias_mean.detach(), gp.coef_mean.detach()
                 S["gp_noise"] = use_noise
@@ -273,17 +351,22 @@ class FineTuner:
                         b1 = self._reparam32(gp.bias_mean.detach(), gp.bias_lgstd.detach(), _TID["gp_b"], ge("bias"), seed)
                 coef = coef.contiguous()
                 w1, S["w1_t"] = self._w2(w1_32)
-                _gemm(x1s, w1, prec=prec, bias=b1, act=ACT_GPMIX, coef=coef, out=hs, out_pre=z1, tag="ffn1")
-                S["coef"] = coef
+                act1, bias1, S["coef"] = ACT_GPMIX, b1, coef
             else:
                 w1_32 = layer.linear1.weight.detach()
                 w1, S["w1_t"] = self._w2(w1_32)
-                _gemm(x1s, w1, prec=prec, bias=layer.linear1.bias.detach(), act=ACT_GELU, out=hs, out_pre=z1,
-                         tag="ffn1")
+                act1, bias1, coef = ACT_GELU, layer.linear1.bias.detach(), None
+            S["drop_ffn"] = self._layer_site(layer, li, "ffn", (T, B))            # dropout on the activation, model.py:1043
+            if S["drop_ffn"] is not None:
+                h32 = self._f32(M, F)
+                _gemm(x1s, w1, prec=prec, bias=bias1, act=act1, coef=coef, out_f32=h32, out_pre=z1, tag="ffn1")
+                _, hs = ops.dropout(h32, S["drop_ffn"], prec=prec, want_f32=False)
+            else:
+                _gemm(x1s, w1, prec=prec, bias=bias1, act=act1, coef=coef, out=hs, out_pre=z1, tag="ffn1")
             S.update(z1=z1, hs=hs)
             # second FFN projection
             if kind == "bayes_ffn":
-                le = eps.get(f"layer{li}")
+                le = self._static_noise(eps.get(f"layer{li}"), pre + "linear2.weight")
                 S["w2_eps"] = le
                 if le is not None or seed is not None:
                     w2_32 = self._reparam32(layer.linear2.weight_mean.detach(), layer.linear2.weight_lgstd.detach(),
@@ -303,7 +386,7 @@ class FineTuner:
                                         "(its parameters are (100, 1, d), model.py:2754-2761)")
                 f = self._f32(M, d)
                 _gemm(hs, w2, prec=prec, bias=b2, out_f32=f, tag="ffn2")
-                le = eps.get(f"layer{li}")
+                le = self._static_noise(eps.get(f"layer{li}"), pre + "hiddens")
                 if le is None:
                     e_bt = None
                 elif v_eps_layout == "btd":
@@ -311,13 +394,24 @@ class FineTuner:
                 else:
                     e_bt = le.permute(1, 0, 2).contiguous().view(M, d)
                 rho = layer.hiddens_lgstd.detach().view(T, d)
-                y2 = ops.vnoise_fwd(f, rho, B, T, eps=e_bt, seed=seed, stream_id=engine._stream_id(_TID_VNOISE + li, 0),
-                                    noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
+                S["drop_d2"] = self._layer_site(layer, li, "d2", (T, B))         # dropout2 AFTER the noise, model.py:2801-2803
+                S["v_stream"] = engine._stream_id(_TID_VNOISE + li, self.rank)   # per-token noise: differs per DP rank
+                if S["drop_d2"] is not None:
+                    fp = ops.vnoise_fwd(f, rho, B, T, eps=e_bt, seed=seed, stream_id=S["v_stream"], noise_std=V_NOISE_STD)
+                    ops.dropout(fp, S["drop_d2"], resid=x1_32, out_f32=y2)
+                else:
+                    y2 = ops.vnoise_fwd(f, rho, B, T, eps=e_bt, seed=seed, stream_id=S["v_stream"],
+                                        noise_std=V_NOISE_STD, resid=x1_32)   # y2 = x1 + fp
                 S.update(f=f, v_eps=e_bt)
-                layer._v_state = {"f": f, "B": B, "T": T, "eps": e_bt, "seed": seed,
-                                  "stream_id": engine._stream_id(_TID_VNOISE + li, 0)}
+                layer._v_state = {"f": f, "B": B, "T": T, "eps": e_bt, "seed": seed, "stream_id": S["v_stream"]}
             else:
-                _gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
+                S["drop_d2"] = self._layer_site(layer, li, "d2", (T, B))         # dropout2, model.py:1045
+                if S["drop_d2"] is not None:
+                    f2 = self._f32(M, d)
+                    _gemm(hs, w2, prec=prec, bias=b2, out_f32=f2, tag="ffn2")
+                    ops.dropout(f2, S["drop_d2"], resid=x1_32, out_f32=y2)
+                else:
+                    _gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
             x32, xs = ops.layernorm(y2, layer.norm2.weight.detach(), layer.norm2.bias.detach(), layer.norm2.eps, prec=prec)
             S["y2"] = y2
             saved.append(S)
@@ -341,15 +435,16 @@ class FineTuner:
             kind, a = S["kind"], layer.self_attn
             dy2 = ops.layernorm_bwd(dx, S["y2"], layer.norm2.weight.detach(), layer.norm2.eps, g[pre + "norm2.weight"],
                                     g[pre + "norm2.bias"])
+            # gradient of the FFN branch = dropout2's mask on dy2 (the residual branch keeps dy2 itself)
+            dbr = dy2 if S["drop_d2"] is None else ops.dropout(dy2, S["drop_d2"])[0]
             if kind == "v":
-                df, klpart = ops.vnoise_bwd(dy2, S["f"], layer.hiddens_lgstd.detach().view(T, d),
+                df, klpart = ops.vnoise_bwd(dbr, S["f"], layer.hiddens_lgstd.detach().view(T, d),
                                             layer.hiddens_mean_p.detach().view(T, d), B, T, kl_scale,
                                             g[pre + "hiddens_lgstd"].view(T, d), g[pre + "hiddens_mean_p"].view(T, d),
-                                            eps=S["v_eps"], seed=seed, stream_id=engine._stream_id(_TID_VNOISE + li, 0),
-                                            noise_std=V_NOISE_STD)
+                                            eps=S["v_eps"], seed=seed, stream_id=S["v_stream"], noise_std=V_NOISE_STD)
                 ops.reduce_sum(klpart.view(-1), kl, scale=0.5 / (M * d), accumulate=True)
             else:
-                df = dy2
+                df = dbr
             dfs = ops.split(df, prec)
             # FFN2: dgrad fused with the activation derivative, wgrad, bias
             dz1 = self._f32(M, S["z1"].shape[1])
@@ -361,6 +456,11 @@ class FineTuner:
             else:
                 _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
                       fast_act=(prec == "bf16"), tag="dgrad:ffn2")
+            if S["drop_ffn"] is not None:
+                # h = m . act(z1): the mask multiplies the gradient elementwise, before or after act'(z1)
+                dz1, dz1s = ops.dropout(dz1, S["drop_ffn"], prec=prec, out_f32=dz1)
+                if kind == "gauss":
+                    ops.dropout(dh, S["drop_ffn"], out_f32=dh)
             dft, ht = _tsplit(df, prec, dfs), _tbf16(S["hs"], prec)
             if kind == "bayes_ffn":
                 G = g[pre + "linear2.weight_mean"]
@@ -387,10 +487,13 @@ class FineTuner:
             # LayerNorm 1, output projection, attention, QKV projection
             dy1 = ops.layernorm_bwd(dx1, S["y1"], layer.norm1.weight.detach(), layer.norm1.eps, g[pre + "norm1.weight"],
                                     g[pre + "norm1.bias"])
-            dy1s = ops.split(dy1, prec)
+            if S["drop_d1"] is not None:     # gradient of the attention branch = dropout1's mask on dy1
+                do1, dy1s = ops.dropout(dy1, S["drop_d1"], prec=prec)
+            else:
+                do1, dy1s = dy1, ops.split(dy1, prec)
             datt = self._f32(M, d)
             _gemm(dy1s, S["wo_t"], prec=prec, out_f32=datt, tag="dgrad:o_net")
-            dy1t, attt = _tsplit(dy1, prec, dy1s), _tbf16(S["atts"], prec)
+            dy1t, attt = _tsplit(do1, prec, dy1s), _tbf16(S["atts"], prec)
             if kind == "bayes_mha":
                 G, lin = g[pre + "self_attn.o_net.weight_mean"], a.o_net
                 self._wgrad(dy1t, attt, G, "o_net")
@@ -402,8 +505,8 @@ class FineTuner:
                                  g[pre + "self_attn.o_net.weight_lgstd"])
             else:
                 self._wgrad(dy1t, attt, g[pre + "self_attn.o_net.weight"], "o_net")
-                ops.colsum(dy1, g[pre + "self_attn.o_net.bias"])
-            dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q, prec=prec)
+                ops.colsum(do1, g[pre + "self_attn.o_net.bias"])
+            dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q, prec=prec, drop=S["drop_attn"])
             dx = self._f32(M, d)
             dqkvs = ops.split(dqkv, prec)
             _gemm(dqkvs, S["wqkv_t"], prec=prec, resid=dy1, out_f32=dx, tag="dgrad:qkv")
@@ -419,6 +522,8 @@ class FineTuner:
                 ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
             if on_layer_done is not None:
                 on_layer_done(li)      # every gradient of layers >= li is final (capture() splits the graph here)
+        if drop_pe is not None:
+            dx, _ = ops.dropout(dx, drop_pe, out_f32=dx)
         if emb_variant:   # back through x0 W~^T: G = dx^T x0 (-> embed_mean, embed_lgstd), dx0 = dx W~
             dxt, x0t = _tsplit(dx, prec), _tbf16(E_in["x0s"], prec)
             if E_in["sampled"]:
@@ -517,7 +622,12 @@ class FineTuner:
         lengths = torch.full((B,), T, dtype=torch.int32, device=dev)
         self.flat_g.zero_()
 
-        _, x = ops.embed(tok, None, m.encoder.weight.detach().float(), None, 1.0, prec=prec, want_f32=False)
+        # self.drop on the embedding and on the LSTM output (model.py:218,220); rows are time-major like the oracle's
+        drop_emb = self._site(m.p_drop, _TID_DROP_EMB, ("emb",))
+        drop_out = self._site(m.p_drop, _TID_DROP_OUT, ("out",))
+        x32, x = ops.embed(tok, None, m.encoder.weight.detach().float(), None, 1.0, prec=prec, want_f32=drop_emb is not None)
+        if drop_emb is not None:
+            _, x = ops.dropout(x32, drop_emb, prec=prec, want_f32=False)
         saved, hT, cT = [], [], []
         for li in range(2):
             P = self._lstm_layer_params(li + 1, eps, seed, sampled)
@@ -525,15 +635,19 @@ class FineTuner:
             w_hh, w_hh_t = self._w2(P["w_hh"])
             gates = self._f32(M, 4 * H)
             _gemm(x, w_ih, prec=prec, bias=P["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
-            _, out, h_last, c_last = ops.lstm_layer(gates, w_hh, h0[li], c0[li], lengths, T, B, H, prec=prec,
-                                                    want_f32=False, want_split=True)
+            out32, out, h_last, c_last = ops.lstm_layer(gates, w_hh, h0[li], c0[li], lengths, T, B, H, prec=prec,
+                                                        want_f32=(li == 1 and drop_out is not None), want_split=True)
             saved.append({"x": x, "out": out, "gates": gates, "w_ih_t": w_ih_t, "w_hh": w_hh, "w_hh_t": w_hh_t})
             hT.append(h_last)
             cT.append(c_last)
             x = out
         self.hidden = (torch.stack(hT), torch.stack(cT))
+        if drop_out is not None:
+            _, x = ops.dropout(out32, drop_out, prec=prec, want_f32=False)
 
         dout, ce, kl, loss = self._loss_and_decoder_grads(x, tgt)
+        if drop_out is not None:
+            dout, _ = ops.dropout(dout, drop_out, out_f32=dout)
 
         for li in (1, 0):
             S, layer = saved[li], li + 1
@@ -584,6 +698,8 @@ class FineTuner:
                     if layer == 1:   # the reference's KL only sees the layer-1 tensors (model.py:736-765)
                         ops.kl_gauss(mu[rows], lg, kl, scale=frac, accumulate=True)
                         ops.kl_gauss_bwd(mu[rows], lg, kl_scale * frac, G[rows], g_lg)
+        if drop_emb is not None:
+            dout, _ = ops.dropout(dout, drop_emb, out_f32=dout)
         ops.embed_bwd(dout, tok, 1.0, g["encoder.weight"])
         ops.reduce_sum(ce, loss)
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
@@ -654,6 +770,10 @@ class FineTuner:
                 buf = torch.zeros_like(layer.linear2.weight_lgstd)
                 cap["eps"][f"layer{li}"] = buf
                 cap["fill"].append((buf, _TID["ffn_w2"], 1.0))
+            elif layer.kind == "bayes_mha":
+                buf = torch.zeros_like(layer.self_attn.o_net.weight_lgstd)
+                cap["eps"][f"layer{li}"] = buf
+                cap["fill"].append((buf, _TID["mha_o"], 1.0))
             elif layer.kind == "gauss" and layer.gpnn.sample:
                 e, gp = {}, layer.gpnn
                 if gp.gpnn_type in (1, 3):
@@ -663,6 +783,20 @@ class FineTuner:
                     e["weights"], e["bias"] = torch.zeros_like(gp.weights_lgstd), torch.zeros_like(gp.bias_lgstd)
                     cap["fill"] += [(e["weights"], _TID["gp_w"], 1.0), (e["bias"], _TID["gp_b"], 1.0)]
                 cap["eps"][f"layer{li}"] = e
+        if getattr(m, "bayes_embed", False):
+            buf = torch.zeros_like(m.embed_lgstd)
+            cap["eps"]["embed"] = buf
+            cap["fill"].append((buf, _TID["embed"], 1.0))
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)   # dropout key of the replay, written per step
+        self._capturing = True
+        try:
+            self._capture_graphs(cap, T, B)
+        finally:
+            self._capturing = False
+        return self
+
+    def _capture_graphs(self, cap, T: int, B: int):
+        m = self.model
         self._refill_noise(0)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -722,7 +856,11 @@ class FineTuner:
 
     def _refill_noise(self, seed: int):
         for buf, tid, std in self._cap["fill"]:
-            ops.philox_normal(seed, engine._stream_id(tid, 0), buf.numel(), self.device, out=buf.view(-1), scale=std)
+            # weight noise is shared by the data-parallel ranks (replicated weights); the per-token noise of the
+            # variational layers belongs to the rank's own rows
+            k = self.rank if tid >= _TID_VNOISE else 0
+            ops.philox_normal(seed, engine._stream_id(tid, k), buf.numel(), self.device, out=buf.view(-1), scale=std)
+        self._seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
 
     def step_captured(self, tokens_tb, targets_tb, seed: int):
         """One step through the captured graphs; (loss, ce, kl) are 0-dim device tensors valid until the

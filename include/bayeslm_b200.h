@@ -407,6 +407,43 @@ int blm_mha_causal_bwd_tc(const float* qkv, int64_t ld, const float* dout, int64
                           int32_t max_len, float q_scale, int32_t precise, float* dqkv, int64_t ldd,
                           blm_stream stream);
 
+/* ------------------------------------------------- dropout of the fine-tune step
+ * The reference trains with nn.Dropout at: the embedding + positional output (model.py:116), the attention
+ * probabilities (model.py:912-913), the attention and FFN residual branches and the FFN activation
+ * (dropout1 / dropout2 / dropout, model.py:1039-1045, 1163-1174, 2275-2285, 2793-2803), and around the LSTM
+ * (model.py:218-221).  A kept element is scaled by 1 / (1 - p).  The multiplier of element i is either read from an
+ * explicit fp32 tensor (`mask`, values 0 or 1/(1-p): parity with masks injected into the oracle) or derived from
+ * Philox4x32-10: word (i & 3) of counter (i >> 2) on stream `stream_id` under key seed + *seed_dev; kept iff
+ * word >= floor(p * 2^32).  `seed_dev` (may be null) is read on the device, so a CUDA graph that captured the call
+ * replays with fresh masks after a 8-byte write.  p == 0 and mask == null: identity.                           */
+typedef struct blm_dropout_desc {
+  const float* mask;         /* explicit multipliers, or null for Philox                  */
+  float p;                   /* drop probability in [0, 1)                                */
+  int32_t reserved;
+  uint64_t seed;             /* Philox key (host part)                                    */
+  const uint64_t* seed_dev;  /* device word added to the key, or null                     */
+  uint64_t stream_id;        /* Philox stream: one per (site, layer)                      */
+} blm_dropout_desc;
+
+/* out = x * m (+ resid), elementwise over n values (n % 4 == 0, 16-B aligned); x null = ones (exports the
+ * multipliers).  Outputs: fp32 and / or bf16 (hi[, lo]); out_f32 may alias x.
+ * replaces: nn.Dropout at model.py:116, 1039, 1043, 1045 and 218-221, and its autograd twin (same call on the
+ * gradient).                                                                                                   */
+int blm_dropout(const float* x, int64_t n, const blm_dropout_desc* drop, const float* resid, float* out_f32,
+                blm_bf16* out_hi, blm_bf16* out_lo, blm_stream stream);
+
+/* blm_mha_causal_bf16 / blm_mha_causal_bwd_tc with dropout on the attention probabilities (model.py:912-913):
+ * O = (m . P) V.  The multiplier of (sequence s, head h, query i, key j) is element
+ * ((s * nhead + h) * L + i) * L + j of the mask / Philox stream, L = max_len rounded up to a multiple of 4.  */
+int blm_mha_causal_bf16_dropout(const blm_bf16* qkv_hi, const blm_bf16* qkv_lo, int64_t ld,
+                                const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                                int32_t max_len, const blm_dropout_desc* drop, float* out_f32, blm_bf16* out_hi,
+                                blm_bf16* out_lo, int64_t ldo, blm_stream stream);
+int blm_mha_causal_bwd_tc_dropout(const float* qkv, int64_t ld, const float* dout, int64_t ldo,
+                                  const int32_t* seq_offsets, int64_t nseq, int32_t nhead, int32_t head_dim,
+                                  int32_t max_len, float q_scale, int32_t precise, const blm_dropout_desc* drop,
+                                  float* dqkv, int64_t ldd, blm_stream stream);
+
 /* GP mixture (model.py:1893-1899): dcoef[i, n] (+)= sum_m dh[m, n] act_i(z[m, n]).              */
 int blm_gpmix_dcoef(const float* z, const float* dh, int64_t ld, int64_t M, int64_t N,
                     int32_t accumulate, float* dcoef, blm_stream stream);

@@ -130,8 +130,10 @@ def causal_mask(T: int) -> Tensor:
     return torch.triu(m, diagonal=1)
 
 
-def _attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, mask: Optional[Tensor]) -> Tensor:
-    """model.py:889-920: heads are contiguous column groups; bmm, additive mask, softmax, bmm."""
+def _attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, mask: Optional[Tensor],
+                    drop: Optional[Tensor] = None) -> Tensor:
+    """model.py:889-920: heads are contiguous column groups; bmm, additive mask, softmax, [dropout], bmm.
+    ``drop``: the nn.Dropout of model.py:913 as an injected multiplier tensor (B * nhead, T, T), values 0 or 1/(1-p)."""
     T, B, d = q.shape
     hd = d // nhead
     q = q.contiguous().view(T, B * nhead, hd).transpose(0, 1)
@@ -141,16 +143,18 @@ def _attention_core(q: Tensor, k: Tensor, v: Tensor, nhead: int, mask: Optional[
     if mask is not None:
         w = w + mask.unsqueeze(0)
     w = F.softmax(w, dim=-1)
+    if drop is not None:
+        w = w * drop
     o = torch.bmm(w, v)
     return o.transpose(0, 1).contiguous().view(T, B, d)
 
 
-def mha(x: Tensor, sd: SD, pre: str, nhead: int, mask: Optional[Tensor]) -> Tensor:
+def mha(x: Tensor, sd: SD, pre: str, nhead: int, mask: Optional[Tensor], drop: Optional[Tensor] = None) -> Tensor:
     """MultiheadAttention.forward, model.py:871-928 (fused qkv_net, q scaled after the bias)."""
     d = x.shape[-1]
     scaling = float(d // nhead) ** -0.5
     q, k, v = F.linear(x, sd[pre + "qkv_net.weight"], sd[pre + "qkv_net.bias"]).chunk(3, dim=-1)
-    o = _attention_core(q * scaling, k, v, nhead, mask)
+    o = _attention_core(q * scaling, k, v, nhead, mask, drop)
     return F.linear(o, sd[pre + "o_net.weight"], sd[pre + "o_net.bias"])
 
 
@@ -159,14 +163,15 @@ def bayes_linear_weight(mu: Tensor, lgstd: Tensor, eps: Optional[Tensor]) -> Ten
     return mu if eps is None else mu + eps * torch.exp(lgstd)
 
 
-def bayes_mha(x: Tensor, sd: SD, pre: str, nhead: int, mask: Optional[Tensor], eps_o: Optional[Tensor]) -> Tensor:
+def bayes_mha(x: Tensor, sd: SD, pre: str, nhead: int, mask: Optional[Tensor], eps_o: Optional[Tensor],
+              drop: Optional[Tensor] = None) -> Tensor:
     """BayesMultiheadAttention.forward, model.py:971-1019: separate q/k/v nets, bias-free Bayesian o_net."""
     d = x.shape[-1]
     scaling = float(d // nhead) ** -0.5
     q = F.linear(x, sd[pre + "q_net.weight"], sd[pre + "q_net.bias"]) * scaling
     k = F.linear(x, sd[pre + "k_net.weight"], sd[pre + "k_net.bias"])
     v = F.linear(x, sd[pre + "v_net.weight"], sd[pre + "v_net.bias"])
-    o = _attention_core(q, k, v, nhead, mask)
+    o = _attention_core(q, k, v, nhead, mask, drop)
     w = bayes_linear_weight(sd[pre + "o_net.weight_mean"], sd[pre + "o_net.weight_lgstd"], eps_o)
     return F.linear(o, w)
 
@@ -194,18 +199,27 @@ def gpnn(x: Tensor, sd: SD, pre: str, gpnn_type: int, eps: Optional[Dict[str, Te
 
 
 def tm_layer(x: Tensor, sd: SD, pre: str, kind: str, nhead: int, mask: Optional[Tensor], cfg: Config,
-             eps=None, aux: Optional[dict] = None) -> Tensor:
+             eps=None, aux: Optional[dict] = None, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """One post-LN encoder layer (model.py:1037-1046, 1162-1176, 2274-2287, 2792-2805).
-    ``eps`` is the layer's injected noise (None = posterior mean / eval)."""
+    ``eps`` is the layer's injected noise (None = posterior mean / eval).  ``masks`` injects the layer's four
+    training-mode nn.Dropout draws as multiplier tensors (0 or 1/(1-p)): 'attn' (B*nhead, T, T) on the attention
+    probabilities (model.py:913), 'd1' (T, B, d) = dropout1 on the attention branch, 'ffn' (T, B, F) = dropout on the
+    activation, 'd2' (T, B, d) = dropout2 on the FFN branch -- after the variational noise, which is added in place
+    first (model.py:2799-2803)."""
+    masks = masks or {}
     if kind == "bayes_mha":
-        a = bayes_mha(x, sd, pre + "self_attn.", nhead, mask, eps)
+        a = bayes_mha(x, sd, pre + "self_attn.", nhead, mask, eps, masks.get("attn"))
     else:
-        a = mha(x, sd, pre + "self_attn.", nhead, mask)
+        a = mha(x, sd, pre + "self_attn.", nhead, mask, masks.get("attn"))
+    if "d1" in masks:
+        a = a * masks["d1"]
     x = _ln(x + a, sd, pre + "norm1.")
     if kind == "gauss":
         h = gpnn(x, sd, pre + "gpnn.", cfg.gauss_pos, eps)
     else:
         h = F.gelu(F.linear(x, sd[pre + "linear1.weight"], sd[pre + "linear1.bias"]))
+    if "ffn" in masks:
+        h = h * masks["ffn"]
     if kind == "bayes_ffn":
         w2 = bayes_linear_weight(sd[pre + "linear2.weight_mean"], sd[pre + "linear2.weight_lgstd"], eps)
         f = F.linear(h, w2)
@@ -217,14 +231,19 @@ def tm_layer(x: Tensor, sd: SD, pre: str, kind: str, nhead: int, mask: Optional[
         f = f + eps * torch.exp(f * sd[pre + "hiddens_lgstd"])
     if aux is not None and kind == "v":
         aux[pre + "hidden"] = f
+    if "d2" in masks:
+        f = f * masks["d2"]
     return _ln(x + f, sd, pre + "norm2.")
 
 
 def transformer_hidden(sd: SD, tokens: Tensor, cfg: Config, eps: Optional[dict] = None,
-                       aux: Optional[dict] = None) -> Tensor:
+                       aux: Optional[dict] = None, masks: Optional[dict] = None) -> Tensor:
     """Everything of {Bayes,Gauss,V}TransformerModel.forward before the decoder
     (model.py:1274-1304, 2341-2360, 2871-2891).  tokens: (T, B) int64.
-    eps: {'layer<i>': noise for layer i, 'embed': noise for the EMB variant}."""
+    eps: {'layer<i>': noise for layer i, 'embed': noise for the EMB variant}.
+    masks (training-mode dropout as injected multipliers): {'pe': (T, B, d) for PositionalEncoding's dropout
+    (model.py:116), 'layer<i>': the layer's masks, see tm_layer}."""
+    masks = masks or {}
     sd, cfg = canonical(sd, cfg)
     eps = eps or {}
     T = tokens.shape[0]
@@ -237,8 +256,11 @@ def transformer_hidden(sd: SD, tokens: Tensor, cfg: Config, eps: Optional[dict] 
         x = F.linear(x, w)
     pe = sd["pos_encoder.pe"] if "pos_encoder.pe" in sd else positional_encoding(5000, d).unsqueeze(1)
     x = x + pe[:T]
+    if "pe" in masks:
+        x = x * masks["pe"]
     for i, kind in enumerate(tm_layer_kinds(cfg)):
-        x = tm_layer(x, sd, f"transformerlayers.{i}.", kind, cfg.nhead, mask, cfg, eps.get(f"layer{i}"), aux)
+        x = tm_layer(x, sd, f"transformerlayers.{i}.", kind, cfg.nhead, mask, cfg, eps.get(f"layer{i}"), aux,
+                     masks.get(f"layer{i}"))
     if emb_variant:
         x = F.linear(x, sd["embed_mean"].t())  # model.py:1303: mean only, transposed
     return x
@@ -247,6 +269,12 @@ def transformer_hidden(sd: SD, tokens: Tensor, cfg: Config, eps: Optional[dict] 
 def transformer_forward(sd: SD, tokens: Tensor, cfg: Config, eps: Optional[dict] = None) -> Tensor:
     """logits (T, B, V) = decoder(hidden), model.py:1304-1306."""
     h = transformer_hidden(sd, tokens, cfg, eps)
+    return F.linear(h, sd["decoder.weight"], sd["decoder.bias"])
+
+
+def transformer_forward_masks(sd: SD, tokens: Tensor, cfg: Config, eps: Optional[dict], masks: Optional[dict]) -> Tensor:
+    """Training-mode logits with injected parameter noise and dropout masks."""
+    h = transformer_hidden(sd, tokens, cfg, eps, None, masks)
     return F.linear(h, sd["decoder.weight"], sd["decoder.bias"])
 
 
@@ -283,16 +311,22 @@ def lstm_layer(x: Tensor, h: Tensor, c: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih
 
 
 def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Config,
-                eps: Optional[Dict[str, Tensor]] = None, return_hidden_states: bool = False):
+                eps: Optional[Dict[str, Tensor]] = None, return_hidden_states: bool = False,
+                masks: Optional[Dict[str, Tensor]] = None):
     """BayesRNNModel.forward in eval / injected-noise mode, model.py:217-222 + 783-828.
     tokens (T, B); hidden = (h, c) each (2, B, H).  Returns logits (T, B, V), (h, c).
-    The GP / Variational cell families (eval mode) are routed to ``cell_rnn_forward``."""
+    The GP / Variational cell families (eval mode) are routed to ``cell_rnn_forward``.
+    masks: the two training-mode ``self.drop`` draws of model.py:218,220 as multipliers: 'emb' (T, B, ninp) on the
+    embedding, 'out' (T, B, H) on the LSTM output (the inter-layer dropout is the literal 0., model.py:813)."""
+    masks = masks or {}
     if cfg.family in ("gauss_lstm", "v_lstm"):
         assert not return_hidden_states
         return cell_rnn_forward(sd, tokens, hidden, cfg)
     sd, cfg = canonical(sd, cfg)
     p = lstm_flat_parameters(sd, cfg.bayes_pos, eps)
     x = F.embedding(tokens, sd["encoder.weight"])
+    if "emb" in masks:
+        x = x * masks["emb"]
     h0, c0 = hidden
     hs, cs = [], []
     for layer in (1, 2):
@@ -300,6 +334,8 @@ def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Conf
                              p[f"bias_ih_{layer}"], p[f"bias_hh_{layer}"])
         hs.append(h)
         cs.append(c)
+    if "out" in masks:
+        x = x * masks["out"]
     new_hidden = (torch.stack(hs), torch.stack(cs))
     if return_hidden_states:
         return x, new_hidden
@@ -626,14 +662,15 @@ def edit_distance(a: Sequence, b: Sequence) -> int:
 
 # ------------------------------------------------------------------- fine-tune step
 def finetune_loss(sd: SD, tokens: Tensor, targets: Tensor, cfg: Config, eps: Optional[dict], kl_scale: float,
-                  hidden=None):
+                  hidden=None, masks: Optional[dict] = None):
     """train.py:319-404: loss = CE(mean over tokens) + KL * kl_scale, kl_scale = seq_len / len(train_data).
-    ``sd`` may hold tensors requiring grad; autograd through this function is the gradient oracle."""
+    ``sd`` may hold tensors requiring grad; autograd through this function is the gradient oracle.
+    ``masks``: the step's dropout draws as injected multiplier tensors (see transformer_hidden / rnn_forward)."""
     aux: dict = {}
     if cfg.family.endswith("lstm"):
-        logits, _ = rnn_forward(sd, tokens, hidden, cfg, eps)
+        logits, _ = rnn_forward(sd, tokens, hidden, cfg, eps, masks=masks)
     else:
-        h = transformer_hidden(sd, tokens, cfg, eps, aux)
+        h = transformer_hidden(sd, tokens, cfg, eps, aux, masks)
         logits = F.linear(h, sd["decoder.weight"], sd["decoder.bias"])
     ce = F.cross_entropy(logits.view(-1, logits.shape[-1]), targets.view(-1))
     kl = model_kl(sd, cfg, aux)

@@ -465,3 +465,91 @@ def test_gelu_grad_epilogue_coalesced(ops, fast):
     acc = (A.hi.double() @ B.hi.double().T).abs()
     assert (err <= (2e-3 if fast else 2e-6) * acc + 1e-6 * acc.max()).all(), err.max().item()
     assert torch.equal(out.hi, out32.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------ dropout (fine-tune step)
+def test_dropout_kernel_philox_and_injected(ops):
+    """blm_dropout: out = x * m (+ resid).  Philox multipliers are 0 or 1/(1-p) with keep rate 1-p, a pure function of
+    (seed + *seed_dev, stream, element); the exported multipliers re-injected as an explicit mask give the same bits."""
+    n, p = 1 << 20, 0.2
+    x = torch.randn(n, device=DEV)
+    r = torch.randn(n, device=DEV)
+    dr = ops.Drop(p, seed=123, stream_id=77)
+    m, _ = ops.dropout(None, dr, n=n, device=x.device)
+    vals = torch.unique(m)
+    assert vals.numel() == 2 and vals[0] == 0 and abs(float(vals[1]) - 1.25) < 1e-6
+    keep = float((m > 0).float().mean())
+    assert abs(keep - 0.8) < 2e-3, keep
+    y, ys = ops.dropout(x, dr, resid=r, prec="bf16x3")
+    assert torch.equal(y, x * m + r)
+    _close(ys.float(), y, 2e-5)
+    y2, _ = ops.dropout(x, ops.Drop(p, mask=m), resid=r)
+    assert torch.equal(y, y2)
+    # in place, other stream -> other mask, device seed word adds to the key
+    z = x.clone()
+    ops.dropout(z, dr, out_f32=z)
+    assert torch.equal(z, x * m)
+    m2, _ = ops.dropout(None, ops.Drop(p, seed=123, stream_id=78), n=n, device=x.device)
+    assert not torch.equal(m, m2)
+    word = torch.tensor([23], dtype=torch.int64, device=DEV)
+    m3, _ = ops.dropout(None, ops.Drop(p, seed=100, stream_id=77, seed_dev=word), n=n, device=x.device)
+    assert torch.equal(m, m3)
+
+
+def _attention_dropout_ref(qkv, dout, offs, nhead, mask_l, L):
+    """float64 forward + autograd of softmax(q k^T + causal) -> * mask -> @ v per (sequence, head)."""
+    M, d3 = qkv.shape
+    d, hd = d3 // 3, d3 // 3 // nhead
+    out = torch.zeros(M, d, dtype=torch.float64, device=qkv.device)
+    grad = torch.zeros(M, d3, dtype=torch.float64, device=qkv.device)
+    for s in range(len(offs) - 1):
+        a, b = int(offs[s]), int(offs[s + 1])
+        T = b - a
+        x = qkv[a:b].double().clone().requires_grad_(True)
+        q, k, v = (x[:, i * d:(i + 1) * d].view(T, nhead, hd).transpose(0, 1) for i in range(3))
+        sc = q @ k.transpose(1, 2)
+        tril = torch.ones(T, T, dtype=torch.bool, device=qkv.device).tril()
+        pr = torch.softmax(sc.masked_fill(~tril, float("-inf")), dim=-1)
+        pr = pr * mask_l[s * nhead:(s + 1) * nhead, :T, :T].double()
+        o = (pr @ v).transpose(0, 1).reshape(T, d)
+        (o * dout[a:b].double()).sum().backward()
+        out[a:b], grad[a:b] = o.detach(), x.grad
+    return out, grad
+
+
+@pytest.mark.parametrize("lens,prec,tol_f,tol_b", [([100] * 3, "bf16x3", 5e-5, 2e-4), ([100] * 3, "bf16", 1e-2, 2e-2),
+                                                   ([7, 26, 32, 1], "bf16x3", 5e-5, 2e-4), ([5, 128, 31, 66], "bf16x3", 5e-5, 2e-4)])
+def test_attention_dropout_forward_and_backward(ops, lens, prec, tol_f, tol_b):
+    """Dropout on the attention probabilities (model.py:912-913) inside the tensor-core kernels: injected multipliers
+    against float64 autograd, and Philox mode == the same step with its own exported multipliers injected."""
+    nhead, hd, p = 4, 64, 0.3
+    d = nhead * hd
+    M, n_seq = sum(lens), len(lens)
+    L = (max(lens) + 3) // 4 * 4
+    offs = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    qkv = torch.randn(M, 3 * d, device=DEV) * 0.7
+    dout = torch.randn(M, d, device=DEV)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    mask = ((torch.rand(n_seq * nhead, L, L, generator=g) >= p).float() / (1 - p)).to(DEV)
+    qs = ops.split(qkv, prec)
+    src = qkv if prec == "bf16x3" else qs.hi.float()
+    ref_o, ref_g = _attention_dropout_ref(src, dout, offs.tolist(), nhead, mask, L)
+    o32, _ = ops.mha_causal_bf16(qs, offs, nhead, max(lens), prec=prec, want_f32=True, drop=ops.Drop(p, mask=mask))
+    _close(o32, ref_o, tol_f)
+    # the backward kernel takes the projection BEFORE the q scaling was folded in: feed q as is with scale 1
+    got = ops.mha_causal_bwd(qkv, dout, offs, nhead, max(lens), 1.0, prec=prec, drop=ops.Drop(p, mask=mask))
+    _, ref_g32 = _attention_dropout_ref(qkv, dout, offs.tolist(), nhead, mask, L)
+    _close(got, ref_g32, tol_b)
+    # Philox: export the multipliers of the stream, inject them, compare bit for bit
+    dr = ops.Drop(p, seed=9, stream_id=1234)
+    pm, _ = ops.dropout(None, dr, n=n_seq * nhead * L * L, device=qkv.device)
+    pm = pm.view(n_seq * nhead, L, L)
+    a1, _ = ops.mha_causal_bf16(qs, offs, nhead, max(lens), prec=prec, want_f32=True, drop=dr)
+    a2, _ = ops.mha_causal_bf16(qs, offs, nhead, max(lens), prec=prec, want_f32=True, drop=ops.Drop(p, mask=pm))
+    assert torch.equal(a1, a2)
+    b1 = ops.mha_causal_bwd(qkv, dout, offs, nhead, max(lens), 1.0, prec=prec, drop=dr)
+    b2 = ops.mha_causal_bwd(qkv, dout, offs, nhead, max(lens), 1.0, prec=prec, drop=ops.Drop(p, mask=pm))
+    assert torch.equal(b1, b2)
+    # and it really drops something
+    plain, _ = ops.mha_causal_bf16(qs, offs, nhead, max(lens), prec=prec, want_f32=True)
+    assert (plain - a1).abs().max() > 1e-2
