@@ -134,6 +134,14 @@ SIGNATURES = {
     "blm_sgd_momentum_split": (C.c_int, [_p, _p, _p, _i64, _f, _f, _p, _f, _f, _p, _p, _p]),
     "blm_lstm_gates_act": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "blm_lstm_bwd_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p]),
+    "blm_vocab_from_text": (_p, [C.c_char_p, _i64]),
+    "blm_vocab_size": (_i64, [_p]),
+    "blm_vocab_id": (_i32, [_p, C.c_char_p, _i64]),
+    "blm_vocab_free": (None, [_p]),
+    "blm_nbest_scan": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, _i32]),
+    "blm_nbest_tokenize": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i32]),
+    "blm_nbest_group": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p]),
+    "blm_scores_format": (_i64, [_p, _p, _p, _p, _p, _i64, _p, _p, _i64]),
     "blm_lstm_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_lstm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
 }

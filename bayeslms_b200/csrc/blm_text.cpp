@@ -24,7 +24,15 @@
 
 namespace {
 
-inline bool is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+// ASCII whitespace of str.split() / str.strip(): space, \t \n \v \f \r, \x1c-\x1f
+struct SpaceTable {
+  bool t[256];
+  constexpr SpaceTable() : t() {
+    for (int c = 0; c < 256; ++c) t[c] = c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
+  }
+};
+constexpr SpaceTable kSpace;
+inline bool is_space(unsigned char c) { return kSpace.t[c]; }
 
 inline uint64_t hash_bytes(const char* s, int64_t n) {
   uint64_t h = 0xcbf29ce484222325ull;   // FNV-1a, finished with a multiply-xorshift mix
@@ -122,14 +130,39 @@ inline LineView view_line(const char* b, const char* e) {
   return v;
 }
 
+// words of str.split(): a word starts wherever a non-space byte follows a space byte (or the start)
 inline int64_t count_words(const char* b, const char* e) {
   int64_t n = 0;
-  while (b < e) {
-    while (b < e && is_space(static_cast<unsigned char>(*b))) ++b;
-    if (b == e) break;
-    ++n;
-    while (b < e && !is_space(static_cast<unsigned char>(*b))) ++b;
+  bool prev_space = true;
+  for (; b < e; ++b) {
+    const bool sp = is_space(static_cast<unsigned char>(*b));
+    n += static_cast<int64_t>(prev_space & !sp);
+    prev_space = sp;
   }
+  return n;
+}
+
+// "%.4f" of a float: v * 10000 is exact in double (24-bit significand x a 14-bit integer), so rounding that product
+// to the nearest-even integer is the correctly rounded decimal printf produces; huge / non-finite values go to printf
+inline int format_score(char* out, float v) {
+  const double y = static_cast<double>(v) * 10000.0;
+  if (!(y > -9.0e17 && y < 9.0e17)) return snprintf(out, 48, "%.4f", static_cast<double>(v));
+  long long r = static_cast<long long>(__builtin_nearbyint(y));   // round-half-even in the default rounding mode
+  char tmp[32];
+  int n = 0;
+  const bool neg = (r < 0) || (r == 0 && __builtin_signbit(y));
+  unsigned long long a = r < 0 ? 0ull - static_cast<unsigned long long>(r) : static_cast<unsigned long long>(r);
+  for (int i = 0; i < 4; ++i) {
+    tmp[n++] = static_cast<char>('0' + a % 10);
+    a /= 10;
+  }
+  tmp[n++] = '.';
+  do {
+    tmp[n++] = static_cast<char>('0' + a % 10);
+    a /= 10;
+  } while (a);
+  if (neg) tmp[n++] = '-';
+  for (int i = 0; i < n; ++i) out[i] = tmp[n - 1 - i];
   return n;
 }
 
@@ -196,37 +229,100 @@ void blm_vocab_free(blm_vocab* v) { delete v; }
  * character occurs (take the slow path); lines that are empty after stripping still count (the reference keeps them
  * as an empty hypothesis with an empty key).                                                                      */
 int blm_nbest_scan(const char* text, int64_t nbytes, int64_t cap_lines, int64_t* line_begin, int32_t* line_tokens,
-                   int64_t* n_lines, int64_t* n_tokens, int32_t* flags) {
+                   int64_t* n_lines, int64_t* n_tokens, int32_t* flags, int32_t n_threads) {
   BLM_REQUIRE(text && nbytes >= 0 && n_lines && n_tokens, BLM_ERR_ARG, "bad nbest_scan arguments");
-  const char* p = text;
   const char* end = text + nbytes;
-  int64_t lines = 0, tokens = 0;
-  int32_t fl = 0;
-  for (const unsigned char* u = reinterpret_cast<const unsigned char*>(text); u < reinterpret_cast<const unsigned char*>(end); ++u)
-    if (*u >= 0xC2 && *u <= 0xE3 && unicode_space_at(u, reinterpret_cast<const unsigned char*>(end))) {
-      fl |= 1;
-      break;
-    }
-  while (p < end) {
-    const char* nl = static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(end - p)));
-    const char* le = nl ? nl : end;
-    if (line_begin) {
-      BLM_REQUIRE(lines < cap_lines, BLM_ERR_SHAPE, "line arrays too small (%lld)", (long long)cap_lines);
-      const LineView v = view_line(p, le);
-      line_begin[lines] = p - text;
-      const int64_t t = count_words(v.hyp, v.end) + 1;
-      if (line_tokens) line_tokens[lines] = static_cast<int32_t>(t);
-      tokens += t;
-    } else {
-      const LineView v = view_line(p, le);
-      tokens += count_words(v.hyp, v.end) + 1;
-    }
-    ++lines;
-    p = nl ? nl + 1 : end;
+  // byte ranges that start right after a newline: one per thread
+  int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads, nbytes / (64 << 10) + 1)));
+  std::vector<const char*> cut(static_cast<size_t>(nt) + 1);
+  cut[0] = text;
+  for (int t = 1; t < nt; ++t) {
+    const char* q = text + nbytes * t / nt;
+    if (q < cut[static_cast<size_t>(t) - 1]) q = cut[static_cast<size_t>(t) - 1];
+    const char* nl = static_cast<const char*>(memchr(q, '\n', static_cast<size_t>(end - q)));
+    cut[static_cast<size_t>(t)] = nl ? nl + 1 : end;
   }
-  if (line_begin) line_begin[lines] = nbytes;
-  *n_lines = lines;
-  *n_tokens = tokens;
+  cut[static_cast<size_t>(nt)] = end;
+  std::vector<int64_t> lines(static_cast<size_t>(nt), 0), tokens(static_cast<size_t>(nt), 0);
+  std::vector<int> flagged(static_cast<size_t>(nt), 0);
+  // pass A: lines per range, and whether Python would have split the text differently -- it reads the file with
+  // universal newlines (a lone '\r' ends a line) and splits on Unicode whitespace; both are looked for only in ranges
+  // that hold a '\r' or a non-ASCII byte at all
+  auto pass_a = [&](int t) {
+    const char* p = cut[static_cast<size_t>(t)];
+    const char* e = cut[static_cast<size_t>(t) + 1];
+    const int64_t nb = e - p;
+    bool suspicious = nb > 0 && memchr(p, '\r', static_cast<size_t>(nb)) != nullptr;
+    if (!suspicious) {
+      uint64_t acc = 0;
+      int64_t i = 0;
+      for (; i + 8 <= nb; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        acc |= w;
+      }
+      for (; i < nb; ++i) acc |= static_cast<unsigned char>(p[i]);
+      suspicious = (acc & 0x8080808080808080ull) != 0;
+    }
+    if (suspicious) {
+      const unsigned char* uend = reinterpret_cast<const unsigned char*>(end);
+      for (const unsigned char* u = reinterpret_cast<const unsigned char*>(p); u < reinterpret_cast<const unsigned char*>(e); ++u)
+        if ((*u == '\r' && (u + 1 == uend || u[1] != '\n')) || (*u >= 0xC2 && *u <= 0xE3 && unicode_space_at(u, uend))) {
+          flagged[static_cast<size_t>(t)] = 1;
+          break;
+        }
+    }
+    int64_t n = 0;
+    while (p < e) {
+      const char* nl = static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(e - p)));
+      ++n;
+      p = nl ? nl + 1 : e;
+    }
+    lines[static_cast<size_t>(t)] = n;
+  };
+  // pass B: line starts and scored positions (words + 1) per line, written at the range's line offset
+  std::vector<int64_t> first(static_cast<size_t>(nt) + 1, 0);
+  auto pass_b = [&](int t) {
+    const char* p = cut[static_cast<size_t>(t)];
+    const char* e = cut[static_cast<size_t>(t) + 1];
+    int64_t i = first[static_cast<size_t>(t)], tk = 0;
+    while (p < e) {
+      const char* nl = static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(e - p)));
+      const char* le = nl ? nl : e;
+      const LineView v = view_line(p, le);
+      const int64_t c = count_words(v.hyp, v.end) + 1;
+      if (line_begin) line_begin[i] = p - text;
+      if (line_tokens) line_tokens[i] = static_cast<int32_t>(c);
+      tk += c;
+      ++i;
+      p = nl ? nl + 1 : e;
+    }
+    tokens[static_cast<size_t>(t)] = tk;
+  };
+  auto run = [&](auto&& fn) {
+    if (nt == 1) {
+      fn(0);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+  };
+  run(pass_a);
+  for (int t = 0; t < nt; ++t) first[static_cast<size_t>(t) + 1] = first[static_cast<size_t>(t)] + lines[static_cast<size_t>(t)];
+  const int64_t total = first[static_cast<size_t>(nt)];
+  BLM_REQUIRE(!(line_begin || line_tokens) || total <= cap_lines, BLM_ERR_SHAPE, "line arrays too small: %lld lines, room for %lld",
+              (long long)total, (long long)cap_lines);
+  run(pass_b);
+  if (line_begin) line_begin[total] = nbytes;
+  int64_t tk = 0;
+  int32_t fl = 0;
+  for (int t = 0; t < nt; ++t) {
+    tk += tokens[static_cast<size_t>(t)];
+    fl |= flagged[static_cast<size_t>(t)];
+  }
+  *n_lines = total;
+  *n_tokens = tk;
   if (flags) *flags = fl;
   return BLM_OK;
 }
@@ -274,7 +370,7 @@ int blm_nbest_tokenize(const blm_vocab* vocab, const char* text, const int64_t* 
     }
   };
   const int64_t n = l1 - l0;
-  int nt = std::max(1, std::min<int64_t>(n_threads, n / 256 + 1));
+  int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_threads, n / 256 + 1)));
   if (nt == 1) {
     work(l0, l1, 0);
   } else {
@@ -329,10 +425,24 @@ int blm_nbest_group(const char* text, const int64_t* line_begin, int64_t n_lines
 int64_t blm_scores_format(const char* text, const int64_t* key_begin, const int32_t* key_len, const int32_t* idx_in_utt,
                           const int64_t* order, int64_t n, const float* scores, char* out, int64_t cap) {
   int64_t w = 0;
-  char num[64];
+  char num[96];
   for (int64_t r = 0; r < n; ++r) {
     const int64_t i = order ? order[r] : r;
-    const int m = snprintf(num, sizeof(num), "-%d %.4f\n", idx_in_utt[i], static_cast<double>(scores[i]));
+    int m = 0;
+    num[m++] = '-';
+    {
+      char d[16];
+      int nd = 0;
+      unsigned v = static_cast<unsigned>(idx_in_utt[i] < 0 ? 0 : idx_in_utt[i]);
+      do {
+        d[nd++] = static_cast<char>('0' + v % 10);
+        v /= 10;
+      } while (v);
+      while (nd) num[m++] = d[--nd];
+    }
+    num[m++] = ' ';
+    m += format_score(num + m, scores[i]);
+    num[m++] = '\n';
     const int64_t need = key_len[i] + m;
     if (out && w + need <= cap) {
       memcpy(out + w, text + key_begin[i], static_cast<size_t>(key_len[i]));

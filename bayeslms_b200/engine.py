@@ -451,10 +451,7 @@ def transformer_score(model, batch: PackedBatch, *, K: int = 0, seed: Optional[i
         xs2 = run2.hidden(run2.prefix(None), None, None, None)
         E, b1 = _scaled_decoder(plan, model, float(inter_alpha))
         E2, b2 = _scaled_decoder(plan2, inter_model, 1.0 - float(inter_alpha))
-        bkey = ("bias", id(plan2), float(inter_alpha))
-        if bkey not in plan.__dict__.setdefault("_scaled", {}):
-            plan._scaled[bkey] = (b1 + b2).contiguous()
-        dec_b, extra = plan._scaled[bkey], ((xs2, E2),)
+        dec_b, extra = b1 + b2, ((xs2, E2),)      # summed per call: both halves live and die with their own plan
     if not samples:
         xs = run.hidden(carry, None, None, None)
         tok_nll = ops.vocab_nll(xs, E, dec_b, batch.targets, prec=prec, extra=extra)
@@ -748,6 +745,11 @@ def lstm_score_flat(rs, tok: np.ndarray, tgt: np.ndarray, offs: np.ndarray, sess
     plan = plan_for(model, prec)
     H = model.nhid
     samples = _normalise_samples(rs.K, rs.seed, rs.eps_list) or [None]
+    # logit interpolation (score.py:157-163, 418-447): the second model -- a plain LSTM LM, built untied in the
+    # reference -- carries ITS OWN hidden chain through hypothesis #0 of every utterance (score.py:261-274 keeps two
+    # caches); its last-layer states then join the vocabulary sweep as extra K segments of the same GEMM
+    inter = getattr(rs, "inter_model", None)
+    plan2 = plan_for(inter, prec) if inter is not None else None
     n_rows = len(offs) - 1
     if n_rows == 0:
         return np.zeros(0, dtype=np.float32)
@@ -768,6 +770,12 @@ def lstm_score_flat(rs, tok: np.ndarray, tgt: np.ndarray, offs: np.ndarray, sess
     init_h = torch.zeros(len(samples), U, 2, S, H, dtype=torch.float32, device=dev)
     init_c = torch.zeros_like(init_h)
     weights = [_lstm_weights(model, plan, k, rs.seed) for k in samples]
+    chains = [(model, plan, weights[k], init_h[k], init_c[k]) for k in range(len(samples))]
+    if inter is not None:
+        H2 = inter.nhid
+        init_h2 = torch.zeros(U, 2, S, H2, dtype=torch.float32, device=dev)
+        init_c2 = torch.zeros_like(init_h2)
+        chains.append((inter, plan2, plan2.lstm, init_h2, init_c2))
     for s0 in range(0, S, LSTM_MAX_ROWS):
         s1 = min(S, s0 + LSTM_MAX_ROWS)
         padded = []
@@ -779,14 +787,14 @@ def lstm_score_flat(rs, tok: np.ndarray, tgt: np.ndarray, offs: np.ndarray, sess
             t_d, l_d, _, _ = _pad_from_flat(tok, starts, ln, dev)
             padded.append((t_d, l_d))
         rs.h2d_bytes += sum(4 * (t.numel() + l.numel()) for t, l in padded)
-        for k in range(len(samples)):
-            h = torch.zeros(2, s1 - s0, H, dtype=torch.float32, device=dev)
+        for net_k, plan_k, w_k, ih_k, ic_k in chains:
+            h = torch.zeros(2, s1 - s0, net_k.nhid, dtype=torch.float32, device=dev)
             c = torch.zeros_like(h)
             for u in range(U):
-                init_h[k, u, :, s0:s1], init_c[k, u, :, s0:s1] = h, c
+                ih_k[u, :, s0:s1], ic_k[u, :, s0:s1] = h, c
                 if u + 1 < U:
                     t_d, l_d = padded[u]
-                    _, _, h, c = _lstm_forward(model, plan, weights[k], t_d, l_d, h, c, want_f32=False, want_split=False)
+                    _, _, h, c = _lstm_forward(net_k, plan_k, w_k, t_d, l_d, h, c, want_f32=False, want_split=False)
 
     # ---------------- phase 2: all hypotheses, longest first, in lock-step batches
     order = np.argsort(-lens_all, kind="stable")
@@ -816,12 +824,22 @@ def lstm_score_flat(rs, tok: np.ndarray, tgt: np.ndarray, offs: np.ndarray, sess
         gather, tgt_d, offs_d = meta_d[:M], meta_d[M:2 * M], meta_d[2 * M:2 * M + B + 1]
         s_idx, u_idx = meta_d[2 * M + B + 1:2 * M + 2 * B + 1].long(), meta_d[2 * M + 2 * B + 1:].long()
         per = torch.empty(len(samples), M, dtype=torch.float32, device=dev)
+        E, dec_b, extra = plan.E, plan.dec_b, ()
+        if inter is not None:
+            a = float(rs.inter_alpha)
+            h0 = init_h2[u_idx, :, s_idx].transpose(0, 1).contiguous()
+            c0 = init_c2[u_idx, :, s_idx].transpose(0, 1).contiguous()
+            out32, _, _, _ = _lstm_forward(inter, plan2, plan2.lstm, tok_d, lens_d, h0, c0, want_f32=True, want_split=False)
+            _, hs2 = ops.embed(gather, None, out32, None, 1.0, prec=prec, want_f32=False)
+            E, b1 = _scaled_decoder(plan, model, a)
+            E2, b2 = _scaled_decoder(plan2, inter, 1.0 - a)
+            dec_b, extra = b1 + b2, ((hs2, E2),)
         for k in range(len(samples)):
             h0 = init_h[k, u_idx, :, s_idx].transpose(0, 1).contiguous()   # [2, B, H]
             c0 = init_c[k, u_idx, :, s_idx].transpose(0, 1).contiguous()
             out32, _, _, _ = _lstm_forward(model, plan, weights[k], tok_d, lens_d, h0, c0, want_f32=True, want_split=False)
             _, hs = ops.embed(gather, None, out32, None, 1.0, prec=prec, want_f32=False)  # row gather + bf16 split
-            ops.vocab_nll(hs, plan.E, plan.dec_b, tgt_d, prec=prec, out=per[k])
+            ops.vocab_nll(hs, E, dec_b, tgt_d, prec=prec, out=per[k], extra=extra)
         tok_nll = per[0] if len(samples) == 1 else ops.mc_combine(per)
         outs.append((idx, ops.segment_sum(tok_nll, offs_d)))
     for idx, dev_scores in outs:

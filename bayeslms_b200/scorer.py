@@ -80,6 +80,97 @@ def write_scores(scores: "OrderedDict[str, List[Tuple[str, float]]]", path: str)
                 f.write("%s-%d %.4f\n" % (key, idx, s))
 
 
+# ------------------------------------------------------ file formats, fast path (C helpers of libbayeslm_b200.so)
+class Vocab:
+    """``words.txt`` held by the library's byte-string hash (blm_vocab_from_text): same ids as :func:`read_vocab`."""
+
+    def __init__(self, path: str):
+        import ctypes as C
+        with open(path, "rb") as f:
+            data = f.read()
+        self._lib = _lib.lib()
+        self._h = self._lib.blm_vocab_from_text(data, len(data))
+        if not self._h:
+            raise ValueError(f"{path}: {self._lib.blm_last_error().decode('utf-8', 'replace')}")
+        self._C = C
+
+    def __len__(self) -> int:
+        return int(self._lib.blm_vocab_size(self._h))
+
+    def id(self, word: str) -> int:
+        b = word.encode("utf-8")
+        return int(self._lib.blm_vocab_id(self._h, b, len(b)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.blm_vocab_free(h)
+
+
+class NbestText:
+    """A ``words_text`` file scanned by the C helpers: per-line byte offsets, scored positions (words + 1), utterance
+    ids in order of first appearance and the 1-based hypothesis index inside the utterance (score.py:20-51, 283-303).
+    ``tokenize`` writes the ids of a line range straight into caller-provided (pinned) int32 buffers."""
+
+    def __init__(self, path: str, threads: Optional[int] = None):
+        import ctypes as C
+        self._C, self._lib = C, _lib.lib()
+        with open(path, "rb") as f:
+            self.data = f.read()
+        self.threads = threads or min(8, os.cpu_count() or 1)
+        n_lines, n_tokens, flags = C.c_int64(), C.c_int64(), C.c_int32()
+        # room for the worst case (every byte a line); np.empty maps the pages lazily, only the used part is touched
+        nl_cap = len(self.data) + 1
+        self.line_begin = np.empty(nl_cap + 1, dtype=np.int64)
+        self.line_tokens = np.empty(nl_cap, dtype=np.int32)
+        _lib.check(self._lib.blm_nbest_scan(self.data, len(self.data), nl_cap, self._p(self.line_begin),
+                                            self._p(self.line_tokens), C.byref(n_lines), C.byref(n_tokens),
+                                            C.byref(flags), self.threads), "blm_nbest_scan")
+        n = self.n_lines = int(n_lines.value)
+        self.n_tokens = int(n_tokens.value)
+        self.needs_slow_path = bool(flags.value & 1)          # Unicode-only whitespace in the text
+        self.line_begin, self.line_tokens = self.line_begin[:n + 1].copy(), self.line_tokens[:n].copy()
+        self.offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(self.line_tokens, out=self.offs[1:])
+        self.utt_of_line = np.empty(n, dtype=np.int32)
+        self.idx_in_utt = np.empty(n, dtype=np.int32)
+        self.key_begin = np.empty(n, dtype=np.int64)
+        self.key_len = np.empty(n, dtype=np.int32)
+        n_utts = C.c_int64()
+        _lib.check(self._lib.blm_nbest_group(self.data, self._p(self.line_begin), n, self._p(self.utt_of_line),
+                                             self._p(self.idx_in_utt), self._p(self.key_begin), self._p(self.key_len),
+                                             C.byref(n_utts)), "blm_nbest_group")
+        self.n_utts = int(n_utts.value)
+        # the reference writes utterances in order of first appearance; with every utterance's lines contiguous (what
+        # the Kaldi pipeline produces) that is the file order
+        self.contiguous = bool(n == 0 or (np.diff(self.utt_of_line) >= 0).all())
+
+    def _p(self, a: np.ndarray):
+        return a.ctypes.data_as(self._C.c_void_p)
+
+    def utt_line_ranges(self) -> np.ndarray:
+        """[n_utts + 1] first line of every utterance (contiguous files)."""
+        return np.concatenate([np.searchsorted(self.utt_of_line, np.arange(self.n_utts), side="left"), [self.n_lines]])
+
+    def tokenize(self, vocab: Vocab, l0: int, l1: int, tok: np.ndarray, tgt: np.ndarray, pos: Optional[np.ndarray]):
+        for a in (tok, tgt) + ((pos,) if pos is not None else ()):
+            assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size >= self.offs[l1] - self.offs[l0]
+        _lib.check(self._lib.blm_nbest_tokenize(vocab._h, self.data, self._p(self.line_begin), self._p(self.offs), l0, l1,
+                                                self._p(tok), self._p(tgt), None if pos is None else self._p(pos),
+                                                self.threads), "blm_nbest_tokenize")
+
+    def format_scores(self, scores: np.ndarray) -> bytes:
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        assert scores.size == self.n_lines
+        order = None if self.contiguous else np.argsort(self.utt_of_line, kind="stable").astype(np.int64)
+        cap = int(self.key_len.sum()) + 72 * self.n_lines
+        buf = self._C.create_string_buffer(cap)
+        n = self._lib.blm_scores_format(self.data, self._p(self.key_begin), self._p(self.key_len), self._p(self.idx_in_utt),
+                                        None if order is None else self._p(order), self.n_lines, self._p(scores), buf, cap)
+        assert 0 <= n <= cap
+        return buf.raw[:n]
+
+
 # ------------------------------------------------------------------------- sharding
 def shard_ranges(weights: Sequence[int], world: int) -> List[Tuple[int, int]]:
     """Split items 0..n into ``world`` contiguous ranges with near-equal total weight."""
@@ -168,8 +259,8 @@ class Rescorer:
         self.model, self.prec, self.K, self.seed, self.max_tokens = model, prec, K, seed, max_tokens
         self.eps_list = eps_list
         self.inter_model, self.inter_alpha = inter_model, inter_alpha
-        if inter_model is not None and model.family.endswith("lstm"):
-            raise NotImplementedError("logit interpolation is wired for the Transformer families only")
+        if inter_model is not None and model.family.endswith("lstm") != inter_model.family.endswith("lstm"):
+            raise ValueError("logit interpolation needs two models of the same kind (score.py:385-447)")
         self.device = next(model.parameters()).device
         self.is_rnn = model.family.endswith("lstm")
         self.h2d_bytes = 0
@@ -228,6 +319,40 @@ class Rescorer:
         self.d2h_bytes += n_hyp * 4
         return self._out[:n_hyp].numpy().copy()
 
+    def score_text_lines(self, nb: "NbestText", vocab: "Vocab", l0: int, l1: int) -> np.ndarray:
+        """Lines [l0, l1) of a scanned ``words_text`` file -> fp32 scores (host).  Each batch is tokenised by the C
+        helper directly into its slice of the pinned staging buffer and sent to the device while the kernels of the
+        previous batch run (launches are asynchronous), and all scores return in one D2H copy."""
+        n_hyp = l1 - l0
+        if n_hyp <= 0:
+            return np.zeros(0, dtype=np.float32)
+        lengths = nb.line_tokens[l0:l1]
+        chunks = _chunks_by_tokens(lengths, self.max_tokens, wave_quantum())
+        need = 3 * int(nb.offs[l1] - nb.offs[l0]) + n_hyp + len(chunks)
+        if self._stage is None or self._stage.numel() < need:
+            self._stage = torch.empty(max(need, 1 << 16), dtype=torch.int32, pin_memory=True)
+        stage, at = self._stage.numpy(), 0
+        outs = []
+        for a, b in chunks:
+            la, lb = l0 + a, l0 + b
+            M = int(nb.offs[lb] - nb.offs[la])
+            n = 3 * M + (b - a + 1)
+            buf = stage[at:at + n]
+            nb.tokenize(vocab, la, lb, buf[:M], buf[M:2 * M], buf[2 * M:3 * M])
+            buf[3 * M:] = nb.offs[la:lb + 1] - nb.offs[la]
+            dev = self._stage[at:at + n].to(self.device, non_blocking=True)
+            at += n
+            batch = PackedBatch(dev[:M], dev[M:2 * M], dev[2 * M:3 * M], dev[3 * M:], int(lengths[a:b].max()), M, b - a)
+            self.h2d_bytes += batch.h2d_bytes
+            outs.append(self._score(batch))
+        res = torch.cat(outs)
+        if self._out is None or self._out.numel() < n_hyp:
+            self._out = torch.empty(max(n_hyp, 1 << 12), dtype=torch.float32, pin_memory=True)
+        self._out[:n_hyp].copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += n_hyp * 4
+        return self._out[:n_hyp].numpy().copy()
+
     def score_sessions(self, sessions):
         """sessions: list of sessions, each a list of utterances, each a list of (input, target)."""
         return engine.lstm_score_sessions(self, sessions)
@@ -282,6 +407,71 @@ def score_nbest(model, nbest: "OrderedDict[str, List[str]]", vocab: Dict[str, in
         a = int(utt_start[u])
         out[k] = [(h, float(flat[a + i])) for i, h in enumerate(nbest[k])]
     return out
+
+
+def score_files(model, nbest_path: str, vocab_path: str, out_path: Optional[str], *, prec: str = "bf16",
+                K: int = 0, seed: Optional[int] = None, max_tokens: int = 65536, session_size: Optional[int] = None,
+                rank: int = 0, world: int = 1, group=None, rescorer: Optional[Rescorer] = None, inter_model=None,
+                inter_alpha: float = 0.8, vocab: Optional[Vocab] = None) -> np.ndarray:
+    """``words_text`` + ``words.txt`` on disk -> ``lmwt.nn`` on disk: what stage 6 of the pipeline runs
+    (lmrescore_nbest_pytorchnn_cuda.sh:197-219), with the text work done by the library's C helpers -- one pass over
+    the file bytes, ids tokenised batch by batch straight into the pinned staging buffer while the GPU scores the
+    previous batch, scores formatted in one pass.  Returns the fp32 scores in file order (every rank).
+
+    Files whose utterances are not contiguous, or that contain Unicode-only whitespace, go through the per-hypothesis
+    Python path (:func:`score_nbest`), which follows the reference's dict semantics literally."""
+    rs = rescorer or Rescorer(model, prec=prec, K=K, seed=seed, max_tokens=max_tokens, inter_model=inter_model,
+                              inter_alpha=inter_alpha)
+    vocab_job = None
+    if vocab is None:      # the vocabulary is parsed on a second host thread while this one scans the n-best text
+        import concurrent.futures
+        pool = concurrent.futures.ThreadPoolExecutor(1)
+        vocab_job = pool.submit(Vocab, vocab_path)
+        pool.shutdown(wait=False)
+    nb = NbestText(nbest_path)
+    if vocab_job is not None:
+        vocab = vocab_job.result()
+    if nb.needs_slow_path or not nb.contiguous:
+        res = score_nbest(model, load_nbest(nbest_path), read_vocab(vocab_path), session_size=session_size, rank=rank,
+                          world=world, group=group, rescorer=rs)
+        if rank == 0 and out_path:
+            write_scores(res, out_path)
+        return np.asarray([sc for items in res.values() for _, sc in items], dtype=np.float32)
+    n = nb.n_lines
+    utt_first = nb.utt_line_ranges()                        # [n_utts + 1]
+    utt_tokens = np.diff(nb.offs[utt_first])
+    if rs.is_rnn:
+        size = session_size or nb.n_utts or 1
+        n_sess = -(-nb.n_utts // size)
+        sess_first_utt = np.minimum(np.arange(n_sess + 1) * size, nb.n_utts)
+        weights = np.diff(nb.offs[utt_first[sess_first_utt]])
+        lo, hi = shard_ranges(weights, world)[rank]
+        l0, l1 = int(utt_first[sess_first_utt[lo]]), int(utt_first[sess_first_utt[hi]])
+        local = np.zeros(0, dtype=np.float32)
+        if l1 > l0:
+            m = int(nb.offs[l1] - nb.offs[l0])
+            tok, tgt = np.empty(m, dtype=np.int32), np.empty(m, dtype=np.int32)
+            nb.tokenize(vocab, l0, l1, tok, tgt, None)
+            utt = nb.utt_of_line[l0:l1].astype(np.int64)
+            local = rs.score_sessions_flat(tok, tgt, nb.offs[l0:l1 + 1] - nb.offs[l0], (utt // size - lo).astype(np.int32),
+                                           (utt % size).astype(np.int32))
+    else:
+        lo, hi = shard_ranges(utt_tokens, world)[rank]
+        l0, l1 = int(utt_first[lo]), int(utt_first[hi])
+        local = rs.score_text_lines(nb, vocab, l0, l1)
+    if world > 1:
+        import torch.distributed as dist
+        full = torch.zeros(n, dtype=torch.float32, device=rs.device if dist.get_backend(group) == "nccl" else "cpu")
+        if l1 > l0:
+            full[l0:l1] = torch.from_numpy(np.ascontiguousarray(local)).to(full.device)
+        dist.all_reduce(full, group=group)                  # disjoint slices: the sum is the gather
+        flat = full.cpu().numpy()
+    else:
+        flat = local
+    if rank == 0 and out_path:
+        with open(out_path, "wb") as f:
+            f.write(nb.format_scores(flat))
+    return flat
 
 
 # ------------------------------------------------------------------------------ CLI
@@ -355,33 +545,34 @@ def main(argv=None) -> int:
     for pth in (args.nbest_list, args.vocabulary, args.model_path):
         if not os.path.exists(pth):
             raise FileNotFoundError(pth)
-    if args.interpolation_flag == 1 and (args.model != "Transformer" or not args.inter_path):
-        raise NotImplementedError("--interpolation_flag 1 needs --model Transformer and an explicit --inter_path "
-                                  "(the reference overwrites the flag with a cluster path, score.py:451-455)")
+    if args.interpolation_flag == 1 and not args.inter_path:
+        raise ValueError("--interpolation_flag 1 needs an explicit --inter_path (the reference overwrites the flag with "
+                         "a path on its authors' cluster, score.py:451-455)")
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl")
-    vocab = read_vocab(args.vocabulary)
+    vocab = Vocab(args.vocabulary)
     net = models.build_model(args, len(vocab))
     load_checkpoint(net, args.model_path)
     net = net.cuda().eval()
     net2 = None
-    if args.interpolation_flag == 1:
-        # the second model is the standard Transformer, tied, same sizes (score.py:385-410)
-        net2 = models.BayesTransformerModel(len(vocab), args.emsize, args.nhead, args.nhid, args.nlayers, 0.5, True,
-                                            "none")
+    if args.interpolation_flag == 1 and args.uncertainty != "none":   # (--uncertainty none has no model_2, score.py:379,416)
+        if args.model == "Transformer":
+            # the second model is the standard Transformer, tied, same sizes (score.py:385-410)
+            net2 = models.BayesTransformerModel(len(vocab), args.emsize, args.nhead, args.nhid, args.nlayers, 0.5, True,
+                                                "none")
+        else:
+            # ... or the plain two-layer LSTM, built UNTIED (score.py:422-423, 432-433, 443-444)
+            net2 = models.BayesRNNModel(args.model, len(vocab), args.emsize, args.nhid, args.nlayers, 0.5, False, 0)
         load_checkpoint(net2, args.inter_path)
         net2 = net2.cuda().eval()
-    nbest = load_nbest(args.nbest_list)
-    res = score_nbest(net, nbest, vocab, prec=args.precision, K=args.num_samples,
-                      seed=args.seed if args.num_samples else None, max_tokens=args.max_tokens,
-                      session_size=args.session_size or None, rank=rank, world=world, inter_model=net2,
-                      inter_alpha=args.inter_alpha)
-    if rank == 0:
-        write_scores(res, args.outfile)
+    score_files(net, args.nbest_list, args.vocabulary, args.outfile, prec=args.precision, K=args.num_samples,
+                seed=args.seed if args.num_samples else None, max_tokens=args.max_tokens,
+                session_size=args.session_size or None, rank=rank, world=world, inter_model=net2,
+                inter_alpha=args.inter_alpha, vocab=vocab)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -127,3 +127,96 @@ def wer(data: SynthNbest, nn_scores: List[np.ndarray], w: float = 0.8, lo: int =
         errs += edit_distance(data.hyps[u][k].tolist(), data.refs[u].tolist())
         words += len(data.refs[u])
     return errs / max(words, 1), picks
+
+
+# ------------------------------------------------------------------ a learnable corpus (peaked models)
+@dataclass
+class MarkovCorpus:
+    """First-order Markov chain over word ids [2, V) with ``branching`` equally likely successors per word: a model
+    fine-tuned on it for a few hundred steps has sharp next-word distributions (entropy ~ ln(branching) nats), which
+    random-init weights do not -- rankings of n-best lists then depend on the words, not on the lengths."""
+    vocab_size: int
+    nxt: np.ndarray      # [V, branching] successor table
+    seed: int
+
+    def stream(self, n: int, sent_len: int = 12, seed: int = 0) -> np.ndarray:
+        """n ids of chain sentences, each followed by <s> (= 0), like data.py:14-54 lays a corpus out."""
+        rng = np.random.RandomState(self.seed * 7919 + seed)
+        out = np.empty(n, dtype=np.int64)
+        cur, k = int(rng.randint(2, self.vocab_size)), 0
+        pick = rng.randint(0, self.nxt.shape[1], size=n)
+        for i in range(n):
+            if k == sent_len:
+                out[i], k = 0, 0
+                cur = int(rng.randint(2, self.vocab_size))
+            else:
+                cur = int(self.nxt[cur, pick[i]])
+                out[i] = cur
+                k += 1
+        return out
+
+    def nbest(self, n_utts: int, n_best: int, seed: int = 0, min_len: int = 5, max_len: int = 25) -> SynthNbest:
+        """n-best lists whose reference sentences follow the chain; the competitors are 1-3 random substitutions /
+        deletions / insertions of it (random words: off-chain, so a trained model separates them clearly)."""
+        rng = np.random.RandomState(self.seed * 104729 + seed)
+        V = self.vocab_size
+        refs, hyps, graph, oldlm = [], [], [], []
+        for _ in range(n_utts):
+            L = rng.randint(min_len, max_len + 1)
+            cur, ref = int(rng.randint(2, V)), []
+            for _ in range(L):
+                cur = int(self.nxt[cur, rng.randint(self.nxt.shape[1])])
+                ref.append(cur)
+            ref = np.asarray(ref, dtype=np.int32)
+            cand = [ref]
+            for _ in range(n_best - 1):
+                h = ref.tolist()
+                for _ in range(rng.randint(1, 4)):
+                    op = rng.randint(3)
+                    if op == 0 and h:
+                        h[rng.randint(len(h))] = int(rng.randint(2, V))
+                    elif op == 1 and len(h) > 1:
+                        del h[rng.randint(len(h))]
+                    else:
+                        h.insert(rng.randint(len(h) + 1), int(rng.randint(2, V)))
+                cand.append(np.asarray(h, dtype=np.int32))
+            order = rng.permutation(n_best)
+            refs.append(ref)
+            hyps.append([cand[i] for i in order])
+            graph.append((rng.standard_normal(n_best) * 2).astype(np.float32))
+            oldlm.append((rng.standard_normal(n_best) * 2).astype(np.float32))
+        return SynthNbest(V, refs, hyps, graph, oldlm)
+
+
+def make_markov(vocab_size: int, branching: int = 3, seed: int = 1111) -> MarkovCorpus:
+    rng = np.random.RandomState(seed)
+    return MarkovCorpus(vocab_size, rng.randint(2, vocab_size, size=(vocab_size, branching)), seed)
+
+
+def ranking_agreement(a: List[np.ndarray], b: List[np.ndarray], min_gap: float = 0.0):
+    """Per-utterance comparison of two score lists (lower = better, the pipeline's convention).  Scores are compared
+    on the output grid of ``lmwt.nn`` (``%.4f``, score.py:302) with ties broken by hypothesis index -- the tie policy
+    of a stable sort over the file order.  Returns a dict: fraction of utterances with the identical FULL ranking, with
+    the identical 1-best, the fraction of hypothesis pairs ordered the same way among pairs whose gap in ``b`` exceeds
+    ``min_gap``, and the largest gap in ``b`` of a pair that ``a`` orders differently."""
+    full = best = 0
+    pairs = agree = 0
+    worst = 0.0
+    for x, y in zip(a, b):
+        qx, qy = np.round(np.asarray(x, dtype=np.float64), 4), np.round(np.asarray(y, dtype=np.float64), 4)
+        rx, ry = np.argsort(qx, kind="stable"), np.argsort(qy, kind="stable")
+        full += int(np.array_equal(rx, ry))
+        best += int(rx[0] == ry[0])
+        dx, dy = qx[:, None] - qx[None, :], qy[:, None] - qy[None, :]
+        iu = np.triu_indices(len(qx), 1)
+        gx, gy = dx[iu], dy[iu]
+        sel = np.abs(gy) > min_gap
+        same = np.sign(gx) == np.sign(gy)
+        pairs += int(sel.sum())
+        agree += int((same & sel).sum())
+        flipped = (~same) & (np.sign(gx) * np.sign(gy) < 0)
+        if flipped.any():
+            worst = max(worst, float(np.abs(gy[flipped]).max()))
+    n = max(len(a), 1)
+    return {"full_ranking": full / n, "one_best": best / n, "pair_order": agree / max(pairs, 1),
+            "largest_flipped_gap": worst, "utterances": len(a), "pairs": pairs}

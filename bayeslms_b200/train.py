@@ -145,6 +145,24 @@ def train_epoch(ft, train_data: torch.Tensor, seq_len: int, epoch: int, *, log_i
     return float(tot) / n_batches
 
 
+def train_steps(ft, ids: torch.Tensor, bsz: int, seq_len: int, steps: int, *, seed: int = 1111) -> List[float]:
+    """``steps`` fine-tune steps over a token stream (batchified like train.py:164-176, wrapping around), through the
+    captured CUDA graphs; returns the loss of every 10th step.  Used to make peaked models for the ranking evidence
+    of bench.py / tests (a random-init model ranks n-best lists by length only)."""
+    data = batchify(ids, bsz, ft.device)
+    kl_scale = float(seq_len) / len(data)
+    ft.model.train()
+    ft.capture(seq_len, bsz, kl_scale)
+    losses, n_rows = [], data.size(0) - 1
+    for k in range(steps):
+        i = (k * seq_len) % max(n_rows - seq_len, 1)
+        x, y = data[i:i + seq_len], data[i + 1:i + 1 + seq_len].reshape(-1)
+        loss, _, _ = ft.step_captured(x, y, seed + k)
+        if k % 10 == 0 or k == steps - 1:
+            losses.append(float(loss))
+    return losses
+
+
 # ------------------------------------------------------------------ schedule (train.py:464-512)
 def fit(model, train_data, val_data, *, lr: float, epochs: int, seq_len: int, clip: float, save: str,
         prec: str = "bf16x3", log_interval: int = 200, seed: int = 1111, patience: int = 8, log=print):

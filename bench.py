@@ -354,6 +354,30 @@ def main():
     e2e_val = n_tokens * world * args.steps / (e2e_ms / 1e3)
     h2d, d2h = rs.h2d_bytes // args.steps, rs.d2h_bytes // args.steps
 
+    # ---- cli_e2e: what stage 6 of the pipeline runs -- words_text + words.txt on disk -> lmwt.nn on disk, through the
+    # scorer's file path (C tokeniser into pinned staging, batches overlapped with the kernels, C formatter)
+    import tempfile
+    from bayeslms_b200.scorer import score_files
+    tmpd = tempfile.mkdtemp(prefix=f"blm_cli_r{rank}_")
+    vocab_path, nbest_path, out_path = (os.path.join(tmpd, n) for n in ("words.txt", "words_text", "lmwt.nn"))
+    with open(vocab_path, "w") as f:
+        f.write("\n".join(synth.vocab_lines(V)) + "\n")
+    with open(nbest_path, "w") as f:
+        f.write("\n".join(data.words_text(lo, hi)) + "\n")
+
+    def cli_step():
+        res = score_files(net, nbest_path, vocab_path, out_path, rescorer=rs)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, torch.from_numpy(res).to(dev))
+        return res
+
+    cli_scores = cli_step()
+    cli_step()
+    cli_ms = timed(cli_step, args.steps)
+    cli_val = n_tokens * world * args.steps / (cli_ms / 1e3)
+    cli_same = bool(np.array_equal(cli_scores, rs.score_packed_host(tok, tgt, pos, offs)))
+    cli_lines = sum(1 for _ in open(out_path))
+
     # ---- K = 4 sampled and precise-mode numbers (same lists)
     k4_steps = max(1, args.steps // 2)
     step(K=4, seed=1111)
@@ -410,6 +434,11 @@ def main():
                        "l2": "activations per batch (>= 0.5 GB) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
+            "cli_e2e": {"value": cli_val, "unit": "tokens/s", "ms_per_step": cli_ms / args.steps,
+                        "ratio_to_e2e": cli_val / e2e_val if e2e_val else None,
+                        "path": "words_text + words.txt on disk -> lmwt.nn on disk (bayeslms_b200.scorer.score_files, the "
+                                "call `python -m bayeslms_b200.scorer` makes), vocabulary parsed every step",
+                        "scores_equal_packed_path": cli_same, "lines_written": cli_lines},
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {"kernel": "gemm_kernel<256,4,EPI_NLL> (vocab projection + online LSE + target gather)",

@@ -506,6 +506,36 @@ int blm_sgd_momentum_split(float* p, const float* g, float* v, int64_t n, float 
                            const float* norm_sq, float max_norm, float grad_scale, blm_bf16* out_hi,
                            blm_bf16* out_lo, blm_stream stream);
 
+/* ------------------------------------------------- scorer file formats (host code, no GPU work)
+ * The reference scorer tokenises one hypothesis at a time in Python (load_nbest score.py:20-51, read_vocab :63-84,
+ * get_input_and_target :87-120) and formats one score at a time (write_scores :283-303).  These entry points do the
+ * same text -> id -> text work in one pass over the file bytes, writing the packed int32 ids straight into the
+ * caller's (pinned) staging buffers -- the layout blm_embed / blm_vocab_nll consume.
+ *
+ * blm_vocab_from_text: `words.txt` bytes ("word idx" per line; any other field count is an error, score.py:79) ->
+ *   word -> id map, id = order of first occurrence.  Null on error (blm_last_error).
+ * blm_nbest_scan: line starts [n_lines + 1] and scored positions per line (words + 1) of a `words_text` file; pass
+ *   null arrays to count only; n_threads host threads split the text at line boundaries.  flags bit 0: the text holds a Unicode-only whitespace character that Python's
+ *   str.split() would split on (the caller then takes its own slow path).
+ * blm_nbest_tokenize: lines [l0, l1) -> tok = <s> w1..wL, tgt = w1..wL <s>, pos = 0..L at offsets offs[i] - offs[l0]
+ *   (offs = prefix sum of the per-line counts); OOV -> <unk>; n_threads host threads split the range.
+ * blm_nbest_group: utterance of every line (key before the last '-', dense ids in order of first appearance -- the
+ *   reference's dict order), 1-based index inside the utterance, key location in the text.
+ * blm_scores_format: "<utt>-<idx> %.4f\n" for the lines in `order`; returns bytes written (or needed, if > cap). */
+typedef struct blm_vocab blm_vocab;
+blm_vocab* blm_vocab_from_text(const char* text, int64_t nbytes);
+int64_t blm_vocab_size(const blm_vocab* vocab);
+int32_t blm_vocab_id(const blm_vocab* vocab, const char* word, int64_t len);
+void blm_vocab_free(blm_vocab* vocab);
+int blm_nbest_scan(const char* text, int64_t nbytes, int64_t cap_lines, int64_t* line_begin, int32_t* line_tokens,
+                   int64_t* n_lines, int64_t* n_tokens, int32_t* flags, int32_t n_threads);
+int blm_nbest_tokenize(const blm_vocab* vocab, const char* text, const int64_t* line_begin, const int64_t* offs,
+                       int64_t l0, int64_t l1, int32_t* tok, int32_t* tgt, int32_t* pos, int32_t n_threads);
+int blm_nbest_group(const char* text, const int64_t* line_begin, int64_t n_lines, int32_t* utt_of_line,
+                    int32_t* idx_in_utt, int64_t* key_begin, int32_t* key_len, int64_t* n_utts);
+int64_t blm_scores_format(const char* text, const int64_t* key_begin, const int32_t* key_len, const int32_t* idx_in_utt,
+                          const int64_t* order, int64_t n, const float* scores, char* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,49 @@ def test_session_scoring_matches_reference_loop(golden):
         assert np.abs(got - np.asarray(rec["lstm_scores"])).max() < tol, prec
 
 
+def test_logit_interpolation_matches_reference_loop(golden, tmp_path):
+    """LSTM logit interpolation (score.py:418-447): the second, untied plain LSTM LM carries its own hidden chain; its
+    states join the vocabulary sweep as extra K segments.  Against the reference-generated loop scores, through the
+    Rescorer and through the CLI (--interpolation_flag 1 --inter_path ...)."""
+    from bayeslms_b200 import scorer as S
+    from bayeslms_b200.scorer import Rescorer
+    rec, loop = golden("interp_lstm.pt"), golden("scorer_loop.pt")
+    vocab = {w: i for i, w in enumerate(loop["vocab_words"])}
+    nbest = OrderedDict()
+    for line in loop["nbest_lines"]:
+        key, _, hyp = line.partition(" ")
+        nbest.setdefault(key.rsplit("-", 1)[0], []).append(hyp or " ")
+    net1 = load_golden_model({"cfg": rec["cfg1"], "state_dict": rec["sd1"]}, DEV)
+    from bayeslms_b200 import model as M
+    c2 = rec["cfg2"]
+    net2 = M.BayesRNNModel("LSTM", c2["ntoken"], c2["ninp"], c2["nhid"], 2, 0.5, False, 0)     # untied, score.py:422
+    net2.load_state_dict(rec["sd2"])
+    net2 = net2.to(DEV).eval()
+    want = np.asarray(rec["scores"])
+    for prec, tol in (("bf16x3", 1e-3), ("bf16", 5e-2)):
+        got = Rescorer(net1, prec=prec, inter_model=net2, inter_alpha=rec["alpha"]).score_sessions(_sessions_from(nbest, vocab))
+        assert np.abs(got - want).max() < tol, (prec, np.abs(got - want).max())
+    # K = 2 posterior samples of model 1 mixed with the (mean) second model, against the oracle
+    sd1, cfg1 = rec["sd1"], O.Config(rec["cfg1"])
+    eps_list = [O.draw_eps(sd1, cfg1, 40 + k) for k in range(2)]
+    ref = O.compute_scores(nbest, vocab, sd1, cfg1, eps_list=eps_list, sd2=rec["sd2"], cfg2=O.Config(c2), alpha=0.6)
+    ref = np.asarray([s for items in ref.values() for _, s in items])
+    got = Rescorer(net1, prec="bf16x3", eps_list=eps_list, inter_model=net2, inter_alpha=0.6).score_sessions(_sessions_from(nbest, vocab))
+    assert np.abs(got - ref).max() < 1e-3
+    # the CLI
+    vp, npth, ck1, ck2, out = (tmp_path / n for n in ("words.txt", "words_text", "m1.pt", "m2.pt", "lmwt.nn"))
+    vp.write_text("".join(f"{w} {i}\n" for i, w in enumerate(loop["vocab_words"])))
+    npth.write_text("\n".join(loop["nbest_lines"]) + "\n")
+    torch.save(rec["sd1"], ck1), torch.save(rec["sd2"], ck2)
+    rc = S.main(["--nbest-list", str(npth), "--outfile", str(out), "--vocabulary", str(vp), "--model-path", str(ck1),
+                 "--model", "LSTM", "--emsize", str(c2["ninp"]), "--nhid", str(c2["nhid"]), "--nlayers", "2",
+                 "--uncertainty", "Bayesian", "--L_bayes_pos", "3", "--interpolation_flag", "1", "--inter_path", str(ck2),
+                 "--inter_alpha", str(rec["alpha"])])
+    assert rc == 0
+    got = np.asarray([float(l.split()[1]) for l in out.read_text().splitlines()])
+    assert np.abs(got - want).max() < 1e-3 + 5e-5
+
+
 @pytest.mark.parametrize("pos", [1, 3])
 def test_injected_eps_and_k_samples_match_oracle(golden, pos):
     from bayeslms_b200.scorer import Rescorer

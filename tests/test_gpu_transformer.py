@@ -8,6 +8,7 @@ Tolerances (stated by BASELINE.json north_star):
 """
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -149,6 +150,35 @@ def test_scorer_files_end_to_end(golden, tmp_path):
     assert keys[:4] == ["utt-a_0-1", "utt-a_0-2", "utt-a_0-3", "utt-a_1-1"]
     got = [float(l.split()[1]) for l in lines]
     assert max(abs(a - b) for a, b in zip(got, rec["tm_scores"])) < 1e-3 + 5e-5
+
+
+@pytest.mark.parametrize("family", ["tm", "lstm"])
+def test_file_path_equals_per_hypothesis_path(golden, tmp_path, family):
+    """score_files (C tokeniser -> pinned staging -> kernels -> C formatter, what the CLI runs) against score_nbest
+    (the per-hypothesis Python restatement of score.py:20-120, 206-303) on the same files: identical lmwt.nn bytes in
+    the same precision mode, for a contiguous file, and the literal dict semantics when an utterance key re-appears
+    later in the file (fallback path)."""
+    from bayeslms_b200 import scorer as S
+    rec = golden("scorer_loop.pt")
+    vp, npth = tmp_path / "words.txt", tmp_path / "words_text"
+    vp.write_text("".join(f"{w} {i}\n" for i, w in enumerate(rec["vocab_words"])))
+    rs = np.random.RandomState(4)
+    lines = []
+    for u in range(23):
+        for n in range(rs.randint(1, 7)):
+            ws = [rec["vocab_words"][rs.randint(2, len(rec["vocab_words"]))] for _ in range(rs.randint(0, 14))]
+            lines.append(f"spk-{u:03d}-{n + 1} " + "  ".join(ws) if ws else f"spk-{u:03d}-{n + 1}")
+    net = load_golden_model({"cfg": rec[f"{family}_cfg"], "state_dict": rec[f"{family}_state_dict"]}, DEV)
+    for variant in ("contiguous", "revisited"):
+        text = lines if variant == "contiguous" else lines + ["spk-003-9 " + rec["vocab_words"][5], "spk-000-7"]
+        npth.write_text("\n".join(text) + "\n")
+        kw = dict(prec="bf16x3", session_size=5 if family == "lstm" else None, max_tokens=300)
+        want = S.score_nbest(net, S.load_nbest(str(npth)), S.read_vocab(str(vp)), **kw)
+        S.write_scores(want, str(tmp_path / "want.nn"))
+        flat = S.score_files(net, str(npth), str(vp), str(tmp_path / "got.nn"), **kw)
+        assert (tmp_path / "got.nn").read_bytes() == (tmp_path / "want.nn").read_bytes(), variant
+        assert flat.shape == (len(text),)
+        assert S.NbestText(str(npth)).contiguous == (variant == "contiguous")
 
 
 def test_fused_sampled_gemm_bit_exact_and_model_level(golden):

@@ -204,6 +204,77 @@ def test_host_parsers_match_oracle(golden, tmp_path):
         S.read_vocab(str(tmp_path / "bad.txt"))
 
 
+def test_c_text_helpers_match_the_reference_parsers(tmp_path):
+    """The library's one-pass tokeniser / formatter (blm_vocab_from_text, blm_nbest_scan / _tokenize / _group,
+    blm_scores_format) against the oracle's restatement of score.py:20-120, 283-303 on awkward text: empty
+    hypotheses, OOV words, tabs and runs of spaces, keys with several dashes, CRLF, blank lines, no final newline,
+    duplicate vocabulary entries, non-ASCII words."""
+    from bayeslms_b200 import scorer as S
+    from oracle import bayeslm_oracle as O
+    rs = np.random.RandomState(0)
+    words = ["<s>", "<unk>"] + [f"w{i}" for i in range(200)] + ["naïve", "日本語", "w5"]      # w5 twice: first index wins
+    vp = tmp_path / "words.txt"
+    vp.write_text("".join(f"{w} {i}\n" for i, w in enumerate(words)), encoding="utf-8")
+    lines = []
+    for u in range(40):
+        for n in range(rs.randint(1, 9)):
+            L = rs.randint(0, 12)
+            ws = [words[rs.randint(2, len(words))] if rs.rand() > 0.1 else "oov%d" % rs.randint(9) for _ in range(L)]
+            sep = ["  ", " ", "\t", " \t "][rs.randint(4)]
+            lines.append(f"sp-k_{u}-seg-{u % 3}-{n + 1} " + sep.join(ws) if ws else f"sp-k_{u}-seg-{u % 3}-{n + 1}")
+    lines[3] += "   "
+    lines[7] = "  " + lines[7]
+    lines.insert(20, "")
+    lines.insert(31, "lonekey")
+    text = "\r\n".join(lines[:50]) + "\r\n" + "\n".join(lines[50:])        # no trailing newline
+    npth = tmp_path / "words_text"
+    npth.write_bytes(text.encode("utf-8"))
+    vocab_py, vocab_c = O.read_vocab(str(vp)), S.Vocab(str(vp))
+    assert len(vocab_c) == len(vocab_py) and all(vocab_c.id(w) == i for w, i in vocab_py.items())
+    assert vocab_c.id("missing") == -1
+    nbest = O.load_nbest(str(npth))
+    nb = S.NbestText(str(npth), threads=3)
+    assert not nb.needs_slow_path
+    want = [O.get_input_and_target(h, vocab_py) for hyps in nbest.values() for h in hyps]
+    assert nb.n_lines == len(want) and nb.n_utts == len(nbest) and nb.n_tokens == sum(len(x) for x, _ in want)
+    assert nb.contiguous == (list(nbest.keys()) == [k for i, k in enumerate(
+        [ln.strip().partition(" ")[0].rsplit("-", 1)[0] for ln in text.replace("\r\n", "\n").split("\n")])
+        if i == 0 or k != [ln.strip().partition(" ")[0].rsplit("-", 1)[0] for ln in text.replace("\r\n", "\n").split("\n")][i - 1]])
+    order = np.argsort(nb.utt_of_line, kind="stable")
+    for (l0, l1) in ((0, nb.n_lines), (5, 77)):
+        m = int(nb.offs[l1] - nb.offs[l0])
+        tok, tgt, pos = (np.full(m, -7, dtype=np.int32) for _ in range(3))
+        nb.tokenize(vocab_c, l0, l1, tok, tgt, pos)
+        for i in range(l0, l1):
+            a, b = int(nb.offs[i] - nb.offs[l0]), int(nb.offs[i + 1] - nb.offs[l0])
+            x, y = want[int(np.nonzero(order == i)[0][0])] if not nb.contiguous else want[i]
+            assert tok[a:b].tolist() == x and tgt[a:b].tolist() == y and pos[a:b].tolist() == list(range(b - a)), i
+    scores_in_ref_order = rs.randn(len(want)).astype(np.float32) * 37
+    ref = {}
+    it = iter(scores_in_ref_order.tolist())
+    for k, hyps in nbest.items():
+        ref[k] = [(h, next(it)) for h in hyps]
+    O.write_scores(ref, str(tmp_path / "ref.nn"))
+    by_line = np.empty(len(want), dtype=np.float32)
+    by_line[order] = scores_in_ref_order
+    assert nb.format_scores(by_line) == (tmp_path / "ref.nn").read_bytes()
+    # vocabulary errors and the flags of the slow path
+    (tmp_path / "bad.txt").write_text("a 0\nb\n")
+    with pytest.raises(ValueError, match="line 2"):
+        S.Vocab(str(tmp_path / "bad.txt"))
+    (tmp_path / "nbsp").write_bytes("u-1 a\u00a0b\n".encode("utf-8"))
+    assert S.NbestText(str(tmp_path / "nbsp")).needs_slow_path
+    (tmp_path / "cr").write_bytes(b"u-1 a\ru-2 b\n")
+    assert S.NbestText(str(tmp_path / "cr")).needs_slow_path
+    (tmp_path / "novocab.txt").write_text("<s> 0\na 1\n")
+    (tmp_path / "oov").write_bytes(b"u-1 a zzz\n")
+    nb2 = S.NbestText(str(tmp_path / "oov"))
+    t = np.zeros(4, dtype=np.int32)
+    from bayeslms_b200._lib import BlmError
+    with pytest.raises(BlmError, match="<unk>"):
+        nb2.tokenize(S.Vocab(str(tmp_path / "novocab.txt")), 0, 1, t, t.copy(), None)
+
+
 def test_shard_ranges_cover_and_balance():
     from bayeslms_b200.scorer import shard_ranges
     w = list(np.random.RandomState(0).randint(1, 50, size=103))

@@ -13,8 +13,10 @@ for f in blm_runtime blm_gemm blm_gemm2 blm_gemm_ln blm_gemm_sampled blm_element
   "$NVCC" "${FLAGS[@]}" -c "$SRC/$f.cu" -o "$ROOT/build/$f.o" &
   pids+=($!)
 done
+"$NVCC" "${FLAGS[@]}" -x cu -c "$SRC/blm_text.cpp" -o "$ROOT/build/blm_text.o" &
+pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libbayeslm_b200.so" \
   "$ROOT"/build/blm_runtime.o "$ROOT"/build/blm_gemm.o "$ROOT"/build/blm_gemm2.o "$ROOT"/build/blm_gemm_ln.o "$ROOT"/build/blm_gemm_sampled.o "$ROOT"/build/blm_elementwise.o \
-  "$ROOT"/build/blm_attention.o "$ROOT"/build/blm_lstm.o "$ROOT"/build/blm_train.o -cudart static
+  "$ROOT"/build/blm_attention.o "$ROOT"/build/blm_lstm.o "$ROOT"/build/blm_train.o "$ROOT"/build/blm_text.o -cudart static
 echo "built $OUT/libbayeslm_b200.so"
