@@ -134,6 +134,13 @@ SIGNATURES = {
     "blm_sgd_momentum_split": (C.c_int, [_p, _p, _p, _i64, _f, _f, _p, _f, _f, _p, _p, _p]),
     "blm_lstm_gates_act": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "blm_lstm_bwd_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p]),
+    "blm_vnn_noise": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "blm_rowgroup_add": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "blm_rowgroup_sum": (C.c_int, [_p, _i64, _i64, _i32, _p, _p]),
+    "blm_vnn_kl": (C.c_int, [_p, _p, _i64, _i32, _f, _p, _p, _p, _p]),
+    "blm_vnn_drho": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p]),
+    "blm_gp_lstm_bwd_step": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p, _p, _i32, _i64, _i32, _p, _p, _p, _i64,
+                                       _p, _p]),
     "blm_vocab_from_text": (_p, [C.c_char_p, _i64]),
     "blm_vocab_size": (_i64, [_p]),
     "blm_vocab_id": (_i32, [_p, C.c_char_p, _i64]),

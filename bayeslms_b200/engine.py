@@ -515,6 +515,14 @@ def v_layer_kl(layer) -> torch.Tensor:
     return out[0]
 
 
+def vnn_kl(vnn) -> torch.Tensor:
+    """KL of one Variational-LSTM cell's VNN from the hidden state the last training step left on the module."""
+    h = vnn.hidden_mean
+    out = torch.zeros(1, dtype=torch.float32, device=h.device)
+    ops.vnn_kl(h.contiguous(), vnn.hidden_lgstd.detach().view(-1), 0.0, out, None, None)
+    return out[0]
+
+
 def kl_sum(terms, minus_one: bool) -> torch.Tensor:
     """sum_i scale_i * 0.5 * mean(mu_i^2 - 2 rho_i + exp(2 rho_i) [- 1]) as a 0-dim device tensor."""
     dev = terms[0][0].device

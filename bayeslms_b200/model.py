@@ -582,6 +582,16 @@ class VNN(nn.Module):
         s = 1.0 / math.sqrt(input_size)
         self.sample = True
         self.hidden_lgstd = _lgstd_like((1, input_size), s)
+        self.hidden_mean = None     # pure hidden state of the last step of the last training-mode forward (model.py:2570)
+
+    def kl_divergence(self, prior=None):
+        """mean(hidden_mean^2 - 2 hidden_lgstd + exp(2 hidden_mean) - 1) / 2 as the reference writes it
+        (model.py:2545-2551; called by train.py:372-377 after a training-mode forward)."""
+        if prior is not None:
+            raise NotImplementedError("prior-centred KL is not on the train.py path")
+        if self.hidden_mean is None:
+            raise RuntimeError("VNN.kl_divergence() needs a training-mode forward first (it reads the hidden it stored)")
+        return _engine.vnn_kl(self)
 
 
 class VLSTMCell(nn.Module):

@@ -781,3 +781,72 @@ def sgd_momentum(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr: float, m
     with _op("sgd_momentum", 1):
         check(lib().blm_sgd_momentum(_ptr(p), _ptr(g), _ptr(v), p.numel(), lr, momentum, _ptr(norm_sq), max_norm,
                                      grad_scale, _stream()), "blm_sgd_momentum")
+
+
+# ------------------------------------------------------------------ training-mode Variational / GP LSTM cells
+def vnn_noise(e: torch.Tensor, rho: torch.Tensor) -> torch.Tensor:
+    """n[t, j] = e[t, j] * exp(rho[j]); e [T, H], rho [H]."""
+    T, H = e.shape
+    assert e.is_contiguous() and rho.is_contiguous() and rho.numel() == H
+    n = torch.empty_like(e)
+    with _op("vnn_noise", 1):
+        check(lib().blm_vnn_noise(_ptr(e), _ptr(rho), T, H, _ptr(n), _stream()), "blm_vnn_noise")
+    return n
+
+
+def rowgroup_add(x: torch.Tensor, r: torch.Tensor, G: int, B: int, *, prec: Optional[str] = None, want_f32: bool = True,
+                 out_f32: Optional[torch.Tensor] = None):
+    """out[g*B + b, :] = x[g*B + b, :] + r[g, :]; returns (fp32 or None, Split or None)."""
+    W = x.shape[-1]
+    assert x.is_contiguous() and r.is_contiguous() and x.numel() == G * B * W and r.numel() == G * W
+    y = out_f32 if out_f32 is not None else (torch.empty_like(x) if want_f32 else None)
+    sp = None
+    if prec is not None:
+        sp = Split(torch.empty(x.shape, dtype=torch.bfloat16, device=x.device),
+                   torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if prec == "bf16x3" else None)
+    with _op("rowgroup_add", 1):
+        check(lib().blm_rowgroup_add(_ptr(x), _ptr(r), G, B, W, _ptr(y), _ptr(None if sp is None else sp.hi),
+                                     _ptr(None if sp is None else sp.lo), _stream()), "blm_rowgroup_add")
+    return y, sp
+
+
+def rowgroup_sum(x: torch.Tensor, G: int, B: int) -> torch.Tensor:
+    """out[g, :] = sum_b x[g*B + b, :]."""
+    W = x.shape[-1]
+    assert x.is_contiguous() and x.numel() == G * B * W
+    out = torch.empty(G, W, dtype=torch.float32, device=x.device)
+    with _op("rowgroup_sum", 1):
+        check(lib().blm_rowgroup_sum(_ptr(x), G, B, W, _ptr(out), _stream()), "blm_rowgroup_sum")
+    return out
+
+
+def vnn_kl(h: torch.Tensor, rho: torch.Tensor, kl_scale: float, kl_out: Optional[torch.Tensor],
+           dh: Optional[torch.Tensor], drho: Optional[torch.Tensor]) -> None:
+    """VNN.kl_divergence on the pure last-step hidden h [B, H] (+= into kl_out[0]) and its scaled gradients (+=)."""
+    B, H = h.shape
+    assert h.is_contiguous() and rho.is_contiguous() and (dh is None or dh.is_contiguous())
+    with _op("vnn_kl", 1):
+        check(lib().blm_vnn_kl(_ptr(h), _ptr(rho), B, H, float(kl_scale), _ptr(kl_out), _ptr(dh), _ptr(drho), _stream()),
+              "blm_vnn_kl")
+
+
+def vnn_drho(dn: torch.Tensor, e: torch.Tensor, rho: torch.Tensor, drho: torch.Tensor) -> None:
+    """drho[j] += exp(rho[j]) sum_t dn[t, j] e[t, j]."""
+    T, H = e.shape
+    assert dn.is_contiguous() and e.is_contiguous() and dn.shape == e.shape
+    with _op("vnn_drho", 1):
+        check(lib().blm_vnn_drho(_ptr(dn), _ptr(e), _ptr(rho), T, H, _ptr(drho), _stream()), "blm_vnn_drho")
+
+
+def gp_lstm_bwd_step(acc5, coef, gate_type: int, c_prev, c_t, dout_t, dh_rec, dc, dc_is_zero: bool, dacc, dacc_s: Split,
+                     dcoef) -> None:
+    """Backward twin of :func:`gp_lstm_cell` for one timestep (see ``blm_gp_lstm_bwd_step``)."""
+    B, H = c_t.shape
+    for x in (c_prev, c_t, dout_t, dc, coef, dcoef):
+        assert x.is_contiguous()
+    assert acc5.stride(1) == 1 and dacc.stride(1) == 1 and dacc_s.hi.stride() == dacc.stride()
+    with _op("gp_lstm_bwd_step", 1):
+        check(lib().blm_gp_lstm_bwd_step(_ptr(acc5), acc5.stride(0), _ptr(coef), coef.shape[0], gate_type, _ptr(c_prev),
+                                         _ptr(c_t), _ptr(dout_t), _ptr(dh_rec), _ptr(dc), int(dc_is_zero), B, H, _ptr(dacc),
+                                         _ptr(dacc_s.hi), _ptr(dacc_s.lo), dacc.stride(0), _ptr(dcoef), _stream()),
+              "blm_gp_lstm_bwd_step")

@@ -81,6 +81,8 @@ _TID = engine._TID
 # Philox streams of the dropout sites: embedding / positional output, LSTM input and output, then four per layer
 _TID_DROP_PE, _TID_DROP_EMB, _TID_DROP_OUT, _TID_DROP_LAYER = 48, 49, 50, 64
 _DROP_SITES = {"attn": 0, "d1": 1, "ffn": 2, "d2": 3}
+_TID_VNN = 40              # Philox streams of the Variational-LSTM per-step noise: 40 + cell index
+_TID_GPCELL = 24           # ... and of the GP-LSTM cells' unit samples: 24 + 3 * cell index + {coef, weights, bias}
 V_NOISE_STD = engine.V_NOISE_STD
 _TID_VNOISE = engine.V_NOISE_TID   # Philox stream ids of the V-layer noise: 32 + layer index
 
@@ -90,9 +92,8 @@ class FineTuner:
 
     def __init__(self, model, lr: float, *, momentum: float = 0.9, clip: float = 0.25, prec: str = "bf16x3",
                  group=None, data_parallel: Optional[bool] = None):
-        if model.family not in ("bayes_tm", "gauss_tm", "v_tm", "std_tm", "bayes_lstm", "std_lstm"):
-            raise NotImplementedError("the fine-tune step is implemented for the Transformer families and the "
-                                      "Bayesian / standard two-layer LSTM")
+        if model.family not in ("bayes_tm", "gauss_tm", "v_tm", "std_tm", "bayes_lstm", "std_lstm", "gauss_lstm", "v_lstm"):
+            raise NotImplementedError(f"no fine-tune step for the {model.family} family")
         self.hidden = None
         self.model, self.lr, self.momentum, self.clip, self.prec = model, float(lr), float(momentum), float(clip), prec
         self.group = group
@@ -261,6 +262,8 @@ class FineTuner:
         self._begin_dropout(masks, seed)
         if self.model.family in ("bayes_lstm", "std_lstm"):
             return self._lstm_forward_backward(tokens_tb, targets_tb, kl_scale, hidden, eps, seed)
+        if self.model.family in ("gauss_lstm", "v_lstm"):
+            return self._cell_forward_backward(tokens_tb, targets_tb, kl_scale, hidden, eps, seed)
         m, prec, dev = self.model, self.prec, self.device
         T, B = tokens_tb.shape
         M, d, nhead = T * B, m.ninp, m.nhead
@@ -705,6 +708,254 @@ class FineTuner:
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
         return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
 
+    # ------------------------------------------------------------------ GP-LSTM / Variational-LSTM cell families
+    def _cell_layers(self):
+        """The recurrent stack of a GaussRNNModel / VariationalRNNModel as a flat list of layers (model.py:1619-1636,
+        2436-2437): nn.LSTM members contribute plain layers, GPLSTMCell / VLSTMCell one layer each."""
+        layers = []
+        for mi, member in enumerate(self.model.rnn.rnn):
+            pre = f"rnn.rnn.{mi}."
+            if isinstance(member, torch.nn.LSTM):
+                for l in range(member.num_layers):
+                    layers.append({"kind": "plain", "pre": pre, "mi": mi, "mod": member,
+                                   "names": {k: f"{pre}{k}_l{l}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}})
+            elif getattr(member, "kind", "") == "gp":
+                layers.append({"kind": "gp", "pre": pre, "mi": mi, "mod": member})
+            else:
+                layers.append({"kind": "v", "pre": pre, "mi": mi, "mod": member,
+                               "names": {"weight_ih": pre + "weights_ih", "weight_hh": pre + "weights_hh",
+                                         "bias_ih": pre + "bias_ih", "bias_hh": pre + "bias_hh"}})
+        return layers
+
+    def _cell_forward_backward(self, tokens_tb, targets_tb, kl_scale, hidden, eps, seed):
+        """One step of GaussRNNModel / VariationalRNNModel (model.py:1354-1359, 2411-2416; KL terms of train.py:360-377).
+        Rows are time-major (row = t*B + b).
+          * plain layers and variational cells run on the persistent recurrence kernel.  A variational cell built with
+            vnn_type 1 adds n_t = e_t exp(hidden_lgstd), e_t ~ N(0, 0.1^2) of shape (1, H), to h after every step
+            (model.py:2506-2507): additive noise commutes with the recurrent product, so W_hh n_{t-1} enters the hoisted
+            input gates as a per-step bias row and the kernel runs on the pure hidden state; its KL
+            (VNN.kl_divergence, model.py:2545-2551) is taken on the pure hidden of the last step;
+          * a GP cell steps through one [B, 5H] product per timestep on [W_hh; W_g(h part)] (gate replaced by the GP
+            mixture, bias_ih doubled, model.py:1743-1777), keeps every pre-activation, and is walked backwards by
+            blm_gp_lstm_bwd_step; its unit samples (coef, weights, bias) once per step only when GPNN.sample is set.
+        ``eps``: {'cell<mi>': (T, 1, H) noise (variational) | {'coef','weights','bias'} (GP)}; else Philox(``seed``)."""
+        m, prec, dev, g = self.model, self.prec, self.device, self.g
+        T, B = tokens_tb.shape
+        M, H = T * B, m.nhid
+        eps = _to_device(eps or {}, dev)
+        if hidden is None:
+            hidden = m.init_hidden(B)
+        h0, c0 = hidden[0].detach().float().contiguous(), hidden[1].detach().float().contiguous()
+        tok = tokens_tb.reshape(-1).to(torch.int32)
+        tgt = targets_tb.reshape(-1).to(torch.int32)
+        lengths = torch.full((B,), T, dtype=torch.int32, device=dev)
+        self.flat_g.zero_()
+        layers = self._cell_layers()
+        drop_emb = self._site(m.p_drop, _TID_DROP_EMB, ("emb",))
+        drop_out = self._site(m.p_drop, _TID_DROP_OUT, ("out",))
+        x32, x = ops.embed(tok, None, m.encoder.weight.detach().float(), None, 1.0, prec=prec, want_f32=drop_emb is not None)
+        if drop_emb is not None:
+            _, x = ops.dropout(x32, drop_emb, prec=prec, want_f32=False)
+        hT, cT, out32 = [], [], None
+        for li, L in enumerate(layers):
+            last = li == len(layers) - 1
+            mod, mi = L["mod"], L["mi"]
+            L["x"] = x
+            if L["kind"] == "gp":
+                out32, x, h_l, c_l = self._gp_cell_forward(L, x, h0[li], c0[li], lengths, T, B, H, eps.get(f"cell{mi}"), seed)
+            else:
+                named = L.setdefault("params", {k: _param(m, n) for k, n in L["names"].items()})
+                w_ih, L["w_ih_t"] = self._w2(named["weight_ih"])
+                L["w_hh"], L["w_hh_t"] = self._w2(named["weight_hh"])
+                bias = (2.0 * named["bias_ih"]) if L["kind"] == "v" else (named["bias_ih"] + named["bias_hh"])
+                gates = self._f32(M, 4 * H)
+                _gemm(x, w_ih, prec=prec, bias=bias.contiguous(), out_f32=gates, tag=f"lstm_in{li + 1}")
+                noisy = L["kind"] == "v" and mod.vnn_type == 1 and (f"cell{mi}" in eps or seed is not None)
+                L["noisy"] = noisy
+                if noisy:
+                    rho = mod.vnn.hidden_lgstd.detach().view(-1)
+                    e = eps.get(f"cell{mi}")
+                    E = (e.reshape(T, H).contiguous() if e is not None else
+                         ops.philox_normal(seed, engine._stream_id(_TID_VNN + mi, 0), T * H, dev, scale=V_NOISE_STD).view(T, H))
+                    N = ops.vnn_noise(E, rho)
+                    n_prev = torch.cat([torch.zeros(1, H, dtype=torch.float32, device=dev), N[:-1]], 0)
+                    g_n = self._f32(T, 4 * H)
+                    _gemm(ops.split(n_prev, prec), L["w_hh"], prec=prec, out_f32=g_n, tag="vnn_bias")   # W_hh n_{t-1}
+                    ops.rowgroup_add(gates, g_n, T, B, out_f32=gates)
+                    L.update(E=E, N=N)
+                need32 = noisy or (last and drop_out is not None)
+                out32, out, h_l, c_l = ops.lstm_layer(gates, L["w_hh"], h0[li], c0[li], lengths, T, B, H, prec=prec,
+                                                      want_f32=need32, want_split=True)
+                L.update(gates=gates, out=out, h_pure=h_l)
+                if L["kind"] == "v":
+                    mod.vnn.hidden_mean = h_l
+                if noisy:
+                    out32, x = ops.rowgroup_add(out32, L["N"], T, B, prec=prec)
+                    h_l, _ = ops.rowgroup_add(h_l, L["N"][T - 1:T].contiguous(), 1, B)
+                else:
+                    x = out
+                L["out_fed"] = x              # what the next layer / step consumed (noised for a variational cell)
+            hT.append(h_l)
+            cT.append(c_l)
+        self.hidden = (torch.stack(hT), torch.stack(cT))
+        if drop_out is not None:
+            _, x = ops.dropout(out32, drop_out, prec=prec, want_f32=False)
+
+        dout, ce, kl, loss = self._loss_and_decoder_grads(x, tgt)
+        if drop_out is not None:
+            dout, _ = ops.dropout(dout, drop_out, out_f32=dout)
+
+        for li in range(len(layers) - 1, -1, -1):
+            L = layers[li]
+            if L["kind"] == "gp":
+                dout = self._gp_cell_backward(L, dout, h0[li], c0[li], T, B, H, kl, kl_scale, eps.get(f"cell{L['mi']}"), seed)
+                continue
+            mod, named, nm = L["mod"], L["params"], L["names"]
+            h0s = ops.split(h0[li], prec)
+            cat = lambda s: Split(torch.cat([h0s.hi, s.hi[:M - B]], 0),  # noqa: E731
+                                  None if h0s.lo is None else torch.cat([h0s.lo, s.lo[:M - B]], 0))
+            gates = L["gates"]
+            _gemm(cat(L["out"]), L["w_hh"], prec=prec, resid=gates, out_f32=gates, tag="lstm_rebuild")
+            c_all = ops.lstm_gates_act(gates, c0[li], T, B, H)
+            if L["kind"] == "v" and mod.vnn_type == 1:
+                rho = mod.vnn.hidden_lgstd.detach().view(-1)
+                g_rho = g[L["pre"] + "vnn.hidden_lgstd"].view(-1)
+                s1 = ops.rowgroup_sum(dout, T, B) if L["noisy"] else None       # d n_t from the consumers of h_t + n_t
+                # KL on the pure last hidden (train.py:372-377): value, and gradient into the last step's dh
+                ops.vnn_kl(L["h_pure"], rho, kl_scale, kl, dout[M - B:], g_rho)
+            dG = self._f32(M, 4 * H)
+            dGs = ops.empty_split(M, 4 * H, prec, dev)
+            dc = self._f32(B, H)
+            dh = [self._f32(B, H), self._f32(B, H)]
+            rec = None
+            for t in range(T - 1, -1, -1):
+                sl = slice(t * B, (t + 1) * B)
+                c_prev = c0[li] if t == 0 else c_all[(t - 1) * B:t * B]
+                dGt = Split(dGs.hi[sl], None if dGs.lo is None else dGs.lo[sl])
+                ops.lstm_bwd_step(gates[sl], c_prev, c_all[sl], dout[sl], rec, dc, t == T - 1, dG[sl], dGt)
+                if t > 0:
+                    rec = dh[t & 1]
+                    _gemm(dGt, L["w_hh_t"], prec=prec, out_f32=rec, tag="lstm_dh")
+            dGT = _tsplit(dG, prec)
+            self._wgrad(dGT, _tbf16(L["x"], prec), g[nm["weight_ih"]], f"lstm_ih{li + 1}")
+            self._wgrad(dGT, _tbf16(cat(L["out_fed"]), prec), g[nm["weight_hh"]], f"lstm_hh{li + 1}")
+            if L["kind"] == "v":        # bias_ih enters both products, bias_hh never (model.py:2519)
+                ops.colsum(dG, g[nm["bias_ih"]], scale=2.0)
+            else:
+                ops.colsum(dG, g[nm["bias_ih"]])
+                ops.colsum(dG, g[nm["bias_hh"]])
+            if L["kind"] == "v" and L["noisy"]:
+                # d n_t = sum_b (dout_t + dh_rec_t) = s1[t] + (sum_b dG_{t+1}) W_hh ; d rho += exp(rho) sum_t d n_t e_t
+                s2 = ops.rowgroup_sum(dG, T, B)
+                s2 = torch.cat([s2[1:], torch.zeros(1, 4 * H, dtype=torch.float32, device=dev)], 0)
+                dn = self._f32(T, H)
+                _gemm(ops.split(s2, prec), L["w_hh_t"], prec=prec, resid=s1, out_f32=dn, tag="vnn_dn")
+                ops.vnn_drho(dn, L["E"], rho, g_rho)
+            dx = self._f32(M, L["x"].hi.shape[1])
+            _gemm(dGs, L["w_ih_t"], prec=prec, out_f32=dx, tag="dgrad:lstm_in")
+            dout = dx
+        if drop_emb is not None:
+            dout, _ = ops.dropout(dout, drop_emb, out_f32=dout)
+        ops.embed_bwd(dout, tok, 1.0, g["encoder.weight"])
+        ops.reduce_sum(ce, loss)
+        ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
+        return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
+
+    def _gp_cell_forward(self, L, x: Split, h0, c0, lengths, T, B, H, le, seed):
+        """GPLSTMCell.forward (model.py:1720-1777) keeping what the backward pass needs."""
+        prec, dev, mod = self.prec, self.device, L["mod"]
+        gp, nin, mi = mod.gpnn, mod.input_size, L["mi"]
+        M = T * B
+        coef, wg, bg = gp.coef_mean.detach(), gp.weights_mean.detach(), gp.bias_mean.detach()
+        noise = bool(gp.sample) and (le is not None or seed is not None)
+        L["noise"] = noise
+        if noise:
+            ge = (lambda k: None) if le is None else le.get
+            tid = _TID_GPCELL + 3 * mi
+            if gp.gpnn_type in (1, 3):
+                coef = self._reparam32(coef, gp.coef_lgstd.detach(), tid, ge("coef"), seed)
+            if gp.gpnn_type in (2, 3):
+                wg = self._reparam32(wg, gp.weights_lgstd.detach(), tid + 1, ge("weights"), seed)
+                bg = self._reparam32(bg, gp.bias_lgstd.detach(), tid + 2, ge("bias"), seed)
+        coef = coef.contiguous()
+        w_in32 = torch.cat([mod.weights_ih.detach(), wg[:, :nin]], 0).contiguous()      # [5H, nin]
+        w_rec32 = torch.cat([mod.weights_hh.detach(), wg[:, nin:]], 0).contiguous()     # [5H, H]
+        bias5 = torch.cat([2.0 * mod.bias_ih.detach(), bg.reshape(-1)], 0).contiguous()
+        w_in, L["w_in_t"] = self._w2(w_in32)
+        w_rec, L["w_rec_t"] = self._w2(w_rec32)
+        pre5 = self._f32(M, 5 * H)
+        _gemm(x, w_in, prec=prec, bias=bias5, out_f32=pre5, tag="gplstm_in")
+        acc_all, c_all = self._f32(M, 5 * H), self._f32(M, H)
+        out32 = self._f32(M, H)
+        outs = ops.empty_split(M, H, prec, dev)
+        h, c = h0.clone(), c0.clone()
+        h_op = ops.split(h, prec)
+        for t in range(T):
+            rows = slice(t * B, (t + 1) * B)
+            _gemm(h_op, w_rec, prec=prec, resid=pre5[rows], out_f32=acc_all[rows], tag="gplstm_rec")
+            ops.gp_lstm_cell(acc_all[rows], coef, mod.gate_type, lengths, t, c, h, h_op, out32[rows],
+                             Split(outs.hi[rows], None if outs.lo is None else outs.lo[rows]))
+            c_all[rows].copy_(c)
+        L.update(acc=acc_all, c_all=c_all, out=outs, coef=coef)
+        return out32, outs, h, c
+
+    def _gp_cell_backward(self, L, dout, h0, c0, T, B, H, kl, kl_scale, le, seed):
+        prec, dev, g, mod = self.prec, self.device, self.g, L["mod"]
+        gp, nin, pre, mi = mod.gpnn, mod.input_size, L["pre"], L["mi"]
+        M = T * B
+        dacc = self._f32(M, 5 * H)
+        daccs = ops.empty_split(M, 5 * H, prec, dev)
+        dc = self._f32(B, H)
+        dh = [self._f32(B, H), self._f32(B, H)]
+        gc = g[pre + "gpnn.coef_mean"]
+        rec = None
+        for t in range(T - 1, -1, -1):
+            sl = slice(t * B, (t + 1) * B)
+            c_prev = c0 if t == 0 else L["c_all"][(t - 1) * B:t * B]
+            dst = Split(daccs.hi[sl], None if daccs.lo is None else daccs.lo[sl])
+            ops.gp_lstm_bwd_step(L["acc"][sl], L["coef"], mod.gate_type, c_prev, L["c_all"][sl], dout[sl], rec, dc, t == T - 1,
+                                 dacc[sl], dst, gc)
+            if t > 0:
+                rec = dh[t & 1]
+                _gemm(dst, L["w_rec_t"], prec=prec, out_f32=rec, tag="gplstm_dh")
+        h0s = ops.split(h0, prec)
+        hprev = Split(torch.cat([h0s.hi, L["out"].hi[:M - B]], 0),
+                      None if h0s.lo is None else torch.cat([h0s.lo, L["out"].lo[:M - B]], 0))
+        # weight gradients: rows [0, 4H) of the stacked products belong to the cell's own matrices, rows [4H, 5H) to the
+        # GP unit, whose weight is laid out [H, nin + H] = [x part | h part] (torch.cat([inp, hx]), model.py:1866-1868)
+        d4, dz = dacc[:, :4 * H], dacc[:, 4 * H:]
+        d4t, dzt = _tsplit(d4, prec), _tsplit(dz, prec)
+        xt, ht = _tbf16(L["x"], prec), _tbf16(hprev, prec)
+        gw = g[pre + "gpnn.weights_mean"]
+        self._wgrad(d4t, xt, g[pre + "weights_ih"], "gp_ih")
+        self._wgrad(d4t, ht, g[pre + "weights_hh"], "gp_hh")
+        self._wgrad(dzt, xt, gw[:, :nin], "gp_wx")
+        self._wgrad(dzt, ht, gw[:, nin:], "gp_wh")
+        ops.colsum(d4, g[pre + "bias_ih"], scale=2.0)          # bias_ih is added twice, bias_hh never (model.py:1748-1752)
+        gb = g[pre + "gpnn.bias_mean"]
+        ops.colsum(dz, gb)
+        sid = lambda k: engine._stream_id(_TID_GPCELL + 3 * mi + k, 0)  # noqa: E731
+        t_ = gp.gpnn_type
+        if t_ in (1, 3):
+            if L["noise"]:
+                ops.reparam_bwd(gc, gp.coef_lgstd.detach(), gc, g[pre + "gpnn.coef_lgstd"],
+                                eps=None if le is None else le.get("coef"), seed=seed, stream_id=sid(0))
+            ops.kl_gauss(gp.coef_mean.detach(), gp.coef_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.coef_mean.detach(), gp.coef_lgstd.detach(), kl_scale, gc, g[pre + "gpnn.coef_lgstd"])
+        if t_ in (2, 3):
+            if L["noise"]:
+                ops.reparam_bwd(gw, gp.weights_lgstd.detach(), gw, g[pre + "gpnn.weights_lgstd"],
+                                eps=None if le is None else le.get("weights"), seed=seed, stream_id=sid(1))
+                ops.reparam_bwd(gb, gp.bias_lgstd.detach(), gb, g[pre + "gpnn.bias_lgstd"],
+                                eps=None if le is None else le.get("bias"), seed=seed, stream_id=sid(2))
+            ops.kl_gauss(gp.weights_mean.detach(), gp.weights_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.weights_mean.detach(), gp.weights_lgstd.detach(), kl_scale, gw, g[pre + "gpnn.weights_lgstd"])
+            ops.kl_gauss(gp.bias_mean.detach(), gp.bias_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.bias_mean.detach(), gp.bias_lgstd.detach(), kl_scale, gb, g[pre + "gpnn.bias_lgstd"])
+        dx = self._f32(M, nin)
+        _gemm(daccs, L["w_in_t"], prec=prec, out_f32=dx, tag="dgrad:gplstm_in")
+        return dx
+
     def _gp_backward(self, layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, le, seed):
         """Gradients of the GP unit (model.py:1780-1902): weights / bias / coef means, their log-sigmas
         through the reparameterisation when the unit samples, and the unit's KL (the '-1' variant)."""
@@ -902,6 +1153,13 @@ def _engine_name(name: str) -> str:
     if m:
         return f"rnn.{m[1]}_{m[2]}_mean_{int(m[3]) + 1}"
     return name
+
+
+def _param(model, name: str) -> torch.Tensor:
+    obj = model
+    for part in name.split("."):
+        obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+    return obj.detach()
 
 
 def _to_device(obj, dev):

@@ -506,6 +506,33 @@ int blm_sgd_momentum_split(float* p, const float* g, float* v, int64_t n, float 
                            const float* norm_sq, float max_norm, float grad_scale, blm_bf16* out_hi,
                            blm_bf16* out_lo, blm_stream stream);
 
+/* ------------------------------------------------- training-mode Variational / GP LSTM cells (row a20)
+ * Variational cell (VLSTMCell + VNN, model.py:2470-2579): in training, after every step h <- h + n_t,
+ * n_t = e_t exp(hidden_lgstd), e_t ~ N(0, 0.1^2) of shape (1, H) shared by the batch rows.  Additive noise commutes
+ * with the recurrent product, so W_hh n_{t-1} is folded into the hoisted input gates as a per-step bias row
+ * (blm_rowgroup_add) and blm_lstm_layer runs unchanged on the pure hidden state.
+ *   blm_vnn_noise:    n[t, j] = e[t, j] exp(rho[j])                                          (model.py:2557-2563)
+ *   blm_rowgroup_add: out[g B + b, :] = x[g B + b, :] + r[g, :], fp32 and / or bf16 (hi, lo); out_f32 may alias x
+ *   blm_rowgroup_sum: out[g, :] = sum_b x[g B + b, :]  (gradient of a per-step row; deterministic)
+ *   blm_vnn_kl:       kl_out[0] += mean_{B,H}(h^2 - 2 rho + exp(2 h) - 1) / 2 on the pure last-step hidden
+ *                     (VNN.kl_divergence, model.py:2545-2551, as written); dh += kl_scale dKL/dh, drho += kl_scale dKL/drho
+ *   blm_vnn_drho:     drho[j] += exp(rho[j]) sum_t dn[t, j] e[t, j]
+ * GP cell (GPLSTMCell.Gplstm, model.py:1743-1777): blm_gp_lstm_bwd_step is the backward twin of blm_gp_lstm_cell for
+ * one timestep: from acc5 (pre-activations i, f, g, o, z), the cell states and dh = dout + dh_rec it writes the
+ * gradient of the five pre-activation blocks (the replaced gate's own block gets 0) as fp32 and bf16 (hi, lo),
+ * updates the carried dL/dc in place and accumulates dcoef[k, u] += sum_b dgate act_k(z).                        */
+int blm_vnn_noise(const float* e, const float* rho, int64_t T, int32_t H, float* n, blm_stream stream);
+int blm_rowgroup_add(const float* x, const float* r, int64_t G, int64_t B, int32_t W, float* out_f32, blm_bf16* out_hi,
+                     blm_bf16* out_lo, blm_stream stream);
+int blm_rowgroup_sum(const float* x, int64_t G, int64_t B, int32_t W, float* out, blm_stream stream);
+int blm_vnn_kl(const float* h, const float* rho, int64_t B, int32_t H, float kl_scale, float* kl_out, float* dh,
+               float* drho, blm_stream stream);
+int blm_vnn_drho(const float* dn, const float* e, const float* rho, int64_t T, int32_t H, float* drho, blm_stream stream);
+int blm_gp_lstm_bwd_step(const float* acc5, int64_t ld, const float* coef, int32_t n_act, int32_t gate_type,
+                         const float* c_prev, const float* c_t, const float* dout, const float* dh_rec, float* dc,
+                         int32_t dc_is_zero, int64_t B, int32_t H, float* dacc, blm_bf16* dacc_hi, blm_bf16* dacc_lo,
+                         int64_t ldd, float* dcoef, blm_stream stream);
+
 /* ------------------------------------------------- scorer file formats (host code, no GPU work)
  * The reference scorer tokenises one hypothesis at a time in Python (load_nbest score.py:20-51, read_vocab :63-84,
  * get_input_and_target :87-120) and formats one score at a time (write_scores :283-303).  These entry points do the

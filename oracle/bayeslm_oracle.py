@@ -321,7 +321,7 @@ def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Conf
     masks = masks or {}
     if cfg.family in ("gauss_lstm", "v_lstm"):
         assert not return_hidden_states
-        return cell_rnn_forward(sd, tokens, hidden, cfg)
+        return cell_rnn_forward(sd, tokens, hidden, cfg, eps, masks)
     sd, cfg = canonical(sd, cfg)
     p = lstm_flat_parameters(sd, cfg.bayes_pos, eps)
     x = F.embedding(tokens, sd["encoder.weight"])
@@ -360,17 +360,27 @@ def gp_lstm_layout(gauss_pos: str) -> List[Tuple[str, int, int]]:
     return [("gp", int(t[0]), int(t[1])), ("gp", int(t[2]), int(t[1]))]
 
 
-def gp_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, gate_type: int):
-    """GPLSTMCell.forward / Gplstm in eval mode (posterior means), model.py:1720-1777, gate_type 1..4:
+def gp_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, gate_type: int, gpnn_type: int = 0,
+                       eps: Optional[Dict[str, Tensor]] = None):
+    """GPLSTMCell.forward / Gplstm, model.py:1720-1777, gate_type 1..4:
     gates = W_ih x + b_ih + W_hh h + b_ih (bias_ih twice, bias_hh never); the chosen gate is replaced by
-    GPNN(cat[x, h]) = sum_i coef[i] * act_i(W_g cat[x, h] + b_g)."""
+    GPNN(cat[x, h]) = sum_i coef[i] * act_i(W_g cat[x, h] + b_g).  ``eps`` = {'coef','weights','bias'}: the GP unit's
+    parameters sampled ONCE per forward call (sample_parameters at model.py:1721-1723; used only when the unit is in
+    training mode with .sample set, model.py:1876-1883); None = posterior means."""
     acts = LSTM_GP_ACTS[gate_type]
+    coef, wg, bg = sd[pre + "gpnn.coef_mean"], sd[pre + "gpnn.weights_mean"], sd[pre + "gpnn.bias_mean"]
+    if eps is not None:
+        if gpnn_type in (1, 3):
+            coef = coef + torch.exp(sd[pre + "gpnn.coef_lgstd"]) * eps["coef"]
+        if gpnn_type in (2, 3):
+            wg = wg + torch.exp(sd[pre + "gpnn.weights_lgstd"]) * eps["weights"]
+            bg = bg + torch.exp(sd[pre + "gpnn.bias_lgstd"]) * eps["bias"]
     outs = []
     for t in range(x.shape[0]):
         gates = F.linear(x[t], sd[pre + "weights_ih"], sd[pre + "bias_ih"]) + F.linear(h, sd[pre + "weights_hh"], sd[pre + "bias_ih"])
         i, f, g, o = gates.chunk(4, 1)
-        z = F.linear(torch.cat([x[t], h], -1), sd[pre + "gpnn.weights_mean"], sd[pre + "gpnn.bias_mean"])
-        gp = sum(getattr(torch, a)(z) * sd[pre + "gpnn.coef_mean"][k] for k, a in enumerate(acts))
+        z = F.linear(torch.cat([x[t], h], -1), wg, bg)
+        gp = sum(getattr(torch, a)(z) * coef[k] for k, a in enumerate(acts))
         i = gp if gate_type == 1 else torch.sigmoid(i)
         f = gp if gate_type == 2 else torch.sigmoid(f)
         g = gp if gate_type == 3 else torch.tanh(g)
@@ -381,17 +391,51 @@ def gp_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, gate_t
     return torch.stack(outs), h, c
 
 
-def cell_rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Config):
+def v_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, noise: Optional[Tensor] = None):
+    """VLSTMCell.forward (model.py:2493-2531): the plain cell with bias_ih on both products; with ``noise`` (T, 1, H)
+    -- training mode of a cell built with vnn_type 1 -- every step's h gets noise[t] * exp(vnn.hidden_lgstd) added
+    before it is stored and fed back (VNN.forward, model.py:2565-2579; the draw is normal_(0, 0.1), model.py:2561).
+    Returns (outputs, h, c, hidden_mean) where hidden_mean is the PURE h of the last step, what VNN.kl_divergence
+    reads (model.py:2549, 2570)."""
+    outs, h_mean = [], h
+    for t in range(x.shape[0]):
+        gates = F.linear(x[t], sd[pre + "weights_ih"], sd[pre + "bias_ih"]) + F.linear(h, sd[pre + "weights_hh"], sd[pre + "bias_ih"])
+        i, f, g, o = gates.chunk(4, 1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        h_mean = h
+        if noise is not None:
+            h = h + noise[t] * torch.exp(sd[pre + "vnn.hidden_lgstd"])
+        outs.append(h)
+    return torch.stack(outs), h, c, h_mean
+
+
+def kl_vnn(sd: SD, pre: str, hidden_mean: Tensor) -> Tensor:
+    """VNN.kl_divergence as written (model.py:2545-2551): mean(h^2 - 2 lgstd + exp(2 h) - 1) / 2 over (B, H), with h the
+    pure hidden state of the last step ("hidden_mean") -- the exponential is of the hidden, not of the log-sigma."""
+    ls = sd[pre + "vnn.hidden_lgstd"]
+    return torch.mean(hidden_mean ** 2 - ls * 2. + torch.exp(hidden_mean * 2) - 1) / 2.
+
+
+def cell_rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Config, eps: Optional[dict] = None,
+                     masks: Optional[Dict[str, Tensor]] = None, aux: Optional[dict] = None):
     """GaussRNNModel.forward (model.py:1354-1359, GPLSTM.forward 1638-1671) and VariationalRNNModel.forward
-    (model.py:2411-2416, VariationalLSTM.forward 2447-2468) in eval mode.  Returns logits (T, B, V), (h, c)."""
+    (model.py:2411-2416, VariationalLSTM.forward 2447-2468).  Returns logits (T, B, V), (h, c).
+    eps = None: eval mode.  Training mode: eps = {'cell<mi>': ...} per member of rnn.rnn -- for a GP cell the
+    {'coef','weights','bias'} draws (only meaningful when GPNN.sample is set), for a variational cell with vnn_type 1
+    the (T, 1, H) per-step noise (already N(0, 0.1^2)); masks = {'emb','out'} dropout multipliers (model.py:1355,1357);
+    aux receives 'cell<mi>.hidden_mean' for the VNN KL."""
+    eps, masks = eps or {}, masks or {}
     x = F.embedding(tokens, sd["encoder.weight"])
+    if "emb" in masks:
+        x = x * masks["emb"]
     h0, c0 = hidden
     hs, cs, li = [], [], 0
     if cfg.family == "gauss_lstm":
-        for mi, (kind, a, _) in enumerate(gp_lstm_layout(cfg.gauss_pos)):
+        for mi, (kind, a, gt) in enumerate(gp_lstm_layout(cfg.gauss_pos)):
             pre = f"rnn.rnn.{mi}."
             if kind == "gp":
-                x, h, c = gp_lstm_cell_layer(x, h0[li], c0[li], sd, pre, a)
+                x, h, c = gp_lstm_cell_layer(x, h0[li], c0[li], sd, pre, a, gt, eps.get(f"cell{mi}"))
                 hs.append(h), cs.append(c)
                 li += 1
             else:
@@ -403,11 +447,15 @@ def cell_rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg:
     elif cfg.family == "v_lstm":
         for mi in range(2):   # VLSTMCell.lstmcell, model.py:2515-2531: bias_ih on both products
             pre = f"rnn.rnn.{mi}."
-            x, h, c = lstm_layer(x, h0[mi], c0[mi], sd[pre + "weights_ih"], sd[pre + "weights_hh"], sd[pre + "bias_ih"],
-                                 sd[pre + "bias_ih"])
+            noise = eps.get(f"cell{mi}") if cfg.v_pos[mi] == "1" else None
+            x, h, c, h_mean = v_lstm_cell_layer(x, h0[mi], c0[mi], sd, pre, noise)
+            if aux is not None:
+                aux[f"cell{mi}.hidden_mean"] = h_mean
             hs.append(h), cs.append(c)
     else:
         raise ValueError(cfg.family)
+    if "out" in masks:
+        x = x * masks["out"]
     return F.linear(x, sd["decoder.weight"], sd["decoder.bias"]), (torch.stack(hs), torch.stack(cs))
 
 
@@ -482,6 +530,18 @@ def model_kl(sd: SD, cfg: Config, aux: Optional[dict] = None) -> Tensor:
         return torch.zeros(())
     if fam == "gauss_tm":
         return kl_gpnn(sd, "transformerlayers.0.gpnn.", cfg.gauss_pos) if cfg.gauss_pos <= 3 else torch.zeros(())
+    if fam == "gauss_lstm":      # train.py:360-371: the GP cells' units, when the position string selects a GP type 1..3
+        kl = torch.zeros(())
+        for mi, (kind, _, gt) in enumerate(gp_lstm_layout(cfg.gauss_pos)):
+            if kind == "gp" and 0 < gt <= 3:
+                kl = kl + kl_gpnn(sd, f"rnn.rnn.{mi}.gpnn.", gt)
+        return kl
+    if fam == "v_lstm":          # train.py:372-377
+        kl = torch.zeros(())
+        for mi in range(2):
+            if cfg.v_pos[mi] == "1":
+                kl = kl + kl_vnn(sd, f"rnn.rnn.{mi}.", aux[f"cell{mi}.hidden_mean"])
+        return kl
     if fam == "v_tm":
         kl = torch.zeros(())
         for i, kind in enumerate(tm_layer_kinds(cfg)):
@@ -667,7 +727,9 @@ def finetune_loss(sd: SD, tokens: Tensor, targets: Tensor, cfg: Config, eps: Opt
     ``sd`` may hold tensors requiring grad; autograd through this function is the gradient oracle.
     ``masks``: the step's dropout draws as injected multiplier tensors (see transformer_hidden / rnn_forward)."""
     aux: dict = {}
-    if cfg.family.endswith("lstm"):
+    if cfg.family in ("gauss_lstm", "v_lstm"):
+        logits, _ = cell_rnn_forward(sd, tokens, hidden, cfg, eps, masks, aux)
+    elif cfg.family.endswith("lstm"):
         logits, _ = rnn_forward(sd, tokens, hidden, cfg, eps, masks=masks)
     else:
         h = transformer_hidden(sd, tokens, cfg, eps, aux, masks)

@@ -384,3 +384,109 @@ def test_lstm_finetune_reduces_the_loss_with_carried_state():
         last = float(ft.step(x, y, 0.01, seed=2 + i, hidden=hidden)[0])
         hidden = ft.hidden
     assert last < l0 - 0.05, (l0, last)
+
+
+# ------------------------------------------------------------------------------ GP-LSTM / Variational-LSTM cells
+def _build_cells(family, pos, H=128, dropout=0.0):
+    from bayeslms_b200 import model as M
+    torch.manual_seed(7)
+    if family == "v_lstm":
+        net = M.VariationalRNNModel("LSTM", V, H, H, 2, dropout, True, pos)
+        cfg = O.Config(family="v_lstm", ntoken=V, ninp=H, nhid=H, nlayers=2, v_pos=pos)
+    else:
+        net = M.GaussRNNModel("LSTM", V, H, H, 2, dropout, True, pos)
+        cfg = O.Config(family="gauss_lstm", ntoken=V, ninp=H, nhid=H, nlayers=2, gauss_pos=pos)
+    with torch.no_grad():
+        net.decoder.bias.uniform_(-0.1, 0.1)
+        for n, p in net.named_parameters():      # the cells initialise their biases to zero: make every path non-trivial
+            if "bias" in n:
+                p.add_(torch.randn_like(p) * 0.05)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net, sd, cfg
+
+
+@pytest.mark.parametrize("family,pos,sampled,dropout", [
+    ("v_lstm", "11", True, 0.0), ("v_lstm", "01", True, 0.0), ("v_lstm", "11", False, 0.0), ("v_lstm", "11", True, 0.3),
+    ("gauss_lstm", "31", False, 0.0), ("gauss_lstm", "31", True, 0.0), ("gauss_lstm", "333", True, 0.0),
+    ("gauss_lstm", "3330", True, 0.0), ("gauss_lstm", "23", True, 0.3), ("gauss_lstm", "12", False, 0.0),
+    ("gauss_lstm", "4131", True, 0.0)])
+def test_cell_families_finetune_step_matches_oracle_autograd(family, pos, sampled, dropout):
+    """GaussRNNModel / VariationalRNNModel fine-tune step (train.py:319-377): loss, the KL of the GP units / of the VNNs,
+    every gradient and the carried-out state against autograd through the oracle's training-mode cells (pinned on the
+    reference by tests/golden/*_train_*.pt), with injected noise: per-step (T, 1, H) VNN noise, or the GP units'
+    (coef, weights, bias) draws with GPNN.sample set; and with injected dropout masks."""
+    from bayeslms_b200.trainer import FineTuner
+    net, sd, cfg = _build_cells(family, pos, dropout=dropout)
+    T, B, H, kl_scale = 9, 4, 128, 0.37
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, V, (T, B), generator=g)
+    y = torch.randint(0, V, (T, B), generator=g)
+    hidden = (torch.randn(2, B, H, generator=g) * 0.3, torch.randn(2, B, H, generator=g) * 0.3)
+    eps = None
+    if sampled:
+        eps = {}
+        if family == "v_lstm":
+            for mi in range(2):
+                if pos[mi] == "1":
+                    eps[f"cell{mi}"] = torch.randn(T, 1, H, generator=g) * 0.1
+        else:
+            for mi, (kind, _, gt) in enumerate(O.gp_lstm_layout(pos)):
+                if kind == "gp":
+                    net.rnn.rnn[mi].gpnn.sample = True
+                    pre, e = f"rnn.rnn.{mi}.gpnn.", {}
+                    if gt in (1, 3):
+                        e["coef"] = torch.randn(sd[pre + "coef_mean"].shape, generator=g)
+                    if gt in (2, 3):
+                        e["weights"] = torch.randn(sd[pre + "weights_mean"].shape, generator=g)
+                        e["bias"] = torch.randn(sd[pre + "bias_mean"].shape, generator=g)
+                    eps[f"cell{mi}"] = e
+    masks = None
+    if dropout:
+        masks = {k: (torch.rand(T, B, H, generator=g) >= dropout).float() / (1.0 - dropout) for k in ("emb", "out")}
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items() if k != "decoder.weight"}
+    leaf["decoder.weight"] = leaf["encoder.weight"]
+    loss, ce, kl = O.finetune_loss(leaf, x, y.view(-1), cfg, eps, kl_scale, hidden=hidden, masks=masks)
+    loss.backward()
+    want_g = {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v))
+              for k, v in leaf.items() if k != "decoder.weight" and v.requires_grad}
+    with torch.no_grad():
+        _, want_hidden = O.cell_rnn_forward(sd, x, hidden, cfg, eps, masks)
+
+    ft = FineTuner(net.to(DEV).train(), 0.05, clip=0.25, prec="bf16x3")
+    l, c, k = ft.forward_backward(x.to(DEV), y.to(DEV), kl_scale, eps=eps, masks=masks,
+                                  hidden=(hidden[0].to(DEV), hidden[1].to(DEV)))
+    assert abs(float(c) - float(ce)) < 2e-4, (float(c), float(ce))
+    assert abs(float(k) - float(kl)) <= 1e-4 * abs(float(kl)) + 1e-7, (float(k), float(kl))
+    assert abs(float(l) - float(loss)) < 2e-4 + 1e-4 * abs(float(loss)), (float(l), float(loss))
+    for got, want in zip(ft.hidden, want_hidden):
+        assert (got.cpu() - want).abs().max().item() < 1e-4
+    bad = []
+    for name, ref in want_g.items():
+        got = ft.g[name].detach().cpu()
+        tol = 2e-3 * ref.abs().max().item() + 1e-7
+        err = (got - ref).abs().max().item()
+        if not err <= tol:
+            bad.append((name, err, ref.abs().max().item()))
+    assert not bad, bad
+    # the accessors train.py:360-377 calls after the forward
+    if family == "v_lstm":
+        acc = sum(float(net.rnn.rnn[mi].vnn.kl_divergence()) for mi in range(2) if pos[mi] == "1")
+    else:
+        acc = sum(float(c.gpnn.kl_divergence()) for c in net.rnn.rnn if hasattr(c, "gpnn"))
+    assert abs(acc - float(kl)) <= 1e-4 * abs(float(kl)) + 1e-7
+
+
+@pytest.mark.parametrize("family,pos", [("v_lstm", "11"), ("gauss_lstm", "31")])
+def test_cell_families_training_reduces_the_loss(family, pos):
+    from bayeslms_b200.trainer import FineTuner
+    net, _, _ = _build_cells(family, pos, dropout=0.1)
+    ft = FineTuner(net.to(DEV).train(), 0.5, clip=0.25, prec="bf16")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, V, (20, 8), generator=g).to(DEV)
+    y = torch.randint(0, V, (20, 8), generator=g).to(DEV)
+    l0 = float(ft.step(x, y, 0.01, seed=1)[0])
+    hidden = None
+    for i in range(12):
+        last = float(ft.step(x, y, 0.01, seed=2 + i, hidden=hidden)[0])
+        hidden = ft.hidden
+    assert last < l0 - 0.05, (l0, last)
