@@ -151,6 +151,7 @@ SIGNATURES = {
     "blm_scores_format": (_i64, [_p, _p, _p, _p, _p, _i64, _p, _p, _i64]),
     "blm_lstm_workspace_bytes": (_i64, [_i64, _i64]),
     "blm_lstm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "blm_lstm_layer_seq": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

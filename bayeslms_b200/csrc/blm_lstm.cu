@@ -50,6 +50,7 @@ struct LstmParams {
   __nv_bfloat16* out_lo;
   float* hT;
   float* cT;
+  float* c_seq;           // optional [T, B, H]: the cell state after every live step (state snapshots of long chains)
   __nv_bfloat16* hbuf[2][2];
   unsigned int* barrier;
 };
@@ -318,6 +319,10 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
               *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
               *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
               store_h8(nh, nl, h);
+              if (p.c_seq) {
+                *reinterpret_cast<float4*>(p.c_seq + ot) = *reinterpret_cast<float4*>(c);
+                *reinterpret_cast<float4*>(p.c_seq + ot + 4) = *reinterpret_cast<float4*>(c + 4);
+              }
               if (p.out_f32) {
                 *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
                 *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
@@ -386,6 +391,14 @@ int64_t blm_lstm_workspace_bytes(int64_t B, int64_t H) {
 int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo, const float* h0,
                    const float* c0, const int32_t* lengths, int64_t T, int64_t B, int64_t H, float* out_f32,
                    blm_bf16* out_hi, blm_bf16* out_lo, float* hT, float* cT, void* workspace, blm_stream stream) {
+  return blm_lstm_layer_seq(gates_x, w_hh_hi, w_hh_lo, h0, c0, lengths, T, B, H, out_f32, out_hi, out_lo, hT, cT, nullptr,
+                            workspace, stream);
+}
+
+int blm_lstm_layer_seq(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo, const float* h0,
+                       const float* c0, const int32_t* lengths, int64_t T, int64_t B, int64_t H, float* out_f32,
+                       blm_bf16* out_hi, blm_bf16* out_lo, float* hT, float* cT, float* c_seq, void* workspace,
+                       blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(num_sms() > 0, BLM_ERR_ARCH, "blm_init() has not been called");
   BLM_REQUIRE(gates_x && w_hh_hi && h0 && c0 && lengths && hT && cT && workspace, BLM_ERR_ARG,
@@ -420,6 +433,8 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   p.hT = hT;
   p.cT = cT;
+  p.c_seq = c_seq;
+  BLM_REQUIRE(aligned16(c_seq), BLM_ERR_ALIGN, "c_seq must be 16-byte aligned");
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   p.barrier = reinterpret_cast<unsigned int*>(ws);
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(ws + 256);

@@ -610,6 +610,24 @@ def _lstm_forward(model, plan: _Plan, weights, tokens_tb: torch.Tensor, lengths:
     return out32, x, torch.stack(hs), torch.stack(cs)
 
 
+def _lstm_chain(model, plan: _Plan, weights, tokens_ts: torch.Tensor, lengths: torch.Tensor, T: int, S: int):
+    """The hypothesis-#0 chains of S sessions as one [T, S] lock-step batch from zero state (plain layers only):
+    returns per layer the fp32 h and c after every step, each [T * S, H]."""
+    H, prec, dev = model.nhid, plan.prec, plan.device
+    _, x = ops.embed(tokens_ts.reshape(-1), None, plan.emb, None, 1.0, prec=prec, want_f32=False)
+    zero = torch.zeros(S, H, dtype=torch.float32, device=dev)
+    hs, cs = [], []
+    for li, W in enumerate(weights):
+        gates = torch.empty(T * S, 4 * H, dtype=torch.float32, device=dev)
+        ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+        c_seq = torch.empty(T * S, H, dtype=torch.float32, device=dev)
+        h_seq, x, _, _ = ops.lstm_layer(gates, W["w_hh"], zero, zero, lengths, T, S, H, prec=prec, want_f32=True,
+                                        want_split=li + 1 < len(weights), c_seq=c_seq)
+        hs.append(h_seq)
+        cs.append(c_seq)
+    return hs, cs
+
+
 def _gp_lstm_layer(plan: _Plan, W, x: Split, h0, c0, lengths, T, B, H, want_f32, want_split):
     """GP-LSTM cell layer (model.py:1720-1777).  The input side of all five blocks (four gates + GP unit) is
     hoisted into one GEMM over all timesteps; each step is one [B, 5H] product on the recurrent weights with the
@@ -784,8 +802,47 @@ def lstm_score_flat(rs, tok: np.ndarray, tgt: np.ndarray, offs: np.ndarray, sess
         init_h2 = torch.zeros(U, 2, S, H2, dtype=torch.float32, device=dev)
         init_c2 = torch.zeros_like(init_h2)
         chains.append((inter, plan2, plan2.lstm, init_h2, init_c2))
+    one_launch = all("gp" not in L for _, pl, _, _, _ in chains for L in pl.lstm) and os.environ.get("BLM_LSTM_CHAIN_LOOP") is None
+    # length of hypothesis #0 of every (session, utterance); a session's LAST utterance feeds nobody
+    ok_su = first >= 0
+    lens0 = np.where(ok_su, lens_all[np.maximum(first, 0)], 0)
+    n_utt = ok_su.sum(1)
+    lens0[np.arange(S), np.maximum(n_utt - 1, 0)] = 0
     for s0 in range(0, S, LSTM_MAX_ROWS):
         s1 = min(S, s0 + LSTM_MAX_ROWS)
+        Sc = s1 - s0
+        if one_launch:
+            # The chain of a session is ONE sequence: hypothesis #0 of utterance 0, 1, 2, ... back to back with the
+            # state carried (score.py:261-274).  All sessions advance in lock step through one recurrence launch per
+            # layer (and one hoisted input GEMM), the state at every utterance boundary is read back from the
+            # per-step (h, c) outputs -- instead of one embedding + 2 GEMMs + 2 recurrence launches per utterance.
+            l0 = lens0[s0:s1]
+            cum = np.cumsum(l0, axis=1)                                   # [Sc, U]: chain position after utterance u
+            T1 = int(cum[:, -1].max()) if cum.size else 0
+            if T1 == 0:
+                continue
+            si, ui = np.nonzero(l0 > 0)
+            L = l0[si, ui]
+            k = np.arange(int(L.sum()), dtype=np.int64) - np.repeat(np.cumsum(L) - L, L)
+            src = np.repeat(offs[first[s0 + si, ui]], L) + k
+            t_of = np.repeat(cum[si, ui] - L, L) + k
+            host = _pin(torch.zeros(T1 * Sc + Sc, dtype=torch.int32))
+            buf = host.numpy()
+            buf[t_of * Sc + np.repeat(si, L)] = tok[src]
+            buf[T1 * Sc:] = cum[:, -1]
+            dev_buf = host.to(dev, non_blocking=True)
+            rs.h2d_bytes += 4 * host.numel()
+            tok_ts, len_d = dev_buf[:T1 * Sc].view(T1, Sc), dev_buf[T1 * Sc:]
+            # state BEFORE utterance u >= 1 = state after chain position cum[:, u - 1] - 1
+            pos = np.maximum(cum[:, :-1] - 1, 0)                          # [Sc, U - 1]
+            gidx = torch.from_numpy((pos * Sc + np.arange(Sc)[:, None]).T.reshape(-1).astype(np.int64)).to(dev)  # (u, s)
+            for net_k, plan_k, w_k, ih_k, ic_k in chains:
+                Hk = net_k.nhid
+                hs, cs = _lstm_chain(net_k, plan_k, w_k, tok_ts, len_d, T1, Sc)
+                for li in range(len(hs)):
+                    ih_k[1:, li, s0:s1] = hs[li].index_select(0, gidx).view(U - 1, Sc, Hk)
+                    ic_k[1:, li, s0:s1] = cs[li].index_select(0, gidx).view(U - 1, Sc, Hk)
+            continue
         padded = []
         for u in range(U - 1):                                        # the last utterance feeds nobody
             r0 = first[s0:s1, u]

@@ -262,9 +262,6 @@ def gemm_sampled(a: Split, mu: Optional[torch.Tensor], sigma: Optional[torch.Ten
         check(lib().blm_gemm_sampled(C.byref(d), _stream()), "blm_gemm_sampled")
 
 
-_nll_ws = {}
-
-
 def vocab_nll(h: Split, e: Split, bias: Optional[torch.Tensor], targets: torch.Tensor, *, prec: str = "bf16",
               extra: Sequence = (), out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-row ``-log softmax(h @ e.T + bias)[target]`` without materialising the logits.
@@ -275,11 +272,7 @@ def vocab_nll(h: Split, e: Split, bias: Optional[torch.Tensor], targets: torch.T
     M, V = h.hi.shape[0], e.hi.shape[0]
     dev = h.hi.device
     nbytes = lib().blm_vocab_nll_workspace_bytes(M, V)
-    key = (dev.index, torch.cuda.current_stream().cuda_stream)
-    ws = _nll_ws.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
-        _nll_ws[key] = ws
+    ws = _workspace("vocab_nll", max(nbytes, 1 << 20), dev)
     if out is None:
         out = torch.empty(M, dtype=torch.float32, device=dev)
     assert targets.dtype == torch.int32 and targets.numel() == M
@@ -478,9 +471,6 @@ def mha_causal_bf16(qkv: Split, seq_offsets: torch.Tensor, nhead: int, max_len: 
     return o, s
 
 
-_kl_ws = {}
-
-
 def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_one: bool = False,
              scale: float = 1.0, accumulate: bool = False) -> torch.Tensor:
     """out[0] (+)= scale * 0.5 * mean(mu^2 - 2 lgstd + exp(2 lgstd) [- 1]) over a 2-D row-slice view."""
@@ -488,23 +478,18 @@ def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_
         mu, lgstd = mu.view(1, -1), lgstd.view(1, -1)
     rows, cols = mu.shape
     assert mu.stride(1) == 1 and lgstd.is_contiguous() and lgstd.shape == mu.shape
-    key = (mu.device.index, torch.cuda.current_stream().cuda_stream)
-    ws = _kl_ws.get(key)
-    if ws is None:
-        ws = torch.zeros(lib().blm_kl_workspace_bytes(), dtype=torch.uint8, device=mu.device)
-        _kl_ws[key] = ws
+    ws = _workspace("kl", lib().blm_kl_workspace_bytes(), mu.device, zero=True)
     with _op("kl_gauss", 1, 4.0 * 2 * rows * cols):
         check(lib().blm_kl_gauss(_ptr(mu), mu.stride(0), _ptr(lgstd), rows, cols, int(minus_one), scale,
                                  int(accumulate), _ptr(out), _ptr(ws), _stream()), "blm_kl_gauss")
     return out
 
 
-_lstm_ws = {}
-
-
 def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.Tensor, lengths: torch.Tensor,
-               T: int, B: int, H: int, *, prec: str = "bf16", want_f32: bool = False, want_split: bool = True):
-    """One LSTM layer over [T, B] lock-stepped rows.  Returns (out_f32 or None, out Split or None, hT, cT)."""
+               T: int, B: int, H: int, *, prec: str = "bf16", want_f32: bool = False, want_split: bool = True,
+               c_seq: Optional[torch.Tensor] = None):
+    """One LSTM layer over [T, B] lock-stepped rows.  Returns (out_f32 or None, out Split or None, hT, cT).
+    ``c_seq`` [T * B, H] fp32 (optional) receives the cell state after every live step."""
     dev = gates_x.device
     assert gates_x.is_contiguous() and gates_x.numel() == T * B * 4 * H and lengths.dtype == torch.int32
     h0, c0 = h0.contiguous(), c0.contiguous()
@@ -513,16 +498,14 @@ def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.T
     hT = torch.empty(B, H, dtype=torch.float32, device=dev)
     cT = torch.empty(B, H, dtype=torch.float32, device=dev)
     nbytes = lib().blm_lstm_workspace_bytes(B, H)
-    key = (dev.index, torch.cuda.current_stream().cuda_stream)
-    ws = _lstm_ws.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
-        _lstm_ws[key] = ws
+    ws = _workspace("lstm", max(nbytes, 1 << 20), dev)
+    if c_seq is not None:
+        assert c_seq.dtype == torch.float32 and c_seq.is_contiguous() and c_seq.numel() == T * B * H
     with _op("lstm_layer", 1, 2.0 * T * B * 4 * H * H):
-        check(lib().blm_lstm_layer(_ptr(gates_x), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
-                                   _ptr(c0), _ptr(lengths), T, B, H, _ptr(out32),
-                                   _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),
-                                   _ptr(hT), _ptr(cT), _ptr(ws), _stream()), "blm_lstm_layer")
+        check(lib().blm_lstm_layer_seq(_ptr(gates_x), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
+                                       _ptr(c0), _ptr(lengths), T, B, H, _ptr(out32),
+                                       _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),
+                                       _ptr(hT), _ptr(cT), _ptr(c_seq), _ptr(ws), _stream()), "blm_lstm_layer")
     return out32, outs, hT, cT
 
 
@@ -604,6 +587,13 @@ _ws_cache = {}
 
 
 def _workspace(kind: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
+    """Scratch memory of one kernel family, cached per (device, stream) -- except while a CUDA graph is being captured:
+    a tensor allocated then lives in the graph's private pool, which is released with the graph, so caching it would
+    hand a dangling pointer to the next capture on the same (re-used) capture stream (found as an illegal address in a
+    later graph's replay).  Captured launches get a fresh block each; stream order keeps its re-use inside the graph
+    correct."""
+    if torch.cuda.is_current_stream_capturing():
+        return (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
     key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:

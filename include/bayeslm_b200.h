@@ -347,6 +347,13 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
                    const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
                    int64_t H, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, float* hT,
                    float* cT, void* workspace, blm_stream stream);
+/* The same launch that also records the cell state after every live step (c_seq [T, B, H] fp32; out_f32 holds h):
+ * one launch can then carry a whole chain of utterances -- hypothesis #0 of utterance after utterance, the hidden
+ * carry of score.py:261-274 -- and the state at every utterance boundary is read back from (out_f32, c_seq).   */
+int blm_lstm_layer_seq(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo,
+                       const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
+                       int64_t H, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, float* hT,
+                       float* cT, float* c_seq, void* workspace, blm_stream stream);
 
 /* GP-LSTM cell update for one timestep (GPLSTMCell.Gplstm, model.py:1743-1777; gpnn_type <= 3,
  * gate_type 1..4 = i, f, g, o).  acc5 [B, 5H] (ld): the four gate pre-activations followed by the GP
