@@ -292,15 +292,35 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
-__global__ void layernorm_bwd_fold_kernel(const float* __restrict__ partial, int blocks, int d, int accumulate,
-                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * d) return;
-  const int which = c / d, col = c - which * d;
-  float t = 0.0f;
-  for (int b = 0; b < blocks; ++b) t += partial[(static_cast<long long>(b) * 2 + which) * d + col];
-  float* out = which == 0 ? dgamma : dbeta;
-  out[col] = accumulate ? out[col] + t : t;
+// Fold of the per-CTA partials: a block owns 32 of the 2 d columns, its eight warps take every eighth partial (fixed
+// order: deterministic) and meet in shared memory.  (One thread per column walking all ~300 partials was a chain of
+// dependent L2 round trips: 25 us for a 12 KB result, 6.5 % of the fine-tune step, profiles/r02a.)
+__global__ void __launch_bounds__(256) layernorm_bwd_fold_kernel(const float* __restrict__ partial, int blocks, int d,
+                                                                 int accumulate, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta) {
+  __shared__ float red[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;      // column of the [2, d] result
+  float t0 = 0.0f, t1 = 0.0f;
+  if (c < 2 * d) {
+    const float* p = partial + c;
+    int b = warp;
+    for (; b + 8 < blocks; b += 16) {
+      t0 += p[static_cast<long long>(b) * 2 * d];
+      t1 += p[static_cast<long long>(b + 8) * 2 * d];
+    }
+    if (b < blocks) t0 += p[static_cast<long long>(b) * 2 * d];
+  }
+  red[warp][lane] = t0 + t1;
+  __syncthreads();
+  if (warp == 0 && c < 2 * d) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    const int which = c / d, col = c - which * d;
+    float* out = which == 0 ? dgamma : dbeta;
+    out[col] = accumulate ? out[col] + t : t;
+  }
 }
 
 // ------------------------------------------------------------------ attention backward
@@ -918,7 +938,7 @@ int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
   else
     layernorm_bwd_kernel<8><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
   BLM_CHECK_CUDA(cudaGetLastError());
-  layernorm_bwd_fold_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>(partial, blocks, d, accumulate, dgamma, dbeta);
+  layernorm_bwd_fold_kernel<<<(2 * d + 31) / 32, 256, 0, st>>>(partial, blocks, d, accumulate, dgamma, dbeta);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

@@ -584,6 +584,7 @@ def colsum(x, out: torch.Tensor, *, scale: float = 1.0, accumulate: bool = False
 
 
 _ws_cache = {}
+CAPTURE_KEEP = []
 
 
 def _workspace(kind: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
@@ -593,7 +594,11 @@ def _workspace(kind: str, nbytes: int, device, zero: bool = False) -> torch.Tens
     later graph's replay).  Captured launches get a fresh block each; stream order keeps its re-use inside the graph
     correct."""
     if torch.cuda.is_current_stream_capturing():
-        return (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+        ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+        # held until the capture ends (trainer clears the list): a capture may span two streams, and a block returned
+        # to the pool here could be re-issued to the other stream while this launch is still unordered against it
+        CAPTURE_KEEP.append(ws)
+        return ws
     key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:

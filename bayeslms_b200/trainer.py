@@ -48,6 +48,11 @@ _MIRROR = os.environ.get("BLM_TRAIN_NO_MIRROR") is None
 # 4.01 ms per step -- only 38 % of the bytes can start early (the tied embedding gradient completes last), the NCCL
 # kernel takes SMs from a backward pass made of 20-70 us kernels, and three small all-reduces pay three latencies.
 _OVERLAP = os.environ.get("BLM_TRAIN_OVERLAP") is not None
+# Captured step: the weight / bias gradients of the plain projections (dW = dY^T X, db = colsum dY) are off the critical
+# path of the backward pass (the dX chain), and at 3200 tokens every GEMM of the step leaves SMs idle (16-128 CTAs on
+# 148 SMs) -- so they are captured on a second stream and fill those SMs while the dX chain proceeds
+# (BLM_TRAIN_WGRAD_STREAM=0 is the A/B switch).
+_WGRAD_STREAM = os.environ.get("BLM_TRAIN_WGRAD_STREAM", "1") != "0"
 
 
 class _T:
@@ -106,6 +111,7 @@ class FineTuner:
                 raise _lib.BlmError("data_parallel=True needs an initialised torch.distributed process group")
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
+        self._keep, self._forked, self._side = [], False, None     # side-stream launches of the captured step (_aside)
         self._drop = None          # per-step dropout state, see _begin_dropout
         self._seed_dev = None      # device int64 [1] added to the dropout key inside captured graphs
         named = list(model.named_parameters())          # tied encoder / decoder weight appears once
@@ -196,6 +202,27 @@ class FineTuner:
     def _wgrad(self, dy_t: Split, x_t: Split, out: torch.Tensor, tag: str):
         """out[N, K] = dY^T X, both operands given transposed ([N, M] and [K, M])."""
         _gemm(dy_t, x_t, prec=self.prec, out_f32=out, tag="wgrad:" + tag)
+
+    def _aside(self, *keep):
+        """Context for launches that are off the critical path: inside a graph capture they go to a second stream,
+        ordered after everything queued so far on the main stream, and are joined by :meth:`_join_aside`.  ``keep``:
+        every tensor those launches touch -- held until the join so that the allocator cannot hand their memory to a
+        main-stream tensor while the side stream still uses it."""
+        import contextlib
+        if not (_WGRAD_STREAM and getattr(self, "_capturing", False) and torch.cuda.is_current_stream_capturing()):
+            return contextlib.nullcontext()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(torch.cuda.current_stream())
+        self._keep.extend(keep)
+        self._forked = True
+        return torch.cuda.stream(self._side)
+
+    def _join_aside(self):
+        if getattr(self, "_forked", False):
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._forked = False
+        self._keep.clear()
 
     def _static_noise(self, e, what: str):
         """While a CUDA graph is being captured every sampled tensor must read its noise from a static buffer that
@@ -476,8 +503,9 @@ class FineTuner:
                 ops.kl_gauss_bwd(lin.weight_mean.detach(), lin.weight_lgstd.detach(), kl_scale, G,
                                  g[pre + "linear2.weight_lgstd"])
             else:
-                self._wgrad(dft, ht, g[pre + "linear2.weight"], "ffn2")
-                ops.colsum(df, g[pre + "linear2.bias"])
+                with self._aside(dfs, df, S["hs"]):
+                    self._wgrad(dft, ht, g[pre + "linear2.weight"], "ffn2")
+                    ops.colsum(df, g[pre + "linear2.bias"])
             # FFN1
             dx1 = self._f32(M, d)
             _gemm(dz1s, S["w1_t"], prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
@@ -485,8 +513,9 @@ class FineTuner:
             if kind == "gauss":
                 self._gp_backward(layer, pre, S, dz1, dz1t, x1t, dh, kl, kl_scale, eps.get(f"layer{li}"), seed)
             else:
-                self._wgrad(dz1t, x1t, g[pre + "linear1.weight"], "ffn1")
-                ops.colsum(dz1, g[pre + "linear1.bias"])
+                with self._aside(dz1, dz1s, S["x1s"]):
+                    self._wgrad(dz1t, x1t, g[pre + "linear1.weight"], "ffn1")
+                    ops.colsum(dz1, g[pre + "linear1.bias"])
             # LayerNorm 1, output projection, attention, QKV projection
             dy1 = ops.layernorm_bwd(dx1, S["y1"], layer.norm1.weight.detach(), layer.norm1.eps, g[pre + "norm1.weight"],
                                     g[pre + "norm1.bias"])
@@ -507,8 +536,9 @@ class FineTuner:
                 ops.kl_gauss_bwd(lin.weight_mean.detach(), lin.weight_lgstd.detach(), kl_scale, G,
                                  g[pre + "self_attn.o_net.weight_lgstd"])
             else:
-                self._wgrad(dy1t, attt, g[pre + "self_attn.o_net.weight"], "o_net")
-                ops.colsum(do1, g[pre + "self_attn.o_net.bias"])
+                with self._aside(dy1s, do1, S["atts"]):
+                    self._wgrad(dy1t, attt, g[pre + "self_attn.o_net.weight"], "o_net")
+                    ops.colsum(do1, g[pre + "self_attn.o_net.bias"])
             dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q, prec=prec, drop=S["drop_attn"])
             dx = self._f32(M, d)
             dqkvs = ops.split(dqkv, prec)
@@ -521,8 +551,9 @@ class FineTuner:
                     self._wgrad(part, xst, g[pre + f"self_attn.{nm}.weight"], nm)
                     ops.colsum(dqkv[:, rows], g[pre + f"self_attn.{nm}.bias"])
             else:
-                self._wgrad(dqkvt, xst, g[pre + "self_attn.qkv_net.weight"], "qkv")
-                ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
+                with self._aside(dqkv, dqkvs, S["xs"]):
+                    self._wgrad(dqkvt, xst, g[pre + "self_attn.qkv_net.weight"], "qkv")
+                    ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
             if on_layer_done is not None:
                 on_layer_done(li)      # every gradient of layers >= li is final (capture() splits the graph here)
         if drop_pe is not None:
@@ -541,7 +572,9 @@ class FineTuner:
             dx0 = self._f32(M, d)
             _gemm(ops.split(dx, prec), E_in["w_in_t"], prec=prec, out_f32=dx0, tag="dgrad:embed_in")
             dx = dx0
-        # embedding: scatter-add on top of the decoder's weight gradient when the weights are tied
+        # embedding: scatter-add on top of the decoder's weight gradient when the weights are tied (so the side stream's
+        # weight gradients are joined first)
+        self._join_aside()
         ops.embed_bwd(dx, tok, math.sqrt(d), g["encoder.weight"])
         # loss = ce + kl * kl_scale
         ops.reduce_sum(ce, loss)
@@ -571,8 +604,9 @@ class FineTuner:
                  tag="dlogits")
         dx = self._f32(M, d)
         _gemm(dZ, Et, prec=prec, out_f32=dx, tag="dgrad:decoder")
-        self._wgrad(_tbf16(dZ, prec), _tbf16(xs, prec), g["decoder.weight"], "decoder")
-        ops.colsum(dZ, g["decoder.bias"])
+        with self._aside(dZ, xs):
+            self._wgrad(_tbf16(dZ, prec), _tbf16(xs, prec), g["decoder.weight"], "decoder")
+            ops.colsum(dZ, g["decoder.bias"])
         return dx, ce, kl, loss
 
     # ------------------------------------------------------------------ LSTM families
@@ -703,6 +737,7 @@ class FineTuner:
                         ops.kl_gauss_bwd(mu[rows], lg, kl_scale * frac, G[rows], g_lg)
         if drop_emb is not None:
             dout, _ = ops.dropout(dout, drop_emb, out_f32=dout)
+        self._join_aside()
         ops.embed_bwd(dout, tok, 1.0, g["encoder.weight"])
         ops.reduce_sum(ce, loss)
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
@@ -856,6 +891,7 @@ class FineTuner:
             dout = dx
         if drop_emb is not None:
             dout, _ = ops.dropout(dout, drop_emb, out_f32=dout)
+        self._join_aside()
         ops.embed_bwd(dout, tok, 1.0, g["encoder.weight"])
         ops.reduce_sum(ce, loss)
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
@@ -1044,6 +1080,7 @@ class FineTuner:
             self._capture_graphs(cap, T, B)
         finally:
             self._capturing = False
+            ops.CAPTURE_KEEP.clear()
         return self
 
     def _capture_graphs(self, cap, T: int, B: int):
@@ -1080,6 +1117,7 @@ class FineTuner:
 
             def cut(li):
                 if li == sl and not state["cut"]:
+                    self._join_aside()
                     cap["g1"].capture_end()
                     cap["g1b"].capture_begin(pool=cap["g1"].pool())
                     state["cut"] = True
