@@ -31,14 +31,15 @@ class _Stats:
     ``timing`` is a dict) CUDA-event brackets around every launch on the launching stream."""
     launches = 0
     timing = None   # None, or {op name: [(start_event, end_event, work), ...]}
+    bytes = {}      # op name -> algorithmic bytes of the bracketed launches (HBM-bound kernels)
 
 
 STATS = _Stats()
 
 
 class _op:
-    def __init__(self, name: str, kernels: int = 1, work: float = 0.0):
-        self.name, self.kernels, self.work = name, kernels, work
+    def __init__(self, name: str, kernels: int = 1, work: float = 0.0, bytes_: float = 0.0):
+        self.name, self.kernels, self.work, self.bytes = name, kernels, work, bytes_
 
     def __enter__(self):
         STATS.launches += self.kernels
@@ -52,6 +53,8 @@ class _op:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             STATS.timing.setdefault(self.name, []).append((self.e0, e1, self.work))
+            if self.bytes:
+                STATS.bytes[self.name] = STATS.bytes.get(self.name, 0.0) + self.bytes
         return False
 
 
@@ -501,7 +504,8 @@ def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.T
     ws = _workspace("lstm", max(nbytes, 1 << 20), dev)
     if c_seq is not None:
         assert c_seq.dtype == torch.float32 and c_seq.is_contiguous() and c_seq.numel() == T * B * H
-    with _op("lstm_layer", 1, 2.0 * T * B * 4 * H * H):
+    # algorithmic bytes per step = W_hh once (4H x H bf16) + gates_x read (B x 4H fp32) + h, c write
+    with _op("lstm_layer", 1, 2.0 * T * B * 4 * H * H, T * (4.0 * H * H * 2 + B * 4.0 * H * 4 + 2.0 * B * H * 4)):
         check(lib().blm_lstm_layer_seq(_ptr(gates_x), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
                                        _ptr(c0), _ptr(lengths), T, B, H, _ptr(out32),
                                        _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),

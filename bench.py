@@ -101,7 +101,7 @@ def build_model(device):
     return net.to(device).eval()
 
 
-def bench_finetune(dev, world, steps, warmup=3):
+def bench_finetune(dev, world, steps, warmup=3, dropout=0.0):
     """BASELINE config 4: Variational Transformer (T_v_pos=11 -> both first layers variational, 5 layers),
     d=512, FFN=4096, V=30000; one fine-tune step = CE + KL, backward, clip, SGD momentum on a per-GPU
     batch of 32 x 100 tokens (train.py step), data parallel with one NCCL all-reduce of the gradients."""
@@ -109,7 +109,7 @@ def bench_finetune(dev, world, steps, warmup=3):
     from bayeslms_b200 import model as M
     from bayeslms_b200.trainer import FineTuner
     torch.manual_seed(1111)
-    net = M.VTransformerModel(V, D, NHEAD, FF, NLAYERS, 0.0, True, "11").to(dev).train()
+    net = M.VTransformerModel(V, D, NHEAD, FF, NLAYERS, dropout, True, "11").to(dev).train()
     ft = FineTuner(net, 0.01, clip=0.25, prec="bf16")
     g = torch.Generator().manual_seed(1111 + int(os.environ.get("RANK", 0)))
     T, B = 100, 32
@@ -130,27 +130,41 @@ def bench_finetune(dev, world, steps, warmup=3):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     losses.append(float(ft.step_captured(x, y, 999)[0]))
+    # algorithmic work of one step: forward + backward = 3 x the forward FLOP of the 5-layer model (SURVEY.md 8d:
+    # 83.3 MFLOP per token forward: 5 layers of QKV / o_net / FFN1 / FFN2 projections + the vocabulary projection);
+    # bytes: parameters read, gradients written + read, momentum read + written, parameters + bf16 copies written
+    n_par = sum(p.numel() for p in net.parameters())
+    flop = 3.0 * 83.3e6 * T * B
+    byts = n_par * (4 + 4 + 4 + 4 + 4 + 4 + 2.0)
+    pk = peaks()
+    tf = flop / (ms.item() / 1e3) / 1e12
     return {"workload": "Variational Transformer LM (T_v_pos=11) 5L d512 FFN4096 V30000 fine-tune step, "
                         "32 x 100 tokens per GPU, CE + KL, clip, SGD momentum", "dtype": "bf16",
             "tokens_per_s": T * B * world / (ms.item() / 1e3), "ms_per_step": ms.item(),
             "parallelism": f"dp{world}: replicated weights, one NCCL all-reduce of the flat gradient buffer per step",
-            "loss_first": losses[0], "loss_last": losses[-1], "dropout": 0.0}
+            "loss_first": losses[0], "loss_last": losses[-1], "dropout": dropout,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
+                         "flop_per_step": flop, "hbm_bytes_per_step": byts,
+                         "floor_ms": 1e3 * (flop / (pk["tensor"] * 1e12) + byts / (pk["hbm"] * 1e9)),
+                         "note": "whole step (154 launches in two CUDA graphs, weight gradients on a second stream); "
+                                 "3 x forward FLOP of the model; M = 3200 tokens fills 16-128 of 148 SMs per GEMM"}}
 
 
-def bench_lstm(dev, world=1, rank=0, steps=2):
-    """BASELINE configs 1 / 5 shape: Bayesian LSTM 2x1024 (emb 1024, L_bayes_pos=3), V=30000, 100-best lists in
-    sessions of 16 utterances (hidden carry through hypothesis #0, score.py:271-274).  End to end: flat host id
-    arrays -> lock-step batches -> persistent recurrence kernel -> vocabulary NLL -> scores on the host.  With N
-    ranks every rank scores its own 8 sessions (session-sharded, weak scaling, no data-path collective); the time is
-    the max over ranks between two barriers."""
+def bench_lstm(dev, world=1, rank=0, steps=1):
+    """BASELINE config 5 at its real per-GPU size: Bayesian LSTM 2x1024 (emb 1024, L_bayes_pos=3), V=30000, 100-best
+    lists, 10 000 utterances as 100 sessions of 100 utterances (hidden carry through hypothesis #0, score.py:271-274)
+    over 8 GPUs = 12 sessions x 100 utterances per GPU (session-sharded, weak scaling, no data-path collective), mean
+    and K = 8 Philox samples.  End to end: flat host id arrays -> lock-step batches -> persistent recurrence kernel ->
+    vocabulary NLL -> scores on the host; wall clock between two barriers, max over ranks.  Also the recurrence
+    kernel's roofline (effective GB/s on the algorithmic bytes, W_hh counted once per step although it
+    never leaves shared memory) from CUDA-event brackets of its launches."""
     import torch.distributed as dist
-    from bayeslms_b200 import model as M, synth
+    from bayeslms_b200 import model as M, ops, synth
     from bayeslms_b200.scorer import Rescorer
     torch.manual_seed(1111)
     net = M.BayesRNNModel("LSTM", V, 1024, 1024, 2, 0.5, True, 3).to(dev).eval()
-    n_sess, per_sess, nbest = 8, 16, 100
+    n_sess, per_sess, nbest = 12, 100, 100
     data = synth.make_nbest(n_sess * per_sess, nbest, V, seed=1112 + rank)
-    # flat host id arrays, rows ordered (session, utterance, hypothesis) -- the LSTM twin of flat_host() above
     tok, tgt, _, offs = data.flat_host()
     utt = np.repeat(np.arange(n_sess * per_sess), [len(u) for u in data.hyps])
     sess_of, utt_of = (utt // per_sess).astype(np.int32), (utt % per_sess).astype(np.int32)
@@ -158,12 +172,15 @@ def bench_lstm(dev, world=1, rank=0, steps=2):
     if world > 1:
         dist.all_reduce(n_tok)
     out = {}
+    pk = peaks()
     for name, kw in (("mean", {}), ("sampled_k8", {"K": 8, "seed": 1111})):
         rs = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS, **kw)
-        rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)       # warm-up (plans, workspaces)
+        if name == "mean":
+            rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)       # warm-up (plans, workspaces)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        ops.STATS.timing, ops.STATS.bytes = ({}, {}) if name == "mean" else (None, {})
         t0 = time.perf_counter()
         for _ in range(steps):
             rs.score_sessions_flat(tok, tgt, offs, sess_of, utt_of)
@@ -172,10 +189,63 @@ def bench_lstm(dev, world=1, rank=0, steps=2):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         out[name] = {"tokens_per_s": n_tok.item() / dt.item(), "ms": dt.item() * 1e3}
+        if name == "mean":
+            timing, ops.STATS.timing = ops.STATS.timing, None
+            ev = timing.get("lstm_layer", [])
+            ms_k = sum(a.elapsed_time(b) for a, b, _ in ev)
+            flop = sum(w for _, _, w in ev)
+            byts = ops.STATS.bytes.get("lstm_layer", 0.0)
+            tot = sum(sum(a.elapsed_time(b) for a, b, _ in v) for v in timing.values()) or 1.0
+            if ms_k:
+                out["recurrence_roofline"] = {
+                    "kernel": "lstm_layer_kernel<16,1,2> (persistent recurrence, W_hh resident in shared memory)",
+                    "bound": "hbm", "achieved": byts / (ms_k / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": byts / (ms_k / 1e3) / 1e9 / pk["hbm"], "launches": len(ev), "share_of_kernel_time": ms_k / tot,
+                    "tensor_tflops": flop / (ms_k / 1e3) / 1e12,
+                    # ncu --set full of one launch at B = 2048 (profiles/r01aw_sampled_gemm_kl_ncu_full.txt): DRAM bytes per
+                    # 8 steps = the gates_x read; W_hh is never re-read
+                    "traffic": 294e6 / 8, "traffic_unit": "DRAM bytes per step at B=2048 (ncu)",
+                    "note": "effective bandwidth on the algorithmic bytes of SURVEY.md 8d (W_hh 8 MiB counted once per step "
+                            "+ gates_x + h, c); it may exceed what DRAM delivers because W_hh stays in shared memory"}
+            out["kernel_time_shares"] = {k: round(sum(a.elapsed_time(b) for a, b, _ in v) / tot, 4)
+                                         for k, v in sorted(timing.items(), key=lambda kv: -sum(a.elapsed_time(b) for a, b, _ in kv[1]))[:6]}
     out["workload"] = (f"Bayesian LSTM 2x1024 L_bayes_pos=3 V30000, {nbest}-best, {n_sess} sessions x {per_sess} utterances "
-                       f"per GPU ({int(n_tok.item())} tokens over {world} GPU(s)), end to end from flat host id arrays incl. "
-                       "batch packing (wall clock, max over ranks)")
+                       f"per GPU ({int(n_tok.item())} tokens over {world} GPU(s); config 5 = 100 sessions over 8 GPUs), end to "
+                       "end from flat host id arrays incl. batch packing (wall clock, max over ranks)")
     return out
+
+
+def cpu_lstm_tokens_per_s(n_utts=100, nbest=20, budget_s=20.0):
+    """BASELINE config 1: Bayesian LSTM 2x1024 (emb 1024, L_bayes_pos=3), V=30000, 20-best lists of 100 utterances, the
+    reference loop on the host cores (oracle port: one hypothesis at a time, batch 1, hidden carried through hypothesis
+    #0, torch CPU fp32).  Bounded: stops at the first utterance boundary after ``budget_s`` seconds."""
+    from bayeslms_b200 import model as M, synth
+    from oracle import bayeslm_oracle as O
+    torch.manual_seed(1111)
+    net = M.BayesRNNModel("LSTM", V, 1024, 1024, 2, 0.5, True, 3)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    cfg = O.Config(family="bayes_lstm", bayes_pos=3, ntoken=V, ninp=1024, nhid=1024, nlayers=2)
+    data = synth.make_nbest(n_utts, nbest, V, seed=1111)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hidden = O.init_hidden(cfg, 1)
+    toks, utts, t0 = 0, 0, time.perf_counter()
+    with torch.no_grad():
+        for utt in data.tokenised():
+            first = None
+            for x, y in utt:
+                lg, nh = O.rnn_forward(sd, torch.tensor(x).view(-1, 1), hidden, cfg)
+                O.sentence_nll(lg, torch.tensor(y))
+                first = first or nh
+                toks += len(x)
+            hidden = first
+            utts += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+    dt = time.perf_counter() - t0
+    return {"value": toks / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"first {utts} of {n_utts} utterances x {nbest}-best ({toks} tokens, {dt:.1f} s), oracle port of the "
+                      "reference loop: batch 1 per hypothesis, hidden carry, torch CPU fp32"}
 
 
 def cpu_port_tokens_per_s(data, n_utts, state_dict):
@@ -338,6 +408,14 @@ def main():
             tf = w / (shares[name] / 1e3) / 1e12
             krf[name] = {"achieved": round(tf, 1), "frac": round(tf / pk["tensor"], 3), "launches": len(evs)}
     achieved = (nll_flops / nll_n) / (nll_ms / nll_n / 1e3) / 1e12 if nll_n else 0.0
+    # the kernel with the largest share of the step's time (FFN1 + GELU in r01), next to the vocabulary kernel
+    dom = max((n for n in timing if sum(w for _, _, w in timing[n]) > 0), key=lambda n: shares[n], default=None)
+    dom_rf = None
+    if dom is not None:
+        dw, dn = sum(w for _, _, w in timing[dom]), len(timing[dom])
+        dtf = dw / (shares[dom] / 1e3) / 1e12
+        dom_rf = {"kernel": dom, "bound": "tensor", "achieved": dtf, "peak": pk["tensor"], "unit": "TFLOP/s",
+                  "frac": dtf / pk["tensor"], "launches": dn, "avg_launch_ms": shares[dom] / dn, "share_of_step": shares[dom] / tot}
 
     # ---- e2e: host ids -> pinned staging -> device -> scores back on the host, every step
     rs = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS)
@@ -388,7 +466,14 @@ def main():
     sg_ms = sum(a.elapsed_time(b) for a, b, _ in sg)
     sg_tf = (sum(w for _, _, w in sg) / (sg_ms / 1e3) / 1e12) if sg_ms else 0.0
     step(prec="bf16x3")
+    ops.STATS.timing = {}
     px_ms = timed(lambda: step(prec="bf16x3"), k4_steps)
+    px_timing, ops.STATS.timing = ops.STATS.timing, None
+    # precise mode issues three bf16 products per GEMM (hi*lo + lo*hi + hi*hi): the tensor pipe does 3 x the
+    # algorithmic FLOP, which is what its roofline fraction is measured on
+    px_flop = sum(w for evs in px_timing.values() for _, _, w in evs)     # (K-concatenated segments are already counted)
+    px_gemm_ms = sum(a.elapsed_time(b) for evs in px_timing.values() for a, b, w in evs if w > 0)
+    px_tf = px_flop / (px_gemm_ms / 1e3) / 1e12 if px_gemm_ms else 0.0
 
     # ---- BASELINE config 3: GP Transformer (T_gauss_pos=3) on the same lists, posterior mean, bf16
     from bayeslms_b200 import model as M
@@ -402,7 +487,47 @@ def main():
 
     gp_step()
     gp_ms = timed(gp_step, k4_steps)
-    del gp_net
+    # ... and with gpnn.sample = True, K = 1: coefficients, weights and bias of the GP unit drawn per call (Philox)
+    gp_net.transformerlayers[0].gpnn.sample = True
+
+    def gp_sampled_step():
+        res = torch.cat([gp_net.score(b, prec="bf16", K=1, seed=1111) for b in batches])
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, res)
+
+    gp_sampled_step()
+    gp_s_ms = timed(gp_sampled_step, k4_steps)
+    gp_net.transformerlayers[0].gpnn.sample = False
+
+    # ---- STRONG scaling (BASELINE config 3 as written): ONE fixed 8000-utterance 50-best list, utterances sharded over
+    # the N ranks, flat host ids -> device -> scores -> one all-gather of the full score vector on every rank
+    strong_utts, blk = 8000, 250          # the list is 32 independently seeded blocks: a rank only generates its shard
+    per = -(-strong_utts // world)
+    per = -(-per // blk) * blk
+    s_lo, s_hi = min(rank * per, strong_utts), min((rank + 1) * per, strong_utts)
+    parts = [synth.make_nbest(blk, NBEST, V, seed=2222 + b).flat_host() for b in range(s_lo // blk, s_hi // blk)]
+    stok = np.concatenate([p[0] for p in parts])
+    stgt = np.concatenate([p[1] for p in parts])
+    spos = np.concatenate([p[2] for p in parts])
+    soffs = np.concatenate([[0]] + [p[3][1:].astype(np.int64) + sum(int(q[3][-1]) for q in parts[:i])
+                                    for i, p in enumerate(parts)]).astype(np.int32)
+    strong_local = torch.tensor([float(soffs[-1])], device=dev)
+    if world > 1:
+        dist.all_reduce(strong_local)
+    strong_tokens = int(strong_local.item())
+    rs_gp = Rescorer(gp_net, prec="bf16", max_tokens=MAX_TOKENS)
+    sgather = torch.zeros(world * per * NBEST, dtype=torch.float32, device=dev)
+    spad = torch.zeros(per * NBEST, dtype=torch.float32, device=dev)
+
+    def strong_step():
+        res = rs_gp.score_packed_host(stok, stgt, spos, soffs)
+        if world > 1:
+            spad[:len(res)].copy_(torch.from_numpy(res), non_blocking=True)
+            dist.all_gather_into_tensor(sgather, spad)
+
+    strong_step()
+    strong_ms = timed(strong_step, 1)
+    del gp_net, rs_gp
 
     # ---- fast-vs-precise agreement on this step's lists (ranking evidence)
     fast = step().float().cpu().numpy()
@@ -411,11 +536,27 @@ def main():
     _, picks_f = synth.wer(data, per_utt(fast), lo=lo)
     wer_p, picks_p = synth.wer(data, per_utt(precise), lo=lo)
 
+    # ---- ranking evidence on a PEAKED model (a random-init LM ranks by length): bayeslms_b200.evidence fine-tunes a
+    # Bayesian Transformer with the BASELINE layer sizes on a synthetic Markov corpus (~1.5 s), then fast vs precise
+    # mode on chain-based 50-best lists; both modes against the CPU oracle: tests/test_gpu_ranking.py,
+    # profiles/r02_ranking_evidence.json
+    from bayeslms_b200 import evidence
+    pk_net, pk_mk, pk_losses = evidence.peaked_model(device=dev)
+    pk_data = pk_mk.nbest(100, NBEST, seed=5 + rank)
+    rank_rep, _, _ = evidence.fast_vs_precise(pk_net, pk_data)
+    rank_rep["model"] = (f"BayesTransformerModel FFN 2L d512 FF4096 h8 V500, 1000 fine-tune steps on a 3-successor Markov corpus "
+                         f"(loss {pk_losses[0]:.2f} -> {pk_losses[-1]:.2f} nats/token), 100 x {NBEST}-best chain-based lists per rank")
+    rank_rep["tie_policy"] = "scores compared on the %.4f grid of lmwt.nn, ties broken by hypothesis index"
+    del pk_net
+
     finetune = bench_finetune(dev, world, max(10, args.steps))
+    finetune["with_dropout_0.2"] = {k: v for k, v in bench_finetune(dev, world, max(10, args.steps), dropout=0.2).items()
+                                    if k in ("ms_per_step", "tokens_per_s", "dropout")}
     lstm = bench_lstm(dev, world, rank)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        lstm["cpu_baseline"] = cpu_lstm_tokens_per_s()          # BASELINE config 1: 20-best x 100 utterances on the host
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
         n_cpu = 40                                      # ~30 k tokens: 8-15 s on the box's host cores
         v_cpu, t_cpu, dt_cpu, cores = cpu_port_tokens_per_s(data, n_cpu, sd)
@@ -451,6 +592,10 @@ def main():
                          "peak_source": pk["src"] + " bf16_tflops_sustained", "launches": nll_n,
                          "avg_launch_ms": nll_ms / nll_n if nll_n else None,
                          "share_of_step": nll_ms / tot},
+            "roofline_dominant_kernel": dom_rf,
+            "whole_step_roofline": {"bound": "tensor", "achieved": 93.8e6 * value / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
+                                    "frac": 93.8e6 * value / 1e12 / pk["tensor"] / world,
+                                    "note": "93.8 MFLOP per token (SURVEY.md 8d) x tokens/s, per GPU"},
             "kernel_time_shares": {k: round(v / tot, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
             "kernel_rooflines": {"unit": "TFLOP/s", "peak": pk["tensor"], **krf},
             "sampled_k4": {"value": n_tokens * world * k4_steps / (k4_ms / 1e3), "unit": "tokens/s", "K": 4,
@@ -464,9 +609,21 @@ def main():
                                "frac": sg_tf / pk["tensor"] if pk["tensor"] else None, "launches": len(sg),
                                "avg_launch_ms": sg_ms / len(sg) if sg else None}},
             "precise": {"value": n_tokens * world * k4_steps / (px_ms / 1e3), "unit": "tokens/s", "dtype": "bf16x3",
+                        "slowdown_vs_bf16": (px_ms / k4_steps) / (ms / args.steps),
+                        "roofline": {"bound": "tensor", "achieved": px_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
+                                     "frac": px_tf / pk["tensor"], "algorithmic_tflops": px_tf / 3.0,
+                                     "note": "all GEMM-shaped kernels of the step; the tensor pipe does 3 x the algorithmic "
+                                             "FLOP (hi*lo + lo*hi + hi*hi), which is what `achieved` counts"},
                         "max_abs_score_diff_vs_bf16": float(np.abs(fast - precise).max()),
                         "one_best_agreement": float(np.mean(np.asarray(picks_f) == np.asarray(picks_p))),
                         "synthetic_wer": wer_p},
+            "ranking_peaked_model": rank_rep,
+            "gp_tm_strong_scaling": {"value": strong_tokens / (strong_ms / 1e3), "unit": "tokens/s", "ms": strong_ms,
+                                     "scaling": "strong", "utterances": strong_utts, "tokens": strong_tokens,
+                                     "workload": f"GP Transformer LM T_gauss_pos=3, ONE fixed {strong_utts}-utterance 50-best list "
+                                                 f"sharded over {world} rank(s), host ids -> scores + all-gather of the full vector"},
+            "gp_tm_sampled_k1": {"value": n_tokens * world * k4_steps / (gp_s_ms / 1e3), "unit": "tokens/s",
+                                 "workload": "same lists, gpnn.sample = True, one Philox sample of (coef, weights, bias) per call"},
             "gp_tm_rescoring": {"value": n_tokens * world * k4_steps / (gp_ms / 1e3), "unit": "tokens/s",
                                 "workload": "GP Transformer LM T_gauss_pos=3 (GP activation mixture in layer 0), same lists, "
                                             "posterior mean, bf16"},
