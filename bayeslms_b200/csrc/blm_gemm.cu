@@ -473,19 +473,30 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
             }
           }
         }
+        if constexpr (EPI == EPI_NLL) {
+          // Canonical vocabulary segments: the online log-sum-exp of a row restarts every p.seg_tiles tiles and leaves
+          // one (max, sum) partial per (segment, column group), whatever group of tiles this work item covers.  The
+          // partition of the vocabulary into work groups depends on M (it is chosen to fill whole waves), the
+          // segments do not: a row's NLL is therefore bit-identical for every batch composition -- what makes the
+          // scores of a list independent of how it is sharded over GPUs (tools/multi_gpu_parity.py).
+          if ((n + 1) % p.seg_tiles == 0 || n + 1 == n1) {
+            if (row_ok) {
+              const long long o = static_cast<long long>((n / p.seg_tiles) * kColGroups + col_grp) * p.M + m;
+              p.part_max[o] = st.run_max;
+              p.part_sum[o] = st.run_sum;
+            }
+            st.run_max = -INFINITY;
+            st.run_sum = 0.0f;
+          }
+        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
       if constexpr (EPI == EPI_NLL) {
-        if (row_ok) {
-          // one partial per (vocabulary group, column group); nll_merge_kernel folds them
-          const long long o = static_cast<long long>(grp * kColGroups + col_grp) * p.M + m;
-          p.part_max[o] = st.run_max;
-          p.part_sum[o] = st.run_sum;
-          p.part_tgt[o] = st.tgt_logit;
-        }
+        if (row_ok)   // the target logit is found by exactly one (group, column group): merged with max, order-free
+          p.part_tgt[static_cast<long long>(grp * kColGroups + col_grp) * p.M + m] = st.tgt_logit;
       }
     }
   }
@@ -503,15 +514,13 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
 
 // nll[m] = ln2 * (gmax2 + log2(sum_g sum_g * 2^(max2_g - gmax2))) - target logit
 __global__ void nll_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                                 const float* __restrict__ part_tgt, int groups, int M,
+                                 const float* __restrict__ part_tgt, int groups, int tgt_groups, int M,
                                  float* __restrict__ nll, float* __restrict__ lse) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float gmax = -INFINITY, tgt = -INFINITY;
-  for (int g = 0; g < groups; ++g) {
-    gmax = fmaxf(gmax, part_max[static_cast<long long>(g) * M + m]);
-    tgt = fmaxf(tgt, part_tgt[static_cast<long long>(g) * M + m]);
-  }
+  for (int g = 0; g < groups; ++g) gmax = fmaxf(gmax, part_max[static_cast<long long>(g) * M + m]);
+  for (int g = 0; g < tgt_groups; ++g) tgt = fmaxf(tgt, part_tgt[static_cast<long long>(g) * M + m]);
   float s = 0.0f;
   for (int g = 0; g < groups; ++g)
     s += part_sum[static_cast<long long>(g) * M + m] * exp2f(part_max[static_cast<long long>(g) * M + m] - gmax);
@@ -1008,6 +1017,23 @@ int blm_gemm(const blm_gemm_desc* d, blm_stream stream) { return blm::gemm_impl(
 // smallest one (<= 8, or what it takes to have one work item per SM) whose last wave is at least 97 % full, else
 // the best found.  A group costs one (max, sum, target) partial per row and one reload of the resident 128 KB
 // hidden tile per work item -- noise next to the 256 KB vocabulary tiles it streams.
+// canonical segment of the vocabulary sweep = 4 tiles = 1024 columns (see the EPI_NLL epilogue).  Measured at
+// M = 65536: 1447 us with 4-tile segments, 1504 us with 2, 1423 us with BLM_NLL_SEG_TILES=0 (the A/B switch: one segment
+// per work group, i.e. the batch-composition-DEPENDENT rounding of the first version).
+static int nll_seg_tiles() {
+  static const int v = [] {
+    const char* e = getenv("BLM_NLL_SEG_TILES");
+    return e ? atoi(e) : 4;
+  }();
+  return v;
+}
+
+static int nll_tiles_per_group(int n_tiles, int g) {
+  const int tpg = (n_tiles + g - 1) / g;
+  const int s = nll_seg_tiles();
+  return s > 0 ? (tpg + s - 1) / s * s : tpg;   // groups are whole segments
+}
+
 static int nll_groups(int64_t M, int64_t V) {
   const int m_tiles = static_cast<int>((M + blm::kBM - 1) / blm::kBM);
   const int n_tiles = static_cast<int>((V + 255) / 256);
@@ -1022,7 +1048,7 @@ static int nll_groups(int64_t M, int64_t V) {
   int best = g_min;
   double best_eff = 0.0;
   for (int g = g_min; g <= g_max; ++g) {
-    const int tpg = (n_tiles + g - 1) / g;
+    const int tpg = nll_tiles_per_group(n_tiles, g);
     const int used = (n_tiles + tpg - 1) / tpg;
     const long long works = static_cast<long long>(m_tiles) * used;
     const long long waves = (works + sms - 1) / sms;
@@ -1037,8 +1063,13 @@ static int nll_groups(int64_t M, int64_t V) {
 }
 
 int64_t blm_vocab_nll_workspace_bytes(int64_t M, int64_t V) {
-  // one (max, sum, target) partial per row, vocabulary group and epilogue column group (<= 4)
-  return 3 * 4 * static_cast<int64_t>(nll_groups(M, V)) * M * static_cast<int64_t>(sizeof(float)) + 64;
+  // per row and epilogue column group (<= 4): one (max, sum) partial per canonical segment of the vocabulary and one
+  // target-logit partial per work group
+  const int64_t n_tiles = (V + 255) / 256;
+  const int64_t segs = nll_seg_tiles() > 0 ? (n_tiles + nll_seg_tiles() - 1) / nll_seg_tiles() : 8;
+  const int64_t per_row = 4 * (2 * segs + static_cast<int64_t>(nll_groups(M, V)));
+  const int64_t legacy = 3 * 4 * static_cast<int64_t>(nll_groups(M, V));          // (the CTA-pair variant's layout)
+  return (per_row > legacy ? per_row : legacy) * M * static_cast<int64_t>(sizeof(float)) + 64;
 }
 
 int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
@@ -1051,7 +1082,7 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   BLM_REQUIRE(aligned16(d->workspace), BLM_ERR_ALIGN, "workspace must be 16-byte aligned");
   const int groups = nll_groups(d->M, d->V);
   const int col_groups = epi_warps256() / 4;
-  BLM_REQUIRE(d->workspace_bytes >= 3ll * col_groups * groups * d->M * (int64_t)sizeof(float), BLM_ERR_ARG,
+  BLM_REQUIRE(d->workspace_bytes >= blm_vocab_nll_workspace_bytes(d->M, d->V) - 64, BLM_ERR_ARG,
               "workspace too small: %lld bytes", (long long)d->workspace_bytes);
 
   GemmParams p;
@@ -1062,15 +1093,18 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   p.N = static_cast<int>(d->V);
   p.m_tiles = static_cast<int>((d->M + kBM - 1) / kBM);
   p.n_tiles = static_cast<int>((d->V + 255) / 256);
-  p.tiles_per_group = (p.n_tiles + groups - 1) / groups;
+  p.tiles_per_group = nll_tiles_per_group(p.n_tiles, groups);
   const int used_groups = (p.n_tiles + p.tiles_per_group - 1) / p.tiles_per_group;  // no empty groups
   p.n_groups = used_groups;
   p.num_works = p.m_tiles * used_groups;
+  p.seg_tiles = nll_seg_tiles() > 0 ? nll_seg_tiles() : p.tiles_per_group;
   p.bias = d->bias;
   p.targets = d->targets;
   float* ws = reinterpret_cast<float*>(d->workspace);
   p.part_max = ws;
-  const int parts = used_groups * col_groups;
+  const int n_segs = (p.n_tiles + p.seg_tiles - 1) / p.seg_tiles;
+  const int parts = n_segs * col_groups;            // (max, sum) partials: per canonical segment
+  const int tgt_parts = used_groups * col_groups;   // target-logit partials: per work group
   p.part_sum = ws + static_cast<int64_t>(parts) * d->M;
   p.part_tgt = ws + 2 * static_cast<int64_t>(parts) * d->M;
   cudaStream_t st = as_stream(stream);
@@ -1097,8 +1131,8 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
     p2.part_tgt = ws + 2 * static_cast<int64_t>(parts2) * d->M;
     rc = gemm2_nll(p2, g2, st);
     if (rc != BLM_OK) return rc;
-    nll_merge_kernel<<<static_cast<int>((d->M + 255) / 256), 256, 0, st>>>(p2.part_max, p2.part_sum, p2.part_tgt, parts2, p.M,
-                                                                         d->nll, d->lse);
+    nll_merge_kernel<<<static_cast<int>((d->M + 255) / 256), 256, 0, st>>>(p2.part_max, p2.part_sum, p2.part_tgt, parts2, parts2,
+                                                                         p.M, d->nll, d->lse);
     BLM_CHECK_CUDA(cudaGetLastError());
     return BLM_OK;
   }
@@ -1109,7 +1143,7 @@ int blm_vocab_nll(const blm_vocab_nll_desc* d, blm_stream stream) {
   if (rc != BLM_OK) return rc;
   const int threads = 256;
   const int blocks = static_cast<int>((d->M + threads - 1) / threads);
-  nll_merge_kernel<<<blocks, threads, 0, st>>>(p.part_max, p.part_sum, p.part_tgt, parts, p.M,
+  nll_merge_kernel<<<blocks, threads, 0, st>>>(p.part_max, p.part_sum, p.part_tgt, parts, tgt_parts, p.M,
                                                d->nll, d->lse);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;

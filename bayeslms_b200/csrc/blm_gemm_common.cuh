@@ -50,7 +50,8 @@ struct GemmParams {
   float grad_scale;
   // EPI_NLL (and the softmax-grad epilogue)
   const int* targets;
-  float* part_max;  // [n_groups, M]
+  int seg_tiles;    // vocabulary sweep: tiles per canonical segment (the online LSE restarts at every segment boundary)
+  float* part_max;  // [n_segments * column groups, M]  (part_tgt: [n_groups * column groups, M])
   float* part_sum;
   float* part_tgt;
   // generate-once mode of blm_gemm_sampled (gen_wt != null): before the first B tile is loaded every CTA builds
