@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 def main():
     from bayeslms_b200 import model as M, synth
     from bayeslms_b200.scorer import score_files
+    sys.stdout.flush()
+    result_fd = os.dup(1)      # stdout carries the JSON only: NCCL's banner and library chatter go to stderr
+    os.dup2(2, 1)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -76,8 +79,8 @@ def main():
                          "score_checksum": float(np.float64(single.astype(np.float64).sum()))}
     if rank == 0:
         ok = all(r["bit_identical_scores"] and r["identical_rankings"] and r["replicas_agree"] for r in results.values())
-        print(json.dumps({"n_gpus": world, "all_ok": ok, "file": f"{data.n_utts} utterances x {NB}-best, V={V}",
-                          "cases": results}, indent=1))
+        os.write(result_fd, (json.dumps({"n_gpus": world, "all_ok": ok, "file": f"{data.n_utts} utterances x {NB}-best, V={V}",
+                                         "cases": results}, indent=1) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
