@@ -225,7 +225,10 @@ __global__ void __launch_bounds__(kWarpAttnWarps * 32) mha_causal_warp_kernel(
 // mostly padding and the kernel is bound by the q/k/v read anyway (4 KB per token), so the warp-level
 // MMA is the right atom here.
 //   KV_ROWS = 32 : one warp per (hypothesis, head), four pairs per CTA          (max_len <= 32)
-//   KV_ROWS = 128: one CTA per (hypothesis, head), warp w owns query rows [32w, 32w + 32)
+//   KV_ROWS = 128: one CTA per (hypothesis, head, 128-row query block), warp w owns query rows [32w, 32w + 32) of
+//                  the block; the CTA of query block b walks the key / value blocks 0..b (flash-attention style:
+//                  K, V re-staged 128 rows at a time, running max / sum / output carried in registers), so a
+//                  hypothesis may be any length -- the reference scores whatever fits its 5000-row positional table
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
@@ -277,50 +280,53 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
     head = static_cast<int>(pair - static_cast<long long>(seq) * nhead);
     row0 = __ldg(seq_offsets + seq);
     T = __ldg(seq_offsets + seq + 1) - row0;
-    if (T > KV_ROWS) {
+    if (KV_ROWS == 32 && T > KV_ROWS) {
       if (lane == 0) printf("blm: sequence %d has %d tokens > %d\n", seq, T, KV_ROWS);
       __trap();
     }
   }
+  const int qb = KV_ROWS == 128 ? static_cast<int>(blockIdx.y) : 0;   // 128-row query block of the pair
+  const int q0 = qb * 128;                                            // its first token
+  if (KV_ROWS == 128 && q0 >= T) return;                              // (whole CTA: one pair per CTA in this variant)
+  const int Tall = T;                                                 // tokens of the hypothesis
+  T = min(T - q0, 128);                                               // query rows of this block (= T when T <= 128)
   const int d = nhead * kMmaAttnHd;
   const int pb = (warp / WPP) * KV_ROWS;  // first shared-memory row of this pair
-  // ---- stage rows [32 qt, 32 qt + 32) of q, k and v of this pair (zero fill past T).  Lane l copies 16-byte chunk
-  // l % 8 of rows l / 8 + 4 it: one pointer and one swizzled offset per (matrix, part), advanced by constants (the
-  // address arithmetic of the first version was 60 % of this kernel's instructions, ncu r01az).  Rows past the last
-  // 16-row tile that holds a valid token are never read by an MMA and are skipped.
-  {
+  // ---- staging: rows [32 qt, 32 qt + 32) of matrices [m0, m1) (0 = q, 1 = k, 2 = v) of this pair, taken from tokens
+  // tok0.. of the hypothesis, zero fill past `valid` rows.  Lane l copies 16-byte chunk l % 8 of rows l / 8 + 4 it: one
+  // pointer and one swizzled offset per (matrix, part), advanced by constants (the address arithmetic of the first
+  // version was 60 % of this kernel's instructions, ncu r01az).  Rows past the last 16-row tile that holds a valid
+  // token are never read by an MMA and are skipped.
+  auto stage = [&](int m0, int m1, int tok0, int valid) {
     const int r0 = lane >> 3, ch = lane & 7;
-    const int rows_used = min(32, ((T - qt * 32 + 15) & ~15));          // 16 or 32 (<= 0: nothing to stage)
+    const int rows_used = min(32, ((valid - qt * 32 + 15) & ~15));      // 16 or 32 (<= 0: nothing to stage)
     const long long row_step = 4 * ld;                                   // elements between two iterations
     // swizzled chunk position alternates with (row & 7) = r0 or r0 + 4
     const uint32_t sw0 = static_cast<uint32_t>((ch ^ r0) << 4), sw1 = static_cast<uint32_t>((ch ^ (r0 + 4)) << 4);
     const uint32_t dst_row = static_cast<uint32_t>((pb + qt * 32 + r0) * kMmaAttnRowBytes);
-#pragma unroll
-    for (int mat = 0; mat < 3; ++mat) {
+    for (int mat = m0; mat < m1; ++mat) {
 #pragma unroll
       for (int part = 0; part < PARTS; ++part) {
         const __nv_bfloat16* src = (part == 0 ? qkv_hi : qkv_lo) + mat * d + head * kMmaAttnHd + ch * 8 +
-                                   static_cast<long long>(row0 + qt * 32 + r0) * ld;
+                                   static_cast<long long>(row0 + tok0 + qt * 32 + r0) * ld;
         const uint32_t dst = tile(mat, part) + dst_row;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           if (it * 4 < rows_used) {
-            const bool ok = qt * 32 + r0 + it * 4 < T;
+            const bool ok = qt * 32 + r0 + it * 4 < valid;
             cp_async16(dst + static_cast<uint32_t>(it * 4 * kMmaAttnRowBytes) + ((it & 1) ? sw1 : sw0),
                        ok ? src + it * row_step : src, ok ? 16u : 0u);
           }
         }
       }
     }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (qt * 32 >= T) return;
+  };
+  stage(0, 1, q0, T);                       // the query rows of this block
+  const bool active = qt * 32 < T;          // this warp owns query rows (all warps stage and meet at the barriers)
 
   const int g = lane >> 2, t4 = lane & 3;
-  const int i_hi = min(T, qt * 32 + 32) - 1;      // last valid query row of this warp
-  const int nmt = (i_hi - qt * 32) / 16 + 1;      // m16 tiles in use (1 or 2)
+  const int i_hi = min(T, qt * 32 + 32) - 1;      // last valid query row of this warp (inside the query block)
+  const int nmt = active ? (i_hi - qt * 32) / 16 + 1 : 0;   // m16 tiles in use (1 or 2)
   constexpr float kLog2e = 1.4426950408889634f;
 
   float o[2][8][4];
@@ -339,8 +345,16 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
     return base + static_cast<uint32_t>(row * kMmaAttnRowBytes + ((chunk ^ (row & 7)) << 4));
   };
 
-  for (int kb = 0; kb <= qt; ++kb) {
-    const int jmax = min(i_hi, kb * 32 + 31);
+  for (int c = 0; c <= qb; ++c) {           // key / value blocks of 128 tokens, up to the query block's own
+  if (c > 0) __syncthreads();               // every warp is done with the previous block's tiles
+  stage(1, 3, c * 128, min(Tall - c * 128, 128));
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int joff = (c - qb) * 128;          // key index relative to the query block: <= -128 for earlier blocks
+  const int kb_last = !active ? -1 : (c == qb ? qt : 3);
+  for (int kb = 0; kb <= kb_last; ++kb) {
+    const int jmax = c == qb ? min(i_hi, kb * 32 + 31) : kb * 32 + 31;
     const int nnt = (jmax - kb * 32) / 8 + 1;  // n8 key tiles in use (1..4)
     float s[2][4][4];
 #pragma unroll
@@ -395,7 +409,7 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
           for (int e = 0; e < 4; ++e) {
             const int i = qt * 32 + mt * 16 + g + ((e >> 1) << 3);
             const int j = kb * 32 + nt * 8 + 2 * t4 + (e & 1);
-            const float v = (j <= i && nt < nnt) ? s[mt][nt][e] * kLog2e : -INFINITY;
+            const float v = (j + joff <= i && nt < nnt) ? s[mt][nt][e] * kLog2e : -INFINITY;
             s[mt][nt][e] = v;
             mx[e >> 1] = fmaxf(mx[e >> 1], v);
           }
@@ -433,8 +447,8 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
             for (int h = 0; h < 2; ++h) {
               const int i = qt * 32 + mt * 16 + g + 8 * h;
               const int j0 = kb * 32 + nt * 8 + 2 * t4;
-              if (nt < nnt && i < T && j0 <= i) {   // (elements with j > i are already zero)
-                const float2 dm = drop_mult2(dr, mbase + static_cast<long long>(i) * ldm + j0);
+              if (nt < nnt && i < T && j0 + joff <= i) {   // (elements with j > i are already zero)
+                const float2 dm = drop_mult2(dr, mbase + static_cast<long long>(q0 + i) * ldm + c * 128 + j0);
                 s[mt][nt][2 * h] *= dm.x;
                 s[mt][nt][2 * h + 1] *= dm.y;
               }
@@ -483,6 +497,8 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
       }
     }
   }
+  }   // key / value blocks
+  if (!active) return;
   // ---- normalise and store: thread holds rows g, g + 8 of each m tile, columns 8 ct + 2 t4 + {0, 1}
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
         const float inv = 1.0f / l;
         const int i = qt * 32 + mt * 16 + g + 8 * h;
         if (i < T) {
-          const long long off = static_cast<long long>(row0 + i) * ldo + head * kMmaAttnHd + 2 * t4;
+          const long long off = static_cast<long long>(row0 + q0 + i) * ldo + head * kMmaAttnHd + 2 * t4;
 #pragma unroll
           for (int ct = 0; ct < 8; ++ct) {
             const float x0 = o[mt][ct][2 * h] * inv, x1 = o[mt][ct][2 * h + 1] * inv;
@@ -993,7 +1009,9 @@ extern "C" int blm_mha_causal_bf16_dropout(const blm_bf16* qkv_hi, const blm_bf1
   const int ldm = (max_len + 3) & ~3;
   BLM_REQUIRE(qkv_hi && seq_offsets && nseq > 0 && nhead > 0, BLM_ERR_ARG, "bad attention arguments");
   BLM_REQUIRE(head_dim == kMmaAttnHd, BLM_ERR_SHAPE, "the tensor-core attention kernel needs head_dim 64, got %d", head_dim);
-  BLM_REQUIRE(max_len > 0 && max_len <= 128, BLM_ERR_SHAPE, "max_len %d not in (0, 128]", max_len);
+  BLM_REQUIRE(max_len > 0 && max_len <= 8192, BLM_ERR_SHAPE, "max_len %d not in (0, 8192]", max_len);
+  BLM_REQUIRE(!dropping || max_len <= 128, BLM_ERR_SHAPE, "attention dropout (training) is limited to 128 tokens per "
+              "sequence like the backward kernel, got %d", max_len);
   BLM_REQUIRE(out_f32 || out_hi, BLM_ERR_ARG, "no output buffer");
   BLM_REQUIRE(!out_lo || out_hi, BLM_ERR_ARG, "out_lo requires out_hi");
   BLM_REQUIRE((ld % 8) == 0 && ld >= 3ll * nhead * head_dim && (ldo % 2) == 0 && ldo >= (int64_t)nhead * head_dim,
@@ -1043,7 +1061,8 @@ extern "C" int blm_mha_causal_bf16_dropout(const blm_bf16* qkv_hi, const blm_bf1
       mha_causal_mma_kernel<false, 32><<<blocks, 128, mma_attn_smem_bytes<false>(), st>>>(qh, ql, ld, seq_offsets, pairs,
                                                                                       nhead, out_f32, oh, ol, ldo);
   } else {
-    const unsigned blocks = static_cast<unsigned>(pairs);
+    // one CTA per (pair, 128-row query block); blocks past a hypothesis' length exit at once
+    const dim3 blocks(static_cast<unsigned>(pairs), static_cast<unsigned>((max_len + 127) / 128));
     if (ql)
       mha_causal_mma_kernel<true, 128><<<blocks, 128, mma_attn_smem_bytes<true>(), st>>>(qh, ql, ld, seq_offsets, pairs, nhead,
                                                                                      out_f32, oh, ol, ldo);

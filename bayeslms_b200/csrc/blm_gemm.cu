@@ -582,13 +582,31 @@ static int set_smem_attr_chunk() {
   return BLM_OK;
 }
 
+// Every GEMM launch goes through here.  A launch that draws its sampled weights first (generate_weights /
+// wait_generated: a grid-wide spin barrier) must have ALL its CTAs resident at once: it is launched cooperatively, so
+// the driver either co-schedules the whole grid -- also when kernels of other streams occupy SMs -- or refuses the
+// launch with an error; it can no longer start partially and spin until the watchdog trap.
+template <typename Kernel>
+static int launch_gemm(Kernel kernel, int grid, int threads, int smem, cudaStream_t st, const GemmParams& p) {
+  if (p.gen_wt) {
+    int per_sm = 0;
+    BLM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    BLM_REQUIRE(static_cast<long long>(per_sm) * num_sms() >= grid, BLM_ERR_SHAPE,
+                "generate-once sampled GEMM: a grid of %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm,
+                num_sms());
+    void* args[] = {const_cast<GemmParams*>(&p)};
+    BLM_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(threads), args, smem, st));
+    return BLM_OK;
+  }
+  kernel<<<grid, threads, smem, st>>>(p);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
 template <int ACT>
 static int launch_chunk(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<128, kStages128, EPI_STORE, ACT, 0, 8, 1>
-      <<<grid, (4 + 8) * 32, SmemLayout<128, kStages128, 0>::kDynBytes, st>>>(p);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+  return launch_gemm(gemm_kernel<128, kStages128, EPI_STORE, ACT, 0, 8, 1>, grid, (4 + 8) * 32, SmemLayout<128, kStages128, 0>::kDynBytes, st, p);
 }
 
 // transposed-store (STG) variants: the fp32-output GEMMs (QKV in training, o_net, FFN2) and the GELU-gradient
@@ -604,10 +622,7 @@ static int set_smem_attr_stg() {
 template <int BN, int STAGES, int CHUNK, int ACT = BLM_ACT_NONE>
 static int launch_stg(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, CHUNK, 1>
-      <<<grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st>>>(p);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+  return launch_gemm(gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, CHUNK, 1>, grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st, p);
 }
 
 // TMA-store (STG == 2) variants: bf16-hi-only outputs of the forward GEMMs (QKV, FFN1)
@@ -630,10 +645,7 @@ static int set_smem_attr_tma16() {
 template <int ACT>
 static int launch_tma16(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<256, kStages256, EPI_STORE, ACT, 0, 16, 0, 2>
-      <<<grid, (4 + 16) * 32, SmemLayout<256, kStages256, 0>::kDynBytes, st>>>(p);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+  return launch_gemm(gemm_kernel<256, kStages256, EPI_STORE, ACT, 0, 16, 0, 2>, grid, (4 + 16) * 32, SmemLayout<256, kStages256, 0>::kDynBytes, st, p);
 }
 
 // A-resident form of the 16-epilogue-warp TMA-store kernel for K <= 512 (QKV, FFN1): the 128 x 512 activation
@@ -650,19 +662,13 @@ static int set_smem_attr_tma16_ares() {
 template <int ACT>
 static int launch_tma16_ares(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<256, kAresStoreStages, EPI_STORE, ACT, kNllAres, 16, 0, 2>
-      <<<grid, (4 + 16) * 32, SmemLayout<256, kAresStoreStages, kNllAres>::kDynBytes, st>>>(p);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+  return launch_gemm(gemm_kernel<256, kAresStoreStages, EPI_STORE, ACT, kNllAres, 16, 0, 2>, grid, (4 + 16) * 32, SmemLayout<256, kAresStoreStages, kNllAres>::kDynBytes, st, p);
 }
 
 template <int BN, int STAGES, int ACT>
 static int launch_tma(const GemmParams& p, cudaStream_t st) {
   const int grid = p.num_works < num_sms() ? p.num_works : num_sms();
-  gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, 0, 2>
-      <<<grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st>>>(p);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+  return launch_gemm(gemm_kernel<BN, STAGES, EPI_STORE, ACT, 0, 8, 0, 2>, grid, (4 + 8) * 32, SmemLayout<BN, STAGES, 0>::kDynBytes, st, p);
 }
 
 int gemm_init() {
@@ -721,14 +727,10 @@ static int launch(const GemmParams& p, cudaStream_t st) {
   constexpr int smem = SmemLayout<BN, STAGES, ARES>::kDynBytes;
   if constexpr (BN == 256) {
     if (epi_warps256() == 16) {
-      gemm_kernel<BN, STAGES, EPI, ACT, ARES, 16><<<grid, (4 + 16) * 32, smem, st>>>(p);
-      BLM_CHECK_CUDA(cudaGetLastError());
-      return BLM_OK;
+      return launch_gemm(gemm_kernel<BN, STAGES, EPI, ACT, ARES, 16>, grid, (4 + 16) * 32, smem, st, p);
     }
   }
-  gemm_kernel<BN, STAGES, EPI, ACT, ARES, 8><<<grid, (4 + 8) * 32, smem, st>>>(p);
-  BLM_CHECK_CUDA(cudaGetLastError());
-  return BLM_OK;
+  return launch_gemm(gemm_kernel<BN, STAGES, EPI, ACT, ARES, 8>, grid, (4 + 8) * 32, smem, st, p);
 }
 
 int gemm2_store(GemmParams p, int act, cudaStream_t st, int tma_store);   // blm_gemm2.cu: CTA-pair (cta_group::2) kernels

@@ -226,6 +226,12 @@ class _TmRun:
         self.nhead = model.nhead
         self.M = batch.n_tokens
         self.dev = plan.device
+        if batch.max_len > plan.pe.shape[0]:
+            raise _lib.BlmError(f"a hypothesis has {batch.max_len} tokens, the positional table of the model has "
+                                f"{plan.pe.shape[0]} rows (PositionalEncoding max_len, model.py:93)")
+        if model.ninp // self.nhead != 64 and batch.max_len > 128:
+            raise _lib.BlmError(f"a hypothesis has {batch.max_len} tokens: the fp32 attention kernel of head dimensions "
+                                "other than 64 handles at most 128 (the tensor-core kernel of head_dim 64 has no limit)")
         self.v_train = None            # (B, T, seed, 0) when the variational layers add their training noise
         self.fused_sampling = False    # True: tile-stationary blm_gemm_sampled (W~ never stored)
         # fast mode default: the sampled FFN weight is drawn inside the GEMM launch (generate-once blm_gemm_sampled);

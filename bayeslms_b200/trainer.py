@@ -53,6 +53,11 @@ _OVERLAP = os.environ.get("BLM_TRAIN_OVERLAP") is not None
 # 148 SMs) -- so they are captured on a second stream and fill those SMs while the dX chain proceeds
 # (BLM_TRAIN_WGRAD_STREAM=0 is the A/B switch).
 _WGRAD_STREAM = os.environ.get("BLM_TRAIN_WGRAD_STREAM", "1") != "0"
+# Data parallel, captured step: the NCCL all-reduce of each layer's gradient range is captured INSIDE the backward graph,
+# on the second stream, as soon as that layer's gradients are final -- it runs while the dX chain works through the lower
+# layers; only the embedding / decoder range (final at the very end) is reduced on the critical path
+# (BLM_TRAIN_NCCL_GRAPH=0: one eager all-reduce of the whole buffer between the two graphs, the r01 scheme).
+_NCCL_IN_GRAPH = os.environ.get("BLM_TRAIN_NCCL_GRAPH", "1") != "0"
 
 
 class _T:
@@ -112,6 +117,7 @@ class FineTuner:
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
         self._keep, self._forked, self._side = [], False, None     # side-stream launches of the captured step (_aside)
+        self._ar_in_graph, self._ar_works = False, []
         self._drop = None          # per-step dropout state, see _begin_dropout
         self._seed_dev = None      # device int64 [1] added to the dropout key inside captured graphs
         named = list(model.named_parameters())          # tied encoder / decoder weight appears once
@@ -217,6 +223,26 @@ class FineTuner:
         self._keep.extend(keep)
         self._forked = True
         return torch.cuda.stream(self._side)
+
+    def _layer_range(self, li: int):
+        """[lo, hi) of layer ``li``'s parameters in the flat buffers (named_parameters keeps a layer contiguous)."""
+        pre = ("transformerlayers.layers." if self.model.family == "std_tm" else "transformerlayers.") + f"{li}."
+        spans = [(o, o + n) for name, (o, n) in self._offs.items() if name.startswith(pre)]
+        return min(a for a, _ in spans), max(b for _, b in spans)
+
+    def _allreduce_in_graph(self, lo: int, hi: int, final: bool = False):
+        """Captured all-reduce of flat_g[lo:hi].  Non-final ranges go to the second stream (asynchronous: the compute
+        of the lower layers overlaps the transfer); everything is waited for when the final range has been issued."""
+        dist = torch.distributed
+        if not final:
+            with self._aside():
+                self._ar_works.append(dist.all_reduce(self.flat_g[lo:hi], group=self.group, async_op=True))
+            return
+        if hi > lo:
+            self._ar_works.append(dist.all_reduce(self.flat_g[lo:hi], group=self.group, async_op=True))
+        for w in self._ar_works:
+            w.wait()
+        self._ar_works = []
 
     def _join_aside(self):
         if getattr(self, "_forked", False):
@@ -556,6 +582,8 @@ class FineTuner:
                     ops.colsum(dqkv, g[pre + "self_attn.qkv_net.bias"])
             if on_layer_done is not None:
                 on_layer_done(li)      # every gradient of layers >= li is final (capture() splits the graph here)
+            if self._ar_in_graph:
+                self._allreduce_in_graph(*self._layer_range(li))
         if drop_pe is not None:
             dx, _ = ops.dropout(dx, drop_pe, out_f32=dx)
         if emb_variant:   # back through x0 W~^T: G = dx^T x0 (-> embed_mean, embed_lgstd), dx0 = dx W~
@@ -579,6 +607,15 @@ class FineTuner:
         # loss = ce + kl * kl_scale
         ops.reduce_sum(ce, loss)
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
+        if self._ar_in_graph:
+            # what is not a layer (embedding / decoder, positional-free extras) sits in [0, first layer) and
+            # [last layer end, total): final only now.  Two ranges -> the second one closes the wait list.
+            nl = len(m.transformerlayers)
+            first_lo = self._layer_range(0)[0] if nl else self.flat_g.numel()
+            last_hi = self._layer_range(nl - 1)[1] if nl else self.flat_g.numel()
+            if first_lo > 0:
+                self._ar_works.append(torch.distributed.all_reduce(self.flat_g[:first_lo], group=self.group, async_op=True))
+            self._allreduce_in_graph(last_hi, self.flat_g.numel(), final=True)
         return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
 
     def _loss_and_decoder_grads(self, xs: Split, tgt: torch.Tensor):
@@ -1106,10 +1143,26 @@ class FineTuner:
             inside = [n for n, (o, _) in self._offs.items() if lo <= o < hi]
             if all(n.startswith("transformerlayers.") and int(n.split(".")[1]) >= sl for n in inside):
                 cap["split"] = (sl, lo, hi)
+        cap["ar_in_graph"] = False
         if cap["split"] is None:
             cap["g1"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cap["g1"]):
-                cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
+            in_graph = self.world > 1 and _NCCL_IN_GRAPH and self.model.family not in ("bayes_lstm", "std_lstm", "gauss_lstm", "v_lstm")
+            if in_graph:
+                # NCCL's watchdog thread polls its events while this thread captures: thread-local capture mode keeps
+                # that legal; one eager all-reduce first so that the communicator exists before the capture starts
+                torch.distributed.all_reduce(torch.zeros(1, device=self.device), group=self.group)
+                torch.cuda.synchronize()
+                self._ar_in_graph = True
+                try:
+                    with torch.cuda.graph(cap["g1"], capture_error_mode="thread_local"):
+                        cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"],
+                                                           v_eps_layout="btd")
+                finally:
+                    self._ar_in_graph = False
+                cap["ar_in_graph"] = True
+            else:
+                with torch.cuda.graph(cap["g1"]):
+                    cap["out"] = self.forward_backward(cap["x"], cap["y"], cap["kl_scale"], eps=cap["eps"], v_eps_layout="btd")
         else:
             sl = cap["split"][0]
             cap["g1"], cap["g1b"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -1170,7 +1223,7 @@ class FineTuner:
                 works.append(dist.all_reduce(self.flat_g[hi:], group=self.group, async_op=True))
             for w in works:
                 w.wait()
-        elif self.world > 1:
+        elif self.world > 1 and not cap.get("ar_in_graph"):
             torch.distributed.all_reduce(self.flat_g, group=self.group)
         cap["g2"].replay()
         self.model.__dict__.pop("_blm_plans", None)

@@ -100,7 +100,8 @@ def _attention_ref(qkv, offs, nhead):
 
 
 ATTN_LENS = [[1, 5, 17, 26, 32, 2], [100, 100, 7], [1, 2, 7, 8, 9, 15, 16, 17, 26, 31, 32, 5, 5, 5, 11, 13, 3],
-             list(range(1, 27)) * 3, [33, 64, 65, 96, 97, 128, 1]]
+             list(range(1, 27)) * 3, [33, 64, 65, 96, 97, 128, 1],
+             [129, 5, 200, 128, 257, 300, 1, 640]]      # > 128 tokens: key / value blocks walked flash-attention style
 
 
 @pytest.mark.parametrize("lens", ATTN_LENS)

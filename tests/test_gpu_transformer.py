@@ -181,6 +181,34 @@ def test_file_path_equals_per_hypothesis_path(golden, tmp_path, family):
         assert S.NbestText(str(npth)).contiguous == (variant == "contiguous")
 
 
+def test_hypotheses_longer_than_128_tokens():
+    """The reference scores any hypothesis that fits its 5000-row positional table (model.py:93); the attention kernel
+    walks key / value blocks of 128 tokens for longer ones.  Head_dim-64 model, hypotheses of 150 / 300 / 40 / 129 tokens,
+    both precision modes against the oracle; the length limit that remains (the positional table) fails up front."""
+    from bayeslms_b200 import _lib, model as M
+    from bayeslms_b200.engine import PackedBatch
+    torch.manual_seed(3)
+    V, d, nhead, ff, nl = 300, 128, 2, 256, 2
+    net = M.BayesTransformerModel(V, d, nhead, ff, nl, 0.5, True, "FFN")
+    with torch.no_grad():
+        net.decoder.bias.uniform_(-0.1, 0.1)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.Config(family="bayes_tm", bayes_pos="FFN", ntoken=V, ninp=d, nhead=nhead, nhid=ff, nlayers=nl)
+    net = net.to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    hyps = [torch.randint(2, V, (n,), generator=g).tolist() for n in (149, 299, 39, 128, 5)]
+    ins, tgts = [[0] + h for h in hyps], [h + [0] for h in hyps]
+    want = _oracle_hyp_nll(sd, cfg, ins, tgts)
+    batch = PackedBatch.from_lists(ins, tgts, DEV)
+    got = net.score(batch, prec="bf16x3").cpu()
+    assert (got - want).abs().max().item() < 3e-3, (got - want).abs().max().item()       # up to 300 tokens per hypothesis
+    fast = net.score(batch, prec="bf16").cpu()
+    assert ((fast - want).abs() <= 1e-1 + 2e-3 * want.abs()).all()
+    too_long = [[0] + [5] * 5000]
+    with pytest.raises(_lib.BlmError, match="positional"):
+        net.score(PackedBatch.from_lists(too_long, [[5] * 5000 + [0]], DEV), prec="bf16")
+
+
 def test_fused_sampled_gemm_bit_exact_and_model_level(golden):
     """blm_gemm_sampled: (i) kernel level, bit-identical to bf16(mu + sigma*eps) fed to the plain GEMM, for
     injected eps and for device Philox noise; (ii) model level, same scores as the materialised path."""

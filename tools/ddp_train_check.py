@@ -51,32 +51,38 @@ if rank == 0:
 assert abs(l_ddp.item() - l_one.item()) < 1e-4
 assert err <= 2e-3 * upd + 1e-7, (err, upd)
 
-# ---- the CUDA-graph path: backward captured as two graphs, all-reduce of the upper layers overlapped with the second
+# ---- the CUDA-graph paths: (a) default -- per-layer NCCL all-reduces captured inside the backward graph on the second
+# stream; (b) opt-in BLM_TRAIN_OVERLAP -- backward captured as two graphs, eager all-reduce of the upper layers in between
 V2, D2, FF2, T2 = 2000, 128, 512, 24
 def build2():
     torch.manual_seed(5)
-    return M.BayesTransformerModel(V2, D2, NHEAD, FF2, 4, 0.0, True, "none").to(dev).train()
+    return M.BayesTransformerModel(V2, D2, NHEAD, FF2, 4, 0.0, True, "FFN").to(dev).train()
 x2 = torch.randint(0, V2, (T2, Bg), generator=g).to(dev)
 y2 = torch.randint(0, V2, (T2, Bg), generator=g).to(dev)
-cap_net = build2()
-_trainer._OVERLAP = True           # exercise the opt-in overlapped path
-fc = FineTuner(cap_net, lr, clip=0.25, prec="bf16x3")
-fc.capture(T2, Bg // world, kl_scale)
-split = fc._cap.get("split")
-for it in range(2):
-    fc.step_captured(x2[:, b0:b1].contiguous(), y2[:, b0:b1].contiguous(), 7 + it)
 one_net = build2()
 fo = FineTuner(one_net, lr, clip=0.25, prec="bf16x3")
 fo.world = 1
-for it in range(2):
+for it in range(3):
     fo.step(x2, y2, kl_scale, seed=7 + it)
 torch.cuda.synchronize()
-err2 = (fc.flat_p - fo.flat_p).abs().max().item()
 upd2 = (fo.flat_v.abs().max() * lr).item()
-if rank == 0:
-    print(f"captured + overlapped all-reduce (split {split}): max |param diff| {err2:.3e} vs max update {upd2:.3e}", flush=True)
-assert split is not None, "the backward graph was not split"
-assert err2 <= 2e-3 * upd2 + 1e-7, (err2, upd2)
+for mode in ("nccl_in_graph", "two_graphs"):
+    _trainer._OVERLAP = mode == "two_graphs"
+    cap_net = build2()
+    fc = FineTuner(cap_net, lr, clip=0.25, prec="bf16x3")
+    fc.capture(T2, Bg // world, kl_scale)
+    for it in range(3):
+        fc.step_captured(x2[:, b0:b1].contiguous(), y2[:, b0:b1].contiguous(), 7 + it)
+    torch.cuda.synchronize()
+    err2 = (fc.flat_p - fo.flat_p).abs().max().item()
+    if rank == 0:
+        print(f"captured step, {mode} (in-graph all-reduce: {fc._cap.get('ar_in_graph')}, split {fc._cap.get('split')}): "
+              f"max |param diff| {err2:.3e} vs max update {upd2:.3e}", flush=True)
+    assert (mode == "nccl_in_graph") == bool(fc._cap.get("ar_in_graph")) or not _trainer._NCCL_IN_GRAPH
+    assert (mode == "two_graphs") == (fc._cap.get("split") is not None)
+    assert err2 <= 2e-3 * upd2 + 1e-7, (mode, err2, upd2)
+    del fc, cap_net
+_trainer._OVERLAP = False
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
