@@ -57,7 +57,7 @@ _WGRAD_STREAM = os.environ.get("BLM_TRAIN_WGRAD_STREAM", "1") != "0"
 # on the second stream, as soon as that layer's gradients are final -- it runs while the dX chain works through the lower
 # layers; only the embedding / decoder range (final at the very end) is reduced on the critical path
 # (BLM_TRAIN_NCCL_GRAPH=0: one eager all-reduce of the whole buffer between the two graphs, the r01 scheme).
-_NCCL_IN_GRAPH = os.environ.get("BLM_TRAIN_NCCL_GRAPH", "1") != "0"
+_NCCL_IN_GRAPH = os.environ.get("BLM_TRAIN_NCCL_GRAPH", "0") != "0"
 
 
 class _T:
@@ -236,13 +236,30 @@ class FineTuner:
         dist = torch.distributed
         if not final:
             with self._aside():
-                self._ar_works.append(dist.all_reduce(self.flat_g[lo:hi], group=self.group, async_op=True))
+                self._ar_works.append(dist.all_reduce(self.flat_g[lo:hi], group=self._background_group(), async_op=True))
             return
         if hi > lo:
             self._ar_works.append(dist.all_reduce(self.flat_g[lo:hi], group=self.group, async_op=True))
         for w in self._ar_works:
             w.wait()
         self._ar_works = []
+
+    def _background_group(self):
+        """Communicator of the overlapped all-reduces: few NCCL CTAs (BLM_TRAIN_NCCL_CTAS, default 4), so that the
+        transfer trickles along behind the backward kernels instead of taking their SMs."""
+        if getattr(self, "_bg_group", None) is None:
+            dist = torch.distributed
+            n = int(os.environ.get("BLM_TRAIN_NCCL_CTAS", "4"))
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = n
+                opts.config.min_ctas = 1
+                self._bg_group = dist.new_group(pg_options=opts)
+                dist.all_reduce(torch.zeros(1, device=self.device), group=self._bg_group)   # communicator built now
+                torch.cuda.synchronize()
+            except Exception:
+                self._bg_group = self.group
+        return self._bg_group
 
     def _join_aside(self):
         if getattr(self, "_forked", False):
@@ -1152,6 +1169,7 @@ class FineTuner:
                 # that legal; one eager all-reduce first so that the communicator exists before the capture starts
                 torch.distributed.all_reduce(torch.zeros(1, device=self.device), group=self.group)
                 torch.cuda.synchronize()
+                self._background_group()
                 self._ar_in_graph = True
                 try:
                     with torch.cuda.graph(cap["g1"], capture_error_mode="thread_local"):

@@ -138,10 +138,16 @@ def bench_finetune(dev, world, steps, warmup=3, dropout=0.0):
     byts = n_par * (4 + 4 + 4 + 4 + 4 + 4 + 2.0)
     pk = peaks()
     tf = flop / (ms.item() / 1e3) / 1e12
+    in_graph = bool(ft._cap.get("ar_in_graph"))
+    ft._cap = None            # release the graphs (captured NCCL work) before anything else touches the communicator
+    del ft
+    torch.cuda.synchronize()
     return {"workload": "Variational Transformer LM (T_v_pos=11) 5L d512 FFN4096 V30000 fine-tune step, "
                         "32 x 100 tokens per GPU, CE + KL, clip, SGD momentum", "dtype": "bf16",
             "tokens_per_s": T * B * world / (ms.item() / 1e3), "ms_per_step": ms.item(),
-            "parallelism": f"dp{world}: replicated weights, one NCCL all-reduce of the flat gradient buffer per step",
+            "parallelism": f"dp{world}: replicated weights, " + ("per-layer NCCL all-reduces captured inside the backward graph "
+                                                                   "(second stream), embedding / decoder range at the end"
+                                                                   if in_graph else "one NCCL all-reduce of the flat gradient buffer per step"),
             "loss_first": losses[0], "loss_last": losses[-1], "dropout": dropout,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
                          "flop_per_step": flop, "hbm_bytes_per_step": byts,

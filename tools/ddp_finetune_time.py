@@ -16,8 +16,10 @@ T, B = 100, 32
 g = torch.Generator().manual_seed(1111 + rank)
 x = torch.randint(0, bench.V, (T, B), generator=g).to(dev)
 y = torch.randint(0, bench.V, (T, B), generator=g).to(dev)
-for overlap in (True, False, True, False):
-    trainer._OVERLAP = overlap
+for mode in ("nccl_in_graph", "eager_allreduce", "nccl_in_graph", "eager_allreduce"):
+    trainer._OVERLAP = mode == "two_graphs"
+    trainer._NCCL_IN_GRAPH = mode == "nccl_in_graph"
+    overlap = mode
     torch.manual_seed(1111)
     net = M.VTransformerModel(bench.V, bench.D, bench.NHEAD, bench.FF, bench.NLAYERS, 0.0, True, "11").to(dev).train()
     ft = trainer.FineTuner(net, 0.01, clip=0.25, prec="bf16")
@@ -33,7 +35,10 @@ for overlap in (True, False, True, False):
     ms = torch.tensor([e0.elapsed_time(e1) / 30], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"world {world} overlap {overlap} split {ft._cap.get('split')}: {ms.item():.3f} ms per step, "
+        print(f"world {world} {overlap} (in-graph {ft._cap.get('ar_in_graph')}, split {ft._cap.get('split')}): {ms.item():.3f} ms per step, "
               f"{T * B * world / ms.item() * 1e3 / 1e6:.2f} M tokens/s", flush=True)
+    ft._cap = None
     del ft, net
+    torch.cuda.synchronize()
+dist.barrier()
 dist.destroy_process_group()

@@ -56,7 +56,11 @@ assert err <= 2e-3 * upd + 1e-7, (err, upd)
 V2, D2, FF2, T2 = 2000, 128, 512, 24
 def build2():
     torch.manual_seed(5)
-    return M.BayesTransformerModel(V2, D2, NHEAD, FF2, 4, 0.0, True, "FFN").to(dev).train()
+    net = M.BayesTransformerModel(V2, D2, NHEAD, FF2, 4, 0.0, True, "FFN")
+    # layer 0 of the Bayesian model drops with the hard-coded 0.2 (model.py:1202,1207): activation masks are drawn per
+    # rank for the rank's own rows, which a single-rank run on the global batch cannot reproduce -- switched off here
+    net.transformerlayers[0].p_drop = 0.0
+    return net.to(dev).train()
 x2 = torch.randint(0, V2, (T2, Bg), generator=g).to(dev)
 y2 = torch.randint(0, V2, (T2, Bg), generator=g).to(dev)
 one_net = build2()
@@ -81,8 +85,12 @@ for mode in ("nccl_in_graph", "two_graphs"):
     assert (mode == "nccl_in_graph") == bool(fc._cap.get("ar_in_graph")) or not _trainer._NCCL_IN_GRAPH
     assert (mode == "two_graphs") == (fc._cap.get("split") is not None)
     assert err2 <= 2e-3 * upd2 + 1e-7, (mode, err2, upd2)
+    fc._cap = None          # release the graphs (they hold captured NCCL work) before the process group goes away
     del fc, cap_net
 _trainer._OVERLAP = False
+import gc
+gc.collect()
+torch.cuda.synchronize()
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
