@@ -166,6 +166,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
 
   int total_kb = 0;
   for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+  const bool x3 = CHUNK && p.x3;        // precise-mode triples: one stage = A.hi, A.lo, B.hi, B.lo of a K block
+  if (x3) total_kb /= 3;                // K blocks of the distinct operands (each feeds three products)
 
   if (warp == 0) {
     // ------------------------------------------------------ TMA producer
@@ -173,6 +175,54 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       if (p.gen_wt) wait_generated(p);
+      if constexpr (CHUNK) {
+        if (x3) {
+          // The split product hi*lo + lo*hi + hi*hi re-uses every operand tile twice.  Loading the three segments one
+          // after the other (six tile loads per K block) made the precise mode bound by the L2 -> shared-memory
+          // traffic of its 128 x 128 tiles (4.05x the bf16 step instead of 3x); here a stage of 64 KB = two ring slots
+          // carries the four distinct tiles once.
+          constexpr int kTile = L::kABytes;                       // 16 KB: [128 x 64] bf16 (BN == 128)
+          constexpr int kStages3 = STAGES / 2;
+          for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
+            const int m_tile = w / p.n_groups;
+            const int grp = w - m_tile * p.n_groups;
+            const int n0 = grp * p.tiles_per_group;
+            const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+            for (int n = n0; n < n1; ++n)
+              for (int ls = 0; ls < p.nseg; ls += 3)
+                for (int kb = 0; kb < p.kblocks[ls]; ++kb) {
+                  mbar_wait(&empty_bar[stage], phase ^ 1u);
+                  mbar_arrive_expect_tx(&full_bar[stage], 4 * kTile);
+                  uint8_t* st = ring + stage * 4 * kTile;
+                  // segment ls = (A.hi, B.lo), ls + 1 = (A.lo, B.hi): their tensor maps name the four tiles
+                  const CUtensorMap* ta[2] = {&p.tmA[ls], &p.tmA[ls + 1]};
+                  const CUtensorMap* tb[2] = {&p.tmB[ls + 1], &p.tmB[ls]};
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    if (!p.a_mn) {
+                      tma_load_2d(st + h * kTile, ta[h], &full_bar[stage], kb * kBK, m_tile * kBM, kEvictNormal);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < kBM / 64; ++j)
+                        tma_load_2d(st + h * kTile + j * 8192, ta[h], &full_bar[stage], m_tile * kBM + 64 * j, kb * kBK, kEvictNormal);
+                    }
+                    if (!p.b_mn) {
+                      tma_load_2d(st + (2 + h) * kTile, tb[h], &full_bar[stage], kb * kBK, n * BN, kEvictLast);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < BN / 64; ++j)
+                        tma_load_2d(st + (2 + h) * kTile + j * 8192, tb[h], &full_bar[stage], n * BN + 64 * j, kb * kBK, kEvictLast);
+                    }
+                  }
+                  if (++stage == kStages3) {
+                    stage = 0;
+                    phase ^= 1u;
+                  }
+                }
+          }
+        }
+      }
+      if (!x3)
       for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
         const int m_tile = w / p.n_groups;
         const int grp = w - m_tile * p.n_groups;
@@ -235,6 +285,55 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) gemm_kernel(const __grid_con
       uint32_t phase = 0, a_phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (CHUNK) {
+        if (x3) {
+          constexpr int kTile = L::kABytes;
+          constexpr int kStages3 = STAGES / 2;
+          for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
+            const int m_tile = w / p.n_groups;
+            const int grp = w - m_tile * p.n_groups;
+            const int n0 = grp * p.tiles_per_group;
+            const int n1 = min(p.n_tiles, n0 + p.tiles_per_group);
+            for (int n = n0; n < n1; ++n)
+              for (int kb0 = 0; kb0 < total_kb; kb0 += p.chunk_kb) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+                const int kb1 = min(total_kb, kb0 + p.chunk_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                  mbar_wait(&full_bar[stage], phase);
+                  tcgen05_fence_after();
+                  const uint32_t st = smem_u32(ring + stage * 4 * kTile);
+                  uint64_t da[2], db[2];
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    da[h] = p.a_mn ? umma_desc_sw128_mn(st + h * kTile) : umma_desc_sw128(st + h * kTile);
+                    db[h] = p.b_mn ? umma_desc_sw128_mn(st + (2 + h) * kTile) : umma_desc_sw128(st + (2 + h) * kTile);
+                  }
+                  // small terms first (the accumulator truncates relative to the running sum): hi*lo, lo*hi, hi*hi
+                  const int ia[3] = {0, 1, 0}, ib[3] = {1, 0, 0};
+#pragma unroll
+                  for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                      umma_bf16_ss(tmem_d, da[ia[t3]] + static_cast<uint64_t>(k) * a_step, db[ib[t3]] + static_cast<uint64_t>(k) * b_step,
+                                   idesc, ((kb - kb0) | k | t3) != 0 ? 1u : 0u);
+                  umma_commit(&empty_bar[stage]);
+                  if (++stage == kStages3) {
+                    stage = 0;
+                    phase ^= 1u;
+                  }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) {
+                  acc = 0;
+                  acc_phase ^= 1u;
+                }
+              }
+          }
+        }
+      }
+      if (!x3)
       for (int w = blockIdx.x; w < p.num_works; w += gridDim.x) {
         const int m_tile = w / p.n_groups;
         const int grp = w - m_tile * p.n_groups;
@@ -954,6 +1053,15 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   const bool stg = p.use_stg && d->act == BLM_ACT_NONE;
   if (chunked) {
     p.chunk_kb = d->k_chunk / kBK;
+    // precise-mode triples (A.hi, B.lo), (A.lo, B.hi), (A.hi, B.hi) over one K range: load the four distinct tiles once
+    // per K block and issue the three products from them (BLM_GEMM_NO_X3=1 is the A/B switch)
+    static const bool no_x3 = getenv("BLM_GEMM_NO_X3") != nullptr;
+    bool triples = !no_x3 && d->nseg % 3 == 0;
+    for (int s = 0; triples && s < d->nseg; s += 3)
+      triples = d->A[s] == d->A[s + 2] && d->B[s + 1] == d->B[s + 2] && d->A[s] != d->A[s + 1] && d->K[s] == d->K[s + 1] &&
+                d->K[s] == d->K[s + 2] && d->lda[s] == d->lda[s + 1] && d->lda[s] == d->lda[s + 2] &&
+                d->ldb[s] == d->ldb[s + 1] && d->ldb[s] == d->ldb[s + 2];
+    p.x3 = triples ? 1 : 0;
     if (stg) return launch_stg<128, kStages128, 1>(p, st);
     if (gstg) return launch_stg<128, kStages128, 1, BLM_ACT_GELU_GRAD>(p, st);
     switch (d->act) {

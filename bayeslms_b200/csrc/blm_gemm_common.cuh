@@ -39,6 +39,8 @@ struct GemmParams {
   int a_mn, b_mn;       // 1: the operand is MN-major: A[s] is [K_s, M] / B[s] is [K_s, N] row-major (wgrad / dgrad
                         // straight from the activations / weights, no transposed copies); boxes of 64 x 64
   int fast_act;         // 1: packed-fp16 evaluation of the activation derivative (GELU_GRAD on the transposed path)
+  int x3;               // chunked kernels: segments come in (A.hi, B.lo), (A.lo, B.hi), (A.hi, B.hi) triples of one K range;
+                        // each ring stage then carries the FOUR distinct tiles once and feeds all three products
   int a_f16;            // 1: A operands are fp16 (instruction descriptor A format F16, B stays BF16)
   int use_stg;          // 1: transpose finished chunks through shared memory for row-coalesced stores
   int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk
