@@ -937,6 +937,12 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   // extra shared-memory round trip costs more issue slots than the wider stores save (FFN1 479 -> 536 us)
   static const char* stg_env = getenv("BLM_STG");  // A/B switch for profiling: 0 = never, 1 = always
   p.use_stg = stg_env ? atoi(stg_env) : (d->out_f32 != nullptr);
+  p.f32_rows32 = d->f32_rows32;
+  if (d->f32_rows32) {
+    BLM_REQUIRE(d->out_f32 && !d->out_pre && d->ldc == d->N && (d->N % 4) == 0, BLM_ERR_ARG,
+                "f32_rows32 needs out_f32 with ldc == N, N %% 4 == 0 and no out_pre");
+    p.use_stg = 0;   // one row per thread IS the coalesced store of this layout
+  }
   p.out_pre = d->out_pre;
   p.aux = d->aux;
   p.ldaux = d->ldaux;

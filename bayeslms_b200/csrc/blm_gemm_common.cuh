@@ -43,6 +43,9 @@ struct GemmParams {
                         // each ring stage then carries the FOUR distinct tiles once and feeds all three products
   int a_f16;            // 1: A operands are fp16 (instruction descriptor A format F16, B stays BF16)
   int use_stg;          // 1: transpose finished chunks through shared memory for row-coalesced stores
+  int f32_rows32;       // 1: out_f32 is stored in 32-row blocks (blm_gemm_desc.f32_rows32): row-per-thread stores are
+                        // then 512 contiguous bytes per warp instruction, and so are the loads of a consumer that
+                        // owns one row per thread (the LSTM gate math on tensor-memory lanes)
   int chunk_kb;         // CHUNK kernels: K blocks per TMEM accumulation chunk
   float* out_pre;       // fp32 copy of the value BEFORE the activation (training: saved pre-activation)
   const float* aux;     // [M, N] fp32, leading dimension ldaux: the pre-activation the *_GRAD epilogues differentiate at
@@ -315,6 +318,12 @@ __device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], i
 
 // ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
 
+// Element offset of (row m, column col) of the fp32 output.  rows32 layout: [ceil(M / 32)][N / 4][32 rows][4 floats].
+__device__ __forceinline__ long long f32_off(const GemmParams& p, int m, int col) {
+  if (!p.f32_rows32) return static_cast<long long>(m) * p.ldc + col;
+  return ((static_cast<long long>(m >> 5) * (p.ldc >> 2) + (col >> 2)) * 32 + (m & 31)) * 4 + (col & 3);
+}
+
 // bias / q-scale / activation / residual / (hi, lo) split / stores for one 32-column chunk.
 // Called by all 32 lanes of an epilogue warp; thread `lane` holds row m = m0 + lane (row_ok = m < M).
 //   sb : this chunk's 32 bias values staged in shared memory (null: read p.bias from global)
@@ -448,7 +457,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
           }
           if (mr < p.M) {
             const long long off = static_cast<long long>(mr) * p.ldc + col;
-            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = x;
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + f32_off(p, mr, col)) = x;
             if (p.out_hi) {
               const uint32_t h0 = pack_bf16x2(x.x, x.y), h1 = pack_bf16x2(x.z, x.w);
               *reinterpret_cast<uint2*>(p.out_hi + off) = make_uint2(h0, h1);
@@ -479,10 +488,11 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
     }
     const long long off = static_cast<long long>(m) * p.ldc + col0;
     if (p.out_f32) {
-      float* o = p.out_f32 + off;
+      float* o = p.out_f32 + f32_off(p, m, col0);
+      const int step = p.f32_rows32 ? 128 : 4;   // consecutive float4 columns of a row are 32 rows apart in rows32
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        *reinterpret_cast<float4*>(o + (j >> 2) * step) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     if (p.out_hi) {
       __nv_bfloat16* oh = p.out_hi + off;
@@ -528,7 +538,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
         z = apply_act<ACT>(z, p.coef, p.N, col);
       }
       if (p.resid) z += __ldg(p.resid + static_cast<long long>(m) * p.ldr + col);
-      if (p.out_f32) p.out_f32[off + j] = z;
+      if (p.out_f32) p.out_f32[f32_off(p, m, col)] = z;
       if (p.out_hi) {
         const __nv_bfloat16 hh = __float2bfloat16_rn(z);
         p.out_hi[off + j] = hh;

@@ -607,10 +607,12 @@ def _lstm_forward(model, plan: _Plan, weights, tokens_tb: torch.Tensor, lengths:
             out32, x, hT, cT = _gp_lstm_layer(plan, W, x, h0[li], c0[li], lengths, T, B, H, last and want_f32,
                                               (not last) or want_split)
         else:
-            gates = torch.empty(T * B, 4 * H, dtype=torch.float32, device=plan.device)
-            ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+            # the hoisted input projection is written in 32-row blocks: the recurrence reads it one row per thread
+            gates = ops.rows32_empty(T * B, 4 * H, plan.device)
+            ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}", f32_rows32=True)
             out32, x, hT, cT = ops.lstm_layer(gates, W["w_hh"], h0[li], c0[li], lengths, T, B, H, prec=prec,
-                                              want_f32=last and want_f32, want_split=(not last) or want_split)
+                                              want_f32=last and want_f32, want_split=(not last) or want_split,
+                                              gx_rows32=True)
         hs.append(hT)
         cs.append(cT)
     return out32, x, torch.stack(hs), torch.stack(cs)
@@ -624,11 +626,11 @@ def _lstm_chain(model, plan: _Plan, weights, tokens_ts: torch.Tensor, lengths: t
     zero = torch.zeros(S, H, dtype=torch.float32, device=dev)
     hs, cs = [], []
     for li, W in enumerate(weights):
-        gates = torch.empty(T * S, 4 * H, dtype=torch.float32, device=dev)
-        ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}")
+        gates = ops.rows32_empty(T * S, 4 * H, dev)
+        ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}", f32_rows32=True)
         c_seq = torch.empty(T * S, H, dtype=torch.float32, device=dev)
         h_seq, x, _, _ = ops.lstm_layer(gates, W["w_hh"], zero, zero, lengths, T, S, H, prec=prec, want_f32=True,
-                                        want_split=li + 1 < len(weights), c_seq=c_seq)
+                                        want_split=li + 1 < len(weights), c_seq=c_seq, gx_rows32=True)
         hs.append(h_seq)
         cs.append(c_seq)
     return hs, cs

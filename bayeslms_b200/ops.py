@@ -123,14 +123,16 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
          out: Optional[Split] = None, extra: Sequence = (), tag: str = "", out_pre: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
          targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None,
-         a_f16: bool = False, a_mn: bool = False, b_mn: bool = False, fast_act: bool = False):
+         a_f16: bool = False, a_mn: bool = False, b_mn: bool = False, fast_act: bool = False,
+         f32_rows32: bool = False):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
     accumulated into the same output (K-concatenation).  ``out_pre`` receives the fp32 value before
     the activation; ``aux`` is the saved pre-activation of the ``*_GRAD`` epilogues; ``lse`` /
     ``targets`` / ``grad_scale`` feed ``ACT_SOFTMAX_GRAD``.  ``k_chunk`` (default: 128 in bf16x3 mode)
     bounds the length of one tensor-core accumulation (see ``blm_gemm_desc.k_chunk``).
     ``a_mn`` / ``b_mn``: the operand is given MN-major, a as [K, M] / b as [K, N] (e.g. ``dW = gemm(dY, X, a_mn=True,
-    b_mn=True)`` with dY [tokens, N], X [tokens, K]; ``dX = gemm(dY, W, b_mn=True)`` with W [N, K])."""
+    b_mn=True)`` with dY [tokens, N], X [tokens, K]; ``dX = gemm(dY, W, b_mn=True)`` with W [N, K]).
+    ``f32_rows32``: ``out_f32`` (``rows32_empty(M, N)``) is written in 32-row blocks (``blm_gemm_desc.f32_rows32``)."""
     segs = _segments(a, b, prec)
     for (a2, b2) in extra:
         segs += _segments(a2, b2, prec)
@@ -170,8 +172,27 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
         d.lse, d.targets, d.grad_scale = _ptr(lse), _ptr(targets), grad_scale
     d.k_chunk = (PRECISE_K_CHUNK if prec == "bf16x3" else 0) if k_chunk is None else k_chunk
     d.a_f16, d.a_mn, d.b_mn, d.fast_act = int(a_f16), int(a_mn), int(b_mn), int(fast_act)
+    if f32_rows32:
+        assert out_f32 is not None and out_f32.is_contiguous() and out_f32.shape == (_pad32(M), N)
+        d.f32_rows32 = 1
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[0 if a_mn else 1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
+
+
+def _pad32(n: int) -> int:
+    return (n + 31) // 32 * 32
+
+
+def rows32_empty(M: int, N: int, device) -> torch.Tensor:
+    """fp32 buffer of a [M, N] matrix in the 32-row-block layout [ceil(M / 32)][N / 4][32 rows][4 floats]."""
+    assert N % 4 == 0
+    return torch.empty(_pad32(M), N, dtype=torch.float32, device=device)
+
+
+def rows32_to_dense(x: torch.Tensor, M: int) -> torch.Tensor:
+    """The [M, N] row-major matrix held by a 32-row-block buffer (tests, debugging)."""
+    N = x.shape[1]
+    return x.view(-1, N // 4, 32, 4).permute(0, 2, 1, 3).reshape(-1, N)[:M]
 
 
 GEMM_LN_WIDTHS = (128, 256, 384, 512)   # d_model values the LayerNorm-fused GEMM covers (blm_gemm_ln)
@@ -490,11 +511,13 @@ def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_
 
 def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.Tensor, lengths: torch.Tensor,
                T: int, B: int, H: int, *, prec: str = "bf16", want_f32: bool = False, want_split: bool = True,
-               c_seq: Optional[torch.Tensor] = None):
+               c_seq: Optional[torch.Tensor] = None, gx_rows32: bool = False):
     """One LSTM layer over [T, B] lock-stepped rows.  Returns (out_f32 or None, out Split or None, hT, cT).
-    ``c_seq`` [T * B, H] fp32 (optional) receives the cell state after every live step."""
+    ``c_seq`` [T * B, H] fp32 (optional) receives the cell state after every live step.  ``gx_rows32``: ``gates_x``
+    is a ``rows32_empty(T * B, 4 * H)`` buffer filled by ``gemm(..., f32_rows32=True)``."""
     dev = gates_x.device
-    assert gates_x.is_contiguous() and gates_x.numel() == T * B * 4 * H and lengths.dtype == torch.int32
+    assert gates_x.is_contiguous() and lengths.dtype == torch.int32
+    assert gates_x.numel() == (_pad32(T * B) if gx_rows32 else T * B) * 4 * H
     h0, c0 = h0.contiguous(), c0.contiguous()
     out32 = torch.empty(T * B, H, dtype=torch.float32, device=dev) if want_f32 else None
     outs = empty_split(T * B, H, prec, dev) if want_split else None
@@ -506,7 +529,7 @@ def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.T
         assert c_seq.dtype == torch.float32 and c_seq.is_contiguous() and c_seq.numel() == T * B * H
     # algorithmic bytes per step = W_hh once (4H x H bf16) + gates_x read (B x 4H fp32) + h, c write
     with _op("lstm_layer", 1, 2.0 * T * B * 4 * H * H, T * (4.0 * H * H * 2 + B * 4.0 * H * 4 + 2.0 * B * H * 4)):
-        check(lib().blm_lstm_layer_seq(_ptr(gates_x), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
+        check(lib().blm_lstm_layer_seq(_ptr(gates_x), int(gx_rows32), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
                                        _ptr(c0), _ptr(lengths), T, B, H, _ptr(out32),
                                        _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),
                                        _ptr(hT), _ptr(cT), _ptr(c_seq), _ptr(ws), _stream()), "blm_lstm_layer")

@@ -134,6 +134,10 @@ typedef struct blm_gemm_desc {
                           and X [tokens, K] as they are (a_mn = b_mn = 1), input gradients dX = dY W take W [N, K]
                           as it is (b_mn = 1): no transposed copies (tcgen05 MN-major shared-memory descriptors)  */
   int32_t fast_act;    /* 1: BLM_ACT_GELU_GRAD evaluates gelu' in packed fp16 (fast mode, <= 1e-3 absolute)            */
+  int32_t f32_rows32;  /* 1: out_f32 is laid out in 32-row blocks, [ceil(M/32)][N/4][32 rows][4 floats] (buffer of
+                          ceil(M/32)*32*N floats; ldc == N, N % 4 == 0; no out_pre).  A consumer that owns one row per
+                          thread -- the LSTM gate math, gx_rows32 of blm_lstm_layer_seq -- then reads 512 contiguous
+                          bytes per warp instruction instead of 32 separate rows.                                     */
 } blm_gemm_desc;
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
@@ -349,8 +353,10 @@ int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16
                    float* cT, void* workspace, blm_stream stream);
 /* The same launch that also records the cell state after every live step (c_seq [T, B, H] fp32; out_f32 holds h):
  * one launch can then carry a whole chain of utterances -- hypothesis #0 of utterance after utterance, the hidden
- * carry of score.py:261-274 -- and the state at every utterance boundary is read back from (out_f32, c_seq).   */
-int blm_lstm_layer_seq(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo,
+ * carry of score.py:261-274 -- and the state at every utterance boundary is read back from (out_f32, c_seq).
+ * gx_rows32 != 0: gates_x was written by blm_gemm with f32_rows32 = 1 over M = T * B rows (32-row blocks), which
+ * makes the gate math's one-row-per-thread reads contiguous; 0: row-major [T, B, 4H].                          */
+int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo,
                        const float* h0, const float* c0, const int32_t* lengths, int64_t T, int64_t B,
                        int64_t H, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo, float* hT,
                        float* cT, float* c_seq, void* workspace, blm_stream stream);

@@ -554,3 +554,78 @@ def test_attention_dropout_forward_and_backward(ops, lens, prec, tol_f, tol_b):
     # and it really drops something
     plain, _ = ops.mha_causal_bf16(qs, offs, nhead, max(lens), prec=prec, want_f32=True)
     assert (plain - a1).abs().max() > 1e-2
+
+
+def _lstm_layer_ref(gx, w, h0, c0, lengths):
+    """fp64 recurrence on the bf16-rounded W_hh; h is re-rounded to bf16 as the operand of the next step (the kernel's
+    bf16 mode), state kept in full precision."""
+    T, B, H4 = gx.shape
+    w = w.to(torch.bfloat16).double()
+    h, c = h0.double().clone(), c0.double().clone()
+    outs = torch.zeros(T, B, H4 // 4, dtype=torch.float64, device=gx.device)
+    for t in range(T):
+        a = gx[t].double() + h.to(torch.bfloat16).double() @ w.t()
+        i, f, g, o = a.chunk(4, dim=1)
+        cn = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        hn = torch.sigmoid(o) * torch.tanh(cn)
+        live = (t < lengths).view(-1, 1)
+        c, h = torch.where(live, cn, c), torch.where(live, hn, h)
+        outs[t] = torch.where(live, hn, torch.zeros_like(hn))
+    return outs, h, c
+
+
+@pytest.mark.parametrize("T,B,H", [(5, 384, 64), (7, 700, 128), (4, 1500, 256), (3, 2048, 1024), (6, 1024, 1024)])
+def test_lstm_pair_kernel_matches_the_single_cta_kernel(ops, monkeypatch, T, B, H):
+    """lstm_pair_kernel (cta_group::2, the default from three 128-row tiles up) against lstm_layer_kernel
+    (BLM_LSTM_NO_PAIR=1) on the same inputs -- same K order, same fp32 accumulation: bit-identical -- and both against
+    the fp64 recurrence.  Ragged batches (B not a multiple of 256), rows of every length incl. 0."""
+    g = torch.Generator(device=DEV).manual_seed(T * 1000 + B + H)
+    gx = torch.randn(T, B, 4 * H, device=DEV, generator=g)
+    w = torch.randn(4 * H, H, device=DEV, generator=g) / H ** 0.5
+    h0 = torch.randn(B, H, device=DEV, generator=g) * 0.5
+    c0 = torch.randn(B, H, device=DEV, generator=g) * 0.5
+    lengths = torch.randint(0, T + 1, (B,), device=DEV, generator=g).to(torch.int32)
+    lengths[:3] = T
+    ws = ops.split(w, "bf16")
+
+    def run(rows32=False):
+        cs = torch.zeros(T * B, H, device=DEV)
+        g2 = gx.view(T * B, 4 * H)
+        if rows32:      # the 32-row-block layout of blm_gemm_desc.f32_rows32
+            pad = ops.rows32_empty(T * B, 4 * H, DEV).zero_()
+            pad[:T * B] = g2
+            g2 = pad.view(-1, 32, H, 4).permute(0, 2, 1, 3).contiguous().view(-1, 4 * H)
+            assert torch.equal(ops.rows32_to_dense(g2, T * B), gx.view(T * B, 4 * H))
+        o32, o, hT, cT = ops.lstm_layer(g2, ws, h0, c0, lengths, T, B, H, prec="bf16", want_f32=True, c_seq=cs,
+                                        gx_rows32=rows32)
+        torch.cuda.synchronize()
+        return o32.clone(), o.hi.clone(), hT.clone(), cT.clone(), cs
+
+    pair = run()
+    pair32 = run(rows32=True)
+    monkeypatch.setenv("BLM_LSTM_NO_PAIR", "1")
+    single = run()
+    single32 = run(rows32=True)
+    for other in (pair32, single, single32):
+        for a, b in zip(pair, other):
+            assert torch.equal(a, b)
+    ro, rh, rc = _lstm_layer_ref(gx, w, h0, c0, lengths)
+    _close(pair[0].view(T, B, H), ro, 2e-3)
+    _close(pair[2], rh, 2e-3)
+    _close(pair[3], rc, 2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,prec", [(300, 512, 200, "bf16"), (4096, 4096, 1024, "bf16"), (1000, 1024, 256, "bf16x3"),
+                                        (77, 64, 64, "bf16x3"), (33, 40, 64, "bf16")])
+def test_gemm_fp32_output_in_32_row_blocks(ops, M, N, K, prec):
+    """blm_gemm_desc.f32_rows32: the same values as the row-major output, bit for bit, in [M/32][N/4][32][4] order
+    (ragged M, N not a multiple of 32)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = ops.split(torch.randn(M, K, device=DEV, generator=g), prec)
+    b = ops.split(torch.randn(N, K, device=DEV, generator=g), prec)
+    bias = torch.randn(N, device=DEV, generator=g)
+    dense = torch.empty(M, N, device=DEV)
+    ops.gemm(a, b, prec=prec, bias=bias, out_f32=dense)
+    blocked = ops.rows32_empty(M, N, DEV)
+    ops.gemm(a, b, prec=prec, bias=bias, out_f32=blocked, f32_rows32=True)
+    assert torch.equal(ops.rows32_to_dense(blocked, M), dense)
