@@ -204,7 +204,8 @@ def bench_lstm(dev, world=1, rank=0, steps=1):
             tot = sum(sum(a.elapsed_time(b) for a, b, _ in v) for v in timing.values()) or 1.0
             if ms_k:
                 out["recurrence_roofline"] = {
-                    "kernel": "lstm_layer_kernel<16,1,2> (persistent recurrence, W_hh resident in shared memory)",
+                    "kernel": "lstm_pair_kernel<2> (persistent recurrence of cta_group::2 pairs, W_hh resident in shared memory; "
+                              "the 12-row hypothesis-#0 chains run lstm_layer_kernel<16,1,2>)",
                     "bound": "hbm", "achieved": byts / (ms_k / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": byts / (ms_k / 1e3) / 1e9 / pk["hbm"], "launches": len(ev), "share_of_kernel_time": ms_k / tot,
                     "tensor_tflops": flop / (ms_k / 1e3) / 1e12,
@@ -213,6 +214,7 @@ def bench_lstm(dev, world=1, rank=0, steps=1):
                     "traffic": 294e6 / 8, "traffic_unit": "DRAM bytes per step at B=2048 (ncu)",
                     "note": "effective bandwidth on the algorithmic bytes of SURVEY.md 8d (W_hh 8 MiB counted once per step "
                             "+ gates_x + h, c); it may exceed what DRAM delivers because W_hh stays in shared memory"}
+            out["kernel_ms_total"] = round(tot / steps, 2)
             out["kernel_time_shares"] = {k: round(sum(a.elapsed_time(b) for a, b, _ in v) / tot, 4)
                                          for k, v in sorted(timing.items(), key=lambda kv: -sum(a.elapsed_time(b) for a, b, _ in kv[1]))[:6]}
     out["workload"] = (f"Bayesian LSTM 2x1024 L_bayes_pos=3 V30000, {nbest}-best, {n_sess} sessions x {per_sess} utterances "
