@@ -827,10 +827,13 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeCooperative;  // the per-step grid barrier needs every CTA resident
+    attr[1].id = cudaLaunchAttributeCooperative;  // the tile flags need every CTA resident
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 2;
+    // Nsight Compute cannot replay a launch that is both clustered and cooperative (LaunchFailed).  For a capture only,
+    // BLM_LSTM_NO_COOP=1 drops the cooperative attribute; residency then rests on the grid (<= 148 CTAs, one per SM)
+    // being alone on the device, which a profiling run is.
+    cfg.numAttrs = getenv("BLM_LSTM_NO_COOP") ? 1 : 2;
     if (sub == 2)
       BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<2>, p));
     else

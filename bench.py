@@ -209,9 +209,9 @@ def bench_lstm(dev, world=1, rank=0, steps=1):
                     "bound": "hbm", "achieved": byts / (ms_k / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": byts / (ms_k / 1e3) / 1e9 / pk["hbm"], "launches": len(ev), "share_of_kernel_time": ms_k / tot,
                     "tensor_tflops": flop / (ms_k / 1e3) / 1e12,
-                    # ncu --set full of one launch at B = 2048 (profiles/r01aw_sampled_gemm_kl_ncu_full.txt): DRAM bytes per
-                    # 8 steps = the gates_x read; W_hh is never re-read
-                    "traffic": 294e6 / 8, "traffic_unit": "DRAM bytes per step at B=2048 (ncu)",
+                    # ncu --set full of one 40-step launch at B = 2048 (profiles/r02d_lstm_pair_vs_single_ncu.txt): DRAM
+                    # read 1371 MB (= gates_x, once) + write 241 MB; W_hh is never re-read
+                    "traffic": (1371.2e6 + 240.8e6) / 40, "traffic_unit": "DRAM bytes per step at B=2048 (ncu, read + write)",
                     "note": "effective bandwidth on the algorithmic bytes of SURVEY.md 8d (W_hh 8 MiB counted once per step "
                             "+ gates_x + h, c); it may exceed what DRAM delivers because W_hh stays in shared memory"}
             out["kernel_ms_total"] = round(tot / steps, 2)
