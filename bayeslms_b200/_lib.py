@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
         ("lse", C.c_void_p), ("targets", C.c_void_p), ("grad_scale", C.c_float), ("k_chunk", C.c_int32),
         ("out_pre", C.c_void_p), ("aux", C.c_void_p), ("ldaux", C.c_int64),
-        ("a_f16", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("fast_act", C.c_int32), ("f32_rows32", C.c_int32),
+        ("a_f16", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("fast_act", C.c_int32), ("f32_rows32", C.c_int32), ("drop", C.c_void_p),
     ]
 
 

@@ -292,6 +292,15 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
   T = min(T - q0, 128);                                               // query rows of this block (= T when T <= 128)
   const int d = nhead * kMmaAttnHd;
   const int pb = (warp / WPP) * KV_ROWS;  // first shared-memory row of this pair
+  // one pair per CTA (KV_ROWS == 128, T <= 128 when dropping): its keep bits are generated once into shared memory
+  __shared__ uint32_t s_keep[(DROP && KV_ROWS == 128) ? 512 : 1];
+  __shared__ unsigned s_kept;
+  float kscale = 0.0f;
+  if constexpr (DROP && KV_ROWS == 128) {
+    const DropParams dr = drop_resolve(dparams);
+    drop_keep_bits(dr, pair * ldm * ldm, ldm * ldm, s_keep, &s_kept, threadIdx.x, 128);
+    kscale = dr.mask ? __uint_as_float(s_kept) : dr.scale;
+  }
   // ---- staging: rows [32 qt, 32 qt + 32) of matrices [m0, m1) (0 = q, 1 = k, 2 = v) of this pair, taken from tokens
   // tok0.. of the hypothesis, zero fill past `valid` rows.  Lane l copies 16-byte chunk l % 8 of rows l / 8 + 4 it: one
   // pointer and one swizzled offset per (matrix, part), advanced by constants (the address arithmetic of the first
@@ -448,7 +457,11 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
               const int i = qt * 32 + mt * 16 + g + 8 * h;
               const int j0 = kb * 32 + nt * 8 + 2 * t4;
               if (nt < nnt && i < T && j0 + joff <= i) {   // (elements with j > i are already zero)
-                const float2 dm = drop_mult2(dr, mbase + static_cast<long long>(q0 + i) * ldm + c * 128 + j0);
+                float2 dm;
+                if constexpr (KV_ROWS == 128)
+                  dm = keep_mult2(s_keep, kscale, (q0 + i) * ldm + c * 128 + j0);
+                else
+                  dm = drop_mult2(dr, mbase + static_cast<long long>(q0 + i) * ldm + c * 128 + j0);
                 s[mt][nt][2 * h] *= dm.x;
                 s[mt][nt][2 * h + 1] *= dm.y;
               }
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(128) mha_causal_mma_kernel(
 // DROP (attention-probability dropout, P' = m . P): dV = P'^T dO, dP = m . (dO V^T), D_i = sum_j P_ij dP_ij,
 // dS = P (dP - D): the multipliers are re-derived from the same mask tensor / Philox stream as in the forward kernel.
 template <bool PRECISE, int MT, bool DROP = false>
-__global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE && !DROP) ? 2 : 1) mha_causal_bwd_mma_kernel(
+__global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE) ? 2 : 1) mha_causal_bwd_mma_kernel(
     const float* __restrict__ qkv, long long ld, const float* __restrict__ dout, long long ldo,
     const int* __restrict__ seq_offsets, int nhead, float q_scale, float* __restrict__ dqkv, long long ldd,
     DropParams dparams = DropParams{}, int ldm = 0) {
@@ -691,8 +704,15 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE && 
     }
   };
 
-  const DropParams dr = DROP ? drop_resolve(dparams) : dparams;
-  const long long mbase = static_cast<long long>(blockIdx.x) * ldm * ldm;
+  // keep bits of this (sequence, head) pair's [ldm x ldm] multipliers, generated once
+  __shared__ uint32_t s_keep[DROP ? 512 : 1];
+  __shared__ unsigned s_kept;
+  float kscale = 0.0f;
+  if constexpr (DROP) {
+    const DropParams dr = drop_resolve(dparams);
+    drop_keep_bits(dr, static_cast<long long>(blockIdx.x) * ldm * ldm, ldm * ldm, s_keep, &s_kept, threadIdx.x, NT);
+    kscale = dr.mask ? __uint_as_float(s_kept) : dr.scale;
+  }
   // dP' -> dP = m . dP' on an accumulator block whose rows are queries r0.. and columns keys c0..
   auto drop_rows = [&](float (&x)[MT][4][4], int r0, int c0, int nmt_, int nnt_) {
 #pragma unroll
@@ -704,7 +724,7 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE && 
           const int i = r0 + mt * 16 + g + 8 * h;
           const int j0 = c0 + nt * 8 + 2 * t4;
           if (mt < nmt_ && nt < nnt_ && i < T && j0 <= i) {
-            const float2 dm = drop_mult2(dr, mbase + static_cast<long long>(i) * ldm + j0);
+            const float2 dm = keep_mult2(s_keep, kscale, i * ldm + j0);
             x[mt][nt][2 * h] *= dm.x;
             x[mt][nt][2 * h + 1] *= dm.y;
           }
@@ -872,7 +892,7 @@ __global__ void __launch_bounds__(128 / (16 * MT) * 32, (MT == 1 && !PRECISE && 
             const bool ok = j <= i && i < T && nt < nnt && mt < nmt;
             const float pv = ok ? ex2f_(fmaf(st[mt][nt][e], kLog2e, -cm[e & 1])) * cl[e & 1] : 0.0f;
             float dm = 1.0f;
-            if constexpr (DROP) dm = ok ? drop_mult1(dr, mbase + static_cast<long long>(i) * ldm + j) : 0.0f;
+            if constexpr (DROP) dm = ok ? keep_mult1(s_keep, kscale, i * ldm + j) : 0.0f;
             st[mt][nt][e] = pv * dm;                                           // P'^T = (m . P)^T
             dpt[mt][nt][e] = ok ? pv * (dm * dpt[mt][nt][e] - cd[e & 1]) : 0.0f;   // dS^T
           }

@@ -938,6 +938,14 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   static const char* stg_env = getenv("BLM_STG");  // A/B switch for profiling: 0 = never, 1 = always
   p.use_stg = stg_env ? atoi(stg_env) : (d->out_f32 != nullptr);
   p.f32_rows32 = d->f32_rows32;
+  if (d->drop && (d->drop->mask || d->drop->p > 0.0f)) {
+    BLM_REQUIRE((d->N % 32) == 0 && d->act != BLM_ACT_SOFTMAX_GRAD && !d->f32_rows32, BLM_ERR_ARG,
+                "fused dropout needs N %% 32 == 0 (N = %lld) and a storing epilogue other than the softmax gradient",
+                (long long)d->N);
+    BLM_REQUIRE(d->drop->p >= 0.0f && d->drop->p < 1.0f, BLM_ERR_ARG, "dropout p = %f", (double)d->drop->p);
+    p.drop_on = 1;
+    p.drop = make_drop_params(d->drop->mask, d->drop->p, d->drop->seed, d->drop->seed_dev, d->drop->stream_id);
+  }
   if (d->f32_rows32) {
     BLM_REQUIRE(d->out_f32 && !d->out_pre && d->ldc == d->N && (d->N % 4) == 0, BLM_ERR_ARG,
                 "f32_rows32 needs out_f32 with ldc == N, N %% 4 == 0 and no out_pre");
@@ -996,7 +1004,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
     const char* e = getenv("BLM_TMA_STORE");
     return e ? atoi(e) != 0 : true;
   }();
-  const bool tma_ok = tma_store_on && !chunked && d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && !d->resid;
+  const bool tma_ok = tma_store_on && !chunked && d->out_hi && !d->out_lo && !d->out_f32 && !d->out_pre && !d->resid && !p.drop_on;
   blm_gemm_desc downgraded;
   if (d->act == BLM_ACT_GPMIX_FAST && !tma_ok) {   // the packed variant only exists on the TMA-store path
     downgraded = *d;

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 
 #include "blm_host.h"
+#include "blm_philox.cuh"
 #include "blm_ptx.cuh"
 
 namespace blm {
@@ -73,6 +74,11 @@ struct GemmParams {
   int gen_K;
   __nv_bfloat16* gen_wt;
   unsigned int* gen_sync;          // [0] arrivals, [1] departures; zero between launches
+  // dropout fused into the storing epilogue (blm_gemm_desc.drop): the multiplier of element (m, col) is element
+  // m * N + col of the site's mask / Philox stream, applied to the activated value before the residual is added
+  // (forward) or to the incoming gradient before the activation derivative and out_pre (the *_GRAD epilogues)
+  int drop_on;
+  DropParams drop;
 };
 
 // ARES > 0: the A operand of a work item (ARES K blocks of 128 x 64) stays resident in shared
@@ -318,6 +324,34 @@ __device__ __forceinline__ void nll_chunk(const GemmParams& p, float (&v)[32], i
 
 // ---- epilogue building blocks: one accumulator row per thread, 32 columns per chunk ----------
 
+// Dropout multipliers of the 32 consecutive elements (m, col0 ..) of a dense [M, N] tensor, N % 32 == 0: eight Philox
+// counters (or eight float4 loads of an explicit mask).
+__device__ __forceinline__ void drop_chunk(const GemmParams& p, float (&v)[32], int m, int col0) {
+  const long long base = static_cast<long long>(m) * p.N + col0;
+  if (p.drop.mask) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 k = __ldg(reinterpret_cast<const float4*>(p.drop.mask + base + j));
+      v[j] *= k.x;
+      v[j + 1] *= k.y;
+      v[j + 2] *= k.z;
+      v[j + 3] *= k.w;
+    }
+    return;
+  }
+  const uint64_t seed = p.drop.seed + (p.drop.seed_dev ? __ldg(reinterpret_cast<const unsigned long long*>(p.drop.seed_dev)) : 0ull);
+  const uint32_t th = p.drop.thresh;
+  const float sc = p.drop.scale;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 w = philox_words4(seed, p.drop.stream, static_cast<uint64_t>(base >> 2) + q);
+    v[4 * q] *= w.x >= th ? sc : 0.0f;
+    v[4 * q + 1] *= w.y >= th ? sc : 0.0f;
+    v[4 * q + 2] *= w.z >= th ? sc : 0.0f;
+    v[4 * q + 3] *= w.w >= th ? sc : 0.0f;
+  }
+}
+
 // Element offset of (row m, column col) of the fp32 output.  rows32 layout: [ceil(M / 32)][N / 4][32 rows][4 floats].
 __device__ __forceinline__ long long f32_off(const GemmParams& p, int m, int col) {
   if (!p.f32_rows32) return static_cast<long long>(m) * p.ldc + col;
@@ -361,6 +395,10 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.col_scale_cols) v[j] *= p.col_scale;
     }
+    constexpr bool kGradAct = ACT == BLM_ACT_GELU_GRAD || ACT == BLM_ACT_GPMIX_GRAD;
+    if constexpr (kGradAct && STG != 2) {
+      if (p.drop_on && row_ok) drop_chunk(p, v, m, col0);   // h = mask . act(z): the mask multiplies dL/dh first
+    }
     if (p.out_pre && row_ok) {
       float* o = p.out_pre + static_cast<long long>(m) * p.ldc + col0;
 #pragma unroll
@@ -396,6 +434,9 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, float (&v)[32],
     } else if constexpr (ACT != BLM_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j], p.coef, p.N, col0 + j);
+    }
+    if constexpr (!kGradAct && ACT != BLM_ACT_SOFTMAX_GRAD && STG != 2) {   // (the TMA-store kernels are inference-only)
+      if (p.drop_on && row_ok) drop_chunk(p, v, m, col0);   // dropout(act(z)), then the residual
     }
     if constexpr (STG == 2) return;
     if constexpr (STG == 1) {

@@ -35,6 +35,7 @@ constexpr int kLABytes = 128 * 64 * 2;
 struct LstmParams {
   CUtensorMap tmH[2][2];  // [buffer][hi, lo] : h state [B, H] bf16, box 128 x 64 (box 32 x 64 in the cluster kernel)
   CUtensorMap tmW[2];     // [hi, lo]         : W_hh [4H, H] bf16, box U x 64
+  int a_box_bytes;        // bytes one h K block brings: box rows x 128 (a one-tile batch loads only its real rows)
   int kb_stagger;         // 1: stagger the K-block order per CTA (A/B switch BLM_LSTM_NO_STAGGER)
   int unit_blocks;        // H / U
   int tiles_per_cta;      // 128-row batch tiles per CTA (batch split)
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
             for (int kbi = 0; kbi < p.kblocks; kbi += kSub) {
               const int kb = (kbi + kb_rot) % p.kblocks;  // staggered K order (experiment, kSub == 1 only)
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              mbar_arrive_expect_tx(&full_bar[stage], kCL > 1 ? kStageBytes : kSub * p.a_box_bytes);
               if constexpr (kCL > 1) {
                 constexpr int kQ = 128 / kCL;  // rows of the tile this CTA fetches for the whole cluster
                 tma_load_2d_multicast(sA + stage * kStageBytes + crank * (kQ * 128), &p.tmH[cur][part], &full_bar[stage],
@@ -786,10 +787,16 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
   const int U = (!w_hh_lo && (H % 16) == 0 && !force_u8) ? 16 : 8;
   const int nb = (U == 16 && p.m_tiles >= 2 && 2 * (H / U) <= num_sms()) ? 2 : 1;
   const int CL = (U == 16 && !no_cluster && ((H / U) % 4) == 0 && p.m_tiles >= 2) ? 4 : 1;
+  // One-tile batches (the hypothesis-#0 chains: one row per session) load only their real rows: a 128-row box would
+  // move 256 KB per CTA and step for a dozen rows, and that stream, not the barrier, was the chain's step time.  The
+  // rows of the shared-memory tile the box does not cover keep whatever they held; they only feed accumulator rows
+  // >= B, which nobody reads.
+  const int box_rows = (p.m_tiles == 1 && getenv("BLM_LSTM_FULL_BOX") == nullptr) ? static_cast<int>((B + 7) / 8 * 8) : 128 / CL;
+  p.a_box_bytes = box_rows * 128;
   for (int buf = 0; buf < 2; ++buf)
     for (int part = 0; part < 2; ++part) {
       p.hbuf[buf][part] = hb + (static_cast<int64_t>(buf) * 2 + part) * B * H;
-      int rc = encode_tmap_bf16(&p.tmH[buf][part], p.hbuf[buf][part], B, H, H, 128 / CL);
+      int rc = encode_tmap_bf16(&p.tmH[buf][part], p.hbuf[buf][part], B, H, H, box_rows);
       if (rc != BLM_OK) return rc;
     }
   p.unit_blocks = static_cast<int>(H / U);

@@ -128,6 +128,52 @@ __device__ __forceinline__ float drop_mult1(const DropParams& d, long long idx) 
   return a >= d.thresh ? d.scale : 0.0f;
 }
 
+// Keep bits of elements [base, base + n) of a dropout site (base % 4 == 0, n % 4 == 0) into shared memory, one bit per
+// element, by all `nthreads` threads of the CTA (ends with __syncthreads).  With an explicit mask *kept receives the bits
+// of the multiplier of a kept element (every kept element of a mask carries the same value 1 / (1 - p)); with Philox the
+// multiplier is d.scale.  The attention kernels read their multipliers from these bits: regenerating Philox words inside
+// the MMA loops cost 60 registers and half the occupancy of the backward kernel (151 -> 351 us per step).
+__device__ __forceinline__ void drop_keep_bits(const DropParams& d, long long base, int n, uint32_t* bits, unsigned* kept,
+                                               int tid, int nthreads) {
+  if (d.mask) {
+    if (tid == 0) *kept = 0u;
+    __syncthreads();
+  }
+  unsigned vmax = 0u;
+  for (int w = tid; w * 32 < n; w += nthreads) {
+    uint32_t word = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = w * 32 + q * 4;
+      if (e < n) {
+        uint32_t b;
+        if (d.mask) {
+          const float2 m0 = __ldg(reinterpret_cast<const float2*>(d.mask + base + e));
+          const float2 m1 = __ldg(reinterpret_cast<const float2*>(d.mask + base + e + 2));
+          b = (m0.x != 0.0f ? 1u : 0u) | (m0.y != 0.0f ? 2u : 0u) | (m1.x != 0.0f ? 4u : 0u) | (m1.y != 0.0f ? 8u : 0u);
+          vmax = max(vmax, __float_as_uint(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m1.x, m1.y))));
+        } else {
+          const uint4 r = philox_words4(d.seed, d.stream, static_cast<uint64_t>(base + e) >> 2);
+          b = (r.x >= d.thresh ? 1u : 0u) | (r.y >= d.thresh ? 2u : 0u) | (r.z >= d.thresh ? 4u : 0u) |
+              (r.w >= d.thresh ? 8u : 0u);
+        }
+        word |= b << (q * 4);
+      }
+    }
+    bits[w] = word;
+  }
+  if (d.mask && vmax) atomicMax(kept, vmax);
+  __syncthreads();
+}
+// multipliers of elements idx, idx + 1 (idx even) / of element idx, relative to `base` above
+__device__ __forceinline__ float2 keep_mult2(const uint32_t* bits, float scale, int idx) {
+  const uint32_t b = bits[idx >> 5] >> (idx & 31);
+  return make_float2((b & 1u) ? scale : 0.0f, (b & 2u) ? scale : 0.0f);
+}
+__device__ __forceinline__ float keep_mult1(const uint32_t* bits, float scale, int idx) {
+  return ((bits[idx >> 5] >> (idx & 31)) & 1u) ? scale : 0.0f;
+}
+
 // w = mu + sigma * eps with sigma = exp(lgstd): one definition so the fused and the materialising
 // kernels round identically.
 __device__ __forceinline__ float reparam_value(float mu, float lgstd, float eps) {

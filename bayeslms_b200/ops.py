@@ -124,7 +124,7 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
          aux: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
          targets: Optional[torch.Tensor] = None, grad_scale: float = 1.0, k_chunk: Optional[int] = None,
          a_f16: bool = False, a_mn: bool = False, b_mn: bool = False, fast_act: bool = False,
-         f32_rows32: bool = False):
+         f32_rows32: bool = False, drop: Optional["Drop"] = None):
     """``epilogue(a @ b.T)`` with a [M, K], b [N, K].  ``extra`` appends more (A, B) Split pairs
     accumulated into the same output (K-concatenation).  ``out_pre`` receives the fp32 value before
     the activation; ``aux`` is the saved pre-activation of the ``*_GRAD`` epilogues; ``lse`` /
@@ -132,7 +132,9 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     bounds the length of one tensor-core accumulation (see ``blm_gemm_desc.k_chunk``).
     ``a_mn`` / ``b_mn``: the operand is given MN-major, a as [K, M] / b as [K, N] (e.g. ``dW = gemm(dY, X, a_mn=True,
     b_mn=True)`` with dY [tokens, N], X [tokens, K]; ``dX = gemm(dY, W, b_mn=True)`` with W [N, K]).
-    ``f32_rows32``: ``out_f32`` (``rows32_empty(M, N)``) is written in 32-row blocks (``blm_gemm_desc.f32_rows32``)."""
+    ``f32_rows32``: ``out_f32`` (``rows32_empty(M, N)``) is written in 32-row blocks (``blm_gemm_desc.f32_rows32``).
+    ``drop``: dropout fused into the epilogue (``blm_gemm_desc.drop``; N % 32 == 0): forward ``resid + m * act(.)``,
+    ``*_GRAD`` epilogues ``(m * acc) * act'(aux)`` with ``out_pre = m * acc``."""
     segs = _segments(a, b, prec)
     for (a2, b2) in extra:
         segs += _segments(a2, b2, prec)
@@ -175,6 +177,11 @@ def gemm(a: Split, b: Split, *, prec: str = "bf16", bias: Optional[torch.Tensor]
     if f32_rows32:
         assert out_f32 is not None and out_f32.is_contiguous() and out_f32.shape == (_pad32(M), N)
         d.f32_rows32 = 1
+    dd = None
+    if drop is not None:
+        assert N % 32 == 0 and (drop.mask is None or drop.mask.numel() == M * N)
+        dd = drop.desc()                 # stays alive until the call returns
+        d.drop = C.addressof(dd)
     with _op("gemm:" + tag if tag else "gemm", 1, 2.0 * M * N * sum(x.shape[0 if a_mn else 1] for x, _ in segs)):
         check(lib().blm_gemm(C.byref(d), _stream()), "blm_gemm")
 

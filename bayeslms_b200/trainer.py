@@ -97,6 +97,13 @@ V_NOISE_STD = engine.V_NOISE_STD
 _TID_VNOISE = engine.V_NOISE_TID   # Philox stream ids of the V-layer noise: 32 + layer index
 
 
+def _fusable(drop, n_cols: int):
+    """The dropout site as a GEMM-epilogue argument (``blm_gemm_desc.drop`` needs N % 32 == 0)."""
+    if drop is not None and n_cols % 32 != 0:
+        raise _lib.BlmError(f"dropout fused into the projection needs a width that is a multiple of 32, got {n_cols}")
+    return drop
+
+
 class FineTuner:
     """Owns the flat parameter / gradient / momentum buffers of ``model`` and runs training steps."""
 
@@ -396,12 +403,8 @@ class FineTuner:
             y1 = self._f32(M, d)
             wo, S["wo_t"] = self._w2(wo32)
             S["drop_d1"] = self._layer_site(layer, li, "d1", (T, B))              # dropout1, model.py:1039
-            if S["drop_d1"] is not None:
-                o32 = self._f32(M, d)
-                _gemm(atts, wo, prec=prec, bias=bo, out_f32=o32, tag="o_net")
-                ops.dropout(o32, S["drop_d1"], resid=x32, out_f32=y1)
-            else:
-                _gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net")
+            # x + dropout1(attention output) in the projection's epilogue
+            _gemm(atts, wo, prec=prec, bias=bo, resid=x32, out_f32=y1, tag="o_net", drop=_fusable(S["drop_d1"], d))
             x1_32, x1s = ops.layernorm(y1, layer.norm1.weight.detach(), layer.norm1.bias.detach(), layer.norm1.eps, prec=prec)
             S.update(qkv32=qkv32, atts=atts, y1=y1, x1_32=x1_32, x1s=x1s)
             # first FFN projection (+ GELU or the GP mixture), pre-activation kept
@@ -430,12 +433,9 @@ class FineTuner:
                 w1, S["w1_t"] = self._w2(w1_32)
                 act1, bias1, coef = ACT_GELU, layer.linear1.bias.detach(), None
             S["drop_ffn"] = self._layer_site(layer, li, "ffn", (T, B))            # dropout on the activation, model.py:1043
-            if S["drop_ffn"] is not None:
-                h32 = self._f32(M, F)
-                _gemm(x1s, w1, prec=prec, bias=bias1, act=act1, coef=coef, out_f32=h32, out_pre=z1, tag="ffn1")
-                _, hs = ops.dropout(h32, S["drop_ffn"], prec=prec, want_f32=False)
-            else:
-                _gemm(x1s, w1, prec=prec, bias=bias1, act=act1, coef=coef, out=hs, out_pre=z1, tag="ffn1")
+            # h = dropout(act(z1)) in the epilogue; z1 (saved for the backward pass) is the unmasked pre-activation
+            _gemm(x1s, w1, prec=prec, bias=bias1, act=act1, coef=coef, out=hs, out_pre=z1, tag="ffn1",
+                  drop=_fusable(S["drop_ffn"], F))
             S.update(z1=z1, hs=hs)
             # second FFN projection
             if kind == "bayes_ffn":
@@ -479,12 +479,7 @@ class FineTuner:
                 layer._v_state = {"f": f, "B": B, "T": T, "eps": e_bt, "seed": seed, "stream_id": S["v_stream"]}
             else:
                 S["drop_d2"] = self._layer_site(layer, li, "d2", (T, B))         # dropout2, model.py:1045
-                if S["drop_d2"] is not None:
-                    f2 = self._f32(M, d)
-                    _gemm(hs, w2, prec=prec, bias=b2, out_f32=f2, tag="ffn2")
-                    ops.dropout(f2, S["drop_d2"], resid=x1_32, out_f32=y2)
-                else:
-                    _gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2")
+                _gemm(hs, w2, prec=prec, bias=b2, resid=x1_32, out_f32=y2, tag="ffn2", drop=_fusable(S["drop_d2"], d))
             x32, xs = ops.layernorm(y2, layer.norm2.weight.detach(), layer.norm2.bias.detach(), layer.norm2.eps, prec=prec)
             S["y2"] = y2
             saved.append(S)
@@ -509,7 +504,13 @@ class FineTuner:
             dy2 = ops.layernorm_bwd(dx, S["y2"], layer.norm2.weight.detach(), layer.norm2.eps, g[pre + "norm2.weight"],
                                     g[pre + "norm2.bias"])
             # gradient of the FFN branch = dropout2's mask on dy2 (the residual branch keeps dy2 itself)
-            dbr = dy2 if S["drop_d2"] is None else ops.dropout(dy2, S["drop_d2"])[0]
+            dfs = None
+            if S["drop_d2"] is None:
+                dbr = dy2
+            elif kind == "v":
+                dbr = ops.dropout(dy2, S["drop_d2"])[0]
+            else:
+                dbr, dfs = ops.dropout(dy2, S["drop_d2"], prec=prec)      # masked gradient and its operand copy in one pass
             if kind == "v":
                 df, klpart = ops.vnoise_bwd(dbr, S["f"], layer.hiddens_lgstd.detach().view(T, d),
                                             layer.hiddens_mean_p.detach().view(T, d), B, T, kl_scale,
@@ -518,22 +519,19 @@ class FineTuner:
                 ops.reduce_sum(klpart.view(-1), kl, scale=0.5 / (M * d), accumulate=True)
             else:
                 df = dbr
-            dfs = ops.split(df, prec)
-            # FFN2: dgrad fused with the activation derivative, wgrad, bias
+            if dfs is None:
+                dfs = ops.split(df, prec)
+            # FFN2: dgrad fused with the activation derivative (and the mask of the FFN dropout), wgrad, bias
             dz1 = self._f32(M, S["z1"].shape[1])
             dz1s = ops.empty_split(M, S["z1"].shape[1], prec, dev)
             if kind == "gauss":
                 dh = torch.empty_like(dz1)
+                # h = m . act(z1): the mask multiplies dL/dh in the epilogue, before act'(z1) and before dh is stored
                 _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,
-                         out=dz1s, out_pre=dh, tag="dgrad:ffn2")
+                         out=dz1s, out_pre=dh, tag="dgrad:ffn2", drop=_fusable(S["drop_ffn"], dz1.shape[1]))
             else:
                 _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GELU_GRAD, aux=S["z1"], out_f32=dz1, out=dz1s,
-                      fast_act=(prec == "bf16"), tag="dgrad:ffn2")
-            if S["drop_ffn"] is not None:
-                # h = m . act(z1): the mask multiplies the gradient elementwise, before or after act'(z1)
-                dz1, dz1s = ops.dropout(dz1, S["drop_ffn"], prec=prec, out_f32=dz1)
-                if kind == "gauss":
-                    ops.dropout(dh, S["drop_ffn"], out_f32=dh)
+                      fast_act=(prec == "bf16"), tag="dgrad:ffn2", drop=_fusable(S["drop_ffn"], dz1.shape[1]))
             dft, ht = _tsplit(df, prec, dfs), _tbf16(S["hs"], prec)
             if kind == "bayes_ffn":
                 G = g[pre + "linear2.weight_mean"]

@@ -96,6 +96,8 @@ int blm_num_sms(void);
  */
 #define BLM_MAX_SEG 6
 
+struct blm_dropout_desc;
+
 typedef struct blm_gemm_desc {
   int64_t M, N;
   int32_t nseg;
@@ -138,6 +140,12 @@ typedef struct blm_gemm_desc {
                           ceil(M/32)*32*N floats; ldc == N, N % 4 == 0; no out_pre).  A consumer that owns one row per
                           thread -- the LSTM gate math, gx_rows32 of blm_lstm_layer_seq -- then reads 512 contiguous
                           bytes per warp instruction instead of 32 separate rows.                                     */
+  const struct blm_dropout_desc* drop;
+                       /* optional (null: none): dropout fused into the epilogue.  Element (m, col) takes multiplier
+                          m * N + col of the site (N % 32 == 0).  Forward epilogues: out = resid + mask . act(acc + bias),
+                          out_pre = the pre-activation, unmasked -- `x + dropout(sublayer(x))`, model.py:1039-1046 in one
+                          launch.  BLM_ACT_*_GRAD: out = (mask . acc) . act'(aux), out_pre = mask . acc -- the backward of
+                          `dropout(act(z))`.  Same multipliers as blm_dropout on the dense [M, N] tensor.               */
 } blm_gemm_desc;
 
 int blm_gemm(const blm_gemm_desc* d, blm_stream stream);
