@@ -223,6 +223,44 @@ def bench_lstm(dev, world=1, rank=0, steps=1):
     return out
 
 
+def cpu_finetune_tokens_per_s(n_seq=4, steps=2):
+    """BASELINE config 4 on the host cores: the oracle's restatement of one train.py step (forward in train mode with
+    seeded hidden noise, CE + KL, autograd backward, clip, SGD momentum) of the 5-layer Variational Transformer on
+    ``n_seq`` sequences of 100 tokens (the GPU step takes 32), torch CPU fp32 on all cores."""
+    from bayeslms_b200 import model as M
+    from oracle import bayeslm_oracle as O
+    torch.manual_seed(1111)
+    net = M.VTransformerModel(V, D, NHEAD, FF, NLAYERS, 0.0, True, "11")
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.Config(family="v_tm", v_pos=3, ntoken=V, ninp=D, nhead=NHEAD, nhid=FF, nlayers=NLAYERS)   # "11" = 3
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    T = 100
+    g = torch.Generator().manual_seed(3)
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and k != "pos_encoder.pe" else v)
+            for k, v in sd.items() if k != "decoder.weight"}
+    leaf["decoder.weight"] = leaf["encoder.weight"]
+    params = [v for k, v in leaf.items() if k != "decoder.weight" and torch.is_tensor(v) and v.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.9)
+    dt = []
+    for it in range(steps + 1):
+        x = torch.randint(0, V, (T, n_seq), generator=g)
+        y = torch.randint(0, V, (T, n_seq), generator=g)
+        eps = {f"layer{i}": torch.randn(T, n_seq, D, generator=g) * 0.1 for i in (0, 1)}
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = O.finetune_loss(leaf, x, y.view(-1), cfg, eps, 1e-3)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.25)
+        opt.step()
+        if it:                      # the first step warms the allocator and the thread pool
+            dt.append(time.perf_counter() - t0)
+    per = sum(dt) / len(dt)
+    return {"value": T * n_seq / per, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of {n_seq} x {T} tokens ({per:.2f} s per step), oracle port of the train.py step "
+                      "(train-mode forward, CE + KL, autograd backward, clip, SGD momentum), torch CPU fp32"}
+
+
 def cpu_lstm_tokens_per_s(n_utts=100, nbest=20, budget_s=20.0):
     """BASELINE config 1: Bayesian LSTM 2x1024 (emb 1024, L_bayes_pos=3), V=30000, 20-best lists of 100 utterances, the
     reference loop on the host cores (oracle port: one hypothesis at a time, batch 1, hidden carried through hypothesis
@@ -565,6 +603,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         lstm["cpu_baseline"] = cpu_lstm_tokens_per_s()          # BASELINE config 1: 20-best x 100 utterances on the host
+        finetune["cpu_baseline"] = cpu_finetune_tokens_per_s()  # BASELINE config 4: the train.py step on the host
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
         n_cpu = 40                                      # ~30 k tokens: 8-15 s on the box's host cores
         v_cpu, t_cpu, dt_cpu, cores = cpu_port_tokens_per_s(data, n_cpu, sd)
