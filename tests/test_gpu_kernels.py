@@ -629,3 +629,47 @@ def test_gemm_fp32_output_in_32_row_blocks(ops, M, N, K, prec):
     blocked = ops.rows32_empty(M, N, DEV)
     ops.gemm(a, b, prec=prec, bias=bias, out_f32=blocked, f32_rows32=True)
     assert torch.equal(ops.rows32_to_dense(blocked, M), dense)
+
+
+@pytest.mark.parametrize("M,N,K,prec", [(3200, 512, 512, "bf16"), (3200, 4096, 512, "bf16"), (300, 256, 200, "bf16x3"),
+                                        (1000, 512, 4096, "bf16x3")])
+def test_gemm_epilogue_dropout_equals_the_dropout_kernel(ops, M, N, K, prec):
+    """blm_gemm_desc.drop: element (m, col) takes multiplier m * N + col of the site.  Forward: out = resid + mask *
+    act(acc + bias), out_pre unmasked.  *_GRAD: out = (mask * acc) * act'(aux), out_pre = mask * acc.  Checked against
+    the unfused composition (same GEMM, then blm_dropout) for a Philox site incl. the device seed word, and for the
+    exported multipliers re-injected as an explicit mask."""
+    from bayeslms_b200.ops import ACT_GELU, ACT_GELU_GRAD, ACT_NONE
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = ops.split(torch.randn(M, K, device=DEV, generator=g) / K ** 0.5, prec)
+    b = ops.split(torch.randn(N, K, device=DEV, generator=g), prec)
+    bias = torch.randn(N, device=DEV, generator=g)
+    resid = torch.randn(M, N, device=DEV, generator=g)
+    aux = torch.randn(M, N, device=DEV, generator=g)
+    word = torch.tensor([5], dtype=torch.int64, device=DEV)
+    site = ops.Drop(0.2, seed=77, stream_id=(64 << 32) | 3, seed_dev=word)
+    mult, _ = ops.dropout(None, site, n=M * N, device=torch.device(DEV))
+    mult = mult.view(M, N)
+    for drop in (site, ops.Drop(0.2, mask=mult.contiguous())):
+        # forward, no activation: resid + mask * (acc + bias)
+        plain = torch.empty(M, N, device=DEV)
+        ops.gemm(a, b, prec=prec, bias=bias, out_f32=plain)
+        got = torch.empty(M, N, device=DEV)
+        ops.gemm(a, b, prec=prec, bias=bias, resid=resid, out_f32=got, drop=drop)
+        assert torch.equal(got, plain * mult + resid)
+        # forward, GELU: the saved pre-activation stays unmasked
+        h, pre = ops.empty_split(M, N, prec, DEV), torch.empty(M, N, device=DEV)
+        h0, pre0 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+        ops.gemm(a, b, prec=prec, bias=bias, act=ACT_GELU, out_f32=h0, out_pre=pre0)
+        ops.gemm(a, b, prec=prec, bias=bias, act=ACT_GELU, out=h, out_pre=pre, drop=drop)
+        assert torch.equal(pre, pre0)
+        want = ops.split(h0 * mult, prec)
+        assert torch.equal(h.hi, want.hi) and (h.lo is None or torch.equal(h.lo, want.lo))
+        # backward: (mask * acc) * gelu'(aux)
+        d0 = torch.empty(M, N, device=DEV)
+        ops.gemm(a, b, prec=prec, act=ACT_NONE, out_f32=d0)
+        dz = torch.empty(M, N, device=DEV)
+        ops.gemm(a, b, prec=prec, act=ACT_GELU_GRAD, aux=aux, out_f32=dz, drop=drop)
+        z = aux.double()
+        gp = 0.5 * (1 + torch.erf(z / 2 ** 0.5)) + z * torch.exp(-0.5 * z * z) / (2 * np.pi) ** 0.5
+        _close(dz, (d0 * mult).double() * gp, 1e-5)
+        assert torch.equal(dz == 0, ((d0 * mult) == 0) | (dz == 0))
