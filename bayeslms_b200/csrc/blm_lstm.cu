@@ -36,6 +36,8 @@ struct LstmParams {
   CUtensorMap tmH[2][2];  // [buffer][hi, lo] : h state [B, H] bf16, box 128 x 64 (box 32 x 64 in the cluster kernel)
   CUtensorMap tmW[2];     // [hi, lo]         : W_hh [4H, H] bf16, box U x 64
   int a_box_bytes;        // bytes one h K block brings: box rows x 128 (a one-tile batch loads only its real rows)
+  int whole_k;            // 1: small one-tile batch -- ALL K blocks of h_{t-1} are loaded at once, packed at a_box_bytes
+                          // stride, and the MMAs run back to back: no ring round trips inside a step
   int kb_stagger;         // 1: stagger the K-block order per CTA (A/B switch BLM_LSTM_NO_STAGGER)
   int unit_blocks;        // H / U
   int tiles_per_cta;      // 128-row batch tiles per CTA (batch split)
@@ -249,6 +251,7 @@ template <int kU, int kCL, int kSub>
 __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_constant__ LstmParams p) {
   constexpr int kNStages = kSub == 2 ? kLStages2 : kLStages;
   constexpr int kStageBytes = kSub * kLABytes;
+  constexpr int kWholeStride = kNStages * kStageBytes / 2 / 1024 * 1024;   // whole_k mode: two half-ring areas
   static_assert(kSub == 1 || kCL == 1, "the cluster experiment keeps one K block per stage");
   constexpr int kLN = 4 * kU;            // MMA N: 4 gates x U units
   constexpr int kLWTile = kLN * 64 * 2;  // one K block of the W slice
@@ -319,6 +322,22 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
     if (warp == 0) {
       if (lane == 0) {
         fence_proxy_async_all();  // h_{t-1} was written with generic stores by other SMs
+        if (kCL == 1 && p.whole_k) {
+          // the hypothesis-#0 chains: a dozen rows, latency is everything.  Two half-ring areas alternate; the 16 KB an
+          // M = 128 descriptor spans past a K block's few real rows overlaps the following K blocks (finite values that
+          // only reach accumulator rows nobody reads)
+          for (int part = 0; part < a_parts; ++part) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.kblocks * p.a_box_bytes));
+            for (int kb = 0; kb < p.kblocks; ++kb)
+              tma_load_2d(sA + stage * kWholeStride + kb * p.a_box_bytes, &p.tmH[cur][part], &full_bar[stage], kb * 64,
+                          mt0 * 128, kEvictNormal);
+            if (++stage == 2) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        } else
         for (int mt = 0; mt < n_mt; ++mt)
           for (int part = 0; part < a_parts; ++part)
             for (int kbi = 0; kbi < p.kblocks; kbi += kSub) {
@@ -347,6 +366,34 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, kLN);  // N = 32 or 64
         tcgen05_fence_after();
+        if (kCL == 1 && p.whole_k) {
+          uint32_t accum = 0;
+          for (int part = 0; part < a_parts; ++part) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kWholeStride + kb * p.a_box_bytes));
+              const uint64_t dw_hi = umma_desc_sw128(smem_u32(sW[0] + kb * kLWTile));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), dw_hi + static_cast<uint64_t>(2 * k), idesc, accum);
+                accum = 1;
+              }
+              if (part == 0 && p.nsplit == 3) {  // h_hi . W_lo
+                const uint64_t dw_lo = umma_desc_sw128(smem_u32(sW[1] + kb * kLWTile));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss(tmem_base, da + static_cast<uint64_t>(2 * k), dw_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == 2) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&tfull_bar[0]);
+        } else
         for (int mt = 0; mt < n_mt; ++mt) {
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kLN);
           uint32_t accum = 0;
@@ -846,6 +893,11 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
     else
       BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<1>, p));
     return BLM_OK;
+  }
+  {
+    const int ring_half = (sub == 2 ? kLStages2 * 2 : kLStages) * kLABytes / 2 / 1024 * 1024;
+    p.whole_k = p.m_tiles == 1 && CL == 1 && !p.kb_stagger && (p.kblocks - 1) * p.a_box_bytes + kLABytes <= ring_half &&
+                getenv("BLM_LSTM_NO_WHOLE_K") == nullptr;
   }
   const dim3 grid(static_cast<unsigned>(p.unit_blocks * nb)), block(kLThreads);
   if (CL > 1) {
