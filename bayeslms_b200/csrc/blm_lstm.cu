@@ -488,6 +488,7 @@ __device__ __forceinline__ void cell_group(const LstmParams& p, const GateIn& in
   const long long o = static_cast<long long>(b) * H + unit;
   const long long ot = (static_cast<long long>(t) * p.B + b) * H + unit;
   __nv_bfloat16* nh = p.hbuf[nxt][0] + o;
+  __nv_bfloat16* nl = p.nsplit == 3 ? p.hbuf[nxt][1] + o : nullptr;
   if (live) {
     float c[8], h[8];
     *reinterpret_cast<float4*>(c) = in.c[0];
@@ -510,7 +511,7 @@ __device__ __forceinline__ void cell_group(const LstmParams& p, const GateIn& in
       *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
       *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
     }
-    store_h8(nh, nullptr, h);
+    store_h8(nh, nl, h);
     if (p.c_seq) {
       *reinterpret_cast<float4*>(p.c_seq + ot) = *reinterpret_cast<float4*>(c);
       *reinterpret_cast<float4*>(p.c_seq + ot + 4) = *reinterpret_cast<float4*>(c + 4);
@@ -519,14 +520,18 @@ __device__ __forceinline__ void cell_group(const LstmParams& p, const GateIn& in
       *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
       *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
     }
-    if (p.out_hi) store_h8(p.out_hi + ot, nullptr, h);
+    if (p.out_hi) store_h8(p.out_hi + ot, p.out_lo ? p.out_lo + ot : nullptr, h);
   } else {
     *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(p.hbuf[cur][0] + o);
+    if (nl) *reinterpret_cast<uint4*>(nl) = *reinterpret_cast<const uint4*>(p.hbuf[cur][1] + o);
     if (p.out_f32) {
       *reinterpret_cast<float4*>(p.out_f32 + ot) = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (p.out_hi) *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
+    if (p.out_hi) {
+      *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
+      if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + ot) = make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
@@ -543,19 +548,22 @@ __device__ __forceinline__ void cell_group(const LstmParams& p, const GateIn& in
 //   warp 1  leader only: MMA issue; multicast commits free the ring slot in both CTAs and publish the accumulator
 //           of a pair tile to both CTAs' epilogue warps
 //   warps 4-11  gates for the CTA's own rows: accumulator columns [64 c, 64 c + 64) are the units of CTA c
-template <int kSub>
+template <int kU, int kSub>
 __global__ void __launch_bounds__(kLThreads, 1) lstm_pair_kernel(const __grid_constant__ LstmParams p) {
-  constexpr int kU = 16;
   constexpr int kNStages = kSub == 2 ? kLStages2 : kLStages;
   constexpr int kStageBytes = kSub * kLABytes;
-  constexpr int kLN = 8 * kU;            // MMA N of the pair: 2 CTAs x 4 gates x 16 units
-  constexpr int kLWTile = 4 * kU * 64 * 2;  // one K block of this CTA's W slice (64 rows)
+  constexpr int kLN = 8 * kU;            // MMA N of the pair: 2 CTAs x 4 gates x kU units
+  constexpr int kLWTile = 4 * kU * 64 * 2;  // one K block of this CTA's W slice (4 kU rows), per part
+  constexpr int GPT = kU / 4;            // groups of 8 units per pair tile (2 CTAs x kU / 8)
+  constexpr int TPW = 512 / kLN / 2;     // pair tiles per epilogue warp set (tiles w, w + 2, ...)
+  constexpr int NQ = GPT * TPW;          // groups per step and warp: 8 either way
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~static_cast<uintptr_t>(1023u));
   const int w_bytes = p.kblocks * kLWTile;
-  uint8_t* sW = smem;
-  uint8_t* sA = smem + w_bytes;
+  uint8_t* sW[2] = {smem, smem + w_bytes};                 // hi, lo (precise mode: kU = 8, both resident)
+  const int a_parts = p.nsplit == 3 ? 2 : 1;
+  uint8_t* sA = smem + a_parts * w_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kNStages * kStageBytes);  // used in the leader only
   uint64_t* empty_bar = full_bar + kNStages;
   uint64_t* tfull_bar = empty_bar + kNStages;  // [kLMaxTiles]
@@ -589,10 +597,12 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_pair_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(w_bytes));
-    for (int kb = 0; kb < p.kblocks; ++kb)
-      for (int g = 0; g < 4; ++g)
-        tma_load_2d(sW + kb * kLWTile + g * (kU * 128), &p.tmW[0], w_bar, kb * 64, g * p.H + j * kU, kEvictFirst);
+    mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(a_parts * w_bytes));
+    for (int part = 0; part < a_parts; ++part)
+      for (int kb = 0; kb < p.kblocks; ++kb)
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(sW[part] + kb * kLWTile + g * (kU * 128), &p.tmW[part], w_bar, kb * 64, g * p.H + j * kU,
+                      kEvictFirst);
   }
   publish_initial_state<kU>(p, row_lo, row_hi, j * kU);
   fence_proxy_async_all();
@@ -611,19 +621,22 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_pair_kernel(const __grid_co
   // every CTA's reads of it (its step-t MMAs of that tile) completed before its own arrival for (t, tile), which all
   // step-(t+1) MMAs of the tile wait for; the tile's accumulator is re-used only after this CTA's own epilogue warps
   // arrived (they arrive after their tcgen05.ld completed).
-  unsigned int* tile_flag = p.barrier + 64 + (bi * 4) * 32;
+  unsigned int* tile_flag = p.barrier + 64 + (bi * 8) * 32;
   const unsigned int flag_per_step = static_cast<unsigned int>(p.unit_blocks) * 4u;
 
   // epilogue warps: warp w of a lane group takes pair tiles w and w + 2; one batch row per thread
   const int lane_grp = warp & 3;
   const int epi_w = (warp - 4) >> 2;
   const int epi_b0 = (mt0 + epi_w) * 256 + static_cast<int>(rank) * 128 + lane_grp * 32 + lane;   // row in tile w
-  int len_a = 0, len_b = 0;
+  int len_t[TPW];   // length of this thread's row in each of its tiles
   GateIn gin[2];
   if (warp >= 4) {
-    if (epi_w < n_mt && epi_b0 < B) len_a = min(__ldg(p.lengths + epi_b0), p.T);
-    if (epi_w + 2 < n_mt && epi_b0 + 512 < B) len_b = min(__ldg(p.lengths + epi_b0 + 512), p.T);
-    if (epi_w < n_mt) load_gate_in(p, gin[0], 0, epi_b0, (j & ~1) * kU, 0 < len_a);
+#pragma unroll
+    for (int ti = 0; ti < TPW; ++ti) {
+      const int b = epi_b0 + 2 * ti * 256;
+      len_t[ti] = (epi_w + 2 * ti < n_mt && b < B) ? min(__ldg(p.lengths + b), p.T) : 0;
+    }
+    if (epi_w < n_mt) load_gate_in(p, gin[0], 0, epi_b0, (j & ~1) * kU, 0 < len_t[0]);
   }
 
   for (int t = 0; t < p.T; ++t) {
@@ -635,19 +648,20 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_pair_kernel(const __grid_co
           // each of the unit_blocks CTAs of this batch block) has arrived t times
           if (t > 0) flag_wait(tile_flag + mt * 32, static_cast<unsigned int>(t) * flag_per_step);
           fence_proxy_async_all();  // h_{t-1} was written with generic stores by other SMs
-          for (int kb = 0; kb < p.kblocks; kb += kSub) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          for (int part = 0; part < a_parts; ++part)
+            for (int kb = 0; kb < p.kblocks; kb += kSub) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
 #pragma unroll
-            for (int sub = 0; sub < kSub; ++sub)
-              tma_load_2d_2sm(sA + stage * kStageBytes + sub * kLABytes, &p.tmH[cur][0], bar, (kb + sub) * 64,
-                              (mt0 + mt) * 256 + static_cast<int>(rank) * 128, kEvictNormal);
-            if (++stage == kNStages) {
-              stage = 0;
-              phase ^= 1u;
+              for (int sub = 0; sub < kSub; ++sub)
+                tma_load_2d_2sm(sA + stage * kStageBytes + sub * kLABytes, &p.tmH[cur][part], bar, (kb + sub) * 64,
+                                (mt0 + mt) * 256 + static_cast<int>(rank) * 128, kEvictNormal);
+              if (++stage == kNStages) {
+                stage = 0;
+                phase ^= 1u;
+              }
             }
-          }
         }
       }
       __syncwarp();
@@ -658,66 +672,74 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_pair_kernel(const __grid_co
         for (int mt = 0; mt < n_mt; ++mt) {
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(mt * kLN);
           uint32_t accum = 0;
-          for (int kb0 = 0; kb0 < p.kblocks; kb0 += kSub) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
+          for (int part = 0; part < a_parts; ++part)
+            for (int kb0 = 0; kb0 < p.kblocks; kb0 += kSub) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
 #pragma unroll
-            for (int sub = 0; sub < kSub; ++sub) {
-              const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kStageBytes + sub * kLABytes));
-              const uint64_t dw = umma_desc_sw128(smem_u32(sW + (kb0 + sub) * kLWTile));
+              for (int sub = 0; sub < kSub; ++sub) {
+                const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * kStageBytes + sub * kLABytes));
+                const uint64_t dw = umma_desc_sw128(smem_u32(sW[0] + (kb0 + sub) * kLWTile));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), dw + static_cast<uint64_t>(2 * k), idesc, accum);
-                accum = 1;
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), dw + static_cast<uint64_t>(2 * k), idesc, accum);
+                  accum = 1;
+                }
+                if (part == 0 && p.nsplit == 3) {  // h_hi . W_lo (part 1 is h_lo . W_hi)
+                  const uint64_t dl = umma_desc_sw128(smem_u32(sW[1] + (kb0 + sub) * kLWTile));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), dl + static_cast<uint64_t>(2 * k), idesc, 1u);
+                }
+              }
+              umma_commit_2sm(&empty_bar[stage], mask2);
+              if (++stage == kNStages) {
+                stage = 0;
+                phase ^= 1u;
               }
             }
-            umma_commit_2sm(&empty_bar[stage], mask2);
-            if (++stage == kNStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
           umma_commit_2sm(&tfull_bar[mt], mask2);
         }
       }
       __syncwarp();
     } else if (warp >= 4) {
-      // groups of the step, in order: (tile w, w + 2) x (leader's units, peer's units) x (units 0-7, 8-15)
+      // groups of the step, in order: tiles w, w + 2, .. x (leader's units, peer's units) x 8-unit groups
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int ti = q >> 2, half = (q >> 1) & 1, u8 = (q & 1) * 8;
+      for (int q = 0; q < NQ; ++q) {
+        constexpr int kG8 = kU / 8;
+        const int ti = q / GPT, half = (q % GPT) / kG8, u8 = ((q % GPT) % kG8) * 8;
         const int mt = epi_w + 2 * ti;
         if (mt >= n_mt) break;
         const int b = epi_b0 + 2 * ti * 256;
-        const int len = ti ? len_b : len_a;
+        const int len = len_t[ti];
         const int unit = ((j & ~1) + half) * kU + u8;
         // request the operands of the next group: next q of this step, or the first group of step t + 1
         {
           const int qn = q + 1;
-          const bool wrap = qn == 8 || epi_w + 2 * (qn >> 2) >= n_mt;
+          const int tin = qn < NQ ? qn / GPT : 0;
+          const bool wrap = qn == NQ || epi_w + 2 * tin >= n_mt;
+          const int halfn = (qn % GPT) / kG8, u8n = ((qn % GPT) % kG8) * 8;
           const int tn = wrap ? t + 1 : t;
-          const int qq = wrap ? 0 : qn;
-          const int tin = qq >> 2;
-          const int bn = epi_b0 + 2 * tin * 256;
-          const int lenn = tin ? len_b : len_a;
-          const int unitn = ((j & ~1) + ((qq >> 1) & 1)) * kU + (qq & 1) * 8;
+          const int bn = wrap ? epi_b0 : epi_b0 + 2 * tin * 256;
+          const int lenn = wrap ? len_t[0] : len_t[tin];
+          const int unitn = wrap ? (j & ~1) * kU : ((j & ~1) + halfn) * kU + u8n;
           load_gate_in(p, gin[(q + 1) & 1], tn, bn, unitn, tn < lenn);
         }
-        if ((q & 3) == 0) {
+        if ((q % GPT) == 0) {
           mbar_wait(&tfull_bar[mt], static_cast<uint32_t>(t & 1));
           tcgen05_fence_after();
         }
         float acc[32];
         __syncwarp();
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                              static_cast<uint32_t>(mt * kLN + half * 64 + u8);
+                              static_cast<uint32_t>(mt * kLN + half * (4 * kU) + u8);
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld_32x8(tcol + static_cast<uint32_t>(g * kU), acc + 8 * g);
         tmem_ld_wait();
         if (b < B) cell_group(p, gin[q & 1], acc, t, b, unit, t < len, t + 1 == len, cur, nxt);
-        if ((q & 3) == 3) {
-          // publish this warp's 32 rows x 32 units of h_t: visible to the async proxy (TMA reads of step t + 1) and at
-          // gpu scope before the flag moves
+        if ((q % GPT) == GPT - 1) {
+          // publish this warp's 32 rows x 2 kU units of h_t: visible to the async proxy (TMA reads of step t + 1) and
+          // at gpu scope before the flag moves
           tcgen05_fence_before();
           fence_proxy_async_all();
           __threadfence();
@@ -750,10 +772,14 @@ int lstm_init() {
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16, 2))));
   BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_layer_kernel<16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16))));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16))));
-  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lstm_smem_bytes(16, 1, 16, 2))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 3, 8))));
+  BLM_CHECK_CUDA(cudaFuncSetAttribute(lstm_pair_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lstm_smem_bytes(16, 3, 8, 2))));
   return BLM_OK;
 }
 
@@ -762,9 +788,9 @@ int lstm_init() {
 extern "C" {
 
 int64_t blm_lstm_workspace_bytes(int64_t B, int64_t H) {
-  // barrier counter + per-tile step flags (2 KB header) + 2 buffers x (hi, lo) x [B, H] bf16 + the running cell state
+  // barrier counter + per-tile step flags (4 KB header) + 2 buffers x (hi, lo) x [B, H] bf16 + the running cell state
   // in 32-row blocks
-  return 2048 + 4 * B * H * 2 + (B + 31) / 32 * 32 * H * 4;
+  return 4096 + 4 * B * H * 2 + (B + 31) / 32 * 32 * H * 4;
 }
 
 int blm_lstm_layer(const float* gates_x, const blm_bf16* w_hh_hi, const blm_bf16* w_hh_lo, const float* h0,
@@ -816,8 +842,8 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
   BLM_REQUIRE(aligned16(c_seq), BLM_ERR_ALIGN, "c_seq must be 16-byte aligned");
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   p.barrier = reinterpret_cast<unsigned int*>(ws);
-  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(ws + 2048);
-  p.c_ws = reinterpret_cast<float*>(ws + 2048 + 4 * B * H * 2);
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(ws + 4096);
+  p.c_ws = reinterpret_cast<float*>(ws + 4096 + 4 * B * H * 2);
   p.gx_rows32 = gx_rows32 ? 1 : 0;
   // bf16 mode: 16 units per CTA and the batch split over two CTA rows (halves the per-step h ingest);
   // precise mode keeps 8 units per CTA (hi + lo slices fill the same 128 KB) and no batch split
@@ -856,17 +882,18 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
   if (rc != BLM_OK) return rc;
 
   cudaStream_t st = as_stream(stream);
-  BLM_CHECK_CUDA(cudaMemsetAsync(p.barrier, 0, 2048, st));
+  BLM_CHECK_CUDA(cudaMemsetAsync(p.barrier, 0, 4096, st));
   void* args[] = {&p};
   static const bool no_sub2 = getenv("BLM_LSTM_NO_SUB2") != nullptr;  // A/B switch for profiling
   const int sub = (!no_sub2 && (p.kblocks % 2) == 0 && !p.kb_stagger) ? 2 : 1;
-  // CTA pairs (lstm_pair_kernel): bf16 mode, three or more 128-row tiles (below that a CTA already streams one tile).
+  // CTA pairs (lstm_pair_kernel): three or more 128-row tiles (below that a CTA already streams one tile); bf16 mode
+  // with 16 units per CTA and the batch split in two, precise mode with 8 units per CTA (hi + lo slices resident).
   // Read per call so that a test can compare both kernels in one process.
   const int pair_tiles = static_cast<int>((B + 255) / 256);
-  const int pair_nb = (pair_tiles >= 2 && 2 * (H / 16) <= num_sms()) ? 2 : 1;
+  const int pair_nb = (pair_tiles >= 2 && 2 * (H / U) <= num_sms()) ? 2 : 1;
   const int pair_tpc = (pair_tiles + pair_nb - 1) / pair_nb;
-  const bool pair = U == 16 && CL == 1 && !p.kb_stagger && (H % 32) == 0 && p.m_tiles >= 3 && pair_tpc * 128 <= 512 &&
-                    getenv("BLM_LSTM_NO_PAIR") == nullptr;
+  const bool pair = CL == 1 && !p.kb_stagger && (H % (2 * U)) == 0 && (U == 16 || w_hh_lo) && p.m_tiles >= 3 &&
+                    pair_tpc * 8 * U <= 512 && H / U <= num_sms() && getenv("BLM_LSTM_NO_PAIR") == nullptr;
   if (pair) {
     p.m_tiles = pair_tiles;
     p.tiles_per_cta = pair_tpc;
@@ -874,7 +901,7 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(static_cast<unsigned>(p.unit_blocks * pair_nb));
     cfg.blockDim = dim3(kLThreads);
-    cfg.dynamicSmemBytes = lstm_smem_bytes(p.kblocks, 1, 16, sub);
+    cfg.dynamicSmemBytes = lstm_smem_bytes(p.kblocks, p.nsplit, U, sub);
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -888,10 +915,17 @@ int blm_lstm_layer_seq(const float* gates_x, int32_t gx_rows32, const blm_bf16* 
     // BLM_LSTM_NO_COOP=1 drops the cooperative attribute; residency then rests on the grid (<= 148 CTAs, one per SM)
     // being alone on the device, which a profiling run is.
     cfg.numAttrs = getenv("BLM_LSTM_NO_COOP") ? 1 : 2;
-    if (sub == 2)
-      BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<2>, p));
-    else
-      BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<1>, p));
+    if (U == 16) {
+      if (sub == 2)
+        BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<16, 2>, p));
+      else
+        BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<16, 1>, p));
+    } else {
+      if (sub == 2)
+        BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<8, 2>, p));
+      else
+        BLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_pair_kernel<8, 1>, p));
+    }
     return BLM_OK;
   }
   {

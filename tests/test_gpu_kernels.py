@@ -556,15 +556,16 @@ def test_attention_dropout_forward_and_backward(ops, lens, prec, tol_f, tol_b):
     assert (plain - a1).abs().max() > 1e-2
 
 
-def _lstm_layer_ref(gx, w, h0, c0, lengths):
-    """fp64 recurrence on the bf16-rounded W_hh; h is re-rounded to bf16 as the operand of the next step (the kernel's
-    bf16 mode), state kept in full precision."""
+def _lstm_layer_ref(gx, w, h0, c0, lengths, rounded=True):
+    """fp64 recurrence.  ``rounded``: on the bf16-rounded W_hh, h re-rounded to bf16 as the operand of the next step
+    (the kernel's bf16 mode); state kept in full precision either way."""
     T, B, H4 = gx.shape
-    w = w.to(torch.bfloat16).double()
+    rnd = (lambda x: x.to(torch.bfloat16).double()) if rounded else (lambda x: x.double())
+    w = rnd(w)
     h, c = h0.double().clone(), c0.double().clone()
     outs = torch.zeros(T, B, H4 // 4, dtype=torch.float64, device=gx.device)
     for t in range(T):
-        a = gx[t].double() + h.to(torch.bfloat16).double() @ w.t()
+        a = gx[t].double() + rnd(h.float()) @ w.t()
         i, f, g, o = a.chunk(4, dim=1)
         cn = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
         hn = torch.sigmoid(o) * torch.tanh(cn)
@@ -574,11 +575,13 @@ def _lstm_layer_ref(gx, w, h0, c0, lengths):
     return outs, h, c
 
 
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("T,B,H", [(5, 384, 64), (7, 700, 128), (4, 1500, 256), (3, 2048, 1024), (6, 1024, 1024)])
-def test_lstm_pair_kernel_matches_the_single_cta_kernel(ops, monkeypatch, T, B, H):
-    """lstm_pair_kernel (cta_group::2, the default from three 128-row tiles up) against lstm_layer_kernel
-    (BLM_LSTM_NO_PAIR=1) on the same inputs -- same K order, same fp32 accumulation: bit-identical -- and both against
-    the fp64 recurrence.  Ragged batches (B not a multiple of 256), rows of every length incl. 0."""
+def test_lstm_pair_kernel_matches_the_single_cta_kernel(ops, monkeypatch, T, B, H, prec):
+    """lstm_pair_kernel (cta_group::2, the default from three 128-row tiles up; 16 units per CTA in bf16 mode, 8 with
+    hi + lo slices in precise mode) against lstm_layer_kernel (BLM_LSTM_NO_PAIR=1) on the same inputs -- same K order,
+    same fp32 accumulation: bit-identical -- and both against the fp64 recurrence.  Ragged batches (B not a multiple of
+    256), rows of every length incl. 0."""
     g = torch.Generator(device=DEV).manual_seed(T * 1000 + B + H)
     gx = torch.randn(T, B, 4 * H, device=DEV, generator=g)
     w = torch.randn(4 * H, H, device=DEV, generator=g) / H ** 0.5
@@ -586,7 +589,7 @@ def test_lstm_pair_kernel_matches_the_single_cta_kernel(ops, monkeypatch, T, B, 
     c0 = torch.randn(B, H, device=DEV, generator=g) * 0.5
     lengths = torch.randint(0, T + 1, (B,), device=DEV, generator=g).to(torch.int32)
     lengths[:3] = T
-    ws = ops.split(w, "bf16")
+    ws = ops.split(w, prec)
 
     def run(rows32=False):
         cs = torch.zeros(T * B, H, device=DEV)
@@ -596,10 +599,10 @@ def test_lstm_pair_kernel_matches_the_single_cta_kernel(ops, monkeypatch, T, B, 
             pad[:T * B] = g2
             g2 = pad.view(-1, 32, H, 4).permute(0, 2, 1, 3).contiguous().view(-1, 4 * H)
             assert torch.equal(ops.rows32_to_dense(g2, T * B), gx.view(T * B, 4 * H))
-        o32, o, hT, cT = ops.lstm_layer(g2, ws, h0, c0, lengths, T, B, H, prec="bf16", want_f32=True, c_seq=cs,
+        o32, o, hT, cT = ops.lstm_layer(g2, ws, h0, c0, lengths, T, B, H, prec=prec, want_f32=True, c_seq=cs,
                                         gx_rows32=rows32)
         torch.cuda.synchronize()
-        return o32.clone(), o.hi.clone(), hT.clone(), cT.clone(), cs
+        return o32.clone(), o.float().clone(), hT.clone(), cT.clone(), cs
 
     pair = run()
     pair32 = run(rows32=True)
@@ -609,10 +612,11 @@ def test_lstm_pair_kernel_matches_the_single_cta_kernel(ops, monkeypatch, T, B, 
     for other in (pair32, single, single32):
         for a, b in zip(pair, other):
             assert torch.equal(a, b)
-    ro, rh, rc = _lstm_layer_ref(gx, w, h0, c0, lengths)
-    _close(pair[0].view(T, B, H), ro, 2e-3)
-    _close(pair[2], rh, 2e-3)
-    _close(pair[3], rc, 2e-3)
+    ro, rh, rc = _lstm_layer_ref(gx, w, h0, c0, lengths, rounded=prec == "bf16")
+    tol = 2e-3 if prec == "bf16" else 3e-5       # bf16: MUFU gate math on rounded operands; precise: ~16 mantissa bits
+    _close(pair[0].view(T, B, H), ro, tol)
+    _close(pair[2], rh, tol)
+    _close(pair[3], rc, tol)
 
 
 @pytest.mark.parametrize("M,N,K,prec", [(300, 512, 200, "bf16"), (4096, 4096, 1024, "bf16"), (1000, 1024, 256, "bf16x3"),
