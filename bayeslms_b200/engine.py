@@ -630,7 +630,7 @@ def _lstm_chain(model, plan: _Plan, weights, tokens_ts: torch.Tensor, lengths: t
         ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag=f"lstm_in{li + 1}", f32_rows32=True)
         c_seq = torch.empty(T * S, H, dtype=torch.float32, device=dev)
         h_seq, x, _, _ = ops.lstm_layer(gates, W["w_hh"], zero, zero, lengths, T, S, H, prec=prec, want_f32=True,
-                                        want_split=li + 1 < len(weights), c_seq=c_seq, gx_rows32=True)
+                                        want_split=li + 1 < len(weights), c_seq=c_seq, gx_rows32=True, tag="chain")
         hs.append(h_seq)
         cs.append(c_seq)
     return hs, cs

@@ -518,7 +518,7 @@ def kl_gauss(mu: torch.Tensor, lgstd: torch.Tensor, out: torch.Tensor, *, minus_
 
 def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.Tensor, lengths: torch.Tensor,
                T: int, B: int, H: int, *, prec: str = "bf16", want_f32: bool = False, want_split: bool = True,
-               c_seq: Optional[torch.Tensor] = None, gx_rows32: bool = False):
+               c_seq: Optional[torch.Tensor] = None, gx_rows32: bool = False, tag: str = ""):
     """One LSTM layer over [T, B] lock-stepped rows.  Returns (out_f32 or None, out Split or None, hT, cT).
     ``c_seq`` [T * B, H] fp32 (optional) receives the cell state after every live step.  ``gx_rows32``: ``gates_x``
     is a ``rows32_empty(T * B, 4 * H)`` buffer filled by ``gemm(..., f32_rows32=True)``."""
@@ -535,7 +535,7 @@ def lstm_layer(gates_x: torch.Tensor, w_hh: Split, h0: torch.Tensor, c0: torch.T
     if c_seq is not None:
         assert c_seq.dtype == torch.float32 and c_seq.is_contiguous() and c_seq.numel() == T * B * H
     # algorithmic bytes per step = W_hh once (4H x H bf16) + gates_x read (B x 4H fp32) + h, c write
-    with _op("lstm_layer", 1, 2.0 * T * B * 4 * H * H, T * (4.0 * H * H * 2 + B * 4.0 * H * 4 + 2.0 * B * H * 4)):
+    with _op("lstm_layer:" + tag if tag else "lstm_layer", 1, 2.0 * T * B * 4 * H * H, T * (4.0 * H * H * 2 + B * 4.0 * H * 4 + 2.0 * B * H * 4)):
         check(lib().blm_lstm_layer_seq(_ptr(gates_x), int(gx_rows32), _ptr(w_hh.hi), _ptr(w_hh.lo if prec == "bf16x3" else None), _ptr(h0),
                                        _ptr(c0), _ptr(lengths), T, B, H, _ptr(out32),
                                        _ptr(None if outs is None else outs.hi), _ptr(None if outs is None else outs.lo),

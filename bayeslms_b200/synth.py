@@ -198,8 +198,10 @@ def ranking_agreement(a: List[np.ndarray], b: List[np.ndarray], min_gap: float =
     on the output grid of ``lmwt.nn`` (``%.4f``, score.py:302) with ties broken by hypothesis index -- the tie policy
     of a stable sort over the file order.  Returns a dict: fraction of utterances with the identical FULL ranking, with
     the identical 1-best, the fraction of hypothesis pairs ordered the same way among pairs whose gap in ``b`` exceeds
-    ``min_gap``, and the largest gap in ``b`` of a pair that ``a`` orders differently."""
-    full = best = 0
+    ``min_gap``, and the largest gap in ``b`` of a pair that ``a`` orders differently.  ``one_best_within_gap`` also
+    counts an utterance whose two 1-best candidates are closer than ``min_gap`` in ``b`` (a tie at the stated
+    tolerance: either choice is a correct 1-best)."""
+    full = best = best_gap = 0
     pairs = agree = 0
     worst = 0.0
     for x, y in zip(a, b):
@@ -207,6 +209,7 @@ def ranking_agreement(a: List[np.ndarray], b: List[np.ndarray], min_gap: float =
         rx, ry = np.argsort(qx, kind="stable"), np.argsort(qy, kind="stable")
         full += int(np.array_equal(rx, ry))
         best += int(rx[0] == ry[0])
+        best_gap += int(rx[0] == ry[0] or abs(qy[rx[0]] - qy[ry[0]]) <= min_gap)
         dx, dy = qx[:, None] - qx[None, :], qy[:, None] - qy[None, :]
         iu = np.triu_indices(len(qx), 1)
         gx, gy = dx[iu], dy[iu]
@@ -218,5 +221,5 @@ def ranking_agreement(a: List[np.ndarray], b: List[np.ndarray], min_gap: float =
         if flipped.any():
             worst = max(worst, float(np.abs(gy[flipped]).max()))
     n = max(len(a), 1)
-    return {"full_ranking": full / n, "one_best": best / n, "pair_order": agree / max(pairs, 1),
+    return {"full_ranking": full / n, "one_best": best / n, "one_best_within_gap": best_gap / n, "pair_order": agree / max(pairs, 1),
             "largest_flipped_gap": worst, "utterances": len(a), "pairs": pairs}

@@ -12,10 +12,19 @@ gather per step).  Reported:
 
   value        tokens/s, posterior mean, bf16 operands / fp32 accumulate, ids already in HBM
   e2e          same through Rescorer.score_packed_host: pinned host ids -> device, scores -> host
+  cli_e2e      same through scorer.score_files: words_text + words.txt on disk -> lmwt.nn on disk (the call the
+               reference's stage-6 command line maps to), vocabulary parsed every step
   sampled_k4   K=4 Philox posterior samples (Monte-Carlo predictive), device-resident
-  precise      bf16x3 (hi/lo split) mode that holds the 1e-3 parity bar
+  precise      bf16x3 (hi/lo split) mode that holds the 1e-3 parity bar, with its own roofline and slowdown
   roofline     the vocabulary-streaming projection+NLL kernel, 2*M*d*V FLOP per launch over the
-               CUDA-event time of its launches, against MEASURED_PEAKS.json (sustained bf16)
+               CUDA-event time of its launches, against MEASURED_PEAKS.json (sustained bf16);
+               roofline_dominant_kernel = the kernel with the largest share of the step (FFN1+GELU),
+               whole_step_roofline = 93.8 MFLOP per token x tokens/s, kernel_rooflines = every GEMM of the step
+  ranking_peaked_model   fast vs precise rankings on a model fine-tuned to sharp distributions (evidence.py)
+  gp_tm_rescoring / gp_tm_sampled_k1 / gp_tm_strong_scaling   BASELINE config 3 (one fixed 8000-utterance list
+               sharded over the ranks for the strong-scaling entry)
+  finetune_step  BASELINE config 4: captured V-Transformer step (roofline, with_dropout_0.2, CPU port of the step)
+  lstm_rescoring BASELINE config 5 at its per-GPU size and config 1 as its cpu_baseline; recurrence_roofline
   cpu_baseline the CPU oracle port (reference algorithm, torch CPU fp32, batch 1 per hypothesis)
                on a bounded sample of the same lists, rank 0, N=1 only
 """
@@ -197,21 +206,26 @@ def bench_lstm(dev, world=1, rank=0, steps=1):
         out[name] = {"tokens_per_s": n_tok.item() / dt.item(), "ms": dt.item() * 1e3}
         if name == "mean":
             timing, ops.STATS.timing = ops.STATS.timing, None
-            ev = timing.get("lstm_layer", [])
+            ev = timing.get("lstm_layer", [])            # the lock-step hypothesis batches (B up to 2048 rows)
             ms_k = sum(a.elapsed_time(b) for a, b, _ in ev)
             flop = sum(w for _, _, w in ev)
             byts = ops.STATS.bytes.get("lstm_layer", 0.0)
             tot = sum(sum(a.elapsed_time(b) for a, b, _ in v) for v in timing.values()) or 1.0
             if ms_k:
+                chain = timing.get("lstm_layer:chain", [])
                 out["recurrence_roofline"] = {
-                    "kernel": "lstm_pair_kernel<2> (persistent recurrence of cta_group::2 pairs, W_hh resident in shared memory; "
-                              "the 12-row hypothesis-#0 chains run lstm_layer_kernel<16,1,2>)",
+                    "kernel": "lstm_pair_kernel<16,2> (persistent recurrence of cta_group::2 pairs, W_hh resident in shared "
+                              "memory), the launches of the lock-step hypothesis batches",
                     "bound": "hbm", "achieved": byts / (ms_k / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": byts / (ms_k / 1e3) / 1e9 / pk["hbm"], "launches": len(ev), "share_of_kernel_time": ms_k / tot,
-                    "tensor_tflops": flop / (ms_k / 1e3) / 1e12,
+                    "tensor_tflops": flop / (ms_k / 1e3) / 1e12, "tensor_frac": flop / (ms_k / 1e3) / 1e12 / pk["tensor"],
                     # ncu --set full of one 40-step launch at B = 2048 (profiles/r02d_lstm_pair_vs_single_ncu.txt): DRAM
                     # read 1371 MB (= gates_x, once) + write 241 MB; W_hh is never re-read
                     "traffic": (1371.2e6 + 240.8e6) / 40, "traffic_unit": "DRAM bytes per step at B=2048 (ncu, read + write)",
+                    "hypothesis0_chains": {"kernel": "lstm_layer_kernel<16,1,2>, one row per session, all K blocks of h at once",
+                                           "launches": len(chain), "ms": sum(a.elapsed_time(b) for a, b, _ in chain),
+                                           "share_of_kernel_time": sum(a.elapsed_time(b) for a, b, _ in chain) / tot,
+                                           "note": "sequential by definition (score.py:271-274): latency-bound, ~10 us per step"},
                     "note": "effective bandwidth on the algorithmic bytes of SURVEY.md 8d (W_hh 8 MiB counted once per step "
                             "+ gates_x + h, c); it may exceed what DRAM delivers because W_hh stays in shared memory"}
             out["kernel_ms_total"] = round(tot / steps, 2)
