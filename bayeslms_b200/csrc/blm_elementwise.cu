@@ -253,7 +253,9 @@ __global__ void gp_lstm_cell_kernel(const float* __restrict__ acc5, long long ld
                                     int H, float* __restrict__ c, float* __restrict__ h,
                                     __nv_bfloat16* __restrict__ h_hi, __nv_bfloat16* __restrict__ h_lo,
                                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-                                    __nv_bfloat16* __restrict__ out_lo) {
+                                    __nv_bfloat16* __restrict__ out_lo, const float* __restrict__ c_in = nullptr) {
+  // gate_type 0: plain cell update from the four pre-activation blocks (no GP block is read); c_in: the cell state the
+  // update starts from, when it is not c itself (GP-LSTM gate type 5: c passed through the GP unit first)
   const long long n = B * H;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -263,15 +265,18 @@ __global__ void gp_lstm_cell_kernel(const float* __restrict__ acc5, long long ld
     float hv = h[i];
     if (live) {
       const float* a = acc5 + b * ld + u;
-      const float z = a[4ll * H];
-      float gp = __ldg(coef + u) * (1.0f / (1.0f + expf(-z)));
-      if (n_act > 1) gp += __ldg(coef + H + u) * tanhf(z);
-      if (n_act > 2) gp += __ldg(coef + 2 * H + u) * fmaxf(z, 0.0f);
+      float gp = 0.0f;
+      if (gate_type != 0) {
+        const float z = a[4ll * H];
+        gp = __ldg(coef + u) * (1.0f / (1.0f + expf(-z)));
+        if (n_act > 1) gp += __ldg(coef + H + u) * tanhf(z);
+        if (n_act > 2) gp += __ldg(coef + 2 * H + u) * fmaxf(z, 0.0f);
+      }
       const float ig = gate_type == 1 ? gp : 1.0f / (1.0f + expf(-a[0]));
       const float fg = gate_type == 2 ? gp : 1.0f / (1.0f + expf(-a[H]));
       const float gg = gate_type == 3 ? gp : tanhf(a[2ll * H]);
       const float og = gate_type == 4 ? gp : 1.0f / (1.0f + expf(-a[3ll * H]));
-      const float cv = fg * c[i] + ig * gg;
+      const float cv = fg * (c_in ? c_in[i] : c[i]) + ig * gg;
       hv = og * tanhf(cv);
       c[i] = cv;
       h[i] = hv;
@@ -435,6 +440,20 @@ int blm_gp_lstm_cell(const float* acc5, int64_t ld, const float* coef, int32_t n
       acc5, ld, coef, n_act, gate_type, lengths, t, B, H, c, h, reinterpret_cast<__nv_bfloat16*>(h_hi),
       reinterpret_cast<__nv_bfloat16*>(h_lo), out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
       reinterpret_cast<__nv_bfloat16*>(out_lo));
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_lstm_cell_step(const float* acc4, int64_t ld, const float* c_in, const int32_t* lengths, int32_t t, int64_t B,
+                       int32_t H, float* c, float* h, blm_bf16* h_hi, blm_bf16* h_lo, float* out_f32, blm_bf16* out_hi,
+                       blm_bf16* out_lo, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(acc4 && lengths && c && h && h_hi && B > 0 && H > 0 && ld >= 4ll * H, BLM_ERR_ARG,
+              "bad lstm_cell_step arguments");
+  gp_lstm_cell_kernel<<<grid_for(B * H, 256, 8), 256, 0, as_stream(stream)>>>(
+      acc4, ld, nullptr, 0, 0, lengths, t, B, H, c, h, reinterpret_cast<__nv_bfloat16*>(h_hi),
+      reinterpret_cast<__nv_bfloat16*>(h_lo), out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      reinterpret_cast<__nv_bfloat16*>(out_lo), c_in);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

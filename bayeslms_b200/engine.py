@@ -152,6 +152,17 @@ def _cell_lstm_plan(self, m):
                 g = lambda n: getattr(member, f"{n}_l{l}").detach().float()  # noqa: E731
                 self.lstm.append({"w_ih": self.split(g("weight_ih")), "w_hh": self.split(g("weight_hh")),
                                   "bias": (g("bias_ih") + g("bias_hh")).contiguous()})
+        elif getattr(member, "kind", "") == "gp" and member.gate_type >= 5:
+            # gate types 5-7: the GP unit sits outside the gate nonlinearities (model.py:1745-1750, 1763-1764) and is
+            # a GEMM with the GP-mixture epilogue: coefficients re-ordered to the epilogue's (tanh, sigmoid, relu, gelu)
+            gp = member.gpnn
+            cm = gp.coef_mean.detach().float()                              # rows: sigmoid, tanh, relu
+            coef4 = torch.stack([cm[1], cm[0], cm[2], torch.zeros_like(cm[0])]).contiguous()
+            b_ih = member.bias_ih.detach().float()
+            self.lstm.append({"w_ih": self.split(member.weights_ih), "w_hh": self.split(member.weights_hh),
+                              "bias": ((2.0 if member.gate_type == 5 else 1.0) * b_ih).contiguous(),
+                              "gp": {"gate": member.gate_type, "coef4": coef4, "wg": self.split(gp.weights_mean),
+                                     "bg": gp.bias_mean.detach().float().contiguous()}})
         elif getattr(member, "kind", "") == "gp":
             gp, nin = member.gpnn, member.input_size
             wg = gp.weights_mean.detach().float()
@@ -641,6 +652,8 @@ def _gp_lstm_layer(plan: _Plan, W, x: Split, h0, c0, lengths, T, B, H, want_f32,
     hoisted into one GEMM over all timesteps; each step is one [B, 5H] product on the recurrent weights with the
     hoisted rows as the residual operand, then the fused cell update."""
     prec, dev = plan.prec, plan.device
+    if W["gp"]["gate"] >= 5:
+        return _gp_lstm_layer_outer(plan, W, x, h0, c0, lengths, T, B, H, want_f32, want_split)
     pre = torch.empty(T * B, 5 * H, dtype=torch.float32, device=dev)
     ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=pre, tag="gplstm_in")
     h = h0.detach().float().contiguous().clone()
@@ -655,6 +668,43 @@ def _gp_lstm_layer(plan: _Plan, W, x: Split, h0, c0, lengths, T, B, H, want_f32,
         ops.gp_lstm_cell(acc, W["gp"]["coef"], W["gp"]["gate"], lengths, t, c, h, h_op,
                          None if out32 is None else out32[rows],
                          None if outs is None else Split(outs.hi[rows], None if outs.lo is None else outs.lo[rows]))
+    return out32, outs, h, c
+
+
+def _gp_lstm_layer_outer(plan: _Plan, W, x: Split, h0, c0, lengths, T, B, H, want_f32, want_split):
+    """GP-LSTM gate types 5 ("cell"), 6 ("hidden"), 7 ("inputs") (model.py:1745-1750, 1763-1764), posterior means.
+    7: gates = GPNN(x) + W_hh h + b_ih -- the GP unit is hoisted over all timesteps as ONE GEMM with the mixture
+       epilogue and the layer then runs on the persistent recurrence kernel;
+    6: gates = W_ih x + b_ih + GPNN(h) -- per step one [B, 4H] GEMM on the GP weights with the mixture epilogue and the
+       hoisted input rows as residual, then the plain cell update;
+    5: c <- GPNN(c) before the update -- per step one [B, H] GEMM on the cell state with the mixture epilogue."""
+    prec, dev, G = plan.prec, plan.device, W["gp"]
+    gate, coef4, wg, bg = G["gate"], G["coef4"], G["wg"], G["bg"]
+    gates = torch.empty(T * B, 4 * H, dtype=torch.float32, device=dev)
+    if gate == 7:
+        ops.gemm(x, wg, prec=prec, bias=bg, act=ACT_GPMIX, coef=coef4, out_f32=gates, tag="gplstm_in")
+        ops.rowgroup_add(gates, W["bias"].view(1, -1), 1, T * B, out_f32=gates)          # + b_ih
+        return ops.lstm_layer(gates, W["w_hh"], h0, c0, lengths, T, B, H, prec=prec, want_f32=want_f32,
+                              want_split=want_split)
+    ops.gemm(x, W["w_ih"], prec=prec, bias=W["bias"], out_f32=gates, tag="gplstm_in")      # bias: b_ih (6) / 2 b_ih (5)
+    h = h0.detach().float().contiguous().clone()
+    c = c0.detach().float().contiguous().clone()
+    h_op = ops.split(h, prec)
+    out32 = torch.empty(T * B, H, dtype=torch.float32, device=dev) if want_f32 else None
+    outs = ops.empty_split(T * B, H, prec, dev) if want_split else None
+    acc = torch.empty(B, 4 * H, dtype=torch.float32, device=dev)
+    c_gp = torch.empty(B, H, dtype=torch.float32, device=dev) if gate == 5 else None
+    for t in range(T):
+        rows = slice(t * B, (t + 1) * B)
+        if gate == 6:
+            ops.gemm(h_op, wg, prec=prec, bias=bg, act=ACT_GPMIX, coef=coef4, resid=gates[rows], out_f32=acc,
+                     tag="gplstm_rec")
+        else:
+            ops.gemm(ops.split(c, prec), wg, prec=prec, bias=bg, act=ACT_GPMIX, coef=coef4, out_f32=c_gp, tag="gplstm_cell")
+            ops.gemm(h_op, W["w_hh"], prec=prec, resid=gates[rows], out_f32=acc, tag="gplstm_rec")
+        ops.lstm_cell_step(acc, lengths, t, c, h, h_op, None if out32 is None else out32[rows],
+                           None if outs is None else Split(outs.hi[rows], None if outs.lo is None else outs.lo[rows]),
+                           c_in=c_gp)
     return out32, outs, h, c
 
 

@@ -530,19 +530,29 @@ class RNNModel(nn.Module):
 
 
 class GPLSTMCell(nn.Module):
-    """LSTM cell whose gate ``gate_type`` (1=i, 2=f, 3=g, 4=o) is a GP unit over cat[x, h]
-    (model.py:1674-1777).  Keeps the reference's bias quirk: ``bias_ih`` is added twice and ``bias_hh``
-    never (model.py:1748-1752).  gate types 5-7 and GPNN2 (gpnn_type 4) are not on the hot path."""
+    """LSTM cell with a GP unit (model.py:1674-1777).  gate_type 1..4 (i, f, g, o): that gate is a GP unit over
+    cat[x, h]; 5 ("cell"): the cell state passes through GPNN(H -> H) before the update; 6 ("hidden"): GPNN(h)
+    (H -> 4H) replaces the recurrent product; 7 ("inputs"): GPNN(x) (in -> 4H) replaces the input product.  Keeps the
+    reference's bias quirk: ``bias_ih`` is used wherever the reference writes it (twice in the plain product form) and
+    ``bias_hh`` never (model.py:1745-1752).  GPNN2 (gpnn_type 4) is rejected: its own KL crashes in the reference."""
     kind = "gp"
 
     def __init__(self, input_size, hidden_size, gate_type=0, gpnn_type=0):
         super().__init__()
-        if not (1 <= gate_type <= 4 and 0 <= gpnn_type <= 3):
+        if not (1 <= gate_type <= 7 and 0 <= gpnn_type <= 3):
             raise NotImplementedError(f"GP-LSTM gate_type {gate_type} / gpnn_type {gpnn_type} is outside the B200 hot path "
-                                      "(gates 1-4 with GPNN types 0-3 are)")
+                                      "(gate types 1-7 with GPNN types 0-3 are)")
+        if gate_type in (5, 6) and input_size != hidden_size:
+            raise ValueError(f"GP-LSTM gate_type {gate_type} feeds a [*, hidden] tensor to GPNN(input_size, ...): the "
+                             f"reference needs input_size == hidden_size, got {input_size} and {hidden_size}")
         self.input_size, self.hidden_size, self.gate_type, self.gpnn_type = input_size, hidden_size, gate_type, gpnn_type
-        act_set = ("sigmoid",) if gate_type == 2 else ("sigmoid", "tanh", "relu")
-        self.gpnn = GPNN(hidden_size + input_size, hidden_size, act_set=act_set, gpnn_type=gpnn_type)
+        if gate_type <= 4:
+            act_set = ("sigmoid",) if gate_type == 2 else ("sigmoid", "tanh", "relu")
+            self.gpnn = GPNN(hidden_size + input_size, hidden_size, act_set=act_set, gpnn_type=gpnn_type)
+        elif gate_type == 5:
+            self.gpnn = GPNN(input_size, hidden_size, act_set=("sigmoid", "tanh", "relu"), gpnn_type=gpnn_type)
+        else:
+            self.gpnn = GPNN(input_size, 4 * hidden_size, act_set=("sigmoid", "tanh", "relu"), gpnn_type=gpnn_type)
         s = 1.0 / math.sqrt(hidden_size)
         self.weights_ih = _uniform((4 * hidden_size, input_size), -s, s)
         self.bias_ih = nn.Parameter(torch.zeros(4 * hidden_size))

@@ -555,6 +555,19 @@ def gp_lstm_cell(acc5: torch.Tensor, coef: torch.Tensor, gate_type: int, lengths
                                      _stream()), "blm_gp_lstm_cell")
 
 
+def lstm_cell_step(acc4: torch.Tensor, lengths: torch.Tensor, t: int, c: torch.Tensor, h: torch.Tensor, h_op: Split,
+                   out_f32: Optional[torch.Tensor], out: Optional[Split], c_in: Optional[torch.Tensor] = None) -> None:
+    """One timestep of the plain cell from pre-activations acc4 [B, 4H] (see ``blm_lstm_cell_step``); c, h in place."""
+    B, H = h.shape
+    assert acc4.stride(1) == 1 and acc4.shape[1] >= 4 * H and c.is_contiguous() and h.is_contiguous()
+    assert c_in is None or (c_in.is_contiguous() and c_in.shape == c.shape)
+    with _op("lstm_cell_step", 1):
+        check(lib().blm_lstm_cell_step(_ptr(acc4), acc4.stride(0), _ptr(c_in), _ptr(lengths), t, B, H, _ptr(c), _ptr(h),
+                                       _ptr(h_op.hi), _ptr(h_op.lo), _ptr(out_f32),
+                                       _ptr(None if out is None else out.hi), _ptr(None if out is None else out.lo),
+                                       _stream()), "blm_lstm_cell_step")
+
+
 # ------------------------------------------------------------------ fine-tune step (backward twins)
 def _ld8(n: int) -> int:
     return (n + 7) // 8 * 8

@@ -807,6 +807,10 @@ class FineTuner:
                     layers.append({"kind": "plain", "pre": pre, "mi": mi, "mod": member,
                                    "names": {k: f"{pre}{k}_l{l}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}})
             elif getattr(member, "kind", "") == "gp":
+                if member.gate_type >= 5:
+                    raise _lib.BlmError(f"fine-tuning a GP-LSTM with gate type {member.gate_type} (GP unit on the cell state / "
+                                        "recurrent / input product, model.py:1745-1750,1763-1764) is not implemented; gate "
+                                        "types 1-4 train, 5-7 are rescoring-only")
                 layers.append({"kind": "gp", "pre": pre, "mi": mi, "mod": member})
             else:
                 layers.append({"kind": "v", "pre": pre, "mi": mi, "mod": member,

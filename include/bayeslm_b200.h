@@ -380,6 +380,13 @@ int blm_gp_lstm_cell(const float* acc5, int64_t ld, const float* coef, int32_t n
                      const int32_t* lengths, int32_t t, int64_t B, int32_t H, float* c, float* h,
                      blm_bf16* h_hi, blm_bf16* h_lo, float* out_f32, blm_bf16* out_hi, blm_bf16* out_lo,
                      blm_stream stream);
+/* Plain cell update for one timestep from the four gate pre-activations acc4 [B, 4H] (ld): the step of the GP-LSTM
+ * gate types 5-7, whose GP unit sits outside the gate nonlinearities (model.py:1745-1750, 1763-1764) and is a
+ * blm_gemm with the BLM_ACT_GPMIX epilogue.  c_in (may be null): the cell state the update starts from when it is
+ * not c itself -- gate type 5, c passed through the GP unit first; c is written for live rows only.          */
+int blm_lstm_cell_step(const float* acc4, int64_t ld, const float* c_in, const int32_t* lengths, int32_t t, int64_t B,
+                       int32_t H, float* c, float* h, blm_bf16* h_hi, blm_bf16* h_lo, float* out_f32,
+                       blm_bf16* out_hi, blm_bf16* out_lo, blm_stream stream);
 
 /* ------------------------------------------------- fine-tune step (train.py:306-438)
  * Backward twins of the kernels above and the optimiser.  The contractions of the backward pass

@@ -344,7 +344,8 @@ def rnn_forward(sd: SD, tokens: Tensor, hidden: Tuple[Tensor, Tensor], cfg: Conf
 
 # ---------------------------------------------------------------- GP-LSTM / Variational-LSTM cells
 LSTM_GP_ACTS = {1: ("sigmoid", "tanh", "relu"), 2: ("sigmoid",), 3: ("sigmoid", "tanh", "relu"),
-                4: ("sigmoid", "tanh", "relu")}   # act_set per gate_type, model.py:1690-1697 (+ GPNN default 1787)
+                4: ("sigmoid", "tanh", "relu"), 5: ("sigmoid", "tanh", "relu"), 6: ("sigmoid", "tanh", "relu"),
+                7: ("sigmoid", "tanh", "relu")}   # act_set per gate_type, model.py:1690-1697 (+ GPNN default 1787)
 
 
 def gp_lstm_layout(gauss_pos: str) -> List[Tuple[str, int, int]]:
@@ -362,11 +363,16 @@ def gp_lstm_layout(gauss_pos: str) -> List[Tuple[str, int, int]]:
 
 def gp_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, gate_type: int, gpnn_type: int = 0,
                        eps: Optional[Dict[str, Tensor]] = None):
-    """GPLSTMCell.forward / Gplstm, model.py:1720-1777, gate_type 1..4:
-    gates = W_ih x + b_ih + W_hh h + b_ih (bias_ih twice, bias_hh never); the chosen gate is replaced by
-    GPNN(cat[x, h]) = sum_i coef[i] * act_i(W_g cat[x, h] + b_g).  ``eps`` = {'coef','weights','bias'}: the GP unit's
-    parameters sampled ONCE per forward call (sample_parameters at model.py:1721-1723; used only when the unit is in
-    training mode with .sample set, model.py:1876-1883); None = posterior means."""
+    """GPLSTMCell.forward / Gplstm, model.py:1720-1777.
+    gate_type 1..4: gates = W_ih x + b_ih + W_hh h + b_ih (bias_ih twice, bias_hh never); the chosen gate is replaced by
+    GPNN(cat[x, h]) = sum_i coef[i] * act_i(W_g cat[x, h] + b_g).
+    gate_type 5 ("cell"): the same gates, and the cell state passes through the GP unit first, c <- GPNN(c)
+    (model.py:1763-1764; GPNN(input_size -> H), so input_size must equal H).
+    gate_type 6 ("hidden"): gates = W_ih x + b_ih + GPNN(h), GPNN(input_size -> 4H) in place of the recurrent product
+    (model.py:1747-1748).  gate_type 7 ("inputs"): gates = GPNN(x) + W_hh h + b_ih (model.py:1749-1750).
+    ``eps`` = {'coef','weights','bias'}: the GP unit's parameters sampled ONCE per forward call (sample_parameters at
+    model.py:1721-1723; used only when the unit is in training mode with .sample set, model.py:1876-1883); None =
+    posterior means."""
     acts = LSTM_GP_ACTS[gate_type]
     coef, wg, bg = sd[pre + "gpnn.coef_mean"], sd[pre + "gpnn.weights_mean"], sd[pre + "gpnn.bias_mean"]
     if eps is not None:
@@ -375,16 +381,28 @@ def gp_lstm_cell_layer(x: Tensor, h: Tensor, c: Tensor, sd: SD, pre: str, gate_t
         if gpnn_type in (2, 3):
             wg = wg + torch.exp(sd[pre + "gpnn.weights_lgstd"]) * eps["weights"]
             bg = bg + torch.exp(sd[pre + "gpnn.bias_lgstd"]) * eps["bias"]
+
+    def unit(v):
+        z = F.linear(v, wg, bg)
+        return sum(getattr(torch, a)(z) * coef[k] for k, a in enumerate(acts))
+
+    w_ih, w_hh, b_ih = sd[pre + "weights_ih"], sd[pre + "weights_hh"], sd[pre + "bias_ih"]
     outs = []
     for t in range(x.shape[0]):
-        gates = F.linear(x[t], sd[pre + "weights_ih"], sd[pre + "bias_ih"]) + F.linear(h, sd[pre + "weights_hh"], sd[pre + "bias_ih"])
+        if gate_type == 6:
+            gates = F.linear(x[t], w_ih, b_ih) + unit(h)
+        elif gate_type == 7:
+            gates = unit(x[t]) + F.linear(h, w_hh, b_ih)
+        else:
+            gates = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_ih)
         i, f, g, o = gates.chunk(4, 1)
-        z = F.linear(torch.cat([x[t], h], -1), wg, bg)
-        gp = sum(getattr(torch, a)(z) * coef[k] for k, a in enumerate(acts))
+        gp = unit(torch.cat([x[t], h], -1)) if gate_type <= 4 else None
         i = gp if gate_type == 1 else torch.sigmoid(i)
         f = gp if gate_type == 2 else torch.sigmoid(f)
         g = gp if gate_type == 3 else torch.tanh(g)
         o = gp if gate_type == 4 else torch.sigmoid(o)
+        if gate_type == 5:
+            c = unit(c)
         c = f * c + i * g
         h = o * torch.tanh(c)
         outs.append(h)

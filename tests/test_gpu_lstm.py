@@ -145,7 +145,7 @@ def test_many_rows_ragged_lengths_two_sessions():
 
 
 CELL_FIXTURES = ["gauss_lstm_31", "gauss_lstm_23", "gauss_lstm_13", "gauss_lstm_43", "gauss_lstm_333",
-                 "gauss_lstm_3330", "v_lstm_11", "v_lstm_01"]
+                 "gauss_lstm_3330", "gauss_lstm_51", "gauss_lstm_62", "gauss_lstm_73", "gauss_lstm_6350", "v_lstm_11", "v_lstm_01"]
 
 
 @pytest.mark.parametrize("name", CELL_FIXTURES)
@@ -166,7 +166,7 @@ def test_gp_and_variational_cells_match_reference_golden(golden, name):
                 assert abs(float(cell.gpnn.kl_divergence()) - ref) <= 1e-4 * abs(ref)
 
 
-@pytest.mark.parametrize("name", ["gauss_lstm_31", "gauss_lstm_3330", "v_lstm_11"])
+@pytest.mark.parametrize("name", ["gauss_lstm_31", "gauss_lstm_3330", "gauss_lstm_73", "gauss_lstm_6350", "v_lstm_11"])
 def test_cell_models_session_scoring_matches_oracle(golden, name):
     """The session scheduler (hidden carry through hypothesis #0, ragged lock-step batches) with GP / V cells
     against the oracle's restatement of the reference scoring loop."""
