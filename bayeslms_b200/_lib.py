@@ -116,6 +116,7 @@ SIGNATURES = {
     "blm_colsum_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _f, _i32, _p, _p, _p]),
     "blm_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),
     "blm_layernorm_bwd": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _i32, _p, _p]),
+    "blm_layernorm_bwd_ex": (C.c_int, [_p, _p, _p, _f, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p]),
     "blm_mha_causal_bwd": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _p, _i64, _p]),
     "blm_mha_causal_bwd_tc": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _i32, _i32, _f, _i32, _p, _i64, _p]),
     "blm_dropout": (C.c_int, [_p, _i64, C.POINTER(DropoutDesc), _p, _p, _p, _p, _p]),

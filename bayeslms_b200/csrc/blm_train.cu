@@ -213,14 +213,19 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, float eps, long long M,
                                                             int d, float* __restrict__ dx,
-                                                            float* __restrict__ partial /* [grid, 2, d] */) {
-  extern __shared__ float sred[];  // [8 warps][2][d]
+                                                            float* __restrict__ partial /* [grid, NP, d] */,
+                                                            __nv_bfloat16* __restrict__ dx_hi = nullptr,
+                                                            __nv_bfloat16* __restrict__ dx_lo = nullptr, int NP = 2) {
+  // NP == 3: a third column sum, of dx itself -- the bias gradient of the projection that feeds this LayerNorm's
+  // residual branch (dbias = colsum(dY) and dY = dx) -- leaves with dgamma / dbeta; dx_hi / dx_lo: the bf16 operand
+  // copies of dx for the dgrad / wgrad GEMMs that follow (one split launch and one colsum launch less per LayerNorm)
+  extern __shared__ float sred[];  // [8 warps][NP][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long warps = static_cast<long long>(gridDim.x) * 8;
   const float inv_d = 1.0f / static_cast<float>(d);
-  float4 ag[MAXV], ab[MAXV];
+  float4 ag[MAXV], ab[MAXV], ax[MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long m = static_cast<long long>(blockIdx.x) * 8 + warp; m < M; m += warps) {
     const float* xr = x + m * d;
     const float* dr = dy + m * d;
@@ -271,6 +276,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.z = rstd * (w[i].z - m1 - v[i].z * m2);
         o.w = rstd * (w[i].w - m1 - v[i].w * m2);
         *reinterpret_cast<float4*>(dx + m * d + c) = o;
+        ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
+        if (dx_hi) {
+          const uint32_t h0 = pack_bf16x2(o.x, o.y), h1 = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx_hi + m * d + c) = make_uint2(h0, h1);
+          if (dx_lo) {
+            const uint32_t l0 = pack_bf16x2(o.x - __uint_as_float(h0 << 16), o.y - __uint_as_float(h0 & 0xffff0000u));
+            const uint32_t l1 = pack_bf16x2(o.z - __uint_as_float(h1 << 16), o.w - __uint_as_float(h1 & 0xffff0000u));
+            *reinterpret_cast<uint2*>(dx_lo + m * d + c) = make_uint2(l0, l1);
+          }
+        }
       }
     }
   }
@@ -278,17 +293,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      *reinterpret_cast<float4*>(sred + (warp * 2 + 0) * d + c) = ag[i];
-      *reinterpret_cast<float4*>(sred + (warp * 2 + 1) * d + c) = ab[i];
+      *reinterpret_cast<float4*>(sred + (warp * NP + 0) * d + c) = ag[i];
+      *reinterpret_cast<float4*>(sred + (warp * NP + 1) * d + c) = ab[i];
+      if (NP == 3) *reinterpret_cast<float4*>(sred + (warp * NP + 2) * d + c) = ax[i];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * d; c += 256) {
+  for (int c = threadIdx.x; c < NP * d; c += 256) {
     const int which = c / d, col = c - which * d;
     float t = 0.0f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += sred[(wv * 2 + which) * d + col];
-    partial[(static_cast<long long>(blockIdx.x) * 2 + which) * d + col] = t;
+    for (int wv = 0; wv < 8; ++wv) t += sred[(wv * NP + which) * d + col];
+    partial[(static_cast<long long>(blockIdx.x) * NP + which) * d + col] = t;
   }
 }
 
@@ -297,29 +313,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // dependent L2 round trips: 25 us for a 12 KB result, 6.5 % of the fine-tune step, profiles/r02a.)
 __global__ void __launch_bounds__(256) layernorm_bwd_fold_kernel(const float* __restrict__ partial, int blocks, int d,
                                                                  int accumulate, float* __restrict__ dgamma,
-                                                                 float* __restrict__ dbeta) {
+                                                                 float* __restrict__ dbeta, float* __restrict__ dxsum = nullptr,
+                                                                 int dxsum_accumulate = 0) {
   __shared__ float red[8][32];
+  const int NP = dxsum ? 3 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 32 + lane;      // column of the [2, d] result
+  const int c = blockIdx.x * 32 + lane;      // column of the [NP, d] result
   float t0 = 0.0f, t1 = 0.0f;
-  if (c < 2 * d) {
+  if (c < NP * d) {
     const float* p = partial + c;
     int b = warp;
     for (; b + 8 < blocks; b += 16) {
-      t0 += p[static_cast<long long>(b) * 2 * d];
-      t1 += p[static_cast<long long>(b + 8) * 2 * d];
+      t0 += p[static_cast<long long>(b) * NP * d];
+      t1 += p[static_cast<long long>(b + 8) * NP * d];
     }
-    if (b < blocks) t0 += p[static_cast<long long>(b) * 2 * d];
+    if (b < blocks) t0 += p[static_cast<long long>(b) * NP * d];
   }
   red[warp][lane] = t0 + t1;
   __syncthreads();
-  if (warp == 0 && c < 2 * d) {
+  if (warp == 0 && c < NP * d) {
     float t = 0.0f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w][lane];
     const int which = c / d, col = c - which * d;
-    float* out = which == 0 ? dgamma : dbeta;
-    out[col] = accumulate ? out[col] + t : t;
+    float* out = which == 0 ? dgamma : which == 1 ? dbeta : dxsum;
+    const int acc = which == 2 ? dxsum_accumulate : accumulate;
+    out[col] = acc ? out[col] + t : t;
   }
 }
 
@@ -899,7 +918,10 @@ int train_init() {
 
 static int colsum_row_splits(int64_t M, int64_t N) {
   const int64_t col_blocks = (N + 127) / 128;
-  int64_t splits = (2 * (blm::num_sms() > 0 ? blm::num_sms() : 148) + col_blocks - 1) / col_blocks;
+  // wide matrices (the [tokens, V] logit gradient: 235 column blocks) need more CTAs per SM to cover the latency of
+  // their one-load-per-row loops: 2 row splits ran at 1.45 TB/s
+  const int64_t per_sm = col_blocks >= 64 ? 8 : 2;
+  int64_t splits = (per_sm * (blm::num_sms() > 0 ? blm::num_sms() : 148) + col_blocks - 1) / col_blocks;
   const int64_t max_by_rows = (M + 31) / 32;  // at least 32 rows per CTA
   if (splits > max_by_rows) splits = max_by_rows;
   if (splits < 1) splits = 1;
@@ -986,27 +1008,40 @@ int64_t blm_layernorm_bwd_workspace_bytes(int64_t M, int32_t d) {
 int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t M, int32_t d,
                       float* dx, float* dgamma, float* dbeta, int32_t accumulate, void* workspace,
                       blm_stream stream) {
+  return blm_layernorm_bwd_ex(dy, x, gamma, eps, M, d, dx, nullptr, nullptr, dgamma, dbeta, accumulate, nullptr, 0, workspace,
+                              stream);
+}
+
+int blm_layernorm_bwd_ex(const float* dy, const float* x, const float* gamma, float eps, int64_t M, int32_t d, float* dx,
+                         blm_bf16* dx_hi, blm_bf16* dx_lo, float* dgamma, float* dbeta, int32_t accumulate, float* dxsum,
+                         int32_t dxsum_accumulate, void* workspace, blm_stream stream) {
   using namespace blm;
   BLM_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && workspace && M > 0, BLM_ERR_ARG, "bad layernorm_bwd arguments");
   BLM_REQUIRE((d % 4) == 0 && d > 0 && d <= 1024, BLM_ERR_SHAPE, "layernorm_bwd width %d must be a multiple of 4 and <= 1024", d);
-  BLM_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx) && aligned16(workspace), BLM_ERR_ALIGN,
-              "layernorm_bwd pointers must be 16-byte aligned");
+  BLM_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx) && aligned16(workspace) &&
+                  (reinterpret_cast<uintptr_t>(dx_hi) & 7u) == 0 && (reinterpret_cast<uintptr_t>(dx_lo) & 7u) == 0,
+              BLM_ERR_ALIGN, "layernorm_bwd pointers must be 16-byte aligned (bf16 copies: 8-byte)");
+  BLM_REQUIRE(!dx_lo || dx_hi, BLM_ERR_ARG, "dx_lo requires dx_hi");
   const int blocks = ln_bwd_blocks(M);
   float* partial = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
-  const size_t smem = sizeof(float) * 8 * 2 * d;
+  const int NP = dxsum ? 3 : 2;
+  const size_t smem = sizeof(float) * 8 * NP * d;
   static bool attr = false;
   if (!attr) {
-    BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+    BLM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
     attr = true;
   }
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dx_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(dx_lo);
   if (d <= 512)
-    layernorm_bwd_kernel<4><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
+    layernorm_bwd_kernel<4><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial, hi, lo, NP);
   else
-    layernorm_bwd_kernel<8><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial);
+    layernorm_bwd_kernel<8><<<blocks, 256, smem, st>>>(dy, x, gamma, eps, M, d, dx, partial, hi, lo, NP);
   BLM_CHECK_CUDA(cudaGetLastError());
-  layernorm_bwd_fold_kernel<<<(2 * d + 31) / 32, 256, 0, st>>>(partial, blocks, d, accumulate, dgamma, dbeta);
+  layernorm_bwd_fold_kernel<<<(NP * d + 31) / 32, 256, 0, st>>>(partial, blocks, d, accumulate, dgamma, dbeta, dxsum,
+                                                               dxsum_accumulate);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

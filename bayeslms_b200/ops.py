@@ -655,16 +655,22 @@ def _workspace(kind: str, nbytes: int, device, zero: bool = False) -> torch.Tens
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, dgamma: torch.Tensor,
-                  dbeta: torch.Tensor, *, accumulate: bool = False) -> torch.Tensor:
-    """Returns dx; x is the LayerNorm input.  dgamma / dbeta are written (or accumulated) in place."""
+                  dbeta: torch.Tensor, *, accumulate: bool = False, prec: Optional[str] = None,
+                  dxsum: Optional[torch.Tensor] = None, dxsum_accumulate: bool = False):
+    """Returns dx; x is the LayerNorm input.  dgamma / dbeta are written (or accumulated) in place.  ``prec``: also
+    return the bf16 (hi[, lo]) copy of dx -> (dx, Split); ``dxsum`` [d] (+)= column sums of dx (the bias gradient of
+    the projection in front of the residual add)."""
     M, d = x.shape
     assert dy.is_contiguous() and x.is_contiguous()
     dx = torch.empty_like(x)
+    sp = empty_split(M, d, prec, x.device) if prec is not None else None
     ws = _workspace("ln_bwd", lib().blm_layernorm_bwd_workspace_bytes(M, d), x.device)
     with _op("layernorm_bwd", 2):
-        check(lib().blm_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), eps, M, d, _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                      int(accumulate), _ptr(ws), _stream()), "blm_layernorm_bwd")
-    return dx
+        check(lib().blm_layernorm_bwd_ex(_ptr(dy), _ptr(x), _ptr(gamma), eps, M, d, _ptr(dx),
+                                         _ptr(None if sp is None else sp.hi), _ptr(None if sp is None else sp.lo),
+                                         _ptr(dgamma), _ptr(dbeta), int(accumulate), _ptr(dxsum), int(dxsum_accumulate),
+                                         _ptr(ws), _stream()), "blm_layernorm_bwd_ex")
+    return dx if prec is None else (dx, sp)
 
 
 def mha_causal_bwd(qkv: torch.Tensor, dout: torch.Tensor, seq_offsets: torch.Tensor, nhead: int, max_len: int,

@@ -501,11 +501,19 @@ class FineTuner:
         for li in range(len(saved) - 1, -1, -1):
             S, layer, pre = saved[li], m.transformerlayers[li], f"transformerlayers.{li}."
             kind, a = S["kind"], layer.self_attn
+            # without dropout2 / the variational noise dy2 IS the gradient of linear2's output: the LayerNorm backward then
+            # also writes its bf16 operand copy and its column sums (= d linear2.bias)
+            ln2_fused = S["drop_d2"] is None and kind != "v"
+            bias2_done = ln2_fused and kind != "bayes_ffn"
             dy2 = ops.layernorm_bwd(dx, S["y2"], layer.norm2.weight.detach(), layer.norm2.eps, g[pre + "norm2.weight"],
-                                    g[pre + "norm2.bias"])
+                                    g[pre + "norm2.bias"], prec=prec if ln2_fused else None,
+                                    dxsum=g[pre + "linear2.bias"] if bias2_done else None)
             # gradient of the FFN branch = dropout2's mask on dy2 (the residual branch keeps dy2 itself)
             dfs = None
-            if S["drop_d2"] is None:
+            if ln2_fused:
+                dy2, dfs = dy2
+                dbr = dy2
+            elif S["drop_d2"] is None:
                 dbr = dy2
             elif kind == "v":
                 dbr = ops.dropout(dy2, S["drop_d2"])[0]
@@ -546,7 +554,8 @@ class FineTuner:
             else:
                 with self._aside(dfs, df, S["hs"]):
                     self._wgrad(dft, ht, g[pre + "linear2.weight"], "ffn2")
-                    ops.colsum(df, g[pre + "linear2.bias"])
+                    if not bias2_done:
+                        ops.colsum(df, g[pre + "linear2.bias"])
             # FFN1
             dx1 = self._f32(M, d)
             _gemm(dz1s, S["w1_t"], prec=prec, resid=dy2, out_f32=dx1, tag="dgrad:ffn1")
@@ -558,12 +567,16 @@ class FineTuner:
                     self._wgrad(dz1t, x1t, g[pre + "linear1.weight"], "ffn1")
                     ops.colsum(dz1, g[pre + "linear1.bias"])
             # LayerNorm 1, output projection, attention, QKV projection
+            ln1_fused = S["drop_d1"] is None
+            bias_o_done = ln1_fused and kind != "bayes_mha"
             dy1 = ops.layernorm_bwd(dx1, S["y1"], layer.norm1.weight.detach(), layer.norm1.eps, g[pre + "norm1.weight"],
-                                    g[pre + "norm1.bias"])
+                                    g[pre + "norm1.bias"], prec=prec if ln1_fused else None,
+                                    dxsum=g[pre + "self_attn.o_net.bias"] if bias_o_done else None)
             if S["drop_d1"] is not None:     # gradient of the attention branch = dropout1's mask on dy1
                 do1, dy1s = ops.dropout(dy1, S["drop_d1"], prec=prec)
             else:
-                do1, dy1s = dy1, ops.split(dy1, prec)
+                dy1, dy1s = dy1
+                do1 = dy1
             datt = self._f32(M, d)
             _gemm(dy1s, S["wo_t"], prec=prec, out_f32=datt, tag="dgrad:o_net")
             dy1t, attt = _tsplit(do1, prec, dy1s), _tbf16(S["atts"], prec)
@@ -579,7 +592,8 @@ class FineTuner:
             else:
                 with self._aside(dy1s, do1, S["atts"]):
                     self._wgrad(dy1t, attt, g[pre + "self_attn.o_net.weight"], "o_net")
-                    ops.colsum(do1, g[pre + "self_attn.o_net.bias"])
+                    if not bias_o_done:
+                        ops.colsum(do1, g[pre + "self_attn.o_net.bias"])
             dqkv = ops.mha_causal_bwd(S["qkv32"], datt, offs, nhead, T, scale_q, prec=prec, drop=S["drop_attn"])
             dx = self._f32(M, d)
             dqkvs = ops.split(dqkv, prec)

@@ -419,6 +419,14 @@ int64_t blm_layernorm_bwd_workspace_bytes(int64_t M, int32_t d);
 int blm_layernorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t M,
                       int32_t d, float* dx, float* dgamma, float* dbeta, int32_t accumulate,
                       void* workspace, blm_stream stream);
+/* The same pass with two by-products of the step it sits in: dx_hi / dx_lo (optional), the bf16 operand copies of dx
+ * for the dgrad / wgrad GEMMs that consume it, and dxsum [d] (optional) (+)= sum_m dx[m, :] -- dx is the gradient of
+ * the projection output that was added to the residual stream, so this is that projection's bias gradient
+ * (`linear2.bias` / `o_net.bias`, model.py:1039-1046).  One split and one column-sum launch less per LayerNorm. */
+int blm_layernorm_bwd_ex(const float* dy, const float* x, const float* gamma, float eps, int64_t M, int32_t d,
+                         float* dx, blm_bf16* dx_hi, blm_bf16* dx_lo, float* dgamma, float* dbeta,
+                         int32_t accumulate, float* dxsum, int32_t dxsum_accumulate, void* workspace,
+                         blm_stream stream);
 
 /* Backward of blm_mha_causal: qkv fp32 [M, 3d] (q already scaled), dout [M, d] -> dqkv [M, 3d];
  * the q block of dqkv is multiplied by q_scale (gradient w.r.t. the unscaled projection,
