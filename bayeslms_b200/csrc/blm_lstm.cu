@@ -240,6 +240,79 @@ __device__ __forceinline__ void publish_initial_state(const LstmParams& p, int r
   }
 }
 
+// The pair kernel's gate math, software-pipelined: the operands of a group of 8 hidden units that do NOT come from the
+// tensor core -- gates_x (4 gates x 8 units) and the cell state -- are requested one group ahead (and, for the first
+// group of a step, before the accumulator is even waited for), so their HBM / L2 latency runs under the previous
+// group's arithmetic instead of being exposed four times per tile (8 of 31 us per step at B = 2048).
+struct GateIn {
+  float4 x[8];   // gates_x: [gate][2 x float4]
+  float4 c[2];   // cell state of the 8 units
+};
+__device__ __forceinline__ void load_gate_in(const LstmParams& p, GateIn& in, int t, int b, int unit, bool live) {
+  if (!live) return;
+  const long long m = static_cast<long long>(t) * p.B + b;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    in.x[2 * g] = __ldg(gx_f4(p, m, g * p.H + unit));
+    in.x[2 * g + 1] = __ldg(gx_f4(p, m, g * p.H + unit + 4));
+  }
+  in.c[0] = *c_f4(p, b, unit);
+  in.c[1] = *c_f4(p, b, unit + 4);
+}
+// acc: the recurrent product [gate][8 units] of the row.  Same arithmetic and stores as cell_update.
+__device__ __forceinline__ void cell_group(const LstmParams& p, const GateIn& in, const float (&acc)[32], int t, int b,
+                                           int unit, bool live, bool last, int cur, int nxt) {
+  const int H = p.H;
+  const long long o = static_cast<long long>(b) * H + unit;
+  const long long ot = (static_cast<long long>(t) * p.B + b) * H + unit;
+  __nv_bfloat16* nh = p.hbuf[nxt][0] + o;
+  __nv_bfloat16* nl = p.nsplit == 3 ? p.hbuf[nxt][1] + o : nullptr;
+  if (live) {
+    float c[8], h[8];
+    *reinterpret_cast<float4*>(c) = in.c[0];
+    *reinterpret_cast<float4*>(c + 4) = in.c[1];
+    const float* x = reinterpret_cast<const float*>(in.x);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float ig = fast_sigmoid(acc[u] + x[u]);
+      const float fg = fast_sigmoid(acc[8 + u] + x[8 + u]);
+      const float gg = fast_tanh(acc[16 + u] + x[16 + u]);
+      const float og = fast_sigmoid(acc[24 + u] + x[24 + u]);
+      c[u] = fmaf(fg, c[u], ig * gg);
+      h[u] = og * fast_tanh(c[u]);
+    }
+    *c_f4(p, b, unit) = *reinterpret_cast<float4*>(c);
+    *c_f4(p, b, unit + 4) = *reinterpret_cast<float4*>(c + 4);
+    if (last) {
+      *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
+      *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
+      *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
+      *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
+    }
+    store_h8(nh, nl, h);
+    if (p.c_seq) {
+      *reinterpret_cast<float4*>(p.c_seq + ot) = *reinterpret_cast<float4*>(c);
+      *reinterpret_cast<float4*>(p.c_seq + ot + 4) = *reinterpret_cast<float4*>(c + 4);
+    }
+    if (p.out_f32) {
+      *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
+      *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
+    }
+    if (p.out_hi) store_h8(p.out_hi + ot, p.out_lo ? p.out_lo + ot : nullptr, h);
+  } else {
+    *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(p.hbuf[cur][0] + o);
+    if (nl) *reinterpret_cast<uint4*>(nl) = *reinterpret_cast<const uint4*>(p.hbuf[cur][1] + o);
+    if (p.out_f32) {
+      *reinterpret_cast<float4*>(p.out_f32 + ot) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (p.out_hi) {
+      *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
+      if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + ot) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 // kCL > 1: kCL CTAs with the same batch block (consecutive unit blocks) form a cluster; every h tile is
 // fetched ONCE per cluster -- CTA r loads rows [32 r, 32 r + 32) of the 128-row tile with TMA multicast
 // into all kCL CTAs -- and a ring slot is released by multicast tcgen05.commit from all kCL MMA warps.
@@ -434,6 +507,26 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
       __syncwarp();
     } else if (warp >= 4) {
       const int lane_grp = warp & 3;
+      if (kCL == 1 && n_mt == 1) {
+        // one tile (the hypothesis-#0 chains, B <= 128): the step is pure latency, so both epilogue warp sets work on
+        // the tile, one 8-unit group each, and request gates_x / the cell state BEFORE they wait for the accumulator
+        const int b = mt0 * 128 + lane_grp * 32 + lane;
+        const int len = b < B ? min(__ldg(p.lengths + b), p.T) : 0;
+        for (int u8 = ((warp - 4) >> 2) * 8; u8 < kU; u8 += 16) {
+          GateIn gin;
+          if (b < B) load_gate_in(p, gin, t, b, j * kU + u8, t < len);
+          mbar_wait(&tfull_bar[0], static_cast<uint32_t>(t & 1));
+          tcgen05_fence_after();
+          float acc[32];
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(g * kU + u8),
+                         acc + 8 * g);
+          tmem_ld_wait();
+          if (b < B) cell_group(p, gin, acc, t, b, j * kU + u8, t < len, t + 1 == len, cur, nxt);
+        }
+      } else
       for (int mt = (warp - 4) >> 2; mt < n_mt; mt += 2) {
         mbar_wait(&tfull_bar[mt], static_cast<uint32_t>(t & 1));
         tcgen05_fence_after();
@@ -460,79 +553,6 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_layer_kernel(const __grid_c
 
   if constexpr (kCL > 1) cluster_sync_all();  // no multicast / remote arrive may target a CTA that has exited
   if (warp == 2) tmem_dealloc<512>(tmem_base);
-}
-
-// The pair kernel's gate math, software-pipelined: the operands of a group of 8 hidden units that do NOT come from the
-// tensor core -- gates_x (4 gates x 8 units) and the cell state -- are requested one group ahead (and, for the first
-// group of a step, before the accumulator is even waited for), so their HBM / L2 latency runs under the previous
-// group's arithmetic instead of being exposed four times per tile (8 of 31 us per step at B = 2048).
-struct GateIn {
-  float4 x[8];   // gates_x: [gate][2 x float4]
-  float4 c[2];   // cell state of the 8 units
-};
-__device__ __forceinline__ void load_gate_in(const LstmParams& p, GateIn& in, int t, int b, int unit, bool live) {
-  if (!live) return;
-  const long long m = static_cast<long long>(t) * p.B + b;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    in.x[2 * g] = __ldg(gx_f4(p, m, g * p.H + unit));
-    in.x[2 * g + 1] = __ldg(gx_f4(p, m, g * p.H + unit + 4));
-  }
-  in.c[0] = *c_f4(p, b, unit);
-  in.c[1] = *c_f4(p, b, unit + 4);
-}
-// acc: the recurrent product [gate][8 units] of the row.  Same arithmetic and stores as cell_update.
-__device__ __forceinline__ void cell_group(const LstmParams& p, const GateIn& in, const float (&acc)[32], int t, int b,
-                                           int unit, bool live, bool last, int cur, int nxt) {
-  const int H = p.H;
-  const long long o = static_cast<long long>(b) * H + unit;
-  const long long ot = (static_cast<long long>(t) * p.B + b) * H + unit;
-  __nv_bfloat16* nh = p.hbuf[nxt][0] + o;
-  __nv_bfloat16* nl = p.nsplit == 3 ? p.hbuf[nxt][1] + o : nullptr;
-  if (live) {
-    float c[8], h[8];
-    *reinterpret_cast<float4*>(c) = in.c[0];
-    *reinterpret_cast<float4*>(c + 4) = in.c[1];
-    const float* x = reinterpret_cast<const float*>(in.x);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float ig = fast_sigmoid(acc[u] + x[u]);
-      const float fg = fast_sigmoid(acc[8 + u] + x[8 + u]);
-      const float gg = fast_tanh(acc[16 + u] + x[16 + u]);
-      const float og = fast_sigmoid(acc[24 + u] + x[24 + u]);
-      c[u] = fmaf(fg, c[u], ig * gg);
-      h[u] = og * fast_tanh(c[u]);
-    }
-    *c_f4(p, b, unit) = *reinterpret_cast<float4*>(c);
-    *c_f4(p, b, unit + 4) = *reinterpret_cast<float4*>(c + 4);
-    if (last) {
-      *reinterpret_cast<float4*>(p.cT + o) = *reinterpret_cast<float4*>(c);
-      *reinterpret_cast<float4*>(p.cT + o + 4) = *reinterpret_cast<float4*>(c + 4);
-      *reinterpret_cast<float4*>(p.hT + o) = *reinterpret_cast<float4*>(h);
-      *reinterpret_cast<float4*>(p.hT + o + 4) = *reinterpret_cast<float4*>(h + 4);
-    }
-    store_h8(nh, nl, h);
-    if (p.c_seq) {
-      *reinterpret_cast<float4*>(p.c_seq + ot) = *reinterpret_cast<float4*>(c);
-      *reinterpret_cast<float4*>(p.c_seq + ot + 4) = *reinterpret_cast<float4*>(c + 4);
-    }
-    if (p.out_f32) {
-      *reinterpret_cast<float4*>(p.out_f32 + ot) = *reinterpret_cast<float4*>(h);
-      *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = *reinterpret_cast<float4*>(h + 4);
-    }
-    if (p.out_hi) store_h8(p.out_hi + ot, p.out_lo ? p.out_lo + ot : nullptr, h);
-  } else {
-    *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(p.hbuf[cur][0] + o);
-    if (nl) *reinterpret_cast<uint4*>(nl) = *reinterpret_cast<const uint4*>(p.hbuf[cur][1] + o);
-    if (p.out_f32) {
-      *reinterpret_cast<float4*>(p.out_f32 + ot) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(p.out_f32 + ot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (p.out_hi) {
-      *reinterpret_cast<uint4*>(p.out_hi + ot) = make_uint4(0, 0, 0, 0);
-      if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + ot) = make_uint4(0, 0, 0, 0);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
