@@ -632,19 +632,32 @@ def colsum(x, out: torch.Tensor, *, scale: float = 1.0, accumulate: bool = False
 
 _ws_cache = {}
 CAPTURE_KEEP = []
+_capture_ws = {}
+
+
+def end_capture() -> None:
+    """Forget the scratch blocks handed out during a CUDA-graph capture (call when the capture has ended, or before a new
+    one begins): they belong to that graph's private pool."""
+    CAPTURE_KEEP.clear()
+    _capture_ws.clear()
 
 
 def _workspace(kind: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
-    """Scratch memory of one kernel family, cached per (device, stream) -- except while a CUDA graph is being captured:
-    a tensor allocated then lives in the graph's private pool, which is released with the graph, so caching it would
-    hand a dangling pointer to the next capture on the same (re-used) capture stream (found as an illegal address in a
-    later graph's replay).  Captured launches get a fresh block each; stream order keeps its re-use inside the graph
-    correct."""
+    """Scratch memory of one kernel family, cached per (device, stream).  While a CUDA graph is being captured the cache is
+    a separate one that lives only as long as the capture (``end_capture``): a tensor allocated then belongs to the
+    graph's private pool, which is released with the graph, so keeping it for the NEXT capture on the same (re-used)
+    capture stream hands out a dangling pointer (found as an illegal address in a later graph's replay).  Inside one
+    capture, launches of a family on the same stream are ordered, so they share their block -- a fresh zeroed block per
+    launch was 27 fill kernels per fine-tune step."""
     if torch.cuda.is_current_stream_capturing():
-        ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
-        # held until the capture ends (trainer clears the list): a capture may span two streams, and a block returned
-        # to the pool here could be re-issued to the other stream while this launch is still unordered against it
-        CAPTURE_KEEP.append(ws)
+        key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
+        ws = _capture_ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+            # held until the capture ends: a capture may span two streams, and a block returned to the pool here could be
+            # re-issued to the other stream while this launch is still unordered against it
+            CAPTURE_KEEP.append(ws)
+            _capture_ws[key] = ws
         return ws
     key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)

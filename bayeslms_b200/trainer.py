@@ -1145,12 +1145,13 @@ class FineTuner:
             cap["eps"]["embed"] = buf
             cap["fill"].append((buf, _TID["embed"], 1.0))
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)   # dropout key of the replay, written per step
+        ops.end_capture()
         self._capturing = True
         try:
             self._capture_graphs(cap, T, B)
         finally:
             self._capturing = False
-            ops.CAPTURE_KEEP.clear()
+            ops.end_capture()
         return self
 
     def _capture_graphs(self, cap, T: int, B: int):
@@ -1222,6 +1223,7 @@ class FineTuner:
             torch.cuda.synchronize()
             if not state["cut"]:
                 cap["split"] = None
+        ops.end_capture()      # the optimiser graph has its own pool: no scratch block of the first graph is reused in it
         cap["g2"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cap["g2"]):
             ops.reduce_sum(self.flat_g, self.norm_sq, squares=True)
