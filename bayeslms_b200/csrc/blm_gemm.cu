@@ -792,6 +792,8 @@ int gemm_init() {
   if ((rc = set_smem_attr_stg<256, kStages256, 0, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<128, kStages128, 0, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_stg<128, kStages128, 1, BLM_ACT_GELU_GRAD>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<128, kStages128, 1, BLM_ACT_GELU>()) != BLM_OK) return rc;
+  if ((rc = set_smem_attr_stg<128, kStages128, 1, BLM_ACT_GPMIX>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_NONE>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_GELU>()) != BLM_OK) return rc;
   if ((rc = set_smem_attr_chunk<BLM_ACT_GPMIX>()) != BLM_OK) return rc;
@@ -936,7 +938,7 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   // store transpose: pays for fp32 outputs (QKV fp32 228 -> 149 us at M = 65536); for bf16-only outputs the
   // extra shared-memory round trip costs more issue slots than the wider stores save (FFN1 479 -> 536 us)
   static const char* stg_env = getenv("BLM_STG");  // A/B switch for profiling: 0 = never, 1 = always
-  p.use_stg = stg_env ? atoi(stg_env) : (d->out_f32 != nullptr);
+  p.use_stg = stg_env ? atoi(stg_env) : (d->out_f32 != nullptr || (d->k_chunk > 0 && d->out_lo != nullptr));
   p.f32_rows32 = d->f32_rows32;
   if (d->drop && (d->drop->mask || d->drop->p > 0.0f)) {
     BLM_REQUIRE((d->N % 32) == 0 && d->act != BLM_ACT_SOFTMAX_GRAD && !d->f32_rows32, BLM_ERR_ARG,
@@ -1078,6 +1080,10 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
     p.x3 = triples ? 1 : 0;
     if (stg) return launch_stg<128, kStages128, 1>(p, st);
     if (gstg) return launch_stg<128, kStages128, 1, BLM_ACT_GELU_GRAD>(p, st);
+    // forward activations with a hi + lo (or fp32) output: the transposed stores pay here as well -- two bf16 tensors
+    // through row-per-thread 16-byte stores were 19 % of the precise FFN1 (813 vs 639 us hi only; 687 us transposed)
+    if (p.use_stg && !d->out_pre && d->act == BLM_ACT_GELU) return launch_stg<128, kStages128, 1, BLM_ACT_GELU>(p, st);
+    if (p.use_stg && !d->out_pre && d->act == BLM_ACT_GPMIX) return launch_stg<128, kStages128, 1, BLM_ACT_GPMIX>(p, st);
     switch (d->act) {
       case BLM_ACT_NONE: return launch_chunk<BLM_ACT_NONE>(p, st);
       case BLM_ACT_GELU: return launch_chunk<BLM_ACT_GELU>(p, st);
