@@ -906,7 +906,18 @@ int gemm_impl(const blm_gemm_desc* d, const GemmGen* gen, blm_stream stream) {
   long long total_k = 0;
   for (int s = 0; s < d->nseg && s < BLM_MAX_SEG; ++s) total_k += (d->K[s] + kBK - 1) / kBK * kBK;
   const bool chunked = d->k_chunk > 0 && total_k > d->k_chunk;
-  const bool use256 = !chunked && (d->N >= 256) && (static_cast<long long>(m_tiles) * n_tiles256 >= num_sms());
+  bool use256 = !chunked && (d->N >= 256) && (static_cast<long long>(m_tiles) * n_tiles256 >= num_sms());
+  if (use256) {
+    // few waves: compare the wave counts of both tile widths (a 128-wide tile costs a little more than half a 256-wide
+    // one).  QKV of the fine-tune step: 25 x 6 = 150 wide tiles on 148 SMs are TWO waves, 300 narrow ones 2.03 narrow
+    // waves = 1.65 wide-tile times.  From 4 wide waves up the wide tile always wins.
+    const long long sms = num_sms();
+    const long long t256 = static_cast<long long>(m_tiles) * n_tiles256;
+    const long long t128 = static_cast<long long>(m_tiles) * ((d->N + 127) / 128);
+    const long long w256 = (t256 + sms - 1) / sms, w128 = (t128 + sms - 1) / sms;
+    static const bool no_wave = getenv("BLM_GEMM_NO_WAVE_FIT") != nullptr;   // A/B switch
+    if (!no_wave && w256 <= 3 && 55 * w128 < 100 * w256) use256 = false;
+  }
   const int BN = use256 ? 256 : 128;
 
   GemmParams p;
