@@ -18,6 +18,16 @@
 //   * a grid-wide barrier (one atomic per CTA, bounded spin) separates the steps.
 // Rows past their own length (right padding) keep (h, c) untouched, so the final state is the
 // state after each row's last valid token (the hidden carry of score.py:271-274).
+//
+// Kernels in this file:
+//   lstm_layer_kernel<U, CL, SUB>  the form described above; used for batches of up to two 128-row tiles and for the
+//       hypothesis-#0 chains (one row per session), where it loads only the real rows, all K blocks at once, and
+//       both epilogue warp sets share the one tile (7.9 us per step at 12 rows);
+//   lstm_pair_kernel<U, SUB>       from three tiles up: cta_group::2 pairs (M = 256), per-tile step flags instead of the
+//       grid barrier, gate operands requested one 8-unit group ahead (20.9 us per step at B = 2048 in bf16 mode with
+//       U = 16; 97.6 us in precise mode with U = 8 and hi + lo slices resident).
+// The input projection gates_x and the running cell state are addressed in 32-row blocks (rows32_f4): one batch row per
+// thread is what the tensor-memory accumulator dictates, and row-major fp32 would make every warp access 32 lines.
 #include <stdlib.h>
 #include <string.h>
 
@@ -38,7 +48,7 @@ struct LstmParams {
   int a_box_bytes;        // bytes one h K block brings: box rows x 128 (a one-tile batch loads only its real rows)
   int whole_k;            // 1: small one-tile batch -- ALL K blocks of h_{t-1} are loaded at once, packed at a_box_bytes
                           // stride, and the MMAs run back to back: no ring round trips inside a step
-  int kb_stagger;         // 1: stagger the K-block order per CTA (A/B switch BLM_LSTM_NO_STAGGER)
+  int kb_stagger;         // 1: stagger the K-block order per CTA (experiment, BLM_LSTM_STAGGER=1)
   int unit_blocks;        // H / U
   int tiles_per_cta;      // 128-row batch tiles per CTA (batch split)
   const float* gates_x;   // [T, B, 4H]; gx_rows32: in 32-row blocks, [ceil(T B / 32)][H][32 rows][4 floats]
