@@ -401,3 +401,33 @@ def test_wave_quantised_chunks():
     assert waves(alt) <= waves(base)
     assert all(sum(lens[a:b]) > 6 * q - 28 for a, b in alt[:-1]) or alt == base
     assert _chunks_by_tokens(lens[:100], 65536, q) == _chunks_by_tokens(lens[:100], 65536)
+
+
+def test_ranking_agreement_counts_ties_at_the_stated_gap():
+    """synth.ranking_agreement: a 1-best that differs between two candidates closer than ``min_gap`` in the reference
+    scores is a tie at that tolerance (one_best_within_gap), a real flip is not."""
+    from bayeslms_b200 import synth
+    ref = [np.array([1.0, 1.01, 5.0]), np.array([2.0, 3.0, 4.0])]
+    got = [np.array([1.02, 1.0, 5.0]), np.array([2.0, 3.0, 4.0])]         # utterance 0: near-tie flipped
+    a = synth.ranking_agreement(got, ref, min_gap=0.05)
+    assert a["one_best"] == 0.5 and a["one_best_within_gap"] == 1.0 and a["pair_order"] == 1.0
+    assert abs(a["largest_flipped_gap"] - 0.01) < 1e-9
+    bad = [np.array([5.0, 1.0, 0.5]), np.array([2.0, 3.0, 4.0])]          # utterance 0: a real flip
+    b = synth.ranking_agreement(bad, ref, min_gap=0.05)
+    assert b["one_best_within_gap"] == 0.5 and b["pair_order"] < 1.0
+
+
+def test_rows32_layout_round_trip():
+    """ops.rows32_to_dense inverts the 32-row-block layout of blm_gemm_desc.f32_rows32 (pure index arithmetic)."""
+    from bayeslms_b200 import ops
+    M, N = 70, 24
+    dense = torch.arange(M * N, dtype=torch.float32).view(M, N)
+    pad = torch.zeros(96, N)
+    pad[:M] = dense
+    blocked = pad.view(3, 32, N // 4, 4).permute(0, 2, 1, 3).contiguous().view(96, N)
+    assert torch.equal(ops.rows32_to_dense(blocked, M), dense)
+    # element (m, col) sits at float offset ((m // 32) * (N // 4) + col // 4) * 128 + (m % 32) * 4 + col % 4
+    flat = blocked.reshape(-1)
+    for m, col in ((0, 0), (31, 23), (32, 5), (69, 20)):
+        off = ((m // 32) * (N // 4) + col // 4) * 128 + (m % 32) * 4 + col % 4
+        assert flat[off] == dense[m, col]
