@@ -107,6 +107,7 @@ SIGNATURES = {
     "blm_kl_workspace_bytes": (_i64, []),
     "blm_kl_gauss": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _f, _i32, _p, _p, _p]),
     "blm_gp_lstm_cell": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "blm_gp3_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     "blm_lstm_cell_step": (C.c_int, [_p, _i64, _p, _p, _i32, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "blm_transpose_split": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "blm_split_transpose": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _p]),

@@ -163,6 +163,48 @@ __global__ void gp_lstm_bwd_step_kernel(const float* __restrict__ acc5, long lon
   if (n_act > 2) dcoef[2 * H + u] += g2;
 }
 
+// Backward of the GP unit of the LSTM cells when it stands alone in front of the gates (gate types 5-7):
+//   h = sum_i coef[i, n] act_i(z), acts (sigmoid, tanh, relu)   (model.py:1787, 1893-1899)
+//   dz = dh . sum_i coef[i, n] act_i'(z),   dcoef[i, n] += sum_m dh[m, n] act_i(z[m, n])
+// One block per 32 columns walks all M rows (M = T B of a fine-tune step: thousands at most): fixed order, no atomics.
+__global__ void __launch_bounds__(256) gp3_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z,
+                                                      const float* __restrict__ coef, long long ld, long long M, int N,
+                                                      float* __restrict__ dz, __nv_bfloat16* __restrict__ dz_hi,
+                                                      __nv_bfloat16* __restrict__ dz_lo, float* __restrict__ dcoef) {
+  __shared__ float red[8][3][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+  if (n < N) {
+    const float c0 = __ldg(coef + n), c1 = __ldg(coef + N + n), c2 = __ldg(coef + 2 * N + n);
+    for (long long m = ty; m < M; m += 8) {
+      const long long o = m * ld + n;
+      const float zz = z[o], d = dh[o];
+      const float sg = 1.0f / (1.0f + expf(-zz)), th = tanhf(zz);
+      a0 += d * sg;
+      a1 += d * th;
+      a2 += d * fmaxf(zz, 0.0f);
+      const float v = d * (c0 * sg * (1.0f - sg) + c1 * (1.0f - th * th) + (zz > 0.0f ? c2 : 0.0f));
+      dz[o] = v;
+      if (dz_hi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        dz_hi[o] = h;
+        if (dz_lo) dz_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+  red[ty][0][tx] = a0;
+  red[ty][1][tx] = a1;
+  red[ty][2][tx] = a2;
+  __syncthreads();
+  if (ty < 3 && n < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][ty][tx];
+    dcoef[static_cast<long long>(ty) * N + n] += t;
+  }
+}
+
 }  // namespace blm
 
 extern "C" {
@@ -225,6 +267,17 @@ int blm_gp_lstm_bwd_step(const float* acc5, int64_t ld, const float* coef, int32
   gp_lstm_bwd_step_kernel<<<(H + 127) / 128, 128, 0, as_stream(stream)>>>(
       acc5, ld, coef, n_act, gate_type, c_prev, c_t, dout, dh_rec, dc, dc_is_zero, B, H, dacc,
       reinterpret_cast<__nv_bfloat16*>(dacc_hi), reinterpret_cast<__nv_bfloat16*>(dacc_lo), ldd, dcoef);
+  BLM_CHECK_CUDA(cudaGetLastError());
+  return BLM_OK;
+}
+
+int blm_gp3_bwd(const float* dh, const float* z, const float* coef, int64_t ld, int64_t M, int32_t N, float* dz,
+                blm_bf16* dz_hi, blm_bf16* dz_lo, float* dcoef, blm_stream stream) {
+  using namespace blm;
+  BLM_REQUIRE(dh && z && coef && dz && dcoef && M > 0 && N > 0 && ld >= N, BLM_ERR_ARG, "bad gp3_bwd arguments");
+  BLM_REQUIRE(!dz_lo || dz_hi, BLM_ERR_ARG, "dz_lo requires dz_hi");
+  gp3_bwd_kernel<<<static_cast<unsigned>((N + 31) / 32), 256, 0, as_stream(stream)>>>(
+      dh, z, coef, ld, M, N, dz, reinterpret_cast<__nv_bfloat16*>(dz_hi), reinterpret_cast<__nv_bfloat16*>(dz_lo), dcoef);
   BLM_CHECK_CUDA(cudaGetLastError());
   return BLM_OK;
 }

@@ -725,6 +725,22 @@ def gpmix_dcoef(z: torch.Tensor, dh: torch.Tensor, dcoef: torch.Tensor, *, accum
     return dcoef
 
 
+def gp3_bwd(dh: torch.Tensor, z: torch.Tensor, coef: torch.Tensor, dcoef: torch.Tensor, prec: str,
+            out: Optional[torch.Tensor] = None, out_split: Optional[Split] = None):
+    """Backward of a stand-alone GP unit with acts (sigmoid, tanh, relu) (``blm_gp3_bwd``): returns (dz fp32, Split);
+    ``dcoef`` [3, N] is accumulated in place.  ``out`` / ``out_split``: write into these (row slices of larger buffers)."""
+    M, N = z.shape
+    assert dh.shape == z.shape and dh.stride() == z.stride() and z.stride(1) == 1 and z.stride(0) == N and coef.is_contiguous()
+    assert dcoef.is_contiguous() and dcoef.shape == coef.shape == (3, N)
+    dz = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=z.device)
+    sp = out_split if out_split is not None else empty_split(M, N, prec, z.device)
+    assert dz.is_contiguous() and sp.hi.is_contiguous() and dz.shape == (M, N)
+    with _op("gp3_bwd", 1):
+        check(lib().blm_gp3_bwd(_ptr(dh), _ptr(z), _ptr(coef), N, M, N, _ptr(dz), _ptr(sp.hi), _ptr(sp.lo), _ptr(dcoef),
+                                _stream()), "blm_gp3_bwd")
+    return dz, sp
+
+
 def _eps_args(eps, seed):
     if eps is not None:
         return _ptr(eps), EPS_PTR, 0

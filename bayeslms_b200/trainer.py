@@ -821,10 +821,13 @@ class FineTuner:
                     layers.append({"kind": "plain", "pre": pre, "mi": mi, "mod": member,
                                    "names": {k: f"{pre}{k}_l{l}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}})
             elif getattr(member, "kind", "") == "gp":
-                if member.gate_type >= 5:
-                    raise _lib.BlmError(f"fine-tuning a GP-LSTM with gate type {member.gate_type} (GP unit on the cell state / "
-                                        "recurrent / input product, model.py:1745-1750,1763-1764) is not implemented; gate "
-                                        "types 1-4 train, 5-7 are rescoring-only")
+                if member.gate_type in (5, 6):   # GP unit on the cell state / in place of the recurrent product: per-step GEMMs
+                    layers.append({"kind": "gp56", "pre": pre, "mi": mi, "mod": member})
+                    continue
+                if member.gate_type == 7:      # gates = GPNN(x) + W_hh h + b_ih: a plain layer behind a GP input transform
+                    layers.append({"kind": "gp7", "pre": pre, "mi": mi, "mod": member,
+                                   "names": {"weight_hh": pre + "weights_hh", "bias_ih": pre + "bias_ih"}})
+                    continue
                 layers.append({"kind": "gp", "pre": pre, "mi": mi, "mod": member})
             else:
                 layers.append({"kind": "v", "pre": pre, "mi": mi, "mod": member,
@@ -868,6 +871,23 @@ class FineTuner:
             L["x"] = x
             if L["kind"] == "gp":
                 out32, x, h_l, c_l = self._gp_cell_forward(L, x, h0[li], c0[li], lengths, T, B, H, eps.get(f"cell{mi}"), seed)
+            elif L["kind"] == "gp56":
+                out32, x, h_l, c_l = self._gp56_forward(L, x, h0[li], c0[li], lengths, T, B, H, eps.get(f"cell{mi}"), seed)
+            elif L["kind"] == "gp7":
+                # gate type 7 (model.py:1749-1750): the GP unit over x is ONE GEMM with the mixture epilogue for all steps
+                # (pre-activation z saved), + b_ih, then the plain recurrence on W_hh
+                coef, coef4, wg, bg = self._gp_unit_sample(L, eps.get(f"cell{mi}"), seed)
+                wgs, L["wg_t"] = self._w2(wg)
+                L["w_hh"], L["w_hh_t"] = self._w2(_param(m, L["names"]["weight_hh"]))
+                gates, z = self._f32(M, 4 * H), self._f32(M, 4 * H)
+                _gemm(x, wgs, prec=prec, bias=bg, act=ACT_GPMIX, coef=coef4, out_f32=gates, out_pre=z, tag="gplstm_in")
+                ops.rowgroup_add(gates, _param(m, L["names"]["bias_ih"]).detach().float().view(1, -1).contiguous(), 1, M,
+                                 out_f32=gates)
+                need32 = last and drop_out is not None
+                out32, out, h_l, c_l = ops.lstm_layer(gates, L["w_hh"], h0[li], c0[li], lengths, T, B, H, prec=prec,
+                                                      want_f32=need32, want_split=True)
+                L.update(gates=gates, out=out, z=z, coef3=coef, out_fed=out)
+                x = out
             else:
                 named = L.setdefault("params", {k: _param(m, n) for k, n in L["names"].items()})
                 w_ih, L["w_ih_t"] = self._w2(named["weight_ih"])
@@ -915,7 +935,10 @@ class FineTuner:
             if L["kind"] == "gp":
                 dout = self._gp_cell_backward(L, dout, h0[li], c0[li], T, B, H, kl, kl_scale, eps.get(f"cell{L['mi']}"), seed)
                 continue
-            mod, named, nm = L["mod"], L["params"], L["names"]
+            if L["kind"] == "gp56":
+                dout = self._gp56_backward(L, dout, h0[li], c0[li], T, B, H, kl, kl_scale, eps.get(f"cell{L['mi']}"), seed)
+                continue
+            mod, named, nm = L["mod"], L.get("params"), L["names"]
             h0s = ops.split(h0[li], prec)
             cat = lambda s: Split(torch.cat([h0s.hi, s.hi[:M - B]], 0),  # noqa: E731
                                   None if h0s.lo is None else torch.cat([h0s.lo, s.lo[:M - B]], 0))
@@ -942,6 +965,9 @@ class FineTuner:
                     rec = dh[t & 1]
                     _gemm(dGt, L["w_hh_t"], prec=prec, out_f32=rec, tag="lstm_dh")
             dGT = _tsplit(dG, prec)
+            if L["kind"] == "gp7":
+                dout = self._gp7_backward(L, dG, dGT, cat(L["out_fed"]), kl, kl_scale, eps.get(f"cell{L['mi']}"), seed)
+                continue
             self._wgrad(dGT, _tbf16(L["x"], prec), g[nm["weight_ih"]], f"lstm_ih{li + 1}")
             self._wgrad(dGT, _tbf16(cat(L["out_fed"]), prec), g[nm["weight_hh"]], f"lstm_hh{li + 1}")
             if L["kind"] == "v":        # bias_ih enters both products, bias_hh never (model.py:2519)
@@ -966,6 +992,151 @@ class FineTuner:
         ops.reduce_sum(ce, loss)
         ops.reduce_sum(kl, loss, scale=float(kl_scale), accumulate=True)
         return self.loss_buf[2], self.loss_buf[0], self.loss_buf[1]
+
+    def _gp7_backward(self, L, dG, dGT, hprev: Split, kl, kl_scale, le, seed):
+        """Tail of the backward pass of a gate-type-7 GP cell: dG [M, 4H] is the gradient of the gate pre-activations
+        gates = GPNN(x) + W_hh h + b_ih.  Returns dx."""
+        prec, g, mod, pre, mi = self.prec, self.g, L["mod"], L["pre"], L["mi"]
+        gp = mod.gpnn
+        self._wgrad(dGT, _tbf16(hprev, prec), g[pre + "weights_hh"], "gp7_hh")
+        ops.colsum(dG, g[pre + "bias_ih"])                       # bias_ih enters once here, bias_hh and weights_ih never
+        gc, gw, gb = g[pre + "gpnn.coef_mean"], g[pre + "gpnn.weights_mean"], g[pre + "gpnn.bias_mean"]
+        dz, dzs = ops.gp3_bwd(dG, L["z"], L["coef3"], gc, prec)
+        self._wgrad(_tsplit(dz, prec, dzs), _tbf16(L["x"], prec), gw, "gp7_w")
+        ops.colsum(dz, gb)
+        self._gp_unit_param_grads(L, kl, kl_scale, le, seed)
+        dx = self._f32(dz.shape[0], L["x"].hi.shape[1])
+        _gemm(dzs, L["wg_t"], prec=prec, out_f32=dx, tag="dgrad:gplstm_in")
+        return dx
+
+    def _gp_unit_sample(self, L, le, seed):
+        """(coef [3, N], W_g, b_g) of a cell's GP unit for this step: posterior means, or one draw when GPNN.sample is set
+        (sample_parameters at model.py:1721-1723), and the coefficient table in the GEMM epilogue's order."""
+        gp, mi = L["mod"].gpnn, L["mi"]
+        coef, wg, bg = gp.coef_mean.detach(), gp.weights_mean.detach(), gp.bias_mean.detach()
+        L["noise"] = bool(gp.sample) and (le is not None or seed is not None)
+        if L["noise"]:
+            ge = (lambda k: None) if le is None else le.get
+            tid = _TID_GPCELL + 3 * mi
+            if gp.gpnn_type in (1, 3):
+                coef = self._reparam32(coef, gp.coef_lgstd.detach(), tid, ge("coef"), seed)
+            if gp.gpnn_type in (2, 3):
+                wg = self._reparam32(wg, gp.weights_lgstd.detach(), tid + 1, ge("weights"), seed)
+                bg = self._reparam32(bg, gp.bias_lgstd.detach(), tid + 2, ge("bias"), seed)
+        coef = coef.float().contiguous()                       # rows: sigmoid, tanh, relu
+        coef4 = torch.stack([coef[1], coef[0], coef[2], torch.zeros_like(coef[0])]).contiguous()   # tanh, sigmoid, relu, gelu
+        return coef, coef4, wg, bg.reshape(-1).float().contiguous()
+
+    def _gp_unit_param_grads(self, L, kl, kl_scale, le, seed):
+        """The GP unit's share of the step once d coef / d W_g / d b_g (of the sampled values) sit in the gradient buffer:
+        chain rule into the log-sigmas for a sampled unit, KL value and KL gradients (train.py:360-369)."""
+        g, pre, mi, gp = self.g, L["pre"], L["mi"], L["mod"].gpnn
+        gc, gw, gb = g[pre + "gpnn.coef_mean"], g[pre + "gpnn.weights_mean"], g[pre + "gpnn.bias_mean"]
+        sid = lambda k: engine._stream_id(_TID_GPCELL + 3 * mi + k, 0)  # noqa: E731
+        t_ = gp.gpnn_type
+        if t_ in (1, 3):
+            if L["noise"]:
+                ops.reparam_bwd(gc, gp.coef_lgstd.detach(), gc, g[pre + "gpnn.coef_lgstd"],
+                                eps=None if le is None else le.get("coef"), seed=seed, stream_id=sid(0))
+            ops.kl_gauss(gp.coef_mean.detach(), gp.coef_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.coef_mean.detach(), gp.coef_lgstd.detach(), kl_scale, gc, g[pre + "gpnn.coef_lgstd"])
+        if t_ in (2, 3):
+            if L["noise"]:
+                ops.reparam_bwd(gw, gp.weights_lgstd.detach(), gw, g[pre + "gpnn.weights_lgstd"],
+                                eps=None if le is None else le.get("weights"), seed=seed, stream_id=sid(1))
+                ops.reparam_bwd(gb, gp.bias_lgstd.detach(), gb, g[pre + "gpnn.bias_lgstd"],
+                                eps=None if le is None else le.get("bias"), seed=seed, stream_id=sid(2))
+            ops.kl_gauss(gp.weights_mean.detach(), gp.weights_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.weights_mean.detach(), gp.weights_lgstd.detach(), kl_scale, gw, g[pre + "gpnn.weights_lgstd"])
+            ops.kl_gauss(gp.bias_mean.detach(), gp.bias_lgstd.detach(), kl, minus_one=True, accumulate=True)
+            ops.kl_gauss_bwd(gp.bias_mean.detach(), gp.bias_lgstd.detach(), kl_scale, gb, g[pre + "gpnn.bias_lgstd"])
+
+    def _gp56_forward(self, L, x: Split, h0, c0, lengths, T, B, H, le, seed):
+        """Gate types 5 ("cell": c <- GPNN(c) before the update, model.py:1763-1764) and 6 ("hidden": gates = W_ih x + b_ih +
+        GPNN(h), model.py:1747-1748): the input product is hoisted, the GP unit is one GEMM with the mixture epilogue
+        per step (pre-activation saved), then the plain cell update."""
+        prec, dev, mod = self.prec, self.device, L["mod"]
+        gate, M = mod.gate_type, T * B
+        coef, coef4, wg, bg = self._gp_unit_sample(L, le, seed)
+        wgs, L["wg_t"] = self._w2(wg)
+        w_ih, L["w_ih_t"] = self._w2(mod.weights_ih)
+        b_ih = mod.bias_ih.detach().float()
+        pre = self._f32(M, 4 * H)
+        _gemm(x, w_ih, prec=prec, bias=((2.0 if gate == 5 else 1.0) * b_ih).contiguous(), out_f32=pre, tag="gplstm_in")
+        NZ = 4 * H if gate == 6 else H
+        acc, zs, c_all = self._f32(M, 4 * H), self._f32(M, NZ), self._f32(M, H)
+        out32 = self._f32(M, H)
+        outs = ops.empty_split(M, H, prec, dev)
+        cgp = self._f32(M, H) if gate == 5 else None
+        if gate == 5:
+            w_hh, L["w_hh_t"] = self._w2(mod.weights_hh)
+        h = h0.clone()
+        h_op = ops.split(h, prec)
+        c_prev = c0.contiguous()
+        for t in range(T):
+            rows = slice(t * B, (t + 1) * B)
+            if gate == 6:
+                _gemm(h_op, wgs, prec=prec, bias=bg, act=ACT_GPMIX, coef=coef4, resid=pre[rows], out_f32=acc[rows],
+                      out_pre=zs[rows], tag="gplstm_rec")
+                c_in = c_prev
+            else:
+                _gemm(ops.split(c_prev, prec), wgs, prec=prec, bias=bg, act=ACT_GPMIX, coef=coef4, out_f32=cgp[rows],
+                      out_pre=zs[rows], tag="gplstm_cell")
+                _gemm(h_op, w_hh, prec=prec, resid=pre[rows], out_f32=acc[rows], tag="gplstm_rec")
+                c_in = cgp[rows]
+            ops.lstm_cell_step(acc[rows], lengths, t, c_all[rows], h, h_op, out32[rows],
+                               Split(outs.hi[rows], None if outs.lo is None else outs.lo[rows]), c_in=c_in)
+            c_prev = c_all[rows]
+        L.update(acc=acc, zs=zs, c_all=c_all, cgp=cgp, out=outs, coef3=coef)
+        return out32, outs, h, c_all[M - B:].clone()
+
+    def _gp56_backward(self, L, dout, h0, c0, T, B, H, kl, kl_scale, le, seed):
+        prec, dev, g, mod, pre = self.prec, self.device, self.g, L["mod"], L["pre"]
+        gate, M = mod.gate_type, T * B
+        acc, zs, c_all, cgp = L["acc"], L["zs"], L["c_all"], L["cgp"]
+        ops.lstm_gates_act(acc, c0, T, B, H)          # pre-activations -> gate values in place (its cell states are not used)
+        gc = g[pre + "gpnn.coef_mean"]
+        NZ = zs.shape[1]
+        dG, dGs = self._f32(M, 4 * H), ops.empty_split(M, 4 * H, prec, dev)
+        dZ, dZs = self._f32(M, NZ), ops.empty_split(M, NZ, prec, dev)
+        dc = self._f32(B, H)
+        dh = [self._f32(B, H), self._f32(B, H)]
+        rec = None
+        for t in range(T - 1, -1, -1):
+            sl = slice(t * B, (t + 1) * B)
+            c_before = c0 if t == 0 else c_all[(t - 1) * B:t * B]
+            dGt = Split(dGs.hi[sl], None if dGs.lo is None else dGs.lo[sl])
+            dZt = Split(dZs.hi[sl], None if dZs.lo is None else dZs.lo[sl])
+            ops.lstm_bwd_step(acc[sl], cgp[sl] if gate == 5 else c_before, c_all[sl], dout[sl], rec, dc, t == T - 1, dG[sl], dGt)
+            if gate == 5:
+                # dc holds dL/dc' of this step's transformed cell state: back through the GP unit to dL/dc_{t-1}
+                ops.gp3_bwd(dc, zs[sl], L["coef3"], gc, prec, out=dZ[sl], out_split=dZt)
+                _gemm(dZt, L["wg_t"], prec=prec, out_f32=dc, tag="gplstm_dc")
+                if t > 0:
+                    rec = dh[t & 1]
+                    _gemm(dGt, L["w_hh_t"], prec=prec, out_f32=rec, tag="gplstm_dh")
+            else:
+                ops.gp3_bwd(dG[sl], zs[sl], L["coef3"], gc, prec, out=dZ[sl], out_split=dZt)
+                if t > 0:
+                    rec = dh[t & 1]
+                    _gemm(dZt, L["wg_t"], prec=prec, out_f32=rec, tag="gplstm_dh")     # dh_{t-1} = dz_t W_g
+        h0s = ops.split(h0, prec)
+        hprev = Split(torch.cat([h0s.hi, L["out"].hi[:M - B]], 0),
+                      None if h0s.lo is None else torch.cat([h0s.lo, L["out"].lo[:M - B]], 0))
+        dGT, dZT = _tsplit(dG, prec, dGs), _tsplit(dZ, prec, dZs)
+        self._wgrad(dGT, _tbf16(L["x"], prec), g[pre + "weights_ih"], "gp56_ih")
+        ops.colsum(dG, g[pre + "bias_ih"], scale=2.0 if gate == 5 else 1.0)
+        if gate == 5:
+            self._wgrad(dGT, _tbf16(hprev, prec), g[pre + "weights_hh"], "gp5_hh")
+            cprev = ops.split(torch.cat([c0, c_all[:M - B]], 0), prec)
+            self._wgrad(dZT, _tbf16(cprev, prec), g[pre + "gpnn.weights_mean"], "gp5_w")
+        else:
+            self._wgrad(dZT, _tbf16(hprev, prec), g[pre + "gpnn.weights_mean"], "gp6_w")
+        ops.colsum(dZ, g[pre + "gpnn.bias_mean"])
+        self._gp_unit_param_grads(L, kl, kl_scale, le, seed)
+        dx = self._f32(M, L["x"].hi.shape[1])
+        _gemm(dGs, L["w_ih_t"], prec=prec, out_f32=dx, tag="dgrad:gplstm_in")
+        return dx
 
     def _gp_cell_forward(self, L, x: Split, h0, c0, lengths, T, B, H, le, seed):
         """GPLSTMCell.forward (model.py:1720-1777) keeping what the backward pass needs."""

@@ -561,6 +561,11 @@ int blm_vnn_noise(const float* e, const float* rho, int64_t T, int32_t H, float*
 int blm_rowgroup_add(const float* x, const float* r, int64_t G, int64_t B, int32_t W, float* out_f32, blm_bf16* out_hi,
                      blm_bf16* out_lo, blm_stream stream);
 int blm_rowgroup_sum(const float* x, int64_t G, int64_t B, int32_t W, float* out, blm_stream stream);
+/* Backward of a stand-alone GP unit of the LSTM cells (gate types 5-7, model.py:1745-1750): h = sum_i coef[i, n]
+ * act_i(z) with acts (sigmoid, tanh, relu); dz = dh . dh/dz (fp32 and optional bf16 hi[, lo]), dcoef[3, N] += sum_m dh
+ * act_i(z).  dh, z, dz share the leading dimension ld.                                                          */
+int blm_gp3_bwd(const float* dh, const float* z, const float* coef, int64_t ld, int64_t M, int32_t N, float* dz,
+                blm_bf16* dz_hi, blm_bf16* dz_lo, float* dcoef, blm_stream stream);
 int blm_vnn_kl(const float* h, const float* rho, int64_t B, int32_t H, float kl_scale, float* kl_out, float* dh,
                float* drho, blm_stream stream);
 int blm_vnn_drho(const float* dn, const float* e, const float* rho, int64_t T, int32_t H, float* drho, blm_stream stream);

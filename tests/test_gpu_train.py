@@ -409,7 +409,13 @@ def _build_cells(family, pos, H=128, dropout=0.0):
     ("v_lstm", "11", True, 0.0), ("v_lstm", "01", True, 0.0), ("v_lstm", "11", False, 0.0), ("v_lstm", "11", True, 0.3),
     ("gauss_lstm", "31", False, 0.0), ("gauss_lstm", "31", True, 0.0), ("gauss_lstm", "333", True, 0.0),
     ("gauss_lstm", "3330", True, 0.0), ("gauss_lstm", "23", True, 0.3), ("gauss_lstm", "12", False, 0.0),
-    ("gauss_lstm", "4131", True, 0.0)])
+    ("gauss_lstm", "4131", True, 0.0),
+    # gate type 7: the GP unit replaces the input product (one mixture GEMM over all steps + blm_gp3_bwd)
+    ("gauss_lstm", "73", True, 0.0), ("gauss_lstm", "71", False, 0.0), ("gauss_lstm", "732", True, 0.0),
+    ("gauss_lstm", "7333", True, 0.3),
+    # gate types 5 / 6: the GP unit on the cell state / in place of the recurrent product, one mixture GEMM per step
+    ("gauss_lstm", "53", True, 0.0), ("gauss_lstm", "61", False, 0.0), ("gauss_lstm", "6353", True, 0.0),
+    ("gauss_lstm", "532", True, 0.3), ("gauss_lstm", "62", True, 0.0)])
 def test_cell_families_finetune_step_matches_oracle_autograd(family, pos, sampled, dropout):
     """GaussRNNModel / VariationalRNNModel fine-tune step (train.py:319-377): loss, the KL of the GP units / of the VNNs,
     every gradient and the carried-out state against autograd through the oracle's training-mode cells (pinned on the
