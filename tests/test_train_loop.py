@@ -134,7 +134,8 @@ def test_schedule_halves_lr_and_reloads_best(tmp_path, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("model,unc,flags", [("Transformer", "Bayesian", ["--T_bayes_pos", "FFN", "--nhead", "2"]),
-                                             ("LSTM", "Bayesian", ["--L_bayes_pos", "3"])])
+                                             ("LSTM", "Bayesian", ["--L_bayes_pos", "3"]),
+                                             ("LSTM", "Gaussian", ["--L_gauss_pos", "63"])])
 def test_training_run_learns_markov_corpus(tmp_path, model, unc, flags, capsys):
     """End to end through main(): corpus files -> 3 epochs -> checkpoint; validation perplexity far below uniform."""
     from bayeslms_b200 import train as T
