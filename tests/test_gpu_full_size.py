@@ -217,3 +217,28 @@ def test_config4_finetune_step_at_full_size():
         if ref.norm() > 1e-6:
             worst = max(worst, ((ft2.g[name].detach().cpu() - ref).norm() / ref.norm()).item())
     assert worst < 2e-2, worst
+
+
+def test_lstm_pair_recurrence_gives_the_same_scores_as_the_single_cta_kernel(monkeypatch):
+    """Engine level, H = 1024 / V = 30000: 320 hypotheses put the lock-step batches on lstm_pair_kernel (three 128-row
+    tiles, both precisions); with BLM_LSTM_NO_PAIR=1 the same batches run on the single-CTA kernel.  Same K order and
+    fp32 accumulation: the scores must be identical bit for bit, and precise mode within 1e-3 of the oracle on a
+    sample of the hypotheses."""
+    from bayeslms_b200.scorer import Rescorer, ids_for
+    net, sd, cfg = _lstm_full()
+    rs = np.random.RandomState(11)
+    vocab = {"<s>": 0, "<unk>": 1, **{f"w{i}": i for i in range(2, V)}}
+    nbest = OrderedDict((f"u{u}", [" ".join(f"w{rs.randint(2, V)}" for _ in range(rs.randint(1, 24))) for n in range(20)])
+                        for u in range(16))
+    sessions = [[[ids_for(h, vocab) for h in hyps] for hyps in nbest.values()]]
+    got = {}
+    for prec in ("bf16", "bf16x3"):
+        monkeypatch.delenv("BLM_LSTM_NO_PAIR", raising=False)
+        got[prec] = Rescorer(net, prec=prec).score_sessions(sessions)
+        monkeypatch.setenv("BLM_LSTM_NO_PAIR", "1")
+        single = Rescorer(net, prec=prec).score_sessions(sessions)
+        assert np.array_equal(got[prec], single), np.abs(got[prec] - single).max()
+    monkeypatch.delenv("BLM_LSTM_NO_PAIR", raising=False)
+    small = OrderedDict(list(nbest.items())[:2])
+    want = np.asarray([s for items in O.compute_scores(small, vocab, sd, cfg).values() for _, s in items])
+    assert np.abs(got["bf16x3"][:40] - want).max() < 1e-3
