@@ -231,6 +231,24 @@ def bench_lstm(dev, world=1, rank=0, steps=1):
             out["kernel_ms_total"] = round(tot / steps, 2)
             out["kernel_time_shares"] = {k: round(sum(a.elapsed_time(b) for a, b, _ in v) / tot, 4)
                                          for k, v in sorted(timing.items(), key=lambda kv: -sum(a.elapsed_time(b) for a, b, _ in kv[1]))[:6]}
+    # the 1e-3-parity mode (bf16x3, the scorer CLI's default) on the first 3 sessions of the same lists
+    n_h = 3 * per_sess * nbest
+    m_p = int(offs[n_h])
+    sub = (tok[:m_p], tgt[:m_p], offs[:n_h + 1], sess_of[:n_h], utt_of[:n_h])
+    rs_p = Rescorer(net, prec="bf16x3", max_tokens=MAX_TOKENS)
+    rs_f = Rescorer(net, prec="bf16", max_tokens=MAX_TOKENS)
+    res = {}
+    for name, r in (("bf16x3", rs_p), ("bf16", rs_f)):
+        r.score_sessions_flat(*sub)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sc = r.score_sessions_flat(*sub)
+        torch.cuda.synchronize()
+        res[name] = (m_p / (time.perf_counter() - t0), sc)
+    out["precise"] = {"tokens_per_s": res["bf16x3"][0], "dtype": "bf16x3", "slowdown_vs_bf16_same_sample": res["bf16"][0] / res["bf16x3"][0],
+                      "max_abs_score_diff_vs_bf16": float(np.abs(res["bf16x3"][1] - res["bf16"][1]).max()),
+                      "sample": f"3 sessions x {per_sess} utterances x {nbest}-best ({m_p} tokens) per GPU; with 3 instead of 12 "
+                                "sessions the sequential hypothesis-#0 chains weigh more (3-row batches)"}
     out["workload"] = (f"Bayesian LSTM 2x1024 L_bayes_pos=3 V30000, {nbest}-best, {n_sess} sessions x {per_sess} utterances "
                        f"per GPU ({int(n_tok.item())} tokens over {world} GPU(s); config 5 = 100 sessions over 8 GPUs), end to "
                        "end from flat host id arrays incl. batch packing (wall clock, max over ranks)")
