@@ -115,6 +115,11 @@ class _Plan:
                 L["gp"] = g
             else:
                 L["w1"], L["b1"] = sp(layer.linear1.weight), layer.linear1.bias.detach().float().contiguous()
+                if getattr(layer, "activation", "gelu") == "relu":
+                    # ReLU (TransformerModel's constructor default) = the GP-mixture epilogue with the relu coefficient only
+                    F_ = layer.linear1.weight.shape[0]
+                    L["act_coef"] = torch.zeros(4, F_, dtype=torch.float32, device=self.device)
+                    L["act_coef"][2] = 1.0
             if layer.kind == "bayes_ffn":
                 L["w2"], L["b2"] = sp(layer.linear2.weight_mean), None
                 L["w2_mu"], L["w2_ls"] = layer.linear2.weight_mean.detach(), layer.linear2.weight_lgstd.detach()
@@ -372,7 +377,7 @@ class _TmRun:
             if kind == "gauss":
                 w1, b1, coef = self.gp_weights(L, sample, seed)
             else:
-                w1, b1, coef = L["w1"], L["b1"], None
+                w1, b1, coef = L["w1"], L["b1"], L.get("act_coef")
             h = self.part_c(L, x1s, w1, b1, coef)
         else:
             h = carry["h"]

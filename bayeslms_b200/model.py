@@ -343,11 +343,12 @@ class _TorchMultiheadAttention(nn.Module):
 
 class _TorchEncoderLayer(_EncoderLayer):
     """Post-LN layer with ``nn.TransformerEncoderLayer``'s keys (self_attn.in_proj_*, self_attn.out_proj.*,
-    linear1, linear2, norm1, norm2); activation = exact-erf GELU, the only one the callers pass
-    (score.py:377, train.py:198-201)."""
+    linear1, linear2, norm1, norm2); activation = exact-erf GELU, the one the callers pass (score.py:377,
+    train.py:198-201), or ReLU, the constructor's default (model.py:124)."""
 
-    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="gelu"):
         super().__init__(d_model, nhead, dim_feedforward, dropout, attn_cls=_TorchMultiheadAttention)
+        self.activation = activation
 
 
 class _TorchEncoder(nn.Module):
@@ -376,12 +377,13 @@ class TransformerModel(_TransformerLM):
 
     def __init__(self, ntoken, ninp, nhead, nhid, nlayers, dropout=0.5, activation="relu", tie_weights=False):
         super().__init__()
-        if activation != "gelu":
-            raise NotImplementedError("the scorer and the trainer build TransformerModel with activation='gelu' "
-                                      "(score.py:377, train.py:198); relu is not on the B200 path")
+        if activation not in ("gelu", "relu"):
+            raise ValueError(f"activation should be relu/gelu, not {activation}")     # torch's own message (model.py:131)
+        self.activation = activation
         self.src_mask = None
         self.pos_encoder = PositionalEncoding(ninp, dropout)
-        self.transformerlayers = _TorchEncoder([_TorchEncoderLayer(ninp, nhead, nhid, dropout) for _ in range(nlayers)])
+        self.transformerlayers = _TorchEncoder([_TorchEncoderLayer(ninp, nhead, nhid, dropout, activation)
+                                                for _ in range(nlayers)])
         self._finish(ntoken, ninp, dropout, tie_weights)
 
 

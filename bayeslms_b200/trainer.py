@@ -432,6 +432,10 @@ class FineTuner:
                 w1_32 = layer.linear1.weight.detach()
                 w1, S["w1_t"] = self._w2(w1_32)
                 act1, bias1, coef = ACT_GELU, layer.linear1.bias.detach(), None
+                if getattr(layer, "activation", "gelu") == "relu":     # ReLU = the mixture epilogue with the relu row only
+                    coef = torch.zeros(4, w1_32.shape[0], dtype=torch.float32, device=dev)
+                    coef[2] = 1.0
+                    act1, S["coef"] = ACT_GPMIX, coef
             S["drop_ffn"] = self._layer_site(layer, li, "ffn", (T, B))            # dropout on the activation, model.py:1043
             # h = dropout(act(z1)) in the epilogue; z1 (saved for the backward pass) is the unmasked pre-activation
             _gemm(x1s, w1, prec=prec, bias=bias1, act=act1, coef=coef, out=hs, out_pre=z1, tag="ffn1",
@@ -532,7 +536,11 @@ class FineTuner:
             # FFN2: dgrad fused with the activation derivative (and the mask of the FFN dropout), wgrad, bias
             dz1 = self._f32(M, S["z1"].shape[1])
             dz1s = ops.empty_split(M, S["z1"].shape[1], prec, dev)
-            if kind == "gauss":
+            relu = kind != "gauss" and getattr(layer, "activation", "gelu") == "relu"
+            if relu:
+                _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1, out=dz1s,
+                      tag="dgrad:ffn2", drop=_fusable(S["drop_ffn"], dz1.shape[1]))
+            elif kind == "gauss":
                 dh = torch.empty_like(dz1)
                 # h = m . act(z1): the mask multiplies dL/dh in the epilogue, before act'(z1) and before dh is stored
                 _gemm(dfs, S["w2_t"], prec=prec, act=ACT_GPMIX_GRAD, aux=S["z1"], coef=S["coef"], out_f32=dz1,

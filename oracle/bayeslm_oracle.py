@@ -217,7 +217,10 @@ def tm_layer(x: Tensor, sd: SD, pre: str, kind: str, nhead: int, mask: Optional[
     if kind == "gauss":
         h = gpnn(x, sd, pre + "gpnn.", cfg.gauss_pos, eps)
     else:
-        h = F.gelu(F.linear(x, sd[pre + "linear1.weight"], sd[pre + "linear1.bias"]))
+        # nn.TransformerEncoderLayer(activation=...) of TransformerModel (model.py:124, 131-135): 'relu' is the constructor's
+        # default, 'gelu' what every caller passes; the reference's own layers are GELU only (model.py:1035)
+        act = F.relu if cfg.get("activation", "gelu") == "relu" else F.gelu
+        h = act(F.linear(x, sd[pre + "linear1.weight"], sd[pre + "linear1.bias"]))
     if "ffn" in masks:
         h = h * masks["ffn"]
     if kind == "bayes_ffn":

@@ -18,7 +18,7 @@ from tests.util import load_golden_model
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TM_NAMES = ["bayes_tm_FFN", "bayes_tm_MHA", "bayes_tm_EMB", "bayes_tm_none", "gauss_tm_0", "gauss_tm_1",
-            "gauss_tm_2", "gauss_tm_3", "v_tm_0", "v_tm_1", "v_tm_2", "v_tm_3", "std_tm"]
+            "gauss_tm_2", "gauss_tm_3", "v_tm_0", "v_tm_1", "v_tm_2", "v_tm_3", "std_tm", "std_tm_relu"]
 
 
 def _batch_from_tb(x, device):

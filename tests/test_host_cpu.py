@@ -46,7 +46,7 @@ def test_product_never_imports_oracle():
 
 @pytest.mark.parametrize("name", ["bayes_tm_FFN", "bayes_tm_MHA", "bayes_tm_EMB", "bayes_tm_none", "gauss_tm_0",
                                   "gauss_tm_3", "v_tm_0", "v_tm_1", "v_tm_2", "v_tm_3", "bayes_lstm_0",
-                                  "bayes_lstm_3", "std_tm", "std_lstm"])
+                                  "bayes_lstm_3", "std_tm", "std_tm_relu", "std_lstm"])
 def test_state_dict_layout_matches_reference(golden, name):
     from tests.util import build_from_cfg
     rec = golden(name + ".pt")
@@ -145,8 +145,10 @@ def test_build_model_follows_the_reference_switch():
     ns = argparse.Namespace(model="LSTM", uncertainty="none", emsize=32, nhid=32, nlayers=2, tied=False)
     m = M.build_model(ns, 40)
     assert isinstance(m, M.RNNModel) and "rnn.weight_hh_l1" in m.state_dict() and m.decoder.weight is not m.encoder.weight
-    with pytest.raises(NotImplementedError):
-        M.TransformerModel(40, 32, 4, 64, 2, 0.5, "relu", True)
+    assert M.TransformerModel(40, 32, 4, 64, 2, 0.5, "relu", True).transformerlayers[0].activation == "relu"
+    assert M.TransformerModel(40, 32, 4, 64, 2).activation == "relu"           # the constructor's default (model.py:124)
+    with pytest.raises(ValueError):
+        M.TransformerModel(40, 32, 4, 64, 2, 0.5, "tanh", True)
     with pytest.raises(NotImplementedError):
         M.RNNModel("GRU", 40, 32, 32, 2)
 

@@ -22,7 +22,8 @@ def build_from_cfg(cfg, device=None):
     elif fam == "v_lstm":
         net = M.VariationalRNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, True, cfg["v_pos"])
     elif fam == "std_tm":
-        net = M.TransformerModel(cfg["ntoken"], cfg["ninp"], cfg["nhead"], cfg["nhid"], cfg["nlayers"], 0.5, "gelu", True)
+        net = M.TransformerModel(cfg["ntoken"], cfg["ninp"], cfg["nhead"], cfg["nhid"], cfg["nlayers"], 0.5,
+                                 cfg.get("activation", "gelu"), True)
     elif fam == "std_lstm":
         net = M.RNNModel("LSTM", cfg["ntoken"], cfg["ninp"], cfg["nhid"], cfg["nlayers"], 0.5, True)
     else:
